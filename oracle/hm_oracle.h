@@ -1,0 +1,136 @@
+/*
+ * hm_oracle.h -- CPU restatement (plain C99) of the HM-7.2 hot-path arithmetic.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is the parity oracle for the CUDA path in
+ * thevc_b200/csrc.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load it.  The product library
+ * (libthevc_cuda.so) never links, loads or calls anything in this directory.
+ *
+ * Every function cites the reference file:line (relative to
+ * /root/reference/source/Lib) whose arithmetic it restates.  The restatement is
+ * pinned against the reference's own compiled functions (oracle/_ref/libhmref.so,
+ * built by oracle/Makefile from the reference sources where they lie) by
+ * tests/test_oracle_vs_ref.py and against the committed vectors in
+ * tests/golden/ (generated from libhmref.so by tests/golden/make_golden.py).
+ *
+ * Conventions (same as the reference): Pel = int16, TCoeff = int32, strides in
+ * elements, `bi` = g_uiBitIncrement (0 for *_main, 2 for he10),
+ * `bd` = g_uiBitDepth + g_uiBitIncrement (8 or 10).
+ */
+#ifndef HM_ORACLE_H
+#define HM_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int16_t Pel;
+
+/* ------------------------------------------------------------------ distortion */
+uint32_t orc_sad(const Pel* org, int so, const Pel* cur, int sc, int w, int h, int subshift, int bi);
+uint32_t orc_sad_generic(const Pel* org, int so, const Pel* cur, int sc, int w, int h, int bi);
+uint32_t orc_sse(const Pel* org, int so, const Pel* cur, int sc, int w, int h, int bi);
+uint32_t orc_hads(const Pel* org, int so, const Pel* cur, int sc, int w, int h, int bi);
+uint32_t orc_calc_had(const Pel* p0, int s0, const Pel* p1, int s1, int w, int h, int bi);
+uint32_t orc_had2x2(const Pel* org, const Pel* cur, int so, int sc);
+uint32_t orc_had4x4(const Pel* org, const Pel* cur, int so, int sc);
+uint32_t orc_had8x8(const Pel* org, const Pel* cur, int so, int sc);
+/* TComRdCost::getDistPart dispatch: dfunc = DF_SSE(1) / DF_SAD(8) / DF_HADS(22) */
+uint32_t orc_get_dist_part(const Pel* cur, int sc, const Pel* org, int so, int w, int h, int dfunc, int bi);
+
+/* motion-vector rate */
+uint32_t orc_mv_component_bits(int v);
+uint32_t orc_mv_bits(int x, int y, int scale, int predx, int predy);
+uint32_t orc_mv_cost(uint32_t lambda_cost, int x, int y, int scale, int predx, int predy);
+uint32_t orc_lambda_motion_sad(double lambda);
+
+/* ------------------------------------------------------------------ interpolation */
+void orc_filter_copy(const Pel* src, int ss, Pel* dst, int ds, int w, int h, int isFirst, int isLast, int bd);
+void orc_filter(int ntaps, int isVert, int isFirst, int isLast, const Pel* src, int ss, Pel* dst, int ds,
+                int w, int h, const int16_t* coeff, int bd);
+void orc_filter_hor_luma(const Pel* src, int ss, Pel* dst, int ds, int w, int h, int frac, int isLast, int bd);
+void orc_filter_ver_luma(const Pel* src, int ss, Pel* dst, int ds, int w, int h, int frac, int isFirst, int isLast, int bd);
+void orc_filter_hor_chroma(const Pel* src, int ss, Pel* dst, int ds, int w, int h, int frac, int isLast, int bd);
+void orc_filter_ver_chroma(const Pel* src, int ss, Pel* dst, int ds, int w, int h, int frac, int isFirst, int isLast, int bd);
+
+/* ------------------------------------------------------------------ motion compensation */
+void orc_pred_inter_luma_blk(const Pel* ref, int rs, int mvx, int mvy, int w, int h, Pel* dst, int ds, int bi_flag, int bd);
+void orc_pred_inter_chroma_blk(const Pel* ref, int rs, int mvx, int mvy, int w, int h, Pel* dst, int ds, int bi_flag, int bd);
+void orc_add_avg(const Pel* s0, int st0, const Pel* s1, int st1, Pel* dst, int ds, int w, int h, int bd);
+void orc_subtract(const Pel* s0, int st0, const Pel* s1, int st1, Pel* dst, int ds, int w, int h);
+void orc_add_clip(const Pel* s0, int st0, const Pel* s1, int st1, Pel* dst, int ds, int w, int h, int bd);
+void orc_remove_high_freq(Pel* dst, int ds, const Pel* src, int ss, int w, int h);
+void orc_extend_border(Pel* pic, int stride, int w, int h, int mx, int my);
+
+/* ------------------------------------------------------------------ motion estimation */
+typedef struct {
+  int pic_w, pic_h;   /* SPS luma size                                      */
+  int cu_x, cu_y;     /* m_uiCUPelX/Y of the TComDataCU doing the search     */
+  int max_cu;         /* g_uiMaxCUWidth == g_uiMaxCUHeight                   */
+} orc_cu_geom;
+
+typedef struct {
+  int mvx, mvy;       /* integer-pel best                                   */
+  uint32_t sad;       /* ruiSAD = best cost minus its rate term             */
+  uint32_t n_sads;    /* number of xTZSearchHelp / candidate evaluations    */
+} orc_me_result;
+
+void orc_clip_mv(const orc_cu_geom* g, int* mvx, int* mvy);
+void orc_set_search_range(const orc_cu_geom* g, int predx, int predy, int srange,
+                          int* lx, int* ty, int* rx, int* by);
+/* org: PU block; ref: pointer to the co-located pel of the PU in the padded reference plane */
+void orc_pattern_search(const Pel* org, int so, const Pel* ref, int rs, int w, int h,
+                        int lx, int ty, int rx, int by, int fen, int bi,
+                        uint32_t lambda_cost, int predx, int predy, orc_me_result* out);
+void orc_tz_search(const orc_cu_geom* g, const Pel* org, int so, const Pel* ref, int rs, int w, int h,
+                   int lx, int ty, int rx, int by, int srange, int fen, int bi,
+                   uint32_t lambda_cost, int predx, int predy, int startx_q, int starty_q,
+                   orc_me_result* out);
+
+typedef struct {
+  int halfx, halfy;   /* rcMvHalf  (-1..1)                                  */
+  int qtrx, qtry;     /* rcMvQter  (-1..1)                                  */
+  uint32_t cost_half; /* ruiCost after half-pel refinement                  */
+  uint32_t cost;      /* ruiCost after quarter-pel refinement               */
+} orc_frac_result;
+
+/* xPatternSearchFracDIF: ref points at the PU's co-located pel; (imvx,imvy) integer MV */
+void orc_frac_search(const Pel* org, int so, const Pel* ref, int rs, int w, int h,
+                     int imvx, int imvy, int hadamard, int bi, int bd,
+                     uint32_t lambda_cost, int predx, int predy, orc_frac_result* out);
+
+/* ------------------------------------------------------------------ transform / quant */
+void orc_dct_matrix(int n, int16_t* out /* n*n row-major T[k][j] */);
+void orc_partial_butterfly(int n, const int16_t* src, int16_t* dst, int shift, int line);
+void orc_partial_butterfly_inverse(int n, const int16_t* src, int16_t* dst, int shift, int line);
+void orc_fast_forward_dst(const int16_t* block, int16_t* coeff, int shift);
+void orc_fast_inverse_dst(const int16_t* tmp, int16_t* block, int shift);
+void orc_xTrMxN(const int16_t* block, int16_t* coeff, int w, int h, int use_dst, int bi);
+void orc_xITrMxN(const int16_t* coeff, int16_t* block, int w, int h, int use_dst, int bi);
+void orc_xT(int use_dst, const Pel* resi, int stride, int32_t* coeff, int w, int h, int bi);
+void orc_xIT(int use_dst, const int32_t* coeff, Pel* resi, int stride, int w, int h, int bi);
+void orc_transform_skip(const Pel* resi, int stride, int32_t* coeff, int w, int h, int bd);
+void orc_itransform_skip(const int32_t* coeff, Pel* resi, int stride, int w, int h, int bd);
+
+typedef struct {
+  int qp_per, qp_rem;   /* m_cQP after setQPforQuant                        */
+  int base_per;         /* cQpBase.m_iPer (ADAPTIVE_QP_SELECTION)           */
+  int is_intra_slice;   /* I_SLICE -> 171 else 85                           */
+  int sign_hide;        /* PPS sign-data-hiding flag                        */
+  int use_arl;          /* m_bUseAdaptQpSelect                              */
+  int bd;               /* g_uiBitDepth + g_uiBitIncrement                  */
+} orc_quant_param;
+
+void orc_set_qp(int qpy, int is_luma, int qp_bd_offset, int chroma_qp_offset, int* per, int* rem);
+void orc_scan(int scan_idx /*0 diag,1 hor,2 ver*/, int log2size, uint32_t* out);
+/* non-RDOQ branch of xQuant + signBitHidingHDQ, flat scaling list */
+void orc_quant(const int32_t* coef, int32_t* qcoef, int32_t* arl, int w, int h,
+               const orc_quant_param* qp, const uint32_t* scan, uint32_t* abs_sum);
+void orc_dequant(const int32_t* qcoef, int32_t* coef, int w, int h, int per, int rem, int bd);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

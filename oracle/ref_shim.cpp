@@ -1,0 +1,287 @@
+/*
+ * ref_shim.cpp -- extern "C" wrappers around the UNMODIFIED reference classes.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Compiled by oracle/Makefile together with the reference's own
+ * TLibCommon sources (taken where they lie under /root/reference) into
+ * oracle/_ref/libhmref.so.  No reference source is copied into this repository; this file
+ * only #includes the reference headers at build time and forwards calls, so that the
+ * restatement in hm_oracle*.c and the CUDA path can be compared with what the reference's
+ * own compiled code returns.  `private`/`protected` are opened for this translation unit
+ * only, to reach TComTrQuant::xT/xIT/xQuant/xDeQuant and TComPrediction::xPredInter*Blk.
+ */
+#include <sstream>
+#include <cstring>
+#include <cstdlib>
+#include <vector>
+
+#define private public
+#define protected public
+#include "TLibCommon/TypeDef.h"
+#include "TLibCommon/CommonDef.h"
+#include "TLibCommon/TComRom.h"
+#include "TLibCommon/TComRdCost.h"
+#include "TLibCommon/TComPattern.h"
+#include "TLibCommon/TComInterpolationFilter.h"
+#include "TLibCommon/TComTrQuant.h"
+#include "TLibCommon/TComDataCU.h"
+#include "TLibCommon/TComSlice.h"
+#include "TLibCommon/TComPic.h"
+#include "TLibCommon/TComPicYuv.h"
+#include "TLibCommon/TComYuv.h"
+#include "TLibCommon/TComPrediction.h"
+#undef private
+#undef protected
+
+/* external-linkage free functions of TLibCommon/TComTrQuant.cpp:417-972 */
+void partialButterfly4(short* src, short* dst, int shift, int line);
+void partialButterfly8(short* src, short* dst, int shift, int line);
+void partialButterfly16(short* src, short* dst, int shift, int line);
+void partialButterfly32(short* src, short* dst, int shift, int line);
+void partialButterflyInverse4(short* src, short* dst, int shift, int line);
+void partialButterflyInverse8(short* src, short* dst, int shift, int line);
+void partialButterflyInverse16(short* src, short* dst, int shift, int line);
+void partialButterflyInverse32(short* src, short* dst, int shift, int line);
+void fastForwardDst(short* block, short* coeff, int shift);
+void fastInverseDst(short* tmp, short* block, int shift);
+void xTrMxN(short* block, short* coeff, int iWidth, int iHeight, UInt uiMode);
+void xITrMxN(short* coeff, short* block, int iWidth, int iHeight, UInt uiMode);
+
+static bool s_rom_ready = false;
+static TComRdCost* s_rd = 0;
+
+extern "C" {
+
+/* mirrors TAppEncCfg::xSetGlobal (App/TAppEncoder/TAppEncCfg.cpp:922-949) for the globals the
+ * hot path reads */
+void ref_init(int internal_bit_depth)
+{
+  if (!s_rom_ready) {
+    initROM();
+    s_rom_ready = true;
+    s_rd = new TComRdCost;
+    s_rd->init();
+  }
+  g_uiMaxCUWidth = 64;
+  g_uiMaxCUHeight = 64;
+  g_uiMaxCUDepth = 4;
+  g_uiAddCUDepth = 1;
+  g_uiBitDepth = 8;
+  g_uiBitIncrement = (UInt)(internal_bit_depth - 8);
+  g_uiBASE_MAX = ((1 << g_uiBitDepth) - 1);
+  g_uiIBDI_MAX = ((1 << (g_uiBitDepth + g_uiBitIncrement)) - 1);
+}
+
+/* ---- distortion: integer-ME SAD exactly as xTZSearchHelp sets it up (TEncSearch.cpp:312-336) */
+unsigned ref_sad_me(const short* org, int so, const short* cur, int sc, int w, int h, int subshift)
+{
+  TComPattern pat;
+  pat.initPattern((Pel*)org, NULL, NULL, w, h, so, 0, 0, 0, 0);
+  DistParam dp;
+  s_rd->setDistParam(&pat, (Pel*)cur, sc, dp);
+  dp.iSubShift = subshift;
+  dp.bApplyWeight = false;
+  return dp.DistFunc(&dp);
+}
+
+/* fractional-ME distortion as xPatternRefinement sets it up (TEncSearch.cpp:721-747) */
+unsigned ref_dist_frac(const short* org, int so, const short* cur, int sc, int w, int h, int hadamard)
+{
+  TComPattern pat;
+  pat.initPattern((Pel*)org, NULL, NULL, w, h, so, 0, 0, 0, 0);
+  DistParam dp;
+  s_rd->setDistParam(&pat, (Pel*)cur, sc, 1, dp, hadamard != 0);
+  dp.bApplyWeight = false;
+  return dp.DistFunc(&dp);
+}
+
+/* TComRdCost::getDistPart, unweighted (TComRdCost.cpp:449-478) */
+unsigned ref_get_dist_part(const short* cur, int sc, const short* org, int so, int w, int h, int dfunc)
+{
+  return s_rd->getDistPart((Pel*)cur, sc, (Pel*)org, so, (UInt)w, (UInt)h, false, (DFunc)dfunc);
+}
+
+unsigned ref_calc_had(const short* p0, int s0, const short* p1, int s1, int w, int h)
+{
+  return s_rd->calcHAD((Pel*)p0, s0, (Pel*)p1, s1, w, h);
+}
+
+unsigned ref_component_bits(int v) { return s_rd->xGetComponentBits(v); }
+
+unsigned ref_mv_cost(double lambda, int x, int y, int scale, int predx, int predy, unsigned* lambda_cost)
+{
+  s_rd->setLambda(lambda);
+  s_rd->getMotionCost(1, 0);
+  TComMv p(predx, predy);
+  s_rd->setPredictor(p);
+  s_rd->setCostScale(scale);
+  if (lambda_cost) *lambda_cost = s_rd->m_uiCost;
+  return s_rd->getCost(x, y);
+}
+
+/* ---- interpolation (TComInterpolationFilter public API) */
+void ref_filter_hor_luma(short* src, int ss, short* dst, int ds, int w, int h, int frac, int isLast)
+{ TComInterpolationFilter f; f.filterHorLuma(src, ss, dst, ds, w, h, frac, isLast != 0); }
+void ref_filter_ver_luma(short* src, int ss, short* dst, int ds, int w, int h, int frac, int isFirst, int isLast)
+{ TComInterpolationFilter f; f.filterVerLuma(src, ss, dst, ds, w, h, frac, isFirst != 0, isLast != 0); }
+void ref_filter_hor_chroma(short* src, int ss, short* dst, int ds, int w, int h, int frac, int isLast)
+{ TComInterpolationFilter f; f.filterHorChroma(src, ss, dst, ds, w, h, frac, isLast != 0); }
+void ref_filter_ver_chroma(short* src, int ss, short* dst, int ds, int w, int h, int frac, int isFirst, int isLast)
+{ TComInterpolationFilter f; f.filterVerChroma(src, ss, dst, ds, w, h, frac, isFirst != 0, isLast != 0); }
+
+/* ---- transforms */
+void ref_partial_butterfly(int n, short* src, short* dst, int shift, int line)
+{
+  switch (n) {
+    case 4: partialButterfly4(src, dst, shift, line); break;
+    case 8: partialButterfly8(src, dst, shift, line); break;
+    case 16: partialButterfly16(src, dst, shift, line); break;
+    default: partialButterfly32(src, dst, shift, line); break;
+  }
+}
+void ref_partial_butterfly_inverse(int n, short* src, short* dst, int shift, int line)
+{
+  switch (n) {
+    case 4: partialButterflyInverse4(src, dst, shift, line); break;
+    case 8: partialButterflyInverse8(src, dst, shift, line); break;
+    case 16: partialButterflyInverse16(src, dst, shift, line); break;
+    default: partialButterflyInverse32(src, dst, shift, line); break;
+  }
+}
+void ref_fast_forward_dst(short* b, short* c, int shift) { fastForwardDst(b, c, shift); }
+void ref_fast_inverse_dst(short* t, short* b, int shift) { fastInverseDst(t, b, shift); }
+void ref_xTrMxN(short* block, short* coeff, int w, int h, int use_dst) { xTrMxN(block, coeff, w, h, use_dst ? 0 : REG_DCT); }
+void ref_xITrMxN(short* coeff, short* block, int w, int h, int use_dst) { xITrMxN(coeff, block, w, h, use_dst ? 0 : REG_DCT); }
+
+void ref_dct_matrix(int n, short* out)
+{
+  for (int k = 0; k < n; k++)
+    for (int j = 0; j < n; j++)
+      out[k * n + j] = n == 4 ? g_aiT4[k][j] : n == 8 ? g_aiT8[k][j] : n == 16 ? g_aiT16[k][j] : g_aiT32[k][j];
+}
+
+/* g_auiSigLastScan[scanIdx][log2-1]; scan_idx 0 diag, 1 hor, 2 ver (ours) */
+void ref_scan(int scan_idx, int log2size, unsigned* out)
+{
+  int ref_idx = scan_idx == 0 ? SCAN_DIAG : (scan_idx == 1 ? SCAN_HOR : SCAN_VER);
+  const UInt* s = g_auiSigLastScan[ref_idx][log2size - 1];
+  memcpy(out, s, sizeof(UInt) << (2 * log2size));
+}
+
+/* ---- TComTrQuant with a minimal CU/slice context --------------------------------------- */
+struct TqCtx {
+  TComTrQuant tq;
+  TComDataCU cu;
+  TComSlice slice;
+  TComSPS sps;
+  TComPPS pps;
+  std::vector<UChar> tskip[3];
+  std::vector<Char> predmode;
+  std::vector<UChar> lumadir, chromadir, depth;
+  Bool bypass[256];
+  bool inited;
+  TqCtx() : inited(false) {}
+};
+static TqCtx* s_tq = 0;
+
+static TqCtx* tq_get()
+{
+  if (!s_tq) {
+    s_tq = new TqCtx;
+    TqCtx* c = s_tq;
+    /* TEncTop.cpp:322-339 init order: RDOQ off here so xQuant takes the plain branch */
+    c->tq.init(64, 64, 32, 0, NULL, NULL, NULL, false, true, false, true);
+    c->tq.setFlatScalingList();
+    c->tq.setUseScalingList(false);
+    const int nparts = 256;
+    for (int i = 0; i < 3; i++) c->tskip[i].assign(nparts, 0);
+    c->predmode.assign(nparts, MODE_INTER);
+    c->lumadir.assign(nparts, DC_IDX);
+    c->chromadir.assign(nparts, DC_IDX);
+    c->depth.assign(nparts, 0);
+    memset(c->bypass, 0, sizeof(c->bypass));
+    c->cu.m_puhTransformSkip[0] = &c->tskip[0][0];
+    c->cu.m_puhTransformSkip[1] = &c->tskip[1][0];
+    c->cu.m_puhTransformSkip[2] = &c->tskip[2][0];
+    c->cu.m_pePredMode = &c->predmode[0];
+    c->cu.m_puhLumaIntraDir = &c->lumadir[0];
+    c->cu.m_puhChromaIntraDir = &c->chromadir[0];
+    c->cu.m_puhDepth = &c->depth[0];
+    c->cu.m_CUTransquantBypass = c->bypass;
+    c->cu.m_pcSlice = &c->slice;
+    c->slice.setSPS(&c->sps);
+    c->slice.setPPS(&c->pps);
+    c->sps.setMaxTrSize(32);
+    c->inited = true;
+  }
+  return s_tq;
+}
+
+static void tq_detach(TqCtx* c)
+{
+  /* the TComDataCU destructor is never run (static lifetime); nothing to free */
+  (void)c;
+}
+
+/* TComTrQuant::xT / xIT (private) */
+void ref_xT(int use_dst, short* resi, int stride, int* coeff, int w, int h)
+{ tq_get()->tq.xT(use_dst ? 0 : REG_DCT, resi, (UInt)stride, coeff, w, h); }
+void ref_xIT(int use_dst, int* coeff, short* resi, int stride, int w, int h)
+{ tq_get()->tq.xIT(use_dst ? 0 : REG_DCT, coeff, resi, (UInt)stride, w, h); }
+void ref_transform_skip(short* resi, int stride, int* coeff, int w, int h)
+{ tq_get()->tq.xTransformSkip(resi, (UInt)stride, coeff, w, h); }
+void ref_itransform_skip(int* coeff, short* resi, int stride, int w, int h)
+{ tq_get()->tq.xITransformSkip(coeff, resi, (UInt)stride, w, h); }
+
+/* setQPforQuant (TComTrQuant.cpp:192-222) */
+void ref_set_qp(int qpy, int is_luma, int qp_bd_offset, int chroma_qp_offset, int* per, int* rem)
+{
+  TqCtx* c = tq_get();
+  c->tq.setQPforQuant(qpy, is_luma ? TEXT_LUMA : TEXT_CHROMA_U, qp_bd_offset, chroma_qp_offset);
+  *per = c->tq.m_cQP.m_iPer;
+  *rem = c->tq.m_cQP.m_iRem;
+}
+
+/* xQuant non-RDOQ branch (TComTrQuant.cpp:1102-1270).
+ * qpy/base_qpy are luma QPs before the bit-depth offset; is_intra_cu selects the scan via
+ * getCoefScanIdx together with luma_dir (intra luma only). */
+void ref_quant(int* coef, int* qcoef, int* arl, int w, int h, int qpy, int base_qpy, int qp_bd_offset,
+               int is_luma, int is_intra_slice, int is_intra_cu, int luma_dir, int sign_hide, int use_arl,
+               unsigned* abs_sum)
+{
+  TqCtx* c = tq_get();
+  c->tq.m_bUseRDOQ = false;
+  c->tq.m_bUseAdaptQpSelect = use_arl != 0;
+  c->tq.m_useTansformSkipFast = false;
+  c->slice.setSliceType(is_intra_slice ? I_SLICE : P_SLICE);
+  c->slice.setSliceQpBase(base_qpy);
+  c->sps.setQpBDOffsetY(qp_bd_offset);
+  c->sps.setQpBDOffsetC(qp_bd_offset);
+  c->pps.setSignHideFlag(sign_hide);
+  c->predmode[0] = is_intra_cu ? MODE_INTRA : MODE_INTER;
+  c->lumadir[0] = (UChar)luma_dir;
+  c->chromadir[0] = (UChar)luma_dir;
+  c->tq.setQPforQuant(qpy, is_luma ? TEXT_LUMA : TEXT_CHROMA_U, qp_bd_offset, 0);
+  UInt acsum = *abs_sum;
+  Int* parl = arl;
+  c->tq.xQuant(&c->cu, coef, qcoef, parl, w, h, acsum, is_luma ? TEXT_LUMA : TEXT_CHROMA_U, 0);
+  *abs_sum = acsum;
+  tq_detach(c);
+}
+
+/* xDeQuant flat branch (TComTrQuant.cpp:1272-1355) */
+void ref_dequant(int* qcoef, int* coef, int w, int h, int qpy, int qp_bd_offset, int is_luma)
+{
+  TqCtx* c = tq_get();
+  c->tq.setUseScalingList(false);
+  c->tq.setQPforQuant(qpy, is_luma ? TEXT_LUMA : TEXT_CHROMA_U, qp_bd_offset, 0);
+  c->tq.xDeQuant(qcoef, coef, w, h, 0);
+}
+
+/* ---- glue (TComYuv / TComPicYuv) */
+void ref_extend_border(short* pic, int stride, int w, int h, int mx, int my)
+{
+  TComPicYuv p;
+  p.xExtendPicCompBorder(pic, stride, w, h, mx, my);
+}
+
+} /* extern "C" */

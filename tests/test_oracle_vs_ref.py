@@ -1,0 +1,250 @@
+"""Pin the C restatement (oracle/hm_oracle*.c) against the reference's OWN compiled functions
+(oracle/_ref/libhmref.so = /root/reference TLibCommon sources + forwarding shim).
+
+CPU only.  This is the "oracle pinned" gate of the task: the reference ships no golden vectors
+(SURVEY.md section 4), so the pin is the reference itself run here, plus tests/golden/.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import ptr
+
+PU_SHAPES = [(64, 64), (64, 32), (32, 64), (64, 16), (64, 48), (16, 64), (48, 64),
+             (32, 32), (32, 16), (16, 32), (32, 8), (32, 24), (8, 32), (24, 32),
+             (16, 16), (16, 8), (8, 16), (16, 4), (16, 12), (4, 16), (12, 16),
+             (8, 8), (8, 4), (4, 8)]
+
+
+def rand_pels(rng, shape, bd, signed_bipred=False):
+    if signed_bipred:
+        return rng.integers(-((1 << bd) - 1), 2 * ((1 << bd) - 1) + 1, size=shape, dtype=np.int64).astype(np.int16)
+    return rng.integers(0, 1 << bd, size=shape, dtype=np.int64).astype(np.int16)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_distortion(orc, hmref, bd):
+    rng = np.random.default_rng(1234 + bd)
+    hmref.ref_init(bd)
+    bi = bd - 8
+    for (w, h) in PU_SHAPES:
+        for trial in range(3):
+            org = rand_pels(rng, (64, 64), bd, signed_bipred=(trial == 2))
+            cur = rand_pels(rng, (80, 96), bd)
+            if trial == 1:  # extremes
+                org[:] = (1 << bd) - 1
+                cur[:] = 0
+            for ss in (0, 1):
+                if ss == 1 and h <= 8:
+                    continue
+                a = orc.orc_sad(ptr(org), 64, ptr(cur, 96 * 3 + 5), 96, w, h, ss, bi)
+                b = hmref.ref_sad_me(ptr(org), 64, ptr(cur, 96 * 3 + 5), 96, w, h, ss)
+                assert a == b, (w, h, ss, trial)
+            for had in (0, 1):
+                a = (orc.orc_hads if had else orc.orc_sad)(ptr(org), 64, ptr(cur, 96 + 1), 96, w, h, *([bi] if had else [0, bi]))
+                b = hmref.ref_dist_frac(ptr(org), 64, ptr(cur, 96 + 1), 96, w, h, had)
+                assert a == b, (w, h, had, trial)
+            for df in (1, 8, 22):
+                a = orc.orc_get_dist_part(ptr(cur, 7), 96, ptr(org), 64, w, h, df, bi)
+                b = hmref.ref_get_dist_part(ptr(cur, 7), 96, ptr(org), 64, w, h, df)
+                assert a == b, (w, h, df, trial)
+            a = orc.orc_calc_had(ptr(org), 64, ptr(cur), 96, w, h, bi)
+            b = hmref.ref_calc_had(ptr(org), 64, ptr(cur), 96, w, h)
+            assert a == b
+    # chroma-sized SSE blocks (2x2 .. 32x32) through getDistPart
+    for n in (2, 4, 8, 16, 32):
+        org = rand_pels(rng, (64, 64), bd)
+        cur = rand_pels(rng, (80, 96), bd)
+        assert orc.orc_get_dist_part(ptr(cur), 96, ptr(org), 64, n, n, 1, bi) == \
+            hmref.ref_get_dist_part(ptr(cur), 96, ptr(org), 64, n, n, 1)
+
+
+def test_mv_cost(orc, hmref):
+    hmref.ref_init(8)
+    rng = np.random.default_rng(7)
+    for v in list(range(-300, 301)) + [-(1 << 14), (1 << 14) - 1, 4096, -4097]:
+        assert orc.orc_mv_component_bits(v) == hmref.ref_component_bits(v)
+    for lam in (0.5, 4.7, 57.908390, 141.3, 1000.25):
+        for _ in range(200):
+            x, y = (int(t) for t in rng.integers(-200, 200, 2))
+            px, py = (int(t) for t in rng.integers(-300, 300, 2))
+            for scale in (0, 1, 2):
+                lc = C.c_uint32()
+                b = hmref.ref_mv_cost(lam, x, y, scale, px, py, C.byref(lc))
+                assert orc.orc_lambda_motion_sad(lam) == lc.value
+                assert orc.orc_mv_cost(lc.value, x, y, scale, px, py) == b
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_interpolation_primitives(orc, hmref, bd):
+    rng = np.random.default_rng(99 + bd)
+    hmref.ref_init(bd)
+    S = 96
+    for trial in range(4):
+        pel = rand_pels(rng, (96, S), bd)
+        if trial == 1:
+            pel[:] = (1 << bd) - 1
+        if trial == 2:
+            pel[::2] = 0
+            pel[1::2] = (1 << bd) - 1
+        mid = rng.integers(-12272, 12209, size=(96, S)).astype(np.int16)  # 14-bit intermediates
+        for (w, h) in [(64, 64), (65, 72), (17, 9), (4, 4), (8, 4), (2, 2), (33, 40)]:
+            off = 8 * S + 8
+            for frac in range(4):
+                for last in (0, 1):
+                    a = np.zeros((80, 80), np.int16); b = np.zeros((80, 80), np.int16)
+                    orc.orc_filter_hor_luma(ptr(pel, off), S, ptr(a), 80, w, h, frac, last, bd)
+                    hmref.ref_filter_hor_luma(ptr(pel, off), S, ptr(b), 80, w, h, frac, last)
+                    assert np.array_equal(a, b), ("hl", w, h, frac, last)
+                for first in (0, 1):
+                    for last in (0, 1):
+                        src = pel if first else mid
+                        a = np.zeros((80, 80), np.int16); b = np.zeros((80, 80), np.int16)
+                        orc.orc_filter_ver_luma(ptr(src, off), S, ptr(a), 80, w, h, frac, first, last, bd)
+                        hmref.ref_filter_ver_luma(ptr(src, off), S, ptr(b), 80, w, h, frac, first, last)
+                        assert np.array_equal(a, b), ("vl", w, h, frac, first, last)
+            for frac in range(8):
+                for last in (0, 1):
+                    a = np.zeros((80, 80), np.int16); b = np.zeros((80, 80), np.int16)
+                    orc.orc_filter_hor_chroma(ptr(pel, off), S, ptr(a), 80, w, h, frac, last, bd)
+                    hmref.ref_filter_hor_chroma(ptr(pel, off), S, ptr(b), 80, w, h, frac, last)
+                    assert np.array_equal(a, b), ("hc", w, h, frac, last)
+                for first in (0, 1):
+                    for last in (0, 1):
+                        src = pel if first else mid
+                        a = np.zeros((80, 80), np.int16); b = np.zeros((80, 80), np.int16)
+                        orc.orc_filter_ver_chroma(ptr(src, off), S, ptr(a), 80, w, h, frac, first, last, bd)
+                        hmref.ref_filter_ver_chroma(ptr(src, off), S, ptr(b), 80, w, h, frac, first, last)
+                        assert np.array_equal(a, b), ("vc", w, h, frac, first, last)
+
+
+def test_dct_tables_and_scans(orc, hmref):
+    hmref.ref_init(8)
+    for n in (4, 8, 16, 32):
+        a = np.zeros(n * n, np.int16); b = np.zeros(n * n, np.int16)
+        orc.orc_dct_matrix(n, a); hmref.ref_dct_matrix(n, b)
+        assert np.array_equal(a, b), n
+    for log2 in (2, 3, 4, 5):
+        for scan in (0, 1, 2):
+            a = np.zeros(1 << (2 * log2), np.uint32); b = np.zeros_like(a)
+            orc.orc_scan(scan, log2, a); hmref.ref_scan(scan, log2, b)
+            assert np.array_equal(a, b), (log2, scan)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_transforms(orc, hmref, bd):
+    rng = np.random.default_rng(5 + bd)
+    hmref.ref_init(bd)
+    bi = bd - 8
+    amp = (1 << bd) - 1
+    for n in (4, 8, 16, 32):
+        for trial in range(6):
+            if trial == 0:
+                blk = np.full(n * n, amp, np.int16)
+            elif trial == 1:
+                blk = np.full(n * n, -amp, np.int16)
+            elif trial == 2:
+                blk = ((np.indices((n, n)).sum(0) % 2) * 2 * amp - amp).astype(np.int16).reshape(-1)
+            elif trial == 3:   # full int16 range exercises the (short) wrap of the forward passes
+                blk = rng.integers(-32768, 32768, n * n).astype(np.int16)
+            else:
+                blk = rng.integers(-amp, amp + 1, n * n).astype(np.int16)
+            for shift in (1, 2, 5, 7, 9, 11, 12):
+                a = np.zeros(n * n, np.int16); b = np.zeros(n * n, np.int16)
+                orc.orc_partial_butterfly(n, blk, a, shift, n); hmref.ref_partial_butterfly(n, blk.copy(), b, shift, n)
+                assert np.array_equal(a, b), ("fwd", n, shift, trial)
+                orc.orc_partial_butterfly_inverse(n, blk, a, shift, n); hmref.ref_partial_butterfly_inverse(n, blk.copy(), b, shift, n)
+                assert np.array_equal(a, b), ("inv", n, shift, trial)
+            for dst in ((0, 1) if n == 4 else (0,)):
+                a = np.zeros(n * n, np.int16); b = np.zeros(n * n, np.int16)
+                orc.orc_xTrMxN(blk, a, n, n, dst, bi); hmref.ref_xTrMxN(blk.copy(), b, n, n, dst)
+                assert np.array_equal(a, b), ("xTr", n, dst, trial)
+                orc.orc_xITrMxN(blk, a, n, n, dst, bi); hmref.ref_xITrMxN(blk.copy(), b, n, n, dst)
+                assert np.array_equal(a, b), ("xITr", n, dst, trial)
+                # strided wrappers
+                resi = rng.integers(-amp, amp + 1, (40, 64)).astype(np.int16)
+                ca = np.zeros(n * n, np.int32); cb = np.zeros(n * n, np.int32)
+                orc.orc_xT(dst, ptr(resi, 64 * 3 + 2), 64, ca, n, n, bi); hmref.ref_xT(dst, ptr(resi, 64 * 3 + 2), 64, cb, n, n)
+                assert np.array_equal(ca, cb)
+                co = rng.integers(-70000, 70000, n * n).astype(np.int32)
+                ra = np.zeros((40, 64), np.int16); rb = np.zeros((40, 64), np.int16)
+                orc.orc_xIT(dst, co, ptr(ra, 65), 64, n, n, bi); hmref.ref_xIT(dst, co.copy(), ptr(rb, 65), 64, n, n)
+                assert np.array_equal(ra, rb)
+    # 4x4 DST primitives and transform skip
+    for trial in range(20):
+        blk = rng.integers(-32768, 32768, 16).astype(np.int16)
+        for shift in (1, 3, 7, 8, 12):
+            a = np.zeros(16, np.int16); b = np.zeros(16, np.int16)
+            orc.orc_fast_forward_dst(blk, a, shift); hmref.ref_fast_forward_dst(blk.copy(), b, shift)
+            assert np.array_equal(a, b)
+            orc.orc_fast_inverse_dst(blk, a, shift); hmref.ref_fast_inverse_dst(blk.copy(), b, shift)
+            assert np.array_equal(a, b)
+        resi = rng.integers(-amp, amp + 1, (8, 16)).astype(np.int16)
+        ca = np.zeros(16, np.int32); cb = np.zeros(16, np.int32)
+        orc.orc_transform_skip(ptr(resi, 17), 16, ca, 4, 4, bd); hmref.ref_transform_skip(ptr(resi, 17), 16, cb, 4, 4)
+        assert np.array_equal(ca, cb)
+        co = rng.integers(-40000, 40000, 16).astype(np.int32)
+        ra = np.zeros((8, 16), np.int16); rb = np.zeros((8, 16), np.int16)
+        orc.orc_itransform_skip(co, ptr(ra, 1), 16, 4, 4, bd); hmref.ref_itransform_skip(co.copy(), ptr(rb, 1), 16, 4, 4)
+        assert np.array_equal(ra, rb)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_quant_dequant(orc, hmref, bd):
+    rng = np.random.default_rng(77 + bd)
+    hmref.ref_init(bd)
+    qp_bd_offset = 6 * (bd - 8)
+    for n in (4, 8, 16, 32):
+        log2 = int(np.log2(n))
+        for qp in (0, 1, 17, 22, 27, 32, 37, 45, 51):
+            for is_luma in ((1, 0) if n < 32 else (1,)):   # 4:2:0: no 32x32 chroma TU exists
+                pa, ra_ = C.c_int(), C.c_int(); pb, rb_ = C.c_int(), C.c_int()
+                orc.orc_set_qp(qp, is_luma, qp_bd_offset, 0, C.byref(pa), C.byref(ra_))
+                hmref.ref_set_qp(qp, is_luma, qp_bd_offset, 0, C.byref(pb), C.byref(rb_))
+                assert (pa.value, ra_.value) == (pb.value, rb_.value)
+                for trial in range(3):
+                    scale = [40, 2000, 32767][trial]
+                    coef = rng.integers(-scale, scale + 1, n * n).astype(np.int32)
+                    if trial == 2:
+                        coef[rng.integers(0, n * n, n)] = 0
+                    for (islice, icu, ldir, sh, arl) in [(1, 1, 26, 1, 1), (0, 0, 1, 1, 0), (0, 1, 10, 1, 1), (1, 1, 0, 0, 0)]:
+                        base_qp = qp if trial != 1 else max(0, qp - 3)
+                        scan_idx = 0
+                        if icu and is_luma and n in (4, 8):
+                            scan_idx = 1 if abs(ldir - 26) < 5 else (2 if abs(ldir - 10) < 5 else 0)
+                        if icu and (not is_luma) and n == 4:
+                            scan_idx = 1 if abs(ldir - 26) < 5 else (2 if abs(ldir - 10) < 5 else 0)
+                        scan = np.zeros(n * n, np.uint32)
+                        orc.orc_scan(scan_idx, log2, scan)
+                        bper, brem = C.c_int(), C.c_int()
+                        orc.orc_set_qp(base_qp, is_luma, qp_bd_offset, 0, C.byref(bper), C.byref(brem))
+                        qpar = oracle.QuantParam(pa.value, ra_.value, bper.value, islice, sh, arl, bd)
+                        qa = np.zeros(n * n, np.int32); qb = np.zeros(n * n, np.int32)
+                        aa = np.zeros(n * n, np.int32); ab = np.zeros(n * n, np.int32)
+                        sa, sb = C.c_uint32(0), C.c_uint32(0)
+                        orc.orc_quant(coef, qa, ptr(aa), n, n, C.byref(qpar), scan, C.byref(sa))
+                        hmref.ref_quant(coef.copy(), qb, ab, n, n, qp, base_qp, qp_bd_offset, is_luma, islice, icu, ldir, sh, arl, C.byref(sb))
+                        assert sa.value == sb.value, (n, qp, trial)
+                        assert np.array_equal(qa, qb), (n, qp, is_luma, trial, islice, icu, ldir)
+                        if arl:
+                            assert np.array_equal(aa, ab)
+                    lev = rng.integers(-40000, 40000, n * n).astype(np.int32)
+                    da = np.zeros(n * n, np.int32); db = np.zeros(n * n, np.int32)
+                    orc.orc_dequant(lev, da, n, n, pa.value, ra_.value, bd)
+                    hmref.ref_dequant(lev.copy(), db, n, n, qp, qp_bd_offset, is_luma)
+                    assert np.array_equal(da, db), (n, qp, is_luma)
+
+
+def test_extend_border(orc, hmref):
+    hmref.ref_init(8)
+    rng = np.random.default_rng(3)
+    w, h, mx, my = 40, 24, 80, 80
+    stride = w + 2 * mx
+    a = np.zeros((h + 2 * my, stride), np.int16)
+    a[my:my + h, mx:mx + w] = rng.integers(0, 256, (h, w))
+    b = a.copy()
+    orc.orc_extend_border(ptr(a, my * stride + mx), stride, w, h, mx, my)
+    hmref.ref_extend_border(ptr(b, my * stride + mx), stride, w, h, mx, my)
+    assert np.array_equal(a, b)
