@@ -1,0 +1,323 @@
+/*
+ * thevc_cuda.h -- C ABI of TLibCuda, the B200 (sm_100a) implementation of the data-parallel
+ * inner loops of the HM-7.2 HEVC codec (fr34k8/thevc).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.  The reference
+ * has no FFI of its own; its boundary is the public C++ API of four leaf classes, so every entry
+ * point below cites the reference interface it replaces (file:line under
+ * /root/reference/source/Lib).  The HM-side shim that binds these (replacement
+ * TComRdCost / TComInterpolationFilter / TComTrQuant / TComPrediction / TEncSearch members) lives
+ * in thevc_b200/host/ and is described in INTEGRATION.md.
+ *
+ * Conventions (identical to the reference): Pel = int16_t, TCoeff = int32_t, strides in ELEMENTS,
+ * motion vectors in quarter luma pels unless a name says otherwise, pictures are planar 4:2:0 with
+ * a replicated margin of max_cu+16 luma pels (TComPicYuv.cpp:71-127).
+ *
+ * Error behaviour: every function returns TVC_OK (0) or a TVC_ERR_* code and never aborts; the HM
+ * shim turns a non-zero status into exit(EXIT_FAILURE) like the reference's own fatal paths
+ * (CommonDef.h:143).  There is NO CPU fallback: without a CUDA device tvc_ctx_create fails.
+ *
+ * Threading: one host thread per context (the reference is single threaded, process-global
+ * state).  Host-pointer entry points are synchronous: results are valid on return.  *_dev entry
+ * points take device pointers, are asynchronous on the context stream and do not synchronise.
+ */
+#ifndef THEVC_CUDA_H
+#define THEVC_CUDA_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TVC_ABI_VERSION 1
+
+enum {
+  TVC_OK = 0,
+  TVC_ERR_ARG = 1,      /* invalid argument / unsupported size */
+  TVC_ERR_CUDA = 2,     /* CUDA runtime error; see tvc_last_error */
+  TVC_ERR_NOMEM = 3,
+  TVC_ERR_STATE = 4     /* e.g. tables queried before tvc_me_prepass */
+};
+
+typedef struct tvc_ctx tvc_ctx;
+
+typedef struct {
+  int width, height;    /* luma picture size (SPS)                                       */
+  int bit_depth;        /* g_uiBitDepth + g_uiBitIncrement: 8 (main) or 10 (he10)         */
+  int max_cu;           /* g_uiMaxCUWidth (64)                                            */
+  int num_slots;        /* number of device picture slots (cur, refs, pred, resi, recon)  */
+  int device;           /* CUDA device ordinal                                            */
+} tvc_config;
+
+/* ---------------------------------------------------------------------------------- context */
+int  tvc_abi_version(void);
+int  tvc_ctx_create(const tvc_config* cfg, tvc_ctx** out);
+void tvc_ctx_destroy(tvc_ctx* ctx);
+/* use a caller-owned cudaStream_t (e.g. torch's current stream) for all launches of this ctx */
+int  tvc_ctx_set_stream(tvc_ctx* ctx, void* cuda_stream);
+int  tvc_sync(tvc_ctx* ctx);
+const char* tvc_last_error(tvc_ctx* ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+uint64_t tvc_launch_count(tvc_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------- pictures
+ * A slot is a device-resident TComPicYuv: three int16 planes with margins, plus (bit_depth 8) a
+ * packed u8 copy of the luma plane used by the integer-ME kernels.
+ * Replaces: TComPicYuv::create / extendPicBorder / copyToPic (TComPicYuv.cpp:71-127, 241-286). */
+enum { TVC_PLANE_Y = 0, TVC_PLANE_U = 1, TVC_PLANE_V = 2 };
+
+/* y,u,v point at pel (0,0) of the host planes.  with_margin != 0 also copies the margins (the
+ * host picture was already border-extended, e.g. a reference reconstruction after
+ * TComSlice::setRefPicList, TComSlice.cpp:402-431).                                          */
+int tvc_pic_upload(tvc_ctx* ctx, int slot, const int16_t* y, int stride_y,
+                   const int16_t* u, const int16_t* v, int stride_c, int with_margin);
+int tvc_pic_download(tvc_ctx* ctx, int slot, int16_t* y, int stride_y,
+                     int16_t* u, int16_t* v, int stride_c, int with_margin);
+/* TComPicYuv::extendPicBorder (TComPicYuv.cpp:241-286) on the device; also refreshes the u8 copy */
+int tvc_pic_extend_border(tvc_ctx* ctx, int slot);
+/* device pointer to pel (0,0) of a plane and its stride in elements (for *_dev users)         */
+int tvc_pic_device_ptr(tvc_ctx* ctx, int slot, int plane, void** ptr, int* stride);
+/* same for the packed u8 luma copy (NULL when bit_depth != 8)                                */
+int tvc_pic_device_ptr_u8(tvc_ctx* ctx, int slot, void** ptr, int* stride);
+
+/* region ops on slots, one plane: TComYuv::subtract* / addClip* / removeHighFreq
+ * (TComYuv.cpp:401-518, 583-633).  dst = a - b ; dst = Clip(a + b) ; dst = 2*dst - a          */
+int tvc_pic_subtract(tvc_ctx* ctx, int dst_slot, int a_slot, int b_slot, int plane, int x, int y, int w, int h);
+int tvc_pic_add_clip(tvc_ctx* ctx, int dst_slot, int a_slot, int b_slot, int plane, int x, int y, int w, int h);
+int tvc_pic_remove_high_freq(tvc_ctx* ctx, int dst_slot, int a_slot, int plane, int x, int y, int w, int h);
+
+/* ---------------------------------------------------------------------------------- distortion
+ * Replaces TComRdCost::xGetSAD* / xGetSSE* / xGetHADs* reached through DistParam::DistFunc,
+ * setDistParam and getDistPart / calcHAD (TComRdCost.cpp:286-478, 490-989, 1314-1656,
+ * 1663-1872, 2122-2287).                                                                     */
+enum { TVC_DIST_SAD = 0, TVC_DIST_SSE = 1, TVC_DIST_HADS = 2 };
+
+/* Drop-in for one DistFunc call on host buffers (copies both blocks, one launch, one result).
+ * sub_shift as DistParam::iSubShift (honoured for SAD only); result already >> bitIncrement.   */
+int tvc_dist_block(tvc_ctx* ctx, int kind, const int16_t* org, int stride_org,
+                   const int16_t* cur, int stride_cur, int w, int h, int sub_shift, uint32_t* out);
+
+typedef struct {
+  int32_t kind;                                   /* TVC_DIST_*                                */
+  int32_t org_slot, org_plane, org_x, org_y;      /* block origin in a picture slot            */
+  int32_t cur_slot, cur_plane, cur_x, cur_y;      /* may reach into the margin                 */
+  int32_t w, h, sub_shift;
+} tvc_dist_job;
+
+/* n independent distortions over device-resident pictures; jobs and out are host arrays       */
+int tvc_dist_batch(tvc_ctx* ctx, int n, const tvc_dist_job* jobs, uint32_t* out);
+/* same with device-resident jobs/out, asynchronous                                            */
+int tvc_dist_batch_dev(tvc_ctx* ctx, int n, const tvc_dist_job* jobs_dev, uint32_t* out_dev);
+
+/* ---------------------------------------------------------------------------------- interpolation
+ * Drop-in for TComInterpolationFilter::filterHorLuma / filterVerLuma / filterHorChroma /
+ * filterVerChroma (TComInterpolationFilter.h:73-76, .cpp:325-415) on host buffers.  src points at
+ * the first output sample's source position exactly as in the reference (taps reach
+ * (N/2-1) elements before it and N/2 after).                                                  */
+int tvc_filter_hor_luma(tvc_ctx* ctx, const int16_t* src, int src_stride, int16_t* dst, int dst_stride,
+                        int w, int h, int frac, int is_last);
+int tvc_filter_ver_luma(tvc_ctx* ctx, const int16_t* src, int src_stride, int16_t* dst, int dst_stride,
+                        int w, int h, int frac, int is_first, int is_last);
+int tvc_filter_hor_chroma(tvc_ctx* ctx, const int16_t* src, int src_stride, int16_t* dst, int dst_stride,
+                          int w, int h, int frac, int is_last);
+int tvc_filter_ver_chroma(tvc_ctx* ctx, const int16_t* src, int src_stride, int16_t* dst, int dst_stride,
+                          int w, int h, int frac, int is_first, int is_last);
+
+/* ---------------------------------------------------------------------------------- motion compensation
+ * Replaces TComPrediction::motionCompensation -> xPredInterUni/Bi -> xPredInterLumaBlk /
+ * xPredInterChromaBlk -> xWeightedAverage/TComYuv::addAvg (TComPrediction.cpp:410-658,
+ * TComYuv.cpp:520-581) for a list of PUs of one picture.  MVs must already be clipped
+ * (TComDataCU::clipMv) as xPredInterUni does (TComPrediction.cpp:485).                         */
+typedef struct {
+  int32_t x, y, w, h;          /* luma PU rectangle in the picture                              */
+  int32_t ref_slot0, mvx0, mvy0;   /* list-0 reference slot (-1: unused) and quarter-pel MV     */
+  int32_t ref_slot1, mvx1, mvy1;   /* list-1 reference slot (-1: unused)                        */
+} tvc_pu;
+
+/* writes Y, U and V predictions of every PU into dst_slot                                     */
+int tvc_mc_batch(tvc_ctx* ctx, int dst_slot, int n, const tvc_pu* pus);
+int tvc_mc_batch_dev(tvc_ctx* ctx, int dst_slot, int n, const tvc_pu* pus_dev);
+
+/* ---------------------------------------------------------------------------------- integer ME
+ * (1) Frame pre-pass: SAD tables.  For every CTU of cur_slot and every reference in ref_slots,
+ * all 129x129 integer candidates around a per-CTU window centre, at 4x4-block granularity, even
+ * and odd rows kept apart (the FEN sub-sampled SAD of PUs taller than 8 uses even rows only,
+ * TEncSearch.cpp:324-330; PU rows are CTU-aligned multiples of 4).  Any PU's SAD at any candidate
+ * is a sum of its blocks' entries, so decisions are those of xGetSAD* (TComRdCost.cpp:518-989).
+ * 8-bit pictures only (u8 SIMD path).
+ *
+ * Table layout (uint16): T[ref][ctu][by 16][parity 2][cand 129*129][bx 16]; cand = (dy+R)*129+(dx+R),
+ * R = TVC_ME_RANGE, dx/dy relative to the CTU's centre.                                        */
+#define TVC_ME_RANGE 64
+#define TVC_ME_CAND  (2 * TVC_ME_RANGE + 1)
+
+typedef struct { int32_t cx, cy; } tvc_me_center;   /* integer-pel window centre of a CTU       */
+
+/* centres: num_refs * num_ctus entries (ref-major) or NULL for all-zero.  Centres are clamped so
+ * that every read stays inside the padded reference plane.                                     */
+int tvc_me_prepass(tvc_ctx* ctx, int cur_slot, int num_refs, const int* ref_slots,
+                   const tvc_me_center* centers);
+/* bytes of table storage tvc_me_prepass needs for num_refs references (allocated lazily)       */
+size_t tvc_me_table_bytes(tvc_ctx* ctx, int num_refs);
+/* device pointer to the tables of the last pre-pass and the (clamped) centres actually used    */
+int tvc_me_tables_dev(tvc_ctx* ctx, void** tables, tvc_me_center** centers_dev);
+/* read one PU's SAD (already <<sub_shift, >>bitIncrement) at `n` candidates from the tables;
+ * test / host-shim access path (TComRdCost DistFunc semantics for integer ME).                 */
+int tvc_me_table_lookup(tvc_ctx* ctx, int ref_index, int pu_x, int pu_y, int pu_w, int pu_h, int fen,
+                        int n, const int16_t* cand_xy /* 2n: integer mv x,y */, uint32_t* out);
+
+/* (2) Search.  Replaces TEncSearch::xMotionEstimation's integer stage: xSetSearchRange is done by
+ * the caller (it needs TComDataCU::clipMv), xPatternSearch (TEncSearch.cpp:4227-4283) or
+ * xPatternSearchFast -> xTZSearch (:4285-4474) run on the device with the reference's visiting
+ * order and strict '<' tie rule.  SADs come from the pre-pass tables when the candidate is
+ * covered (use_tables), else from the pictures.                                               */
+enum { TVC_ME_FULL = 0, TVC_ME_TZ = 1 };
+
+typedef struct {
+  int32_t ref_index;           /* index into the pre-pass ref_slots (tables) ...                */
+  int32_t ref_slot;            /* ... and the slot itself (on-demand SAD path)                  */
+  int32_t x, y, w, h;          /* luma PU rectangle                                             */
+  int32_t mode;                /* TVC_ME_FULL / TVC_ME_TZ                                       */
+  int32_t fen;                 /* getUseFastEnc(): sub-sample rows when h > 8                   */
+  int32_t search_range;        /* m_iSearchRange (TZ distance bound)                            */
+  int32_t lx, ty, rx, by;      /* window from xSetSearchRange, integer pels                     */
+  int32_t predx, predy;        /* rate predictor (quarter pels), TComRdCost::setPredictor       */
+  int32_t startx, starty;      /* TZ start point, integer pels (clipMv(pred) >> 2)              */
+  uint32_t lambda_cost;        /* m_uiCost after getMotionCost(1,0): floor(65536*sqrt(lambda))  */
+} tvc_me_job;
+
+typedef struct {
+  int32_t mvx, mvy;            /* best integer MV                                               */
+  uint32_t sad;                /* ruiSAD: best cost minus its rate term                         */
+  uint32_t n_sads;             /* candidates evaluated                                          */
+} tvc_me_result;
+
+int tvc_me_search_batch(tvc_ctx* ctx, int cur_slot, int use_tables, int n, const tvc_me_job* jobs,
+                        tvc_me_result* out);
+int tvc_me_search_batch_dev(tvc_ctx* ctx, int cur_slot, int use_tables, int n, const tvc_me_job* jobs_dev,
+                            tvc_me_result* out_dev);
+
+/* ---------------------------------------------------------------------------------- fractional ME
+ * Replaces TEncSearch::xPatternSearchFracDIF = xExtDIFUpSamplingH + xPatternRefinement(2) +
+ * xExtDIFUpSamplingQ + xPatternRefinement(1) (TEncSearch.cpp:4476-4514, 5982-6175, 711-760):
+ * 8-tap interpolation of the half/quarter planes around the integer MV and 9+9 Hadamard-SATD
+ * (or SAD) evaluations with the MV rate at cost scale 1 then 0.                               */
+typedef struct {
+  int32_t ref_slot;
+  int32_t x, y, w, h;
+  int32_t imvx, imvy;          /* integer MV from the integer stage                             */
+  int32_t predx, predy;        /* rate predictor, quarter pels                                  */
+  uint32_t lambda_cost;
+  int32_t hadamard;            /* getUseHADME()                                                 */
+} tvc_frac_job;
+
+typedef struct {
+  int32_t halfx, halfy;        /* rcMvHalf in {-1,0,1}                                          */
+  int32_t qtrx, qtry;          /* rcMvQter in {-1,0,1}                                          */
+  uint32_t cost_half, cost;    /* ruiCost after each refinement                                 */
+} tvc_frac_result;
+
+int tvc_me_frac_batch(tvc_ctx* ctx, int cur_slot, int n, const tvc_frac_job* jobs, tvc_frac_result* out);
+int tvc_me_frac_batch_dev(tvc_ctx* ctx, int cur_slot, int n, const tvc_frac_job* jobs_dev, tvc_frac_result* out_dev);
+
+/* ---------------------------------------------------------------------------------- frame-level ME pre-pass
+ * The TEncCu frame pre-pass named by the north star: for one picture and up to 8 references it
+ * runs tvc_me_prepass (SAD tables), then -- for EVERY PU of the HM partition census of every CTU
+ * (593 PU instances per CTU = 13 part shapes x 21 CUs at depths 0-2 + 5 x 64 CUs at
+ * depth 3; census order below) and every reference -- xMotionEstimation's integer stage
+ * (xSetSearchRange + xTZSearch, TEncSearch.cpp:4209-4225, 4302-4474) and fractional stage
+ * (xPatternSearchFracDIF, :4476-4514), all on the device.  The AMVP predictor is a sequential
+ * output of the CU loop, so the pre-pass takes one predictor GUESS per
+ * (reference, CTU), in quarter pels; it is used as rate predictor, search-window centre (after
+ * TComDataCU::clipMv with the PU's own CU origin, TComDataCU.cpp:3505-3517) and TZ start of every
+ * PU of that CTU, and (clipped with the CTU origin, >> 2) as the SAD-table centre.  A host whose
+ * real predictor differs re-runs tvc_me_search_batch for that PU; it still reads the tables.
+ *
+ * Census order inside a CTU (index 0..592): depth 0,1,2,3; CUs of a depth in raster order; parts of
+ * a CU: 2Nx2N, 2NxN[0,1], Nx2N[0,1], then (CU >= 16 only) 2NxnU[0,1], 2NxnD[0,1], nLx2N[0,1],
+ * nRx2N[0,1].  tvc_me_census writes the rectangles.  Result index = (ref * num_ctus + ctu) * 593 + k.
+ * PUs that do not lie inside the picture (bottom/right partial CTUs) get n_sads == 0.           */
+#define TVC_ME_CENSUS 593
+typedef struct { int16_t x, y, w, h, cu_x, cu_y; } tvc_census_pu;   /* relative to the CTU origin    */
+int tvc_me_census(tvc_census_pu* out /* TVC_ME_CENSUS entries */);
+
+typedef struct {
+  int32_t search_range;        /* m_iSearchRange (64 in every cfg)                               */
+  int32_t fen;                 /* FastEncoderDecision                                            */
+  int32_t hadamard;            /* HadamardME                                                     */
+  int32_t use_tables;          /* 1: integer search reads the SAD tables; 0: on-demand SADs only  */
+  int32_t do_frac;             /* 0: integer stage only                                          */
+  uint32_t lambda_cost;        /* floor(65536*sqrt(lambda))                                      */
+} tvc_me_frame_cfg;
+
+/* pred_qpel: num_refs * num_ctus predictor guesses (quarter pels, ref-major) or NULL for zero.
+ * int_out / frac_out: host arrays of num_refs * num_ctus * TVC_ME_CENSUS entries (either may be NULL). */
+int tvc_me_frame(tvc_ctx* ctx, int cur_slot, int num_refs, const int* ref_slots, const tvc_me_center* pred_qpel,
+                 const tvc_me_frame_cfg* cfg, tvc_me_result* int_out, tvc_frac_result* frac_out);
+/* asynchronous, results stay on the device (pred_qpel is still a HOST array: it is tiny)         */
+int tvc_me_frame_dev(tvc_ctx* ctx, int cur_slot, int num_refs, const int* ref_slots, const tvc_me_center* pred_qpel,
+                     const tvc_me_frame_cfg* cfg, tvc_me_result** int_dev, tvc_frac_result** frac_dev);
+
+/* ---------------------------------------------------------------------------------- transform / quant
+ * Replaces TComTrQuant::transformNxN = xT (-> xTrMxN -> partialButterfly4/8/16/32 /
+ * fastForwardDst) or xTransformSkip, then xQuant's non-RDOQ branch with signBitHidingHDQ; and
+ * invtransformNxN = xDeQuant + xIT / xITransformSkip (TComTrQuant.cpp:417-972, 977-1355,
+ * 1373-1704).  Flat scaling lists (ScalingList 0 in every cfg).  RDOQ (xRateDistOptQuant) stays on
+ * the host: tvc_fwd_transform_batch returns the Int coefficients it consumes.                  */
+enum {
+  TVC_TU_DST = 1,              /* 4x4 intra luma: uiMode != REG_DCT                              */
+  TVC_TU_SKIP = 2,             /* transform skip (4x4)                                           */
+  TVC_TU_BYPASS = 4            /* cu_transquant_bypass: copy                                     */
+};
+
+typedef struct {
+  int32_t plane;               /* TVC_PLANE_*                                                    */
+  int32_t x, y;                /* TU origin in samples of that plane                             */
+  int32_t log2_size;           /* 2..5                                                           */
+  int32_t flags;               /* TVC_TU_*                                                       */
+  int32_t scan_idx;            /* 0 diag, 1 hor, 2 ver (sign-data hiding walks the coding scan)  */
+  int32_t qp_per, qp_rem;      /* m_cQP after setQPforQuant                                      */
+  int32_t base_per;            /* per of the slice base QP (ADAPTIVE_QP_SELECTION)               */
+  int32_t coef_offset;         /* element offset of this TU's w*h raster in the coefficient buffer */
+} tvc_tu;
+
+typedef struct {
+  int32_t is_intra_slice;      /* rounding 171 (I) / 85 (P,B) >> 9                               */
+  int32_t sign_hide;           /* PPS sign_data_hiding                                           */
+  int32_t use_arl;             /* m_bUseAdaptQpSelect: also write ARL coefficients               */
+} tvc_quant_cfg;
+
+/* residual plane (resi_slot) -> forward transform -> Int coefficients (TCoeff raster per TU)   */
+int tvc_fwd_transform_batch(tvc_ctx* ctx, int resi_slot, int n, const tvc_tu* tus, int32_t* coef, size_t coef_elems);
+/* residual -> transform -> quant (+sign hiding): levels, optional ARL, per-TU uiAbsSum          */
+int tvc_fwd_tq_batch(tvc_ctx* ctx, int resi_slot, int n, const tvc_tu* tus, const tvc_quant_cfg* qc,
+                     int32_t* levels, int32_t* arl /* or NULL */, size_t coef_elems, uint32_t* abs_sum);
+/* levels -> dequant -> inverse transform -> residual written into resi_slot; if pred_slot >= 0
+ * also recon_slot = Clip(pred + resi) (TComYuv::addClip)                                        */
+int tvc_inv_tq_batch(tvc_ctx* ctx, int resi_slot, int pred_slot, int recon_slot, int n, const tvc_tu* tus,
+                     const int32_t* levels, size_t coef_elems);
+/* device-resident variants (tus_dev / coefficient buffers on the device), asynchronous.  The TU
+ * list must be grouped by ascending log2_size (the host-pointer entry points require the same);
+ * counts[4] = number of 4x4, 8x8, 16x16, 32x32 TUs (host array).                               */
+int tvc_fwd_tq_batch_dev(tvc_ctx* ctx, int resi_slot, int n, const tvc_tu* tus_dev, const int32_t* counts,
+                         const tvc_quant_cfg* qc, int32_t* levels_dev, int32_t* arl_dev, uint32_t* abs_sum_dev);
+int tvc_inv_tq_batch_dev(tvc_ctx* ctx, int resi_slot, int pred_slot, int recon_slot, int n, const tvc_tu* tus_dev,
+                         const int32_t* counts, const int32_t* levels_dev);
+
+/* drop-ins on host blocks for the leaf members (one TU per call)                                */
+int tvc_xT(tvc_ctx* ctx, int use_dst, const int16_t* resi, int stride, int32_t* coef, int w, int h);
+int tvc_xIT(tvc_ctx* ctx, int use_dst, const int32_t* coef, int16_t* resi, int stride, int w, int h);
+int tvc_xDeQuant(tvc_ctx* ctx, const int32_t* qcoef, int32_t* coef, int w, int h, int per, int rem);
+
+/* ---------------------------------------------------------------------------------- diagnostics
+ * integer-pipe micro-benchmarks used for the ME roofline denominator; returns the
+ * measured rate in giga-instructions/s for the whole GPU                                        */
+enum { TVC_UB_VABSDIFF4 = 0, TVC_UB_IADD3 = 1, TVC_UB_IMAD = 2, TVC_UB_LDS128 = 3 };
+int tvc_ubench(tvc_ctx* ctx, int which, double* ginstr_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THEVC_CUDA_H */

@@ -1,0 +1,124 @@
+// tvc_internal.cuh -- shared definitions of the TLibCuda implementation (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/thevc_cuda.h"
+
+namespace tvc {
+
+constexpr int kNumSM = 148;          // B200
+constexpr int kMaxSlots = 32;
+constexpr int kMaxRefs = 16;
+
+// Device-resident TComPicYuv: int16 planes with margins (TComPicYuv.cpp:71-127) and, for 8-bit
+// content, a packed u8 copy of luma for the integer-ME SIMD path.
+struct Pic {
+  int16_t* buf[3] = {nullptr, nullptr, nullptr};   // allocation base (top-left of the margin)
+  int16_t* org[3] = {nullptr, nullptr, nullptr};   // pel (0,0)
+  int stride[3] = {0, 0, 0};                       // elements
+  int w[3] = {0, 0, 0}, h[3] = {0, 0, 0};
+  int mx[3] = {0, 0, 0}, my[3] = {0, 0, 0};        // margins
+  uint8_t* buf8 = nullptr;                         // packed luma copy (base incl. margin)
+  uint8_t* org8 = nullptr;
+  int stride8 = 0;
+  CUtensorMap tmap_cur;                            // u8 luma, box 64x64
+  CUtensorMap tmap_ref;                            // u8 luma, box 192x192
+  bool has_tmap = false;
+};
+
+// plane table handed to kernels by value
+struct PlaneTable {
+  int16_t* org[kMaxSlots][3];
+  int stride[3];
+};
+
+struct Scratch {
+  void* dev = nullptr;
+  void* host = nullptr;     // pinned
+  size_t bytes = 0;
+};
+
+}  // namespace tvc
+
+struct tvc_ctx {
+  tvc_config cfg;
+  int bi;                         // bitIncrement = bit_depth - 8
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::vector<tvc::Pic> pics;
+  tvc::PlaneTable planes;
+  tvc::Scratch in, out;           // staging for host-pointer entry points
+  std::string err;
+  uint64_t launches = 0;
+  int num_ctus_x = 0, num_ctus_y = 0;
+  // ME tables
+  uint16_t* me_tables = nullptr;
+  size_t me_table_bytes = 0;
+  tvc_me_center* me_centers = nullptr;      // device, num_refs * num_ctus
+  int me_num_refs = 0;
+  int me_ref_slots[tvc::kMaxRefs];
+  int me_cur_slot = -1;
+  // frame-level ME pre-pass buffers (device): jobs, integer results, frac jobs, frac results
+  tvc_me_job* fr_jobs = nullptr;
+  tvc_me_result* fr_int = nullptr;
+  tvc_frac_job* fr_fjobs = nullptr;
+  tvc_frac_result* fr_frac = nullptr;
+  size_t fr_cap = 0;              // entries
+  // dedicated pinned staging of the asynchronous ME entry points (an event guards host reuse)
+  tvc::Scratch me_stage, fr_stage;
+  cudaEvent_t me_ev = nullptr, fr_ev = nullptr;
+  // driver entry point for tensor maps
+  void* encode_tiled = nullptr;
+};
+
+namespace tvc {
+
+int set_err(tvc_ctx* c, int code, const char* fmt, ...);
+int check_cuda(tvc_ctx* c, cudaError_t e, const char* what);
+int ensure_scratch(tvc_ctx* c, Scratch& s, size_t bytes);
+// wait until the previous asynchronous H2D copy out of a staging buffer has executed, (re)size it
+int stage_acquire(tvc_ctx* c, Scratch& s, cudaEvent_t& ev, size_t bytes);
+inline bool valid_slot(const tvc_ctx* c, int s) { return s >= 0 && s < (int)c->pics.size(); }
+
+#define TVC_CUDA(c, expr)                                                       \
+  do {                                                                          \
+    cudaError_t _e = (expr);                                                    \
+    if (_e != cudaSuccess) return tvc::check_cuda((c), _e, #expr);              \
+  } while (0)
+
+#define TVC_LAUNCH_CHECK(c)                                                     \
+  do {                                                                          \
+    (c)->launches++;                                                            \
+    cudaError_t _e = cudaGetLastError();                                        \
+    if (_e != cudaSuccess) return tvc::check_cuda((c), _e, "kernel launch");    \
+  } while (0)
+
+// ---- table layout of the ME pre-pass (shared by producer and consumers) ----------------------
+// T[ref][ctu][by 16][q 4][slot 129*129][par 2][bx 4] uint16.  Within one dy row the 129 dx values
+// are stored permuted so that the 8 candidates a producer warp handles together (equal dx mod 16)
+// are adjacent: slot(dx) = ((dx+64)&15)*8 + ((dx+64)>>4) for dx < 64, and 128 for dx == +64.
+constexpr int kMeR = TVC_ME_RANGE;
+constexpr int kMeC = TVC_ME_CAND;                       // 129
+constexpr int kMeCands = kMeC * kMeC;                   // 16641
+constexpr size_t kMeGranule = 8;                        // uint16 per (cand, by, q): par 2 x bx 4
+constexpr size_t kMeCtuElems = (size_t)16 * 4 * kMeCands * kMeGranule;   // uint16 per (ref, ctu)
+
+__host__ __device__ inline int me_dx_slot(int dx)
+{
+  int u = dx + kMeR;
+  return (u == 2 * kMeR) ? 2 * kMeR : ((u & 15) * 8 + (u >> 4));
+}
+// element index (uint16 units) inside one (ref, ctu) table
+__host__ __device__ inline size_t me_entry(int by, int q, int dy, int dx)
+{
+  return (((size_t)(by * 4 + q) * kMeCands) + (size_t)(dy + kMeR) * kMeC + me_dx_slot(dx)) * kMeGranule;
+}
+
+}  // namespace tvc

@@ -1,0 +1,186 @@
+// tvc_interp.cu -- TComInterpolationFilter drop-ins and batched motion compensation
+// (TComInterpolationFilter.cpp:325-415; TComPrediction.cpp:410-658; TComYuv.cpp:520-581).
+#include "tvc_internal.cuh"
+#include "tvc_interp.cuh"
+
+namespace tvc {
+
+// generic block filter on a dense staging buffer: one thread per output sample
+template <int N>
+__global__ void k_filter_block(const int16_t* __restrict__ src, int ss, int16_t* __restrict__ dst, int w, int h,
+                               int frac, int isVert, int isFirst, int isLast, int bd)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w * h) return;
+  int y = i / w, x = i - y * w;
+  dst[i] = if_sample<N>(src + (size_t)y * ss + x, isVert ? ss : 1, frac, isFirst != 0, isLast != 0, bd);
+}
+
+static int filter_dropin(tvc_ctx* c, int ntaps, int isVert, const int16_t* src, int ss, int16_t* dst, int ds, int w,
+                         int h, int frac, int isFirst, int isLast)
+{
+  if (!c || !src || !dst || w <= 0 || h <= 0 || w > 256 || h > 256 || frac < 0 || frac >= (ntaps == 8 ? 4 : 8))
+    return set_err(c, TVC_ERR_ARG, "tvc_filter_*: bad argument");
+  int before = frac ? (ntaps / 2 - 1) : 0, after = frac ? (ntaps / 2) : 0;
+  int x0 = isVert ? 0 : -before, x1 = isVert ? w : w + after;
+  int y0 = isVert ? -before : 0, y1 = isVert ? h + after : h;
+  int sw = x1 - x0, sh = y1 - y0;
+  size_t in_bytes = (size_t)sw * sh * 2, out_bytes = (size_t)w * h * 2;
+  int r;
+  if ((r = ensure_scratch(c, c->in, in_bytes))) return r;
+  if ((r = ensure_scratch(c, c->out, out_bytes))) return r;
+  int16_t* hp = (int16_t*)c->in.host;
+  for (int y = 0; y < sh; y++) memcpy(hp + (size_t)y * sw, src + (ptrdiff_t)(y0 + y) * ss + x0, (size_t)sw * 2);
+  TVC_CUDA(c, cudaMemcpyAsync(c->in.dev, hp, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  const int16_t* dsrc = (const int16_t*)c->in.dev + (size_t)(-y0) * sw + (-x0);
+  int n = w * h;
+  if (ntaps == 8)
+    k_filter_block<8><<<(n + 255) / 256, 256, 0, c->stream>>>(dsrc, sw, (int16_t*)c->out.dev, w, h, frac, isVert, isFirst, isLast, c->cfg.bit_depth);
+  else
+    k_filter_block<4><<<(n + 255) / 256, 256, 0, c->stream>>>(dsrc, sw, (int16_t*)c->out.dev, w, h, frac, isVert, isFirst, isLast, c->cfg.bit_depth);
+  TVC_LAUNCH_CHECK(c);
+  TVC_CUDA(c, cudaMemcpyAsync(c->out.host, c->out.dev, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  TVC_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int16_t* op = (const int16_t*)c->out.host;
+  for (int y = 0; y < h; y++) memcpy(dst + (ptrdiff_t)y * ds, op + (size_t)y * w, (size_t)w * 2);
+  return TVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ MC
+// One CTA per (PU, plane).  xPredInterLumaBlk / xPredInterChromaBlk (TComPrediction.cpp:554-645):
+// frac in one direction -> single 1-D pass; both -> horizontal pass over h+N-1 rows into shared
+// memory (14-bit intermediates) then vertical pass.  Bi-prediction keeps both lists at 14 bits
+// and averages with TComYuv::addAvg's rounding (TComYuv.cpp:537-549).
+constexpr int kMcMaxW = 64, kMcMaxH = 64;
+
+template <int N>
+__device__ void mc_one_list(const int16_t* __restrict__ ref, int rs, int mvx, int mvy, int w, int h, bool bi, int bd,
+                            int16_t* __restrict__ tmp /* smem w*(h+N-1) */, int16_t* __restrict__ dst, int ds)
+{
+  constexpr int FB = (N == 8) ? 2 : 3;           // fractional bits
+  constexpr int FM = (1 << FB) - 1;
+  ref += (mvx >> FB) + (ptrdiff_t)(mvy >> FB) * rs;
+  int xf = mvx & FM, yf = mvy & FM;
+  bool last = !bi;
+  int n = w * h;
+  if (yf == 0) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      int y = i / w, x = i - y * w;
+      dst[(size_t)y * ds + x] = if_sample<N>(ref + (ptrdiff_t)y * rs + x, 1, xf, true, last, bd);
+    }
+  } else if (xf == 0) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      int y = i / w, x = i - y * w;
+      dst[(size_t)y * ds + x] = if_sample<N>(ref + (ptrdiff_t)y * rs + x, rs, yf, true, last, bd);
+    }
+  } else {
+    constexpr int HB = N / 2 - 1;
+    int th = h + N - 1;
+    const int16_t* r0 = ref - (ptrdiff_t)HB * rs;
+    for (int i = threadIdx.x; i < w * th; i += blockDim.x) {
+      int y = i / w, x = i - y * w;
+      tmp[i] = if_sample<N>(r0 + (ptrdiff_t)y * rs + x, 1, xf, true, false, bd);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      int y = i / w, x = i - y * w;
+      dst[(size_t)y * ds + x] = if_sample<N>(tmp + (y + HB) * w + x, w, yf, false, last, bd);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_mc_batch(PlaneTable pt, int dst_slot, int n, const tvc_pu* __restrict__ pus, int bd)
+{
+  __shared__ int16_t s_tmp[kMcMaxW * (kMcMaxH + 7)];
+  __shared__ int16_t s_l0[kMcMaxW * kMcMaxH];
+  __shared__ int16_t s_l1[kMcMaxW * kMcMaxH];
+  int pl = blockIdx.y;
+  tvc_pu pu = pus[blockIdx.x];
+  int sh = pl ? 1 : 0;
+  int w = pu.w >> sh, h = pu.h >> sh, x0 = pu.x >> sh, y0 = pu.y >> sh;
+  int stride = pt.stride[pl];
+  int16_t* dst = pt.org[dst_slot][pl] + (ptrdiff_t)y0 * stride + x0;
+  bool use0 = pu.ref_slot0 >= 0, use1 = pu.ref_slot1 >= 0;
+  bool bi = use0 && use1;
+  if (!bi) {
+    int slot = use0 ? pu.ref_slot0 : pu.ref_slot1;
+    int mvx = use0 ? pu.mvx0 : pu.mvx1, mvy = use0 ? pu.mvy0 : pu.mvy1;
+    const int16_t* ref = pt.org[slot][pl] + (ptrdiff_t)y0 * stride + x0;
+    if (pl == 0) mc_one_list<8>(ref, stride, mvx, mvy, w, h, false, bd, s_tmp, dst, stride);
+    else         mc_one_list<4>(ref, stride, mvx, mvy, w, h, false, bd, s_tmp, dst, stride);
+    return;
+  }
+  const int16_t* ref0 = pt.org[pu.ref_slot0][pl] + (ptrdiff_t)y0 * stride + x0;
+  const int16_t* ref1 = pt.org[pu.ref_slot1][pl] + (ptrdiff_t)y0 * stride + x0;
+  if (pl == 0) mc_one_list<8>(ref0, stride, pu.mvx0, pu.mvy0, w, h, true, bd, s_tmp, s_l0, w);
+  else         mc_one_list<4>(ref0, stride, pu.mvx0, pu.mvy0, w, h, true, bd, s_tmp, s_l0, w);
+  __syncthreads();
+  if (pl == 0) mc_one_list<8>(ref1, stride, pu.mvx1, pu.mvy1, w, h, true, bd, s_tmp, s_l1, w);
+  else         mc_one_list<4>(ref1, stride, pu.mvx1, pu.mvy1, w, h, true, bd, s_tmp, s_l1, w);
+  __syncthreads();
+  int shiftNum = kIfPrec + 1 - bd;
+  int offset = (1 << (shiftNum - 1)) + 2 * kIfOffs;
+  int maxv = (1 << bd) - 1;
+  for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+    int y = i / w, x = i - y * w;
+    int v = ((int)s_l0[i] + (int)s_l1[i] + offset) >> shiftNum;
+    v = v < 0 ? 0 : (v > maxv ? maxv : v);
+    dst[(size_t)y * stride + x] = (int16_t)v;
+  }
+}
+
+}  // namespace tvc
+
+using namespace tvc;
+
+extern "C" {
+
+int tvc_filter_hor_luma(tvc_ctx* c, const int16_t* s, int ss, int16_t* d, int ds, int w, int h, int frac, int is_last)
+{ return filter_dropin(c, 8, 0, s, ss, d, ds, w, h, frac, 1, is_last != 0); }
+int tvc_filter_ver_luma(tvc_ctx* c, const int16_t* s, int ss, int16_t* d, int ds, int w, int h, int frac, int is_first, int is_last)
+{ return filter_dropin(c, 8, 1, s, ss, d, ds, w, h, frac, is_first != 0, is_last != 0); }
+int tvc_filter_hor_chroma(tvc_ctx* c, const int16_t* s, int ss, int16_t* d, int ds, int w, int h, int frac, int is_last)
+{ return filter_dropin(c, 4, 0, s, ss, d, ds, w, h, frac, 1, is_last != 0); }
+int tvc_filter_ver_chroma(tvc_ctx* c, const int16_t* s, int ss, int16_t* d, int ds, int w, int h, int frac, int is_first, int is_last)
+{ return filter_dropin(c, 4, 1, s, ss, d, ds, w, h, frac, is_first != 0, is_last != 0); }
+
+int tvc_mc_batch_dev(tvc_ctx* c, int dst_slot, int n, const tvc_pu* pus_dev)
+{
+  if (!c || !valid_slot(c, dst_slot) || n < 0 || (n && !pus_dev)) return set_err(c, TVC_ERR_ARG, "tvc_mc_batch_dev: bad argument");
+  if (n == 0) return TVC_OK;
+  dim3 grd(n, 3);
+  k_mc_batch<<<grd, 256, 0, c->stream>>>(c->planes, dst_slot, n, pus_dev, c->cfg.bit_depth);
+  TVC_LAUNCH_CHECK(c);
+  return TVC_OK;
+}
+
+int tvc_mc_batch(tvc_ctx* c, int dst_slot, int n, const tvc_pu* pus)
+{
+  if (!c || !valid_slot(c, dst_slot) || n < 0 || (n && !pus)) return set_err(c, TVC_ERR_ARG, "tvc_mc_batch: bad argument");
+  if (n == 0) return TVC_OK;
+  const Pic& p = c->pics[dst_slot];
+  for (int i = 0; i < n; i++) {
+    const tvc_pu& u = pus[i];
+    bool ok = u.w > 0 && u.h > 0 && u.w <= 64 && u.h <= 64 && !(u.w & 3) && !(u.h & 3) && u.x >= 0 && u.y >= 0 &&
+              u.x + u.w <= p.w[0] + p.mx[0] && u.y + u.h <= p.h[0] + p.my[0] && (u.ref_slot0 >= 0 || u.ref_slot1 >= 0) &&
+              (u.ref_slot0 < 0 || valid_slot(c, u.ref_slot0)) && (u.ref_slot1 < 0 || valid_slot(c, u.ref_slot1));
+    // the 8-tap window of a clipped MV stays inside the margin (TComDataCU::clipMv, TComDataCU.cpp:3505)
+    for (int l = 0; ok && l < 2; l++) {
+      int slot = l ? u.ref_slot1 : u.ref_slot0;
+      if (slot < 0) continue;
+      int mvx = l ? u.mvx1 : u.mvx0, mvy = l ? u.mvy1 : u.mvy0;
+      int ix = u.x + (mvx >> 2), iy = u.y + (mvy >> 2);
+      ok = ix - 3 >= -p.mx[0] && iy - 3 >= -p.my[0] && ix + u.w + 4 <= p.w[0] + p.mx[0] && iy + u.h + 4 <= p.h[0] + p.my[0];
+    }
+    if (!ok) return set_err(c, TVC_ERR_ARG, "tvc_mc_batch: PU %d invalid or MV reaches outside the padded picture", i);
+  }
+  int r;
+  if ((r = ensure_scratch(c, c->in, (size_t)n * sizeof(tvc_pu)))) return r;
+  memcpy(c->in.host, pus, (size_t)n * sizeof(tvc_pu));
+  TVC_CUDA(c, cudaMemcpyAsync(c->in.dev, c->in.host, (size_t)n * sizeof(tvc_pu), cudaMemcpyHostToDevice, c->stream));
+  if ((r = tvc_mc_batch_dev(c, dst_slot, n, (const tvc_pu*)c->in.dev))) return r;
+  TVC_CUDA(c, cudaStreamSynchronize(c->stream));
+  return TVC_OK;
+}
+
+}  // extern "C"

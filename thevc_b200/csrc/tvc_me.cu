@@ -1,0 +1,1036 @@
+// tvc_me.cu -- motion estimation on the device.
+//
+//  (1) k_me_sad_tables : per-frame pre-pass.  One CTA per (CTU, reference): the 192x192 u8 search
+//      window and the 64x64 u8 current CTU are staged into shared memory with TMA
+//      (cp.async.bulk.tensor.2d + mbarrier), then every warp walks tasks of 8 dx (equal dx mod 16,
+//      so the byte alignment is warp-uniform) x 4 column quarters x 8 dy, sliding an 8-row register
+//      window over the reference and accumulating VABSDIFF4.U8.ACC into even-row / odd-row sums of
+//      every 4x4 block (TComRdCost.cpp:518-989 with the FEN row sub-sampling of
+//      TEncSearch.cpp:324-330).  Output: uint16 tables, layout in tvc_internal.cuh.
+//  (2) k_me_search     : xPatternSearch / xTZSearch (TEncSearch.cpp:4227-4474) per PU job, one warp
+//      per job, SADs from the tables (or from the pictures), MV rate added per candidate
+//      (TComRdCost.h:196-213), reference visiting order and strict '<'.
+//  (3) k_me_frac       : xPatternSearchFracDIF (TEncSearch.cpp:4476-4514): 8-tap half/quarter
+//      interpolation around the integer MV and 9+9 Hadamard SATD evaluations, one CTA per job,
+//      14-bit intermediates in shared memory, Hadamard butterflies in registers + warp shuffles.
+#include "tvc_internal.cuh"
+#include "tvc_interp.cuh"
+
+namespace tvc {
+
+// ================================================================================ (1) SAD tables
+constexpr int kWinW = 192, kWinH = 192;
+constexpr int kSmemWin = kWinW * kWinH;          // 36864
+constexpr int kSmemCur = 64 * 64;                // 4096
+constexpr int kSmemTables = kSmemWin + kSmemCur + 64;
+
+struct MeMaps {
+  CUtensorMap cur;
+  CUtensorMap ref[8];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar)
+{
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t vsad4_acc(uint32_t a, uint32_t b, uint32_t c)
+{
+  uint32_t d;
+  asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// one warp task.  Lane parameters: X = byte offset of the lane's 16-byte cur quarter inside a window
+// row for its dx (X = dx+64 + 16q, X & 15 == align16 for all lanes), dyb = first dy (0-based, i.e.
+// dy+64) of its DYB consecutive dy values.  WO = (align16 >> 2) is the word offset inside the
+// 16-byte chunk, SH = (align16 & 3) * 8 the funnel shift; both warp-uniform.
+template <int DYB, int WO>
+__device__ __forceinline__ void sad_task(const uint8_t* __restrict__ win, const uint8_t* __restrict__ cur, int X, int SH,
+                                         int dyb, int q, bool active, uint16_t* __restrict__ tbl, int dxslot)
+{
+  const uint8_t* wbase = win + (X & ~15);
+  const uint8_t* cbase = cur + 16 * q;
+  uint32_t R[DYB][4];      // aligned reference words of DYB consecutive window rows (slot = row & (DYB-1))
+  auto load_row = [&](int row, uint32_t* dst) {
+    const uint4* p = reinterpret_cast<const uint4*>(wbase + row * kWinW);
+    uint4 lo = p[0], hi = p[1];
+    uint32_t W[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int m = 0; m < 4; m++) dst[m] = __funnelshift_r(W[WO + m], W[WO + m + 1], SH);
+  };
+#pragma unroll
+  for (int d = 0; d < DYB - 1; d++) load_row(dyb + d, R[d]);
+
+  uint32_t E[DYB][4], O[DYB][4];
+  for (int y0 = 0; y0 < 64; y0 += (DYB >= 4 ? DYB : 4)) {
+#pragma unroll
+    for (int yy = 0; yy < (DYB >= 4 ? DYB : 4); yy++) {
+      const int y = y0 + yy;
+      load_row(dyb + y + DYB - 1, R[(yy + DYB - 1) % DYB]);
+      const uint4 c4 = *reinterpret_cast<const uint4*>(cbase + y * 64);
+      const uint32_t C[4] = {c4.x, c4.y, c4.z, c4.w};
+      const int r = yy & 3;
+#pragma unroll
+      for (int d = 0; d < DYB; d++) {
+        const uint32_t* rr = R[(yy + d) % DYB];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          if (r == 0) E[d][m] = vsad4_acc(C[m], rr[m], 0u);
+          else if (r == 1) O[d][m] = vsad4_acc(C[m], rr[m], 0u);
+          else if (r == 2) E[d][m] = vsad4_acc(C[m], rr[m], E[d][m]);
+          else O[d][m] = vsad4_acc(C[m], rr[m], O[d][m]);
+        }
+      }
+      if (r == 3 && active) {
+        const int by = y >> 2;
+#pragma unroll
+        for (int d = 0; d < DYB; d++) {
+          uint4 o;
+          o.x = E[d][0] | (E[d][1] << 16);
+          o.y = E[d][2] | (E[d][3] << 16);
+          o.z = O[d][0] | (O[d][1] << 16);
+          o.w = O[d][2] | (O[d][3] << 16);
+          size_t e = (((size_t)(by * 4 + q) * kMeCands) + (size_t)(dyb + d) * kMeC + dxslot) * kMeGranule;
+          *reinterpret_cast<uint4*>(tbl + e) = o;
+        }
+      }
+    }
+  }
+}
+
+template <int DYB>
+__device__ __forceinline__ void sad_task_wo(int wo, const uint8_t* win, const uint8_t* cur, int X, int SH, int dyb, int q,
+                                            bool active, uint16_t* tbl, int dxslot)
+{
+  switch (wo) {
+    case 0: sad_task<DYB, 0>(win, cur, X, SH, dyb, q, active, tbl, dxslot); break;
+    case 1: sad_task<DYB, 1>(win, cur, X, SH, dyb, q, active, tbl, dxslot); break;
+    case 2: sad_task<DYB, 2>(win, cur, X, SH, dyb, q, active, tbl, dxslot); break;
+    default: sad_task<DYB, 3>(win, cur, X, SH, dyb, q, active, tbl, dxslot); break;
+  }
+}
+
+__global__ void __launch_bounds__(256, 2)
+k_me_sad_tables(const __grid_constant__ MeMaps maps, int num_ctus, int ctus_x, int mx, int my,
+                const tvc_me_center* __restrict__ centers, uint16_t* __restrict__ tables)
+{
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* win = smem;
+  uint8_t* cur = smem + kSmemWin;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kSmemWin + kSmemCur);
+  const int ctu = blockIdx.x, ref = blockIdx.y;
+  const int cx0 = (ctu % ctus_x) * 64, cy0 = (ctu / ctus_x) * 64;
+  const tvc_me_center cen = centers[(size_t)ref * num_ctus + ctu];
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, kSmemWin + kSmemCur);
+    tma_load_2d(win, &maps.ref[ref], mx + cx0 + cen.cx - kMeR, my + cy0 + cen.cy - kMeR, bar);
+    tma_load_2d(cur, &maps.cur, mx + cx0, my + cy0, bar);
+  }
+  mbar_wait(bar, 0);
+
+  uint16_t* tbl = tables + ((size_t)ref * num_ctus + ctu) * kMeCtuElems;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = lane & 3, i8 = lane >> 2;
+  // tasks: [0,256) (a,g) 8 dx x 8 dy ; [256,272) (a) last dy row ; [272,274) dx=+64 column, 8 dy-groups
+  // per warp ; 274 the (+64,+64) corner.
+  for (int t = warp; t < 275; t += 8) {
+    if (t < 256) {
+      int a = t & 15, g = t >> 4;
+      int u = a + 16 * i8;
+      sad_task_wo<8>((a >> 2) & 3, win, cur, u + 16 * q, (a & 3) * 8, g * 8, q, true, tbl, a * 8 + i8);
+    } else if (t < 272) {
+      int a = t - 256;
+      int u = a + 16 * i8;
+      sad_task_wo<1>((a >> 2) & 3, win, cur, u + 16 * q, (a & 3) * 8, 128, q, true, tbl, a * 8 + i8);
+    } else if (t < 274) {
+      int g = (t - 272) * 8 + i8;
+      sad_task_wo<8>(0, win, cur, 128 + 16 * q, 0, g * 8, q, true, tbl, 128);
+    } else {
+      sad_task_wo<1>(0, win, cur, 128 + 16 * q, 0, 128, q, i8 == 0, tbl, 128);
+    }
+  }
+}
+
+// ---- table read: SAD of a PU (inside one CTU) at candidate (dx,dy) relative to the table centre.
+// Lanes split the (block-row, quarter) granules; result valid in all lanes after the reduction.
+__device__ __forceinline__ uint32_t table_pu_sad_partial(const uint16_t* __restrict__ tbl, int bx0, int by0, int nbx,
+                                                         int nby, bool even_only, int dy, int dx, int lane)
+{
+  // granules: by in [by0, by0+nby), q in [bx0/4, (bx0+nbx-1)/4]
+  const int q0 = bx0 >> 2, q1 = (bx0 + nbx - 1) >> 2, nq = q1 - q0 + 1;
+  const int total = nby * nq;
+  uint32_t acc = 0;
+  const size_t cand = (size_t)(dy + kMeR) * kMeC + me_dx_slot(dx);
+  for (int i = lane; i < total; i += 32) {
+    int by = by0 + i / nq, q = q0 + i % nq;
+    const uint4 g = *reinterpret_cast<const uint4*>(tbl + (((size_t)(by * 4 + q) * kMeCands) + cand) * kMeGranule);
+    uint32_t ev[4] = {g.x & 0xffffu, g.x >> 16, g.y & 0xffffu, g.y >> 16};
+    uint32_t od[4] = {g.z & 0xffffu, g.z >> 16, g.w & 0xffffu, g.w >> 16};
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      int bx = q * 4 + m;
+      if (bx >= bx0 && bx < bx0 + nbx) acc += even_only ? ev[m] : (ev[m] + od[m]);
+    }
+  }
+  return acc;
+}
+
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ================================================================================ (2) search
+__device__ __forceinline__ uint32_t mv_comp_bits(int v)
+{
+  // xGetComponentBits (TComRdCost.cpp:270-284): 2*floor(log2(t)) + 1 with t = v<=0 ? -2v+1 : 2v
+  uint32_t t = (v <= 0) ? (uint32_t)((-v << 1) + 1) : (uint32_t)(v << 1);
+  return 2u * (31u - (uint32_t)__clz(t)) + 1u;
+}
+__device__ __forceinline__ uint32_t mv_cost(uint32_t lc, int x, int y, int scale, int px, int py)
+{
+  uint32_t bits = mv_comp_bits((x << scale) - px) + mv_comp_bits((y << scale) - py);
+  return (lc * bits) >> 16;
+}
+
+struct SearchCtx {
+  // SAD sources
+  const uint16_t* tbl;      // table of (ref, ctu) or nullptr
+  int tcx, tcy;             // table centre
+  int bx0, by0, nbx, nby;   // PU in 4x4 blocks inside the CTU
+  const int16_t* org; int so;
+  const int16_t* ref; int rs;   // co-located pel of the PU in the reference plane
+  int w, h, sub, bi;
+  uint32_t lc; int px, py;
+  int lx, ty, rx, by;
+  // state (IntTZSearchStruct)
+  uint32_t best_sad; int best_x, best_y; uint32_t best_dist, best_round; int point_nr;
+  uint32_t n_sads;
+  int lane;
+};
+
+__device__ uint32_t cand_sad(const SearchCtx& s, int x, int y)
+{
+  int dx = x - s.tcx, dy = y - s.tcy;
+  uint32_t acc;
+  if (s.tbl && dx >= -kMeR && dx <= kMeR && dy >= -kMeR && dy <= kMeR) {
+    acc = table_pu_sad_partial(s.tbl, s.bx0, s.by0, s.nbx, s.nby, s.sub != 0, dy, dx, s.lane);
+  } else {
+    const int16_t* c = s.ref + (ptrdiff_t)y * s.rs + x;
+    int step = 1 << s.sub, nrows = s.h >> s.sub, total = s.w * nrows;
+    acc = 0;
+    for (int i = s.lane; i < total; i += 32) {
+      int r = i / s.w, xx = i - r * s.w;
+      acc += (uint32_t)abs((int)s.org[(r * step) * s.so + xx] - (int)c[(ptrdiff_t)(r * step) * s.rs + xx]);
+    }
+  }
+  acc = warp_sum_u32(acc);
+  return (acc << s.sub) >> s.bi;
+}
+
+// xTZSearchHelp (TEncSearch.cpp:312-349)
+__device__ __forceinline__ void tz_help(SearchCtx& s, int x, int y, int point_nr, uint32_t dist)
+{
+  uint32_t sad = cand_sad(s, x, y) + mv_cost(s.lc, x, y, 2, s.px, s.py);
+  s.n_sads++;
+  if (sad < s.best_sad) {
+    s.best_sad = sad; s.best_x = x; s.best_y = y;
+    s.best_dist = dist; s.best_round = 0; s.point_nr = point_nr;
+  }
+}
+
+// xTZ2PointSearch (TEncSearch.cpp:351-476)
+__device__ void tz_two_point(SearchCtx& s)
+{
+  int x = s.best_x, y = s.best_y;
+  bool up = (y - 1) >= s.ty, dn = (y + 1) <= s.by, lf = (x - 1) >= s.lx, rt = (x + 1) <= s.rx;
+  switch (s.point_nr) {
+    case 1: if (lf) tz_help(s, x - 1, y, 0, 2); if (up) tz_help(s, x, y - 1, 0, 2); break;
+    case 2: if (up) { if (lf) tz_help(s, x - 1, y - 1, 0, 2); if (rt) tz_help(s, x + 1, y - 1, 0, 2); } break;
+    case 3: if (up) tz_help(s, x, y - 1, 0, 2); if (rt) tz_help(s, x + 1, y, 0, 2); break;
+    case 4: if (lf) { if (dn) tz_help(s, x - 1, y + 1, 0, 2); if (up) tz_help(s, x - 1, y - 1, 0, 2); } break;
+    case 5: if (rt) { if (up) tz_help(s, x + 1, y - 1, 0, 2); if (dn) tz_help(s, x + 1, y + 1, 0, 2); } break;
+    case 6: if (lf) tz_help(s, x - 1, y, 0, 2); if (dn) tz_help(s, x, y + 1, 0, 2); break;
+    case 7: if (dn) { if (lf) tz_help(s, x - 1, y + 1, 0, 2); if (rt) tz_help(s, x + 1, y + 1, 0, 2); } break;
+    case 8: if (rt) tz_help(s, x + 1, y, 0, 2); if (dn) tz_help(s, x, y + 1, 0, 2); break;
+    default: break;   // the reference asserts; unreachable (distance 1 always carries a point number)
+  }
+}
+
+// xTZ8PointDiamondSearch (TEncSearch.cpp:535-707)
+__device__ void tz_diamond(SearchCtx& s, int sx, int sy, int d)
+{
+  int top = sy - d, bot = sy + d, lef = sx - d, rig = sx + d;
+  s.best_round += 1;
+  if (d == 1) {
+    if (top >= s.ty) tz_help(s, sx, top, 2, d);
+    if (lef >= s.lx) tz_help(s, lef, sy, 4, d);
+    if (rig <= s.rx) tz_help(s, rig, sy, 5, d);
+    if (bot <= s.by) tz_help(s, sx, bot, 7, d);
+    return;
+  }
+  bool inside = top >= s.ty && lef >= s.lx && rig <= s.rx && bot <= s.by;
+  if (d <= 8) {
+    int h2 = d >> 1;
+    int top2 = sy - h2, bot2 = sy + h2, lef2 = sx - h2, rig2 = sx + h2;
+    if (top >= s.ty) tz_help(s, sx, top, 2, d);
+    if (inside || top2 >= s.ty) {
+      if (inside || lef2 >= s.lx) tz_help(s, lef2, top2, 1, h2);
+      if (inside || rig2 <= s.rx) tz_help(s, rig2, top2, 3, h2);
+    }
+    if (lef >= s.lx) tz_help(s, lef, sy, 4, d);
+    if (rig <= s.rx) tz_help(s, rig, sy, 5, d);
+    if (inside || bot2 <= s.by) {
+      if (inside || lef2 >= s.lx) tz_help(s, lef2, bot2, 6, h2);
+      if (inside || rig2 <= s.rx) tz_help(s, rig2, bot2, 8, h2);
+    }
+    if (bot <= s.by) tz_help(s, sx, bot, 7, d);
+    return;
+  }
+  int qd = d >> 2;
+  if (top >= s.ty) tz_help(s, sx, top, 0, d);
+  if (lef >= s.lx) tz_help(s, lef, sy, 0, d);
+  if (rig <= s.rx) tz_help(s, rig, sy, 0, d);
+  if (bot <= s.by) tz_help(s, sx, bot, 0, d);
+  for (int i = 1; i < 4; i++) {
+    int yt = top + qd * i, yb = bot - qd * i, xl = sx - qd * i, xr = sx + qd * i;
+    if (inside || yt >= s.ty) {
+      if (inside || xl >= s.lx) tz_help(s, xl, yt, 0, d);
+      if (inside || xr <= s.rx) tz_help(s, xr, yt, 0, d);
+    }
+    if (inside || yb <= s.by) {
+      if (inside || xl >= s.lx) tz_help(s, xl, yb, 0, d);
+      if (inside || xr <= s.rx) tz_help(s, xr, yb, 0, d);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_me_search(PlaneTable pt, int cur_slot, int n, const tvc_me_job* __restrict__ jobs, tvc_me_result* __restrict__ out,
+            const uint16_t* __restrict__ tables, const tvc_me_center* __restrict__ centers, int num_ctus, int ctus_x,
+            int bi)
+{
+  int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= n) return;
+  const tvc_me_job jb = jobs[j];
+  if (jb.w <= 0) {                       // census PU outside the picture (frame pre-pass)
+    if ((threadIdx.x & 31) == 0) out[j] = tvc_me_result{0, 0, 0u, 0u};
+    return;
+  }
+  SearchCtx s;
+  s.lane = threadIdx.x & 31;
+  s.so = pt.stride[0]; s.rs = pt.stride[0];
+  s.org = pt.org[cur_slot][0] + (ptrdiff_t)jb.y * s.so + jb.x;
+  s.ref = pt.org[jb.ref_slot][0] + (ptrdiff_t)jb.y * s.rs + jb.x;
+  s.w = jb.w; s.h = jb.h; s.bi = bi;
+  s.sub = (jb.fen && jb.h > 8) ? 1 : 0;                      // TEncSearch.cpp:324-330 / 4245-4251
+  s.lc = jb.lambda_cost; s.px = jb.predx; s.py = jb.predy;
+  s.lx = jb.lx; s.ty = jb.ty; s.rx = jb.rx; s.by = jb.by;
+  s.tbl = nullptr; s.tcx = 0; s.tcy = 0;
+  int ctu = (jb.y >> 6) * ctus_x + (jb.x >> 6);
+  if (tables) {
+    s.tbl = tables + ((size_t)jb.ref_index * num_ctus + ctu) * kMeCtuElems;
+    tvc_me_center cen = centers[(size_t)jb.ref_index * num_ctus + ctu];
+    s.tcx = cen.cx; s.tcy = cen.cy;
+  }
+  s.bx0 = (jb.x & 63) >> 2; s.by0 = (jb.y & 63) >> 2; s.nbx = jb.w >> 2; s.nby = jb.h >> 2;
+  s.best_sad = 0xFFFFFFFFu; s.best_x = 0; s.best_y = 0; s.best_dist = 0; s.best_round = 0; s.point_nr = 0;
+  s.n_sads = 0;
+
+  if (jb.mode == TVC_ME_FULL) {
+    // xPatternSearch (TEncSearch.cpp:4227-4283): raster, y outer, strict '<'
+    for (int y = s.ty; y <= s.by; y++)
+      for (int x = s.lx; x <= s.rx; x++) {
+        uint32_t sad = cand_sad(s, x, y) + mv_cost(s.lc, x, y, 2, s.px, s.py);
+        s.n_sads++;
+        if (sad < s.best_sad) { s.best_sad = sad; s.best_x = x; s.best_y = y; }
+      }
+  } else {
+    // xTZSearch with TZ_SEARCH_CONFIGURATION (TEncSearch.cpp:293-309, 4302-4474)
+    const int raster = 5, srange = jb.search_range;
+    tz_help(s, jb.startx, jb.starty, 0, 0);
+    tz_help(s, 0, 0, 0, 0);
+    int sx = s.best_x, sy = s.best_y;
+    for (int d = 1; d <= srange; d *= 2) {
+      tz_diamond(s, sx, sy, d);
+      if (s.best_round >= 3) break;                           // bFirstSearchStop, uiFirstSearchRounds
+    }
+    if (s.best_dist == 1) { s.best_dist = 0; tz_two_point(s); }
+    if ((int)s.best_dist > raster) {
+      s.best_dist = raster;
+      for (int y = s.ty; y <= s.by; y += raster)
+        for (int x = s.lx; x <= s.rx; x += raster) tz_help(s, x, y, 0, raster);
+    }
+    while (s.best_dist > 0) {
+      sx = s.best_x; sy = s.best_y;
+      s.best_dist = 0; s.point_nr = 0;
+      for (int d = 1; d < srange + 1; d *= 2) tz_diamond(s, sx, sy, d);
+      if (s.best_dist == 1) {
+        s.best_dist = 0;
+        if (s.point_nr != 0) tz_two_point(s);
+      }
+    }
+  }
+  if (s.lane == 0) {
+    tvc_me_result r;
+    r.mvx = s.best_x; r.mvy = s.best_y;
+    r.sad = s.best_sad - mv_cost(s.lc, s.best_x, s.best_y, 2, s.px, s.py);
+    r.n_sads = s.n_sads;
+    out[j] = r;
+  }
+}
+
+__global__ void k_me_table_lookup(const uint16_t* __restrict__ tables, const tvc_me_center* __restrict__ centers,
+                                  int num_ctus, int ctus_x, int ref_index, int pu_x, int pu_y, int pu_w, int pu_h, int fen,
+                                  int n, const int16_t* __restrict__ cand, uint32_t* __restrict__ out, int bi)
+{
+  int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= n) return;
+  int lane = threadIdx.x & 31;
+  int ctu = (pu_y >> 6) * ctus_x + (pu_x >> 6);
+  const uint16_t* tbl = tables + ((size_t)ref_index * num_ctus + ctu) * kMeCtuElems;
+  tvc_me_center cen = centers[(size_t)ref_index * num_ctus + ctu];
+  int dx = cand[2 * j] - cen.cx, dy = cand[2 * j + 1] - cen.cy;
+  int sub = (fen && pu_h > 8) ? 1 : 0;
+  uint32_t acc = 0;
+  bool inside = dx >= -kMeR && dx <= kMeR && dy >= -kMeR && dy <= kMeR;
+  if (inside)
+    acc = table_pu_sad_partial(tbl, (pu_x & 63) >> 2, (pu_y & 63) >> 2, pu_w >> 2, pu_h >> 2, sub != 0, dy, dx, lane);
+  acc = warp_sum_u32(acc);
+  if (lane == 0) out[j] = inside ? ((acc << sub) >> bi) : 0xFFFFFFFFu;
+}
+
+// ================================================================================ (3) fractional
+constexpr int kFrW = 64, kFrH = 64;
+constexpr int kFrHP = 66;                         // pitch of the horizontal-pass planes (w+1 -> even)
+constexpr int kFrHRows = kFrH + 8;
+constexpr int kFrSmem = 4 * kFrHP * kFrHRows * 2 + kFrW * kFrH * 2 + 64 * 4;
+
+// xPatternRefinement candidate orders (TEncSearch.cpp:47-71)
+__constant__ int8_t c_refine_h[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {1, -1}, {-1, 1}, {1, 1}};
+__constant__ int8_t c_refine_q[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {1, 1}};
+
+// prediction sample of candidate (fx,fy) (quarter units, -3..3) at (x,y): vertical stage over the
+// 14-bit horizontal planes, isFirst=false, isLast=true (TEncSearch.cpp:5998-6013, 6066-6174 all end in
+// filterVerLuma(..., false, true)).
+__device__ __forceinline__ int frac_pred(const int16_t* __restrict__ H, int fx, int fy, int x, int y, int bd)
+{
+  const int ix = fx < 0 ? -1 : 0, f = fx & 3;
+  const int iy = fy < 0 ? -1 : 0, g = fy & 3;
+  const int16_t* p = H + f * (kFrHP * kFrHRows) + (y + iy + 4) * kFrHP + (x + ix + 1);
+  return if_sample<8>(p, kFrHP, g, false, true, bd);
+}
+
+template <int TS>
+__device__ __forceinline__ uint32_t frac_tile_satd(const int16_t* __restrict__ H, const int16_t* __restrict__ org, int fx,
+                                                   int fy, int tx, int ty, int c, int bd)
+{
+  // TS lanes per tile; lane c owns column tx+c: vertical Hadamard in registers, horizontal by shuffles
+  int d[TS];
+#pragma unroll
+  for (int r = 0; r < TS; r++) d[r] = (int)org[(ty + r) * kFrW + tx + c] - frac_pred(H, fx, fy, tx + c, ty + r, bd);
+#pragma unroll
+  for (int len = 1; len < TS; len <<= 1)
+#pragma unroll
+    for (int i = 0; i < TS; i += 2 * len)
+#pragma unroll
+      for (int k = i; k < i + len; k++) { int a = d[k], b = d[k + len]; d[k] = a + b; d[k + len] = a - b; }
+#pragma unroll
+  for (int m = 1; m < TS; m <<= 1) {
+#pragma unroll
+    for (int r = 0; r < TS; r++) {
+      int o = __shfl_xor_sync(0xffffffffu, d[r], m);
+      d[r] = (c & m) ? (o - d[r]) : (d[r] + o);
+    }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int r = 0; r < TS; r++) s += (uint32_t)abs(d[r]);
+#pragma unroll
+  for (int m = 1; m < TS; m <<= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  return TS == 8 ? ((s + 2) >> 2) : ((s + 1) >> 1);      // xCalcHADs8x8 / 4x4 rounding
+}
+
+__global__ void __launch_bounds__(128)
+k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ jobs, tvc_frac_result* __restrict__ out, int bd)
+{
+  extern __shared__ __align__(16) uint8_t fsm[];
+  int16_t* H = reinterpret_cast<int16_t*>(fsm);
+  int16_t* org = H + 4 * kFrHP * kFrHRows;
+  uint32_t* cost = reinterpret_cast<uint32_t*>(org + kFrW * kFrH);   // 9 accumulators + results
+  __shared__ int s_half[2];
+  const tvc_frac_job jb = jobs[blockIdx.x];
+  if (jb.w <= 0) {                       // census PU outside the picture (frame pre-pass)
+    if (threadIdx.x == 0) out[blockIdx.x] = tvc_frac_result{0, 0, 0, 0, 0u, 0u};
+    return;
+  }
+  const int w = jb.w, h = jb.h, bi = bd - 8;
+  const int stride = pt.stride[0];
+  const int16_t* ref = pt.org[jb.ref_slot][0] + (ptrdiff_t)(jb.y + jb.imvy) * stride + jb.x + jb.imvx;
+  const int16_t* cur = pt.org[cur_slot][0] + (ptrdiff_t)jb.y * stride + jb.x;
+  const int tid = threadIdx.x;
+
+  // horizontal pass (isFirst, !isLast): planes f = 0..3 over columns -1..w-1 and rows -4..h+3
+  // (xExtDIFUpSamplingH/Q, TEncSearch.cpp:5994-5996, 6043-6064)
+  const int hw = w + 1, hh = h + 8;
+  for (int i = tid; i < 4 * hw * hh; i += blockDim.x) {
+    int f = i / (hw * hh), rem = i - f * (hw * hh);
+    int r = rem / hw, x = rem - r * hw;
+    const int16_t* p = ref + (ptrdiff_t)(r - 4) * stride + (x - 1);
+    H[f * (kFrHP * kFrHRows) + r * kFrHP + x] = if_sample<8>(p, 1, f, true, false, bd);
+  }
+  for (int i = tid; i < w * h; i += blockDim.x) {
+    int r = i / w, x = i - r * w;
+    org[r * kFrW + x] = cur[(ptrdiff_t)r * stride + x];
+  }
+  if (tid < 16) cost[tid] = 0;
+  __syncthreads();
+
+  const bool t8 = ((w & 7) == 0) && ((h & 7) == 0);
+  const int TS = (jb.hadamard ? (t8 ? 8 : 4) : 4);
+  const int tiles_x = w / TS, tiles = tiles_x * (h / TS);
+  const int lanes_per_tile = TS, groups = blockDim.x / lanes_per_tile;
+  const int grp = tid / lanes_per_tile, c = tid % lanes_per_tile;
+
+  int basex = 0, basey = 0;       // quarter-unit offset of the pass centre
+  int hx = 0, hy = 0;
+  uint32_t cost_half = 0, cost_q = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    const int fr = pass == 0 ? 2 : 1;
+    // evaluate 9 candidates; units (cand, tile) spread over the lane groups.  The loop bound is
+    // rounded up so every lane of a warp executes the shuffles.
+    const int units = 9 * tiles;
+    const int iters = (units + groups - 1) / groups;
+    for (int it = 0; it < iters; it++) {
+      int u = it * groups + grp;
+      bool valid = u < units;
+      int uu = valid ? u : 0;
+      int cand = uu / tiles, t = uu - cand * tiles;
+      int tyy = (t / tiles_x) * TS, txx = (t % tiles_x) * TS;
+      const int8_t* rf = pass == 0 ? c_refine_h[cand] : c_refine_q[cand];
+      int fx = basex + rf[0] * fr, fy = basey + rf[1] * fr;
+      uint32_t v;
+      if (jb.hadamard) {
+        v = (TS == 8) ? frac_tile_satd<8>(H, org, fx, fy, txx, tyy, c, bd) : frac_tile_satd<4>(H, org, fx, fy, txx, tyy, c, bd);
+      } else {
+        // SAD (xGetSAD*, iSubShift 0): 4x4 tile, lane c = column
+        uint32_t sd = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) sd += (uint32_t)abs((int)org[(tyy + r) * kFrW + txx + c] - frac_pred(H, fx, fy, txx + c, tyy + r, bd));
+        sd += __shfl_xor_sync(0xffffffffu, sd, 1);
+        sd += __shfl_xor_sync(0xffffffffu, sd, 2);
+        v = sd;
+      }
+      if (valid && c == 0) atomicAdd(&cost[cand], v);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      // xPatternRefinement (TEncSearch.cpp:730-757): dist >> bitIncrement + rate, strict '<', order as listed
+      uint32_t best = 0xFFFFFFFFu; int best_i = 0;
+      int scale = pass == 0 ? 1 : 0;
+      int ax = pass == 0 ? (jb.imvx << 1) : (((jb.imvx << 1) + hx) << 1);
+      int ay = pass == 0 ? (jb.imvy << 1) : (((jb.imvy << 1) + hy) << 1);
+      for (int i = 0; i < 9; i++) {
+        const int8_t* rf = pass == 0 ? c_refine_h[i] : c_refine_q[i];
+        uint32_t d = (cost[i] >> bi) + mv_cost(jb.lambda_cost, ax + rf[0], ay + rf[1], scale, jb.predx, jb.predy);
+        if (d < best) { best = d; best_i = i; }
+      }
+      const int8_t* rb = pass == 0 ? c_refine_h[best_i] : c_refine_q[best_i];
+      s_half[0] = rb[0]; s_half[1] = rb[1];
+      cost[9] = best;
+      for (int i = 0; i < 9; i++) cost[i] = 0;
+    }
+    __syncthreads();
+    if (pass == 0) {
+      hx = s_half[0]; hy = s_half[1]; cost_half = cost[9];
+      basex = hx * 2; basey = hy * 2;
+    } else {
+      cost_q = cost[9];
+      if (tid == 0) {
+        tvc_frac_result r;
+        r.halfx = hx; r.halfy = hy; r.qtrx = s_half[0]; r.qtry = s_half[1];
+        r.cost_half = cost_half; r.cost = cost_q;
+        out[blockIdx.x] = r;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+
+// ================================================================================ (4) frame pre-pass
+__constant__ tvc_census_pu c_census[TVC_ME_CENSUS];
+
+static void build_census(tvc_census_pu* out)
+{
+  int n = 0;
+  for (int depth = 0; depth < 4; depth++) {
+    int s = 64 >> depth;
+    for (int cy = 0; cy < 64; cy += s)
+      for (int cx = 0; cx < 64; cx += s) {
+        int q = s / 4, hs = s / 2;
+        int parts[13][4] = {{0, 0, s, s}, {0, 0, s, hs}, {0, hs, s, hs}, {0, 0, hs, s}, {hs, 0, hs, s},
+                            {0, 0, s, q}, {0, q, s, s - q}, {0, 0, s, s - q}, {0, s - q, s, q},
+                            {0, 0, q, s}, {q, 0, s - q, s}, {0, 0, s - q, s}, {s - q, 0, q, s}};
+        int np = s >= 16 ? 13 : 5;
+        for (int k = 0; k < np; k++) {
+          out[n].x = (int16_t)(cx + parts[k][0]); out[n].y = (int16_t)(cy + parts[k][1]);
+          out[n].w = (int16_t)parts[k][2]; out[n].h = (int16_t)parts[k][3];
+          out[n].cu_x = (int16_t)cx; out[n].cu_y = (int16_t)cy;
+          n++;
+        }
+      }
+  }
+}
+
+// TComDataCU::clipMv (TComDataCU.cpp:3505-3517), quarter pels
+__device__ __forceinline__ void clip_mv(int pic_w, int pic_h, int cu_x, int cu_y, int& x, int& y)
+{
+  int hmax = (pic_w + 8 - cu_x - 1) * 4, hmin = (-64 - 8 - cu_x + 1) * 4;
+  int vmax = (pic_h + 8 - cu_y - 1) * 4, vmin = (-64 - 8 - cu_y + 1) * 4;
+  x = min(hmax, max(hmin, x));
+  y = min(vmax, max(vmin, y));
+}
+
+__global__ void k_me_frame_jobs(int pic_w, int pic_h, int num_ctus, int ctus_x, int num_refs, const int* __restrict__ ref_slots,
+                                const tvc_me_center* __restrict__ pred, tvc_me_frame_cfg cfg, tvc_me_job* __restrict__ jobs)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int total = num_refs * num_ctus * TVC_ME_CENSUS;
+  if (i >= total) return;
+  int k = i % TVC_ME_CENSUS, rc = i / TVC_ME_CENSUS, ctu = rc % num_ctus, ref = rc / num_ctus;
+  const tvc_census_pu cp = c_census[k];
+  int x0 = (ctu % ctus_x) * 64, y0 = (ctu / ctus_x) * 64;
+  tvc_me_job j;
+  j.ref_index = ref; j.ref_slot = ref_slots[ref];
+  j.x = x0 + cp.x; j.y = y0 + cp.y; j.w = cp.w; j.h = cp.h;
+  if (j.x + j.w > pic_w || j.y + j.h > pic_h) j.w = 0;
+  j.mode = TVC_ME_TZ; j.fen = cfg.fen; j.search_range = cfg.search_range;
+  const tvc_me_center p = pred[rc];
+  const int cu_x = x0 + cp.cu_x, cu_y = y0 + cp.cu_y;
+  // xSetSearchRange (TEncSearch.cpp:4209-4225)
+  int px = p.cx, py = p.cy;
+  clip_mv(pic_w, pic_h, cu_x, cu_y, px, py);
+  int lx = px - (cfg.search_range << 2), ty = py - (cfg.search_range << 2);
+  int rx = px + (cfg.search_range << 2), by = py + (cfg.search_range << 2);
+  clip_mv(pic_w, pic_h, cu_x, cu_y, lx, ty);
+  clip_mv(pic_w, pic_h, cu_x, cu_y, rx, by);
+  j.lx = lx >> 2; j.ty = ty >> 2; j.rx = rx >> 2; j.by = by >> 2;
+  j.predx = p.cx; j.predy = p.cy;
+  j.startx = px >> 2; j.starty = py >> 2;          // xTZSearch :4311-4312
+  j.lambda_cost = cfg.lambda_cost;
+  jobs[i] = j;
+}
+
+__global__ void k_me_frame_frac_jobs(int n, const tvc_me_job* __restrict__ jobs, const tvc_me_result* __restrict__ res,
+                                     int hadamard, tvc_frac_job* __restrict__ fj)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const tvc_me_job j = jobs[i];
+  const tvc_me_result r = res[i];
+  tvc_frac_job f;
+  f.ref_slot = j.ref_slot; f.x = j.x; f.y = j.y; f.w = j.w; f.h = j.h;
+  f.imvx = r.mvx; f.imvy = r.mvy; f.predx = j.predx; f.predy = j.predy;
+  f.lambda_cost = j.lambda_cost; f.hadamard = hadamard;
+  fj[i] = f;
+}
+
+// ================================================================================ micro-benchmarks
+__global__ void k_ub_vabsdiff4(uint32_t* out, int iters, uint32_t a0, uint32_t b0)
+{
+  uint32_t a = a0 + threadIdx.x, b = b0 * threadIdx.x;
+  uint32_t acc[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = vsad4_acc(a, b ^ acc[(k + 1) & 7], acc[k]);
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += acc[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void k_ub_iadd3(uint32_t* out, int iters, uint32_t a0, uint32_t b0)
+{
+  uint32_t a = a0 + threadIdx.x, b = b0 * threadIdx.x;
+  uint32_t acc[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) asm volatile("add.u32 %0, %0, %1;" : "+r"(acc[k]) : "r"(a));
+#pragma unroll
+    for (int k = 0; k < 8; k++) asm volatile("add.u32 %0, %0, %1;" : "+r"(acc[k]) : "r"(b));
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += acc[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void k_ub_imad(uint32_t* out, int iters, uint32_t a0, uint32_t b0)
+{
+  uint32_t a = a0 + threadIdx.x, b = b0 * threadIdx.x + 3;
+  uint32_t acc[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(acc[k]) : "r"(a), "r"(b));
+#pragma unroll
+    for (int k = 0; k < 8; k++) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(acc[k]) : "r"(b), "r"(a));
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += acc[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void k_ub_lds128(uint32_t* out, int iters)
+{
+  __shared__ uint4 buf[1024];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) buf[i] = make_uint4(i, i + 1, i + 2, i + 3);
+  __syncthreads();
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  int idx = threadIdx.x;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uint4 v = buf[(idx + k * 32) & 1023];
+      acc.x += v.x; acc.y ^= v.y; acc.z += v.z; acc.w ^= v.w;
+    }
+    idx = (idx + acc.x) & 1023;
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc.x + acc.y + acc.z + acc.w;
+}
+
+}  // namespace tvc
+
+using namespace tvc;
+
+extern "C" {
+
+size_t tvc_me_table_bytes(tvc_ctx* c, int num_refs)
+{
+  if (!c || num_refs <= 0) return 0;
+  return (size_t)num_refs * c->num_ctus_x * c->num_ctus_y * kMeCtuElems * sizeof(uint16_t);
+}
+
+int tvc_me_prepass(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slots, const tvc_me_center* centers)
+{
+  if (!c || !valid_slot(c, cur_slot) || num_refs <= 0 || num_refs > 8 || !ref_slots)
+    return set_err(c, TVC_ERR_ARG, "tvc_me_prepass: bad argument (1..8 references)");
+  if (c->cfg.bit_depth != 8) return set_err(c, TVC_ERR_ARG, "tvc_me_prepass: the SAD-table path is the 8-bit u8 SIMD path");
+  for (int r = 0; r < num_refs; r++)
+    if (!valid_slot(c, ref_slots[r]) || !c->pics[ref_slots[r]].has_tmap) return set_err(c, TVC_ERR_ARG, "tvc_me_prepass: bad reference slot or no tensor map");
+  if (!c->pics[cur_slot].has_tmap) return set_err(c, TVC_ERR_STATE, "tvc_me_prepass: tensor maps unavailable (cuTensorMapEncodeTiled)");
+  const int nctu = c->num_ctus_x * c->num_ctus_y;
+  size_t need = tvc_me_table_bytes(c, num_refs);
+  if (need > c->me_table_bytes) {
+    if (c->me_tables) cudaFree(c->me_tables);
+    c->me_tables = nullptr; c->me_table_bytes = 0;
+    if (cudaMalloc(&c->me_tables, need) != cudaSuccess) { cudaGetLastError(); return set_err(c, TVC_ERR_NOMEM, "tvc_me_prepass: cannot allocate %zu bytes of SAD tables", need); }
+    c->me_table_bytes = need;
+  }
+  if (!c->me_centers) TVC_CUDA(c, cudaMalloc(&c->me_centers, sizeof(tvc_me_center) * 8 * nctu));
+  // clamp the centres so that the 192x192 window stays inside the padded plane
+  const Pic& p = c->pics[cur_slot];
+  int r;
+  if ((r = stage_acquire(c, c->me_stage, c->me_ev, sizeof(tvc_me_center) * (size_t)num_refs * nctu))) return r;
+  tvc_me_center* hc = (tvc_me_center*)c->me_stage.host;
+  for (int rf = 0; rf < num_refs; rf++)
+    for (int k = 0; k < nctu; k++) {
+      int x0 = (k % c->num_ctus_x) * 64, y0 = (k / c->num_ctus_x) * 64;
+      tvc_me_center ce = centers ? centers[(size_t)rf * nctu + k] : tvc_me_center{0, 0};
+      int lo_x = -p.mx[0] - x0 + kMeR, hi_x = p.w[0] + p.mx[0] - x0 - 64 - kMeR;
+      int lo_y = -p.my[0] - y0 + kMeR, hi_y = p.h[0] + p.my[0] - y0 - 64 - kMeR;
+      if (hi_x < lo_x) hi_x = lo_x;
+      if (hi_y < lo_y) hi_y = lo_y;
+      ce.cx = ce.cx < lo_x ? lo_x : (ce.cx > hi_x ? hi_x : ce.cx);
+      ce.cy = ce.cy < lo_y ? lo_y : (ce.cy > hi_y ? hi_y : ce.cy);
+      hc[(size_t)rf * nctu + k] = ce;
+    }
+  TVC_CUDA(c, cudaMemcpyAsync(c->me_centers, hc, sizeof(tvc_me_center) * (size_t)num_refs * nctu, cudaMemcpyHostToDevice, c->stream));
+  TVC_CUDA(c, cudaEventRecord(c->me_ev, c->stream));
+  MeMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  maps.cur = c->pics[cur_slot].tmap_cur;
+  for (int rf = 0; rf < num_refs; rf++) maps.ref[rf] = c->pics[ref_slots[rf]].tmap_ref;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables));
+    attr_set = true;
+  }
+  dim3 grd(nctu, num_refs);
+  k_me_sad_tables<<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables);
+  TVC_LAUNCH_CHECK(c);
+  c->me_num_refs = num_refs;
+  c->me_cur_slot = cur_slot;
+  for (int rf = 0; rf < num_refs; rf++) c->me_ref_slots[rf] = ref_slots[rf];
+  return TVC_OK;
+}
+
+int tvc_me_tables_dev(tvc_ctx* c, void** tables, tvc_me_center** centers_dev)
+{
+  if (!c || !c->me_tables || c->me_num_refs == 0) return set_err(c, TVC_ERR_STATE, "tvc_me_tables_dev: no pre-pass has run");
+  if (tables) *tables = c->me_tables;
+  if (centers_dev) *centers_dev = c->me_centers;
+  return TVC_OK;
+}
+
+int tvc_me_table_lookup(tvc_ctx* c, int ref_index, int pu_x, int pu_y, int pu_w, int pu_h, int fen, int n,
+                        const int16_t* cand_xy, uint32_t* out)
+{
+  if (!c || !c->me_tables || c->me_num_refs == 0) return set_err(c, TVC_ERR_STATE, "tvc_me_table_lookup: no pre-pass has run");
+  if (ref_index < 0 || ref_index >= c->me_num_refs || n < 0 || (n && (!cand_xy || !out)) || (pu_w & 3) || (pu_h & 3) ||
+      pu_w <= 0 || pu_h <= 0 || pu_x < 0 || pu_y < 0 || (pu_x & 3) || (pu_y & 3) || (pu_x & 63) + pu_w > 64 || (pu_y & 63) + pu_h > 64 ||
+      pu_x >= c->num_ctus_x * 64 || pu_y >= c->num_ctus_y * 64)
+    return set_err(c, TVC_ERR_ARG, "tvc_me_table_lookup: bad argument");
+  if (n == 0) return TVC_OK;
+  int r;
+  if ((r = ensure_scratch(c, c->in, (size_t)n * 4))) return r;
+  if ((r = ensure_scratch(c, c->out, (size_t)n * 4))) return r;
+  memcpy(c->in.host, cand_xy, (size_t)n * 4);
+  TVC_CUDA(c, cudaMemcpyAsync(c->in.dev, c->in.host, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  k_me_table_lookup<<<(n + 3) / 4, 128, 0, c->stream>>>(c->me_tables, c->me_centers, c->num_ctus_x * c->num_ctus_y, c->num_ctus_x,
+                                                         ref_index, pu_x, pu_y, pu_w, pu_h, fen, n, (const int16_t*)c->in.dev,
+                                                         (uint32_t*)c->out.dev, c->bi);
+  TVC_LAUNCH_CHECK(c);
+  TVC_CUDA(c, cudaMemcpyAsync(c->out.host, c->out.dev, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  TVC_CUDA(c, cudaStreamSynchronize(c->stream));
+  memcpy(out, c->out.host, (size_t)n * 4);
+  return TVC_OK;
+}
+
+int tvc_me_search_batch_dev(tvc_ctx* c, int cur_slot, int use_tables, int n, const tvc_me_job* jobs_dev, tvc_me_result* out_dev)
+{
+  if (!c || !valid_slot(c, cur_slot) || n < 0 || (n && (!jobs_dev || !out_dev))) return set_err(c, TVC_ERR_ARG, "tvc_me_search_batch_dev: bad argument");
+  if (use_tables && (!c->me_tables || c->me_num_refs == 0 || c->me_cur_slot != cur_slot))
+    return set_err(c, TVC_ERR_STATE, "tvc_me_search_batch: tables requested but no pre-pass for this picture");
+  if (n == 0) return TVC_OK;
+  k_me_search<<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, use_tables ? c->me_tables : nullptr,
+                                                  c->me_centers, c->num_ctus_x * c->num_ctus_y, c->num_ctus_x, c->bi);
+  TVC_LAUNCH_CHECK(c);
+  return TVC_OK;
+}
+
+int tvc_me_search_batch(tvc_ctx* c, int cur_slot, int use_tables, int n, const tvc_me_job* jobs, tvc_me_result* out)
+{
+  if (!c || !valid_slot(c, cur_slot) || n < 0 || (n && (!jobs || !out))) return set_err(c, TVC_ERR_ARG, "tvc_me_search_batch: bad argument");
+  if (n == 0) return TVC_OK;
+  const Pic& p = c->pics[cur_slot];
+  for (int i = 0; i < n; i++) {
+    const tvc_me_job& j = jobs[i];
+    bool ok = valid_slot(c, j.ref_slot) && j.w > 0 && j.h > 0 && j.w <= 64 && j.h <= 64 && !(j.w & 3) && !(j.h & 3) && !(j.x & 3) &&
+              !(j.y & 3) && j.x >= 0 && j.y >= 0 && (j.x & 63) + j.w <= 64 && (j.y & 63) + j.h <= 64 &&
+              j.x < c->num_ctus_x * 64 && j.y < c->num_ctus_y * 64 && j.lx <= j.rx && j.ty <= j.by &&
+              (j.mode == TVC_ME_FULL || j.mode == TVC_ME_TZ) && j.search_range >= 1 && j.search_range <= 256 &&
+              (!use_tables || (j.ref_index >= 0 && j.ref_index < c->me_num_refs && c->me_ref_slots[j.ref_index] == j.ref_slot));
+    // every candidate the search may touch must read inside the padded plane
+    if (ok) {
+      int minx = j.lx < 0 ? j.lx : 0, maxx = j.rx > 0 ? j.rx : 0, miny = j.ty < 0 ? j.ty : 0, maxy = j.by > 0 ? j.by : 0;
+      if (j.mode == TVC_ME_TZ) { minx = minx < j.startx ? minx : j.startx; maxx = maxx > j.startx ? maxx : j.startx;
+                                 miny = miny < j.starty ? miny : j.starty; maxy = maxy > j.starty ? maxy : j.starty; }
+      ok = j.x + minx >= -p.mx[0] && j.y + miny >= -p.my[0] && j.x + j.w + maxx <= p.w[0] + p.mx[0] && j.y + j.h + maxy <= p.h[0] + p.my[0];
+    }
+    if (!ok) return set_err(c, TVC_ERR_ARG, "tvc_me_search_batch: job %d invalid", i);
+  }
+  int r;
+  if ((r = ensure_scratch(c, c->in, (size_t)n * sizeof(tvc_me_job)))) return r;
+  if ((r = ensure_scratch(c, c->out, (size_t)n * sizeof(tvc_me_result)))) return r;
+  memcpy(c->in.host, jobs, (size_t)n * sizeof(tvc_me_job));
+  TVC_CUDA(c, cudaMemcpyAsync(c->in.dev, c->in.host, (size_t)n * sizeof(tvc_me_job), cudaMemcpyHostToDevice, c->stream));
+  if ((r = tvc_me_search_batch_dev(c, cur_slot, use_tables, n, (const tvc_me_job*)c->in.dev, (tvc_me_result*)c->out.dev))) return r;
+  TVC_CUDA(c, cudaMemcpyAsync(c->out.host, c->out.dev, (size_t)n * sizeof(tvc_me_result), cudaMemcpyDeviceToHost, c->stream));
+  TVC_CUDA(c, cudaStreamSynchronize(c->stream));
+  memcpy(out, c->out.host, (size_t)n * sizeof(tvc_me_result));
+  return TVC_OK;
+}
+
+int tvc_me_frac_batch_dev(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job* jobs_dev, tvc_frac_result* out_dev)
+{
+  if (!c || !valid_slot(c, cur_slot) || n < 0 || (n && (!jobs_dev || !out_dev))) return set_err(c, TVC_ERR_ARG, "tvc_me_frac_batch_dev: bad argument");
+  if (n == 0) return TVC_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TVC_CUDA(c, cudaFuncSetAttribute(k_me_frac, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrSmem));
+    attr_set = true;
+  }
+  k_me_frac<<<n, 128, kFrSmem, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, c->cfg.bit_depth);
+  TVC_LAUNCH_CHECK(c);
+  return TVC_OK;
+}
+
+int tvc_me_frac_batch(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job* jobs, tvc_frac_result* out)
+{
+  if (!c || !valid_slot(c, cur_slot) || n < 0 || (n && (!jobs || !out))) return set_err(c, TVC_ERR_ARG, "tvc_me_frac_batch: bad argument");
+  if (n == 0) return TVC_OK;
+  const Pic& p = c->pics[cur_slot];
+  for (int i = 0; i < n; i++) {
+    const tvc_frac_job& j = jobs[i];
+    bool ok = valid_slot(c, j.ref_slot) && j.w > 0 && j.h > 0 && j.w <= 64 && j.h <= 64 && !(j.w & 3) && !(j.h & 3) && j.x >= 0 && j.y >= 0 &&
+              j.x + j.w <= p.w[0] + p.mx[0] && j.y + j.h <= p.h[0] + p.my[0];
+    if (ok) {
+      int ix = j.x + j.imvx, iy = j.y + j.imvy;   // 8-tap reach: -4 .. +4 around the block (+-1 for the half-pel shift)
+      ok = ix - 5 >= -p.mx[0] && iy - 5 >= -p.my[0] && ix + j.w + 5 <= p.w[0] + p.mx[0] && iy + j.h + 5 <= p.h[0] + p.my[0];
+    }
+    if (!ok) return set_err(c, TVC_ERR_ARG, "tvc_me_frac_batch: job %d invalid or reaches outside the padded picture", i);
+  }
+  int r;
+  if ((r = ensure_scratch(c, c->in, (size_t)n * sizeof(tvc_frac_job)))) return r;
+  if ((r = ensure_scratch(c, c->out, (size_t)n * sizeof(tvc_frac_result)))) return r;
+  memcpy(c->in.host, jobs, (size_t)n * sizeof(tvc_frac_job));
+  TVC_CUDA(c, cudaMemcpyAsync(c->in.dev, c->in.host, (size_t)n * sizeof(tvc_frac_job), cudaMemcpyHostToDevice, c->stream));
+  if ((r = tvc_me_frac_batch_dev(c, cur_slot, n, (const tvc_frac_job*)c->in.dev, (tvc_frac_result*)c->out.dev))) return r;
+  TVC_CUDA(c, cudaMemcpyAsync(c->out.host, c->out.dev, (size_t)n * sizeof(tvc_frac_result), cudaMemcpyDeviceToHost, c->stream));
+  TVC_CUDA(c, cudaStreamSynchronize(c->stream));
+  memcpy(out, c->out.host, (size_t)n * sizeof(tvc_frac_result));
+  return TVC_OK;
+}
+
+
+int tvc_me_census(tvc_census_pu* out)
+{
+  if (!out) return TVC_ERR_ARG;
+  build_census(out);
+  return TVC_OK;
+}
+
+int tvc_me_frame_dev(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slots, const tvc_me_center* pred_qpel,
+                     const tvc_me_frame_cfg* cfg, tvc_me_result** int_dev, tvc_frac_result** frac_dev)
+{
+  if (!c || !valid_slot(c, cur_slot) || num_refs <= 0 || num_refs > 8 || !ref_slots || !cfg || cfg->search_range < 1 ||
+      cfg->search_range > 256)
+    return set_err(c, TVC_ERR_ARG, "tvc_me_frame: bad argument");
+  for (int r = 0; r < num_refs; r++)
+    if (!valid_slot(c, ref_slots[r])) return set_err(c, TVC_ERR_ARG, "tvc_me_frame: bad reference slot");
+  const int nctu = c->num_ctus_x * c->num_ctus_y;
+  const size_t n = (size_t)num_refs * nctu * TVC_ME_CENSUS;
+  static int census_dev = -1;
+  if (census_dev != c->cfg.device) {
+    tvc_census_pu h[TVC_ME_CENSUS];
+    build_census(h);
+    TVC_CUDA(c, cudaMemcpyToSymbol(c_census, h, sizeof(h)));
+    census_dev = c->cfg.device;
+  }
+  if (n > c->fr_cap) {
+    if (c->fr_jobs) cudaFree(c->fr_jobs);
+    if (c->fr_int) cudaFree(c->fr_int);
+    if (c->fr_fjobs) cudaFree(c->fr_fjobs);
+    if (c->fr_frac) cudaFree(c->fr_frac);
+    c->fr_jobs = nullptr; c->fr_int = nullptr; c->fr_fjobs = nullptr; c->fr_frac = nullptr; c->fr_cap = 0;
+    TVC_CUDA(c, cudaMalloc(&c->fr_jobs, n * sizeof(tvc_me_job)));
+    TVC_CUDA(c, cudaMalloc(&c->fr_int, n * sizeof(tvc_me_result)));
+    TVC_CUDA(c, cudaMalloc(&c->fr_fjobs, n * sizeof(tvc_frac_job)));
+    TVC_CUDA(c, cudaMalloc(&c->fr_frac, n * sizeof(tvc_frac_result)));
+    c->fr_cap = n;
+  }
+  // predictors (quarter pels) and table centres (CTU-level clipMv, integer pels) on the host: tiny
+  const size_t np = (size_t)num_refs * nctu;
+  int r;
+  if ((r = stage_acquire(c, c->fr_stage, c->fr_ev, np * sizeof(tvc_me_center) + 8 * sizeof(int)))) return r;
+  std::vector<tvc_me_center> centers(np);
+  tvc_me_center* hp = (tvc_me_center*)c->fr_stage.host;
+  int* hslots = (int*)((char*)c->fr_stage.host + np * sizeof(tvc_me_center));
+  const int pw = c->cfg.width, ph = c->cfg.height;
+  for (size_t i = 0; i < np; i++) {
+    tvc_me_center p = pred_qpel ? pred_qpel[i] : tvc_me_center{0, 0};
+    hp[i] = p;
+    int ctu = (int)(i % nctu), x0 = (ctu % c->num_ctus_x) * 64, y0 = (ctu / c->num_ctus_x) * 64;
+    int hmax = (pw + 8 - x0 - 1) * 4, hmin = (-64 - 8 - x0 + 1) * 4, vmax = (ph + 8 - y0 - 1) * 4, vmin = (-64 - 8 - y0 + 1) * 4;
+    int x = p.cx < hmin ? hmin : (p.cx > hmax ? hmax : p.cx), y = p.cy < vmin ? vmin : (p.cy > vmax ? vmax : p.cy);
+    centers[i].cx = x >> 2; centers[i].cy = y >> 2;
+  }
+  for (int k = 0; k < num_refs; k++) hslots[k] = ref_slots[k];
+  if (cfg->use_tables && (r = tvc_me_prepass(c, cur_slot, num_refs, ref_slots, centers.data()))) return r;
+  TVC_CUDA(c, cudaMemcpyAsync(c->fr_stage.dev, c->fr_stage.host, np * sizeof(tvc_me_center) + num_refs * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  TVC_CUDA(c, cudaEventRecord(c->fr_ev, c->stream));
+  const tvc_me_center* dpred = (const tvc_me_center*)c->fr_stage.dev;
+  const int* dslots = (const int*)((char*)c->fr_stage.dev + np * sizeof(tvc_me_center));
+  k_me_frame_jobs<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(pw, ph, nctu, c->num_ctus_x, num_refs, dslots, dpred, *cfg, c->fr_jobs);
+  TVC_LAUNCH_CHECK(c);
+  if ((r = tvc_me_search_batch_dev(c, cur_slot, cfg->use_tables, (int)n, c->fr_jobs, c->fr_int))) return r;
+  if (cfg->do_frac) {
+    k_me_frame_frac_jobs<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((int)n, c->fr_jobs, c->fr_int, cfg->hadamard, c->fr_fjobs);
+    TVC_LAUNCH_CHECK(c);
+    if ((r = tvc_me_frac_batch_dev(c, cur_slot, (int)n, c->fr_fjobs, c->fr_frac))) return r;
+  }
+  if (int_dev) *int_dev = c->fr_int;
+  if (frac_dev) *frac_dev = cfg->do_frac ? c->fr_frac : nullptr;
+  return TVC_OK;
+}
+
+int tvc_me_frame(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slots, const tvc_me_center* pred_qpel,
+                 const tvc_me_frame_cfg* cfg, tvc_me_result* int_out, tvc_frac_result* frac_out)
+{
+  tvc_me_result* di = nullptr;
+  tvc_frac_result* df = nullptr;
+  int r = tvc_me_frame_dev(c, cur_slot, num_refs, ref_slots, pred_qpel, cfg, &di, &df);
+  if (r) return r;
+  const size_t n = (size_t)num_refs * c->num_ctus_x * c->num_ctus_y * TVC_ME_CENSUS;
+  if (int_out) TVC_CUDA(c, cudaMemcpyAsync(int_out, di, n * sizeof(tvc_me_result), cudaMemcpyDeviceToHost, c->stream));
+  if (frac_out && df) TVC_CUDA(c, cudaMemcpyAsync(frac_out, df, n * sizeof(tvc_frac_result), cudaMemcpyDeviceToHost, c->stream));
+  TVC_CUDA(c, cudaStreamSynchronize(c->stream));
+  return TVC_OK;
+}
+
+int tvc_ubench(tvc_ctx* c, int which, double* ginstr_per_s)
+{
+  if (!c || !ginstr_per_s || which < 0 || which > 3) return set_err(c, TVC_ERR_ARG, "tvc_ubench: bad argument");
+  const int blocks = kNumSM * 8, threads = 256, iters = 4096;
+  uint32_t* d = nullptr;
+  TVC_CUDA(c, cudaMalloc(&d, (size_t)blocks * threads * 4));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double per_thread = 0;
+  for (int rep = 0; rep < 3; rep++) {
+    if (rep == 2) cudaEventRecord(e0, c->stream);
+    switch (which) {
+      case TVC_UB_VABSDIFF4: k_ub_vabsdiff4<<<blocks, threads, 0, c->stream>>>(d, iters, 0x01020304u, 0x11213141u); per_thread = 8.0 * iters; break;
+      case TVC_UB_IADD3: k_ub_iadd3<<<blocks, threads, 0, c->stream>>>(d, iters, 0x01020304u, 0x11213141u); per_thread = 16.0 * iters; break;
+      case TVC_UB_IMAD: k_ub_imad<<<blocks, threads, 0, c->stream>>>(d, iters, 0x01020304u, 0x11213141u); per_thread = 16.0 * iters; break;
+      default: k_ub_lds128<<<blocks, threads, 0, c->stream>>>(d, iters); per_thread = 8.0 * iters; break;
+    }
+    c->launches++;
+  }
+  cudaEventRecord(e1, c->stream);
+  cudaError_t e = cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  if (e != cudaSuccess) return check_cuda(c, e, "tvc_ubench");
+  *ginstr_per_s = per_thread * blocks * threads / (ms * 1e-3) / 1e9;
+  return TVC_OK;
+}
+
+}  // extern "C"

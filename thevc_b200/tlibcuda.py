@@ -1,0 +1,272 @@
+"""Object wrapper over the C ABI: the calls a Python user of TLibCuda makes.
+
+All compute goes through libthevc_cuda.so; a missing library or a missing GPU raises ``TvcError``
+(no fallback).  Host pictures mirror the reference's TComPicYuv layout (planar int16, margin
+max_cu+16 around luma; TComPicYuv.cpp:71-127).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import (CensusPU, Config, DistJob, FracJob, FracResult, MeCenter, MeFrameCfg, MeJob, MeResult, PU, QuantCfg, TU, ptr)
+
+
+class TvcError(RuntimeError):
+    pass
+
+
+class HostPic:
+    """Host-side TComPicYuv: three padded int16 planes.  ``y[r, c]`` views exclude the margin."""
+
+    def __init__(self, width: int, height: int, max_cu: int = 64):
+        self.w, self.h = width, height
+        self.mx = self.my = max_cu + 16
+        self.cmx = self.cmy = self.mx >> 1
+        self.stride = width + 2 * self.mx
+        self.cstride = (width >> 1) + 2 * self.cmx
+        self.buf_y = np.zeros((height + 2 * self.my, self.stride), np.int16)
+        self.buf_u = np.zeros(((height >> 1) + 2 * self.cmy, self.cstride), np.int16)
+        self.buf_v = np.zeros_like(self.buf_u)
+
+    @property
+    def y(self):
+        return self.buf_y[self.my:self.my + self.h, self.mx:self.mx + self.w]
+
+    @property
+    def u(self):
+        return self.buf_u[self.cmy:self.cmy + (self.h >> 1), self.cmx:self.cmx + (self.w >> 1)]
+
+    @property
+    def v(self):
+        return self.buf_v[self.cmy:self.cmy + (self.h >> 1), self.cmx:self.cmx + (self.w >> 1)]
+
+    def origin(self, plane: int) -> int:
+        """element offset of pel (0,0) inside the plane buffer"""
+        return (self.my * self.stride + self.mx) if plane == 0 else (self.cmy * self.cstride + self.cmx)
+
+    def plane(self, p: int) -> np.ndarray:
+        return (self.buf_y, self.buf_u, self.buf_v)[p]
+
+    def extend_border(self) -> None:
+        """TComPicYuv::extendPicBorder (edge replication into the margin), host-side."""
+        for buf, w, h, mx, my in ((self.buf_y, self.w, self.h, self.mx, self.my),
+                                  (self.buf_u, self.w >> 1, self.h >> 1, self.cmx, self.cmy),
+                                  (self.buf_v, self.w >> 1, self.h >> 1, self.cmx, self.cmy)):
+            core = buf[my:my + h, mx:mx + w]
+            buf[my:my + h, :mx] = core[:, :1]
+            buf[my:my + h, mx + w:] = core[:, -1:]
+            buf[:my, :] = buf[my:my + 1, :]
+            buf[my + h:, :] = buf[my + h - 1:my + h, :]
+
+
+def _arr(struct_t, items: Sequence):
+    a = (struct_t * len(items))()
+    for i, it in enumerate(items):
+        a[i] = it
+    return a
+
+
+class TLibCuda:
+    """One context = one encoder/decoder instance on one GPU (the reference is one instance per
+    process; multi-GPU = one process per GPU)."""
+
+    def __init__(self, width: int, height: int, bit_depth: int = 8, num_slots: int = 8, device: int = 0,
+                 max_cu: int = 64, stream: Optional[int] = None):
+        self.L = capi.load()
+        self.cfg = Config(width, height, bit_depth, max_cu, num_slots, device)
+        h = C.c_void_p()
+        rc = self.L.tvc_ctx_create(C.byref(self.cfg), C.byref(h))
+        if rc != 0 or not h.value:
+            raise TvcError("tvc_ctx_create failed (rc=%d): no CUDA device / out of memory -- there is no CPU fallback" % rc)
+        self.h = h
+        self.width, self.height, self.bit_depth = width, height, bit_depth
+        self.ctus_x = (width + max_cu - 1) // max_cu
+        self.ctus_y = (height + max_cu - 1) // max_cu
+        if stream is not None:
+            self._ck(self.L.tvc_ctx_set_stream(self.h, C.c_void_p(stream)))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.tvc_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise TvcError("libthevc_cuda error %d: %s" % (rc, self.L.tvc_last_error(self.h).decode()))
+
+    # ------------------------------------------------------------------ pictures
+    def upload(self, slot: int, pic: HostPic, with_margin: bool = True):
+        self._ck(self.L.tvc_pic_upload(self.h, slot, ptr(pic.buf_y, pic.origin(0)), pic.stride,
+                                       ptr(pic.buf_u, pic.origin(1)), ptr(pic.buf_v, pic.origin(1)), pic.cstride,
+                                       1 if with_margin else 0))
+
+    def download(self, slot: int, with_margin: bool = True) -> HostPic:
+        pic = HostPic(self.width, self.height, self.cfg.max_cu)
+        self._ck(self.L.tvc_pic_download(self.h, slot, ptr(pic.buf_y, pic.origin(0)), pic.stride,
+                                         ptr(pic.buf_u, pic.origin(1)), ptr(pic.buf_v, pic.origin(1)), pic.cstride,
+                                         1 if with_margin else 0))
+        return pic
+
+    def extend_border(self, slot: int):
+        self._ck(self.L.tvc_pic_extend_border(self.h, slot))
+
+    def sync(self):
+        self._ck(self.L.tvc_sync(self.h))
+
+    def launch_count(self) -> int:
+        return int(self.L.tvc_launch_count(self.h))
+
+    def subtract(self, dst, a, b, plane, x, y, w, h):
+        self._ck(self.L.tvc_pic_subtract(self.h, dst, a, b, plane, x, y, w, h))
+
+    def add_clip(self, dst, a, b, plane, x, y, w, h):
+        self._ck(self.L.tvc_pic_add_clip(self.h, dst, a, b, plane, x, y, w, h))
+
+    def remove_high_freq(self, dst, a, plane, x, y, w, h):
+        self._ck(self.L.tvc_pic_remove_high_freq(self.h, dst, a, plane, x, y, w, h))
+
+    # ------------------------------------------------------------------ distortion
+    def dist_block(self, kind: int, org: np.ndarray, org_off: int, so: int, cur: np.ndarray, cur_off: int, sc: int,
+                   w: int, h: int, sub_shift: int = 0) -> int:
+        out = C.c_uint32()
+        self._ck(self.L.tvc_dist_block(self.h, kind, ptr(org, org_off), so, ptr(cur, cur_off), sc, w, h, sub_shift, C.byref(out)))
+        return out.value
+
+    def dist_batch(self, jobs: Sequence[DistJob]) -> np.ndarray:
+        n = len(jobs)
+        out = np.zeros(n, np.uint32)
+        if n:
+            arr = _arr(DistJob, jobs)
+            self._ck(self.L.tvc_dist_batch(self.h, n, C.cast(arr, C.c_void_p), ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ interpolation drop-ins
+    def filter_hor_luma(self, src, src_off, ss, dst, dst_off, ds, w, h, frac, is_last):
+        self._ck(self.L.tvc_filter_hor_luma(self.h, ptr(src, src_off), ss, ptr(dst, dst_off), ds, w, h, frac, int(is_last)))
+
+    def filter_ver_luma(self, src, src_off, ss, dst, dst_off, ds, w, h, frac, is_first, is_last):
+        self._ck(self.L.tvc_filter_ver_luma(self.h, ptr(src, src_off), ss, ptr(dst, dst_off), ds, w, h, frac, int(is_first), int(is_last)))
+
+    def filter_hor_chroma(self, src, src_off, ss, dst, dst_off, ds, w, h, frac, is_last):
+        self._ck(self.L.tvc_filter_hor_chroma(self.h, ptr(src, src_off), ss, ptr(dst, dst_off), ds, w, h, frac, int(is_last)))
+
+    def filter_ver_chroma(self, src, src_off, ss, dst, dst_off, ds, w, h, frac, is_first, is_last):
+        self._ck(self.L.tvc_filter_ver_chroma(self.h, ptr(src, src_off), ss, ptr(dst, dst_off), ds, w, h, frac, int(is_first), int(is_last)))
+
+    # ------------------------------------------------------------------ MC
+    def mc_batch(self, dst_slot: int, pus: Sequence[PU]):
+        if len(pus):
+            arr = _arr(PU, pus)
+            self._ck(self.L.tvc_mc_batch(self.h, dst_slot, len(pus), C.cast(arr, C.c_void_p)))
+
+    # ------------------------------------------------------------------ ME
+    def me_prepass(self, cur_slot: int, ref_slots: Sequence[int], centers: Optional[np.ndarray] = None):
+        """centers: int32 array [num_refs, num_ctus, 2] (cx, cy) or None"""
+        refs = (C.c_int * len(ref_slots))(*ref_slots)
+        cp = None
+        if centers is not None:
+            centers = np.ascontiguousarray(centers, np.int32)
+            assert centers.shape == (len(ref_slots), self.ctus_x * self.ctus_y, 2)
+            cp = ptr(centers)
+        self._ck(self.L.tvc_me_prepass(self.h, cur_slot, len(ref_slots), C.cast(refs, C.c_void_p), cp))
+
+    def me_table_bytes(self, num_refs: int) -> int:
+        return int(self.L.tvc_me_table_bytes(self.h, num_refs))
+
+    def me_table_lookup(self, ref_index, pu_x, pu_y, pu_w, pu_h, fen, cand_xy: np.ndarray) -> np.ndarray:
+        cand = np.ascontiguousarray(cand_xy, np.int16).reshape(-1, 2)
+        out = np.zeros(len(cand), np.uint32)
+        self._ck(self.L.tvc_me_table_lookup(self.h, ref_index, pu_x, pu_y, pu_w, pu_h, int(fen), len(cand), ptr(cand), ptr(out)))
+        return out
+
+    def me_search_batch(self, cur_slot: int, jobs: Sequence[MeJob], use_tables: bool):
+        n = len(jobs)
+        res = (MeResult * n)()
+        if n:
+            arr = _arr(MeJob, jobs)
+            self._ck(self.L.tvc_me_search_batch(self.h, cur_slot, int(use_tables), n, C.cast(arr, C.c_void_p), C.cast(res, C.c_void_p)))
+        return list(res)
+
+    def me_frac_batch(self, cur_slot: int, jobs: Sequence[FracJob]):
+        n = len(jobs)
+        res = (FracResult * n)()
+        if n:
+            arr = _arr(FracJob, jobs)
+            self._ck(self.L.tvc_me_frac_batch(self.h, cur_slot, n, C.cast(arr, C.c_void_p), C.cast(res, C.c_void_p)))
+        return list(res)
+
+    def me_census(self) -> np.ndarray:
+        """the 593 PU rectangles of a CTU in result order: int16 [593, 6] = x, y, w, h, cu_x, cu_y"""
+        out = np.zeros((capi.ME_CENSUS, 6), np.int16)
+        self._ck(self.L.tvc_me_census(ptr(out)))
+        return out
+
+    def me_frame(self, cur_slot: int, ref_slots: Sequence[int], pred_qpel: Optional[np.ndarray], lambda_cost: int,
+                 search_range: int = 64, fen: bool = True, hadamard: bool = True, use_tables: bool = True,
+                 do_frac: bool = True):
+        """frame pre-pass; returns (int_results, frac_results) as structured arrays [num_refs, num_ctus, 593]"""
+        nr, nctu = len(ref_slots), self.ctus_x * self.ctus_y
+        refs = (C.c_int * nr)(*ref_slots)
+        pp = None
+        if pred_qpel is not None:
+            pred_qpel = np.ascontiguousarray(pred_qpel, np.int32)
+            assert pred_qpel.shape == (nr, nctu, 2)
+            pp = ptr(pred_qpel)
+        cfg = MeFrameCfg(search_range, int(fen), int(hadamard), int(use_tables), int(do_frac), lambda_cost)
+        ires = np.zeros((nr, nctu, capi.ME_CENSUS), capi.ME_RESULT_DTYPE)
+        fres = np.zeros((nr, nctu, capi.ME_CENSUS), capi.FRAC_RESULT_DTYPE)
+        self._ck(self.L.tvc_me_frame(self.h, cur_slot, nr, C.cast(refs, C.c_void_p), pp, C.byref(cfg), ptr(ires),
+                                     ptr(fres) if do_frac else None))
+        return ires, fres
+
+    # ------------------------------------------------------------------ TQ
+    def fwd_transform_batch(self, resi_slot: int, tus: Sequence[TU], coef_elems: int) -> np.ndarray:
+        coef = np.zeros(coef_elems, np.int32)
+        arr = _arr(TU, tus)
+        self._ck(self.L.tvc_fwd_transform_batch(self.h, resi_slot, len(tus), C.cast(arr, C.c_void_p), ptr(coef), coef_elems))
+        return coef
+
+    def fwd_tq_batch(self, resi_slot: int, tus: Sequence[TU], qc: QuantCfg, coef_elems: int, want_arl: bool = False):
+        lev = np.zeros(coef_elems, np.int32)
+        arl = np.zeros(coef_elems, np.int32) if want_arl else None
+        abs_sum = np.zeros(len(tus), np.uint32)
+        arr = _arr(TU, tus)
+        self._ck(self.L.tvc_fwd_tq_batch(self.h, resi_slot, len(tus), C.cast(arr, C.c_void_p), C.byref(qc), ptr(lev),
+                                         ptr(arl) if want_arl else None, coef_elems, ptr(abs_sum)))
+        return lev, arl, abs_sum
+
+    def inv_tq_batch(self, resi_slot: int, pred_slot: int, recon_slot: int, tus: Sequence[TU], levels: np.ndarray):
+        levels = np.ascontiguousarray(levels, np.int32)
+        arr = _arr(TU, tus)
+        self._ck(self.L.tvc_inv_tq_batch(self.h, resi_slot, pred_slot, recon_slot, len(tus), C.cast(arr, C.c_void_p),
+                                         ptr(levels), levels.size))
+
+    def xT(self, use_dst: int, resi: np.ndarray, off: int, stride: int, n: int) -> np.ndarray:
+        coef = np.zeros(n * n, np.int32)
+        self._ck(self.L.tvc_xT(self.h, use_dst, ptr(resi, off), stride, ptr(coef), n, n))
+        return coef
+
+    def xIT(self, use_dst: int, coef: np.ndarray, resi: np.ndarray, off: int, stride: int, n: int):
+        coef = np.ascontiguousarray(coef, np.int32)
+        self._ck(self.L.tvc_xIT(self.h, use_dst, ptr(coef), ptr(resi, off), stride, n, n))
+
+    def xDeQuant(self, q: np.ndarray, n: int, per: int, rem: int) -> np.ndarray:
+        q = np.ascontiguousarray(q, np.int32)
+        out = np.zeros(n * n, np.int32)
+        self._ck(self.L.tvc_xDeQuant(self.h, ptr(q), ptr(out), n, n, per, rem))
+        return out
+
+    def ubench(self, which: int) -> float:
+        v = C.c_double()
+        self._ck(self.L.tvc_ubench(self.h, which, C.byref(v)))
+        return v.value
