@@ -1,0 +1,608 @@
+#!/usr/bin/env python
+"""bench.py -- hot-path throughput of one 1080p low-delay-P picture (BASELINE.json configs[1]).
+
+A "step" is one pass of the ported hot path over one synthetic 1920x1080 P picture with 4 reference
+pictures (cfg/encoder_lowdelay_P_main.cfg: SR 64, FEN 1, HadamardME 1, AMP 1, 8-bit):
+
+  1. ME frame pre-pass  : SAD tables of all 129x129 integer candidates per CTU and reference, then for
+                          every PU of the partition census (593 per CTU) x 4 references the integer TZ
+                          search (xTZSearch) and the fractional search (xPatternSearchFracDIF);
+  2. motion compensation: Y/U/V prediction of the whole picture from a PU partition with quarter-pel MVs;
+  3. residual           : org - pred (three planes);
+  4. transform + quant  : every TU size (luma 4..32, chroma 4..16) tiled over the picture (the residual
+                          quadtree visits each size), non-RDOQ quantiser with sign-data hiding;
+  5. dequant + inverse transform + reconstruction for the same TUs.
+
+`value`  = frames/s with every input resident in HBM (device-pointer ABI entry points).
+`e2e`    = the same through the host-pointer C ABI: pictures, TU/PU lists and levels are copied
+           host->device from pinned memory and ME results, levels and the reconstruction are copied back,
+           all inside the timed region.
+`--impl reference` times the CPU restatement of the same reference functions (oracle/, all host cores)
+on a bounded sample of CTUs of the same workload.
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "1080p LDP hot-path fps (ME pre-pass + interp/MC + TQ per P picture)"
+UNIT = "frames/s"
+W, H, BD = 1920, 1080, 8
+NUM_REFS = 4
+SEARCH_RANGE = 64
+LAMBDA = 57.908390             # sqrt-lambda domain value HM derives for QP 32 P pictures (any value works)
+QP = 32
+SLOT_CUR, SLOT_PRED, SLOT_RESI, SLOT_RESI2, SLOT_RECON = 0, 5, 6, 7, 8
+NUM_SLOTS = 9
+
+
+# --------------------------------------------------------------------------------------- workload
+def chroma_qp(qp):
+    """chroma QP mapping of TComTrQuant::setQPforQuant (TComTrQuant.cpp:192-222, table TComRom.cpp:380-386)"""
+    tab = [29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37, 37]
+    if qp < 30:
+        return qp
+    if qp >= 44:
+        return qp - 6
+    return tab[qp - 30]
+
+
+def make_tu_list(w, h, qp, bd):
+    from thevc_b200.capi import TU_DTYPE
+    per_l, rem_l = (qp + 6 * (bd - 8)) // 6, (qp + 6 * (bd - 8)) % 6
+    qc = chroma_qp(qp) + 6 * (bd - 8)
+    per_c, rem_c = qc // 6, qc % 6
+    rows = []
+    off = 0
+    counts = [0, 0, 0, 0]
+    for log2 in (2, 3, 4, 5):
+        n = 1 << log2
+        for plane in (0, 1, 2):
+            if plane and log2 == 5:
+                continue
+            pw, ph = (w, h) if plane == 0 else (w // 2, h // 2)
+            xs = np.arange(0, pw - n + 1, n, dtype=np.int32)
+            ys = np.arange(0, ph - n + 1, n, dtype=np.int32)
+            gx, gy = np.meshgrid(xs, ys)
+            k = gx.size
+            a = np.zeros(k, TU_DTYPE)
+            a["plane"] = plane
+            a["x"] = gx.ravel()
+            a["y"] = gy.ravel()
+            a["log2_size"] = log2
+            a["flags"] = 0
+            a["scan_idx"] = 0
+            a["qp_per"] = per_l if plane == 0 else per_c
+            a["qp_rem"] = rem_l if plane == 0 else rem_c
+            a["base_per"] = a["qp_per"]
+            a["coef_offset"] = off + np.arange(k, dtype=np.int64) * (n * n)
+            off += k * n * n
+            counts[log2 - 2] += k
+            rows.append(a)
+    return np.concatenate(rows), np.array(counts, np.int32), off
+
+
+def make_pu_list(w, h, rng, ctu_filter=None):
+    """uni-predicted PU partition of the picture: CTU k uses CU size 64 >> (k % 4) with 2Nx2N parts;
+    quarter-pel MVs within +-16 pels (most are 2-D fractional: the separable two-pass case)."""
+    from thevc_b200.capi import PU_DTYPE
+    rows = []
+    ctus_x, ctus_y = (w + 63) // 64, (h + 63) // 64
+    for ctu in range(ctus_x * ctus_y):
+        if ctu_filter is not None and ctu not in ctu_filter:
+            rng.integers(0, 1, 1)
+            continue
+        x0, y0 = (ctu % ctus_x) * 64, (ctu // ctus_x) * 64
+        s = 64 >> (ctu % 4)
+        for yy in range(0, 64, s):
+            for xx in range(0, 64, s):
+                if x0 + xx + s > w or y0 + yy + s > h:
+                    continue
+                rows.append((x0 + xx, y0 + yy, s, s, 1 + (ctu + xx // s) % NUM_REFS, 0, 0, -1, 0, 0))
+    a = np.array(rows, PU_DTYPE)
+    mv = rng.integers(-64, 65, (len(a), 2)).astype(np.int32)
+    a["mvx0"], a["mvy0"] = mv[:, 0], mv[:, 1]
+    return a
+
+
+class Workload:
+    def __init__(self, seed, pinned):
+        import synth
+        from thevc_b200.tlibcuda import HostPic
+        if pinned:
+            import torch
+
+            def alloc(shape):
+                t = torch.zeros(shape, dtype=torch.int16).pin_memory()
+                self._keep.append(t)
+                return t.numpy()
+        else:
+            alloc = None
+        self._keep = []
+        self.alloc = alloc
+        seq = synth.make_sequence(W, H, NUM_REFS + 1, seed=seed)
+        self.pics = []
+        for i in range(NUM_REFS + 1):          # slot 0 = current picture (newest), slots 1..4 = refs, nearest first
+            f = seq[NUM_REFS - i]
+            p = HostPic(W, H, alloc=alloc)
+            p.y[:], p.u[:], p.v[:] = f
+            p.extend_border()
+            self.pics.append(p)
+        self.ctus_x, self.ctus_y = (W + 63) // 64, (H + 63) // 64
+        self.nctu = self.ctus_x * self.ctus_y
+        rng = np.random.default_rng(seed + 1)
+        # predictor guesses (quarter pels): the synthetic global motion (3,5) px/frame x temporal distance + noise
+        self.pred = np.zeros((NUM_REFS, self.nctu, 2), np.int32)
+        for r in range(NUM_REFS):
+            self.pred[r, :, 0] = -3 * 4 * (r + 1)      # background content moves by (-3,-5)*dt relative to the past
+            self.pred[r, :, 1] = -5 * 4 * (r + 1)
+        self.pred += rng.integers(-6, 7, self.pred.shape).astype(np.int32)
+        self.pus = make_pu_list(W, H, rng)
+        self.tus, self.tu_counts, self.coef_elems = make_tu_list(W, H, QP, BD)
+
+    def pic_bytes(self):
+        p = self.pics[0]
+        return p.buf_y.nbytes + p.buf_u.nbytes + p.buf_v.nbytes
+
+
+def census_valid_mask(census, ctus_x, ctus_y):
+    """[nctu, 593] bool: PU lies inside the 1080p picture"""
+    m = np.zeros((ctus_x * ctus_y, len(census)), bool)
+    for ctu in range(ctus_x * ctus_y):
+        x0, y0 = (ctu % ctus_x) * 64, (ctu // ctus_x) * 64
+        m[ctu] = (x0 + census[:, 0] + census[:, 2] <= W) & (y0 + census[:, 1] + census[:, 3] <= H)
+    return m
+
+
+# --------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def _cpu_ctu_work(args):
+    """the reference functions (oracle port) over ONE CTU of the workload: ME for the census x 4 refs,
+    MC of the CTU's PUs, T+Q and IQ+IT+recon of the CTU's TUs.  Returns seconds per phase."""
+    seed, ctu = args
+    import oracle
+    orc = oracle.lib()
+    wl = _CPU_WL.get(seed)
+    if wl is None:
+        wl = Workload(seed, pinned=False)
+        _CPU_WL[seed] = wl
+    from oracle import ptr as optr
+    cur = wl.pics[0]
+    x0, y0 = (ctu % wl.ctus_x) * 64, (ctu // wl.ctus_x) * 64
+    lc = orc.orc_lambda_motion_sad(LAMBDA)
+    refs = (C.c_void_p * NUM_REFS)(*[optr(wl.pics[1 + r].buf_y, wl.pics[1 + r].origin(0)).value for r in range(NUM_REFS)])
+    ires = (oracle.MeResult * (NUM_REFS * 593))()
+    fres = (oracle.FracResult * (NUM_REFS * 593))()
+    pred = np.ascontiguousarray(wl.pred[:, ctu, :].reshape(-1), np.int32)
+    t0 = time.perf_counter()
+    orc.orc_me_frame_ctu(optr(cur.buf_y, cur.origin(0)), refs, NUM_REFS, cur.stride, W, H, x0, y0, optr(pred), lc, SEARCH_RANGE, 1, 1, 1, BD,
+                         ires, fres)
+    t1 = time.perf_counter()
+    # MC
+    pus = wl.pus[(wl.pus["x"] >= x0) & (wl.pus["x"] < x0 + 64) & (wl.pus["y"] >= y0) & (wl.pus["y"] < y0 + 64)]
+    pus = np.ascontiguousarray(pus)
+    from thevc_b200.tlibcuda import HostPic
+    st = _CPU_WL.setdefault(("scratch", seed), [HostPic(W, H) for _ in range(4)])
+    predp, resi, resi2, recon = st
+    planes = (C.c_void_p * ((NUM_REFS + 1) * 3))()
+    for s in range(NUM_REFS + 1):
+        for pl in range(3):
+            planes[s * 3 + pl] = optr(wl.pics[s].plane(pl), wl.pics[s].origin(pl)).value
+
+    def tri(pic):
+        return (C.c_void_p * 3)(*[optr(pic.plane(pl), pic.origin(pl)).value for pl in range(3)])
+    orc.orc_mc_batch(planes, cur.stride, cur.cstride, tri(predp), len(pus), optr(pus.view(np.int32)), BD)
+    t2 = time.perf_counter()
+    for pl in range(3):
+        sh = 1 if pl else 0
+        stp = cur.stride if pl == 0 else cur.cstride
+        o = cur.origin(pl) + (y0 >> sh) * stp + (x0 >> sh)
+        bw, bh = min(64, W - x0) >> sh, min(64, H - y0) >> sh
+        orc.orc_subtract(optr(cur.plane(pl), o), stp, optr(predp.plane(pl), o), stp, optr(resi.plane(pl), o), stp, bw, bh)
+    t3 = time.perf_counter()
+    tus = wl.tus
+    sh = (tus["plane"] > 0).astype(np.int32)
+    m = ((tus["x"] << sh) >= x0) & ((tus["x"] << sh) < x0 + 64) & ((tus["y"] << sh) >= y0) & ((tus["y"] << sh) < y0 + 64)
+    sel = np.ascontiguousarray(tus[m])
+    sizes = 1 << (2 * sel["log2_size"].astype(np.int64))
+    sel["coef_offset"] = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    levels = np.zeros(int(sizes.sum()), np.int32)
+    abs_sum = np.zeros(len(sel), np.uint32)
+    orc.orc_fwd_tq_batch(tri(resi), cur.stride, cur.cstride, len(sel), optr(sel.view(np.int32)), 0, 1, BD, optr(levels), optr(abs_sum))
+    t4 = time.perf_counter()
+    orc.orc_inv_tq_batch(tri(resi2), tri(predp), tri(recon), cur.stride, cur.cstride, len(sel), optr(sel.view(np.int32)), BD, optr(levels))
+    t5 = time.perf_counter()
+    n_sads = int(sum(r.n_sads for r in ires))
+    return {"me": t1 - t0, "mc": t2 - t1, "sub": t3 - t2, "fwd_tq": t4 - t3, "inv_tq": t5 - t4, "total": t5 - t0, "n_sads": n_sads}
+
+
+_CPU_WL = {}
+
+
+def cpu_sample_ctus(n, nctu, ctus_x):
+    """n interior CTUs spread over the picture (every census PU valid)"""
+    rows = (H // 64)            # full CTU rows
+    cand = [r * ctus_x + c for r in range(rows) for c in range(ctus_x)]
+    step = max(1, len(cand) // n)
+    return [cand[(i * step + 7) % len(cand)] for i in range(n)]
+
+
+def frame_ctu_equiv(valid):
+    """number of full-CTU equivalents in one picture (partial bottom CTUs weighted by valid census PUs)"""
+    return float(valid.sum()) / valid.shape[1]
+
+
+def run_cpu_baseline(seed, n_ctus, cores):
+    """oracle port on `cores` processes over n_ctus CTUs; returns fps and detail"""
+    import multiprocessing as mp
+    import oracle
+    oracle.build()
+    wl_dims = ((W + 63) // 64, (H + 63) // 64)
+    ctus = cpu_sample_ctus(n_ctus, wl_dims[0] * wl_dims[1], wl_dims[0])
+    t0 = time.perf_counter()
+    if cores == 1:
+        res = [_cpu_ctu_work((seed, c)) for c in ctus]
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            pool.map(_cpu_warm, [seed] * cores)
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_ctu_work, [(seed, c) for c in ctus], chunksize=1)
+    wall = time.perf_counter() - t0
+    return wall, res, ctus
+
+
+def _cpu_warm(seed):
+    if seed not in _CPU_WL:
+        _CPU_WL[seed] = Workload(seed, pinned=False)
+    return 0
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; libhmref.so holds only
+    the leaf classes, the search loops live in TEncSearch which needs the whole encoder), all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    cores = os.cpu_count() or 1
+    import thevc_b200.capi as capi  # noqa: F401  (struct dtypes only; no GPU use on this arm)
+    census = np.zeros((593, 6), np.int16)
+    oracle.lib().orc_census(census.ctypes.data_as(C.c_void_p))
+    valid = census_valid_mask(census, (W + 63) // 64, (H + 63) // 64)
+    equiv = frame_ctu_equiv(valid)
+    per_step = 4 * cores                  # four CTUs per core and step
+    _cpu_warm(args.seed)
+    times = []
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_cpu_warm, [args.seed] * cores)
+        for s in range(args.warmup + args.steps):
+            ctus = cpu_sample_ctus(per_step * (args.warmup + args.steps), 0, (W + 63) // 64)[s * per_step:(s + 1) * per_step]
+            t0 = time.perf_counter()
+            pool.map(_cpu_ctu_work, [(args.seed, c) for c in ctus], chunksize=1)
+            dt = time.perf_counter() - t0
+            if s >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    fps = (per_step * len(times) / equiv) / total
+    line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/int16/int32", "data": "synthetic", "impl": "reference",
+            "config": workload_config(),
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d CTUs per step (four per core) of the %.1f CTU-equivalents of a picture: census ME x4 refs + MC + T/Q + IQ/IT" % (per_step, equiv)},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config():
+    return {"workload": "cfg/encoder_lowdelay_P_main.cfg 1920x1080 8-bit synthetic, 1 P picture x 4 refs, SR 64, FEN 1, HAD 1: "
+                        "ME pre-pass (SAD tables + TZ + frac for the 593-PU census of 510 CTUs) + MC + residual + T/Q + IQ/IT",
+            "width": W, "height": H, "num_refs": NUM_REFS, "search_range": SEARCH_RANGE, "qp": QP,
+            "l2": "inputs+outputs per step (34.8 GB of SAD tables) exceed the 126 MB L2; no explicit flush",
+            "parallelism": "independent sequences per GPU, no collective"}
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+def gpu_arm(args):
+    import torch
+    from thevc_b200 import TLibCuda, capi
+    from thevc_b200.capi import MeFrameCfg, QuantCfg, ptr
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    stream = torch.cuda.Stream()
+    wl = Workload(args.seed + rank, pinned=True)
+    t = TLibCuda(W, H, BD, num_slots=NUM_SLOTS, device=local, stream=stream.cuda_stream)
+    L, h = t.L, t.h
+    lc = int(np.floor(65536.0 * np.sqrt(LAMBDA)))       # TComRdCost::setLambda (TComRdCost.cpp:167-173)
+    census = t.me_census()
+    valid = census_valid_mask(census, wl.ctus_x, wl.ctus_y)
+
+    for s, p in enumerate(wl.pics):
+        t.upload(s, p)
+    refs = (C.c_int * NUM_REFS)(*range(1, NUM_REFS + 1))
+    mcfg = MeFrameCfg(SEARCH_RANGE, 1, 1, 1, 1, lc)
+    qc = QuantCfg(0, 1, 0)
+    n_pu, n_tu = len(wl.pus), len(wl.tus)
+
+    def dev(a):
+        return torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).cuda(local)
+    pus_d, tus_d = dev(wl.pus), dev(wl.tus)
+    levels_d = torch.zeros(wl.coef_elems, dtype=torch.int32, device="cuda")
+    abs_d = torch.zeros(n_tu, dtype=torch.int32, device="cuda")
+    counts = wl.tu_counts
+    pi, pf = C.c_void_p(), C.c_void_p()
+    pred = wl.pred
+    planes_wh = [(0, W, H), (1, W // 2, H // 2), (2, W // 2, H // 2)]
+
+    def ck(rc):
+        if rc:
+            raise RuntimeError("libthevc_cuda error %d: %s" % (rc, L.tvc_last_error(h).decode()))
+
+    def step_device():
+        ck(L.tvc_me_frame_dev(h, SLOT_CUR, NUM_REFS, refs, ptr(pred), C.byref(mcfg), C.byref(pi), C.byref(pf)))
+        ck(L.tvc_mc_batch_dev(h, SLOT_PRED, n_pu, C.c_void_p(pus_d.data_ptr())))
+        for pl, pw, ph in planes_wh:
+            ck(L.tvc_pic_subtract(h, SLOT_RESI, SLOT_CUR, SLOT_PRED, pl, 0, 0, pw, ph))
+        ck(L.tvc_fwd_tq_batch_dev(h, SLOT_RESI, n_tu, C.c_void_p(tus_d.data_ptr()), ptr(counts), C.byref(qc),
+                                  C.c_void_p(levels_d.data_ptr()), None, C.c_void_p(abs_d.data_ptr())))
+        ck(L.tvc_inv_tq_batch_dev(h, SLOT_RESI2, SLOT_PRED, SLOT_RECON, n_tu, C.c_void_p(tus_d.data_ptr()), ptr(counts),
+                                  C.c_void_p(levels_d.data_ptr())))
+
+    # ---- host-pointer (e2e) path buffers, pinned
+    def pinned(shape, dtype):
+        tt = torch.zeros(shape, dtype=dtype).pin_memory()
+        return tt, tt.numpy()
+    _k1, ires_h = pinned((NUM_REFS * wl.nctu * 593, 4), torch.int32)
+    _k2, fres_h = pinned((NUM_REFS * wl.nctu * 593, 6), torch.int32)
+    _k3, levels_h = pinned((wl.coef_elems,), torch.int32)
+    _k4, abs_h = pinned((n_tu,), torch.int32)
+    recon_h = type(wl.pics[0])(W, H, alloc=wl.alloc)
+
+    def step_e2e():
+        for s, p in enumerate(wl.pics):
+            t.upload(s, p)
+        ck(L.tvc_me_frame(h, SLOT_CUR, NUM_REFS, refs, ptr(pred), C.byref(mcfg), ptr(ires_h), ptr(fres_h)))
+        ck(L.tvc_mc_batch(h, SLOT_PRED, n_pu, ptr(wl.pus)))
+        for pl, pw, ph in planes_wh:
+            ck(L.tvc_pic_subtract(h, SLOT_RESI, SLOT_CUR, SLOT_PRED, pl, 0, 0, pw, ph))
+        ck(L.tvc_fwd_tq_batch(h, SLOT_RESI, n_tu, ptr(wl.tus), C.byref(qc), ptr(levels_h), None, wl.coef_elems, ptr(abs_h)))
+        ck(L.tvc_inv_tq_batch(h, SLOT_RESI2, SLOT_PRED, SLOT_RECON, n_tu, ptr(wl.tus), ptr(levels_h), wl.coef_elems))
+        t.download(SLOT_RECON, into=recon_h)
+
+    h2d = (NUM_REFS + 1) * wl.pic_bytes() + wl.pred.nbytes + wl.pus.nbytes + 2 * wl.tus.nbytes + levels_h.nbytes
+    d2h = ires_h.nbytes + fres_h.nbytes + levels_h.nbytes + abs_h.nbytes + wl.pic_bytes()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world > 1:
+            import torch.distributed as dist
+            tt = torch.tensor([v], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+        return v
+
+    clocks = ClockSampler(local) if rank == 0 else None
+
+    # ---- device-resident timing (value)
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step_device()
+        t.prof_enable(True)
+        t.prof_read(reset=True)
+        launches0 = t.launch_count()
+        barrier()
+        if clocks:
+            clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        e1.record(stream)
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        clk = clocks.stop() if clocks else None
+        launches = t.launch_count() - launches0
+        phases = t.prof_read(reset=True)
+        t.prof_enable(False)
+    ms_total = max_over_ranks(ms_total)
+    ms_step = ms_total / args.steps
+    value = world * 1e3 / ms_step
+
+    # integer-ME candidate counts of this workload (for the algorithmic byte count of the search kernel);
+    # run once more outside the timed region, results to the host
+    ires_flat = np.zeros((NUM_REFS * wl.nctu * 593, 4), np.int32)
+    mcfg_nofrac = MeFrameCfg(SEARCH_RANGE, 1, 1, 1, 0, lc)
+    ck(L.tvc_me_frame(h, SLOT_CUR, NUM_REFS, refs, ptr(pred), C.byref(mcfg_nofrac), ptr(ires_flat), None))
+    n_sads = ires_flat[:, 3].astype(np.int64).reshape(NUM_REFS, wl.nctu, 593)
+
+    # ---- e2e timing (host buffers through the host-pointer ABI)
+    with torch.cuda.stream(stream):
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_e2e()
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record(stream)
+        k_e2e = max(1, min(args.steps, 5))
+        for _ in range(k_e2e):
+            step_e2e()
+        e3.record(stream)
+        barrier()
+        ms_e2e = max_over_ranks(e2.elapsed_time(e3)) / k_e2e
+
+    if rank != 0:
+        t.close()
+        return
+
+    # ---- roofline of the dominant kernel (per launch = per step for these frame-level kernels)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    n_valid = int(valid.sum()) * NUM_REFS
+    table_bytes = t.me_table_bytes(NUM_REFS)
+    win_bytes = NUM_REFS * wl.nctu * (208 * 192 + 64 * 64)
+    # search: 16-byte table granules read per evaluated candidate of a PU = (h/4) * (number of 16-column quarters it touches)
+    gran = (census[:, 3] // 4) * ((census[:, 0] + census[:, 2] - 1) // 16 - census[:, 0] // 16 + 1)
+    search_bytes = float((n_sads * gran[None, None, :]).sum()) * 16
+    pu_area = (census[:, 2].astype(np.int64) * census[:, 3])
+    cw, chh = census[:, 2].astype(np.int64), census[:, 3].astype(np.int64)
+    frac_bytes = float((valid * (((cw + 8) * (chh + 8) + pu_area) * 2 + 24)[None, :]).sum()) * NUM_REFS
+    samples_tq = float(sum((1 << (2 * int(l))) * int(c) for l, c in zip((2, 3, 4, 5), counts)))
+    alg_bytes = {
+        "me_tables": table_bytes + win_bytes,
+        "me_search": search_bytes + n_valid * (72 + 16),
+        "me_frac": frac_bytes,
+        "mc": float(sum(int(p["w"]) * int(p["h"]) for p in wl.pus)) * 1.5 * 2 * 2,
+        "fwd_tq": samples_tq * (2 + 4),
+        "inv_tq": samples_tq * (4 + 2 + 2 + 2),
+    }
+    ph_ms = {k: (v[0] / args.steps) for k, v in phases.items()}
+    dom = max((k for k in ph_ms if k in alg_bytes), key=lambda k: ph_ms[k])
+    groups_per_step = max(1, phases[dom][1] // args.steps)
+    ach = alg_bytes[dom] / (ph_ms[dom] * 1e-3) / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src, "launch_ms": ph_ms[dom] / groups_per_step,
+                "algorithmic_bytes_per_launch": alg_bytes[dom] / groups_per_step}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get(dom)
+        except Exception:
+            pass
+    sad_pels = float(NUM_REFS * wl.nctu) * 129 * 129 * 4096
+    satd_pels = float((valid * pu_area[None, :]).sum()) * NUM_REFS * 18
+    sub = {
+        "phase_ms_per_step": ph_ms,
+        "phase_GBps": {k: alg_bytes[k] / (ph_ms[k] * 1e-3) / 1e9 for k in alg_bytes if ph_ms.get(k, 0) > 0},
+        "me_sad_table_gpel_per_s": sad_pels / (ph_ms["me_tables"] * 1e-3) / 1e9 if ph_ms["me_tables"] > 0 else None,
+        "me_frac_satd_gpel_per_s": satd_pels / (ph_ms["me_frac"] * 1e-3) / 1e9 if ph_ms["me_frac"] > 0 else None,
+        "tz_candidates_per_step": int(n_sads.sum()),
+        "me_jobs_per_step": n_valid,
+    }
+
+    # ---- CPU baseline (oracle port, one core, bounded sample)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        wall, res, ctus = run_cpu_baseline(args.seed, args.cpu_ctus, 1)
+        equiv = frame_ctu_equiv(valid)
+        per_ctu = wall / len(ctus)
+        cpu = {"value": 1.0 / (per_ctu * equiv), "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "%d interior CTUs of %.1f CTU-equivalents per picture (%.1f s of CPU work): census ME x4 refs + MC + T/Q + IQ/IT" % (len(ctus), equiv, wall),
+               "phase_s_per_ctu": {k: float(np.mean([r[k] for r in res])) for k in ("me", "mc", "fwd_tq", "inv_tq")}}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/int16/int32", "data": "synthetic", "config": workload_config(),
+            "e2e": {"value": world * 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e, "steps": k_e2e},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "detail": sub}
+    print(json.dumps(line))
+    t.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seed", type=int, default=20261018)
+    ap.add_argument("--cpu-ctus", type=int, default=48, help="CTUs of the CPU-baseline sample (1 core)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        try:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+        except Exception:
+            pass
+
+
+if __name__ == "__main__":
+    main()

@@ -311,6 +311,18 @@ int tvc_xT(tvc_ctx* ctx, int use_dst, const int16_t* resi, int stride, int32_t* 
 int tvc_xIT(tvc_ctx* ctx, int use_dst, const int32_t* coef, int16_t* resi, int stride, int w, int h);
 int tvc_xDeQuant(tvc_ctx* ctx, const int32_t* qcoef, int32_t* coef, int w, int h, int per, int rem);
 
+/* ---------------------------------------------------------------------------------- per-phase device timing
+ * CUDA events recorded on the context stream around every kernel group, so that bench.py can report
+ * each kernel's duration measured live inside the timed region (not under a profiler).         */
+enum {
+  TVC_PH_ME_TABLES = 0, TVC_PH_ME_SEARCH = 1, TVC_PH_ME_FRAC = 2, TVC_PH_MC = 3, TVC_PH_FWD_TQ = 4,
+  TVC_PH_INV_TQ = 5, TVC_PH_OTHER = 6, TVC_PH_COUNT = 7
+};
+int tvc_prof_enable(tvc_ctx* ctx, int on);
+/* synchronises the stream, adds the elapsed time of every recorded pair to per-phase sums and returns
+ * the sums (milliseconds) and the number of timed kernel groups per phase; reset != 0 clears them */
+int tvc_prof_read(tvc_ctx* ctx, double* ms_sum, uint64_t* groups, int reset);
+
 /* ---------------------------------------------------------------------------------- diagnostics
  * integer-pipe micro-benchmarks used for the ME roofline denominator; returns the
  * measured rate in giga-instructions/s for the whole GPU                                        */

@@ -51,7 +51,7 @@ def build(force: bool = False) -> None:
     """Compile libhm_oracle.so (always possible) and, when /root/reference is present,
     _ref/libhmref.so.  Building the checker is not using it."""
     so = os.path.join(HERE, "libhm_oracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("hm_oracle.c", "hm_oracle_me.c", "hm_oracle_tq.c", "hm_oracle.h")]
+    srcs = [os.path.join(HERE, f) for f in ("hm_oracle.c", "hm_oracle_me.c", "hm_oracle_tq.c", "hm_oracle_frame.c", "hm_oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", HERE, "-B", "oracle"])
     ref_so = os.path.join(HERE, "_ref", "libhmref.so")
@@ -126,6 +126,12 @@ def lib():
     L.orc_quant.argtypes = [i32p, i32p, vp, ci, ci, C.POINTER(QuantParam), u32p, C.POINTER(cu)]
     L.orc_quant.restype = None
     L.orc_dequant.argtypes = [i32p, i32p, ci, ci, ci, ci, ci]; L.orc_dequant.restype = None
+    L.orc_census.argtypes = [vp]; L.orc_census.restype = None
+    L.orc_me_frame_ctu.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, cu, ci, ci, ci, ci, ci, vp, vp]
+    L.orc_me_frame_ctu.restype = None
+    L.orc_mc_batch.argtypes = [vp, ci, ci, vp, ci, vp, ci]; L.orc_mc_batch.restype = None
+    L.orc_fwd_tq_batch.argtypes = [vp, ci, ci, ci, vp, ci, ci, ci, vp, vp]; L.orc_fwd_tq_batch.restype = None
+    L.orc_inv_tq_batch.argtypes = [vp, vp, vp, ci, ci, ci, vp, ci, vp]; L.orc_inv_tq_batch.restype = None
     _LIB = L
     return L
 

@@ -130,6 +130,18 @@ void orc_quant(const int32_t* coef, int32_t* qcoef, int32_t* arl, int w, int h,
                const orc_quant_param* qp, const uint32_t* scan, uint32_t* abs_sum);
 void orc_dequant(const int32_t* qcoef, int32_t* coef, int w, int h, int per, int rem, int bd);
 
+/* ------------------------------------------------------------------ frame-level drivers (hm_oracle_frame.c) */
+#define ORC_CENSUS 593
+void orc_census(int16_t* out /* ORC_CENSUS * 6: x, y, w, h, cu_x, cu_y */);
+void orc_me_frame_ctu(const Pel* cur, const Pel* const* refs, int num_refs, int stride, int pic_w, int pic_h,
+                      int ctu_x, int ctu_y, const int32_t* pred_qpel, uint32_t lambda_cost, int srange, int fen,
+                      int hadamard, int do_frac, int bd, orc_me_result* int_out, orc_frac_result* frac_out);
+void orc_mc_batch(const Pel* const* ref_planes, int stride_y, int stride_c, Pel* const* dst, int n, const int32_t* pus, int bd);
+void orc_fwd_tq_batch(const Pel* const* resi, int stride_y, int stride_c, int n, const int32_t* tus,
+                      int is_intra_slice, int sign_hide, int bd, int32_t* levels, uint32_t* abs_sum);
+void orc_inv_tq_batch(Pel* const* resi, const Pel* const* pred, Pel* const* recon, int stride_y, int stride_c, int n,
+                      const int32_t* tus, int bd, const int32_t* levels);
+
 #ifdef __cplusplus
 }
 #endif

@@ -180,7 +180,7 @@ int tvc_ctx_create(const tvc_config* cfg, tvc_ctx** out)
       if (c->encode_tiled) {
         int rows = p.h[0] + 2 * p.my[0];
         if (make_tmap_u8(c, &p.tmap_cur, p.buf8, p.stride8, rows, p.stride8, 64, 64) == TVC_OK &&
-            make_tmap_u8(c, &p.tmap_ref, p.buf8, p.stride8, rows, p.stride8, 192, 192) == TVC_OK)
+            make_tmap_u8(c, &p.tmap_ref, p.buf8, p.stride8, rows, p.stride8, 208, 192) == TVC_OK)
           p.has_tmap = true;
       }
     }
@@ -209,6 +209,8 @@ void tvc_ctx_destroy(tvc_ctx* c)
     if (sc->dev) cudaFree(sc->dev);
     if (sc->host) cudaFreeHost(sc->host);
   }
+  for (auto& p : c->prof_live) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (auto e : c->prof_pool) cudaEventDestroy(e);
   if (c->me_ev) cudaEventDestroy(c->me_ev);
   if (c->fr_ev) cudaEventDestroy(c->fr_ev);
   if (c->fr_jobs) cudaFree(c->fr_jobs);
@@ -291,6 +293,31 @@ int tvc_pic_extend_border(tvc_ctx* c, int slot)
   return refresh_u8(c, p);
 }
 
+int tvc_prof_enable(tvc_ctx* c, int on)
+{
+  if (!c) return TVC_ERR_ARG;
+  c->prof_on = on != 0;
+  return TVC_OK;
+}
+
+int tvc_prof_read(tvc_ctx* c, double* ms_sum, uint64_t* groups, int reset)
+{
+  if (!c) return TVC_ERR_ARG;
+  TVC_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (auto& p : c->prof_live) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { c->prof_ms[p.phase] += ms; c->prof_n[p.phase]++; }
+    c->prof_pool.push_back(p.a); c->prof_pool.push_back(p.b);
+  }
+  c->prof_live.clear();
+  for (int i = 0; i < TVC_PH_COUNT; i++) {
+    if (ms_sum) ms_sum[i] = c->prof_ms[i];
+    if (groups) groups[i] = c->prof_n[i];
+    if (reset) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+  }
+  return TVC_OK;
+}
+
 int tvc_pic_device_ptr(tvc_ctx* c, int slot, int plane, void** ptr, int* stride)
 {
   if (!c || !valid_slot(c, slot) || plane < 0 || plane > 2 || !ptr) return set_err(c, TVC_ERR_ARG, "tvc_pic_device_ptr: bad argument");
@@ -315,6 +342,7 @@ static int region_op(tvc_ctx* c, int op, int dst, int a, int b, int plane, int x
   if (w <= 0 || h <= 0 || x < -p.mx[plane] || y < -p.my[plane] || x + w > p.w[plane] + p.mx[plane] || y + h > p.h[plane] + p.my[plane])
     return set_err(c, TVC_ERR_ARG, "region op: rectangle outside the padded plane");
   size_t off = (size_t)((ptrdiff_t)y * p.stride[plane] + x);
+  ProfScope ps(c, TVC_PH_OTHER);
   dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
   const int16_t* pb = (op != 2) ? c->pics[b].org[plane] + (ptrdiff_t)off : nullptr;
   k_region_op<<<grd, blk, 0, c->stream>>>(op, p.org[plane] + (ptrdiff_t)off, c->pics[a].org[plane] + (ptrdiff_t)off, pb,

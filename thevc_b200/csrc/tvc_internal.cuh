@@ -29,7 +29,7 @@ struct Pic {
   uint8_t* org8 = nullptr;
   int stride8 = 0;
   CUtensorMap tmap_cur;                            // u8 luma, box 64x64
-  CUtensorMap tmap_ref;                            // u8 luma, box 192x192
+  CUtensorMap tmap_ref;                            // u8 luma, box 208x192 (192 + 16 alignment slack)
   bool has_tmap = false;
 };
 
@@ -74,6 +74,13 @@ struct tvc_ctx {
   // dedicated pinned staging of the asynchronous ME entry points (an event guards host reuse)
   tvc::Scratch me_stage, fr_stage;
   cudaEvent_t me_ev = nullptr, fr_ev = nullptr;
+  // per-phase timing (tvc_prof_*)
+  bool prof_on = false;
+  struct ProfPair { int phase; cudaEvent_t a, b; };
+  std::vector<ProfPair> prof_live;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[TVC_PH_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+  uint64_t prof_n[TVC_PH_COUNT] = {0, 0, 0, 0, 0, 0, 0};
   // driver entry point for tensor maps
   void* encode_tiled = nullptr;
 };
@@ -99,6 +106,26 @@ inline bool valid_slot(const tvc_ctx* c, int s) { return s >= 0 && s < (int)c->p
     cudaError_t _e = cudaGetLastError();                                        \
     if (_e != cudaSuccess) return tvc::check_cuda((c), _e, "kernel launch");    \
   } while (0)
+
+// RAII timer of one kernel group on the context stream (no-op unless tvc_prof_enable(ctx, 1))
+struct ProfScope {
+  tvc_ctx* c; cudaEvent_t b = nullptr;
+  ProfScope(tvc_ctx* ctx, int phase) : c(ctx)
+  {
+    if (!c || !c->prof_on) return;
+    cudaEvent_t a = take(); b = take();
+    cudaEventRecord(a, c->stream);
+    c->prof_live.push_back({phase, a, b});
+  }
+  ~ProfScope() { if (b) cudaEventRecord(b, c->stream); }
+  cudaEvent_t take()
+  {
+    cudaEvent_t e = nullptr;
+    if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+  }
+};
 
 // ---- table layout of the ME pre-pass (shared by producer and consumers) ----------------------
 // T[ref][ctu][by 16][q 4][slot 129*129][par 2][bx 4] uint16.  Within one dy row the 129 dx values

@@ -149,6 +149,7 @@ int tvc_mc_batch_dev(tvc_ctx* c, int dst_slot, int n, const tvc_pu* pus_dev)
   if (!c || !valid_slot(c, dst_slot) || n < 0 || (n && !pus_dev)) return set_err(c, TVC_ERR_ARG, "tvc_mc_batch_dev: bad argument");
   if (n == 0) return TVC_OK;
   dim3 grd(n, 3);
+  ProfScope ps(c, TVC_PH_MC);
   k_mc_batch<<<grd, 256, 0, c->stream>>>(c->planes, dst_slot, n, pus_dev, c->cfg.bit_depth);
   TVC_LAUNCH_CHECK(c);
   return TVC_OK;

@@ -19,7 +19,9 @@
 namespace tvc {
 
 // ================================================================================ (1) SAD tables
-constexpr int kWinW = 192, kWinH = 192;
+// TMA needs a 16-byte aligned start coordinate: the window is loaded from its start rounded down to
+// 16, 16 bytes wider, and every task adds the remainder e = start & 15 to its byte offset.
+constexpr int kWinW = 208, kWinH = 192;
 constexpr int kSmemWin = kWinW * kWinH;          // 36864
 constexpr int kSmemCur = 64 * 64;                // 4096
 constexpr int kSmemTables = kSmemWin + kSmemCur + 64;
@@ -154,9 +156,11 @@ k_me_sad_tables(const __grid_constant__ MeMaps maps, int num_ctus, int ctus_x, i
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  const int wx = mx + cx0 + cen.cx - kMeR;
+  const int e = wx & 15;
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar, kSmemWin + kSmemCur);
-    tma_load_2d(win, &maps.ref[ref], mx + cx0 + cen.cx - kMeR, my + cy0 + cen.cy - kMeR, bar);
+    tma_load_2d(win, &maps.ref[ref], wx - e, my + cy0 + cen.cy - kMeR, bar);
     tma_load_2d(cur, &maps.cur, mx + cx0, my + cy0, bar);
   }
   mbar_wait(bar, 0);
@@ -169,17 +173,17 @@ k_me_sad_tables(const __grid_constant__ MeMaps maps, int num_ctus, int ctus_x, i
   for (int t = warp; t < 275; t += 8) {
     if (t < 256) {
       int a = t & 15, g = t >> 4;
-      int u = a + 16 * i8;
-      sad_task_wo<8>((a >> 2) & 3, win, cur, u + 16 * q, (a & 3) * 8, g * 8, q, true, tbl, a * 8 + i8);
+      int u = a + 16 * i8, al = (a + e) & 15;
+      sad_task_wo<8>(al >> 2, win, cur, u + 16 * q + e, (al & 3) * 8, g * 8, q, true, tbl, a * 8 + i8);
     } else if (t < 272) {
       int a = t - 256;
-      int u = a + 16 * i8;
-      sad_task_wo<1>((a >> 2) & 3, win, cur, u + 16 * q, (a & 3) * 8, 128, q, true, tbl, a * 8 + i8);
+      int u = a + 16 * i8, al = (a + e) & 15;
+      sad_task_wo<1>(al >> 2, win, cur, u + 16 * q + e, (al & 3) * 8, 128, q, true, tbl, a * 8 + i8);
     } else if (t < 274) {
       int g = (t - 272) * 8 + i8;
-      sad_task_wo<8>(0, win, cur, 128 + 16 * q, 0, g * 8, q, true, tbl, 128);
+      sad_task_wo<8>(e >> 2, win, cur, 128 + 16 * q + e, (e & 3) * 8, g * 8, q, true, tbl, 128);
     } else {
-      sad_task_wo<1>(0, win, cur, 128 + 16 * q, 0, 128, q, i8 == 0, tbl, 128);
+      sad_task_wo<1>(e >> 2, win, cur, 128 + 16 * q + e, (e & 3) * 8, 128, q, i8 == 0, tbl, 128);
     }
   }
 }
@@ -791,6 +795,7 @@ int tvc_me_prepass(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slots,
     attr_set = true;
   }
   dim3 grd(nctu, num_refs);
+  ProfScope ps(c, TVC_PH_ME_TABLES);
   k_me_sad_tables<<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables);
   TVC_LAUNCH_CHECK(c);
   c->me_num_refs = num_refs;
@@ -837,6 +842,7 @@ int tvc_me_search_batch_dev(tvc_ctx* c, int cur_slot, int use_tables, int n, con
   if (use_tables && (!c->me_tables || c->me_num_refs == 0 || c->me_cur_slot != cur_slot))
     return set_err(c, TVC_ERR_STATE, "tvc_me_search_batch: tables requested but no pre-pass for this picture");
   if (n == 0) return TVC_OK;
+  ProfScope ps(c, TVC_PH_ME_SEARCH);
   k_me_search<<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, use_tables ? c->me_tables : nullptr,
                                                   c->me_centers, c->num_ctus_x * c->num_ctus_y, c->num_ctus_x, c->bi);
   TVC_LAUNCH_CHECK(c);
@@ -885,6 +891,7 @@ int tvc_me_frac_batch_dev(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job* j
     TVC_CUDA(c, cudaFuncSetAttribute(k_me_frac, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrSmem));
     attr_set = true;
   }
+  ProfScope ps(c, TVC_PH_ME_FRAC);
   k_me_frac<<<n, 128, kFrSmem, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, c->cfg.bit_depth);
   TVC_LAUNCH_CHECK(c);
   return TVC_OK;
@@ -976,12 +983,18 @@ int tvc_me_frame_dev(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slot
   TVC_CUDA(c, cudaEventRecord(c->fr_ev, c->stream));
   const tvc_me_center* dpred = (const tvc_me_center*)c->fr_stage.dev;
   const int* dslots = (const int*)((char*)c->fr_stage.dev + np * sizeof(tvc_me_center));
-  k_me_frame_jobs<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(pw, ph, nctu, c->num_ctus_x, num_refs, dslots, dpred, *cfg, c->fr_jobs);
-  TVC_LAUNCH_CHECK(c);
+  {
+    ProfScope ps(c, TVC_PH_OTHER);
+    k_me_frame_jobs<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(pw, ph, nctu, c->num_ctus_x, num_refs, dslots, dpred, *cfg, c->fr_jobs);
+    TVC_LAUNCH_CHECK(c);
+  }
   if ((r = tvc_me_search_batch_dev(c, cur_slot, cfg->use_tables, (int)n, c->fr_jobs, c->fr_int))) return r;
   if (cfg->do_frac) {
-    k_me_frame_frac_jobs<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((int)n, c->fr_jobs, c->fr_int, cfg->hadamard, c->fr_fjobs);
-    TVC_LAUNCH_CHECK(c);
+    {
+      ProfScope ps(c, TVC_PH_OTHER);
+      k_me_frame_frac_jobs<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((int)n, c->fr_jobs, c->fr_int, cfg->hadamard, c->fr_fjobs);
+      TVC_LAUNCH_CHECK(c);
+    }
     if ((r = tvc_me_frac_batch_dev(c, cur_slot, (int)n, c->fr_fjobs, c->fr_frac))) return r;
   }
   if (int_dev) *int_dev = c->fr_int;

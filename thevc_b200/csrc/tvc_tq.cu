@@ -430,6 +430,7 @@ static int launch_fwd(tvc_ctx* c, int resi_slot, const int counts[4], const tvc_
   int r = ensure_scans(c, st);
   if (r) return r;
   int off = 0, bd = c->cfg.bit_depth;
+  ProfScope ps(c, TVC_PH_FWD_TQ);
 #define TVC_FWD(L)                                                                                              \
   if (counts[L - 2] > 0) {                                                                                      \
     int per_cta = 4 * (32 >> L), n = counts[L - 2];                                                             \
@@ -447,6 +448,7 @@ static int launch_inv(tvc_ctx* c, int resi_slot, int pred_slot, int recon_slot, 
                       const int32_t* levels_dev, int dequant)
 {
   int off = 0, bd = c->cfg.bit_depth;
+  ProfScope ps(c, TVC_PH_INV_TQ);
 #define TVC_INV(L)                                                                                              \
   if (counts[L - 2] > 0) {                                                                                      \
     int per_cta = 4 * (32 >> L), n = counts[L - 2];                                                             \
@@ -511,23 +513,26 @@ static int fwd_host(tvc_ctx* c, bool quant, int resi_slot, int n, const tvc_tu* 
   if ((r = ensure_scratch(c, c->out, 2 * coef_bytes + abs_bytes))) return r;
   memcpy(c->in.host, tus, (size_t)n * sizeof(tvc_tu));
   TVC_CUDA(c, cudaMemcpyAsync(c->in.dev, c->in.host, (size_t)n * sizeof(tvc_tu), cudaMemcpyHostToDevice, c->stream));
+  // device / pinned layout: [coefficients][abs sums][ARL coefficients]; only what was produced is copied back
   int32_t* d_coef = (int32_t*)c->out.dev;
-  int32_t* d_arl = (int32_t*)((char*)c->out.dev + coef_bytes);
-  uint32_t* d_abs = (uint32_t*)((char*)c->out.dev + 2 * coef_bytes);
+  uint32_t* d_abs = (uint32_t*)((char*)c->out.dev + coef_bytes);
+  int32_t* d_arl = (int32_t*)((char*)c->out.dev + coef_bytes + abs_bytes);
+  const bool want_arl = quant && arl && qc->use_arl;
   tvc_quant_cfg q0 = {0, 0, 0};
-  if (quant) r = launch_fwd<true>(c, resi_slot, counts, (const tvc_tu*)c->in.dev, *qc, d_coef, arl ? d_arl : nullptr, d_abs);
+  if (quant) r = launch_fwd<true>(c, resi_slot, counts, (const tvc_tu*)c->in.dev, *qc, d_coef, want_arl ? d_arl : nullptr, d_abs);
   else r = launch_fwd<false>(c, resi_slot, counts, (const tvc_tu*)c->in.dev, q0, d_coef, nullptr, nullptr);
   if (r) return r;
-  TVC_CUDA(c, cudaMemcpyAsync(c->out.host, c->out.dev, 2 * coef_bytes + abs_bytes, cudaMemcpyDeviceToHost, c->stream));
+  size_t back = coef_bytes + (quant ? abs_bytes : 0) + (want_arl ? coef_bytes : 0);
+  TVC_CUDA(c, cudaMemcpyAsync(c->out.host, c->out.dev, back, cudaMemcpyDeviceToHost, c->stream));
   TVC_CUDA(c, cudaStreamSynchronize(c->stream));
   // only the TU rasters are defined; copy them out TU by TU
   const int32_t* h_coef = (const int32_t*)c->out.host;
-  const int32_t* h_arl = (const int32_t*)((char*)c->out.host + coef_bytes);
-  const uint32_t* h_abs = (const uint32_t*)((char*)c->out.host + 2 * coef_bytes);
+  const uint32_t* h_abs = (const uint32_t*)((char*)c->out.host + coef_bytes);
+  const int32_t* h_arl = (const int32_t*)((char*)c->out.host + coef_bytes + abs_bytes);
   for (int i = 0; i < n; i++) {
     size_t nn = (size_t)1 << (2 * tus[i].log2_size);
     memcpy(coef + tus[i].coef_offset, h_coef + tus[i].coef_offset, nn * 4);
-    if (quant && arl && qc->use_arl) memcpy(arl + tus[i].coef_offset, h_arl + tus[i].coef_offset, nn * 4);
+    if (want_arl) memcpy(arl + tus[i].coef_offset, h_arl + tus[i].coef_offset, nn * 4);
   }
   if (quant && abs_sum) memcpy(abs_sum, h_abs, (size_t)n * 4);
   return TVC_OK;

@@ -22,15 +22,18 @@ class TvcError(RuntimeError):
 class HostPic:
     """Host-side TComPicYuv: three padded int16 planes.  ``y[r, c]`` views exclude the margin."""
 
-    def __init__(self, width: int, height: int, max_cu: int = 64):
+    def __init__(self, width: int, height: int, max_cu: int = 64, alloc=None):
+        """alloc(shape) -> zeroed C-contiguous int16 array; pass a pinned-memory allocator for
+        asynchronous uploads (default: numpy)"""
+        alloc = alloc or (lambda shape: np.zeros(shape, np.int16))
         self.w, self.h = width, height
         self.mx = self.my = max_cu + 16
         self.cmx = self.cmy = self.mx >> 1
         self.stride = width + 2 * self.mx
         self.cstride = (width >> 1) + 2 * self.cmx
-        self.buf_y = np.zeros((height + 2 * self.my, self.stride), np.int16)
-        self.buf_u = np.zeros(((height >> 1) + 2 * self.cmy, self.cstride), np.int16)
-        self.buf_v = np.zeros_like(self.buf_u)
+        self.buf_y = alloc((height + 2 * self.my, self.stride))
+        self.buf_u = alloc(((height >> 1) + 2 * self.cmy, self.cstride))
+        self.buf_v = alloc(((height >> 1) + 2 * self.cmy, self.cstride))
 
     @property
     def y(self):
@@ -110,8 +113,8 @@ class TLibCuda:
                                        ptr(pic.buf_u, pic.origin(1)), ptr(pic.buf_v, pic.origin(1)), pic.cstride,
                                        1 if with_margin else 0))
 
-    def download(self, slot: int, with_margin: bool = True) -> HostPic:
-        pic = HostPic(self.width, self.height, self.cfg.max_cu)
+    def download(self, slot: int, with_margin: bool = True, into: Optional[HostPic] = None) -> HostPic:
+        pic = into if into is not None else HostPic(self.width, self.height, self.cfg.max_cu)
         self._ck(self.L.tvc_pic_download(self.h, slot, ptr(pic.buf_y, pic.origin(0)), pic.stride,
                                          ptr(pic.buf_u, pic.origin(1)), ptr(pic.buf_v, pic.origin(1)), pic.cstride,
                                          1 if with_margin else 0))
@@ -265,6 +268,16 @@ class TLibCuda:
         out = np.zeros(n * n, np.int32)
         self._ck(self.L.tvc_xDeQuant(self.h, ptr(q), ptr(out), n, n, per, rem))
         return out
+
+    def prof_enable(self, on: bool = True):
+        self._ck(self.L.tvc_prof_enable(self.h, int(on)))
+
+    def prof_read(self, reset: bool = True):
+        """{phase: (ms_sum, kernel_groups)} measured with CUDA events on the context stream"""
+        ms = np.zeros(len(capi.PHASES), np.float64)
+        n = np.zeros(len(capi.PHASES), np.uint64)
+        self._ck(self.L.tvc_prof_read(self.h, ptr(ms), ptr(n), int(reset)))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(capi.PHASES)}
 
     def ubench(self, which: int) -> float:
         v = C.c_double()
