@@ -351,6 +351,8 @@ def _me_jobs(orc, rng, cur, n, mode, srange, ref_index=0, ref_slot=1, lam=57.9):
             continue
         # CU origin for clipMv = the CU that owns the PU; use the enclosing CU of the PU's depth
         predx, predy = (int(v) for v in rng.integers(-60, 61, 2))
+        if len(jobs) % 5 == 4:      # far predictor: the zero vector lies outside the search window
+            predx, predy = (int(v) for v in rng.integers(-520, 521, 2))
         g = oracle.CuGeom(W, H, cx0, cy0, 64)     # m_uiCUPelX/Y of the CTU-level TComDataCU
         lx, ty, rx, by = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         orc.orc_set_search_range(C.byref(g), predx, predy, srange, C.byref(lx), C.byref(ty), C.byref(rx), C.byref(by))

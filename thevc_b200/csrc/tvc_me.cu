@@ -8,8 +8,9 @@
 //      every 4x4 block (TComRdCost.cpp:518-989 with the FEN row sub-sampling of
 //      TEncSearch.cpp:324-330).  Output: uint16 tables, layout in tvc_internal.cuh.
 //  (2) k_me_search     : xPatternSearch / xTZSearch (TEncSearch.cpp:4227-4474) per PU job, one warp
-//      per job, SADs from the tables (or from the pictures), MV rate added per candidate
-//      (TComRdCost.h:196-213), reference visiting order and strict '<'.
+//      per job and one lane per candidate of a diamond round / raster batch, SADs from the tables
+//      (or from the pictures), MV rate added per candidate (TComRdCost.h:196-213); the reference's
+//      sequential strict-'<' update is replayed as an ordered arg-min per round.
 //  (3) k_me_frac       : xPatternSearchFracDIF (TEncSearch.cpp:4476-4514): 8-tap half/quarter
 //      interpolation around the integer MV and 9+9 Hadamard SATD evaluations, one CTA per job,
 //      14-bit intermediates in shared memory, Hadamard butterflies in registers + warp shuffles.
@@ -189,7 +190,7 @@ k_me_sad_tables(const __grid_constant__ MeMaps maps, int num_ctus, int ctus_x, i
 }
 
 // ---- table read: SAD of a PU (inside one CTU) at candidate (dx,dy) relative to the table centre.
-// Lanes split the (block-row, quarter) granules; result valid in all lanes after the reduction.
+// Cooperative form: lanes split the (block-row, quarter) granules; caller reduces over the warp.
 __device__ __forceinline__ uint32_t table_pu_sad_partial(const uint16_t* __restrict__ tbl, int bx0, int by0, int nbx,
                                                          int nby, bool even_only, int dy, int dx, int lane)
 {
@@ -220,6 +221,13 @@ __device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v)
 }
 
 // ================================================================================ (2) search
+// One warp per PU job, ONE LANE PER CANDIDATE.  The reference evaluates candidates one after the
+// other (xTZSearchHelp, TEncSearch.cpp:312-349: strict '<' against the running best), but inside a
+// diamond round, a raster scan or the 2-point step the candidate set is fixed beforehand, so all
+// costs of a batch are computed in parallel (each lane sums its candidate's table granules, many
+// independent 16-byte loads in flight) and the sequential update is replayed afterwards as an
+// ordered arg-min per round: the first candidate in visiting order that attains the round minimum
+// wins iff it is strictly below the best so far -- exactly the state the sequential loop ends in.
 __device__ __forceinline__ uint32_t mv_comp_bits(int v)
 {
   // xGetComponentBits (TComRdCost.cpp:270-284): 2*floor(log2(t)) + 1 with t = v<=0 ? -2v+1 : 2v
@@ -232,11 +240,14 @@ __device__ __forceinline__ uint32_t mv_cost(uint32_t lc, int x, int y, int scale
   return (lc * bits) >> 16;
 }
 
+constexpr uint32_t kNoCost = 0xFFFFFFFFu;
+
 struct SearchCtx {
   // SAD sources
   const uint16_t* tbl;      // table of (ref, ctu) or nullptr
   int tcx, tcy;             // table centre
-  int bx0, by0, nbx, nby;   // PU in 4x4 blocks inside the CTU
+  int by0, nby, q0, nq;     // PU rows in 4x4 blocks / 16-column quarters it touches
+  uint32_t m01[4], m23[4];  // per touched quarter: packed-u16 masks of the blocks inside the PU
   const int16_t* org; int so;
   const int16_t* ref; int rs;   // co-located pel of the PU in the reference plane
   int w, h, sub, bi;
@@ -248,99 +259,212 @@ struct SearchCtx {
   int lane;
 };
 
-__device__ uint32_t cand_sad(const SearchCtx& s, int x, int y)
+// this lane's candidate: sum of the PU's table granules (even rows only when sub-sampled)
+__device__ __forceinline__ uint32_t table_pu_sad_lane(const SearchCtx& s, int dx, int dy)
 {
-  int dx = x - s.tcx, dy = y - s.tcy;
-  uint32_t acc;
-  if (s.tbl && dx >= -kMeR && dx <= kMeR && dy >= -kMeR && dy <= kMeR) {
-    acc = table_pu_sad_partial(s.tbl, s.bx0, s.by0, s.nbx, s.nby, s.sub != 0, dy, dx, s.lane);
-  } else {
-    const int16_t* c = s.ref + (ptrdiff_t)y * s.rs + x;
-    int step = 1 << s.sub, nrows = s.h >> s.sub, total = s.w * nrows;
-    acc = 0;
-    for (int i = s.lane; i < total; i += 32) {
-      int r = i / s.w, xx = i - r * s.w;
-      acc += (uint32_t)abs((int)s.org[(r * step) * s.so + xx] - (int)c[(ptrdiff_t)(r * step) * s.rs + xx]);
+  const size_t cand = (size_t)(dy + kMeR) * kMeC + me_dx_slot(dx);
+  const uint16_t* base = s.tbl + cand * kMeGranule;
+  uint32_t acc = 0;
+  const bool all = s.sub == 0;
+  for (int qi = 0; qi < s.nq; qi++) {
+    const uint32_t ma = s.m01[qi], mb = s.m23[qi];
+    const uint16_t* p = base + (size_t)(s.by0 * 4 + s.q0 + qi) * kMeCands * kMeGranule;
+#pragma unroll 4
+    for (int r = 0; r < s.nby; r++) {
+      const uint4 g = __ldg(reinterpret_cast<const uint4*>(p + (size_t)r * 4 * kMeCands * kMeGranule));
+      uint32_t v = (g.x & ma) + (g.y & mb);                 // packed u16 pairs, each <= 2 * 2040
+      if (all) v += (g.z & ma) + (g.w & mb);                // <= 4 * 2040 < 65536
+      acc += (v & 0xffffu) + (v >> 16);
     }
   }
-  acc = warp_sum_u32(acc);
-  return (acc << s.sub) >> s.bi;
+  return acc;
 }
 
-// xTZSearchHelp (TEncSearch.cpp:312-349)
-__device__ __forceinline__ void tz_help(SearchCtx& s, int x, int y, int point_nr, uint32_t dist)
+// whole-warp SAD of one candidate straight from the pictures (candidate outside the table window,
+// no tables, 10-bit): xGetSAD* with iSubShift (TComRdCost.cpp:518-989)
+__device__ uint32_t direct_sad_warp(const SearchCtx& s, int x, int y)
 {
-  uint32_t sad = cand_sad(s, x, y) + mv_cost(s.lc, x, y, 2, s.px, s.py);
-  s.n_sads++;
-  if (sad < s.best_sad) {
-    s.best_sad = sad; s.best_x = x; s.best_y = y;
-    s.best_dist = dist; s.best_round = 0; s.point_nr = point_nr;
+  const int16_t* c = s.ref + (ptrdiff_t)y * s.rs + x;
+  int step = 1 << s.sub, nrows = s.h >> s.sub, total = s.w * nrows;
+  uint32_t acc = 0;
+  for (int i = s.lane; i < total; i += 32) {
+    int r = i / s.w, xx = i - r * s.w;
+    acc += (uint32_t)abs((int)s.org[(r * step) * s.so + xx] - (int)c[(ptrdiff_t)(r * step) * s.rs + xx]);
+  }
+  return warp_sum_u32(acc);
+}
+
+// cost (SAD + MV rate at scale 2) of this lane's candidate; kNoCost for lanes without one.
+// Warp-collective: every lane must call it.
+__device__ uint32_t eval_batch(const SearchCtx& s, bool valid, int x, int y)
+{
+  uint32_t sad = 0;
+  bool direct = false;
+  if (valid) {
+    int dx = x - s.tcx, dy = y - s.tcy;
+    if (s.tbl && dx >= -kMeR && dx <= kMeR && dy >= -kMeR && dy <= kMeR) sad = table_pu_sad_lane(s, dx, dy);
+    else direct = true;
+  }
+  unsigned m = __ballot_sync(0xffffffffu, direct);
+  while (m) {
+    int src = __ffs(m) - 1;
+    m &= m - 1;
+    int cx = __shfl_sync(0xffffffffu, x, src), cy = __shfl_sync(0xffffffffu, y, src);
+    uint32_t v = direct_sad_warp(s, cx, cy);
+    if (s.lane == src) sad = v;
+  }
+  if (!valid) return kNoCost;
+  return ((sad << s.sub) >> s.bi) + mv_cost(s.lc, x, y, 2, s.px, s.py);
+}
+
+// replay of the sequential xTZSearchHelp updates for the lanes [a, b) (one round, visiting order =
+// lane order).  Returns nothing; updates the (warp-uniform) state.
+__device__ __forceinline__ void replay_round(SearchCtx& s, int a, int b, uint32_t cost, int x, int y, int pt, uint32_t dist)
+{
+  const bool in = s.lane >= a && s.lane < b;
+  const uint32_t c = in ? cost : kNoCost;
+  s.n_sads += __popc(__ballot_sync(0xffffffffu, c != kNoCost));
+  const uint32_t mn = __reduce_min_sync(0xffffffffu, c);
+  if (mn < s.best_sad) {
+    const int src = __ffs(__ballot_sync(0xffffffffu, c == mn)) - 1;
+    s.best_sad = mn;
+    s.best_x = __shfl_sync(0xffffffffu, x, src);
+    s.best_y = __shfl_sync(0xffffffffu, y, src);
+    s.best_dist = __shfl_sync(0xffffffffu, dist, src);
+    s.point_nr = __shfl_sync(0xffffffffu, pt, src);
+    s.best_round = 0;
   }
 }
 
-// xTZ2PointSearch (TEncSearch.cpp:351-476)
-__device__ void tz_two_point(SearchCtx& s)
-{
-  int x = s.best_x, y = s.best_y;
-  bool up = (y - 1) >= s.ty, dn = (y + 1) <= s.by, lf = (x - 1) >= s.lx, rt = (x + 1) <= s.rx;
-  switch (s.point_nr) {
-    case 1: if (lf) tz_help(s, x - 1, y, 0, 2); if (up) tz_help(s, x, y - 1, 0, 2); break;
-    case 2: if (up) { if (lf) tz_help(s, x - 1, y - 1, 0, 2); if (rt) tz_help(s, x + 1, y - 1, 0, 2); } break;
-    case 3: if (up) tz_help(s, x, y - 1, 0, 2); if (rt) tz_help(s, x + 1, y, 0, 2); break;
-    case 4: if (lf) { if (dn) tz_help(s, x - 1, y + 1, 0, 2); if (up) tz_help(s, x - 1, y - 1, 0, 2); } break;
-    case 5: if (rt) { if (up) tz_help(s, x + 1, y - 1, 0, 2); if (dn) tz_help(s, x + 1, y + 1, 0, 2); } break;
-    case 6: if (lf) tz_help(s, x - 1, y, 0, 2); if (dn) tz_help(s, x, y + 1, 0, 2); break;
-    case 7: if (dn) { if (lf) tz_help(s, x - 1, y + 1, 0, 2); if (rt) tz_help(s, x + 1, y + 1, 0, 2); } break;
-    case 8: if (rt) tz_help(s, x + 1, y, 0, 2); if (dn) tz_help(s, x, y + 1, 0, 2); break;
-    default: break;   // the reference asserts; unreachable (distance 1 always carries a point number)
-  }
-}
+__device__ __forceinline__ int round_size(int d) { return d == 1 ? 4 : (d <= 8 ? 8 : 16); }
 
-// xTZ8PointDiamondSearch (TEncSearch.cpp:535-707)
-__device__ void tz_diamond(SearchCtx& s, int sx, int sy, int d)
+// i-th candidate (visiting order) of xTZ8PointDiamondSearch (TEncSearch.cpp:535-707) around (sx,sy) at
+// distance d, with the reference's own border tests: it only tests the edges a point can cross when
+// the centre is inside the window, and the centre CAN be outside (the zero vector is probed
+// unconditionally, :4336-4339), so the tests are restated one by one rather than as "point in window".
+__device__ __forceinline__ bool diamond_cand(const SearchCtx& s, int sx, int sy, int d, int i, int& x, int& y, int& pt,
+                                             uint32_t& dist)
 {
-  int top = sy - d, bot = sy + d, lef = sx - d, rig = sx + d;
-  s.best_round += 1;
+  const int top = sy - d, bot = sy + d, lef = sx - d, rig = sx + d;
+  const bool t_ok = top >= s.ty, b_ok = bot <= s.by, l_ok = lef >= s.lx, r_ok = rig <= s.rx;
   if (d == 1) {
-    if (top >= s.ty) tz_help(s, sx, top, 2, d);
-    if (lef >= s.lx) tz_help(s, lef, sy, 4, d);
-    if (rig <= s.rx) tz_help(s, rig, sy, 5, d);
-    if (bot <= s.by) tz_help(s, sx, bot, 7, d);
-    return;
+    switch (i) {
+      case 0: x = sx; y = top; pt = 2; dist = 1; return t_ok;
+      case 1: x = lef; y = sy; pt = 4; dist = 1; return l_ok;
+      case 2: x = rig; y = sy; pt = 5; dist = 1; return r_ok;
+      default: x = sx; y = bot; pt = 7; dist = 1; return b_ok;
+    }
   }
-  bool inside = top >= s.ty && lef >= s.lx && rig <= s.rx && bot <= s.by;
+  const bool inside = t_ok && b_ok && l_ok && r_ok;
   if (d <= 8) {
-    int h2 = d >> 1;
-    int top2 = sy - h2, bot2 = sy + h2, lef2 = sx - h2, rig2 = sx + h2;
-    if (top >= s.ty) tz_help(s, sx, top, 2, d);
-    if (inside || top2 >= s.ty) {
-      if (inside || lef2 >= s.lx) tz_help(s, lef2, top2, 1, h2);
-      if (inside || rig2 <= s.rx) tz_help(s, rig2, top2, 3, h2);
+    const int h2 = d >> 1;
+    const int top2 = sy - h2, bot2 = sy + h2, lef2 = sx - h2, rig2 = sx + h2;
+    switch (i) {
+      case 0: x = sx; y = top; pt = 2; dist = d; return t_ok;
+      case 1: x = lef2; y = top2; pt = 1; dist = h2; return inside || (top2 >= s.ty && lef2 >= s.lx);
+      case 2: x = rig2; y = top2; pt = 3; dist = h2; return inside || (top2 >= s.ty && rig2 <= s.rx);
+      case 3: x = lef; y = sy; pt = 4; dist = d; return l_ok;
+      case 4: x = rig; y = sy; pt = 5; dist = d; return r_ok;
+      case 5: x = lef2; y = bot2; pt = 6; dist = h2; return inside || (bot2 <= s.by && lef2 >= s.lx);
+      case 6: x = rig2; y = bot2; pt = 8; dist = h2; return inside || (bot2 <= s.by && rig2 <= s.rx);
+      default: x = sx; y = bot; pt = 7; dist = d; return b_ok;
     }
-    if (lef >= s.lx) tz_help(s, lef, sy, 4, d);
-    if (rig <= s.rx) tz_help(s, rig, sy, 5, d);
-    if (inside || bot2 <= s.by) {
-      if (inside || lef2 >= s.lx) tz_help(s, lef2, bot2, 6, h2);
-      if (inside || rig2 <= s.rx) tz_help(s, rig2, bot2, 8, h2);
-    }
-    if (bot <= s.by) tz_help(s, sx, bot, 7, d);
-    return;
   }
-  int qd = d >> 2;
-  if (top >= s.ty) tz_help(s, sx, top, 0, d);
-  if (lef >= s.lx) tz_help(s, lef, sy, 0, d);
-  if (rig <= s.rx) tz_help(s, rig, sy, 0, d);
-  if (bot <= s.by) tz_help(s, sx, bot, 0, d);
-  for (int i = 1; i < 4; i++) {
-    int yt = top + qd * i, yb = bot - qd * i, xl = sx - qd * i, xr = sx + qd * i;
-    if (inside || yt >= s.ty) {
-      if (inside || xl >= s.lx) tz_help(s, xl, yt, 0, d);
-      if (inside || xr <= s.rx) tz_help(s, xr, yt, 0, d);
+  pt = 0; dist = (uint32_t)d;
+  switch (i) {
+    case 0: x = sx; y = top; return t_ok;
+    case 1: x = lef; y = sy; return l_ok;
+    case 2: x = rig; y = sy; return r_ok;
+    case 3: x = sx; y = bot; return b_ok;
+    default: break;
+  }
+  const int qd = d >> 2, k = ((i - 4) >> 2) + 1, j = (i - 4) & 3;   // k = 1..3 ; j: (xl,yt) (xr,yt) (xl,yb) (xr,yb)
+  const bool right = (j & 1) != 0, low = (j & 2) != 0;
+  x = right ? sx + qd * k : sx - qd * k;
+  y = low ? bot - qd * k : top + qd * k;
+  return inside || ((low ? y <= s.by : y >= s.ty) && (right ? x <= s.rx : x >= s.lx));
+}
+
+// rounds d = d0, 2*d0, ... of one diamond sweep around (sx,sy), batched 32 candidates at a time.
+// first_search: stop when three consecutive rounds brought no improvement (bFirstSearchStop,
+// uiFirstSearchRounds = 3; TEncSearch.cpp:4346-4361).
+__device__ void diamond_sweep(SearchCtx& s, int sx, int sy, int srange, bool first_search)
+{
+  int d = 1;
+  while (d <= srange) {
+    // rounds of this batch: greedily while they fit into 32 lanes
+    int nr = 0, tot = 0, dd = d;
+    while (dd <= srange && tot + round_size(dd) <= 32) { tot += round_size(dd); dd <<= 1; nr++; }
+    // this lane's candidate
+    int rd = d, off = 0, x = 0, y = 0, pt = 0;
+    uint32_t dist = 0;
+    bool valid = false;
+    for (int r = 0; r < nr; r++) {
+      int sz = round_size(rd);
+      if (s.lane >= off && s.lane < off + sz) { valid = diamond_cand(s, sx, sy, rd, s.lane - off, x, y, pt, dist); break; }
+      off += sz; rd <<= 1;
     }
-    if (inside || yb <= s.by) {
-      if (inside || xl >= s.lx) tz_help(s, xl, yb, 0, d);
-      if (inside || xr <= s.rx) tz_help(s, xr, yb, 0, d);
+    const uint32_t cost = eval_batch(s, valid, x, y);
+    off = 0; rd = d;
+    for (int r = 0; r < nr; r++) {
+      int sz = round_size(rd);
+      s.best_round += 1;
+      replay_round(s, off, off + sz, cost, x, y, pt, dist);
+      if (first_search && s.best_round >= 3) return;
+      off += sz; rd <<= 1;
     }
+    d = dd;
+  }
+}
+
+// xTZ2PointSearch (TEncSearch.cpp:351-476): the two untested neighbours of the best point; border
+// tests as in the reference (only the edges named there)
+__device__ void two_point(SearchCtx& s)
+{
+  const int bx = s.best_x, by = s.best_y;
+  const bool up = (by - 1) >= s.ty, dn = (by + 1) <= s.by, lf = (bx - 1) >= s.lx, rt = (bx + 1) <= s.rx;
+  int x = 0, y = 0;
+  bool valid = false;
+  if (s.lane < 2) {
+    const bool f = s.lane == 0;
+    switch (s.point_nr) {
+      case 1: x = f ? bx - 1 : bx; y = f ? by : by - 1; valid = f ? lf : up; break;
+      case 2: x = f ? bx - 1 : bx + 1; y = by - 1; valid = up && (f ? lf : rt); break;
+      case 3: x = f ? bx : bx + 1; y = f ? by - 1 : by; valid = f ? up : rt; break;
+      case 4: x = bx - 1; y = f ? by + 1 : by - 1; valid = lf && (f ? dn : up); break;
+      case 5: x = bx + 1; y = f ? by - 1 : by + 1; valid = rt && (f ? up : dn); break;
+      case 6: x = f ? bx - 1 : bx; y = f ? by : by + 1; valid = f ? lf : dn; break;
+      case 7: x = f ? bx - 1 : bx + 1; y = by + 1; valid = dn && (f ? lf : rt); break;
+      case 8: x = f ? bx + 1 : bx; y = f ? by : by + 1; valid = f ? rt : dn; break;
+      default: break;   // the reference asserts; unreachable (distance 1 always carries a point number)
+    }
+  }
+  const uint32_t cost = eval_batch(s, valid, x, y);
+  replay_round(s, 0, 2, cost, x, y, 0, 2u);
+}
+
+// raster over the window with the given step (xPatternSearch with step 1, TEncSearch.cpp:4227-4283;
+// the TZ raster stage with step iRaster, :4389-4400): y outer, x inner, strict '<'
+__device__ void raster_scan(SearchCtx& s, int step, uint32_t dist_tag)
+{
+  const int nx = (s.rx - s.lx) / step + 1, ny = (s.by - s.ty) / step + 1, N = nx * ny;
+  uint32_t lbest = kNoCost;
+  int lidx = 0x7fffffff;
+  for (int base = 0; base < N; base += 32) {
+    const int i = base + s.lane;
+    const bool valid = i < N;
+    const int iy = valid ? i / nx : 0, ix = valid ? i - iy * nx : 0;
+    const uint32_t c = eval_batch(s, valid, s.lx + ix * step, s.ty + iy * step);
+    if (c < lbest) { lbest = c; lidx = i; }
+  }
+  s.n_sads += (uint32_t)N;
+  const uint32_t mn = __reduce_min_sync(0xffffffffu, lbest);
+  if (mn < s.best_sad) {
+    const int idx = (int)__reduce_min_sync(0xffffffffu, (unsigned)(lbest == mn ? lidx : 0x7fffffff));
+    s.best_sad = mn;
+    s.best_x = s.lx + (idx % nx) * step;
+    s.best_y = s.ty + (idx / nx) * step;
+    s.best_dist = dist_tag; s.best_round = 0; s.point_nr = 0;
   }
 }
 
@@ -372,41 +496,50 @@ k_me_search(PlaneTable pt, int cur_slot, int n, const tvc_me_job* __restrict__ j
     tvc_me_center cen = centers[(size_t)jb.ref_index * num_ctus + ctu];
     s.tcx = cen.cx; s.tcy = cen.cy;
   }
-  s.bx0 = (jb.x & 63) >> 2; s.by0 = (jb.y & 63) >> 2; s.nbx = jb.w >> 2; s.nby = jb.h >> 2;
-  s.best_sad = 0xFFFFFFFFu; s.best_x = 0; s.best_y = 0; s.best_dist = 0; s.best_round = 0; s.point_nr = 0;
+  {
+    const int bx0 = (jb.x & 63) >> 2, nbx = jb.w >> 2;
+    s.by0 = (jb.y & 63) >> 2; s.nby = jb.h >> 2;
+    s.q0 = bx0 >> 2; s.nq = ((bx0 + nbx - 1) >> 2) - s.q0 + 1;
+#pragma unroll
+    for (int qi = 0; qi < 4; qi++) {
+      uint32_t a = 0, b = 0;
+      const int b0 = (s.q0 + qi) * 4;
+      if (b0 + 0 >= bx0 && b0 + 0 < bx0 + nbx) a |= 0x0000ffffu;
+      if (b0 + 1 >= bx0 && b0 + 1 < bx0 + nbx) a |= 0xffff0000u;
+      if (b0 + 2 >= bx0 && b0 + 2 < bx0 + nbx) b |= 0x0000ffffu;
+      if (b0 + 3 >= bx0 && b0 + 3 < bx0 + nbx) b |= 0xffff0000u;
+      s.m01[qi] = a; s.m23[qi] = b;
+    }
+  }
+  s.best_sad = kNoCost; s.best_x = 0; s.best_y = 0; s.best_dist = 0; s.best_round = 0; s.point_nr = 0;
   s.n_sads = 0;
 
   if (jb.mode == TVC_ME_FULL) {
-    // xPatternSearch (TEncSearch.cpp:4227-4283): raster, y outer, strict '<'
-    for (int y = s.ty; y <= s.by; y++)
-      for (int x = s.lx; x <= s.rx; x++) {
-        uint32_t sad = cand_sad(s, x, y) + mv_cost(s.lc, x, y, 2, s.px, s.py);
-        s.n_sads++;
-        if (sad < s.best_sad) { s.best_sad = sad; s.best_x = x; s.best_y = y; }
-      }
+    raster_scan(s, 1, 0);
   } else {
     // xTZSearch with TZ_SEARCH_CONFIGURATION (TEncSearch.cpp:293-309, 4302-4474)
     const int raster = 5, srange = jb.search_range;
-    tz_help(s, jb.startx, jb.starty, 0, 0);
-    tz_help(s, 0, 0, 0, 0);
-    int sx = s.best_x, sy = s.best_y;
-    for (int d = 1; d <= srange; d *= 2) {
-      tz_diamond(s, sx, sy, d);
-      if (s.best_round >= 3) break;                           // bFirstSearchStop, uiFirstSearchRounds
+    {
+      // start point (the clipped predictor) then the zero vector (:4320, :4336-4339), sequentially
+      const int x = s.lane == 0 ? jb.startx : 0, y = s.lane == 0 ? jb.starty : 0;
+      const uint32_t cost = eval_batch(s, s.lane < 2, x, y);
+      replay_round(s, 0, 1, cost, x, y, 0, 0u);
+      replay_round(s, 1, 2, cost, x, y, 0, 0u);
+      s.best_round = 0;
     }
-    if (s.best_dist == 1) { s.best_dist = 0; tz_two_point(s); }
-    if ((int)s.best_dist > raster) {
+    diamond_sweep(s, s.best_x, s.best_y, srange, true);        // first search :4346-4361
+    if (s.best_dist == 1) { s.best_dist = 0; two_point(s); }   // :4382-4386
+    if ((int)s.best_dist > raster) {                           // :4389-4400
       s.best_dist = raster;
-      for (int y = s.ty; y <= s.by; y += raster)
-        for (int x = s.lx; x <= s.rx; x += raster) tz_help(s, x, y, 0, raster);
+      raster_scan(s, raster, raster);
     }
-    while (s.best_dist > 0) {
-      sx = s.best_x; sy = s.best_y;
+    while (s.best_dist > 0) {                                  // star refinement :4435-4468
+      const int sx = s.best_x, sy = s.best_y;
       s.best_dist = 0; s.point_nr = 0;
-      for (int d = 1; d < srange + 1; d *= 2) tz_diamond(s, sx, sy, d);
+      diamond_sweep(s, sx, sy, srange, false);
       if (s.best_dist == 1) {
         s.best_dist = 0;
-        if (s.point_nr != 0) tz_two_point(s);
+        if (s.point_nr != 0) two_point(s);
       }
     }
   }
