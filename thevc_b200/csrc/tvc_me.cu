@@ -16,6 +16,7 @@
 //      14-bit intermediates in shared memory, Hadamard butterflies in registers + warp shuffles.
 #include "tvc_internal.cuh"
 #include "tvc_interp.cuh"
+#include <stdlib.h>
 
 namespace tvc {
 
@@ -241,6 +242,13 @@ __device__ __forceinline__ uint32_t mv_cost(uint32_t lc, int x, int y, int scale
 }
 
 constexpr uint32_t kNoCost = 0xFFFFFFFFu;
+#ifndef TVC_SEARCH_ROW_UNROLL
+#define TVC_SEARCH_ROW_UNROLL 1
+#endif
+#ifndef TVC_RASTER_K
+#define TVC_RASTER_K 4
+#endif
+constexpr int kSearchRowUnroll = TVC_SEARCH_ROW_UNROLL;
 
 struct SearchCtx {
   // SAD sources
@@ -259,203 +267,249 @@ struct SearchCtx {
   int lane;
 };
 
-// this lane's candidate: sum of the PU's table granules (even rows only when sub-sampled)
-__device__ __forceinline__ uint32_t table_pu_sad_lane(const SearchCtx& s, int dx, int dy)
-{
-  const size_t cand = (size_t)(dy + kMeR) * kMeC + me_dx_slot(dx);
-  const uint16_t* base = s.tbl + cand * kMeGranule;
-  uint32_t acc = 0;
-  const bool all = s.sub == 0;
-  for (int qi = 0; qi < s.nq; qi++) {
-    const uint32_t ma = s.m01[qi], mb = s.m23[qi];
-    const uint16_t* p = base + (size_t)(s.by0 * 4 + s.q0 + qi) * kMeCands * kMeGranule;
-#pragma unroll 4
-    for (int r = 0; r < s.nby; r++) {
-      const uint4 g = __ldg(reinterpret_cast<const uint4*>(p + (size_t)r * 4 * kMeCands * kMeGranule));
-      uint32_t v = (g.x & ma) + (g.y & mb);                 // packed u16 pairs, each <= 2 * 2040
-      if (all) v += (g.z & ma) + (g.w & mb);                // <= 4 * 2040 < 65536
-      acc += (v & 0xffffu) + (v >> 16);
-    }
-  }
-  return acc;
-}
-
 // whole-warp SAD of one candidate straight from the pictures (candidate outside the table window,
 // no tables, 10-bit): xGetSAD* with iSubShift (TComRdCost.cpp:518-989)
-__device__ uint32_t direct_sad_warp(const SearchCtx& s, int x, int y)
+__device__ __noinline__ uint32_t direct_sad_warp(const int16_t* __restrict__ org, int so, const int16_t* __restrict__ c, int rs,
+                                                 int w, int h, int sub, int lane)
 {
-  const int16_t* c = s.ref + (ptrdiff_t)y * s.rs + x;
-  int step = 1 << s.sub, nrows = s.h >> s.sub, total = s.w * nrows;
+  int step = 1 << sub, nrows = h >> sub, total = w * nrows;
   uint32_t acc = 0;
-  for (int i = s.lane; i < total; i += 32) {
-    int r = i / s.w, xx = i - r * s.w;
-    acc += (uint32_t)abs((int)s.org[(r * step) * s.so + xx] - (int)c[(ptrdiff_t)(r * step) * s.rs + xx]);
+  for (int i = lane; i < total; i += 32) {
+    int r = i / w, xx = i - r * w;
+    acc += (uint32_t)abs((int)org[(r * step) * so + xx] - (int)c[(ptrdiff_t)(r * step) * rs + xx]);
   }
   return warp_sum_u32(acc);
 }
 
-// cost (SAD + MV rate at scale 2) of this lane's candidate; kNoCost for lanes without one.
+// cost (SAD + MV rate at scale 2) of this lane's K candidates; kNoCost for slots without one.  The K
+// table sums run interleaved so that K * granules independent 16-byte loads are in flight per lane.
 // Warp-collective: every lane must call it.
-__device__ uint32_t eval_batch(const SearchCtx& s, bool valid, int x, int y)
+template <int K>
+__device__ __forceinline__ void eval_multi(const SearchCtx& s, const bool (&valid)[K], const int (&x)[K], const int (&y)[K],
+                                           uint32_t (&cost)[K])
 {
-  uint32_t sad = 0;
-  bool direct = false;
-  if (valid) {
-    int dx = x - s.tcx, dy = y - s.tcy;
-    if (s.tbl && dx >= -kMeR && dx <= kMeR && dy >= -kMeR && dy <= kMeR) sad = table_pu_sad_lane(s, dx, dy);
-    else direct = true;
+  uint32_t sad[K];
+  bool tab[K], direct[K];
+  uint32_t base[K];             // granule index inside this (ref, CTU) table (1.06 M granules: fits 32 bits)
+  bool any_direct = false;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const int dx = x[k] - s.tcx, dy = y[k] - s.tcy;
+    const bool cov = s.tbl && dx >= -kMeR && dx <= kMeR && dy >= -kMeR && dy <= kMeR;
+    tab[k] = valid[k] && cov;
+    direct[k] = valid[k] && !cov;
+    any_direct |= direct[k];
+    const uint32_t cand = tab[k] ? (uint32_t)((dy + kMeR) * kMeC + me_dx_slot(dx)) : 0u;
+    base[k] = cand + (uint32_t)(s.by0 * 4 + s.q0) * kMeCands;
+    sad[k] = 0;
   }
-  unsigned m = __ballot_sync(0xffffffffu, direct);
-  while (m) {
-    int src = __ffs(m) - 1;
-    m &= m - 1;
-    int cx = __shfl_sync(0xffffffffu, x, src), cy = __shfl_sync(0xffffffffu, y, src);
-    uint32_t v = direct_sad_warp(s, cx, cy);
-    if (s.lane == src) sad = v;
+  const uint4* __restrict__ tg = reinterpret_cast<const uint4*>(s.tbl);
+  constexpr uint32_t kRow = 4u * kMeCands;      // next block row, same quarter (granules)
+  constexpr uint32_t kQtr = (uint32_t)kMeCands; // next quarter, same block row
+  const bool all = s.sub == 0;
+#pragma unroll
+  for (int qi = 0; qi < 4; qi++) {
+    if (qi < s.nq) {
+      const uint32_t ma = s.m01[qi], mb = s.m23[qi];
+#pragma unroll kSearchRowUnroll
+      for (int r = 0; r < s.nby; r++) {
+        uint4 g[K];
+#pragma unroll
+        for (int k = 0; k < K; k++)
+          if (tab[k]) g[k] = __ldg(tg + (base[k] + qi * kQtr + (uint32_t)r * kRow));
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          if (tab[k]) {
+            uint32_t v = (g[k].x & ma) + (g[k].y & mb);         // packed u16 pairs, each <= 2 * 2040
+            if (all) v += (g[k].z & ma) + (g[k].w & mb);        // <= 4 * 2040 < 65536
+            sad[k] += (v & 0xffffu) + (v >> 16);
+          }
+        }
+      }
+    }
   }
-  if (!valid) return kNoCost;
-  return ((sad << s.sub) >> s.bi) + mv_cost(s.lc, x, y, 2, s.px, s.py);
-}
-
-// replay of the sequential xTZSearchHelp updates for the lanes [a, b) (one round, visiting order =
-// lane order).  Returns nothing; updates the (warp-uniform) state.
-__device__ __forceinline__ void replay_round(SearchCtx& s, int a, int b, uint32_t cost, int x, int y, int pt, uint32_t dist)
-{
-  const bool in = s.lane >= a && s.lane < b;
-  const uint32_t c = in ? cost : kNoCost;
-  s.n_sads += __popc(__ballot_sync(0xffffffffu, c != kNoCost));
-  const uint32_t mn = __reduce_min_sync(0xffffffffu, c);
-  if (mn < s.best_sad) {
-    const int src = __ffs(__ballot_sync(0xffffffffu, c == mn)) - 1;
-    s.best_sad = mn;
-    s.best_x = __shfl_sync(0xffffffffu, x, src);
-    s.best_y = __shfl_sync(0xffffffffu, y, src);
-    s.best_dist = __shfl_sync(0xffffffffu, dist, src);
-    s.point_nr = __shfl_sync(0xffffffffu, pt, src);
-    s.best_round = 0;
+  if (__any_sync(0xffffffffu, any_direct)) {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      unsigned m = __ballot_sync(0xffffffffu, direct[k]);
+      while (m) {
+        int src = __ffs(m) - 1;
+        m &= m - 1;
+        int cx = __shfl_sync(0xffffffffu, x[k], src), cy = __shfl_sync(0xffffffffu, y[k], src);
+        uint32_t v = direct_sad_warp(s.org, s.so, s.ref + (ptrdiff_t)cy * s.rs + cx, s.rs, s.w, s.h, s.sub, s.lane);
+        if (s.lane == src) sad[k] = v;
+      }
+    }
   }
+#pragma unroll
+  for (int k = 0; k < K; k++)
+    cost[k] = valid[k] ? ((sad[k] << s.sub) >> s.bi) + mv_cost(s.lc, x[k], y[k], 2, s.px, s.py) : kNoCost;
 }
 
 __device__ __forceinline__ int round_size(int d) { return d == 1 ? 4 : (d <= 8 ? 8 : 16); }
 
 // i-th candidate (visiting order) of xTZ8PointDiamondSearch (TEncSearch.cpp:535-707) around (sx,sy) at
-// distance d, with the reference's own border tests: it only tests the edges a point can cross when
-// the centre is inside the window, and the centre CAN be outside (the zero vector is probed
-// unconditionally, :4336-4339), so the tests are restated one by one rather than as "point in window".
+// distance d, with the reference's own border tests: an axis point (top / left / right / bottom at
+// distance d) is tested against the one edge it can cross, an off-axis point is taken when the four
+// axis points are inside ("check border") or else when it passes the vertical and the horizontal edge
+// on its own side.  The centre CAN be outside the window (the zero vector is probed unconditionally,
+// :4336-4339), so these are not the same as "point in window" and are restated as written.
+// Branch-free: every lane of a batch holds a different i.
+//   d == 1 : 4 points  top(2) left(4) right(5) bottom(7)
+//   d <= 8 : 8 points  top(2) TL(1) TR(3) left(4) right(5) BL(6) BR(8) bottom(7); diagonals at d/2, tagged d/2
+//   d  > 8 : 16 points top left right bottom, then k = 1..3: (xl,yt) (xr,yt) (xl,yb) (xr,yb), all tagged 0 / d
 __device__ __forceinline__ bool diamond_cand(const SearchCtx& s, int sx, int sy, int d, int i, int& x, int& y, int& pt,
                                              uint32_t& dist)
 {
-  const int top = sy - d, bot = sy + d, lef = sx - d, rig = sx + d;
-  const bool t_ok = top >= s.ty, b_ok = bot <= s.by, l_ok = lef >= s.lx, r_ok = rig <= s.rx;
+  int ux, uy, unit, ptn;          // offset = (ux, uy) * unit
+  bool axis;
   if (d == 1) {
-    switch (i) {
-      case 0: x = sx; y = top; pt = 2; dist = 1; return t_ok;
-      case 1: x = lef; y = sy; pt = 4; dist = 1; return l_ok;
-      case 2: x = rig; y = sy; pt = 5; dist = 1; return r_ok;
-      default: x = sx; y = bot; pt = 7; dist = 1; return b_ok;
+    // i: 0 top, 1 left, 2 right, 3 bottom
+    ux = (i == 1) ? -1 : (i == 2 ? 1 : 0);
+    uy = (i == 0) ? -1 : (i == 3 ? 1 : 0);
+    unit = 1; axis = true;
+    ptn = (0x7542 >> (4 * i)) & 15;
+    dist = 1;
+  } else if (d <= 8) {
+    // nibble tables indexed by i (LSB first): ux+2, uy+2 in half-distance units, point number
+    ux = (int)((0x23140312u >> (4 * i)) & 15) - 2;     // 0,-1,+1,-2,+2,-1,+1,0
+    uy = (int)((0x43322110u >> (4 * i)) & 15) - 2;     // -2,-1,-1,0,0,+1,+1,+2
+    ptn = (int)((0x78654312u >> (4 * i)) & 15);        // 2,1,3,4,5,6,8,7
+    unit = d >> 1;
+    axis = (ux == 0) || (uy == 0);
+    dist = axis ? (uint32_t)d : (uint32_t)(d >> 1);
+  } else {
+    unit = d >> 2;
+    if (i < 4) {
+      ux = (i == 1) ? -4 : (i == 2 ? 4 : 0);
+      uy = (i == 0) ? -4 : (i == 3 ? 4 : 0);
+      axis = true;
+    } else {
+      const int k = ((i - 4) >> 2) + 1, j = (i - 4) & 3;
+      ux = (j & 1) ? k : -k;
+      uy = (j & 2) ? 4 - k : k - 4;
+      axis = false;
     }
+    ptn = 0; dist = (uint32_t)d;
   }
-  const bool inside = t_ok && b_ok && l_ok && r_ok;
-  if (d <= 8) {
-    const int h2 = d >> 1;
-    const int top2 = sy - h2, bot2 = sy + h2, lef2 = sx - h2, rig2 = sx + h2;
-    switch (i) {
-      case 0: x = sx; y = top; pt = 2; dist = d; return t_ok;
-      case 1: x = lef2; y = top2; pt = 1; dist = h2; return inside || (top2 >= s.ty && lef2 >= s.lx);
-      case 2: x = rig2; y = top2; pt = 3; dist = h2; return inside || (top2 >= s.ty && rig2 <= s.rx);
-      case 3: x = lef; y = sy; pt = 4; dist = d; return l_ok;
-      case 4: x = rig; y = sy; pt = 5; dist = d; return r_ok;
-      case 5: x = lef2; y = bot2; pt = 6; dist = h2; return inside || (bot2 <= s.by && lef2 >= s.lx);
-      case 6: x = rig2; y = bot2; pt = 8; dist = h2; return inside || (bot2 <= s.by && rig2 <= s.rx);
-      default: x = sx; y = bot; pt = 7; dist = d; return b_ok;
-    }
-  }
-  pt = 0; dist = (uint32_t)d;
-  switch (i) {
-    case 0: x = sx; y = top; return t_ok;
-    case 1: x = lef; y = sy; return l_ok;
-    case 2: x = rig; y = sy; return r_ok;
-    case 3: x = sx; y = bot; return b_ok;
-    default: break;
-  }
-  const int qd = d >> 2, k = ((i - 4) >> 2) + 1, j = (i - 4) & 3;   // k = 1..3 ; j: (xl,yt) (xr,yt) (xl,yb) (xr,yb)
-  const bool right = (j & 1) != 0, low = (j & 2) != 0;
-  x = right ? sx + qd * k : sx - qd * k;
-  y = low ? bot - qd * k : top + qd * k;
-  return inside || ((low ? y <= s.by : y >= s.ty) && (right ? x <= s.rx : x >= s.lx));
+  x = sx + ux * unit; y = sy + uy * unit; pt = ptn;
+  const bool yc = uy < 0 ? (y >= s.ty) : (y <= s.by);
+  const bool xc = ux < 0 ? (x >= s.lx) : (x <= s.rx);
+  const bool inside = (sy - d) >= s.ty && (sy + d) <= s.by && (sx - d) >= s.lx && (sx + d) <= s.rx;
+  return axis ? (ux == 0 ? yc : xc) : (inside || (yc && xc));
 }
 
-// rounds d = d0, 2*d0, ... of one diamond sweep around (sx,sy), batched 32 candidates at a time.
-// first_search: stop when three consecutive rounds brought no improvement (bFirstSearchStop,
-// uiFirstSearchRounds = 3; TEncSearch.cpp:4346-4361).
-__device__ void diamond_sweep(SearchCtx& s, int sx, int sy, int srange, bool first_search)
+// One diamond sweep (rounds d = 1, 2, 4, ... <= srange) around (sx,sy).  All candidates of the sweep
+// are known beforehand, so they are evaluated together: candidate c of the sweep (visiting order) is
+// slot c >> 5 of lane c & 31.  The reference's sequential update is then replayed round by round as an
+// ordered arg-min.  first_search: stop when three consecutive rounds brought no improvement
+// (bFirstSearchStop, uiFirstSearchRounds = 3; TEncSearch.cpp:4346-4361) -- candidates of later rounds
+// were evaluated speculatively and are neither counted nor used.
+template <int K>
+__device__ __forceinline__ void diamond_sweep(SearchCtx& s, int sx, int sy, int srange, bool first_search)
 {
-  int d = 1;
-  while (d <= srange) {
-    // rounds of this batch: greedily while they fit into 32 lanes
-    int nr = 0, tot = 0, dd = d;
-    while (dd <= srange && tot + round_size(dd) <= 32) { tot += round_size(dd); dd <<= 1; nr++; }
-    // this lane's candidate
-    int rd = d, off = 0, x = 0, y = 0, pt = 0;
-    uint32_t dist = 0;
-    bool valid = false;
-    for (int r = 0; r < nr; r++) {
-      int sz = round_size(rd);
-      if (s.lane >= off && s.lane < off + sz) { valid = diamond_cand(s, sx, sy, rd, s.lane - off, x, y, pt, dist); break; }
-      off += sz; rd <<= 1;
+  bool valid[K];
+  int x[K], y[K];
+  uint32_t cost[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const int c = s.lane + 32 * k;
+    int off = 0, d = 1, pt;
+    uint32_t dist;
+    valid[k] = false; x[k] = 0; y[k] = 0;
+    while (d <= srange) {
+      const int sz = round_size(d);
+      if (c < off + sz) { valid[k] = diamond_cand(s, sx, sy, d, c - off, x[k], y[k], pt, dist); break; }
+      off += sz; d <<= 1;
     }
-    const uint32_t cost = eval_batch(s, valid, x, y);
-    off = 0; rd = d;
-    for (int r = 0; r < nr; r++) {
-      int sz = round_size(rd);
-      s.best_round += 1;
-      replay_round(s, off, off + sz, cost, x, y, pt, dist);
-      if (first_search && s.best_round >= 3) return;
-      off += sz; rd <<= 1;
+  }
+  eval_multi<K>(s, valid, x, y, cost);
+  int off = 0;
+  for (int d = 1; d <= srange; d <<= 1) {
+    const int sz = round_size(d);
+    // this lane's candidate of the round, if any (a round has <= 16 candidates: at most one per lane)
+    uint32_t c = kNoCost;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const int ci = s.lane + 32 * k;
+      if (ci >= off && ci < off + sz) c = cost[k];
     }
-    d = dd;
+    s.best_round += 1;
+    s.n_sads += __popc(__ballot_sync(0xffffffffu, c != kNoCost));
+    const uint32_t mn = __reduce_min_sync(0xffffffffu, c);
+    if (mn < s.best_sad) {
+      // first candidate in visiting order that attains the minimum
+      const unsigned pos = (unsigned)((s.lane - off) & 31);
+      const int i = (int)__reduce_min_sync(0xffffffffu, c == mn ? pos : 0xffu);
+      int bx, by, pt;
+      uint32_t dist;
+      diamond_cand(s, sx, sy, d, i, bx, by, pt, dist);
+      s.best_sad = mn; s.best_x = bx; s.best_y = by; s.best_dist = dist; s.point_nr = pt; s.best_round = 0;
+    }
+    if (first_search && s.best_round >= 3) return;
+    off += sz;
   }
 }
 
 // xTZ2PointSearch (TEncSearch.cpp:351-476): the two untested neighbours of the best point; border
 // tests as in the reference (only the edges named there)
-__device__ void two_point(SearchCtx& s)
+__device__ __forceinline__ void two_point(SearchCtx& s)
 {
   const int bx = s.best_x, by = s.best_y;
   const bool up = (by - 1) >= s.ty, dn = (by + 1) <= s.by, lf = (bx - 1) >= s.lx, rt = (bx + 1) <= s.rx;
-  int x = 0, y = 0;
-  bool valid = false;
+  int x[1] = {0}, y[1] = {0};
+  bool valid[1] = {false};
   if (s.lane < 2) {
     const bool f = s.lane == 0;
     switch (s.point_nr) {
-      case 1: x = f ? bx - 1 : bx; y = f ? by : by - 1; valid = f ? lf : up; break;
-      case 2: x = f ? bx - 1 : bx + 1; y = by - 1; valid = up && (f ? lf : rt); break;
-      case 3: x = f ? bx : bx + 1; y = f ? by - 1 : by; valid = f ? up : rt; break;
-      case 4: x = bx - 1; y = f ? by + 1 : by - 1; valid = lf && (f ? dn : up); break;
-      case 5: x = bx + 1; y = f ? by - 1 : by + 1; valid = rt && (f ? up : dn); break;
-      case 6: x = f ? bx - 1 : bx; y = f ? by : by + 1; valid = f ? lf : dn; break;
-      case 7: x = f ? bx - 1 : bx + 1; y = by + 1; valid = dn && (f ? lf : rt); break;
-      case 8: x = f ? bx + 1 : bx; y = f ? by : by + 1; valid = f ? rt : dn; break;
+      case 1: x[0] = f ? bx - 1 : bx; y[0] = f ? by : by - 1; valid[0] = f ? lf : up; break;
+      case 2: x[0] = f ? bx - 1 : bx + 1; y[0] = by - 1; valid[0] = up && (f ? lf : rt); break;
+      case 3: x[0] = f ? bx : bx + 1; y[0] = f ? by - 1 : by; valid[0] = f ? up : rt; break;
+      case 4: x[0] = bx - 1; y[0] = f ? by + 1 : by - 1; valid[0] = lf && (f ? dn : up); break;
+      case 5: x[0] = bx + 1; y[0] = f ? by - 1 : by + 1; valid[0] = rt && (f ? up : dn); break;
+      case 6: x[0] = f ? bx - 1 : bx; y[0] = f ? by : by + 1; valid[0] = f ? lf : dn; break;
+      case 7: x[0] = f ? bx - 1 : bx + 1; y[0] = by + 1; valid[0] = dn && (f ? lf : rt); break;
+      case 8: x[0] = f ? bx + 1 : bx; y[0] = f ? by : by + 1; valid[0] = f ? rt : dn; break;
       default: break;   // the reference asserts; unreachable (distance 1 always carries a point number)
     }
   }
-  const uint32_t cost = eval_batch(s, valid, x, y);
-  replay_round(s, 0, 2, cost, x, y, 0, 2u);
+  uint32_t cost[1];
+  eval_multi<1>(s, valid, x, y, cost);
+  s.n_sads += __popc(__ballot_sync(0xffffffffu, cost[0] != kNoCost));
+  const uint32_t mn = __reduce_min_sync(0xffffffffu, cost[0]);
+  if (mn < s.best_sad) {
+    const int src = __ffs(__ballot_sync(0xffffffffu, cost[0] == mn)) - 1;
+    s.best_sad = mn;
+    s.best_x = __shfl_sync(0xffffffffu, x[0], src);
+    s.best_y = __shfl_sync(0xffffffffu, y[0], src);
+    s.best_dist = 2; s.point_nr = 0; s.best_round = 0;
+  }
 }
 
 // raster over the window with the given step (xPatternSearch with step 1, TEncSearch.cpp:4227-4283;
-// the TZ raster stage with step iRaster, :4389-4400): y outer, x inner, strict '<'
-__device__ void raster_scan(SearchCtx& s, int step, uint32_t dist_tag)
+// the TZ raster stage with step iRaster, :4389-4400): y outer, x inner, strict '<'.  K candidates per
+// lane and iteration.
+template <int K>
+__device__ __forceinline__ void raster_scan(SearchCtx& s, int step, uint32_t dist_tag)
 {
   const int nx = (s.rx - s.lx) / step + 1, ny = (s.by - s.ty) / step + 1, N = nx * ny;
   uint32_t lbest = kNoCost;
   int lidx = 0x7fffffff;
-  for (int base = 0; base < N; base += 32) {
-    const int i = base + s.lane;
-    const bool valid = i < N;
-    const int iy = valid ? i / nx : 0, ix = valid ? i - iy * nx : 0;
-    const uint32_t c = eval_batch(s, valid, s.lx + ix * step, s.ty + iy * step);
-    if (c < lbest) { lbest = c; lidx = i; }
+  for (int base = 0; base < N; base += 32 * K) {
+    bool valid[K];
+    int x[K], y[K];
+    uint32_t cost[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const int i = base + 32 * k + s.lane;
+      valid[k] = i < N;
+      const int iy = valid[k] ? i / nx : 0, ix = valid[k] ? i - iy * nx : 0;
+      x[k] = s.lx + ix * step; y[k] = s.ty + iy * step;
+    }
+    eval_multi<K>(s, valid, x, y, cost);
+#pragma unroll
+    for (int k = 0; k < K; k++)
+      if (cost[k] < lbest) { lbest = cost[k]; lidx = base + 32 * k + s.lane; }     // increasing index within a lane
   }
   s.n_sads += (uint32_t)N;
   const uint32_t mn = __reduce_min_sync(0xffffffffu, lbest);
@@ -468,7 +522,8 @@ __device__ void raster_scan(SearchCtx& s, int step, uint32_t dist_tag)
   }
 }
 
-__global__ void __launch_bounds__(128)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_me_search(PlaneTable pt, int cur_slot, int n, const tvc_me_job* __restrict__ jobs, tvc_me_result* __restrict__ out,
             const uint16_t* __restrict__ tables, const tvc_me_center* __restrict__ centers, int num_ctus, int ctus_x,
             int bi)
@@ -515,28 +570,33 @@ k_me_search(PlaneTable pt, int cur_slot, int n, const tvc_me_job* __restrict__ j
   s.n_sads = 0;
 
   if (jb.mode == TVC_ME_FULL) {
-    raster_scan(s, 1, 0);
+    raster_scan<TVC_RASTER_K>(s, 1, 0);
   } else {
     // xTZSearch with TZ_SEARCH_CONFIGURATION (TEncSearch.cpp:293-309, 4302-4474)
     const int raster = 5, srange = jb.search_range;
     {
       // start point (the clipped predictor) then the zero vector (:4320, :4336-4339), sequentially
-      const int x = s.lane == 0 ? jb.startx : 0, y = s.lane == 0 ? jb.starty : 0;
-      const uint32_t cost = eval_batch(s, s.lane < 2, x, y);
-      replay_round(s, 0, 1, cost, x, y, 0, 0u);
-      replay_round(s, 1, 2, cost, x, y, 0, 0u);
-      s.best_round = 0;
+      const int x[1] = {s.lane == 0 ? jb.startx : 0}, y[1] = {s.lane == 0 ? jb.starty : 0};
+      const bool valid[1] = {s.lane < 2};
+      uint32_t cost[1];
+      eval_multi<1>(s, valid, x, y, cost);
+      const uint32_t c0 = __shfl_sync(0xffffffffu, cost[0], 0), c1 = __shfl_sync(0xffffffffu, cost[0], 1);
+      s.n_sads += 2;
+      s.best_sad = c0; s.best_x = jb.startx; s.best_y = jb.starty;
+      if (c1 < c0) { s.best_sad = c1; s.best_x = 0; s.best_y = 0; }
+      s.best_dist = 0; s.best_round = 0; s.point_nr = 0;
     }
-    diamond_sweep(s, s.best_x, s.best_y, srange, true);        // first search :4346-4361
+    // a sweep holds 4 + 3*8 + 3*16 = 76 candidates for search range 64: 3 per lane (the ABI bounds the range)
+    diamond_sweep<3>(s, s.best_x, s.best_y, srange, true);      // first search :4346-4361
     if (s.best_dist == 1) { s.best_dist = 0; two_point(s); }   // :4382-4386
     if ((int)s.best_dist > raster) {                           // :4389-4400
       s.best_dist = raster;
-      raster_scan(s, raster, raster);
+      raster_scan<TVC_RASTER_K>(s, raster, raster);
     }
     while (s.best_dist > 0) {                                  // star refinement :4435-4468
       const int sx = s.best_x, sy = s.best_y;
       s.best_dist = 0; s.point_nr = 0;
-      diamond_sweep(s, sx, sy, srange, false);
+      diamond_sweep<3>(s, sx, sy, srange, false);
       if (s.best_dist == 1) {
         s.best_dist = 0;
         if (s.point_nr != 0) two_point(s);
@@ -573,34 +633,49 @@ __global__ void k_me_table_lookup(const uint16_t* __restrict__ tables, const tvc
 }
 
 // ================================================================================ (3) fractional
-constexpr int kFrW = 64, kFrH = 64;
-constexpr int kFrHP = 66;                         // pitch of the horizontal-pass planes (w+1 -> even)
-constexpr int kFrHRows = kFrH + 8;
-constexpr int kFrSmem = 4 * kFrHP * kFrHRows * 2 + kFrW * kFrH * 2 + 64 * 4;
+// xPatternSearchFracDIF (TEncSearch.cpp:4476-4514).  The reference builds half/quarter planes with
+// filterHorLuma(isLast=false) followed by filterVerLuma(isFirst=false, isLast=true)
+// (xExtDIFUpSamplingH/Q, :5982-6175) and evaluates 9 + 9 candidates (xPatternRefinement, :711-760).
+// Every candidate sample therefore is: 14-bit horizontal stage at fraction fx&3, column shifted by
+// (fx<0 ? -1 : 0); vertical stage at fraction fy&3, row shifted by (fy<0 ? -1 : 0); the planes the
+// reference materialises are exactly these values (tests/test_gpu_parity.py::test_me_frac pins it).
+//
+// One job per thread group of NT threads, JPC groups per CTA.  Shared memory per job: the reference
+// window R (w+8)x(h+8), the four horizontal planes H[f] over columns -1..w-1 and rows -4..h+3, the
+// original block.  Candidate stage: a work unit is (Hadamard tile, horizontal fraction); TS lanes
+// each own one tile column, keep the TS+8 rows of H[f] they need in registers (sliding window: one
+// shared-memory load per row instead of eight) and produce the three vertical candidates of that
+// horizontal fraction, Hadamard in registers (vertical) and shuffles (horizontal).
+template <int MAXW, int MAXH>
+struct FracSmem {
+  static constexpr int RP = MAXW + 8;                  // pitch of R
+  static constexpr int HP = MAXW + 2;                  // pitch of the horizontal planes (w+1 columns -> even)
+  static constexpr int HR = MAXH + 8;
+  int16_t R[RP * (MAXH + 8)];
+  int16_t H[4][HP * HR];
+  int16_t org[MAXW * MAXH];
+  uint32_t cost[12];
+  int sel[4];
+};
 
 // xPatternRefinement candidate orders (TEncSearch.cpp:47-71)
 __constant__ int8_t c_refine_h[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {1, -1}, {-1, 1}, {1, 1}};
 __constant__ int8_t c_refine_q[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {1, 1}};
 
-// prediction sample of candidate (fx,fy) (quarter units, -3..3) at (x,y): vertical stage over the
-// 14-bit horizontal planes, isFirst=false, isLast=true (TEncSearch.cpp:5998-6013, 6066-6174 all end in
-// filterVerLuma(..., false, true)).
-__device__ __forceinline__ int frac_pred(const int16_t* __restrict__ H, int fx, int fy, int x, int y, int bd)
+// candidate index (in the reference's order) of offset (ox, oy) in {-1,0,1}^2 for the half / quarter pass
+__device__ __forceinline__ int refine_index(bool half, int ox, int oy)
 {
-  const int ix = fx < 0 ? -1 : 0, f = fx & 3;
-  const int iy = fy < 0 ? -1 : 0, g = fy & 3;
-  const int16_t* p = H + f * (kFrHP * kFrHRows) + (y + iy + 4) * kFrHP + (x + ix + 1);
-  return if_sample<8>(p, kFrHP, g, false, true, bd);
+  // half:    (0,0) (0,-1) (0,1) (-1,0) (1,0) (-1,-1) (1,-1) (-1,1) (1,1)
+  // quarter: (0,0) (0,-1) (0,1) (-1,-1) (1,-1) (-1,0) (1,0) (-1,1) (1,1)
+  const int key = (oy + 1) * 3 + (ox + 1);      // 0..8: (-1,-1) (0,-1) (1,-1) (-1,0) (0,0) (1,0) (-1,1) (0,1) (1,1)
+  const unsigned long long th = 0x827403615ull, tq = 0x827605413ull;   // nibble per key, LSB first
+  return (int)(((half ? th : tq) >> (4 * key)) & 15);
 }
 
 template <int TS>
-__device__ __forceinline__ uint32_t frac_tile_satd(const int16_t* __restrict__ H, const int16_t* __restrict__ org, int fx,
-                                                   int fy, int tx, int ty, int c, int bd)
+__device__ __forceinline__ uint32_t had_cols(int (&d)[TS], int c)
 {
-  // TS lanes per tile; lane c owns column tx+c: vertical Hadamard in registers, horizontal by shuffles
-  int d[TS];
-#pragma unroll
-  for (int r = 0; r < TS; r++) d[r] = (int)org[(ty + r) * kFrW + tx + c] - frac_pred(H, fx, fy, tx + c, ty + r, bd);
+  // lane c of a TS-lane group holds column c of a TS x TS difference tile: 2-D Hadamard, sum |.|, per-tile rounding
 #pragma unroll
   for (int len = 1; len < TS; len <<= 1)
 #pragma unroll
@@ -620,115 +695,171 @@ __device__ __forceinline__ uint32_t frac_tile_satd(const int16_t* __restrict__ H
   for (int r = 0; r < TS; r++) s += (uint32_t)abs(d[r]);
 #pragma unroll
   for (int m = 1; m < TS; m <<= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-  return TS == 8 ? ((s + 2) >> 2) : ((s + 1) >> 1);      // xCalcHADs8x8 / 4x4 rounding
+  return TS == 8 ? ((s + 2) >> 2) : ((s + 1) >> 1);      // xCalcHADs8x8 / 4x4 rounding (TComRdCost.cpp:1773,1869)
 }
 
-__global__ void __launch_bounds__(128)
-k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ jobs, tvc_frac_result* __restrict__ out, int bd)
+// one work unit: tile (tx,ty), horizontal candidate fx; produces the distortions of fy = fy0 - dq, fy0, fy0 + dq
+template <int TS, int HP>
+__device__ __forceinline__ void frac_unit(const int16_t* __restrict__ H, int plane_elems, const int16_t* __restrict__ org, int opitch,
+                                          int fx, int fy0, int dq, int tx, int ty, int c, bool hadamard, int bd, uint32_t (&out)[3])
 {
-  extern __shared__ __align__(16) uint8_t fsm[];
-  int16_t* H = reinterpret_cast<int16_t*>(fsm);
-  int16_t* org = H + 4 * kFrHP * kFrHRows;
-  uint32_t* cost = reinterpret_cast<uint32_t*>(org + kFrW * kFrH);   // 9 accumulators + results
-  __shared__ int s_half[2];
-  const tvc_frac_job jb = jobs[blockIdx.x];
-  if (jb.w <= 0) {                       // census PU outside the picture (frame pre-pass)
-    if (threadIdx.x == 0) out[blockIdx.x] = tvc_frac_result{0, 0, 0, 0, 0u, 0u};
-    return;
-  }
-  const int w = jb.w, h = jb.h, bi = bd - 8;
-  const int stride = pt.stride[0];
-  const int16_t* ref = pt.org[jb.ref_slot][0] + (ptrdiff_t)(jb.y + jb.imvy) * stride + jb.x + jb.imvx;
-  const int16_t* cur = pt.org[cur_slot][0] + (ptrdiff_t)jb.y * stride + jb.x;
-  const int tid = threadIdx.x;
-
-  // horizontal pass (isFirst, !isLast): planes f = 0..3 over columns -1..w-1 and rows -4..h+3
-  // (xExtDIFUpSamplingH/Q, TEncSearch.cpp:5994-5996, 6043-6064)
-  const int hw = w + 1, hh = h + 8;
-  for (int i = tid; i < 4 * hw * hh; i += blockDim.x) {
-    int f = i / (hw * hh), rem = i - f * (hw * hh);
-    int r = rem / hw, x = rem - r * hw;
-    const int16_t* p = ref + (ptrdiff_t)(r - 4) * stride + (x - 1);
-    H[f * (kFrHP * kFrHRows) + r * kFrHP + x] = if_sample<8>(p, 1, f, true, false, bd);
-  }
-  for (int i = tid; i < w * h; i += blockDim.x) {
-    int r = i / w, x = i - r * w;
-    org[r * kFrW + x] = cur[(ptrdiff_t)r * stride + x];
-  }
-  if (tid < 16) cost[tid] = 0;
-  __syncthreads();
-
-  const bool t8 = ((w & 7) == 0) && ((h & 7) == 0);
-  const int TS = (jb.hadamard ? (t8 ? 8 : 4) : 4);
-  const int tiles_x = w / TS, tiles = tiles_x * (h / TS);
-  const int lanes_per_tile = TS, groups = blockDim.x / lanes_per_tile;
-  const int grp = tid / lanes_per_tile, c = tid % lanes_per_tile;
-
-  int basex = 0, basey = 0;       // quarter-unit offset of the pass centre
-  int hx = 0, hy = 0;
-  uint32_t cost_half = 0, cost_q = 0;
-  for (int pass = 0; pass < 2; pass++) {
-    const int fr = pass == 0 ? 2 : 1;
-    // evaluate 9 candidates; units (cand, tile) spread over the lane groups.  The loop bound is
-    // rounded up so every lane of a warp executes the shuffles.
-    const int units = 9 * tiles;
-    const int iters = (units + groups - 1) / groups;
-    for (int it = 0; it < iters; it++) {
-      int u = it * groups + grp;
-      bool valid = u < units;
-      int uu = valid ? u : 0;
-      int cand = uu / tiles, t = uu - cand * tiles;
-      int tyy = (t / tiles_x) * TS, txx = (t % tiles_x) * TS;
-      const int8_t* rf = pass == 0 ? c_refine_h[cand] : c_refine_q[cand];
-      int fx = basex + rf[0] * fr, fy = basey + rf[1] * fr;
-      uint32_t v;
-      if (jb.hadamard) {
-        v = (TS == 8) ? frac_tile_satd<8>(H, org, fx, fy, txx, tyy, c, bd) : frac_tile_satd<4>(H, org, fx, fy, txx, tyy, c, bd);
-      } else {
-        // SAD (xGetSAD*, iSubShift 0): 4x4 tile, lane c = column
-        uint32_t sd = 0;
+  const int ix = fx < 0 ? -1 : 0, f = fx & 3;
+  const int16_t* p = H + f * plane_elems + ty * HP + (tx + c + ix + 1);     // row index 0 of H is picture row -4
+  int v[TS + 8];
 #pragma unroll
-        for (int r = 0; r < 4; r++) sd += (uint32_t)abs((int)org[(tyy + r) * kFrW + txx + c] - frac_pred(H, fx, fy, txx + c, tyy + r, bd));
-        sd += __shfl_xor_sync(0xffffffffu, sd, 1);
-        sd += __shfl_xor_sync(0xffffffffu, sd, 2);
-        v = sd;
-      }
-      if (valid && c == 0) atomicAdd(&cost[cand], v);
+  for (int j = 0; j < TS + 8; j++) v[j] = p[j * HP];                        // rows ty-4 .. ty+TS+3
+  int o[TS];
+#pragma unroll
+  for (int r = 0; r < TS; r++) o[r] = org[(ty + r) * opitch + tx + c];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int fy = fy0 + (k - 1) * dq;
+    const bool up = fy < 0;                                                  // row shift -1
+    const int g = fy & 3;
+    int wv[TS + 7];                                                          // window rows ty-3+iy .. (static indexing)
+#pragma unroll
+    for (int j = 0; j < TS + 7; j++) wv[j] = up ? v[j] : v[j + 1];
+    int cf[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) cf[t] = c_luma_taps[g][t];
+    int d[TS];
+#pragma unroll
+    for (int r = 0; r < TS; r++) {
+      int sum = 0;
+#pragma unroll
+      for (int t = 0; t < 8; t++) sum += wv[r + t] * cf[t];
+      // g == 0: taps are {0,0,0,64,0,0,0,0} and the reference takes the filterCopy branch instead
+      // (TComInterpolationFilter.cpp:124-145); fy == 0 implies no row shift, so wv[r+3] is the sample itself
+      const int pred = g == 0 ? (int)if_copy(wv[r + 3], false, true, bd) : (int)if_round(sum, false, true, bd);
+      d[r] = o[r] - pred;
     }
-    __syncthreads();
-    if (tid == 0) {
+    if (hadamard) out[k] = had_cols<TS>(d, c);
+    else {
+      uint32_t s = 0;
+#pragma unroll
+      for (int r = 0; r < TS; r++) s += (uint32_t)abs(d[r]);
+#pragma unroll
+      for (int m = 1; m < TS; m <<= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+      out[k] = s;
+    }
+  }
+}
+
+template <int MAXW, int MAXH, int NT, int JPC>
+__global__ void __launch_bounds__(NT * JPC)
+k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ jobs, tvc_frac_result* __restrict__ out, int bd,
+          int span, int stride, int first)
+{
+  using SM = FracSmem<MAXW, MAXH>;
+  extern __shared__ __align__(16) uint8_t fsm[];
+  const int grp = threadIdx.x / NT, tid = threadIdx.x % NT;
+  SM& S = reinterpret_cast<SM*>(fsm)[grp];
+  // job index: the frame pre-pass launches one census size class at a time (span jobs out of every stride)
+  const int b = blockIdx.x * JPC + grp;
+  const bool have = b < n;
+  const int ji = have ? (b / span) * stride + first + (b % span) : 0;
+  auto sync = [&]() { if (JPC == 1) __syncthreads(); else __syncwarp(); };
+  const tvc_frac_job jb = jobs[ji];
+  const bool live = have && jb.w > 0 && jb.w <= MAXW && jb.h <= MAXH;
+  if (!live) {
+    if (have && tid == 0 && jb.w <= 0) out[ji] = tvc_frac_result{0, 0, 0, 0, 0u, 0u};   // census PU outside the picture
+    if (JPC == 1) return;
+  }
+  const int w = live ? jb.w : 4, h = live ? jb.h : 4, bi = bd - 8;
+  const int gstride = pt.stride[0];
+  if (live) {
+    const int16_t* ref = pt.org[jb.ref_slot][0] + (ptrdiff_t)(jb.y + jb.imvy - 4) * gstride + jb.x + jb.imvx - 4;
+    const int16_t* cur = pt.org[cur_slot][0] + (ptrdiff_t)jb.y * gstride + jb.x;
+    const int rw = w + 8, rh = h + 8;
+    for (int i = tid; i < rw * rh; i += NT) {
+      int r = i / rw, x = i - r * rw;
+      S.R[r * SM::RP + x] = ref[(ptrdiff_t)r * gstride + x];
+    }
+    for (int i = tid; i < w * h; i += NT) {
+      int r = i / w, x = i - r * w;
+      S.org[r * MAXW + x] = cur[(ptrdiff_t)r * gstride + x];
+    }
+    if (tid < 12) S.cost[tid] = 0;
+  }
+  sync();
+  if (live) {
+    // horizontal stage (isFirst, !isLast): H[f][r][xi], xi = 0..w <-> picture column xi-1, r = 0..h+7 <-> row r-4
+    const int hw = w + 1, hh = h + 8;
+    for (int i = tid; i < hw * hh; i += NT) {
+      int r = i / hw, xi = i - r * hw;
+      const int16_t* p = &S.R[r * SM::RP + xi];          // taps: picture columns (xi-1)-3 .. (xi-1)+4 = R columns xi .. xi+7
+      int t[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) t[k] = p[k];
+      S.H[0][r * SM::HP + xi] = if_copy(t[3], true, false, bd);
+#pragma unroll
+      for (int f = 1; f < 4; f++) {
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) sum += t[k] * (int)c_luma_taps[f][k];
+        S.H[f][r * SM::HP + xi] = if_round(sum, true, false, bd);
+      }
+    }
+  }
+  sync();
+
+  const bool t8 = jb.hadamard && ((w & 7) == 0) && ((h & 7) == 0);
+  const int TS = t8 ? 8 : 4;
+  const int tiles_x = w / TS, tiles = tiles_x * (h / TS);
+  const int groups = NT / TS, ug = tid / TS, c = tid % TS;
+  int basex = 0, basey = 0, hx = 0, hy = 0;
+  uint32_t cost_half = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    const int dq = pass == 0 ? 2 : 1;
+    if (live) {
+      const int units = 3 * tiles;
+      const int iters = (units + groups - 1) / groups;      // rounded up: every lane of a warp executes the shuffles
+      for (int it = 0; it < iters; it++) {
+        const int u = it * groups + ug;
+        const bool valid = u < units;
+        const int uu = valid ? u : 0;
+        const int fxi = uu / tiles, t = uu - fxi * tiles;
+        const int tyy = (t / tiles_x) * TS, txx = (t % tiles_x) * TS;
+        const int ox = fxi - 1;
+        uint32_t v[3];
+        if (t8) frac_unit<8, SM::HP>(&S.H[0][0], SM::HP * SM::HR, S.org, MAXW, basex + ox * dq, basey, dq, txx, tyy, c, true, bd, v);
+        else frac_unit<4, SM::HP>(&S.H[0][0], SM::HP * SM::HR, S.org, MAXW, basex + ox * dq, basey, dq, txx, tyy, c, jb.hadamard != 0, bd, v);
+        if (valid && c == 0) {
+#pragma unroll
+          for (int k = 0; k < 3; k++) atomicAdd(&S.cost[refine_index(pass == 0, ox, k - 1)], v[k]);
+        }
+      }
+    }
+    sync();
+    if (live && tid == 0) {
       // xPatternRefinement (TEncSearch.cpp:730-757): dist >> bitIncrement + rate, strict '<', order as listed
       uint32_t best = 0xFFFFFFFFu; int best_i = 0;
-      int scale = pass == 0 ? 1 : 0;
-      int ax = pass == 0 ? (jb.imvx << 1) : (((jb.imvx << 1) + hx) << 1);
-      int ay = pass == 0 ? (jb.imvy << 1) : (((jb.imvy << 1) + hy) << 1);
+      const int scale = pass == 0 ? 1 : 0;
+      const int ax = pass == 0 ? (jb.imvx << 1) : (((jb.imvx << 1) + hx) << 1);
+      const int ay = pass == 0 ? (jb.imvy << 1) : (((jb.imvy << 1) + hy) << 1);
       for (int i = 0; i < 9; i++) {
         const int8_t* rf = pass == 0 ? c_refine_h[i] : c_refine_q[i];
-        uint32_t d = (cost[i] >> bi) + mv_cost(jb.lambda_cost, ax + rf[0], ay + rf[1], scale, jb.predx, jb.predy);
+        uint32_t d = (S.cost[i] >> bi) + mv_cost(jb.lambda_cost, ax + rf[0], ay + rf[1], scale, jb.predx, jb.predy);
         if (d < best) { best = d; best_i = i; }
       }
       const int8_t* rb = pass == 0 ? c_refine_h[best_i] : c_refine_q[best_i];
-      s_half[0] = rb[0]; s_half[1] = rb[1];
-      cost[9] = best;
-      for (int i = 0; i < 9; i++) cost[i] = 0;
+      S.sel[0] = rb[0]; S.sel[1] = rb[1];
+      S.cost[9] = best;
+      for (int i = 0; i < 9; i++) S.cost[i] = 0;
     }
-    __syncthreads();
+    sync();
     if (pass == 0) {
-      hx = s_half[0]; hy = s_half[1]; cost_half = cost[9];
+      hx = S.sel[0]; hy = S.sel[1]; cost_half = S.cost[9];
       basex = hx * 2; basey = hy * 2;
-    } else {
-      cost_q = cost[9];
-      if (tid == 0) {
-        tvc_frac_result r;
-        r.halfx = hx; r.halfy = hy; r.qtrx = s_half[0]; r.qtry = s_half[1];
-        r.cost_half = cost_half; r.cost = cost_q;
-        out[blockIdx.x] = r;
-      }
+    } else if (live && tid == 0) {
+      tvc_frac_result r;
+      r.halfx = hx; r.halfy = hy; r.qtrx = S.sel[0]; r.qtry = S.sel[1];
+      r.cost_half = cost_half; r.cost = S.cost[9];
+      out[ji] = r;
     }
-    __syncthreads();
+    sync();
   }
 }
-
 
 // ================================================================================ (4) frame pre-pass
 __constant__ tvc_census_pu c_census[TVC_ME_CENSUS];
@@ -870,6 +1001,37 @@ __global__ void k_ub_lds128(uint32_t* out, int iters)
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc.x + acc.y + acc.z + acc.w;
 }
 
+template <int MAXW, int MAXH, int NT, int JPC>
+static int launch_frac_class(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job* jobs_dev, tvc_frac_result* out_dev, int span,
+                             int stride, int first)
+{
+  if (n <= 0) return TVC_OK;
+  constexpr size_t smem = sizeof(FracSmem<MAXW, MAXH>) * JPC;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TVC_CUDA(c, cudaFuncSetAttribute(k_me_frac<MAXW, MAXH, NT, JPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  k_me_frac<MAXW, MAXH, NT, JPC><<<(n + JPC - 1) / JPC, NT * JPC, smem, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev,
+                                                                                      c->cfg.bit_depth, span, stride, first);
+  TVC_LAUNCH_CHECK(c);
+  return TVC_OK;
+}
+
+// census == true: jobs are laid out [ref*ctu][593] in census order; one launch per CU depth so that the
+// thread count and shared memory of a CTA fit the PU sizes of that depth
+static int launch_frac(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job* jobs_dev, tvc_frac_result* out_dev, bool census)
+{
+  ProfScope ps(c, TVC_PH_ME_FRAC);
+  if (!census) return launch_frac_class<64, 64, 256, 1>(c, cur_slot, n, jobs_dev, out_dev, n, 0, 0);
+  const int groups = n / TVC_ME_CENSUS;
+  int r;
+  if ((r = launch_frac_class<64, 64, 256, 1>(c, cur_slot, groups * 13, jobs_dev, out_dev, 13, TVC_ME_CENSUS, 0))) return r;
+  if ((r = launch_frac_class<32, 32, 128, 1>(c, cur_slot, groups * 52, jobs_dev, out_dev, 52, TVC_ME_CENSUS, 13))) return r;
+  if ((r = launch_frac_class<16, 16, 64, 1>(c, cur_slot, groups * 208, jobs_dev, out_dev, 208, TVC_ME_CENSUS, 65))) return r;
+  return launch_frac_class<8, 8, 32, 4>(c, cur_slot, groups * 320, jobs_dev, out_dev, 320, TVC_ME_CENSUS, 273);
+}
+
 }  // namespace tvc
 
 using namespace tvc;
@@ -976,8 +1138,14 @@ int tvc_me_search_batch_dev(tvc_ctx* c, int cur_slot, int use_tables, int n, con
     return set_err(c, TVC_ERR_STATE, "tvc_me_search_batch: tables requested but no pre-pass for this picture");
   if (n == 0) return TVC_OK;
   ProfScope ps(c, TVC_PH_ME_SEARCH);
-  k_me_search<<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, use_tables ? c->me_tables : nullptr,
-                                                  c->me_centers, c->num_ctus_x * c->num_ctus_y, c->num_ctus_x, c->bi);
+  static int variant = -1;       // tuning knob: resident blocks per SM the kernel is compiled for
+  if (variant < 0) { const char* e = getenv("TVC_SEARCH_MINB"); variant = e ? atoi(e) : 4; }
+  const uint16_t* tb = use_tables ? c->me_tables : nullptr;
+  const int nctu = c->num_ctus_x * c->num_ctus_y;
+  if (variant >= 8) k_me_search<8><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi);
+  else if (variant >= 6) k_me_search<6><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi);
+  else if (variant >= 4) k_me_search<4><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi);
+  else k_me_search<1><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi);
   TVC_LAUNCH_CHECK(c);
   return TVC_OK;
 }
@@ -992,7 +1160,7 @@ int tvc_me_search_batch(tvc_ctx* c, int cur_slot, int use_tables, int n, const t
     bool ok = valid_slot(c, j.ref_slot) && j.w > 0 && j.h > 0 && j.w <= 64 && j.h <= 64 && !(j.w & 3) && !(j.h & 3) && !(j.x & 3) &&
               !(j.y & 3) && j.x >= 0 && j.y >= 0 && (j.x & 63) + j.w <= 64 && (j.y & 63) + j.h <= 64 &&
               j.x < c->num_ctus_x * 64 && j.y < c->num_ctus_y * 64 && j.lx <= j.rx && j.ty <= j.by &&
-              (j.mode == TVC_ME_FULL || j.mode == TVC_ME_TZ) && j.search_range >= 1 && j.search_range <= 256 &&
+              (j.mode == TVC_ME_FULL || j.mode == TVC_ME_TZ) && j.search_range >= 1 && j.search_range <= TVC_ME_RANGE &&
               (!use_tables || (j.ref_index >= 0 && j.ref_index < c->me_num_refs && c->me_ref_slots[j.ref_index] == j.ref_slot));
     // every candidate the search may touch must read inside the padded plane
     if (ok) {
@@ -1019,15 +1187,7 @@ int tvc_me_frac_batch_dev(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job* j
 {
   if (!c || !valid_slot(c, cur_slot) || n < 0 || (n && (!jobs_dev || !out_dev))) return set_err(c, TVC_ERR_ARG, "tvc_me_frac_batch_dev: bad argument");
   if (n == 0) return TVC_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TVC_CUDA(c, cudaFuncSetAttribute(k_me_frac, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrSmem));
-    attr_set = true;
-  }
-  ProfScope ps(c, TVC_PH_ME_FRAC);
-  k_me_frac<<<n, 128, kFrSmem, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, c->cfg.bit_depth);
-  TVC_LAUNCH_CHECK(c);
-  return TVC_OK;
+  return launch_frac(c, cur_slot, n, jobs_dev, out_dev, false);
 }
 
 int tvc_me_frac_batch(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job* jobs, tvc_frac_result* out)
@@ -1069,7 +1229,7 @@ int tvc_me_frame_dev(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slot
                      const tvc_me_frame_cfg* cfg, tvc_me_result** int_dev, tvc_frac_result** frac_dev)
 {
   if (!c || !valid_slot(c, cur_slot) || num_refs <= 0 || num_refs > 8 || !ref_slots || !cfg || cfg->search_range < 1 ||
-      cfg->search_range > 256)
+      cfg->search_range > TVC_ME_RANGE)
     return set_err(c, TVC_ERR_ARG, "tvc_me_frame: bad argument");
   for (int r = 0; r < num_refs; r++)
     if (!valid_slot(c, ref_slots[r])) return set_err(c, TVC_ERR_ARG, "tvc_me_frame: bad reference slot");
@@ -1128,7 +1288,7 @@ int tvc_me_frame_dev(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slot
       k_me_frame_frac_jobs<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((int)n, c->fr_jobs, c->fr_int, cfg->hadamard, c->fr_fjobs);
       TVC_LAUNCH_CHECK(c);
     }
-    if ((r = tvc_me_frac_batch_dev(c, cur_slot, (int)n, c->fr_fjobs, c->fr_frac))) return r;
+    if ((r = launch_frac(c, cur_slot, (int)n, c->fr_fjobs, c->fr_frac, true))) return r;
   }
   if (int_dev) *int_dev = c->fr_int;
   if (frac_dev) *frac_dev = cfg->do_frac ? c->fr_frac : nullptr;
