@@ -334,7 +334,7 @@ def reference_arm(args):
     oracle.lib().orc_census(census.ctypes.data_as(C.c_void_p))
     valid = census_valid_mask(census, (W + 63) // 64, (H + 63) // 64)
     equiv = frame_ctu_equiv(valid)
-    per_step = 4 * cores                  # four CTUs per core and step
+    per_step = args.ref_ctus_per_core * cores
     _cpu_warm(args.seed)
     times = []
     import multiprocessing as mp
@@ -354,7 +354,7 @@ def reference_arm(args):
             "dtype": "u8/int16/int32", "data": "synthetic", "impl": "reference",
             "config": workload_config(),
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d CTUs per step (four per core) of the %.1f CTU-equivalents of a picture: census ME x4 refs + MC + T/Q + IQ/IT" % (per_step, equiv)},
+                             "sample": "%d CTUs per step of the %.1f CTU-equivalents of a picture: census ME x4 refs + MC + T/Q + IQ/IT" % (per_step, equiv)},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -365,6 +365,27 @@ def workload_config():
             "width": W, "height": H, "num_refs": NUM_REFS, "search_range": SEARCH_RANGE, "qp": QP,
             "l2": "inputs+outputs per step (34.8 GB of SAD tables) exceed the 126 MB L2; no explicit flush",
             "parallelism": "independent sequences per GPU, no collective"}
+
+
+# --------------------------------------------------------------------------------------- N > 1 host logic
+def rank_seed(seed, rank):
+    """independent synthetic sequence per rank (an LDP sequence is one dependency chain)"""
+    return seed + 7919 * rank
+
+
+def max_over_ranks(v, world, device="cuda"):
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        tt = torch.tensor([v], dtype=torch.float64, device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+    return v
+
+
+def aggregate_fps(ms_per_step, world):
+    """whole-job throughput: every rank finishes one picture per step"""
+    return world * 1e3 / ms_per_step
 
 
 # --------------------------------------------------------------------------------------- GPU arm
@@ -381,7 +402,7 @@ def gpu_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     stream = torch.cuda.Stream()
-    wl = Workload(args.seed + rank, pinned=True)
+    wl = Workload(rank_seed(args.seed, rank), pinned=True)
     t = TLibCuda(W, H, BD, num_slots=NUM_SLOTS, device=local, stream=stream.cuda_stream)
     L, h = t.L, t.h
     lc = int(np.floor(65536.0 * np.sqrt(LAMBDA)))       # TComRdCost::setLambda (TComRdCost.cpp:167-173)
@@ -449,14 +470,6 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(v):
-        if world > 1:
-            import torch.distributed as dist
-            tt = torch.tensor([v], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            return float(tt.item())
-        return v
-
     clocks = ClockSampler(local) if rank == 0 else None
 
     # ---- device-resident timing (value)
@@ -480,9 +493,9 @@ def gpu_arm(args):
         launches = t.launch_count() - launches0
         phases = t.prof_read(reset=True)
         t.prof_enable(False)
-    ms_total = max_over_ranks(ms_total)
+    ms_total = max_over_ranks(ms_total, world)
     ms_step = ms_total / args.steps
-    value = world * 1e3 / ms_step
+    value = aggregate_fps(ms_step, world)
 
     # integer-ME candidate counts of this workload (for the algorithmic byte count of the search kernel);
     # run once more outside the timed region, results to the host
@@ -503,7 +516,7 @@ def gpu_arm(args):
             step_e2e()
         e3.record(stream)
         barrier()
-        ms_e2e = max_over_ranks(e2.elapsed_time(e3)) / k_e2e
+        ms_e2e = max_over_ranks(e2.elapsed_time(e3), world) / k_e2e
 
     if rank != 0:
         t.close()
@@ -572,7 +585,7 @@ def gpu_arm(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/int16/int32", "data": "synthetic", "config": workload_config(),
-            "e2e": {"value": world * 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "e2e": {"value": aggregate_fps(ms_e2e, world), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e, "steps": k_e2e},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "detail": sub}
     print(json.dumps(line))
@@ -588,6 +601,7 @@ def main():
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--cpu-ctus", type=int, default=48, help="CTUs of the CPU-baseline sample (1 core)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-ctus-per-core", type=int, default=4, help="--impl reference: CTUs per core and step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)

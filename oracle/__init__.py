@@ -173,6 +173,15 @@ def ref():
     R.ref_quant.restype = None
     R.ref_dequant.argtypes = [i32p, i32p, ci, ci, ci, ci, ci]; R.ref_dequant.restype = None
     R.ref_extend_border.argtypes = [vp, ci, ci, ci, ci, ci]; R.ref_extend_border.restype = None
+    ip = C.POINTER(ci)
+    R.ref_me_setup.argtypes = [ci, ci, ci, ci, ci]; R.ref_me_setup.restype = None
+    R.ref_set_search_range.argtypes = [ci, ci, ci, ci, ci, ip]; R.ref_set_search_range.restype = None
+    R.ref_int_search.argtypes = [ci, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, C.c_double, ci, ci, ci, ci, ip]
+    R.ref_int_search.restype = None
+    R.ref_frac_search.argtypes = [vp, ci, vp, ci, ci, ci, ci, ci, C.c_double, ci, ci, ip]; R.ref_frac_search.restype = None
+    R.ref_mc_set_ref.argtypes = [vp, vp, vp, ci, ci]; R.ref_mc_set_ref.restype = None
+    R.ref_mc_pu.argtypes = [ci, ci, ci, ci, ci, ci, ci, vp, vp, vp]; R.ref_mc_pu.restype = None
+    R.ref_add_avg.argtypes = [vp] * 6 + [ci, ci] + [vp] * 3; R.ref_add_avg.restype = None
     _REF = R
     return R
 

@@ -7,7 +7,8 @@
  * only #includes the reference headers at build time and forwards calls, so that the
  * restatement in hm_oracle*.c and the CUDA path can be compared with what the reference's
  * own compiled code returns.  `private`/`protected` are opened for this translation unit
- * only, to reach TComTrQuant::xT/xIT/xQuant/xDeQuant and TComPrediction::xPredInter*Blk.
+ * only, to reach TComTrQuant::xT/xIT/xQuant/xDeQuant, TComPrediction::xPredInter*Blk and
+ * TEncSearch::xSetSearchRange / xTZSearch / xPatternSearch / xPatternSearchFracDIF.
  */
 #include <sstream>
 #include <cstring>
@@ -29,6 +30,8 @@
 #include "TLibCommon/TComPicYuv.h"
 #include "TLibCommon/TComYuv.h"
 #include "TLibCommon/TComPrediction.h"
+#include "TLibEncoder/TEncCfg.h"
+#include "TLibEncoder/TEncSearch.h"
 #undef private
 #undef protected
 
@@ -282,6 +285,149 @@ void ref_extend_border(short* pic, int stride, int w, int h, int mx, int my)
 {
   TComPicYuv p;
   p.xExtendPicCompBorder(pic, stride, w, h, mx, my);
+}
+
+
+/* ==================================================================================== motion search
+ * The reference's own TEncSearch members, driven the way xMotionEstimation drives them
+ * (TEncSearch.cpp:4120-4207): getMotionCost(1,0) -> setPredictor -> setCostScale(2) ->
+ * xSetSearchRange -> xPatternSearch / xTZSearch -> setCostScale(1) -> xPatternSearchFracDIF.
+ * The TComDataCU carries only what clipMv reads (CU origin, SPS picture size). */
+static TEncSearch* s_search = 0;
+static TEncCfg* s_cfg = 0;
+static TComDataCU* s_cu = 0;
+static TComSlice* s_slice = 0;
+static TComSPS* s_sps = 0;
+
+void ref_me_setup(int pic_w, int pic_h, int search_range, int fen, int hadme)
+{
+  if (!s_search) {
+    s_cfg = new TEncCfg;
+    s_search = new TEncSearch;
+    s_search->initTempBuff();                 /* m_filteredBlock / m_filteredBlockTmp (TComPrediction.cpp:85-95) */
+    s_cu = new TComDataCU;
+    s_slice = new TComSlice;
+    s_sps = new TComSPS;
+    s_slice->setSPS(s_sps);
+    s_cu->m_pcSlice = s_slice;
+    UInt* tmp = &g_auiZscanToRaster[0];       /* TEncCu::create, TEncCu.cpp:99-105 */
+    initZscanToRaster(g_uiMaxCUDepth + 1, 1, 0, tmp);
+    initRasterToZscan(g_uiMaxCUWidth, g_uiMaxCUHeight, g_uiMaxCUDepth + 1);
+    initRasterToPelXY(g_uiMaxCUWidth, g_uiMaxCUHeight, g_uiMaxCUDepth + 1);
+  }
+  s_cfg->setUseHADME(hadme != 0);
+  s_cfg->setUseFastEnc(fen != 0);
+  s_search->m_pcEncCfg = s_cfg;
+  s_search->m_pcRdCost = s_rd;
+  s_search->m_iSearchRange = search_range;
+  s_search->m_bipredSearchRange = 4;
+  s_search->m_iFastSearch = 1;
+  s_sps->setPicWidthInLumaSamples(pic_w);
+  s_sps->setPicHeightInLumaSamples(pic_h);
+}
+
+static void me_prepare(int cu_x, int cu_y, double lambda, int predx, int predy, int cost_scale)
+{
+  s_cu->m_uiCUPelX = cu_x;
+  s_cu->m_uiCUPelY = cu_y;
+  s_rd->setLambda(lambda);
+  s_rd->getMotionCost(1, 0);
+  TComMv pred(predx, predy);
+  s_rd->setPredictor(pred);
+  s_rd->setCostScale(cost_scale);
+}
+
+void ref_set_search_range(int cu_x, int cu_y, int predx, int predy, int srange, int* out4)
+{
+  s_cu->m_uiCUPelX = cu_x;
+  s_cu->m_uiCUPelY = cu_y;
+  TComMv pred(predx, predy), lt, rb;
+  s_search->xSetSearchRange(s_cu, pred, srange, lt, rb);
+  out4[0] = lt.getHor(); out4[1] = lt.getVer(); out4[2] = rb.getHor(); out4[3] = rb.getVer();
+}
+
+/* mode 0: xPatternSearch (full); 1: xTZSearch.  ref points at the PU's co-located pel. out = mvx, mvy, sad */
+void ref_int_search(int mode, short* org, int so, short* ref, int rs, int w, int h, int cu_x, int cu_y,
+                    int lx, int ty, int rx, int by, double lambda, int predx, int predy, int startx_q, int starty_q, int* out3)
+{
+  me_prepare(cu_x, cu_y, lambda, predx, predy, 2);
+  TComPattern pat;
+  pat.initPattern(org, NULL, NULL, w, h, so, 0, 0, 0, 0);
+  TComMv lt(lx, ty), rb(rx, by), mv(startx_q, starty_q);
+  UInt sad = 0;
+  if (mode == 0) s_search->xPatternSearch(&pat, ref, rs, &lt, &rb, mv, sad);
+  else s_search->xTZSearch(s_cu, &pat, ref, rs, &lt, &rb, mv, sad);
+  out3[0] = mv.getHor(); out3[1] = mv.getVer(); out3[2] = (int)sad;
+}
+
+/* xPatternSearchFracDIF at integer MV (imvx, imvy); out = halfx, halfy, qtrx, qtry, cost */
+void ref_frac_search(short* org, int so, short* ref, int rs, int w, int h, int imvx, int imvy, double lambda,
+                     int predx, int predy, int* out5)
+{
+  me_prepare(0, 0, lambda, predx, predy, 1);         /* cost scale 1 for the half-pel pass (:4187) */
+  TComPattern pat;
+  pat.initPattern(org, NULL, NULL, w, h, so, 0, 0, 0, 0);
+  TComMv mvi(imvx, imvy), half, qtr;
+  UInt cost = 0;
+  s_search->xPatternSearchFracDIF(s_cu, &pat, ref, rs, &mvi, half, qtr, cost, false);
+  out5[0] = half.getHor(); out5[1] = half.getVer(); out5[2] = qtr.getHor(); out5[3] = qtr.getVer(); out5[4] = (int)cost;
+}
+
+/* ==================================================================================== motion compensation
+ * TComPrediction::xPredInterLumaBlk / xPredInterChromaBlk (TComPrediction.cpp:554-645) on a real
+ * TComPicYuv: the caller's padded planes are copied into it (margins included). */
+static TComPicYuv* s_refpic = 0;
+static TComYuv* s_dst = 0;
+static int s_ref_w = 0, s_ref_h = 0;
+
+void ref_mc_set_ref(const short* y, const short* u, const short* v, int w, int h)
+{
+  /* y/u/v: full padded buffers, luma margin 80, stride w+160 (TComPicYuv layout) */
+  if (!s_refpic || s_ref_w != w || s_ref_h != h) {
+    s_refpic = new TComPicYuv;
+    s_refpic->create(w, h, g_uiMaxCUWidth, g_uiMaxCUHeight, g_uiMaxCUDepth);
+    s_ref_w = w; s_ref_h = h;
+    if (!s_dst) { s_dst = new TComYuv; s_dst->create(g_uiMaxCUWidth, g_uiMaxCUHeight); }
+  }
+  memcpy(s_refpic->getBufY(), y, sizeof(short) * (size_t)(w + 160) * (h + 160));
+  memcpy(s_refpic->getBufU(), u, sizeof(short) * (size_t)(w / 2 + 80) * (h / 2 + 80));
+  memcpy(s_refpic->getBufV(), v, sizeof(short) * (size_t)(w / 2 + 80) * (h / 2 + 80));
+}
+
+/* PU at luma (x, y); out_y w*h, out_u/out_v (w/2)*(h/2), dense */
+void ref_mc_pu(int x, int y, int w, int h, int mvx, int mvy, int bi, short* out_y, short* out_u, short* out_v)
+{
+  int ctus_x = (s_ref_w + 63) / 64;
+  s_cu->m_uiCUAddr = (y / 64) * ctus_x + (x / 64);
+  s_cu->m_uiAbsIdxInLCU = g_auiRasterToZscan[((y % 64) / 4) * 16 + (x % 64) / 4];
+  TComMv mv(mvx, mvy);
+  TComYuv* dst = s_dst;
+  s_search->xPredInterLumaBlk(s_cu, s_refpic, 0, &mv, w, h, dst, bi != 0);
+  s_search->xPredInterChromaBlk(s_cu, s_refpic, 0, &mv, w, h, dst, bi != 0);
+  for (int r = 0; r < h; r++) memcpy(out_y + r * w, s_dst->getLumaAddr() + r * s_dst->getStride(), sizeof(short) * w);
+  for (int r = 0; r < h / 2; r++) {
+    memcpy(out_u + r * (w / 2), s_dst->getCbAddr() + r * s_dst->getCStride(), sizeof(short) * (w / 2));
+    memcpy(out_v + r * (w / 2), s_dst->getCrAddr() + r * s_dst->getCStride(), sizeof(short) * (w / 2));
+  }
+}
+
+/* TComYuv::addAvg (TComYuv.cpp:520-581) on two 14-bit predictions */
+void ref_add_avg(const short* a_y, const short* a_u, const short* a_v, const short* b_y, const short* b_u, const short* b_v,
+                 int w, int h, short* o_y, short* o_u, short* o_v)
+{
+  static TComYuv *A = 0, *B = 0, *D = 0;
+  if (!A) { A = new TComYuv; B = new TComYuv; D = new TComYuv; A->create(64, 64); B->create(64, 64); D->create(64, 64); }
+  for (int r = 0; r < h; r++) {
+    memcpy(A->getLumaAddr() + r * 64, a_y + r * w, 2 * w);
+    memcpy(B->getLumaAddr() + r * 64, b_y + r * w, 2 * w);
+  }
+  for (int r = 0; r < h / 2; r++) {
+    memcpy(A->getCbAddr() + r * 32, a_u + r * (w / 2), w); memcpy(A->getCrAddr() + r * 32, a_v + r * (w / 2), w);
+    memcpy(B->getCbAddr() + r * 32, b_u + r * (w / 2), w); memcpy(B->getCrAddr() + r * 32, b_v + r * (w / 2), w);
+  }
+  D->addAvg(A, B, 0, w, h);
+  for (int r = 0; r < h; r++) memcpy(o_y + r * w, D->getLumaAddr() + r * 64, 2 * w);
+  for (int r = 0; r < h / 2; r++) { memcpy(o_u + r * (w / 2), D->getCbAddr() + r * 32, w); memcpy(o_v + r * (w / 2), D->getCrAddr() + r * 32, w); }
 }
 
 } /* extern "C" */

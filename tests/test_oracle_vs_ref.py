@@ -248,3 +248,153 @@ def test_extend_border(orc, hmref):
     orc.orc_extend_border(ptr(a, my * stride + mx), stride, w, h, mx, my)
     hmref.ref_extend_border(ptr(b, my * stride + mx), stride, w, h, mx, my)
     assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# motion search and motion compensation: the restatement against the reference's own TEncSearch /
+# TComPrediction members (xSetSearchRange, xTZSearch, xPatternSearch, xPatternSearchFracDIF,
+# xPredInterLumaBlk / xPredInterChromaBlk, TComYuv::addAvg)
+def _census():
+    out = []
+    for depth in range(4):
+        s = 64 >> depth
+        for cy in range(0, 64, s):
+            for cx in range(0, 64, s):
+                parts = [(0, 0, s, s), (0, 0, s, s // 2), (0, s // 2, s, s // 2), (0, 0, s // 2, s), (s // 2, 0, s // 2, s)]
+                if s >= 16:
+                    q = s // 4
+                    parts += [(0, 0, s, q), (0, q, s, s - q), (0, 0, s, s - q), (0, s - q, s, q),
+                              (0, 0, q, s), (q, 0, s - q, s), (0, 0, s - q, s), (s - q, 0, q, s)]
+                for (x, y, w, h) in parts:
+                    out.append((cx + x, cy + y, w, h, cx, cy))
+    return out
+
+
+def _padded(rng, w, h, bd, kind):
+    import synth
+    if kind == "noise":
+        return synth.random_pic(rng, w, h, bd)
+    seq = synth.make_sequence(w, h, 2, seed=int(rng.integers(1, 1 << 30)), bit_depth=bd)
+    return synth.to_hostpic(seq[0], w, h), synth.to_hostpic(seq[1], w, h)
+
+
+def test_census_matches_abi_order(orc):
+    c = np.zeros((593, 6), np.int16)
+    orc.orc_census(c.ctypes.data_as(C.c_void_p))
+    assert [tuple(int(v) for v in r) for r in c] == _census()
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_motion_search_vs_reference(orc, hmref, bd):
+    W, H = 416, 240
+    hmref.ref_init(bd)
+    rng = np.random.default_rng(400 + bd)
+    census = _census()
+    lam = 57.908390
+    lc = orc.orc_lambda_motion_sad(lam)
+    checked = 0
+    for content in ("synthetic", "noise"):
+        if content == "noise":
+            cur, ref = _padded(rng, W, H, bd, "noise"), _padded(rng, W, H, bd, "noise")
+        else:
+            ref, cur = _padded(rng, W, H, bd, "synthetic")
+        for fen in (1, 0):
+            for had in (1, 0):
+                hmref.ref_me_setup(W, H, 64, fen, had)
+                for trial in range(70 if content == "synthetic" else 30):
+                    ctu = int(rng.integers(0, 7 * 4))
+                    x0, y0 = (ctu % 7) * 64, (ctu // 7) * 64
+                    px, py, w, h, cux, cuy = census[int(rng.integers(0, 593))]
+                    x, y = x0 + px, y0 + py
+                    if x + w > W or y + h > H:
+                        continue
+                    predx, predy = (int(v) for v in rng.integers(-60, 61, 2))
+                    if trial % 5 == 4:
+                        predx, predy = (int(v) for v in rng.integers(-520, 521, 2))
+                    if trial % 17 == 16:
+                        predx, predy = -4000, 4000
+                    g = oracle.CuGeom(W, H, x0 + cux, y0 + cuy, 64)
+                    lx, ty, rx, by = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+                    orc.orc_set_search_range(C.byref(g), predx, predy, 64, C.byref(lx), C.byref(ty), C.byref(rx), C.byref(by))
+                    r4 = (C.c_int * 4)()
+                    hmref.ref_set_search_range(x0 + cux, y0 + cuy, predx, predy, 64, r4)
+                    assert (lx.value, ty.value, rx.value, by.value) == tuple(r4)
+                    o = ptr(cur.buf_y, cur.origin(0) + y * cur.stride + x)
+                    r = ptr(ref.buf_y, ref.origin(0) + y * ref.stride + x)
+                    # integer stage: TZ on the full window; exhaustive on a +-4 window (bi-pred refinement size)
+                    e = oracle.MeResult()
+                    orc.orc_tz_search(C.byref(g), o, cur.stride, r, ref.stride, w, h, lx.value, ty.value, rx.value, by.value,
+                                      64, fen, bd - 8, lc, predx, predy, predx, predy, C.byref(e))
+                    o3 = (C.c_int * 3)()
+                    hmref.ref_int_search(1, o, cur.stride, r, ref.stride, w, h, x0 + cux, y0 + cuy, lx.value, ty.value, rx.value,
+                                         by.value, lam, predx, predy, predx, predy, o3)
+                    assert (e.mvx, e.mvy, e.sad) == (o3[0], o3[1], o3[2] & 0xffffffff), ("tz", content, fen, x, y, w, h, predx, predy)
+                    l4 = (C.c_int * 4)()
+                    hmref.ref_set_search_range(x0 + cux, y0 + cuy, predx, predy, 4, l4)
+                    orc.orc_pattern_search(o, cur.stride, r, ref.stride, w, h, l4[0], l4[1], l4[2], l4[3], fen, bd - 8, lc, predx, predy,
+                                           C.byref(e))
+                    hmref.ref_int_search(0, o, cur.stride, r, ref.stride, w, h, x0 + cux, y0 + cuy, l4[0], l4[1], l4[2], l4[3],
+                                         lam, predx, predy, predx, predy, o3)
+                    assert (e.mvx, e.mvy, e.sad) == (o3[0], o3[1], o3[2] & 0xffffffff), ("full", content, fen, x, y, w, h)
+                    # fractional stage at the integer MV the search found
+                    f = oracle.FracResult()
+                    orc.orc_frac_search(o, cur.stride, r, ref.stride, w, h, e.mvx, e.mvy, had, bd - 8, bd, lc, predx, predy, C.byref(f))
+                    o5 = (C.c_int * 5)()
+                    hmref.ref_frac_search(o, cur.stride, r, ref.stride, w, h, e.mvx, e.mvy, lam, predx, predy, o5)
+                    assert (f.halfx, f.halfy, f.qtrx, f.qtry, f.cost) == (o5[0], o5[1], o5[2], o5[3], o5[4] & 0xffffffff), \
+                        ("frac", content, had, x, y, w, h, e.mvx, e.mvy)
+                    checked += 1
+    assert checked > 300
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_motion_compensation_vs_reference(orc, hmref, bd):
+    W, H = 416, 240
+    hmref.ref_init(bd)
+    hmref.ref_me_setup(W, H, 64, 1, 1)
+    rng = np.random.default_rng(500 + bd)
+    ref = _padded(rng, W, H, bd, "noise")
+    assert ref.stride == W + 160 and ref.buf_y.shape[0] == H + 160
+    hmref.ref_mc_set_ref(ptr(ref.buf_y), ptr(ref.buf_u), ptr(ref.buf_v), W, H)
+    census = _census()
+    n = 0
+    for trial in range(300):
+        ctu = int(rng.integers(0, 7 * 3))
+        x0, y0 = (ctu % 7) * 64, (ctu // 7) * 64
+        px, py, w, h, cux, cuy = census[int(rng.integers(0, 593))]
+        x, y = x0 + px, y0 + py
+        if x + w > W or y + h > H:
+            continue
+        mv = [int(v) for v in rng.integers(-300, 300, 2)]
+        if trial % 7 == 0:
+            mv[0] &= ~3
+        if trial % 11 == 0:
+            mv[1] &= ~3
+        if trial % 13 == 0:
+            mv = [-4000, 4000]
+        g = oracle.CuGeom(W, H, x0 + cux, y0 + cuy, 64)
+        a, b = C.c_int(mv[0]), C.c_int(mv[1])
+        orc.orc_clip_mv(C.byref(g), C.byref(a), C.byref(b))
+        mvx, mvy = a.value, b.value
+        outs = {}
+        for bi in (0, 1):
+            ey = np.zeros((h, w), np.int16); eu = np.zeros((h // 2, w // 2), np.int16); ev = np.zeros_like(eu)
+            orc.orc_pred_inter_luma_blk(ptr(ref.buf_y, ref.origin(0) + y * ref.stride + x), ref.stride, mvx, mvy, w, h, ptr(ey), w, bi, bd)
+            co = ref.origin(1) + (y // 2) * ref.cstride + x // 2
+            orc.orc_pred_inter_chroma_blk(ptr(ref.buf_u, co), ref.cstride, mvx, mvy, w, h, ptr(eu), w // 2, bi, bd)
+            orc.orc_pred_inter_chroma_blk(ptr(ref.buf_v, co), ref.cstride, mvx, mvy, w, h, ptr(ev), w // 2, bi, bd)
+            ry = np.zeros((h, w), np.int16); ru = np.zeros((h // 2, w // 2), np.int16); rv = np.zeros_like(ru)
+            hmref.ref_mc_pu(x, y, w, h, mvx, mvy, bi, ptr(ry), ptr(ru), ptr(rv))
+            assert np.array_equal(ey, ry) and np.array_equal(eu, ru) and np.array_equal(ev, rv), (bi, x, y, w, h, mvx, mvy)
+            outs[bi] = (ey, eu, ev)
+        # bi-prediction average of the 14-bit prediction with a shifted copy of itself
+        a14 = outs[1]
+        b14 = tuple(np.ascontiguousarray(np.roll(p, 1, axis=1)) for p in a14)
+        oy = np.zeros((h, w), np.int16); ou = np.zeros((h // 2, w // 2), np.int16); ov = np.zeros_like(ou)
+        hmref.ref_add_avg(ptr(a14[0]), ptr(a14[1]), ptr(a14[2]), ptr(b14[0]), ptr(b14[1]), ptr(b14[2]), w, h, ptr(oy), ptr(ou), ptr(ov))
+        for pa, pb, po, (ww, hh) in ((a14[0], b14[0], oy, (w, h)), (a14[1], b14[1], ou, (w // 2, h // 2)), (a14[2], b14[2], ov, (w // 2, h // 2))):
+            e = np.zeros((hh, ww), np.int16)
+            orc.orc_add_avg(ptr(pa), ww, ptr(pb), ww, ptr(e), ww, ww, hh, bd)
+            assert np.array_equal(e, po)
+        n += 1
+    assert n > 150
