@@ -1,0 +1,72 @@
+"""Write patched copies of the few reference translation units that get a TLibCuda hook into a build
+directory.  The reference sources are read where they lie (never copied into this repository); every
+patch is a one-line insertion at a uniquely matching anchor, asserted below.
+
+usage: patch_hm.py <reference root> <output dir>
+"""
+import os
+import re
+import sys
+
+
+def rd(path):
+    # bytes preserved one to one (the reference mixes line endings and has a few non-ASCII comment bytes)
+    return open(path, encoding="latin-1", newline="").read()
+
+
+def wr(path, text):
+    open(path, "w", encoding="latin-1", newline="").write(text)
+
+
+def sub_once(text, pattern, repl, name, flags=0):
+    new, n = re.subn(pattern, repl, text, count=0, flags=flags)
+    assert n == 1, "%s: anchor matched %d times" % (name, n)
+    return new
+
+
+def main():
+    ref, out = sys.argv[1], sys.argv[2]
+    lib = os.path.join(ref, "source", "Lib")
+    os.makedirs(os.path.join(out, "TLibCommon"), exist_ok=True)
+    os.makedirs(os.path.join(out, "TLibEncoder"), exist_ok=True)
+
+    # ---- TEncSearch.cpp: xTZSearch and xPatternSearchFracDIF
+    s = rd(os.path.join(lib, "TLibEncoder", "TEncSearch.cpp"))
+    s = sub_once(s, r'(#include "TEncSearch.h"\r?\n)', r'\1#include "tlibcuda_hm.h"\n', "TEncSearch include")
+    s = sub_once(s, r'(Void TEncSearch::xTZSearch\( TComDataCU\* pcCU,[^\n]*\r?\n\{\r?\n)',
+                 r'\1  if ( tlibcuda_tz_search( pcCU, pcPatternKey, piRefY, iRefStride, pcMvSrchRngLT, pcMvSrchRngRB, rcMv, ruiSAD, m_pcRdCost, m_pcEncCfg, m_iSearchRange ) ) return;\n',
+                 "xTZSearch")
+    s = sub_once(s, r'(Void TEncSearch::xPatternSearchFracDIF\(TComDataCU\* pcCU,.*?\n\s*\)\r?\n\{\r?\n)',
+                 r'\1  if ( tlibcuda_frac_search( pcPatternKey, piRefY, iRefStride, pcMvInt, rcMvHalf, rcMvQter, ruiCost, m_pcRdCost, m_pcEncCfg, biPred ) ) return;\n',
+                 "xPatternSearchFracDIF", flags=re.S)
+    wr(os.path.join(out, "TLibEncoder", "TEncSearch.cpp"), s)
+
+    # ---- TEncGOP.cpp: picture-start hook before the slice is compressed
+    s = rd(os.path.join(lib, "TLibEncoder", "TEncGOP.cpp"))
+    s = sub_once(s, r'(#include "TEncGOP.h"\r?\n)', r'\1#include "tlibcuda_hm.h"\n', "TEncGOP include")
+    s = sub_once(s, r'(\n)([ \t]*m_pcSliceEncoder->precompressSlice\( pcPic \);\r?\n)',
+                 r'\1        tlibcuda_picture_start( pcPic, pcSlice );\n\2', "compressGOP")
+    wr(os.path.join(out, "TLibEncoder", "TEncGOP.cpp"), s)
+
+    # ---- AnnexBwrite.h: gcc portability (non-const reference to an rvalue)
+    s = rd(os.path.join(lib, "TLibEncoder", "AnnexBwrite.h"))
+    s = sub_once(s, r'string &P = nalu\.m_nalUnitData\.str\(\);', 'const string &P = nalu.m_nalUnitData.str();', "AnnexBwrite")
+    wr(os.path.join(out, "TLibEncoder", "AnnexBwrite.h"), s)
+
+    # ---- TComTrQuant.cpp: xT, xIT, xDeQuant hooks + two MSVC for-scope uses gcc rejects
+    s = rd(os.path.join(lib, "TLibCommon", "TComTrQuant.cpp"))
+    s = sub_once(s, r'(#include "TComTrQuant.h"\r?\n)', r'\1#include "tlibcuda_hm.h"\n', "TComTrQuant include")
+    s = sub_once(s, r'for \(Int iCGScanPos = uiCGNum-1;', 'Int iCGScanPos; for (iCGScanPos = uiCGNum-1;', "for-scope 1")
+    s = sub_once(s, r'for \( Int scanPos = 0; scanPos < iBestLastIdxP1;', 'Int scanPos; for ( scanPos = 0; scanPos < iBestLastIdxP1;', "for-scope 2")
+    s = sub_once(s, r'(Void TComTrQuant::xT\( UInt uiMode, Pel\* piBlkResi, UInt uiStride, Int\* psCoeff, Int iWidth, Int iHeight \)\r?\n\{\r?\n)',
+                 r'\1  if ( tlibcuda_xT( uiMode, piBlkResi, uiStride, psCoeff, iWidth, iHeight ) ) return;\n', "xT")
+    s = sub_once(s, r'(Void TComTrQuant::xIT\( UInt uiMode, Int\* plCoef, Pel\* pResidual, UInt uiStride, Int iWidth, Int iHeight \)\r?\n\{\r?\n)',
+                 r'\1  if ( tlibcuda_xIT( uiMode, plCoef, pResidual, uiStride, iWidth, iHeight ) ) return;\n', "xIT")
+    s = sub_once(s, r'(Void TComTrQuant::xDeQuant\( const TCoeff\* pSrc, Int\* pDes, Int iWidth, Int iHeight, Int scalingListType \)\r?\n\{\r?\n)',
+                 r'\1  if ( !getUseScalingList() && tlibcuda_xDeQuant( pSrc, pDes, iWidth, iHeight, m_cQP.m_iPer, m_cQP.m_iRem ) ) return;\n', "xDeQuant")
+    wr(os.path.join(out, "TLibCommon", "TComTrQuant.cpp"), s)
+    print("patched 4 files into", out)
+
+
+if __name__ == "__main__":
+    main()

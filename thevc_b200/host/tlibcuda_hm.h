@@ -1,0 +1,41 @@
+/*
+ * tlibcuda_hm.h -- hook points that bind HM 7.2 (fr34k8/thevc) to libthevc_cuda.so.
+ *
+ * This header and tlibcuda_hm.cpp are the "source/Lib/TLibCuda" shim of INTEGRATION.md.  They are
+ * compiled together with the reference's own sources (taken where they lie, patched on the fly by
+ * patch_hm.py; see Makefile) into build/hm/TAppEncoderCuda.  Each hook replaces the body of one
+ * reference member and returns true when the CUDA path produced the result; it returns false only
+ * for cases this round does not port (bi-prediction search, scaling lists), in which case the
+ * reference's own code below the hook runs -- that is the reference's implementation, not a CPU
+ * fallback of ours.  A CUDA error is fatal (exit(EXIT_FAILURE)), like the reference's own errors.
+ *
+ * Which hooks are active is chosen with the environment variable TVC_HM (comma list of
+ * me,frac,tq,tables; default "me,frac,tq,tables"; "none" runs the unmodified path).
+ */
+#ifndef TLIBCUDA_HM_H
+#define TLIBCUDA_HM_H
+
+class TComDataCU;
+class TComPattern;
+class TComMv;
+class TComRdCost;
+class TEncCfg;
+class TComPic;
+class TComSlice;
+
+/* TEncGOP::compressGOP, before compressSlice (TEncGOP.cpp:576): upload the current original and every
+ * reference reconstruction (final + border-extended at this point), run the SAD-table pre-pass */
+void tlibcuda_picture_start(TComPic* pic, TComSlice* slice);
+
+/* TEncSearch::xTZSearch (TEncSearch.cpp:4302) */
+bool tlibcuda_tz_search(TComDataCU* cu, TComPattern* key, short* refY, int refStride, TComMv* lt, TComMv* rb, TComMv& rcMv,
+                        unsigned& ruiSAD, TComRdCost* rd, TEncCfg* cfg, int searchRange);
+/* TEncSearch::xPatternSearchFracDIF (TEncSearch.cpp:4476) */
+bool tlibcuda_frac_search(TComPattern* key, short* refY, int refStride, TComMv* mvInt, TComMv& half, TComMv& qter,
+                          unsigned& ruiCost, TComRdCost* rd, TEncCfg* cfg, bool biPred);
+/* TComTrQuant::xT / xIT / xDeQuant (TComTrQuant.cpp:1542, 1583, 1272) */
+bool tlibcuda_xT(unsigned mode, short* resi, unsigned stride, int* coef, int w, int h);
+bool tlibcuda_xIT(unsigned mode, int* coef, short* resi, unsigned stride, int w, int h);
+bool tlibcuda_xDeQuant(const int* src, int* dst, int w, int h, int per, int rem);
+
+#endif
