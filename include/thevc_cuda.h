@@ -148,8 +148,8 @@ int tvc_mc_batch_dev(tvc_ctx* ctx, int dst_slot, int n, const tvc_pu* pus_dev);
  * is a sum of its blocks' entries, so decisions are those of xGetSAD* (TComRdCost.cpp:518-989).
  * 8-bit pictures only (u8 SIMD path).
  *
- * Table layout (uint16): T[ref][ctu][by 16][parity 2][cand 129*129][bx 16]; cand = (dy+R)*129+(dx+R),
- * R = TVC_ME_RANGE, dx/dy relative to the CTU's centre.                                        */
+ * Table layout (uint16): T[ref][ctu][cand 129*129][by 16][q 4][parity 2][bx 4]; cand = (dy+R)*129+(dx+R),
+ * R = TVC_ME_RANGE, dx/dy relative to the CTU's centre; 1 KB per candidate, 17.04 MB per (ref, CTU).  */
 #define TVC_ME_RANGE 64
 #define TVC_ME_CAND  (2 * TVC_ME_RANGE + 1)
 

@@ -55,6 +55,9 @@ def _md5(path):
     ("encoder_lowdelay_P_main.cfg", 3, ()),                 # C2 at the CPU-runnable size: ME + frac + transforms on the GPU
     ("encoder_intra_main.cfg", 2, ()),                      # C1: transforms / dequant only
     ("encoder_lowdelay_P_main.cfg", 2, ("--RDOQ=0",)),      # non-RDOQ quantiser path of the host around the GPU transforms
+    ("encoder_randomaccess_main.cfg", 5, ()),               # C3 (B slices): uni-pred searches on the GPU, bi-pred refinement on the reference path
+    ("encoder_intra_he10.cfg", 2, ()),                      # C4: 10-bit internal (bitIncrement 2) transforms / dequant
+    ("encoder_lowdelay_main.cfg", 3, ()),                   # low-delay B with 10-bit off: generalised B pictures
 ])
 def test_bitstream_md5_identical_to_reference(tmp_path, cfg, frames, extra):
     _need()

@@ -128,24 +128,23 @@ struct ProfScope {
 };
 
 // ---- table layout of the ME pre-pass (shared by producer and consumers) ----------------------
-// T[ref][ctu][by 16][q 4][slot 129*129][par 2][bx 4] uint16.  Within one dy row the 129 dx values
-// are stored permuted so that the 8 candidates a producer warp handles together (equal dx mod 16)
-// are adjacent: slot(dx) = ((dx+64)&15)*8 + ((dx+64)>>4) for dx < 64, and 128 for dx == +64.
+// T[ref][ctu][cand 129*129][by 16][q 4][par 2][bx 4] uint16: one candidate = 1 KB contiguous
+// (cand = (dy+64)*129 + (dx+64)); inside it block row `by`, then the 16-column quarter `q`, then one
+// 16-byte granule = even-row SADs of the quarter's four 4x4 blocks followed by their odd-row SADs.
+// Producer: the four lanes of one dx write 64 contiguous bytes per block row (full sectors);
+// consumers: a PU's granules of one candidate all lie inside that candidate's 1 KB, a full-candidate
+// read (raster pre-pass) is one coalesced 1 KB load.
 constexpr int kMeR = TVC_ME_RANGE;
 constexpr int kMeC = TVC_ME_CAND;                       // 129
 constexpr int kMeCands = kMeC * kMeC;                   // 16641
 constexpr size_t kMeGranule = 8;                        // uint16 per (cand, by, q): par 2 x bx 4
-constexpr size_t kMeCtuElems = (size_t)16 * 4 * kMeCands * kMeGranule;   // uint16 per (ref, ctu)
+constexpr int kMeCandGranules = 64;                     // granules per candidate (16 block rows x 4 quarters)
+constexpr size_t kMeCtuElems = (size_t)kMeCands * kMeCandGranules * kMeGranule;   // uint16 per (ref, ctu)
 
-__host__ __device__ inline int me_dx_slot(int dx)
+// granule index of (candidate, block row, quarter) inside one (ref, ctu) table
+__host__ __device__ inline uint32_t me_granule(int dy, int dx, int by, int q)
 {
-  int u = dx + kMeR;
-  return (u == 2 * kMeR) ? 2 * kMeR : ((u & 15) * 8 + (u >> 4));
-}
-// element index (uint16 units) inside one (ref, ctu) table
-__host__ __device__ inline size_t me_entry(int by, int q, int dy, int dx)
-{
-  return (((size_t)(by * 4 + q) * kMeCands) + (size_t)(dy + kMeR) * kMeC + me_dx_slot(dx)) * kMeGranule;
+  return (uint32_t)(((dy + kMeR) * kMeC + (dx + kMeR)) * kMeCandGranules + by * 4 + q);
 }
 
 }  // namespace tvc

@@ -77,7 +77,7 @@ __device__ __forceinline__ uint32_t vsad4_acc(uint32_t a, uint32_t b, uint32_t c
 // 16-byte chunk, SH = (align16 & 3) * 8 the funnel shift; both warp-uniform.
 template <int DYB, int WO>
 __device__ __forceinline__ void sad_task(const uint8_t* __restrict__ win, const uint8_t* __restrict__ cur, int X, int SH,
-                                         int dyb, int q, bool active, uint16_t* __restrict__ tbl, int dxslot)
+                                         int dyb, int q, bool active, uint16_t* __restrict__ tbl, int dxc)
 {
   const uint8_t* wbase = win + (X & ~15);
   const uint8_t* cbase = cur + 16 * q;
@@ -121,7 +121,7 @@ __device__ __forceinline__ void sad_task(const uint8_t* __restrict__ win, const 
           o.y = E[d][2] | (E[d][3] << 16);
           o.z = O[d][0] | (O[d][1] << 16);
           o.w = O[d][2] | (O[d][3] << 16);
-          size_t e = (((size_t)(by * 4 + q) * kMeCands) + (size_t)(dyb + d) * kMeC + dxslot) * kMeGranule;
+          size_t e = ((size_t)((dyb + d) * kMeC + dxc) * kMeCandGranules + by * 4 + q) * kMeGranule;
           *reinterpret_cast<uint4*>(tbl + e) = o;
         }
       }
@@ -131,13 +131,13 @@ __device__ __forceinline__ void sad_task(const uint8_t* __restrict__ win, const 
 
 template <int DYB>
 __device__ __forceinline__ void sad_task_wo(int wo, const uint8_t* win, const uint8_t* cur, int X, int SH, int dyb, int q,
-                                            bool active, uint16_t* tbl, int dxslot)
+                                            bool active, uint16_t* tbl, int dxc)
 {
   switch (wo) {
-    case 0: sad_task<DYB, 0>(win, cur, X, SH, dyb, q, active, tbl, dxslot); break;
-    case 1: sad_task<DYB, 1>(win, cur, X, SH, dyb, q, active, tbl, dxslot); break;
-    case 2: sad_task<DYB, 2>(win, cur, X, SH, dyb, q, active, tbl, dxslot); break;
-    default: sad_task<DYB, 3>(win, cur, X, SH, dyb, q, active, tbl, dxslot); break;
+    case 0: sad_task<DYB, 0>(win, cur, X, SH, dyb, q, active, tbl, dxc); break;
+    case 1: sad_task<DYB, 1>(win, cur, X, SH, dyb, q, active, tbl, dxc); break;
+    case 2: sad_task<DYB, 2>(win, cur, X, SH, dyb, q, active, tbl, dxc); break;
+    default: sad_task<DYB, 3>(win, cur, X, SH, dyb, q, active, tbl, dxc); break;
   }
 }
 
@@ -176,11 +176,11 @@ k_me_sad_tables(const __grid_constant__ MeMaps maps, int num_ctus, int ctus_x, i
     if (t < 256) {
       int a = t & 15, g = t >> 4;
       int u = a + 16 * i8, al = (a + e) & 15;
-      sad_task_wo<8>(al >> 2, win, cur, u + 16 * q + e, (al & 3) * 8, g * 8, q, true, tbl, a * 8 + i8);
+      sad_task_wo<8>(al >> 2, win, cur, u + 16 * q + e, (al & 3) * 8, g * 8, q, true, tbl, u);
     } else if (t < 272) {
       int a = t - 256;
       int u = a + 16 * i8, al = (a + e) & 15;
-      sad_task_wo<1>(al >> 2, win, cur, u + 16 * q + e, (al & 3) * 8, 128, q, true, tbl, a * 8 + i8);
+      sad_task_wo<1>(al >> 2, win, cur, u + 16 * q + e, (al & 3) * 8, 128, q, true, tbl, u);
     } else if (t < 274) {
       int g = (t - 272) * 8 + i8;
       sad_task_wo<8>(e >> 2, win, cur, 128 + 16 * q + e, (e & 3) * 8, g * 8, q, true, tbl, 128);
@@ -199,10 +199,9 @@ __device__ __forceinline__ uint32_t table_pu_sad_partial(const uint16_t* __restr
   const int q0 = bx0 >> 2, q1 = (bx0 + nbx - 1) >> 2, nq = q1 - q0 + 1;
   const int total = nby * nq;
   uint32_t acc = 0;
-  const size_t cand = (size_t)(dy + kMeR) * kMeC + me_dx_slot(dx);
   for (int i = lane; i < total; i += 32) {
     int by = by0 + i / nq, q = q0 + i % nq;
-    const uint4 g = *reinterpret_cast<const uint4*>(tbl + (((size_t)(by * 4 + q) * kMeCands) + cand) * kMeGranule);
+    const uint4 g = *reinterpret_cast<const uint4*>(tbl + (size_t)me_granule(dy, dx, by, q) * kMeGranule);
     uint32_t ev[4] = {g.x & 0xffffu, g.x >> 16, g.y & 0xffffu, g.y >> 16};
     uint32_t od[4] = {g.z & 0xffffu, g.z >> 16, g.w & 0xffffu, g.w >> 16};
 #pragma unroll
@@ -299,13 +298,12 @@ __device__ __forceinline__ void eval_multi(const SearchCtx& s, const bool (&vali
     tab[k] = valid[k] && cov;
     direct[k] = valid[k] && !cov;
     any_direct |= direct[k];
-    const uint32_t cand = tab[k] ? (uint32_t)((dy + kMeR) * kMeC + me_dx_slot(dx)) : 0u;
-    base[k] = cand + (uint32_t)(s.by0 * 4 + s.q0) * kMeCands;
+    base[k] = tab[k] ? me_granule(dy, dx, s.by0, s.q0) : 0u;
     sad[k] = 0;
   }
   const uint4* __restrict__ tg = reinterpret_cast<const uint4*>(s.tbl);
-  constexpr uint32_t kRow = 4u * kMeCands;      // next block row, same quarter (granules)
-  constexpr uint32_t kQtr = (uint32_t)kMeCands; // next quarter, same block row
+  constexpr uint32_t kRow = 4u;                 // next block row, same quarter (granules)
+  constexpr uint32_t kQtr = 1u;                 // next quarter, same block row
   const bool all = s.sub == 0;
 #pragma unroll
   for (int qi = 0; qi < 4; qi++) {
