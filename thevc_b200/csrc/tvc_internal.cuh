@@ -70,6 +70,7 @@ struct tvc_ctx {
   tvc_me_result* fr_int = nullptr;
   tvc_frac_job* fr_fjobs = nullptr;
   tvc_frac_result* fr_frac = nullptr;
+  void* fr_rast = nullptr;        // shared raster-stage results (RasterBest per job)
   size_t fr_cap = 0;              // entries
   // dedicated pinned staging of the asynchronous ME entry points (an event guards host reuse)
   tvc::Scratch me_stage, fr_stage;

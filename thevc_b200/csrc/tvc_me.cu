@@ -220,6 +220,8 @@ __device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v)
   return v;
 }
 
+__constant__ tvc_census_pu c_census[TVC_ME_CENSUS];     // partition census of a CTU (frame pre-pass)
+
 // ================================================================================ (2) search
 // One warp per PU job, ONE LANE PER CANDIDATE.  The reference evaluates candidates one after the
 // other (xTZSearchHelp, TEncSearch.cpp:312-349: strict '<' against the running best), but inside a
@@ -520,11 +522,122 @@ __device__ __forceinline__ void raster_scan(SearchCtx& s, int step, uint32_t dis
   }
 }
 
+// ================================================================================ (2b) shared raster stage
+// In the frame pre-pass every PU of a CTU searches the same window around the same predictor, and
+// the TZ raster stage (TEncSearch.cpp:4389-4400: every 5th candidate of the whole window, taken by
+// about half of the PUs and then ~80% of all their SAD evaluations) visits the SAME candidates for all
+// 593 PUs.  k_me_raster therefore walks the raster once per (CTU, reference): each candidate is one
+// coalesced 1 KB read; its 256 even-row and 256 odd-row block SADs are turned into two 17x17 integral
+// images in shared memory, from which every PU's SAD is four look-ups; each PU thread keeps the
+// running (cost, first index) minimum in visiting order with strict '<' -- the state xTZSearchHelp
+// would reach.  k_me_search consumes the result when its own window equals the CTU's.
+struct RasterBest { uint32_t cost; int32_t idx; };
+constexpr int kRastChunk = 4;                   // candidates per iteration
+constexpr int kRastThreads = 640;               // >= TVC_ME_CENSUS PU threads
+
+__global__ void __launch_bounds__(kRastThreads)
+k_me_raster(const tvc_me_job* __restrict__ jobs, const uint16_t* __restrict__ tables, const tvc_me_center* __restrict__ centers,
+            int num_ctus, int raster, int bi, RasterBest* __restrict__ out)
+{
+  __shared__ uint32_t IE[kRastChunk][17 * 17];  // integral of even-row block SADs
+  __shared__ uint32_t IA[kRastChunk][17 * 17];  // integral of even+odd
+  __shared__ uint32_t s_mvc[kRastChunk];
+  const int ctu = blockIdx.x, ref = blockIdx.y, tid = threadIdx.x;
+  const size_t rc = (size_t)ref * num_ctus + ctu;
+  const tvc_me_job* jb0 = jobs + rc * TVC_ME_CENSUS;
+  const tvc_me_job j0 = jb0[0];                  // the 64x64 PU: its window is the CTU's
+  RasterBest* o = out + rc * TVC_ME_CENSUS;
+  const tvc_me_center cen = centers[rc];
+  const int nx = (j0.rx - j0.lx) / raster + 1, ny = (j0.by - j0.ty) / raster + 1, N = nx * ny;
+  const int x_last = j0.lx + (nx - 1) * raster, y_last = j0.ty + (ny - 1) * raster;
+  const bool covered = j0.w > 0 && j0.mode == TVC_ME_TZ && j0.lx - cen.cx >= -kMeR && x_last - cen.cx <= kMeR &&
+                       j0.ty - cen.cy >= -kMeR && y_last - cen.cy <= kMeR;
+  if (!covered) {                                // partial CTU / window leaves the table: every PU rasters on its own
+    for (int k = tid; k < TVC_ME_CENSUS; k += kRastThreads) o[k] = RasterBest{kNoCost, -1};
+    return;
+  }
+  const uint4* __restrict__ tg = reinterpret_cast<const uint4*>(tables + rc * kMeCtuElems);
+  // this thread's PU
+  const bool is_pu = tid < TVC_ME_CENSUS;
+  const tvc_census_pu cp = c_census[is_pu ? tid : 0];
+  const bool pu_ok = is_pu && jb0[is_pu ? tid : 0].w > 0;
+  const int bx0 = cp.x >> 2, by0 = cp.y >> 2, bx1 = (cp.x + cp.w) >> 2, by1 = (cp.y + cp.h) >> 2;
+  const int sub = (j0.fen && cp.h > 8) ? 1 : 0;
+  const int c00 = by0 * 17 + bx0, c01 = by0 * 17 + bx1, c10 = by1 * 17 + bx0, c11 = by1 * 17 + bx1;
+  uint32_t best = kNoCost;
+  int best_i = -1;
+  // loader role: thread t < 256 fetches granule (t & 63) of candidate (t >> 6) of the chunk
+  const int lc = tid >> 6, lg = tid & 63;
+  auto fetch = [&](int base) -> uint4 {
+    const int i = base + lc;
+    if (tid >= 64 * kRastChunk || i >= N) return make_uint4(0, 0, 0, 0);
+    const int iy = i / nx, ix = i - iy * nx;
+    const int dx = j0.lx + ix * raster - cen.cx, dy = j0.ty + iy * raster - cen.cy;
+    return __ldg(tg + me_granule(dy, dx, 0, 0) + lg);
+  };
+  if (tid < 17 * kRastChunk) {                   // zero row / column of the integrals
+    const int c = tid / 17, k = tid % 17;
+    IE[c][k] = 0; IA[c][k] = 0; IE[c][k * 17] = 0; IA[c][k * 17] = 0;
+  }
+  uint4 g = fetch(0);
+  for (int base = 0; base < N; base += kRastChunk) {
+    // (1) scatter the granule: block row lg >> 2, blocks 4*(lg & 3) .. +3
+    if (tid < 64 * kRastChunk) {
+      const int by = lg >> 2, bx = (lg & 3) * 4;
+      uint32_t* e = &IE[lc][(by + 1) * 17 + bx + 1];
+      uint32_t* a = &IA[lc][(by + 1) * 17 + bx + 1];
+      const uint32_t e0 = g.x & 0xffffu, e1 = g.x >> 16, e2 = g.y & 0xffffu, e3 = g.y >> 16;
+      e[0] = e0; e[1] = e1; e[2] = e2; e[3] = e3;
+      a[0] = e0 + (g.z & 0xffffu); a[1] = e1 + (g.z >> 16); a[2] = e2 + (g.w & 0xffffu); a[3] = e3 + (g.w >> 16);
+    } else if (tid < 64 * kRastChunk + kRastChunk) {
+      const int c = tid - 64 * kRastChunk, i = base + c;
+      if (i < N) {
+        const int iy = i / nx, ix = i - iy * nx;
+        s_mvc[c] = mv_cost(j0.lambda_cost, j0.lx + ix * raster, j0.ty + iy * raster, 2, j0.predx, j0.predy);
+      }
+    }
+    g = fetch(base + kRastChunk);                // next chunk's loads fly during the scans below
+    __syncthreads();
+    // (2) row prefix sums: 2 images x chunk x 16 rows
+    if (tid < 2 * kRastChunk * 16) {
+      const int img = tid / (kRastChunk * 16), c = (tid / 16) % kRastChunk, r = tid % 16;
+      uint32_t* p = (img ? IA[c] : IE[c]) + (r + 1) * 17 + 1;
+      uint32_t s = 0;
+#pragma unroll
+      for (int x = 0; x < 16; x++) { s += p[x]; p[x] = s; }
+    }
+    __syncthreads();
+    // (3) column prefix sums
+    if (tid < 2 * kRastChunk * 16) {
+      const int img = tid / (kRastChunk * 16), c = (tid / 16) % kRastChunk, x = tid % 16;
+      uint32_t* p = (img ? IA[c] : IE[c]) + 17 + x + 1;
+      uint32_t s = 0;
+#pragma unroll
+      for (int r = 0; r < 16; r++) { s += p[r * 17]; p[r * 17] = s; }
+    }
+    __syncthreads();
+    // (4) every PU: cost of the chunk's candidates in visiting order
+    if (pu_ok) {
+#pragma unroll
+      for (int c = 0; c < kRastChunk; c++) {
+        if (base + c < N) {
+          const uint32_t* I = sub ? IE[c] : IA[c];
+          const uint32_t sad = I[c11] - I[c01] - I[c10] + I[c00];
+          const uint32_t cost = ((sad << sub) >> bi) + s_mvc[c];
+          if (cost < best) { best = cost; best_i = base + c; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (is_pu) o[tid] = RasterBest{pu_ok ? best : kNoCost, pu_ok ? best_i : -1};
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB)
 k_me_search(PlaneTable pt, int cur_slot, int n, const tvc_me_job* __restrict__ jobs, tvc_me_result* __restrict__ out,
             const uint16_t* __restrict__ tables, const tvc_me_center* __restrict__ centers, int num_ctus, int ctus_x,
-            int bi)
+            int bi, const RasterBest* __restrict__ rast)
 {
   int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (j >= n) return;
@@ -589,7 +702,24 @@ k_me_search(PlaneTable pt, int cur_slot, int n, const tvc_me_job* __restrict__ j
     if (s.best_dist == 1) { s.best_dist = 0; two_point(s); }   // :4382-4386
     if ((int)s.best_dist > raster) {                           // :4389-4400
       s.best_dist = raster;
-      raster_scan<TVC_RASTER_K>(s, raster, raster);
+      // frame pre-pass: the raster of this PU was walked by k_me_raster if its window is the CTU's
+      bool shared = false;
+      if (rast) {
+        const RasterBest rb = rast[j];
+        const tvc_me_job& j0 = jobs[j - (j % TVC_ME_CENSUS)];
+        shared = rb.idx >= 0 && j0.lx == jb.lx && j0.ty == jb.ty && j0.rx == jb.rx && j0.by == jb.by;
+        if (shared) {
+          const int nx = (s.rx - s.lx) / raster + 1, ny = (s.by - s.ty) / raster + 1;
+          s.n_sads += (uint32_t)(nx * ny);
+          if (rb.cost < s.best_sad) {
+            s.best_sad = rb.cost;
+            s.best_x = s.lx + (rb.idx % nx) * raster;
+            s.best_y = s.ty + (rb.idx / nx) * raster;
+            s.best_dist = raster; s.best_round = 0; s.point_nr = 0;
+          }
+        }
+      }
+      if (!shared) raster_scan<TVC_RASTER_K>(s, raster, raster);
     }
     while (s.best_dist > 0) {                                  // star refinement :4435-4468
       const int sx = s.best_x, sy = s.best_y;
@@ -860,8 +990,6 @@ k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ j
 }
 
 // ================================================================================ (4) frame pre-pass
-__constant__ tvc_census_pu c_census[TVC_ME_CENSUS];
-
 static void build_census(tvc_census_pu* out)
 {
   int n = 0;
@@ -1129,7 +1257,8 @@ int tvc_me_table_lookup(tvc_ctx* c, int ref_index, int pu_x, int pu_y, int pu_w,
   return TVC_OK;
 }
 
-int tvc_me_search_batch_dev(tvc_ctx* c, int cur_slot, int use_tables, int n, const tvc_me_job* jobs_dev, tvc_me_result* out_dev)
+static int launch_search(tvc_ctx* c, int cur_slot, int use_tables, int n, const tvc_me_job* jobs_dev, tvc_me_result* out_dev,
+                         const RasterBest* rast)
 {
   if (!c || !valid_slot(c, cur_slot) || n < 0 || (n && (!jobs_dev || !out_dev))) return set_err(c, TVC_ERR_ARG, "tvc_me_search_batch_dev: bad argument");
   if (use_tables && (!c->me_tables || c->me_num_refs == 0 || c->me_cur_slot != cur_slot))
@@ -1140,12 +1269,17 @@ int tvc_me_search_batch_dev(tvc_ctx* c, int cur_slot, int use_tables, int n, con
   if (variant < 0) { const char* e = getenv("TVC_SEARCH_MINB"); variant = e ? atoi(e) : 4; }
   const uint16_t* tb = use_tables ? c->me_tables : nullptr;
   const int nctu = c->num_ctus_x * c->num_ctus_y;
-  if (variant >= 8) k_me_search<8><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi);
-  else if (variant >= 6) k_me_search<6><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi);
-  else if (variant >= 4) k_me_search<4><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi);
-  else k_me_search<1><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi);
+  if (variant >= 8) k_me_search<8><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast);
+  else if (variant >= 6) k_me_search<6><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast);
+  else if (variant >= 4) k_me_search<4><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast);
+  else k_me_search<1><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast);
   TVC_LAUNCH_CHECK(c);
   return TVC_OK;
+}
+
+int tvc_me_search_batch_dev(tvc_ctx* c, int cur_slot, int use_tables, int n, const tvc_me_job* jobs_dev, tvc_me_result* out_dev)
+{
+  return launch_search(c, cur_slot, use_tables, n, jobs_dev, out_dev, nullptr);
 }
 
 int tvc_me_search_batch(tvc_ctx* c, int cur_slot, int use_tables, int n, const tvc_me_job* jobs, tvc_me_result* out)
@@ -1245,11 +1379,14 @@ int tvc_me_frame_dev(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slot
     if (c->fr_int) cudaFree(c->fr_int);
     if (c->fr_fjobs) cudaFree(c->fr_fjobs);
     if (c->fr_frac) cudaFree(c->fr_frac);
+    if (c->fr_rast) cudaFree(c->fr_rast);
+    c->fr_rast = nullptr;
     c->fr_jobs = nullptr; c->fr_int = nullptr; c->fr_fjobs = nullptr; c->fr_frac = nullptr; c->fr_cap = 0;
     TVC_CUDA(c, cudaMalloc(&c->fr_jobs, n * sizeof(tvc_me_job)));
     TVC_CUDA(c, cudaMalloc(&c->fr_int, n * sizeof(tvc_me_result)));
     TVC_CUDA(c, cudaMalloc(&c->fr_fjobs, n * sizeof(tvc_frac_job)));
     TVC_CUDA(c, cudaMalloc(&c->fr_frac, n * sizeof(tvc_frac_result)));
+    TVC_CUDA(c, cudaMalloc(&c->fr_rast, n * 8));
     c->fr_cap = n;
   }
   // predictors (quarter pels) and table centres (CTU-level clipMv, integer pels) on the host: tiny
@@ -1279,7 +1416,17 @@ int tvc_me_frame_dev(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slot
     k_me_frame_jobs<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(pw, ph, nctu, c->num_ctus_x, num_refs, dslots, dpred, *cfg, c->fr_jobs);
     TVC_LAUNCH_CHECK(c);
   }
-  if ((r = tvc_me_search_batch_dev(c, cur_slot, cfg->use_tables, (int)n, c->fr_jobs, c->fr_int))) return r;
+  const RasterBest* rast = nullptr;
+  static int use_rast = -1;      // tuning knob (TVC_ME_RASTER=0 walks the raster per PU)
+  if (use_rast < 0) { const char* e = getenv("TVC_ME_RASTER"); use_rast = e ? atoi(e) : 1; }
+  if (cfg->use_tables && use_rast) {
+    ProfScope ps(c, TVC_PH_ME_SEARCH);
+    dim3 grd(nctu, num_refs);
+    k_me_raster<<<grd, kRastThreads, 0, c->stream>>>(c->fr_jobs, c->me_tables, c->me_centers, nctu, 5, c->bi, (RasterBest*)c->fr_rast);
+    TVC_LAUNCH_CHECK(c);
+    rast = (const RasterBest*)c->fr_rast;
+  }
+  if ((r = launch_search(c, cur_slot, cfg->use_tables, (int)n, c->fr_jobs, c->fr_int, rast))) return r;
   if (cfg->do_frac) {
     {
       ProfScope ps(c, TVC_PH_OTHER);
