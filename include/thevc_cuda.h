@@ -140,6 +140,13 @@ typedef struct {
 int tvc_mc_batch(tvc_ctx* ctx, int dst_slot, int n, const tvc_pu* pus);
 int tvc_mc_batch_dev(tvc_ctx* ctx, int dst_slot, int n, const tvc_pu* pus_dev);
 
+/* One PU, one reference list, into caller buffers: TComPrediction::xPredInterUni = xPredInterLumaBlk +
+ * xPredInterChromaBlk (TComPrediction.cpp:483-490, 554-645).  (x, y, w, h) luma rectangle, MV already
+ * clipped, dst_* point at the PU's first sample inside a TComYuv.  bi != 0 keeps the 14-bit intermediate
+ * that TComYuv::addAvg averages later (xPredInterBi, :492-552).                                  */
+int tvc_mc_block(tvc_ctx* ctx, int ref_slot, int x, int y, int w, int h, int mvx, int mvy, int bi,
+                 int16_t* dst_y, int stride_y, int16_t* dst_u, int16_t* dst_v, int stride_c);
+
 /* ---------------------------------------------------------------------------------- integer ME
  * (1) Frame pre-pass: SAD tables.  For every CTU of cur_slot and every reference in ref_slots,
  * all 129x129 integer candidates around a per-CTU window centre, at 4x4-block granularity, even
@@ -289,7 +296,10 @@ typedef struct {
   int32_t use_arl;             /* m_bUseAdaptQpSelect: also write ARL coefficients               */
 } tvc_quant_cfg;
 
-/* residual plane (resi_slot) -> forward transform -> Int coefficients (TCoeff raster per TU)   */
+/* Host-pointer entry points copy directly from / into page-locked caller buffers (cudaHostAlloc /
+ * cudaHostRegister) and stage pageable ones.  Elements of a coefficient / level buffer that no TU of the
+ * list covers are unspecified on return.
+ * residual plane (resi_slot) -> forward transform -> Int coefficients (TCoeff raster per TU)   */
 int tvc_fwd_transform_batch(tvc_ctx* ctx, int resi_slot, int n, const tvc_tu* tus, int32_t* coef, size_t coef_elems);
 /* residual -> transform -> quant (+sign hiding): levels, optional ARL, per-TU uiAbsSum          */
 int tvc_fwd_tq_batch(tvc_ctx* ctx, int resi_slot, int n, const tvc_tu* tus, const tvc_quant_cfg* qc,

@@ -274,6 +274,32 @@ def test_mc_batch(ctx8, ctx10, orc, bd):
                 assert np.array_equal(g, exp[plane]), (plane, pu.x, pu.y, pu.w, pu.h, pu.mvx0, pu.mvy0, pu.mvx1, pu.mvy1)
 
 
+@pytest.mark.parametrize("bd", [8, 10])
+def test_mc_block_dropin(ctx8, ctx10, orc, bd):
+    """tvc_mc_block = xPredInterUni (luma + both chroma planes) into caller buffers, final and 14-bit forms"""
+    t = ctx8 if bd == 8 else ctx10
+    rng = np.random.default_rng(45 + bd)
+    ref = _pic(rng, bd)
+    t.upload(1, ref)
+    for k in range(60):
+        w, h = PU_SHAPES[k % len(PU_SHAPES)]
+        x, y = int(rng.integers(0, (W - w) // 4 + 1)) * 4, int(rng.integers(0, (H - h) // 4 + 1)) * 4
+        mv = [int(v) for v in rng.integers(-300, 300, 2)]
+        if k % 7 == 0:
+            mv[0] &= ~3
+        if k % 5 == 0:
+            mv[1] &= ~3
+        mvx, mvy = _clip_mv(orc, x, y, mv[0], mv[1])
+        for bi in (0, 1):
+            gy, gu, gv = t.mc_block(1, x, y, w, h, mvx, mvy, bool(bi))
+            ey = np.zeros((h, w), np.int16); eu = np.zeros((h // 2, w // 2), np.int16); ev = np.zeros_like(eu)
+            orc.orc_pred_inter_luma_blk(optr(ref.buf_y, ref.origin(0) + y * ref.stride + x), ref.stride, mvx, mvy, w, h, optr(ey), w, bi, bd)
+            co = ref.origin(1) + (y // 2) * ref.cstride + x // 2
+            orc.orc_pred_inter_chroma_blk(optr(ref.buf_u, co), ref.cstride, mvx, mvy, w, h, optr(eu), w // 2, bi, bd)
+            orc.orc_pred_inter_chroma_blk(optr(ref.buf_v, co), ref.cstride, mvx, mvy, w, h, optr(ev), w // 2, bi, bd)
+            assert np.array_equal(gy, ey) and np.array_equal(gu, eu) and np.array_equal(gv, ev), (k, bi, x, y, w, h, mvx, mvy)
+
+
 # ----------------------------------------------------------------------------------- integer ME
 def _ctu_pus():
     """all 593 PU rectangles of one CTU, relative to the CTU origin"""

@@ -18,13 +18,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ENC_CUDA = os.path.join(ROOT, "build", "hm", "TAppEncoderCuda")
 ENC_REF = os.path.join(ROOT, "oracle", "_ref", "bin", "TAppEncoderStatic")
 DEC_REF = os.path.join(ROOT, "oracle", "_ref", "bin", "TAppDecoderStatic")
+DEC_CUDA = os.path.join(ROOT, "build", "hm", "TAppDecoderCuda")
 CFG = os.path.join(ROOT, "build", "hm", "cfg")
 
 pytestmark = pytest.mark.gpu
 
 
 def _need():
-    for p in (ENC_CUDA, ENC_REF, DEC_REF):
+    for p in (ENC_CUDA, ENC_REF, DEC_REF, DEC_CUDA):
         if not os.path.exists(p):
             pytest.skip("%s not built (needs /root/reference at build time)" % os.path.relpath(p, ROOT))
 
@@ -57,7 +58,7 @@ def _md5(path):
     ("encoder_lowdelay_P_main.cfg", 2, ("--RDOQ=0",)),      # non-RDOQ quantiser path of the host around the GPU transforms
     ("encoder_randomaccess_main.cfg", 5, ()),               # C3 (B slices): uni-pred searches on the GPU, bi-pred refinement on the reference path
     ("encoder_intra_he10.cfg", 2, ()),                      # C4: 10-bit internal (bitIncrement 2) transforms / dequant
-    ("encoder_lowdelay_main.cfg", 3, ()),                   # low-delay B with 10-bit off: generalised B pictures
+    ("encoder_lowdelay_main.cfg", 2, ()),                   # low-delay B with 10-bit off: generalised B pictures
 ])
 def test_bitstream_md5_identical_to_reference(tmp_path, cfg, frames, extra):
     _need()
@@ -66,7 +67,7 @@ def test_bitstream_md5_identical_to_reference(tmp_path, cfg, frames, extra):
     _yuv(yuv, w, h, frames)
     ref_bin, cuda_bin = str(tmp_path / "ref.bin"), str(tmp_path / "cuda.bin")
     _encode(ENC_REF, cfg, yuv, w, h, frames, ref_bin, extra=extra)
-    r = _encode(ENC_CUDA, cfg, yuv, w, h, frames, cuda_bin, env={"TVC_HM": "me,frac,tq,tables"}, extra=extra)
+    r = _encode(ENC_CUDA, cfg, yuv, w, h, frames, cuda_bin, env={"TVC_HM": "me,frac,tq,mc,tables"}, extra=extra)
     served = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda:")]
     assert served and "kernel launches" in served[-1], r.stderr[-500:]
     print(served[-1])
@@ -79,3 +80,12 @@ def test_bitstream_md5_identical_to_reference(tmp_path, cfg, frames, extra):
     d = subprocess.run([DEC_REF, "-b", cuda_bin, "-o", str(tmp_path / "dec.yuv")], capture_output=True, text=True, timeout=600)
     assert d.returncode == 0
     assert "ERROR" not in d.stdout and d.stdout.count("(OK)") >= frames
+    # C5: the reference decoder with the hooks (xIT, xDeQuant, xPredInterUni on the GPU) reconstructs the same pictures
+    e = dict(os.environ, TVC_HM="tq,mc")
+    dc = subprocess.run([DEC_CUDA, "-b", cuda_bin, "-o", str(tmp_path / "dec_cuda.yuv")], capture_output=True, text=True, timeout=1500, env=e)
+    assert dc.returncode == 0, dc.stdout[-800:] + dc.stderr[-800:]
+    assert "ERROR" not in dc.stdout and dc.stdout.count("(OK)") >= frames
+    dserved = [ln for ln in dc.stderr.splitlines() if ln.startswith("TLibCuda:")]
+    assert dserved and " 0 xIT" not in dserved[-1], dc.stderr[-500:]
+    print("decoder", dserved[-1])
+    assert _md5(str(tmp_path / "dec_cuda.yuv")) == _md5(str(tmp_path / "dec.yuv"))

@@ -119,6 +119,7 @@ SIGNATURES = {
     "tvc_filter_ver_chroma": (ci, [vp, vp, ci, vp, ci, ci, ci, ci, ci, ci]),
     "tvc_mc_batch": (ci, [vp, ci, ci, vp]),
     "tvc_mc_batch_dev": (ci, [vp, ci, ci, vp]),
+    "tvc_mc_block": (ci, [vp, ci, ci, ci, ci, ci, ci, ci, ci, vp, ci, vp, vp, ci]),
     "tvc_me_prepass": (ci, [vp, ci, ci, vp, vp]),
     "tvc_me_table_bytes": (C.c_size_t, [vp, ci]),
     "tvc_me_tables_dev": (ci, [vp, C.POINTER(vp), C.POINTER(vp)]),

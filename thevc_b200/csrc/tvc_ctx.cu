@@ -33,6 +33,13 @@ int ensure_scratch(tvc_ctx* c, Scratch& s, size_t bytes)
   return TVC_OK;
 }
 
+bool is_pinned(const void* p)
+{
+  cudaPointerAttributes a;
+  if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 int stage_acquire(tvc_ctx* c, Scratch& s, cudaEvent_t& ev, size_t bytes)
 {
   if (!ev) TVC_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));

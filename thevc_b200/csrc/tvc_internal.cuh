@@ -93,6 +93,9 @@ int check_cuda(tvc_ctx* c, cudaError_t e, const char* what);
 int ensure_scratch(tvc_ctx* c, Scratch& s, size_t bytes);
 // wait until the previous asynchronous H2D copy out of a staging buffer has executed, (re)size it
 int stage_acquire(tvc_ctx* c, Scratch& s, cudaEvent_t& ev, size_t bytes);
+// true when p is page-locked host memory CUDA knows about (cudaHostAlloc / cudaHostRegister): the
+// host-pointer entry points then copy straight from / into the caller's buffer instead of staging
+bool is_pinned(const void* p);
 inline bool valid_slot(const tvc_ctx* c, int s) { return s >= 0 && s < (int)c->pics.size(); }
 
 #define TVC_CUDA(c, expr)                                                       \

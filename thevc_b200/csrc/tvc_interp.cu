@@ -129,6 +129,19 @@ __global__ void __launch_bounds__(256) k_mc_batch(PlaneTable pt, int dst_slot, i
   }
 }
 
+// one PU, one list, dense output [Y w*h][U (w/2)(h/2)][V]: the drop-in for xPredInterUni
+__global__ void __launch_bounds__(256) k_mc_block(PlaneTable pt, int ref_slot, int x, int y, int w, int h, int mvx, int mvy, int bi,
+                                                  int bd, int16_t* __restrict__ out)
+{
+  __shared__ int16_t s_tmp[kMcMaxW * (kMcMaxH + 7)];
+  const int pl = blockIdx.x, sh = pl ? 1 : 0;
+  const int pw = w >> sh, ph = h >> sh, x0 = x >> sh, y0 = y >> sh, stride = pt.stride[pl];
+  const int16_t* ref = pt.org[ref_slot][pl] + (ptrdiff_t)y0 * stride + x0;
+  int16_t* dst = out + (pl == 0 ? 0 : (pl == 1 ? w * h : w * h + pw * ph));
+  if (pl == 0) mc_one_list<8>(ref, stride, mvx, mvy, pw, ph, bi != 0, bd, s_tmp, dst, pw);
+  else         mc_one_list<4>(ref, stride, mvx, mvy, pw, ph, bi != 0, bd, s_tmp, dst, pw);
+}
+
 }  // namespace tvc
 
 using namespace tvc;
@@ -143,6 +156,38 @@ int tvc_filter_hor_chroma(tvc_ctx* c, const int16_t* s, int ss, int16_t* d, int 
 { return filter_dropin(c, 4, 0, s, ss, d, ds, w, h, frac, 1, is_last != 0); }
 int tvc_filter_ver_chroma(tvc_ctx* c, const int16_t* s, int ss, int16_t* d, int ds, int w, int h, int frac, int is_first, int is_last)
 { return filter_dropin(c, 4, 1, s, ss, d, ds, w, h, frac, is_first != 0, is_last != 0); }
+
+int tvc_mc_block(tvc_ctx* c, int ref_slot, int x, int y, int w, int h, int mvx, int mvy, int bi, int16_t* dst_y, int stride_y,
+                 int16_t* dst_u, int16_t* dst_v, int stride_c)
+{
+  if (!c || !valid_slot(c, ref_slot) || !dst_y || !dst_u || !dst_v || w <= 0 || h <= 0 || w > 64 || h > 64 || (w & 3) || (h & 3) ||
+      x < 0 || y < 0)
+    return set_err(c, TVC_ERR_ARG, "tvc_mc_block: bad argument");
+  const Pic& p = c->pics[ref_slot];
+  const int ix = x + (mvx >> 2), iy = y + (mvy >> 2);
+  if (ix - 3 < -p.mx[0] || iy - 3 < -p.my[0] || ix + w + 4 > p.w[0] + p.mx[0] || iy + h + 4 > p.h[0] + p.my[0])
+    return set_err(c, TVC_ERR_ARG, "tvc_mc_block: MV reaches outside the padded picture (clipMv first)");
+  const size_t elems = (size_t)w * h * 3 / 2;
+  int r;
+  if ((r = ensure_scratch(c, c->out, elems * 2))) return r;
+  {
+    ProfScope ps(c, TVC_PH_MC);
+    k_mc_block<<<3, 256, 0, c->stream>>>(c->planes, ref_slot, x, y, w, h, mvx, mvy, bi, c->cfg.bit_depth, (int16_t*)c->out.dev);
+    TVC_LAUNCH_CHECK(c);
+  }
+  TVC_CUDA(c, cudaMemcpyAsync(c->out.host, c->out.dev, elems * 2, cudaMemcpyDeviceToHost, c->stream));
+  TVC_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int16_t* o = (const int16_t*)c->out.host;
+  for (int r2 = 0; r2 < h; r2++) memcpy(dst_y + (ptrdiff_t)r2 * stride_y, o + (size_t)r2 * w, (size_t)w * 2);
+  const int cw = w >> 1, ch = h >> 1;
+  const int16_t* ou = o + (size_t)w * h;
+  const int16_t* ov = ou + (size_t)cw * ch;
+  for (int r2 = 0; r2 < ch; r2++) {
+    memcpy(dst_u + (ptrdiff_t)r2 * stride_c, ou + (size_t)r2 * cw, (size_t)cw * 2);
+    memcpy(dst_v + (ptrdiff_t)r2 * stride_c, ov + (size_t)r2 * cw, (size_t)cw * 2);
+  }
+  return TVC_OK;
+}
 
 int tvc_mc_batch_dev(tvc_ctx* c, int dst_slot, int n, const tvc_pu* pus_dev)
 {

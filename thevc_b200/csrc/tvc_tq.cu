@@ -509,32 +509,35 @@ static int fwd_host(tvc_ctx* c, bool quant, int resi_slot, int n, const tvc_tu* 
   size_t tu_bytes = ((size_t)n * sizeof(tvc_tu) + 255) & ~(size_t)255;
   size_t coef_bytes = ((coef_elems * 4) + 255) & ~(size_t)255;
   size_t abs_bytes = (((size_t)n * 4) + 255) & ~(size_t)255;
+  const bool want_arl = quant && arl && qc->use_arl;
+  // page-locked caller buffers are copied directly; pageable ones go through the pinned staging area
+  const bool pin_tus = is_pinned(tus), pin_out = is_pinned(coef) && (!want_arl || is_pinned(arl)) && (!abs_sum || is_pinned(abs_sum));
   if ((r = ensure_scratch(c, c->in, tu_bytes))) return r;
   if ((r = ensure_scratch(c, c->out, 2 * coef_bytes + abs_bytes))) return r;
-  memcpy(c->in.host, tus, (size_t)n * sizeof(tvc_tu));
-  TVC_CUDA(c, cudaMemcpyAsync(c->in.dev, c->in.host, (size_t)n * sizeof(tvc_tu), cudaMemcpyHostToDevice, c->stream));
-  // device / pinned layout: [coefficients][abs sums][ARL coefficients]; only what was produced is copied back
+  const void* tu_src = tus;
+  if (!pin_tus) { memcpy(c->in.host, tus, (size_t)n * sizeof(tvc_tu)); tu_src = c->in.host; }
+  TVC_CUDA(c, cudaMemcpyAsync(c->in.dev, tu_src, (size_t)n * sizeof(tvc_tu), cudaMemcpyHostToDevice, c->stream));
+  // device layout: [coefficients][abs sums][ARL coefficients]; only what was produced is copied back
   int32_t* d_coef = (int32_t*)c->out.dev;
   uint32_t* d_abs = (uint32_t*)((char*)c->out.dev + coef_bytes);
   int32_t* d_arl = (int32_t*)((char*)c->out.dev + coef_bytes + abs_bytes);
-  const bool want_arl = quant && arl && qc->use_arl;
   tvc_quant_cfg q0 = {0, 0, 0};
   if (quant) r = launch_fwd<true>(c, resi_slot, counts, (const tvc_tu*)c->in.dev, *qc, d_coef, want_arl ? d_arl : nullptr, d_abs);
   else r = launch_fwd<false>(c, resi_slot, counts, (const tvc_tu*)c->in.dev, q0, d_coef, nullptr, nullptr);
   if (r) return r;
+  if (pin_out) {
+    TVC_CUDA(c, cudaMemcpyAsync(coef, d_coef, coef_elems * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (want_arl) TVC_CUDA(c, cudaMemcpyAsync(arl, d_arl, coef_elems * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (quant && abs_sum) TVC_CUDA(c, cudaMemcpyAsync(abs_sum, d_abs, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    TVC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TVC_OK;
+  }
   size_t back = coef_bytes + (quant ? abs_bytes : 0) + (want_arl ? coef_bytes : 0);
   TVC_CUDA(c, cudaMemcpyAsync(c->out.host, c->out.dev, back, cudaMemcpyDeviceToHost, c->stream));
   TVC_CUDA(c, cudaStreamSynchronize(c->stream));
-  // only the TU rasters are defined; copy them out TU by TU
-  const int32_t* h_coef = (const int32_t*)c->out.host;
-  const uint32_t* h_abs = (const uint32_t*)((char*)c->out.host + coef_bytes);
-  const int32_t* h_arl = (const int32_t*)((char*)c->out.host + coef_bytes + abs_bytes);
-  for (int i = 0; i < n; i++) {
-    size_t nn = (size_t)1 << (2 * tus[i].log2_size);
-    memcpy(coef + tus[i].coef_offset, h_coef + tus[i].coef_offset, nn * 4);
-    if (want_arl) memcpy(arl + tus[i].coef_offset, h_arl + tus[i].coef_offset, nn * 4);
-  }
-  if (quant && abs_sum) memcpy(abs_sum, h_abs, (size_t)n * 4);
+  memcpy(coef, c->out.host, coef_elems * 4);
+  if (want_arl) memcpy(arl, (char*)c->out.host + coef_bytes + abs_bytes, coef_elems * 4);
+  if (quant && abs_sum) memcpy(abs_sum, (char*)c->out.host + coef_bytes, (size_t)n * 4);
   return TVC_OK;
 }
 
@@ -561,9 +564,13 @@ int tvc_inv_tq_batch(tvc_ctx* c, int resi_slot, int pred_slot, int recon_slot, i
   if ((r = validate_tus(c, resi_slot, n, tus, coef_elems, counts))) return r;
   size_t tu_bytes = ((size_t)n * sizeof(tvc_tu) + 255) & ~(size_t)255;
   if ((r = ensure_scratch(c, c->in, tu_bytes + coef_elems * 4))) return r;
-  memcpy(c->in.host, tus, (size_t)n * sizeof(tvc_tu));
-  memcpy((char*)c->in.host + tu_bytes, levels, coef_elems * 4);
-  TVC_CUDA(c, cudaMemcpyAsync(c->in.dev, c->in.host, tu_bytes + coef_elems * 4, cudaMemcpyHostToDevice, c->stream));
+  const bool pin_tus = is_pinned(tus), pin_lev = is_pinned(levels);
+  const void* tu_src = tus;
+  const void* lev_src = levels;
+  if (!pin_tus) { memcpy(c->in.host, tus, (size_t)n * sizeof(tvc_tu)); tu_src = c->in.host; }
+  if (!pin_lev) { memcpy((char*)c->in.host + tu_bytes, levels, coef_elems * 4); lev_src = (char*)c->in.host + tu_bytes; }
+  TVC_CUDA(c, cudaMemcpyAsync(c->in.dev, tu_src, (size_t)n * sizeof(tvc_tu), cudaMemcpyHostToDevice, c->stream));
+  TVC_CUDA(c, cudaMemcpyAsync((char*)c->in.dev + tu_bytes, lev_src, coef_elems * 4, cudaMemcpyHostToDevice, c->stream));
   if ((r = launch_inv(c, resi_slot, pred_slot, recon_slot, counts, (const tvc_tu*)c->in.dev,
                       (const int32_t*)((char*)c->in.dev + tu_bytes), 1)))
     return r;

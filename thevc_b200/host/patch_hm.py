@@ -65,7 +65,14 @@ def main():
     s = sub_once(s, r'(Void TComTrQuant::xDeQuant\( const TCoeff\* pSrc, Int\* pDes, Int iWidth, Int iHeight, Int scalingListType \)\r?\n\{\r?\n)',
                  r'\1  if ( !getUseScalingList() && tlibcuda_xDeQuant( pSrc, pDes, iWidth, iHeight, m_cQP.m_iPer, m_cQP.m_iRem ) ) return;\n', "xDeQuant")
     wr(os.path.join(out, "TLibCommon", "TComTrQuant.cpp"), s)
-    print("patched 4 files into", out)
+    # ---- TComPrediction.cpp: xPredInterUni (shared by encoder and decoder)
+    s = rd(os.path.join(lib, "TLibCommon", "TComPrediction.cpp"))
+    s = sub_once(s, r'(#include "TComPrediction.h"\r?\n)', r'\1#include "tlibcuda_hm.h"\n', "TComPrediction include")
+    s = sub_once(s, r'(Void TComPrediction::xPredInterUni \(.*?pcCU->clipMv\(cMv\);\r?\n)',
+                 r'\1  if ( tlibcuda_pred_inter_uni( pcCU, pcCU->getSlice()->getRefPic( eRefPicList, iRefIdx ), uiPartAddr, cMv.getHor(), cMv.getVer(), iWidth, iHeight, rpcYuvPred, bi ) ) return;\n',
+                 "xPredInterUni", flags=re.S)
+    wr(os.path.join(out, "TLibCommon", "TComPrediction.cpp"), s)
+    print("patched 5 files into", out)
 
 
 if __name__ == "__main__":

@@ -20,6 +20,7 @@
 #include "TLibCommon/TComPicYuv.h"
 #include "TLibCommon/TComSlice.h"
 #include "TLibCommon/TComMv.h"
+#include "TLibCommon/TComYuv.h"
 #include "TLibEncoder/TEncCfg.h"
 
 #include "tlibcuda_hm.h"
@@ -36,14 +37,14 @@ struct DevPic {                 // one registered TComPicYuv: host buffer range 
 
 struct State {
   tvc_ctx* h = nullptr;
-  bool on_me = true, on_frac = true, on_tq = true, on_tables = true, verbose = false, disabled = false;
+  bool on_me = true, on_frac = true, on_tq = true, on_mc = true, on_tables = true, verbose = false, disabled = false;
   int w = 0, ht = 0;
   std::vector<DevPic> slots;
   unsigned long long clock = 0;
   int cur_slot = -1;
   int table_refs[8];
   int num_table_refs = 0;
-  unsigned long long n_tz = 0, n_frac = 0, n_xt = 0, n_xit = 0, n_dq = 0;
+  unsigned long long n_tz = 0, n_frac = 0, n_xt = 0, n_xit = 0, n_dq = 0, n_mc = 0;
 };
 
 State& S()
@@ -67,8 +68,8 @@ void report()
 {
   State& s = S();
   if (s.h)
-    fprintf(stderr, "TLibCuda: %llu xTZSearch, %llu xPatternSearchFracDIF, %llu xT, %llu xIT, %llu xDeQuant calls served; %llu kernel launches\n",
-            s.n_tz, s.n_frac, s.n_xt, s.n_xit, s.n_dq, (unsigned long long)tvc_launch_count(s.h));
+    fprintf(stderr, "TLibCuda: %llu xTZSearch, %llu xPatternSearchFracDIF, %llu xT, %llu xIT, %llu xDeQuant, %llu xPredInterUni calls served; %llu kernel launches\n",
+            s.n_tz, s.n_frac, s.n_xt, s.n_xit, s.n_dq, s.n_mc, (unsigned long long)tvc_launch_count(s.h));
 }
 
 void parse_env()
@@ -79,6 +80,7 @@ void parse_env()
   s.on_me = strstr(e, "me") != nullptr;
   s.on_frac = strstr(e, "frac") != nullptr;
   s.on_tq = strstr(e, "tq") != nullptr;
+  s.on_mc = strstr(e, "mc") != nullptr;
   s.on_tables = strstr(e, "tables") != nullptr;
   s.verbose = strstr(e, "verbose") != nullptr;
 }
@@ -86,9 +88,14 @@ void parse_env()
 void ensure_ctx(int w, int ht)
 {
   State& s = S();
-  if (s.h || s.disabled) return;
-  parse_env();
-  if (!s.on_me && !s.on_frac && !s.on_tq) { s.disabled = true; return; }     // TVC_HM=none: the unmodified path
+  if (s.disabled || (s.h && s.w >= w && s.ht >= ht)) return;
+  static bool parsed = false;
+  if (!parsed) { parse_env(); parsed = true; atexit(report); }
+  if (!s.on_me && !s.on_frac && !s.on_tq && !s.on_mc) { s.disabled = true; return; }     // TVC_HM=none: the unmodified path
+  if (s.h) {                  // the decoder learns the picture size after its first transforms: start over with the real size
+    tvc_ctx_destroy(s.h);
+    s.h = nullptr;
+  }
   tvc_config c;
   c.width = w; c.height = ht;
   c.bit_depth = (int)(g_uiBitDepth + g_uiBitIncrement);
@@ -101,8 +108,8 @@ void ensure_ctx(int w, int ht)
     exit(EXIT_FAILURE);
   }
   s.w = w; s.ht = ht;
-  s.slots.resize(c.num_slots);
-  atexit(report);
+  s.slots.assign(c.num_slots, DevPic());
+  s.cur_slot = -1; s.num_table_refs = 0;
 }
 
 // slot of a picture buffer; uploads it when the slot does not hold this picture's current content
@@ -229,8 +236,33 @@ bool tlibcuda_frac_search(TComPattern* key, short* refY, int refStride, TComMv* 
   return true;
 }
 
+bool tlibcuda_pred_inter_uni(TComDataCU* cu, TComPic* refPic, unsigned partAddr, int mvx, int mvy, int w, int h,
+                             TComYuv* dst, bool bi)
+{
+  TComPicYuv* rec = refPic->getPicYuvRec();
+  ensure_ctx(rec->getWidth(), rec->getHeight());
+  State& s = S();
+  if (!s.h || !s.on_mc) return false;
+  const int slot = slot_for(rec, refPic->getPOC(), false, true);
+  const unsigned z = cu->getZorderIdxInCU() + partAddr;
+  const unsigned raster = g_auiZscanToRaster[z];
+  const int ctus_x = (int)cu->getPic()->getFrameWidthInCU();
+  const int x = (int)(cu->getAddr() % ctus_x) * (int)g_uiMaxCUWidth + (int)g_auiRasterToPelX[raster];
+  const int y = (int)(cu->getAddr() / ctus_x) * (int)g_uiMaxCUHeight + (int)g_auiRasterToPelY[raster];
+  CK(tvc_mc_block(s.h, slot, x, y, w, h, mvx, mvy, bi ? 1 : 0, dst->getLumaAddr(partAddr), (int)dst->getStride(),
+                  dst->getCbAddr(partAddr), dst->getCrAddr(partAddr), (int)dst->getCStride()));
+  s.n_mc++;
+  return true;
+}
+
+static void ensure_tq_ctx()
+{
+  if (!S().h && !S().disabled) ensure_ctx(64, 64);        // transforms need no picture slots
+}
+
 bool tlibcuda_xT(unsigned mode, short* resi, unsigned stride, int* coef, int w, int h)
 {
+  ensure_tq_ctx();
   State& s = S();
   if (!s.h || !s.on_tq || w != h) return false;
   CK(tvc_xT(s.h, (w == 4 && mode != REG_DCT) ? 1 : 0, resi, (int)stride, coef, w, h));
@@ -240,6 +272,7 @@ bool tlibcuda_xT(unsigned mode, short* resi, unsigned stride, int* coef, int w, 
 
 bool tlibcuda_xIT(unsigned mode, int* coef, short* resi, unsigned stride, int w, int h)
 {
+  ensure_tq_ctx();
   State& s = S();
   if (!s.h || !s.on_tq || w != h) return false;
   CK(tvc_xIT(s.h, (w == 4 && mode != REG_DCT) ? 1 : 0, coef, resi, (int)stride, w, h));
@@ -249,6 +282,7 @@ bool tlibcuda_xIT(unsigned mode, int* coef, short* resi, unsigned stride, int w,
 
 bool tlibcuda_xDeQuant(const int* src, int* dst, int w, int h, int per, int rem)
 {
+  ensure_tq_ctx();
   State& s = S();
   if (!s.h || !s.on_tq || w != h) return false;
   CK(tvc_xDeQuant(s.h, src, dst, w, h, per, rem));

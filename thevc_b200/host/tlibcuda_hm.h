@@ -10,7 +10,7 @@
  * fallback of ours.  A CUDA error is fatal (exit(EXIT_FAILURE)), like the reference's own errors.
  *
  * Which hooks are active is chosen with the environment variable TVC_HM (comma list of
- * me,frac,tq,tables; default "me,frac,tq,tables"; "none" runs the unmodified path).
+ * me,frac,tq,mc,tables; default all; "none" runs the unmodified path).
  */
 #ifndef TLIBCUDA_HM_H
 #define TLIBCUDA_HM_H
@@ -22,6 +22,7 @@ class TComRdCost;
 class TEncCfg;
 class TComPic;
 class TComSlice;
+class TComYuv;
 
 /* TEncGOP::compressGOP, before compressSlice (TEncGOP.cpp:576): upload the current original and every
  * reference reconstruction (final + border-extended at this point), run the SAD-table pre-pass */
@@ -33,6 +34,10 @@ bool tlibcuda_tz_search(TComDataCU* cu, TComPattern* key, short* refY, int refSt
 /* TEncSearch::xPatternSearchFracDIF (TEncSearch.cpp:4476) */
 bool tlibcuda_frac_search(TComPattern* key, short* refY, int refStride, TComMv* mvInt, TComMv& half, TComMv& qter,
                           unsigned& ruiCost, TComRdCost* rd, TEncCfg* cfg, bool biPred);
+/* TComPrediction::xPredInterUni (TComPrediction.cpp:483-490), after clipMv: luma + chroma prediction of one PU
+ * from one reference picture into the TComYuv (bi: 14-bit intermediates for addAvg) */
+bool tlibcuda_pred_inter_uni(TComDataCU* cu, TComPic* refPic, unsigned partAddr, int mvx, int mvy, int w, int h,
+                             TComYuv* dst, bool bi);
 /* TComTrQuant::xT / xIT / xDeQuant (TComTrQuant.cpp:1542, 1583, 1272) */
 bool tlibcuda_xT(unsigned mode, short* resi, unsigned stride, int* coef, int w, int h);
 bool tlibcuda_xIT(unsigned mode, int* coef, short* resi, unsigned stride, int w, int h);

@@ -172,6 +172,12 @@ class TLibCuda:
             arr = _arr(PU, pus)
             self._ck(self.L.tvc_mc_batch(self.h, dst_slot, len(pus), C.cast(arr, C.c_void_p)))
 
+    def mc_block(self, ref_slot: int, x: int, y: int, w: int, h: int, mvx: int, mvy: int, bi: bool):
+        """one PU from one reference into dense arrays (Y w*h, U/V (w/2)*(h/2)); bi keeps 14-bit intermediates"""
+        oy = np.zeros((h, w), np.int16); ou = np.zeros((h // 2, w // 2), np.int16); ov = np.zeros_like(ou)
+        self._ck(self.L.tvc_mc_block(self.h, ref_slot, x, y, w, h, mvx, mvy, int(bi), ptr(oy), w, ptr(ou), ptr(ov), w // 2))
+        return oy, ou, ov
+
     # ------------------------------------------------------------------ ME
     def me_prepass(self, cur_slot: int, ref_slots: Sequence[int], centers: Optional[np.ndarray] = None):
         """centers: int32 array [num_refs, num_ctus, 2] (cx, cy) or None"""
