@@ -178,11 +178,12 @@ class ClockSampler:
         self.idx = gpu_index
         self.proc = None
         self.lines = []
+        self.marks = []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
         except OSError:
@@ -190,12 +191,16 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def mark(self):
+        """start / end of the timed region: only samples between the first and last mark are reported"""
+        self.marks.append(time.perf_counter())
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -203,7 +208,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lo = self.marks[0] if self.marks else 0.0
+        hi = self.marks[-1] + 0.05 if len(self.marks) > 1 else float("inf")
+        inside = [ln for (ts, ln) in self.lines if lo <= ts <= hi]
+        if not inside:                      # region shorter than one sampling period: nearest samples
+            inside = [ln for (_, ln) in self.lines[-2:]]
+        for ln in inside:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -399,6 +409,8 @@ def gpu_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     stream = torch.cuda.Stream()
@@ -473,6 +485,8 @@ def gpu_arm(args):
     clocks = ClockSampler(local) if rank == 0 else None
 
     # ---- device-resident timing (value)
+    if clocks:
+        clocks.start()
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
             step_device()
@@ -481,13 +495,15 @@ def gpu_arm(args):
         launches0 = t.launch_count()
         barrier()
         if clocks:
-            clocks.start()
+            clocks.mark()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
             step_device()
         e1.record(stream)
         barrier()
+        if clocks:
+            clocks.mark()
         ms_total = e0.elapsed_time(e1)
         clk = clocks.stop() if clocks else None
         launches = t.launch_count() - launches0
@@ -503,6 +519,7 @@ def gpu_arm(args):
     mcfg_nofrac = MeFrameCfg(SEARCH_RANGE, 1, 1, 1, 0, lc)
     ck(L.tvc_me_frame(h, SLOT_CUR, NUM_REFS, refs, ptr(pred), C.byref(mcfg_nofrac), ptr(ires_flat), None))
     n_sads = ires_flat[:, 3].astype(np.int64).reshape(NUM_REFS, wl.nctu, 593)
+    me_stats = t.me_frame_stats()       # exact work counters of that call (table granules, raster candidates)
 
     # ---- e2e timing (host buffers through the host-pointer ABI)
     with torch.cuda.stream(stream):
@@ -533,16 +550,19 @@ def gpu_arm(args):
     n_valid = int(valid.sum()) * NUM_REFS
     table_bytes = t.me_table_bytes(NUM_REFS)
     win_bytes = NUM_REFS * wl.nctu * (208 * 192 + 64 * 64)
-    # search: 16-byte table granules read per evaluated candidate of a PU = (h/4) * (number of 16-column quarters it touches)
-    gran = (census[:, 3] // 4) * ((census[:, 0] + census[:, 2] - 1) // 16 - census[:, 0] // 16 + 1)
-    search_bytes = float((n_sads * gran[None, None, :]).sum()) * 16
+    # search: 16-byte table granules the candidates each PU search evaluated itself required (counted on the
+    # device; candidates served by the shared raster stage and speculative evaluations excluded);
+    # raster: one 1 KB candidate block per raster candidate of every (CTU, reference)
+    search_bytes = float(me_stats["search_granules"]) * 16
+    raster_bytes = float(me_stats["raster_candidates"]) * 1024 + n_valid * 8
     pu_area = (census[:, 2].astype(np.int64) * census[:, 3])
     cw, chh = census[:, 2].astype(np.int64), census[:, 3].astype(np.int64)
     frac_bytes = float((valid * (((cw + 8) * (chh + 8) + pu_area) * 2 + 24)[None, :]).sum()) * NUM_REFS
     samples_tq = float(sum((1 << (2 * int(l))) * int(c) for l, c in zip((2, 3, 4, 5), counts)))
     alg_bytes = {
         "me_tables": table_bytes + win_bytes,
-        "me_search": search_bytes + n_valid * (72 + 16),
+        "me_search": search_bytes + n_valid * (72 + 16 + 8),
+        "me_raster": raster_bytes,
         "me_frac": frac_bytes,
         "mc": float(sum(int(p["w"]) * int(p["h"]) for p in wl.pus)) * 1.5 * 2 * 2,
         "fwd_tq": samples_tq * (2 + 4),
@@ -555,12 +575,24 @@ def gpu_arm(args):
     roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": None, "peak_source": peak_src, "launch_ms": ph_ms[dom] / groups_per_step,
                 "algorithmic_bytes_per_launch": alg_bytes[dom] / groups_per_step}
+    traffic = {}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get(dom)
+            traffic = json.load(open(traffic_file))
         except Exception:
-            pass
+            traffic = {}
+    roofline["traffic"] = traffic.get(dom, {}).get("dram_bytes_per_launch") if isinstance(traffic.get(dom), dict) else traffic.get(dom)
+    if isinstance(traffic.get(dom), dict) and traffic[dom].get("note"):
+        roofline["note"] = traffic[dom]["note"]
+    # every ME kernel against the same HBM peak (the step has no single dominant kernel: four of them take 7-8 ms each)
+    kernels = {}
+    for k in ("me_tables", "me_raster", "me_search", "me_frac"):
+        if ph_ms.get(k, 0) > 0:
+            a = alg_bytes[k] / (ph_ms[k] * 1e-3) / 1e9
+            kernels[k] = {"ms": ph_ms[k], "algorithmic_GB": alg_bytes[k] / 1e9, "achieved_GBps": a, "frac_of_hbm_peak": a / peak,
+                          "traffic": (traffic.get(k) or {}).get("dram_bytes_per_launch") if isinstance(traffic.get(k), dict) else None,
+                          "bound": (traffic.get(k) or {}).get("bound") if isinstance(traffic.get(k), dict) else None}
     sad_pels = float(NUM_REFS * wl.nctu) * 129 * 129 * 4096
     satd_pels = float((valid * pu_area[None, :]).sum()) * NUM_REFS * 18
     sub = {
@@ -568,6 +600,8 @@ def gpu_arm(args):
         "phase_GBps": {k: alg_bytes[k] / (ph_ms[k] * 1e-3) / 1e9 for k in alg_bytes if ph_ms.get(k, 0) > 0},
         "me_sad_table_gpel_per_s": sad_pels / (ph_ms["me_tables"] * 1e-3) / 1e9 if ph_ms["me_tables"] > 0 else None,
         "me_frac_satd_gpel_per_s": satd_pels / (ph_ms["me_frac"] * 1e-3) / 1e9 if ph_ms["me_frac"] > 0 else None,
+        "kernels": kernels,
+        "me_work": me_stats,
         "tz_candidates_per_step": int(n_sads.sum()),
         "me_jobs_per_step": n_valid,
     }

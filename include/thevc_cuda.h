@@ -267,6 +267,12 @@ int tvc_me_frame(tvc_ctx* ctx, int cur_slot, int num_refs, const int* ref_slots,
 int tvc_me_frame_dev(tvc_ctx* ctx, int cur_slot, int num_refs, const int* ref_slots, const tvc_me_center* pred_qpel,
                      const tvc_me_frame_cfg* cfg, tvc_me_result** int_dev, tvc_frac_result** frac_dev);
 
+/* work counters of the last tvc_me_frame[_dev] call (for roofline accounting): stats[0] = 16-byte table
+ * granules the reference-visible candidates of k_me_search required (candidates each PU search evaluated
+ * itself x granules of that PU; speculative evaluations not counted), stats[1] = candidates served by the
+ * shared raster stage, stats[2] = raster candidates walked by k_me_raster (1 KB each).  Synchronises.  */
+int tvc_me_frame_stats(tvc_ctx* ctx, uint64_t stats[3]);
+
 /* ---------------------------------------------------------------------------------- transform / quant
  * Replaces TComTrQuant::transformNxN = xT (-> xTrMxN -> partialButterfly4/8/16/32 /
  * fastForwardDst) or xTransformSkip, then xQuant's non-RDOQ branch with signBitHidingHDQ; and
@@ -326,7 +332,7 @@ int tvc_xDeQuant(tvc_ctx* ctx, const int32_t* qcoef, int32_t* coef, int w, int h
  * each kernel's duration measured live inside the timed region (not under a profiler).         */
 enum {
   TVC_PH_ME_TABLES = 0, TVC_PH_ME_SEARCH = 1, TVC_PH_ME_FRAC = 2, TVC_PH_MC = 3, TVC_PH_FWD_TQ = 4,
-  TVC_PH_INV_TQ = 5, TVC_PH_OTHER = 6, TVC_PH_COUNT = 7
+  TVC_PH_INV_TQ = 5, TVC_PH_OTHER = 6, TVC_PH_ME_RASTER = 7, TVC_PH_COUNT = 8
 };
 int tvc_prof_enable(tvc_ctx* ctx, int on);
 /* synchronises the stream, adds the elapsed time of every recorded pair to per-phase sums and returns

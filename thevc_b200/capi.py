@@ -75,7 +75,7 @@ class MeFrameCfg(C.Structure):
 
 
 ME_CENSUS = 593
-PHASES = ("me_tables", "me_search", "me_frac", "mc", "fwd_tq", "inv_tq", "other")
+PHASES = ("me_tables", "me_search", "me_frac", "mc", "fwd_tq", "inv_tq", "other", "me_raster")
 
 # numpy views of the ABI structs (same layout) for bulk results
 ME_RESULT_DTYPE = np.dtype([("mvx", "<i4"), ("mvy", "<i4"), ("sad", "<u4"), ("n_sads", "<u4")])
@@ -131,6 +131,7 @@ SIGNATURES = {
     "tvc_me_census": (ci, [vp]),
     "tvc_me_frame": (ci, [vp, ci, ci, vp, vp, C.POINTER(MeFrameCfg), vp, vp]),
     "tvc_me_frame_dev": (ci, [vp, ci, ci, vp, vp, C.POINTER(MeFrameCfg), C.POINTER(vp), C.POINTER(vp)]),
+    "tvc_me_frame_stats": (ci, [vp, vp]),
     "tvc_fwd_transform_batch": (ci, [vp, ci, ci, vp, vp, C.c_size_t]),
     "tvc_fwd_tq_batch": (ci, [vp, ci, ci, vp, C.POINTER(QuantCfg), vp, vp, C.c_size_t, vp]),
     "tvc_inv_tq_batch": (ci, [vp, ci, ci, ci, ci, vp, vp, C.c_size_t]),

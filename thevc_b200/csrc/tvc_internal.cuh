@@ -71,6 +71,7 @@ struct tvc_ctx {
   tvc_frac_job* fr_fjobs = nullptr;
   tvc_frac_result* fr_frac = nullptr;
   void* fr_rast = nullptr;        // shared raster-stage results (RasterBest per job)
+  unsigned long long* fr_stats = nullptr;   // device: 3 work counters (tvc_me_frame_stats)
   size_t fr_cap = 0;              // entries
   // dedicated pinned staging of the asynchronous ME entry points (an event guards host reuse)
   tvc::Scratch me_stage, fr_stage;
@@ -80,8 +81,8 @@ struct tvc_ctx {
   struct ProfPair { int phase; cudaEvent_t a, b; };
   std::vector<ProfPair> prof_live;
   std::vector<cudaEvent_t> prof_pool;
-  double prof_ms[TVC_PH_COUNT] = {0, 0, 0, 0, 0, 0, 0};
-  uint64_t prof_n[TVC_PH_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+  double prof_ms[TVC_PH_COUNT] = {};
+  uint64_t prof_n[TVC_PH_COUNT] = {};
   // driver entry point for tensor maps
   void* encode_tiled = nullptr;
 };

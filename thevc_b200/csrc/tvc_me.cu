@@ -399,14 +399,14 @@ __device__ __forceinline__ bool diamond_cand(const SearchCtx& s, int sx, int sy,
   return axis ? (ux == 0 ? yc : xc) : (inside || (yc && xc));
 }
 
-// One diamond sweep (rounds d = 1, 2, 4, ... <= srange) around (sx,sy).  All candidates of the sweep
-// are known beforehand, so they are evaluated together: candidate c of the sweep (visiting order) is
-// slot c >> 5 of lane c & 31.  The reference's sequential update is then replayed round by round as an
-// ordered arg-min.  first_search: stop when three consecutive rounds brought no improvement
-// (bFirstSearchStop, uiFirstSearchRounds = 3; TEncSearch.cpp:4346-4361) -- candidates of later rounds
-// were evaluated speculatively and are neither counted nor used.
+// Diamond rounds d = d0, 2*d0, ... <= dmax around (sx,sy).  All candidates of these rounds are known
+// beforehand, so they are evaluated together: candidate c (visiting order) is slot c >> 5 of lane
+// c & 31.  The reference's sequential update is then replayed as an ordered arg-min.
+// first_search: the reference stops when three consecutive rounds brought no improvement
+// (bFirstSearchStop, uiFirstSearchRounds = 3; TEncSearch.cpp:4346-4361): candidates of later rounds were
+// evaluated speculatively and are neither counted nor used; returns true when stopped.
 template <int K>
-__device__ __forceinline__ void diamond_sweep(SearchCtx& s, int sx, int sy, int srange, bool first_search)
+__device__ __forceinline__ bool diamond_sweep(SearchCtx& s, int sx, int sy, int d0, int dmax, bool first_search)
 {
   bool valid[K];
   int x[K], y[K];
@@ -414,18 +414,41 @@ __device__ __forceinline__ void diamond_sweep(SearchCtx& s, int sx, int sy, int 
 #pragma unroll
   for (int k = 0; k < K; k++) {
     const int c = s.lane + 32 * k;
-    int off = 0, d = 1, pt;
+    int off = 0, d = d0, pt;
     uint32_t dist;
     valid[k] = false; x[k] = 0; y[k] = 0;
-    while (d <= srange) {
+    while (d <= dmax) {
       const int sz = round_size(d);
       if (c < off + sz) { valid[k] = diamond_cand(s, sx, sy, d, c - off, x[k], y[k], pt, dist); break; }
       off += sz; d <<= 1;
     }
   }
   eval_multi<K>(s, valid, x, y, cost);
+  if (!first_search) {
+    // star refinement: every round of the sweep runs (no early stop), so the sequential updates collapse
+    // into ONE ordered arg-min over the whole sweep: first candidate in visiting order with the minimum
+    uint32_t lb = kNoCost;
+    int lc = 0x7fffffff, nvalid = 0;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      nvalid += cost[k] != kNoCost;
+      if (cost[k] < lb) { lb = cost[k]; lc = s.lane + 32 * k; }     // slots of a lane are in visiting order
+    }
+    s.n_sads += __reduce_add_sync(0xffffffffu, (unsigned)nvalid);
+    const uint32_t mn = __reduce_min_sync(0xffffffffu, lb);
+    if (mn < s.best_sad) {
+      const int c = (int)__reduce_min_sync(0xffffffffu, (unsigned)(lb == mn ? lc : 0x7fffffff));
+      int off = 0, d = d0;
+      while (c >= off + round_size(d)) { off += round_size(d); d <<= 1; }
+      int bx, by, pt;
+      uint32_t dist;
+      diamond_cand(s, sx, sy, d, c - off, bx, by, pt, dist);
+      s.best_sad = mn; s.best_x = bx; s.best_y = by; s.best_dist = dist; s.point_nr = pt; s.best_round = 0;
+    }
+    return false;
+  }
   int off = 0;
-  for (int d = 1; d <= srange; d <<= 1) {
+  for (int d = d0; d <= dmax; d <<= 1) {
     const int sz = round_size(d);
     // this lane's candidate of the round, if any (a round has <= 16 candidates: at most one per lane)
     uint32_t c = kNoCost;
@@ -446,9 +469,10 @@ __device__ __forceinline__ void diamond_sweep(SearchCtx& s, int sx, int sy, int 
       diamond_cand(s, sx, sy, d, i, bx, by, pt, dist);
       s.best_sad = mn; s.best_x = bx; s.best_y = by; s.best_dist = dist; s.point_nr = pt; s.best_round = 0;
     }
-    if (first_search && s.best_round >= 3) return;
+    if (s.best_round >= 3) return true;
     off += sz;
   }
+  return false;
 }
 
 // xTZ2PointSearch (TEncSearch.cpp:351-476): the two untested neighbours of the best point; border
@@ -537,7 +561,7 @@ constexpr int kRastThreads = 640;               // >= TVC_ME_CENSUS PU threads
 
 __global__ void __launch_bounds__(kRastThreads)
 k_me_raster(const tvc_me_job* __restrict__ jobs, const uint16_t* __restrict__ tables, const tvc_me_center* __restrict__ centers,
-            int num_ctus, int raster, int bi, RasterBest* __restrict__ out)
+            int num_ctus, int raster, int bi, RasterBest* __restrict__ out, unsigned long long* __restrict__ stats)
 {
   __shared__ uint32_t IE[kRastChunk][17 * 17];  // integral of even-row block SADs
   __shared__ uint32_t IA[kRastChunk][17 * 17];  // integral of even+odd
@@ -631,13 +655,14 @@ k_me_raster(const tvc_me_job* __restrict__ jobs, const uint16_t* __restrict__ ta
     __syncthreads();
   }
   if (is_pu) o[tid] = RasterBest{pu_ok ? best : kNoCost, pu_ok ? best_i : -1};
+  if (tid == 0 && stats) atomicAdd(&stats[2], (unsigned long long)N);
 }
 
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB)
 k_me_search(PlaneTable pt, int cur_slot, int n, const tvc_me_job* __restrict__ jobs, tvc_me_result* __restrict__ out,
             const uint16_t* __restrict__ tables, const tvc_me_center* __restrict__ centers, int num_ctus, int ctus_x,
-            int bi, const RasterBest* __restrict__ rast)
+            int bi, const RasterBest* __restrict__ rast, unsigned long long* __restrict__ stats)
 {
   int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (j >= n) return;
@@ -679,6 +704,7 @@ k_me_search(PlaneTable pt, int cur_slot, int n, const tvc_me_job* __restrict__ j
   }
   s.best_sad = kNoCost; s.best_x = 0; s.best_y = 0; s.best_dist = 0; s.best_round = 0; s.point_nr = 0;
   s.n_sads = 0;
+  uint32_t served = 0;          // candidates of this job that the shared raster stage evaluated
 
   if (jb.mode == TVC_ME_FULL) {
     raster_scan<TVC_RASTER_K>(s, 1, 0);
@@ -698,7 +724,10 @@ k_me_search(PlaneTable pt, int cur_slot, int n, const tvc_me_job* __restrict__ j
       s.best_dist = 0; s.best_round = 0; s.point_nr = 0;
     }
     // a sweep holds 4 + 3*8 + 3*16 = 76 candidates for search range 64: 3 per lane (the ABI bounds the range)
-    diamond_sweep<3>(s, s.best_x, s.best_y, srange, true);      // first search :4346-4361
+    // first search :4346-4361.  All 76 candidates of the seven rounds are evaluated at once although the
+    // reference usually stops after three rounds: measured on B200, issuing the rounds in stages (1..8,
+    // 16..32, 64) costs more in serial latency (9.1 ms) than the speculative loads cost in bandwidth (8.2 ms).
+    diamond_sweep<3>(s, s.best_x, s.best_y, 1, srange, true);
     if (s.best_dist == 1) { s.best_dist = 0; two_point(s); }   // :4382-4386
     if ((int)s.best_dist > raster) {                           // :4389-4400
       s.best_dist = raster;
@@ -711,6 +740,7 @@ k_me_search(PlaneTable pt, int cur_slot, int n, const tvc_me_job* __restrict__ j
         if (shared) {
           const int nx = (s.rx - s.lx) / raster + 1, ny = (s.by - s.ty) / raster + 1;
           s.n_sads += (uint32_t)(nx * ny);
+          served = (uint32_t)(nx * ny);
           if (rb.cost < s.best_sad) {
             s.best_sad = rb.cost;
             s.best_x = s.lx + (rb.idx % nx) * raster;
@@ -724,7 +754,7 @@ k_me_search(PlaneTable pt, int cur_slot, int n, const tvc_me_job* __restrict__ j
     while (s.best_dist > 0) {                                  // star refinement :4435-4468
       const int sx = s.best_x, sy = s.best_y;
       s.best_dist = 0; s.point_nr = 0;
-      diamond_sweep<3>(s, sx, sy, srange, false);
+      diamond_sweep<3>(s, sx, sy, 1, srange, false);
       if (s.best_dist == 1) {
         s.best_dist = 0;
         if (s.point_nr != 0) two_point(s);
@@ -737,6 +767,10 @@ k_me_search(PlaneTable pt, int cur_slot, int n, const tvc_me_job* __restrict__ j
     r.sad = s.best_sad - mv_cost(s.lc, s.best_x, s.best_y, 2, s.px, s.py);
     r.n_sads = s.n_sads;
     out[j] = r;
+    if (stats) {
+      atomicAdd(&stats[0], (unsigned long long)(s.n_sads - served) * (unsigned)(s.nby * s.nq));
+      atomicAdd(&stats[1], (unsigned long long)served);
+    }
   }
 }
 
@@ -812,24 +846,49 @@ __device__ __forceinline__ uint32_t had_cols(int (&d)[TS], int c)
       for (int k = i; k < i + len; k++) { int a = d[k], b = d[k + len]; d[k] = a + b; d[k + len] = a - b; }
 #pragma unroll
   for (int m = 1; m < TS; m <<= 1) {
+    // butterfly across lanes: the lane with bit m clear gets mine + other, its partner other - mine:
+    // other + sgn * mine, one multiply-add per element
+    const int sgn = (c & m) ? -1 : 1;
 #pragma unroll
-    for (int r = 0; r < TS; r++) {
-      int o = __shfl_xor_sync(0xffffffffu, d[r], m);
-      d[r] = (c & m) ? (o - d[r]) : (d[r] + o);
-    }
+    for (int r = 0; r < TS; r++) d[r] = __shfl_xor_sync(0xffffffffu, d[r], m) + sgn * d[r];
   }
   uint32_t s = 0;
 #pragma unroll
-  for (int r = 0; r < TS; r++) s += (uint32_t)abs(d[r]);
+  for (int r = 0; r < TS; r++) s = __sad(d[r], 0, s);
 #pragma unroll
   for (int m = 1; m < TS; m <<= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
   return TS == 8 ? ((s + 2) >> 2) : ((s + 1) >> 1);      // xCalcHADs8x8 / 4x4 rounding (TComRdCost.cpp:1773,1869)
 }
 
 // one work unit: tile (tx,ty), horizontal candidate fx; produces the distortions of fy = fy0 - dq, fy0, fy0 + dq
+// second-stage rounding of TComInterpolationFilter::filter (isFirst = false, isLast = true,
+// TComInterpolationFilter.cpp:204-238) and of filterCopy (:124-145) with the shifts / offsets of the job's
+// bit depth folded into constants: (Short)((sum + offset) >> shift), then clip to [0, maxv]
+struct VRound { int shift, offset, cshift, coffset, maxv; };
+__device__ __forceinline__ VRound make_vround(int bd)
+{
+  VRound v;
+  const int head = kIfPrec - bd;
+  v.shift = kIfFilt + head; v.offset = (1 << (v.shift - 1)) + (kIfOffs << kIfFilt);
+  v.cshift = head; v.coffset = kIfOffs + (head ? (1 << (head - 1)) : 0);
+  v.maxv = (1 << bd) - 1;
+  return v;
+}
+// The reference casts to Short before clipping.  Here the operands are this kernel's own first-stage
+// outputs (|H| <= 12272 << (bd-8) ... bounded by the pel range), so (sum + offset) >> shift lies far inside
+// the int16 range and the cast is the identity; the clip is one min-with-relu instruction.
+__device__ __forceinline__ int vround_filter(int sum_plus_offset, const VRound& v)
+{
+  return __vimin_s32_relu(sum_plus_offset >> v.shift, v.maxv);
+}
+__device__ __forceinline__ int vround_copy(int smp, const VRound& v)
+{
+  return __vimin_s32_relu((smp + v.coffset) >> v.cshift, v.maxv);
+}
+
 template <int TS, int HP>
 __device__ __forceinline__ void frac_unit(const int16_t* __restrict__ H, int plane_elems, const int16_t* __restrict__ org, int opitch,
-                                          int fx, int fy0, int dq, int tx, int ty, int c, bool hadamard, int bd, uint32_t (&out)[3])
+                                          int fx, int fy0, int dq, int tx, int ty, int c, bool hadamard, const VRound& vr, uint32_t (&out)[3])
 {
   const int ix = fx < 0 ? -1 : 0, f = fx & 3;
   const int16_t* p = H + f * plane_elems + ty * HP + (tx + c + ix + 1);     // row index 0 of H is picture row -4
@@ -844,22 +903,34 @@ __device__ __forceinline__ void frac_unit(const int16_t* __restrict__ H, int pla
     const int fy = fy0 + (k - 1) * dq;
     const bool up = fy < 0;                                                  // row shift -1
     const int g = fy & 3;
-    int wv[TS + 7];                                                          // window rows ty-3+iy .. (static indexing)
-#pragma unroll
-    for (int j = 0; j < TS + 7; j++) wv[j] = up ? v[j] : v[j + 1];
-    int cf[8];
-#pragma unroll
-    for (int t = 0; t < 8; t++) cf[t] = c_luma_taps[g][t];
     int d[TS];
+    // fy is the same for every thread of the CTA (it depends on the pass and on k only): uniform branches
+    if (g == 0) {
+      // integer row: the reference takes the filterCopy branch (TComInterpolationFilter.cpp:124-145); fy == 0 has
+      // no row shift, so the sample is window row r + 4
 #pragma unroll
-    for (int r = 0; r < TS; r++) {
-      int sum = 0;
+      for (int r = 0; r < TS; r++) d[r] = o[r] - vround_copy(v[r + 4], vr);
+    } else {
+      int cf[8];
 #pragma unroll
-      for (int t = 0; t < 8; t++) sum += wv[r + t] * cf[t];
-      // g == 0: taps are {0,0,0,64,0,0,0,0} and the reference takes the filterCopy branch instead
-      // (TComInterpolationFilter.cpp:124-145); fy == 0 implies no row shift, so wv[r+3] is the sample itself
-      const int pred = g == 0 ? (int)if_copy(wv[r + 3], false, true, bd) : (int)if_round(sum, false, true, bd);
-      d[r] = o[r] - pred;
+      for (int t = 0; t < 8; t++) cf[t] = c_luma_taps[g][t];
+      if (up) {
+#pragma unroll
+        for (int r = 0; r < TS; r++) {
+          int sum = vr.offset;
+#pragma unroll
+          for (int t = 0; t < 8; t++) sum += v[r + t] * cf[t];
+          d[r] = o[r] - vround_filter(sum, vr);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < TS; r++) {
+          int sum = vr.offset;
+#pragma unroll
+          for (int t = 0; t < 8; t++) sum += v[r + 1 + t] * cf[t];
+          d[r] = o[r] - vround_filter(sum, vr);
+        }
+      }
     }
     if (hadamard) out[k] = had_cols<TS>(d, c);
     else {
@@ -931,6 +1002,7 @@ k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ j
   }
   sync();
 
+  const VRound vr = make_vround(bd);
   const bool t8 = jb.hadamard && ((w & 7) == 0) && ((h & 7) == 0);
   const int TS = t8 ? 8 : 4;
   const int tiles_x = w / TS, tiles = tiles_x * (h / TS);
@@ -950,8 +1022,8 @@ k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ j
         const int tyy = (t / tiles_x) * TS, txx = (t % tiles_x) * TS;
         const int ox = fxi - 1;
         uint32_t v[3];
-        if (t8) frac_unit<8, SM::HP>(&S.H[0][0], SM::HP * SM::HR, S.org, MAXW, basex + ox * dq, basey, dq, txx, tyy, c, true, bd, v);
-        else frac_unit<4, SM::HP>(&S.H[0][0], SM::HP * SM::HR, S.org, MAXW, basex + ox * dq, basey, dq, txx, tyy, c, jb.hadamard != 0, bd, v);
+        if (t8) frac_unit<8, SM::HP>(&S.H[0][0], SM::HP * SM::HR, S.org, MAXW, basex + ox * dq, basey, dq, txx, tyy, c, true, vr, v);
+        else frac_unit<4, SM::HP>(&S.H[0][0], SM::HP * SM::HR, S.org, MAXW, basex + ox * dq, basey, dq, txx, tyy, c, jb.hadamard != 0, vr, v);
         if (valid && c == 0) {
 #pragma unroll
           for (int k = 0; k < 3; k++) atomicAdd(&S.cost[refine_index(pass == 0, ox, k - 1)], v[k]);
@@ -959,21 +1031,21 @@ k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ j
       }
     }
     sync();
-    if (live && tid == 0) {
-      // xPatternRefinement (TEncSearch.cpp:730-757): dist >> bitIncrement + rate, strict '<', order as listed
-      uint32_t best = 0xFFFFFFFFu; int best_i = 0;
+    if (tid < 32) {
+      // xPatternRefinement (TEncSearch.cpp:730-757): dist >> bitIncrement + rate, strict '<' in the listed order =
+      // the first candidate that attains the minimum.  Lane i holds candidate i.
       const int scale = pass == 0 ? 1 : 0;
       const int ax = pass == 0 ? (jb.imvx << 1) : (((jb.imvx << 1) + hx) << 1);
       const int ay = pass == 0 ? (jb.imvy << 1) : (((jb.imvy << 1) + hy) << 1);
-      for (int i = 0; i < 9; i++) {
-        const int8_t* rf = pass == 0 ? c_refine_h[i] : c_refine_q[i];
-        uint32_t d = (S.cost[i] >> bi) + mv_cost(jb.lambda_cost, ax + rf[0], ay + rf[1], scale, jb.predx, jb.predy);
-        if (d < best) { best = d; best_i = i; }
-      }
-      const int8_t* rb = pass == 0 ? c_refine_h[best_i] : c_refine_q[best_i];
-      S.sel[0] = rb[0]; S.sel[1] = rb[1];
-      S.cost[9] = best;
-      for (int i = 0; i < 9; i++) S.cost[i] = 0;
+      const int i = tid < 9 ? tid : 0;
+      const int8_t* rf = pass == 0 ? c_refine_h[i] : c_refine_q[i];
+      uint32_t dcost = 0xFFFFFFFFu;
+      if (live && tid < 9) dcost = (S.cost[i] >> bi) + mv_cost(jb.lambda_cost, ax + rf[0], ay + rf[1], scale, jb.predx, jb.predy);
+      const uint32_t best = __reduce_min_sync(0xffffffffu, dcost);
+      const int best_i = __ffs(__ballot_sync(0xffffffffu, dcost == best)) - 1;
+      __syncwarp();
+      if (live && tid == best_i) { S.sel[0] = rf[0]; S.sel[1] = rf[1]; S.cost[9] = best; }
+      if (live && tid < 9) S.cost[tid] = 0;
     }
     sync();
     if (pass == 0) {
@@ -1154,7 +1226,7 @@ static int launch_frac(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job* jobs
   int r;
   if ((r = launch_frac_class<64, 64, 256, 1>(c, cur_slot, groups * 13, jobs_dev, out_dev, 13, TVC_ME_CENSUS, 0))) return r;
   if ((r = launch_frac_class<32, 32, 128, 1>(c, cur_slot, groups * 52, jobs_dev, out_dev, 52, TVC_ME_CENSUS, 13))) return r;
-  if ((r = launch_frac_class<16, 16, 64, 1>(c, cur_slot, groups * 208, jobs_dev, out_dev, 208, TVC_ME_CENSUS, 65))) return r;
+  if ((r = launch_frac_class<16, 16, 32, 4>(c, cur_slot, groups * 208, jobs_dev, out_dev, 208, TVC_ME_CENSUS, 65))) return r;
   return launch_frac_class<8, 8, 32, 4>(c, cur_slot, groups * 320, jobs_dev, out_dev, 320, TVC_ME_CENSUS, 273);
 }
 
@@ -1258,7 +1330,7 @@ int tvc_me_table_lookup(tvc_ctx* c, int ref_index, int pu_x, int pu_y, int pu_w,
 }
 
 static int launch_search(tvc_ctx* c, int cur_slot, int use_tables, int n, const tvc_me_job* jobs_dev, tvc_me_result* out_dev,
-                         const RasterBest* rast)
+                         const RasterBest* rast, unsigned long long* stats)
 {
   if (!c || !valid_slot(c, cur_slot) || n < 0 || (n && (!jobs_dev || !out_dev))) return set_err(c, TVC_ERR_ARG, "tvc_me_search_batch_dev: bad argument");
   if (use_tables && (!c->me_tables || c->me_num_refs == 0 || c->me_cur_slot != cur_slot))
@@ -1269,17 +1341,17 @@ static int launch_search(tvc_ctx* c, int cur_slot, int use_tables, int n, const 
   if (variant < 0) { const char* e = getenv("TVC_SEARCH_MINB"); variant = e ? atoi(e) : 4; }
   const uint16_t* tb = use_tables ? c->me_tables : nullptr;
   const int nctu = c->num_ctus_x * c->num_ctus_y;
-  if (variant >= 8) k_me_search<8><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast);
-  else if (variant >= 6) k_me_search<6><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast);
-  else if (variant >= 4) k_me_search<4><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast);
-  else k_me_search<1><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast);
+  if (variant >= 8) k_me_search<8><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast, stats);
+  else if (variant >= 6) k_me_search<6><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast, stats);
+  else if (variant >= 4) k_me_search<4><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast, stats);
+  else k_me_search<1><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast, stats);
   TVC_LAUNCH_CHECK(c);
   return TVC_OK;
 }
 
 int tvc_me_search_batch_dev(tvc_ctx* c, int cur_slot, int use_tables, int n, const tvc_me_job* jobs_dev, tvc_me_result* out_dev)
 {
-  return launch_search(c, cur_slot, use_tables, n, jobs_dev, out_dev, nullptr);
+  return launch_search(c, cur_slot, use_tables, n, jobs_dev, out_dev, nullptr, nullptr);
 }
 
 int tvc_me_search_batch(tvc_ctx* c, int cur_slot, int use_tables, int n, const tvc_me_job* jobs, tvc_me_result* out)
@@ -1416,17 +1488,19 @@ int tvc_me_frame_dev(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slot
     k_me_frame_jobs<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(pw, ph, nctu, c->num_ctus_x, num_refs, dslots, dpred, *cfg, c->fr_jobs);
     TVC_LAUNCH_CHECK(c);
   }
+  if (!c->fr_stats) TVC_CUDA(c, cudaMalloc(&c->fr_stats, 3 * sizeof(unsigned long long)));
+  TVC_CUDA(c, cudaMemsetAsync(c->fr_stats, 0, 3 * sizeof(unsigned long long), c->stream));
   const RasterBest* rast = nullptr;
   static int use_rast = -1;      // tuning knob (TVC_ME_RASTER=0 walks the raster per PU)
   if (use_rast < 0) { const char* e = getenv("TVC_ME_RASTER"); use_rast = e ? atoi(e) : 1; }
   if (cfg->use_tables && use_rast) {
-    ProfScope ps(c, TVC_PH_ME_SEARCH);
+    ProfScope ps(c, TVC_PH_ME_RASTER);
     dim3 grd(nctu, num_refs);
-    k_me_raster<<<grd, kRastThreads, 0, c->stream>>>(c->fr_jobs, c->me_tables, c->me_centers, nctu, 5, c->bi, (RasterBest*)c->fr_rast);
+    k_me_raster<<<grd, kRastThreads, 0, c->stream>>>(c->fr_jobs, c->me_tables, c->me_centers, nctu, 5, c->bi, (RasterBest*)c->fr_rast, c->fr_stats);
     TVC_LAUNCH_CHECK(c);
     rast = (const RasterBest*)c->fr_rast;
   }
-  if ((r = launch_search(c, cur_slot, cfg->use_tables, (int)n, c->fr_jobs, c->fr_int, rast))) return r;
+  if ((r = launch_search(c, cur_slot, cfg->use_tables, (int)n, c->fr_jobs, c->fr_int, rast, c->fr_stats))) return r;
   if (cfg->do_frac) {
     {
       ProfScope ps(c, TVC_PH_OTHER);
@@ -1437,6 +1511,17 @@ int tvc_me_frame_dev(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slot
   }
   if (int_dev) *int_dev = c->fr_int;
   if (frac_dev) *frac_dev = cfg->do_frac ? c->fr_frac : nullptr;
+  return TVC_OK;
+}
+
+int tvc_me_frame_stats(tvc_ctx* c, uint64_t stats[3])
+{
+  if (!c || !stats) return set_err(c, TVC_ERR_ARG, "tvc_me_frame_stats: bad argument");
+  if (!c->fr_stats) return set_err(c, TVC_ERR_STATE, "tvc_me_frame_stats: no frame pre-pass has run");
+  unsigned long long h[3];
+  TVC_CUDA(c, cudaMemcpyAsync(h, c->fr_stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  TVC_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 3; i++) stats[i] = h[i];
   return TVC_OK;
 }
 

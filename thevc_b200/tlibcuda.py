@@ -238,6 +238,11 @@ class TLibCuda:
                                      ptr(fres) if do_frac else None))
         return ires, fres
 
+    def me_frame_stats(self):
+        st = np.zeros(3, np.uint64)
+        self._ck(self.L.tvc_me_frame_stats(self.h, ptr(st)))
+        return {"search_granules": int(st[0]), "raster_served_candidates": int(st[1]), "raster_candidates": int(st[2])}
+
     # ------------------------------------------------------------------ TQ
     def fwd_transform_batch(self, resi_slot: int, tus: Sequence[TU], coef_elems: int) -> np.ndarray:
         coef = np.zeros(coef_elems, np.int32)
