@@ -811,10 +811,12 @@ __global__ void k_me_table_lookup(const uint16_t* __restrict__ tables, const tvc
 template <int MAXW, int MAXH>
 struct FracSmem {
   static constexpr int RP = MAXW + 8;                  // pitch of R
-  static constexpr int HP = MAXW + 2;                  // pitch of the horizontal planes (w+1 columns -> even)
-  static constexpr int HR = MAXH + 8;
+  static constexpr int HC = MAXW + 1;                  // columns of a horizontal plane (picture columns -1 .. w-1)
+  static constexpr int HR = MAXH + 8;                  // rows (picture rows -4 .. h+3)
+  static constexpr int CP = HR + 4;                    // column pitch: planes are stored COLUMN-major so that a lane's
+                                                       // vertical window is contiguous (64-bit loads, packed int16 pairs)
   int16_t R[RP * (MAXH + 8)];
-  int16_t H[4][HP * HR];
+  alignas(8) int16_t H[4][HC * CP];
   int16_t org[MAXW * MAXH];
   uint32_t cost[12];
   int sel[4];
@@ -886,15 +888,29 @@ __device__ __forceinline__ int vround_copy(int smp, const VRound& v)
   return __vimin_s32_relu((smp + v.coffset) >> v.cshift, v.maxv);
 }
 
-template <int TS, int HP>
+// 8 luma taps of fraction g packed as signed bytes: TA = c0..c3, TB = c4..c7 (operands of dp2a.lo / dp2a.hi)
+__device__ __forceinline__ void packed_taps(int g, int& ta, int& tb)
+{
+  const int8_t* cf = c_luma_taps[g];
+  ta = (cf[0] & 0xff) | ((cf[1] & 0xff) << 8) | ((cf[2] & 0xff) << 16) | ((int)cf[3] << 24);
+  tb = (cf[4] & 0xff) | ((cf[5] & 0xff) << 8) | ((cf[6] & 0xff) << 16) | ((int)cf[7] << 24);
+}
+
+template <int TS, int CP>
 __device__ __forceinline__ void frac_unit(const int16_t* __restrict__ H, int plane_elems, const int16_t* __restrict__ org, int opitch,
                                           int fx, int fy0, int dq, int tx, int ty, int c, bool hadamard, const VRound& vr, uint32_t (&out)[3])
 {
   const int ix = fx < 0 ? -1 : 0, f = fx & 3;
-  const int16_t* p = H + f * plane_elems + ty * HP + (tx + c + ix + 1);     // row index 0 of H is picture row -4
-  int v[TS + 8];
+  // column tx+c+ix of the plane (column index 0 is picture column -1), rows ty-4 .. ty+TS+3 (row index 0 is picture
+  // row -4): TS+8 consecutive int16 = (TS+8)/2 packed pairs; ty is a multiple of 4 and CP of 4: 8-byte aligned
+  constexpr int NW = (TS + 8) / 2;
+  const uint2* p = reinterpret_cast<const uint2*>(H + f * plane_elems + (tx + c + ix + 1) * CP + ty);
+  int W[NW];                                   // W[j] = rows (2j, 2j+1) of the window
 #pragma unroll
-  for (int j = 0; j < TS + 8; j++) v[j] = p[j * HP];                        // rows ty-4 .. ty+TS+3
+  for (int j = 0; j < NW / 2; j++) { const uint2 q = p[j]; W[2 * j] = (int)q.x; W[2 * j + 1] = (int)q.y; }
+  int P[NW - 1];                               // P[j] = rows (2j+1, 2j+2)
+#pragma unroll
+  for (int j = 0; j < NW - 1; j++) P[j] = (int)__funnelshift_r((unsigned)W[j], (unsigned)W[j + 1], 16);
   int o[TS];
 #pragma unroll
   for (int r = 0; r < TS; r++) o[r] = org[(ty + r) * opitch + tx + c];
@@ -907,36 +923,34 @@ __device__ __forceinline__ void frac_unit(const int16_t* __restrict__ H, int pla
     // fy is the same for every thread of the CTA (it depends on the pass and on k only): uniform branches
     if (g == 0) {
       // integer row: the reference takes the filterCopy branch (TComInterpolationFilter.cpp:124-145); fy == 0 has
-      // no row shift, so the sample is window row r + 4
+      // no row shift, so the sample is window row r + 4 (dp2a with taps (1,0) / (0,1) extracts a sign-extended half)
 #pragma unroll
-      for (int r = 0; r < TS; r++) d[r] = o[r] - vround_copy(v[r + 4], vr);
+      for (int r = 0; r < TS; r++) {
+        const int smp = ((r + 4) & 1) ? __dp2a_lo(W[(r + 4) >> 1], 0x0100, 0) : __dp2a_lo(W[(r + 4) >> 1], 0x0001, 0);
+        d[r] = o[r] - vround_copy(smp, vr);
+      }
     } else {
-      int cf[8];
+      int ta, tb;
+      packed_taps(g, ta, tb);
+      // output r filters window rows s0 .. s0+7 with s0 = r (row shift -1) or r + 1: four dp2a on packed row pairs
 #pragma unroll
-      for (int t = 0; t < 8; t++) cf[t] = c_luma_taps[g][t];
-      if (up) {
-#pragma unroll
-        for (int r = 0; r < TS; r++) {
-          int sum = vr.offset;
-#pragma unroll
-          for (int t = 0; t < 8; t++) sum += v[r + t] * cf[t];
-          d[r] = o[r] - vround_filter(sum, vr);
+      for (int r = 0; r < TS; r++) {
+        int sum = vr.offset;
+        if (up) {
+          if (r & 1) { const int j = (r - 1) >> 1; sum = __dp2a_lo(P[j], ta, sum); sum = __dp2a_hi(P[j + 1], ta, sum); sum = __dp2a_lo(P[j + 2], tb, sum); sum = __dp2a_hi(P[j + 3], tb, sum); }
+          else { const int j = r >> 1; sum = __dp2a_lo(W[j], ta, sum); sum = __dp2a_hi(W[j + 1], ta, sum); sum = __dp2a_lo(W[j + 2], tb, sum); sum = __dp2a_hi(W[j + 3], tb, sum); }
+        } else {
+          if (r & 1) { const int j = (r + 1) >> 1; sum = __dp2a_lo(W[j], ta, sum); sum = __dp2a_hi(W[j + 1], ta, sum); sum = __dp2a_lo(W[j + 2], tb, sum); sum = __dp2a_hi(W[j + 3], tb, sum); }
+          else { const int j = r >> 1; sum = __dp2a_lo(P[j], ta, sum); sum = __dp2a_hi(P[j + 1], ta, sum); sum = __dp2a_lo(P[j + 2], tb, sum); sum = __dp2a_hi(P[j + 3], tb, sum); }
         }
-      } else {
-#pragma unroll
-        for (int r = 0; r < TS; r++) {
-          int sum = vr.offset;
-#pragma unroll
-          for (int t = 0; t < 8; t++) sum += v[r + 1 + t] * cf[t];
-          d[r] = o[r] - vround_filter(sum, vr);
-        }
+        d[r] = o[r] - vround_filter(sum, vr);
       }
     }
     if (hadamard) out[k] = had_cols<TS>(d, c);
     else {
       uint32_t s = 0;
 #pragma unroll
-      for (int r = 0; r < TS; r++) s += (uint32_t)abs(d[r]);
+      for (int r = 0; r < TS; r++) s = __sad(d[r], 0, s);
 #pragma unroll
       for (int m = 1; m < TS; m <<= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
       out[k] = s;
@@ -990,13 +1004,13 @@ k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ j
       int t[8];
 #pragma unroll
       for (int k = 0; k < 8; k++) t[k] = p[k];
-      S.H[0][r * SM::HP + xi] = if_copy(t[3], true, false, bd);
+      S.H[0][xi * SM::CP + r] = if_copy(t[3], true, false, bd);
 #pragma unroll
       for (int f = 1; f < 4; f++) {
         int sum = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) sum += t[k] * (int)c_luma_taps[f][k];
-        S.H[f][r * SM::HP + xi] = if_round(sum, true, false, bd);
+        S.H[f][xi * SM::CP + r] = if_round(sum, true, false, bd);
       }
     }
   }
@@ -1022,8 +1036,8 @@ k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ j
         const int tyy = (t / tiles_x) * TS, txx = (t % tiles_x) * TS;
         const int ox = fxi - 1;
         uint32_t v[3];
-        if (t8) frac_unit<8, SM::HP>(&S.H[0][0], SM::HP * SM::HR, S.org, MAXW, basex + ox * dq, basey, dq, txx, tyy, c, true, vr, v);
-        else frac_unit<4, SM::HP>(&S.H[0][0], SM::HP * SM::HR, S.org, MAXW, basex + ox * dq, basey, dq, txx, tyy, c, jb.hadamard != 0, vr, v);
+        if (t8) frac_unit<8, SM::CP>(&S.H[0][0], SM::HC * SM::CP, S.org, MAXW, basex + ox * dq, basey, dq, txx, tyy, c, true, vr, v);
+        else frac_unit<4, SM::CP>(&S.H[0][0], SM::HC * SM::CP, S.org, MAXW, basex + ox * dq, basey, dq, txx, tyy, c, jb.hadamard != 0, vr, v);
         if (valid && c == 0) {
 #pragma unroll
           for (int k = 0; k < 3; k++) atomicAdd(&S.cost[refine_index(pass == 0, ox, k - 1)], v[k]);
@@ -1180,6 +1194,21 @@ __global__ void k_ub_imad(uint32_t* out, int iters, uint32_t a0, uint32_t b0)
 #pragma unroll
   for (int k = 0; k < 8; k++) s += acc[k];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void k_ub_dp2a(uint32_t* out, int iters, uint32_t a0, uint32_t b0)
+{
+  int a = (int)(a0 + threadIdx.x), b = (int)(b0 * threadIdx.x + 3);
+  int acc[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = __dp2a_lo(a, b, acc[k]);
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = __dp2a_hi(b, a, acc[k]);
+  }
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += acc[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)s;
 }
 __global__ void k_ub_lds128(uint32_t* out, int iters)
 {
@@ -1342,6 +1371,7 @@ static int launch_search(tvc_ctx* c, int cur_slot, int use_tables, int n, const 
   const uint16_t* tb = use_tables ? c->me_tables : nullptr;
   const int nctu = c->num_ctus_x * c->num_ctus_y;
   if (variant >= 8) k_me_search<8><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast, stats);
+  else if (variant == 5) k_me_search<5><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast, stats);
   else if (variant >= 6) k_me_search<6><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast, stats);
   else if (variant >= 4) k_me_search<4><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast, stats);
   else k_me_search<1><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast, stats);
@@ -1541,7 +1571,7 @@ int tvc_me_frame(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slots, c
 
 int tvc_ubench(tvc_ctx* c, int which, double* ginstr_per_s)
 {
-  if (!c || !ginstr_per_s || which < 0 || which > 3) return set_err(c, TVC_ERR_ARG, "tvc_ubench: bad argument");
+  if (!c || !ginstr_per_s || which < 0 || which > 4) return set_err(c, TVC_ERR_ARG, "tvc_ubench: bad argument");
   const int blocks = kNumSM * 8, threads = 256, iters = 4096;
   uint32_t* d = nullptr;
   TVC_CUDA(c, cudaMalloc(&d, (size_t)blocks * threads * 4));
@@ -1554,6 +1584,7 @@ int tvc_ubench(tvc_ctx* c, int which, double* ginstr_per_s)
       case TVC_UB_VABSDIFF4: k_ub_vabsdiff4<<<blocks, threads, 0, c->stream>>>(d, iters, 0x01020304u, 0x11213141u); per_thread = 8.0 * iters; break;
       case TVC_UB_IADD3: k_ub_iadd3<<<blocks, threads, 0, c->stream>>>(d, iters, 0x01020304u, 0x11213141u); per_thread = 16.0 * iters; break;
       case TVC_UB_IMAD: k_ub_imad<<<blocks, threads, 0, c->stream>>>(d, iters, 0x01020304u, 0x11213141u); per_thread = 16.0 * iters; break;
+      case TVC_UB_DP2A: k_ub_dp2a<<<blocks, threads, 0, c->stream>>>(d, iters, 0x01020304u, 0x11213141u); per_thread = 16.0 * iters; break;
       default: k_ub_lds128<<<blocks, threads, 0, c->stream>>>(d, iters); per_thread = 8.0 * iters; break;
     }
     c->launches++;
