@@ -9,8 +9,9 @@ pictures (cfg/encoder_lowdelay_P_main.cfg: SR 64, FEN 1, HadamardME 1, AMP 1, 8-
                           search (xTZSearch) and the fractional search (xPatternSearchFracDIF);
   2. motion compensation: Y/U/V prediction of the whole picture from a PU partition with quarter-pel MVs;
   3. residual           : org - pred (three planes);
-  4. transform + quant  : every TU size (luma 4..32, chroma 4..16) tiled over the picture (the residual
-                          quadtree visits each size), non-RDOQ quantiser with sign-data hiding;
+  4. transform + RDOQ   : every TU size (luma 4..32, chroma 4..16) tiled over the picture (the residual
+                          quadtree visits each size); forward transform, then xRateDistOptQuant (RDOQ 1 in the
+                          cfg) with sign-data hiding against a synthetic CABAC bit-estimate table;
   5. dequant + inverse transform + reconstruction for the same TUs.
 
 `value`  = frames/s with every input resident in HBM (device-pointer ABI entry points).
@@ -40,7 +41,7 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-METRIC = "1080p LDP hot-path fps (ME pre-pass + interp/MC + TQ per P picture)"
+METRIC = "1080p LDP hot-path fps (ME pre-pass + interp/MC + T/RDOQ/IQ/IT per P picture)"
 UNIT = "frames/s"
 W, H, BD = 1920, 1080, 8
 NUM_REFS = 4
@@ -95,6 +96,23 @@ def make_tu_list(w, h, qp, bd):
             counts[log2 - 2] += k
             rows.append(a)
     return np.concatenate(rows), np.array(counts, np.int32), off
+
+
+def make_rdoq_list(tus, lam_luma, lam_chroma):
+    """tvc_rdoq_tu of every TU: inter TUs, diagonal scan, luma at transform depth 0 (root cbf), chroma cbf context 5,
+    one bit-estimate table (index 0)"""
+    from thevc_b200.capi import RDOQ_TU_DTYPE
+    a = np.zeros(len(tus), RDOQ_TU_DTYPE)
+    luma = tus["plane"] == 0
+    a["log2_size"] = tus["log2_size"]
+    a["is_luma"] = luma
+    a["scan_idx"] = 0
+    a["qp_per"], a["qp_rem"] = tus["qp_per"], tus["qp_rem"]
+    a["cbf_ctx"] = np.where(luma, -1, 5)
+    a["est_index"] = 0
+    a["coef_offset"] = tus["coef_offset"]
+    a["lambda_"] = np.where(luma, lam_luma, lam_chroma)
+    return a
 
 
 def make_pu_list(w, h, rng, ctu_filter=None):
@@ -154,6 +172,11 @@ class Workload:
         self.pred += rng.integers(-6, 7, self.pred.shape).astype(np.int32)
         self.pus = make_pu_list(W, H, rng)
         self.tus, self.tu_counts, self.coef_elems = make_tu_list(W, H, QP, BD)
+        import rdoq_cases
+        self.lam_luma, self.lam_chroma = rdoq_cases.lambda_for(QP), rdoq_cases.lambda_for(QP) * 0.85
+        self.rtus = make_rdoq_list(self.tus, self.lam_luma, self.lam_chroma)
+        self.est = rdoq_cases.make_est(np.random.default_rng(seed + 2))      # oracle.EstBits == tvc_est_bits layout
+        self.est_bytes = np.frombuffer(bytes(self.est), np.uint8).copy()
 
     def pic_bytes(self):
         p = self.pics[0]
@@ -281,7 +304,8 @@ def _cpu_ctu_work(args):
     sel["coef_offset"] = np.concatenate([[0], np.cumsum(sizes)[:-1]])
     levels = np.zeros(int(sizes.sum()), np.int32)
     abs_sum = np.zeros(len(sel), np.uint32)
-    orc.orc_fwd_tq_batch(tri(resi), cur.stride, cur.cstride, len(sel), optr(sel.view(np.int32)), 0, 1, BD, optr(levels), optr(abs_sum))
+    orc.orc_fwd_rdoq_batch(tri(resi), cur.stride, cur.cstride, len(sel), optr(sel.view(np.int32)), 1, BD, C.byref(wl.est), wl.lam_luma,
+                           wl.lam_chroma, optr(levels), optr(abs_sum))
     t4 = time.perf_counter()
     orc.orc_inv_tq_batch(tri(resi2), tri(predp), tri(recon), cur.stride, cur.cstride, len(sel), optr(sel.view(np.int32)), BD, optr(levels))
     t5 = time.perf_counter()
@@ -364,14 +388,14 @@ def reference_arm(args):
             "dtype": "u8/int16/int32", "data": "synthetic", "impl": "reference",
             "config": workload_config(),
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d CTUs per step of the %.1f CTU-equivalents of a picture: census ME x4 refs + MC + T/Q + IQ/IT" % (per_step, equiv)},
+                             "sample": "%d CTUs per step of the %.1f CTU-equivalents of a picture: census ME x4 refs + MC + T + RDOQ + IQ/IT" % (per_step, equiv)},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 def workload_config():
     return {"workload": "cfg/encoder_lowdelay_P_main.cfg 1920x1080 8-bit synthetic, 1 P picture x 4 refs, SR 64, FEN 1, HAD 1: "
-                        "ME pre-pass (SAD tables + TZ + frac for the 593-PU census of 510 CTUs) + MC + residual + T/Q + IQ/IT",
+                        "ME pre-pass (SAD tables + TZ + frac for the 593-PU census of 510 CTUs) + MC + residual + T + RDOQ + IQ/IT",
             "width": W, "height": H, "num_refs": NUM_REFS, "search_range": SEARCH_RANGE, "qp": QP,
             "l2": "inputs+outputs per step (34.8 GB of SAD tables) exceed the 126 MB L2; no explicit flush",
             "parallelism": "independent sequences per GPU, no collective"}
@@ -430,8 +454,9 @@ def gpu_arm(args):
 
     def dev(a):
         return torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).cuda(local)
-    pus_d, tus_d = dev(wl.pus), dev(wl.tus)
+    pus_d, tus_d, rtus_d, est_d = dev(wl.pus), dev(wl.tus), dev(wl.rtus), dev(wl.est_bytes)
     levels_d = torch.zeros(wl.coef_elems, dtype=torch.int32, device="cuda")
+    coef_d = torch.zeros(wl.coef_elems, dtype=torch.int32, device="cuda")
     abs_d = torch.zeros(n_tu, dtype=torch.int32, device="cuda")
     counts = wl.tu_counts
     pi, pf = C.c_void_p(), C.c_void_p()
@@ -447,8 +472,10 @@ def gpu_arm(args):
         ck(L.tvc_mc_batch_dev(h, SLOT_PRED, n_pu, C.c_void_p(pus_d.data_ptr())))
         for pl, pw, ph in planes_wh:
             ck(L.tvc_pic_subtract(h, SLOT_RESI, SLOT_CUR, SLOT_PRED, pl, 0, 0, pw, ph))
-        ck(L.tvc_fwd_tq_batch_dev(h, SLOT_RESI, n_tu, C.c_void_p(tus_d.data_ptr()), ptr(counts), C.byref(qc),
-                                  C.c_void_p(levels_d.data_ptr()), None, C.c_void_p(abs_d.data_ptr())))
+        ck(L.tvc_fwd_transform_batch_dev(h, SLOT_RESI, n_tu, C.c_void_p(tus_d.data_ptr()), ptr(counts), C.c_void_p(coef_d.data_ptr())))
+        ck(L.tvc_rdoq_batch_dev(h, n_tu, C.c_void_p(rtus_d.data_ptr()), 1, C.c_void_p(est_d.data_ptr()), C.byref(qc),
+                                C.c_void_p(coef_d.data_ptr()), C.c_void_p(levels_d.data_ptr()), None, wl.coef_elems,
+                                C.c_void_p(abs_d.data_ptr())))
         ck(L.tvc_inv_tq_batch_dev(h, SLOT_RESI2, SLOT_PRED, SLOT_RECON, n_tu, C.c_void_p(tus_d.data_ptr()), ptr(counts),
                                   C.c_void_p(levels_d.data_ptr())))
 
@@ -469,11 +496,12 @@ def gpu_arm(args):
         ck(L.tvc_mc_batch(h, SLOT_PRED, n_pu, ptr(wl.pus)))
         for pl, pw, ph in planes_wh:
             ck(L.tvc_pic_subtract(h, SLOT_RESI, SLOT_CUR, SLOT_PRED, pl, 0, 0, pw, ph))
-        ck(L.tvc_fwd_tq_batch(h, SLOT_RESI, n_tu, ptr(wl.tus), C.byref(qc), ptr(levels_h), None, wl.coef_elems, ptr(abs_h)))
+        ck(L.tvc_fwd_rdoq_batch(h, SLOT_RESI, n_tu, ptr(wl.tus), ptr(wl.rtus), 1, ptr(wl.est_bytes), C.byref(qc), ptr(levels_h), None,
+                                wl.coef_elems, ptr(abs_h)))
         ck(L.tvc_inv_tq_batch(h, SLOT_RESI2, SLOT_PRED, SLOT_RECON, n_tu, ptr(wl.tus), ptr(levels_h), wl.coef_elems))
         t.download(SLOT_RECON, into=recon_h)
 
-    h2d = (NUM_REFS + 1) * wl.pic_bytes() + wl.pred.nbytes + wl.pus.nbytes + 2 * wl.tus.nbytes + levels_h.nbytes
+    h2d = (NUM_REFS + 1) * wl.pic_bytes() + wl.pred.nbytes + wl.pus.nbytes + 2 * wl.tus.nbytes + wl.rtus.nbytes + wl.est_bytes.nbytes + levels_h.nbytes
     d2h = ires_h.nbytes + fres_h.nbytes + levels_h.nbytes + abs_h.nbytes + wl.pic_bytes()
 
     def barrier():
@@ -566,6 +594,7 @@ def gpu_arm(args):
         "me_frac": frac_bytes,
         "mc": float(sum(int(p["w"]) * int(p["h"]) for p in wl.pus)) * 1.5 * 2 * 2,
         "fwd_tq": samples_tq * (2 + 4),
+        "rdoq": samples_tq * (4 + 4) + float(n_tu) * 40,
         "inv_tq": samples_tq * (4 + 2 + 2 + 2),
     }
     ph_ms = {k: (v[0] / args.steps) for k, v in phases.items()}
@@ -587,7 +616,7 @@ def gpu_arm(args):
         roofline["note"] = traffic[dom]["note"]
     # every ME kernel against the same HBM peak (the step has no single dominant kernel: four of them take 7-8 ms each)
     kernels = {}
-    for k in ("me_tables", "me_raster", "me_search", "me_frac"):
+    for k in ("me_tables", "me_raster", "me_search", "me_frac", "rdoq"):
         if ph_ms.get(k, 0) > 0:
             a = alg_bytes[k] / (ph_ms[k] * 1e-3) / 1e9
             kernels[k] = {"ms": ph_ms[k], "algorithmic_GB": alg_bytes[k] / 1e9, "achieved_GBps": a, "frac_of_hbm_peak": a / peak,
@@ -613,7 +642,7 @@ def gpu_arm(args):
         equiv = frame_ctu_equiv(valid)
         per_ctu = wall / len(ctus)
         cpu = {"value": 1.0 / (per_ctu * equiv), "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "%d interior CTUs of %.1f CTU-equivalents per picture (%.1f s of CPU work): census ME x4 refs + MC + T/Q + IQ/IT" % (len(ctus), equiv, wall),
+               "sample": "%d interior CTUs of %.1f CTU-equivalents per picture (%.1f s of CPU work): census ME x4 refs + MC + T + RDOQ + IQ/IT" % (len(ctus), equiv, wall),
                "phase_s_per_ctu": {k: float(np.mean([r[k] for r in res])) for k in ("me", "mc", "fwd_tq", "inv_tq")}}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

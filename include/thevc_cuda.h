@@ -327,12 +327,67 @@ int tvc_xT(tvc_ctx* ctx, int use_dst, const int16_t* resi, int stride, int32_t* 
 int tvc_xIT(tvc_ctx* ctx, int use_dst, const int32_t* coef, int16_t* resi, int stride, int w, int h);
 int tvc_xDeQuant(tvc_ctx* ctx, const int32_t* qcoef, int32_t* coef, int w, int h, int per, int rem);
 
+/* ---------------------------------------------------------------------------------- RDOQ
+ * Replaces TComTrQuant::xRateDistOptQuant (TComTrQuant.cpp:1719-2305) with its helpers xGetCodedLevel,
+ * xGetICRateCost, xGetICRate, xGetRateLast, xGetRateSigCoef, xGetRateSigCoeffGroup (:2446-2698),
+ * getSigCtxInc, calcPatternSigCtx, getSigCoeffGroupCtxInc (:2315-2428, 2707-2743) and the flat-list
+ * error scale of setErrScaleCoeff (:2794-2817), batched over TUs.  The Lagrangian costs are IEEE
+ * doubles evaluated in the reference's order without FMA contraction, so levels, uiAbsSum and ARL
+ * coefficients are the reference's.  The CABAC bit estimates are an INPUT: the host's
+ * TEncEntropy::estimateBit fills them from its live context models exactly as today.           */
+typedef struct {                 /* estBitsSbacStruct, TComTrQuant.h:59-72: same members, same order, so
+                                    HM passes m_pcEstBitsSbac with a cast                            */
+  int32_t sig_cg[2][2];          /* significantCoeffGroupBits */
+  int32_t sig[42][2];            /* significantBits           */
+  int32_t last_x[32];            /* lastXBits                 */
+  int32_t last_y[32];            /* lastYBits                 */
+  int32_t greater_one[24][2];    /* m_greaterOneBits          */
+  int32_t level_abs[6][2];       /* m_levelAbsBits            */
+  int32_t block_cbp[15][2];      /* blockCbpBits              */
+  int32_t block_root_cbp[4][2];  /* blockRootCbpBits          */
+  int32_t scan_zigzag[2], scan_non_zigzag[2];
+} tvc_est_bits;
+
+typedef struct {
+  int32_t log2_size;           /* 2..5                                                           */
+  int32_t is_luma;             /* eTType == TEXT_LUMA                                            */
+  int32_t scan_idx;            /* 0 diag (also for SCAN_ZIGZAG), 1 hor, 2 ver; 1/2 only for log2 <= 3 */
+  int32_t qp_per, qp_rem;      /* m_cQP after setQPforQuant                                      */
+  int32_t cbf_ctx;             /* < 0: inter luma TU at transform depth 0 (blockRootCbpBits[0]);
+                                  else the blockCbpBits row: luma (trDepth==0 ? 1 : 0), chroma 5 + trDepth */
+  int32_t est_index;           /* which tvc_est_bits of the call's table array                   */
+  int32_t coef_offset;         /* element offset of this TU's raster in coef / levels / arl      */
+  double lambda;               /* m_dLambda after selectLambda                                   */
+} tvc_rdoq_tu;
+
+/* coef: xT output (tvc_fwd_transform_batch layout); levels: signed TCoeff out; arl: written only when
+ * qc->use_arl (else untouched, may be NULL); abs_sum[i] = uiAbsSum of TU i.  qc->is_intra_slice is unused. */
+int tvc_rdoq_batch(tvc_ctx* ctx, int n, const tvc_rdoq_tu* tus, int n_est, const tvc_est_bits* est,
+                   const tvc_quant_cfg* qc, const int32_t* coef, int32_t* levels, int32_t* arl, size_t coef_elems,
+                   uint32_t* abs_sum);
+/* device-resident, asynchronous on the context stream */
+int tvc_rdoq_batch_dev(tvc_ctx* ctx, int n, const tvc_rdoq_tu* tus_dev, int n_est, const tvc_est_bits* est_dev,
+                       const tvc_quant_cfg* qc, const int32_t* coef_dev, int32_t* levels_dev, int32_t* arl_dev,
+                       size_t coef_elems, uint32_t* abs_sum_dev);
+/* residual plane -> forward transform (device coefficients, no host copy) for tvc_rdoq_batch_dev */
+int tvc_fwd_transform_batch_dev(tvc_ctx* ctx, int resi_slot, int n, const tvc_tu* tus_dev, const int32_t* counts,
+                                int32_t* coef_dev);
+/* transformNxN with RDOQ on: residual plane -> xT -> xRateDistOptQuant, coefficients stay on the device.
+ * tus[i] and rdoq_tus[i] describe the same TU (same log2_size and coef_offset); host pointers.  */
+int tvc_fwd_rdoq_batch(tvc_ctx* ctx, int resi_slot, int n, const tvc_tu* tus, const tvc_rdoq_tu* rdoq_tus, int n_est,
+                       const tvc_est_bits* est, const tvc_quant_cfg* qc, int32_t* levels, int32_t* arl, size_t coef_elems,
+                       uint32_t* abs_sum);
+/* drop-in for one xRateDistOptQuant call on host blocks (w x w, raster)                          */
+int tvc_xRateDistOptQuant(tvc_ctx* ctx, const int32_t* coef, int32_t* qcoef, int32_t* arl, int w, int is_luma,
+                          int scan_idx, int qp_per, int qp_rem, int cbf_ctx, int sign_hide, int use_arl,
+                          double lambda, const tvc_est_bits* est, uint32_t* abs_sum);
+
 /* ---------------------------------------------------------------------------------- per-phase device timing
  * CUDA events recorded on the context stream around every kernel group, so that bench.py can report
  * each kernel's duration measured live inside the timed region (not under a profiler).         */
 enum {
   TVC_PH_ME_TABLES = 0, TVC_PH_ME_SEARCH = 1, TVC_PH_ME_FRAC = 2, TVC_PH_MC = 3, TVC_PH_FWD_TQ = 4,
-  TVC_PH_INV_TQ = 5, TVC_PH_OTHER = 6, TVC_PH_ME_RASTER = 7, TVC_PH_COUNT = 8
+  TVC_PH_INV_TQ = 5, TVC_PH_OTHER = 6, TVC_PH_ME_RASTER = 7, TVC_PH_RDOQ = 8, TVC_PH_COUNT = 9
 };
 int tvc_prof_enable(tvc_ctx* ctx, int on);
 /* synchronises the stream, adds the elapsed time of every recorded pair to per-phase sums and returns

@@ -42,6 +42,18 @@ class FracResult(C.Structure):
     _fields_ = [("halfx", ci), ("halfy", ci), ("qtrx", ci), ("qtry", ci), ("cost_half", cu), ("cost", cu)]
 
 
+class EstBits(C.Structure):
+    """estBitsSbacStruct (TComTrQuant.h:59-72) as 254 plain ints, same member order"""
+    _fields_ = [("sig_cg", ci * 2 * 2), ("sig", ci * 2 * 42), ("last_x", ci * 32), ("last_y", ci * 32),
+                ("greater_one", ci * 2 * 24), ("level_abs", ci * 2 * 6), ("block_cbp", ci * 2 * 15),
+                ("block_root_cbp", ci * 2 * 4), ("scan_zigzag", ci * 2), ("scan_non_zigzag", ci * 2)]
+
+
+class RdoqParam(C.Structure):
+    _fields_ = [("log2_size", ci), ("is_luma", ci), ("scan_idx", ci), ("qp_per", ci), ("qp_rem", ci), ("bd", ci),
+                ("cbf_ctx", ci), ("sign_hide", ci), ("use_arl", ci), ("lambda_", C.c_double)]
+
+
 class QuantParam(C.Structure):
     _fields_ = [("qp_per", ci), ("qp_rem", ci), ("base_per", ci), ("is_intra_slice", ci),
                 ("sign_hide", ci), ("use_arl", ci), ("bd", ci)]
@@ -51,7 +63,7 @@ def build(force: bool = False) -> None:
     """Compile libhm_oracle.so (always possible) and, when /root/reference is present,
     _ref/libhmref.so.  Building the checker is not using it."""
     so = os.path.join(HERE, "libhm_oracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("hm_oracle.c", "hm_oracle_me.c", "hm_oracle_tq.c", "hm_oracle_frame.c", "hm_oracle.h")]
+    srcs = [os.path.join(HERE, f) for f in ("hm_oracle.c", "hm_oracle_me.c", "hm_oracle_tq.c", "hm_oracle_frame.c", "hm_oracle_rdoq.c", "hm_oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", HERE, "-B", "oracle"])
     ref_so = os.path.join(HERE, "_ref", "libhmref.so")
@@ -126,11 +138,16 @@ def lib():
     L.orc_quant.argtypes = [i32p, i32p, vp, ci, ci, C.POINTER(QuantParam), u32p, C.POINTER(cu)]
     L.orc_quant.restype = None
     L.orc_dequant.argtypes = [i32p, i32p, ci, ci, ci, ci, ci]; L.orc_dequant.restype = None
+    L.orc_rdoq.argtypes = [i32p, i32p, vp, C.POINTER(RdoqParam), C.POINTER(EstBits), u32p, C.POINTER(cu)]
+    L.orc_rdoq.restype = None
+    L.orc_rdoq_err_scale.argtypes = [ci, ci, ci]; L.orc_rdoq_err_scale.restype = C.c_double
     L.orc_census.argtypes = [vp]; L.orc_census.restype = None
     L.orc_me_frame_ctu.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, cu, ci, ci, ci, ci, ci, vp, vp]
     L.orc_me_frame_ctu.restype = None
     L.orc_mc_batch.argtypes = [vp, ci, ci, vp, ci, vp, ci]; L.orc_mc_batch.restype = None
     L.orc_fwd_tq_batch.argtypes = [vp, ci, ci, ci, vp, ci, ci, ci, vp, vp]; L.orc_fwd_tq_batch.restype = None
+    L.orc_fwd_rdoq_batch.argtypes = [vp, ci, ci, ci, vp, ci, ci, C.POINTER(EstBits), C.c_double, C.c_double, vp, vp]
+    L.orc_fwd_rdoq_batch.restype = None
     L.orc_inv_tq_batch.argtypes = [vp, vp, vp, ci, ci, ci, vp, ci, vp]; L.orc_inv_tq_batch.restype = None
     _LIB = L
     return L
@@ -171,6 +188,10 @@ def ref():
     R.ref_set_qp.argtypes = [ci, ci, ci, ci, C.POINTER(ci), C.POINTER(ci)]; R.ref_set_qp.restype = None
     R.ref_quant.argtypes = [i32p, i32p, i32p, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, C.POINTER(cu)]
     R.ref_quant.restype = None
+    if hasattr(R, "ref_rdoq"):
+        R.ref_rdoq.argtypes = [i32p, i32p, i32p, ci, ci, ci, ci, ci, ci, ci, ci, ci, C.c_double, C.POINTER(EstBits), C.POINTER(cu)]
+        R.ref_rdoq.restype = None
+        R.ref_est_bits_size.argtypes = []; R.ref_est_bits_size.restype = ci
     R.ref_dequant.argtypes = [i32p, i32p, ci, ci, ci, ci, ci]; R.ref_dequant.restype = None
     R.ref_extend_border.argtypes = [vp, ci, ci, ci, ci, ci]; R.ref_extend_border.restype = None
     ip = C.POINTER(ci)

@@ -130,6 +130,37 @@ void orc_quant(const int32_t* coef, int32_t* qcoef, int32_t* arl, int w, int h,
                const orc_quant_param* qp, const uint32_t* scan, uint32_t* abs_sum);
 void orc_dequant(const int32_t* qcoef, int32_t* coef, int w, int h, int per, int rem, int bd);
 
+/* ------------------------------------------------------------------ RDOQ (hm_oracle_rdoq.c) */
+/* estBitsSbacStruct, TComTrQuant.h:59-72: same members, same order, plain ints */
+typedef struct {
+  int32_t sig_cg[2][2];          /* significantCoeffGroupBits[NUM_SIG_CG_FLAG_CTX][2]   */
+  int32_t sig[42][2];            /* significantBits[NUM_SIG_FLAG_CTX][2]                */
+  int32_t last_x[32];            /* lastXBits                                           */
+  int32_t last_y[32];            /* lastYBits                                           */
+  int32_t greater_one[24][2];    /* m_greaterOneBits[NUM_ONE_FLAG_CTX][2]               */
+  int32_t level_abs[6][2];       /* m_levelAbsBits[NUM_ABS_FLAG_CTX][2]                 */
+  int32_t block_cbp[15][2];      /* blockCbpBits[3*NUM_QT_CBF_CTX][2]                   */
+  int32_t block_root_cbp[4][2];  /* blockRootCbpBits[4][2]                              */
+  int32_t scan_zigzag[2], scan_non_zigzag[2];
+} orc_est_bits;
+
+typedef struct {
+  int log2_size;        /* 2..5                                              */
+  int is_luma;          /* eTType == TEXT_LUMA                               */
+  int scan_idx;         /* 0 diag, 1 hor, 2 ver (zigzag is mapped to diag)   */
+  int qp_per, qp_rem;   /* m_cQP after setQPforQuant                         */
+  int bd;               /* g_uiBitDepth + g_uiBitIncrement                   */
+  int cbf_ctx;          /* < 0: inter luma TU at transform depth 0 (root cbf);
+                           else index into blockCbpBits (chroma offset included) */
+  int sign_hide;        /* PPS sign-data-hiding flag                         */
+  int use_arl;          /* m_bUseAdaptQpSelect                               */
+  double lambda;        /* m_dLambda (selectLambda)                          */
+} orc_rdoq_param;
+
+double orc_rdoq_err_scale(int log2_size, int qp_rem, int bd);
+void orc_rdoq(const int32_t* coef, int32_t* qcoef, int32_t* arl, const orc_rdoq_param* p,
+              const orc_est_bits* est, const uint32_t* scan, uint32_t* abs_sum);
+
 /* ------------------------------------------------------------------ frame-level drivers (hm_oracle_frame.c) */
 #define ORC_CENSUS 593
 void orc_census(int16_t* out /* ORC_CENSUS * 6: x, y, w, h, cu_x, cu_y */);
@@ -139,6 +170,8 @@ void orc_me_frame_ctu(const Pel* cur, const Pel* const* refs, int num_refs, int 
 void orc_mc_batch(const Pel* const* ref_planes, int stride_y, int stride_c, Pel* const* dst, int n, const int32_t* pus, int bd);
 void orc_fwd_tq_batch(const Pel* const* resi, int stride_y, int stride_c, int n, const int32_t* tus,
                       int is_intra_slice, int sign_hide, int bd, int32_t* levels, uint32_t* abs_sum);
+void orc_fwd_rdoq_batch(const Pel* const* resi, int stride_y, int stride_c, int n, const int32_t* tus, int sign_hide, int bd,
+                        const orc_est_bits* est, double lambda_luma, double lambda_chroma, int32_t* levels, uint32_t* abs_sum);
 void orc_inv_tq_batch(Pel* const* resi, const Pel* const* pred, Pel* const* recon, int stride_y, int stride_c, int n,
                       const int32_t* tus, int bd, const int32_t* levels);
 

@@ -120,6 +120,27 @@ void orc_fwd_tq_batch(const Pel* const* resi /* [plane] */, int stride_y, int st
   }
 }
 
+/* transformNxN with the RDOQ quantiser (xT + xRateDistOptQuant) over a TU list: inter TUs (diagonal scan), luma
+ * at transform depth 0 (root cbf) and chroma cbf context 5, one bit-estimate table and Lagrangian for the batch
+ * (the bench workload; per-TU contexts are exercised by the RDOQ parity tests). */
+void orc_fwd_rdoq_batch(const Pel* const* resi, int stride_y, int stride_c, int n, const int32_t* tus, int sign_hide, int bd,
+                        const orc_est_bits* est, double lambda_luma, double lambda_chroma, int32_t* levels, uint32_t* abs_sum)
+{
+  int32_t coef[32 * 32];
+  uint32_t scan[32 * 32];
+  for (int i = 0; i < n; i++) {
+    const int32_t* t = tus + 10 * i;
+    int pl = t[0], N = 1 << t[3], st = pl ? stride_c : stride_y;
+    const Pel* r = resi[pl] + (ptrdiff_t)t[2] * st + t[1];
+    orc_xT(0, r, st, coef, N, N, bd - 8);
+    orc_rdoq_param p = {t[3], pl == 0, 0, t[6], t[7], bd, pl == 0 ? -1 : 5, sign_hide, 0, pl == 0 ? lambda_luma : lambda_chroma};
+    orc_scan(0, t[3], scan);
+    uint32_t s = 0;
+    orc_rdoq(coef, levels + t[9], 0, &p, est, scan, &s);
+    if (abs_sum) abs_sum[i] = s;
+  }
+}
+
 void orc_inv_tq_batch(Pel* const* resi, const Pel* const* pred, Pel* const* recon, int stride_y, int stride_c, int n,
                       const int32_t* tus, int bd, const int32_t* levels)
 {

@@ -271,6 +271,41 @@ void ref_quant(int* coef, int* qcoef, int* arl, int w, int h, int qpy, int base_
   tq_detach(c);
 }
 
+/* xRateDistOptQuant (TComTrQuant.cpp:1719-2305, private) through xQuant with RDOQ switched on.
+ * est points at 254 ints laid out like estBitsSbacStruct (TComTrQuant.h:59-72) and is copied into the
+ * quantiser's own table; the minimal CU carries what the function reads: prediction mode, intra
+ * directions (-> getCoefScanIdx), transform index (-> cbf context), PPS sign hiding.  The flat scaling
+ * lists are rebuilt on every call because their error scale depends on g_uiBitIncrement. */
+void ref_rdoq(int* coef, int* qcoef, int* arl, int w, int qpy, int qp_bd_offset, int is_luma, int is_intra_cu,
+              int intra_dir, int tr_idx, int sign_hide, int use_arl, double lambda, const int* est, unsigned* abs_sum)
+{
+  TqCtx* c = tq_get();
+  static std::vector<UChar> tridx(256, 0);
+  c->tq.setFlatScalingList();
+  c->tq.m_bUseRDOQ = true;
+  c->tq.m_bUseAdaptQpSelect = use_arl != 0;
+  c->tq.m_useTansformSkipFast = false;
+  c->slice.setSliceType(is_intra_cu ? I_SLICE : P_SLICE);
+  c->sps.setQpBDOffsetY(qp_bd_offset);
+  c->sps.setQpBDOffsetC(qp_bd_offset);
+  c->pps.setSignHideFlag(sign_hide);
+  c->predmode[0] = is_intra_cu ? MODE_INTRA : MODE_INTER;
+  c->lumadir[0] = (UChar)intra_dir;
+  c->chromadir[0] = (UChar)intra_dir;
+  tridx[0] = (UChar)tr_idx;
+  c->cu.m_puhTrIdx = &tridx[0];
+  memcpy(c->tq.m_pcEstBitsSbac, est, sizeof(estBitsSbacStruct));
+  c->tq.setLambda(lambda, lambda);
+  c->tq.selectLambda(is_luma ? TEXT_LUMA : TEXT_CHROMA_U);
+  c->tq.setQPforQuant(qpy, is_luma ? TEXT_LUMA : TEXT_CHROMA_U, qp_bd_offset, 0);
+  UInt acsum = *abs_sum;
+  Int* parl = arl;
+  c->tq.xQuant(&c->cu, coef, qcoef, parl, w, w, acsum, is_luma ? TEXT_LUMA : TEXT_CHROMA_U, 0);
+  *abs_sum = acsum;
+  c->tq.m_bUseRDOQ = false;
+}
+int ref_est_bits_size(void) { return (int)sizeof(estBitsSbacStruct); }
+
 /* xDeQuant flat branch (TComTrQuant.cpp:1272-1355) */
 void ref_dequant(int* qcoef, int* coef, int w, int h, int qpy, int qp_bd_offset, int is_luma)
 {

@@ -204,3 +204,57 @@ def test_cuda_reproduces_reference_goldens(bd):
                mg.crc(p.v[pu.y // 2:(pu.y + pu.h) // 2, pu.x // 2:(pu.x + pu.w) // 2]))
         assert got == tuple(int(v) for v in mc)
     t.close()
+
+
+# ----------------------------------------------------------------------------------- RDOQ goldens
+def _rdoq_cases():
+    import make_rdoq_golden as mr
+    g = np.load(os.path.join(HERE, "golden", "rdoq_golden.npz"))
+    ests = []
+    for row in g["est"]:
+        e = oracle.EstBits()
+        C.memmove(C.byref(e), np.ascontiguousarray(row, np.int32).ctypes.data, C.sizeof(e))
+        ests.append(e)
+    cases = [dict(zip(mr.COLS, (int(v) for v in p))) for p in g["params"]]
+    return g, ests, cases
+
+
+def test_oracle_reproduces_rdoq_goldens(orc):
+    """xRateDistOptQuant outputs of the compiled reference (rdoq_golden.npz) == the C restatement"""
+    g, ests, cases = _rdoq_cases()
+    for c, lam in zip(cases, g["lambdas"]):
+        nn = 1 << (2 * c["log2"])
+        o = c["offset"]
+        scan = np.zeros(nn, np.uint32)
+        orc.orc_scan(c["scan_idx"], c["log2"], scan)
+        par = oracle.RdoqParam(c["log2"], c["is_luma"], c["scan_idx"], c["per"], c["rem"], c["bd"], c["cbf_ctx"], c["sign_hide"],
+                               c["use_arl"], float(lam))
+        q = np.zeros(nn, np.int32); a = np.zeros(nn, np.int32); s = C.c_uint32(0)
+        orc.orc_rdoq(np.ascontiguousarray(g["coef"][o:o + nn]), q, ptr(a), C.byref(par), C.byref(ests[c["est"]]), scan, C.byref(s))
+        assert np.array_equal(q, g["levels"][o:o + nn]) and s.value == c["abs_sum"], c
+        assert np.array_equal(a, g["arl"][o:o + nn]), c
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bd", [8, 10])
+def test_cuda_reproduces_rdoq_goldens(bd):
+    from thevc_b200 import TLibCuda
+    from thevc_b200.capi import EstBits, QuantCfg, RdoqTU
+    g, ests, cases = _rdoq_cases()
+    abi_est = []
+    for e in ests:
+        x = EstBits(); C.memmove(C.byref(x), C.byref(e), C.sizeof(x)); abi_est.append(x)
+    t = TLibCuda(mg.W, mg.H, bd, num_slots=1)
+    try:
+        for sh in (0, 1):
+            for arl in (0, 1):
+                sel = [(c, float(l)) for c, l in zip(cases, g["lambdas"]) if c["bd"] == bd and c["sign_hide"] == sh and c["use_arl"] == arl]
+                tus = [RdoqTU(c["log2"], c["is_luma"], c["scan_idx"], c["per"], c["rem"], c["cbf_ctx"], c["est"], c["offset"], l) for c, l in sel]
+                lev, ga, sums = t.rdoq_batch(tus, abi_est, QuantCfg(0, sh, arl), g["coef"])
+                for i, (c, _) in enumerate(sel):
+                    nn, o = 1 << (2 * c["log2"]), c["offset"]
+                    assert np.array_equal(lev[o:o + nn], g["levels"][o:o + nn]) and int(sums[i]) == c["abs_sum"], c
+                    if arl:
+                        assert np.array_equal(ga[o:o + nn], g["arl"][o:o + nn]), c
+    finally:
+        t.close()

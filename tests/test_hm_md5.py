@@ -1,5 +1,5 @@
 """End-to-end drop-in check (north star): the reference encoder with the TLibCuda hooks
-(build/hm/TAppEncoderCuda: xTZSearch, xPatternSearchFracDIF, xT, xIT, xDeQuant served by the CUDA
+(build/hm/TAppEncoderCuda: xTZSearch, xPatternSearchFracDIF, xT, xIT, xDeQuant, xRateDistOptQuant served by the CUDA
 library, SAD tables on) must write the SAME BITSTREAM as the unmodified reference encoder
 (oracle/_ref/bin/TAppEncoderStatic), and the reference decoder must accept it with matching picture
 hashes.  Both binaries are built from /root/reference by committed recipes (thevc_b200/host/Makefile,
@@ -67,13 +67,15 @@ def test_bitstream_md5_identical_to_reference(tmp_path, cfg, frames, extra):
     _yuv(yuv, w, h, frames)
     ref_bin, cuda_bin = str(tmp_path / "ref.bin"), str(tmp_path / "cuda.bin")
     _encode(ENC_REF, cfg, yuv, w, h, frames, ref_bin, extra=extra)
-    r = _encode(ENC_CUDA, cfg, yuv, w, h, frames, cuda_bin, env={"TVC_HM": "me,frac,tq,mc,tables"}, extra=extra)
+    r = _encode(ENC_CUDA, cfg, yuv, w, h, frames, cuda_bin, env={"TVC_HM": "me,frac,tq,rdoq,mc,tables"}, extra=extra)
     served = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda:")]
     assert served and "kernel launches" in served[-1], r.stderr[-500:]
     print(served[-1])
     if "lowdelay" in cfg:
         assert " 0 xTZSearch" not in served[-1]              # the hooks really ran
     assert " 0 xT," not in served[-1]
+    if "--RDOQ=0" not in extra:
+        assert " 0 xRateDistOptQuant" not in served[-1]      # RDOQ=1 in every cfg: the quantiser decisions came from k_rdoq
     assert os.path.getsize(ref_bin) > 1000
     assert _md5(cuda_bin) == _md5(ref_bin)
     # the reference decoder accepts the stream and every picture hash matches

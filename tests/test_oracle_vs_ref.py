@@ -398,3 +398,47 @@ def test_motion_compensation_vs_reference(orc, hmref, bd):
             assert np.array_equal(e, po)
         n += 1
     assert n > 150
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_rdoq(orc, hmref, bd):
+    """xRateDistOptQuant (TComTrQuant.cpp:1719-2305): levels, uiAbsSum and ARL coefficients of the restatement
+    equal the reference's for every TU size, scan, cbf context, with and without sign-data hiding."""
+    import rdoq_cases as rc
+    rng = np.random.default_rng(4242 + bd)
+    hmref.ref_init(bd)
+    qp_bd_offset = 6 * (bd - 8)
+    changed = zeroed = 0
+    for n in (4, 8, 16, 32):
+        log2 = int(np.log2(n))
+        for qp in (4, 22, 27, 32, 37, 51):
+            est = rc.make_est(rng)
+            for is_luma in ((1, 0) if n < 32 else (1,)):
+                per, rem = C.c_int(), C.c_int()
+                orc.orc_set_qp(qp, is_luma, qp_bd_offset, 0, C.byref(per), C.byref(rem))
+                for kind in range(6):
+                    for (icu, ldir, tr_idx, sh, arl) in [(0, 1, 0, 1, 1), (0, 1, 1, 1, 0), (1, 26, 0, 1, 1), (1, 10, 1, 1, 0),
+                                                         (1, 1, 0, 0, 0), (1, 34, 2, 1, 0)]:
+                        coef = rc.make_coef(rng, log2, per.value, bd, kind)
+                        lam = rc.lambda_for(qp) * float(rng.uniform(0.5, 2.0))
+                        scan_idx = rc.scan_idx_for(icu, is_luma, n, ldir)
+                        scan = np.zeros(n * n, np.uint32)
+                        orc.orc_scan(scan_idx, log2, scan)
+                        par = oracle.RdoqParam(log2, is_luma, scan_idx, per.value, rem.value, bd,
+                                               rc.cbf_ctx_for(icu, is_luma, tr_idx), sh, arl, lam)
+                        qa = np.zeros(n * n, np.int32); qb = np.zeros(n * n, np.int32)
+                        aa = np.full(n * n, -7, np.int32); ab = np.full(n * n, -7, np.int32)
+                        sa, sb = C.c_uint32(0), C.c_uint32(0)
+                        orc.orc_rdoq(coef, qa, ptr(aa), C.byref(par), C.byref(est), scan, C.byref(sa))
+                        hmref.ref_rdoq(coef.copy(), qb, ab, n, qp, qp_bd_offset, is_luma, icu, ldir, tr_idx, sh, arl, lam,
+                                       C.byref(est), C.byref(sb))
+                        key = (n, qp, is_luma, kind, icu, ldir, tr_idx, sh, arl)
+                        assert sa.value == sb.value, key
+                        assert np.array_equal(qa, qb), key
+                        assert np.array_equal(aa, ab), key
+                        # how much RDOQ moved away from plain rounding (the test must exercise the decisions)
+                        plain = (np.abs(coef).astype(np.int64) * [26214, 23302, 20560, 18396, 16384, 14564][rem.value]
+                                 + (1 << (14 + per.value + 15 - bd - log2 - 1))) >> (14 + per.value + 15 - bd - log2)
+                        changed += int(np.count_nonzero(np.abs(qa) != np.minimum(plain, 1 << 30)))
+                        zeroed += int(np.count_nonzero((qa == 0) & (plain > 0)))
+    assert changed > 5000 and zeroed > 3000, (changed, zeroed)

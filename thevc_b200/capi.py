@@ -75,7 +75,7 @@ class MeFrameCfg(C.Structure):
 
 
 ME_CENSUS = 593
-PHASES = ("me_tables", "me_search", "me_frac", "mc", "fwd_tq", "inv_tq", "other", "me_raster")
+PHASES = ("me_tables", "me_search", "me_frac", "mc", "fwd_tq", "inv_tq", "other", "me_raster", "rdoq")
 
 # numpy views of the ABI structs (same layout) for bulk results
 ME_RESULT_DTYPE = np.dtype([("mvx", "<i4"), ("mvy", "<i4"), ("sad", "<u4"), ("n_sads", "<u4")])
@@ -92,6 +92,21 @@ class TU(C.Structure):
 class QuantCfg(C.Structure):
     _fields_ = [("is_intra_slice", i32), ("sign_hide", i32), ("use_arl", i32)]
 
+
+class EstBits(C.Structure):
+    """tvc_est_bits = estBitsSbacStruct (TComTrQuant.h:59-72)"""
+    _fields_ = [("sig_cg", i32 * 2 * 2), ("sig", i32 * 2 * 42), ("last_x", i32 * 32), ("last_y", i32 * 32),
+                ("greater_one", i32 * 2 * 24), ("level_abs", i32 * 2 * 6), ("block_cbp", i32 * 2 * 15),
+                ("block_root_cbp", i32 * 2 * 4), ("scan_zigzag", i32 * 2), ("scan_non_zigzag", i32 * 2)]
+
+
+class RdoqTU(C.Structure):
+    _fields_ = [("log2_size", i32), ("is_luma", i32), ("scan_idx", i32), ("qp_per", i32), ("qp_rem", i32),
+                ("cbf_ctx", i32), ("est_index", i32), ("coef_offset", i32), ("lambda_", C.c_double)]
+
+
+RDOQ_TU_DTYPE = np.dtype([(n, "<i4") for n in ("log2_size", "is_luma", "scan_idx", "qp_per", "qp_rem", "cbf_ctx", "est_index",
+                                               "coef_offset")] + [("lambda_", "<f8")])
 
 # every symbol include/thevc_cuda.h declares: name -> (restype, argtypes)
 SIGNATURES = {
@@ -137,6 +152,11 @@ SIGNATURES = {
     "tvc_inv_tq_batch": (ci, [vp, ci, ci, ci, ci, vp, vp, C.c_size_t]),
     "tvc_fwd_tq_batch_dev": (ci, [vp, ci, ci, vp, vp, C.POINTER(QuantCfg), vp, vp, vp]),
     "tvc_inv_tq_batch_dev": (ci, [vp, ci, ci, ci, ci, vp, vp, vp]),
+    "tvc_rdoq_batch": (ci, [vp, ci, vp, ci, vp, C.POINTER(QuantCfg), vp, vp, vp, C.c_size_t, vp]),
+    "tvc_rdoq_batch_dev": (ci, [vp, ci, vp, ci, vp, C.POINTER(QuantCfg), vp, vp, vp, C.c_size_t, vp]),
+    "tvc_fwd_transform_batch_dev": (ci, [vp, ci, ci, vp, vp, vp]),
+    "tvc_fwd_rdoq_batch": (ci, [vp, ci, ci, vp, vp, ci, vp, C.POINTER(QuantCfg), vp, vp, C.c_size_t, vp]),
+    "tvc_xRateDistOptQuant": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, C.c_double, vp, C.POINTER(u32)]),
     "tvc_xT": (ci, [vp, ci, vp, ci, vp, ci, ci]),
     "tvc_xIT": (ci, [vp, ci, vp, vp, ci, ci, ci]),
     "tvc_xDeQuant": (ci, [vp, vp, vp, ci, ci, ci, ci]),

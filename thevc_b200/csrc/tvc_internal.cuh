@@ -55,6 +55,8 @@ struct tvc_ctx {
   std::vector<tvc::Pic> pics;
   tvc::PlaneTable planes;
   tvc::Scratch in, out;           // staging for host-pointer entry points
+  void* rdoq_scratch = nullptr;   // per-coefficient RDOQ working arrays (device)
+  size_t rdoq_scratch_elems = 0;
   std::string err;
   uint64_t launches = 0;
   int num_ctus_x = 0, num_ctus_y = 0;
@@ -131,6 +133,12 @@ struct ProfScope {
     return e;
   }
 };
+
+// coding scans (initSigLastScan, TComRom.cpp:564-690) on the device: [scan_idx 0 diag,1 hor,2 ver][log2-2]
+struct ScanTables { const uint16_t* s[3][4]; };
+int ensure_scans(tvc_ctx* c, ScanTables& st);          // tvc_tq.cu
+// range-checks a host TU list (grouped by ascending log2_size) and counts TUs per size
+int validate_tus(tvc_ctx* c, int plane_slot, int n, const tvc_tu* tus, size_t coef_elems, int counts[4]);   // tvc_tq.cu
 
 // ---- table layout of the ME pre-pass (shared by producer and consumers) ----------------------
 // T[ref][ctu][cand 129*129][by 16][q 4][par 2][bx 4] uint16: one candidate = 1 KB contiguous

@@ -48,7 +48,6 @@ __device__ __forceinline__ int tcoef(int k, int n, bool dst)
 
 __device__ __forceinline__ int clip16(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }
 
-struct ScanTables { const uint16_t* s[3][4]; };   // [scan_idx][log2-2], device pointers
 
 template <int LOG2> struct TuSmem {
   static constexpr int N = 1 << LOG2;
@@ -383,7 +382,7 @@ static void build_scan(int scan_idx, int log2, std::vector<uint16_t>& out)
   }
 }
 
-static int ensure_scans(tvc_ctx* c, ScanTables& st)
+int ensure_scans(tvc_ctx* c, ScanTables& st)
 {
   if (g_scan_device != c->cfg.device) {
     for (int s = 0; s < 3; s++)
@@ -401,7 +400,7 @@ static int ensure_scans(tvc_ctx* c, ScanTables& st)
   return TVC_OK;
 }
 
-static int validate_tus(tvc_ctx* c, int plane_slot, int n, const tvc_tu* tus, size_t coef_elems, int counts[4])
+int validate_tus(tvc_ctx* c, int plane_slot, int n, const tvc_tu* tus, size_t coef_elems, int counts[4])
 {
   const Pic& p = c->pics[plane_slot];
   counts[0] = counts[1] = counts[2] = counts[3] = 0;
@@ -486,6 +485,16 @@ int tvc_fwd_tq_batch_dev(tvc_ctx* c, int resi_slot, int n, const tvc_tu* tus_dev
   if (n == 0) return TVC_OK;
   int cn[4] = {counts[0], counts[1], counts[2], counts[3]};
   return launch_fwd<true>(c, resi_slot, cn, tus_dev, *qc, levels_dev, arl_dev, abs_sum_dev);
+}
+
+int tvc_fwd_transform_batch_dev(tvc_ctx* c, int resi_slot, int n, const tvc_tu* tus_dev, const int32_t* counts, int32_t* coef_dev)
+{
+  if (!c || !valid_slot(c, resi_slot) || n < 0 || (n && (!tus_dev || !coef_dev)) || check_counts(n, counts))
+    return set_err(c, TVC_ERR_ARG, "tvc_fwd_transform_batch_dev: bad argument");
+  if (n == 0) return TVC_OK;
+  int cn[4] = {counts[0], counts[1], counts[2], counts[3]};
+  tvc_quant_cfg q0 = {0, 0, 0};
+  return launch_fwd<false>(c, resi_slot, cn, tus_dev, q0, coef_dev, nullptr, nullptr);
 }
 
 int tvc_inv_tq_batch_dev(tvc_ctx* c, int resi_slot, int pred_slot, int recon_slot, int n, const tvc_tu* tus_dev,

@@ -64,6 +64,9 @@ def main():
                  r'\1  if ( tlibcuda_xIT( uiMode, plCoef, pResidual, uiStride, iWidth, iHeight ) ) return;\n', "xIT")
     s = sub_once(s, r'(Void TComTrQuant::xDeQuant\( const TCoeff\* pSrc, Int\* pDes, Int iWidth, Int iHeight, Int scalingListType \)\r?\n\{\r?\n)',
                  r'\1  if ( !getUseScalingList() && tlibcuda_xDeQuant( pSrc, pDes, iWidth, iHeight, m_cQP.m_iPer, m_cQP.m_iRem ) ) return;\n', "xDeQuant")
+    s = sub_once(s, r'(  Int    iQBits      = m_cQP\.m_iBits;\r?\n  Double dTemp       = 0;)',
+                 r'  if ( !getUseScalingList() && tlibcuda_rdoq( pcCU, plSrcCoeff, piDstCoeff, piArlDstCoeff, uiWidth, uiHeight, uiAbsSum, (int)eTType, uiAbsPartIdx, m_cQP.m_iPer, m_cQP.m_iRem, m_dLambda, m_pcEstBitsSbac, m_bUseAdaptQpSelect ) ) return;\n\1',
+                 "xRateDistOptQuant")
     wr(os.path.join(out, "TLibCommon", "TComTrQuant.cpp"), s)
     # ---- TComPrediction.cpp: xPredInterUni (shared by encoder and decoder)
     s = rd(os.path.join(lib, "TLibCommon", "TComPrediction.cpp"))

@@ -14,6 +14,7 @@
 #undef private
 #undef protected
 #include "TLibCommon/TComRom.h"
+#include "TLibCommon/ContextTables.h"
 #include "TLibCommon/TComPattern.h"
 #include "TLibCommon/TComDataCU.h"
 #include "TLibCommon/TComPic.h"
@@ -37,14 +38,14 @@ struct DevPic {                 // one registered TComPicYuv: host buffer range 
 
 struct State {
   tvc_ctx* h = nullptr;
-  bool on_me = true, on_frac = true, on_tq = true, on_mc = true, on_tables = true, verbose = false, disabled = false;
+  bool on_me = true, on_frac = true, on_tq = true, on_rdoq = true, on_mc = true, on_tables = true, verbose = false, disabled = false;
   int w = 0, ht = 0;
   std::vector<DevPic> slots;
   unsigned long long clock = 0;
   int cur_slot = -1;
   int table_refs[8];
   int num_table_refs = 0;
-  unsigned long long n_tz = 0, n_frac = 0, n_xt = 0, n_xit = 0, n_dq = 0, n_mc = 0;
+  unsigned long long n_tz = 0, n_frac = 0, n_xt = 0, n_xit = 0, n_dq = 0, n_mc = 0, n_rdoq = 0;
 };
 
 State& S()
@@ -68,8 +69,8 @@ void report()
 {
   State& s = S();
   if (s.h)
-    fprintf(stderr, "TLibCuda: %llu xTZSearch, %llu xPatternSearchFracDIF, %llu xT, %llu xIT, %llu xDeQuant, %llu xPredInterUni calls served; %llu kernel launches\n",
-            s.n_tz, s.n_frac, s.n_xt, s.n_xit, s.n_dq, s.n_mc, (unsigned long long)tvc_launch_count(s.h));
+    fprintf(stderr, "TLibCuda: %llu xTZSearch, %llu xPatternSearchFracDIF, %llu xT, %llu xIT, %llu xDeQuant, %llu xRateDistOptQuant, %llu xPredInterUni calls served; %llu kernel launches\n",
+            s.n_tz, s.n_frac, s.n_xt, s.n_xit, s.n_dq, s.n_rdoq, s.n_mc, (unsigned long long)tvc_launch_count(s.h));
 }
 
 void parse_env()
@@ -80,6 +81,7 @@ void parse_env()
   s.on_me = strstr(e, "me") != nullptr;
   s.on_frac = strstr(e, "frac") != nullptr;
   s.on_tq = strstr(e, "tq") != nullptr;
+  s.on_rdoq = strstr(e, "rdoq") != nullptr;
   s.on_mc = strstr(e, "mc") != nullptr;
   s.on_tables = strstr(e, "tables") != nullptr;
   s.verbose = strstr(e, "verbose") != nullptr;
@@ -91,7 +93,7 @@ void ensure_ctx(int w, int ht)
   if (s.disabled || (s.h && s.w >= w && s.ht >= ht)) return;
   static bool parsed = false;
   if (!parsed) { parse_env(); parsed = true; atexit(report); }
-  if (!s.on_me && !s.on_frac && !s.on_tq && !s.on_mc) { s.disabled = true; return; }     // TVC_HM=none: the unmodified path
+  if (!s.on_me && !s.on_frac && !s.on_tq && !s.on_rdoq && !s.on_mc) { s.disabled = true; return; }     // TVC_HM=none: the unmodified path
   if (s.h) {                  // the decoder learns the picture size after its first transforms: start over with the real size
     tvc_ctx_destroy(s.h);
     s.h = nullptr;
@@ -287,5 +289,26 @@ bool tlibcuda_xDeQuant(const int* src, int* dst, int w, int h, int per, int rem)
   if (!s.h || !s.on_tq || w != h) return false;
   CK(tvc_xDeQuant(s.h, src, dst, w, h, per, rem));
   s.n_dq++;
+  return true;
+}
+
+bool tlibcuda_rdoq(TComDataCU* cu, int* src, int* dst, int* arl, unsigned w, unsigned h, unsigned& absSum, int ttype,
+                   unsigned absPartIdx, int per, int rem, double lambda, const void* est, bool useArl)
+{
+  ensure_tq_ctx();
+  State& s = S();
+  if (!s.h || !s.on_rdoq || w != h) return false;
+  static_assert(sizeof(tvc_est_bits) == 254 * sizeof(int), "estBitsSbacStruct layout");
+  const bool luma = ttype == TEXT_LUMA;
+  const bool intra = cu->isIntra(absPartIdx);
+  unsigned scan = cu->getCoefScanIdx(absPartIdx, w, luma, intra);        // :1767-1772
+  const int scan_idx = scan == SCAN_HOR ? 1 : (scan == SCAN_VER ? 2 : 0);
+  int cbf_ctx;                                                             // :2103-2115
+  if (!intra && luma && cu->getTransformIdx(absPartIdx) == 0) cbf_ctx = -1;
+  else cbf_ctx = (ttype ? TEXT_CHROMA : ttype) * NUM_QT_CBF_CTX + (int)cu->getCtxQtCbf(absPartIdx, (TextType)ttype, cu->getTransformIdx(absPartIdx));
+  if (!useArl) memset(arl, 0, sizeof(int) * w * h);                        // :1783
+  CK(tvc_xRateDistOptQuant(s.h, src, dst, arl, (int)w, luma ? 1 : 0, scan_idx, per, rem, cbf_ctx,
+                           cu->getSlice()->getPPS()->getSignHideFlag() ? 1 : 0, useArl ? 1 : 0, lambda, (const tvc_est_bits*)est, &absSum));
+  s.n_rdoq++;
   return true;
 }

@@ -10,7 +10,7 @@
  * fallback of ours.  A CUDA error is fatal (exit(EXIT_FAILURE)), like the reference's own errors.
  *
  * Which hooks are active is chosen with the environment variable TVC_HM (comma list of
- * me,frac,tq,mc,tables; default all; "none" runs the unmodified path).
+ * me,frac,tq,rdoq,mc,tables; default all; "none" runs the unmodified path).
  */
 #ifndef TLIBCUDA_HM_H
 #define TLIBCUDA_HM_H
@@ -42,5 +42,8 @@ bool tlibcuda_pred_inter_uni(TComDataCU* cu, TComPic* refPic, unsigned partAddr,
 bool tlibcuda_xT(unsigned mode, short* resi, unsigned stride, int* coef, int w, int h);
 bool tlibcuda_xIT(unsigned mode, int* coef, short* resi, unsigned stride, int w, int h);
 bool tlibcuda_xDeQuant(const int* src, int* dst, int w, int h, int per, int rem);
+/* TComTrQuant::xRateDistOptQuant (TComTrQuant.cpp:1719): est is m_pcEstBitsSbac (estBitsSbacStruct == tvc_est_bits) */
+bool tlibcuda_rdoq(TComDataCU* cu, int* src, int* dst, int* arl, unsigned w, unsigned h, unsigned& absSum, int ttype,
+                   unsigned absPartIdx, int per, int rem, double lambda, const void* est, bool useArl);
 
 #endif

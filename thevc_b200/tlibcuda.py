@@ -12,7 +12,8 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import capi
-from .capi import (CensusPU, Config, DistJob, FracJob, FracResult, MeCenter, MeFrameCfg, MeJob, MeResult, PU, QuantCfg, TU, ptr)
+from .capi import (CensusPU, Config, DistJob, EstBits, FracJob, FracResult, MeCenter, MeFrameCfg, MeJob, MeResult, PU, QuantCfg,
+                   RdoqTU, TU, ptr)
 
 
 class TvcError(RuntimeError):
@@ -264,6 +265,39 @@ class TLibCuda:
         arr = _arr(TU, tus)
         self._ck(self.L.tvc_inv_tq_batch(self.h, resi_slot, pred_slot, recon_slot, len(tus), C.cast(arr, C.c_void_p),
                                          ptr(levels), levels.size))
+
+    def rdoq_batch(self, tus: Sequence[RdoqTU], est: Sequence[EstBits], qc: QuantCfg, coef: np.ndarray):
+        """xRateDistOptQuant over a TU list: (levels, arl or None, abs_sum)"""
+        coef = np.ascontiguousarray(coef, np.int32)
+        lev = np.zeros(coef.size, np.int32)
+        arl = np.zeros(coef.size, np.int32) if qc.use_arl else None
+        abs_sum = np.zeros(len(tus), np.uint32)
+        ta, ea = _arr(RdoqTU, tus), _arr(EstBits, est)
+        self._ck(self.L.tvc_rdoq_batch(self.h, len(tus), C.cast(ta, C.c_void_p), len(est), C.cast(ea, C.c_void_p), C.byref(qc),
+                                       ptr(coef), ptr(lev), ptr(arl) if arl is not None else None, coef.size, ptr(abs_sum)))
+        return lev, arl, abs_sum
+
+    def fwd_rdoq_batch(self, resi_slot: int, tus: Sequence[TU], rtus: Sequence[RdoqTU], est: Sequence[EstBits], qc: QuantCfg,
+                       coef_elems: int):
+        """transformNxN with RDOQ on (xT + xRateDistOptQuant), coefficients stay on the device"""
+        lev = np.zeros(coef_elems, np.int32)
+        arl = np.zeros(coef_elems, np.int32) if qc.use_arl else None
+        abs_sum = np.zeros(len(tus), np.uint32)
+        ta, ra, ea = _arr(TU, tus), _arr(RdoqTU, rtus), _arr(EstBits, est)
+        self._ck(self.L.tvc_fwd_rdoq_batch(self.h, resi_slot, len(tus), C.cast(ta, C.c_void_p), C.cast(ra, C.c_void_p), len(est),
+                                           C.cast(ea, C.c_void_p), C.byref(qc), ptr(lev), ptr(arl) if arl is not None else None,
+                                           coef_elems, ptr(abs_sum)))
+        return lev, arl, abs_sum
+
+    def xRateDistOptQuant(self, coef: np.ndarray, n: int, is_luma: int, scan_idx: int, per: int, rem: int, cbf_ctx: int,
+                          sign_hide: int, use_arl: int, lam: float, est: EstBits):
+        coef = np.ascontiguousarray(coef, np.int32)
+        q = np.zeros(n * n, np.int32)
+        arl = np.zeros(n * n, np.int32)
+        s = C.c_uint32(0)
+        self._ck(self.L.tvc_xRateDistOptQuant(self.h, ptr(coef), ptr(q), ptr(arl), n, is_luma, scan_idx, per, rem, cbf_ctx,
+                                              sign_hide, use_arl, lam, C.byref(est), C.byref(s)))
+        return q, arl, s.value
 
     def xT(self, use_dst: int, resi: np.ndarray, off: int, stride: int, n: int) -> np.ndarray:
         coef = np.zeros(n * n, np.int32)
