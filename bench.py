@@ -401,6 +401,60 @@ def workload_config():
             "parallelism": "independent sequences per GPU, no collective"}
 
 
+# --------------------------------------------------------------------------------------- whole-encoder leg
+def run_hm_encode(frames, device_index=0):
+    """BASELINE.json metric (i): end-to-end 1080p low-delay-P encode.  The unmodified reference encoder
+    (oracle/_ref/bin/TAppEncoderStatic) and the reference encoder with the TLibCuda hooks (build/hm/TAppEncoderCuda:
+    integer + fractional ME of the CU loop served by look-up from census-wide tvc_me_ctu batches on the GPU; CABAC, RDO,
+    transforms stay the host's own code) encode the same synthetic 1920x1080 sequence, concurrently, one process each.
+    fps = frames / wall time of the whole process (start-up, I picture and file I/O included); bitstream md5 compared."""
+    import hashlib
+    import tempfile
+    import synth
+    enc_ref = os.path.join(ROOT, "oracle", "_ref", "bin", "TAppEncoderStatic")
+    enc_cuda = os.path.join(ROOT, "build", "hm", "TAppEncoderCuda")
+    cfg = os.path.join(ROOT, "build", "hm", "cfg", "encoder_lowdelay_P_main.cfg")
+    for pth in (enc_ref, enc_cuda, cfg):
+        if not os.path.exists(pth):
+            return {"unavailable": "%s not built (needs /root/reference at build time)" % os.path.relpath(pth, ROOT)}
+    with tempfile.TemporaryDirectory() as d:
+        yuv = os.path.join(d, "in.yuv")
+        seq = synth.make_sequence(W, H, frames, seed=20261018)
+        with open(yuv, "wb") as f:
+            for y, u, v in seq:
+                f.write(y.astype(np.uint8).tobytes()); f.write(u.astype(np.uint8).tobytes()); f.write(v.astype(np.uint8).tobytes())
+        base = ["-c", cfg, "-i", yuv, "-wdt", str(W), "-hgt", str(H), "-fr", "30", "-f", str(frames), "--SEIpictureDigest=1"]
+        env = dict(os.environ, TVC_HM="me,frac,tables", CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(device_index)))
+        t0 = time.perf_counter()
+        pr = subprocess.Popen([enc_ref] + base + ["-b", os.path.join(d, "ref.bin")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        pc = subprocess.Popen([enc_cuda] + base + ["-b", os.path.join(d, "cuda.bin")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+        done = {}
+
+        def wait(name, p):
+            out, err = p.communicate()
+            done[name] = (time.perf_counter() - t0, p.returncode, out, err or "")
+        th = [threading.Thread(target=wait, args=("ref", pr)), threading.Thread(target=wait, args=("cuda", pc))]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        if done["ref"][1] != 0 or done["cuda"][1] != 0:
+            return {"error": "encoder exit codes ref=%d cuda=%d: %s" % (done["ref"][1], done["cuda"][1], done["cuda"][3][-300:])}
+
+        def md5(pth):
+            return hashlib.md5(open(pth, "rb").read()).hexdigest()
+
+        def ets(out):
+            return [int(ln.split("[ET")[1].split("]")[0]) for ln in out.splitlines() if ln.startswith("POC") and "[ET" in ln]
+        m_ref, m_cuda = md5(os.path.join(d, "ref.bin")), md5(os.path.join(d, "cuda.bin"))
+        served = [ln for ln in done["cuda"][3].splitlines() if ln.startswith("TLibCuda")]
+        return {"frames": frames, "config": "cfg/encoder_lowdelay_P_main.cfg 1920x1080 synthetic, 1 I + %d P pictures, one process per encoder" % (frames - 1),
+                "reference_fps": frames / done["ref"][0], "ours_fps": frames / done["cuda"][0],
+                "reference_wall_s": done["ref"][0], "ours_wall_s": done["cuda"][0],
+                "reference_picture_seconds": ets(done["ref"][2]), "ours_picture_seconds": ets(done["cuda"][2]),
+                "bitstream_md5_equal": m_ref == m_cuda, "bitstream_md5": m_cuda, "hooks": served}
+
+
 # --------------------------------------------------------------------------------------- N > 1 host logic
 def rank_seed(seed, rank):
     """independent synthetic sequence per rank (an LDP sequence is one dependency chain)"""
@@ -645,6 +699,16 @@ def gpu_arm(args):
                "sample": "%d interior CTUs of %.1f CTU-equivalents per picture (%.1f s of CPU work): census ME x4 refs + MC + T + RDOQ + IQ/IT" % (len(ctus), equiv, wall),
                "phase_s_per_ctu": {k: float(np.mean([r[k] for r in res])) for k in ("me", "mc", "fwd_tq", "inv_tq")}}
 
+    # ---- whole-encoder leg (metric (i) of BASELINE.json): after the context is gone so that the encoder's own 34.8 GB
+    # of SAD tables fit beside nothing else
+    t.close()
+    t = None
+    if world == 1 and args.hm_frames > 0:
+        try:
+            sub["hm_encode"] = run_hm_encode(args.hm_frames, local)
+        except Exception as ex:      # the leg must never take the hot-path line down with it
+            sub["hm_encode"] = {"error": repr(ex)[:300]}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/int16/int32", "data": "synthetic", "config": workload_config(),
@@ -652,7 +716,6 @@ def gpu_arm(args):
                     "ms_per_step": ms_e2e, "steps": k_e2e},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "detail": sub}
     print(json.dumps(line))
-    t.close()
 
 
 def main():
@@ -664,6 +727,7 @@ def main():
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--cpu-ctus", type=int, default=48, help="CTUs of the CPU-baseline sample (1 core)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--hm-frames", type=int, default=5, help="pictures of the whole-encoder 1080p leg (0 = skip)")
     ap.add_argument("--ref-ctus-per-core", type=int, default=4, help="--impl reference: CTUs per core and step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -516,6 +516,53 @@ def test_me_frame_prepass(ctx8, orc):
     assert checked > 2000
 
 
+def test_me_ctu_group(ctx8, orc):
+    """tvc_me_ctu: one (CTU, reference) census group with an explicit predictor.  The frame pre-pass run with that
+    predictor for the CTU gives the same 593 results (itself oracle-checked above); predictors different from the one the
+    SAD tables were centred on are served too (candidates outside the table window are evaluated from the pictures),
+    checked against the oracle; and the table-less form agrees."""
+    t = ctx8
+    seq = synth.make_sequence(W, H, 3)
+    cur = synth.to_hostpic(seq[2], W, H)
+    refs = [synth.to_hostpic(seq[1], W, H), synth.to_hostpic(seq[0], W, H)]
+    t.upload(0, cur); t.upload(1, refs[0]); t.upload(2, refs[1])
+    nctu = t.ctus_x * t.ctus_y
+    rng = np.random.default_rng(65)
+    pred = rng.integers(-40, 41, (2, nctu, 2)).astype(np.int32)
+    lc = orc.orc_lambda_motion_sad(41.3)
+    ires, fres = t.me_frame(0, [1, 2], pred, lc)          # leaves the SAD tables of this picture behind
+    census = t.me_census()
+    for (ri, ctu) in [(0, 0), (1, 9), (0, nctu - 1), (1, t.ctus_x * (t.ctus_y - 1))]:
+        gi, gf = t.me_ctu(0, ri, 1 + ri, ctu, pred[ri, ctu], lc)
+        assert np.array_equal(gi, ires[ri, ctu]) and np.array_equal(gf, fres[ri, ctu]), (ri, ctu)
+        gi2, gf2 = t.me_ctu(0, -1, 1 + ri, ctu, pred[ri, ctu], lc, use_tables=False)
+        assert np.array_equal(gi2, gi) and np.array_equal(gf2, gf)
+    # a predictor 30 pels away from the table centre: mixed table / direct evaluation
+    ri, ctu = 1, 8
+    p2 = (int(pred[ri, ctu, 0]) + 120, int(pred[ri, ctu, 1]) - 96)
+    gi, gf = t.me_ctu(0, ri, 1 + ri, ctu, p2, lc)
+    x0, y0 = (ctu % t.ctus_x) * 64, (ctu // t.ctus_x) * 64
+    ref = refs[ri]
+    for k in rng.choice(593, 80, replace=False):
+        px, py, w, h, cux, cuy = (int(v) for v in census[k])
+        x, y = x0 + px, y0 + py
+        if x + w > W or y + h > H:
+            assert gi[k]["n_sads"] == 0
+            continue
+        g = oracle.CuGeom(W, H, x0 + cux, y0 + cuy, 64)
+        lx, ty, rx, by = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        orc.orc_set_search_range(C.byref(g), p2[0], p2[1], 64, C.byref(lx), C.byref(ty), C.byref(rx), C.byref(by))
+        o = optr(cur.buf_y, cur.origin(0) + y * cur.stride + x)
+        r = optr(ref.buf_y, ref.origin(0) + y * ref.stride + x)
+        e = oracle.MeResult()
+        orc.orc_tz_search(C.byref(g), o, cur.stride, r, ref.stride, w, h, lx.value, ty.value, rx.value, by.value,
+                          64, 1, 0, lc, p2[0], p2[1], p2[0], p2[1], C.byref(e))
+        assert (gi[k]["mvx"], gi[k]["mvy"], gi[k]["sad"], gi[k]["n_sads"]) == (e.mvx, e.mvy, e.sad, e.n_sads), k
+        f = oracle.FracResult()
+        orc.orc_frac_search(o, cur.stride, r, ref.stride, w, h, e.mvx, e.mvy, 1, 0, 8, lc, p2[0], p2[1], C.byref(f))
+        assert (gf[k]["halfx"], gf[k]["halfy"], gf[k]["qtrx"], gf[k]["qtry"], gf[k]["cost"]) == (f.halfx, f.halfy, f.qtrx, f.qtry, f.cost), k
+
+
 # ----------------------------------------------------------------------------------- fractional ME
 @pytest.mark.parametrize("bd", [8, 10])
 def test_me_frac(ctx8, ctx10, orc, bd):

@@ -67,7 +67,7 @@ def test_bitstream_md5_identical_to_reference(tmp_path, cfg, frames, extra):
     _yuv(yuv, w, h, frames)
     ref_bin, cuda_bin = str(tmp_path / "ref.bin"), str(tmp_path / "cuda.bin")
     _encode(ENC_REF, cfg, yuv, w, h, frames, ref_bin, extra=extra)
-    r = _encode(ENC_CUDA, cfg, yuv, w, h, frames, cuda_bin, env={"TVC_HM": "me,frac,tq,rdoq,mc,tables"}, extra=extra)
+    r = _encode(ENC_CUDA, cfg, yuv, w, h, frames, cuda_bin, env={"TVC_HM": "me,frac,tq,rdoq,mc,tables,verify"}, extra=extra)
     served = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda:")]
     assert served and "kernel launches" in served[-1], r.stderr[-500:]
     print(served[-1])
@@ -91,3 +91,23 @@ def test_bitstream_md5_identical_to_reference(tmp_path, cfg, frames, extra):
     assert dserved and " 0 xIT" not in dserved[-1], dc.stderr[-500:]
     print("decoder", dserved[-1])
     assert _md5(str(tmp_path / "dec_cuda.yuv")) == _md5(str(tmp_path / "dec.yuv"))
+
+
+def test_census_lookup_serves_the_cu_loop(tmp_path):
+    """The fast configuration: integer + fractional ME of the CU loop served by look-up from census-wide
+    (CTU, reference, predictor) batches (tvc_me_ctu), everything else on the host's own code.  Same bitstream as the
+    unmodified reference; most searches are look-ups."""
+    _need()
+    w, h, frames = 416, 240, 4
+    yuv = str(tmp_path / "in.yuv")
+    _yuv(yuv, w, h, frames)
+    ref_bin, cuda_bin = str(tmp_path / "ref.bin"), str(tmp_path / "cuda.bin")
+    _encode(ENC_REF, "encoder_lowdelay_P_main.cfg", yuv, w, h, frames, ref_bin)
+    r = _encode(ENC_CUDA, "encoder_lowdelay_P_main.cfg", yuv, w, h, frames, cuda_bin, env={"TVC_HM": "me,frac,tables"})
+    assert _md5(cuda_bin) == _md5(ref_bin)
+    line = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda look-up:")]
+    assert line, r.stderr[-600:]
+    print(line[-1])
+    f = line[-1].split()
+    served, total = int(f[2]), int(f[4])
+    assert total > 10000 and served > 0.8 * total, line[-1]

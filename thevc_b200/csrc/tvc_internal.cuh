@@ -55,6 +55,8 @@ struct tvc_ctx {
   std::vector<tvc::Pic> pics;
   tvc::PlaneTable planes;
   tvc::Scratch in, out;           // staging for host-pointer entry points
+  void* ctu_buf = nullptr;        // tvc_me_ctu: jobs / results of one (CTU, reference) group (device)
+  void* ctu_host = nullptr;       // pinned copy of its results
   void* rdoq_scratch = nullptr;   // per-coefficient RDOQ working arrays (device)
   size_t rdoq_scratch_elems = 0;
   std::string err;

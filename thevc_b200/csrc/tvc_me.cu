@@ -1107,21 +1107,18 @@ __device__ __forceinline__ void clip_mv(int pic_w, int pic_h, int cu_x, int cu_y
   y = min(vmax, max(vmin, y));
 }
 
-__global__ void k_me_frame_jobs(int pic_w, int pic_h, int num_ctus, int ctus_x, int num_refs, const int* __restrict__ ref_slots,
-                                const tvc_me_center* __restrict__ pred, tvc_me_frame_cfg cfg, tvc_me_job* __restrict__ jobs)
+// census PU k of CTU `ctu` against one reference with predictor p (quarter pels): the job xMotionEstimation would hand to
+// xTZSearch (window by xSetSearchRange, start = clipped predictor >> 2)
+__device__ __forceinline__ tvc_me_job census_job(int pic_w, int pic_h, int ctus_x, int ctu, int k, int ref_index, int ref_slot,
+                                                 tvc_me_center p, const tvc_me_frame_cfg& cfg)
 {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int total = num_refs * num_ctus * TVC_ME_CENSUS;
-  if (i >= total) return;
-  int k = i % TVC_ME_CENSUS, rc = i / TVC_ME_CENSUS, ctu = rc % num_ctus, ref = rc / num_ctus;
   const tvc_census_pu cp = c_census[k];
   int x0 = (ctu % ctus_x) * 64, y0 = (ctu / ctus_x) * 64;
   tvc_me_job j;
-  j.ref_index = ref; j.ref_slot = ref_slots[ref];
+  j.ref_index = ref_index; j.ref_slot = ref_slot;
   j.x = x0 + cp.x; j.y = y0 + cp.y; j.w = cp.w; j.h = cp.h;
   if (j.x + j.w > pic_w || j.y + j.h > pic_h) j.w = 0;
   j.mode = TVC_ME_TZ; j.fen = cfg.fen; j.search_range = cfg.search_range;
-  const tvc_me_center p = pred[rc];
   const int cu_x = x0 + cp.cu_x, cu_y = y0 + cp.cu_y;
   // xSetSearchRange (TEncSearch.cpp:4209-4225)
   int px = p.cx, py = p.cy;
@@ -1134,7 +1131,26 @@ __global__ void k_me_frame_jobs(int pic_w, int pic_h, int num_ctus, int ctus_x, 
   j.predx = p.cx; j.predy = p.cy;
   j.startx = px >> 2; j.starty = py >> 2;          // xTZSearch :4311-4312
   j.lambda_cost = cfg.lambda_cost;
-  jobs[i] = j;
+  return j;
+}
+
+__global__ void k_me_frame_jobs(int pic_w, int pic_h, int num_ctus, int ctus_x, int num_refs, const int* __restrict__ ref_slots,
+                                const tvc_me_center* __restrict__ pred, tvc_me_frame_cfg cfg, tvc_me_job* __restrict__ jobs)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int total = num_refs * num_ctus * TVC_ME_CENSUS;
+  if (i >= total) return;
+  int k = i % TVC_ME_CENSUS, rc = i / TVC_ME_CENSUS, ctu = rc % num_ctus, ref = rc / num_ctus;
+  jobs[i] = census_job(pic_w, pic_h, ctus_x, ctu, k, ref, ref_slots[ref], pred[rc], cfg);
+}
+
+// one (CTU, reference) group with an explicit predictor (tvc_me_ctu)
+__global__ void k_me_ctu_jobs(int pic_w, int pic_h, int ctus_x, int ctu, int ref_index, int ref_slot, tvc_me_center pred,
+                              tvc_me_frame_cfg cfg, tvc_me_job* __restrict__ jobs)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= TVC_ME_CENSUS) return;
+  jobs[k] = census_job(pic_w, pic_h, ctus_x, ctu, k, ref_index, ref_slot, pred, cfg);
 }
 
 __global__ void k_me_frame_frac_jobs(int n, const tvc_me_job* __restrict__ jobs, const tvc_me_result* __restrict__ res,
@@ -1459,6 +1475,18 @@ int tvc_me_census(tvc_census_pu* out)
   return TVC_OK;
 }
 
+static int ensure_census(tvc_ctx* c)
+{
+  static int census_dev = -1;
+  if (census_dev != c->cfg.device) {
+    tvc_census_pu h[TVC_ME_CENSUS];
+    build_census(h);
+    TVC_CUDA(c, cudaMemcpyToSymbol(c_census, h, sizeof(h)));
+    census_dev = c->cfg.device;
+  }
+  return TVC_OK;
+}
+
 int tvc_me_frame_dev(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slots, const tvc_me_center* pred_qpel,
                      const tvc_me_frame_cfg* cfg, tvc_me_result** int_dev, tvc_frac_result** frac_dev)
 {
@@ -1469,13 +1497,8 @@ int tvc_me_frame_dev(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slot
     if (!valid_slot(c, ref_slots[r])) return set_err(c, TVC_ERR_ARG, "tvc_me_frame: bad reference slot");
   const int nctu = c->num_ctus_x * c->num_ctus_y;
   const size_t n = (size_t)num_refs * nctu * TVC_ME_CENSUS;
-  static int census_dev = -1;
-  if (census_dev != c->cfg.device) {
-    tvc_census_pu h[TVC_ME_CENSUS];
-    build_census(h);
-    TVC_CUDA(c, cudaMemcpyToSymbol(c_census, h, sizeof(h)));
-    census_dev = c->cfg.device;
-  }
+  int r0;
+  if ((r0 = ensure_census(c))) return r0;
   if (n > c->fr_cap) {
     if (c->fr_jobs) cudaFree(c->fr_jobs);
     if (c->fr_int) cudaFree(c->fr_int);
@@ -1566,6 +1589,46 @@ int tvc_me_frame(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slots, c
   if (int_out) TVC_CUDA(c, cudaMemcpyAsync(int_out, di, n * sizeof(tvc_me_result), cudaMemcpyDeviceToHost, c->stream));
   if (frac_out && df) TVC_CUDA(c, cudaMemcpyAsync(frac_out, df, n * sizeof(tvc_frac_result), cudaMemcpyDeviceToHost, c->stream));
   TVC_CUDA(c, cudaStreamSynchronize(c->stream));
+  return TVC_OK;
+}
+
+int tvc_me_ctu(tvc_ctx* c, int cur_slot, int ref_index, int ref_slot, int ctu, tvc_me_center pred_qpel, const tvc_me_frame_cfg* cfg,
+               tvc_me_result* int_out, tvc_frac_result* frac_out)
+{
+  if (!c || !valid_slot(c, cur_slot) || !valid_slot(c, ref_slot) || !cfg || cfg->search_range < 1 || cfg->search_range > TVC_ME_RANGE ||
+      ctu < 0 || ctu >= c->num_ctus_x * c->num_ctus_y || !int_out || (cfg->do_frac && !frac_out))
+    return set_err(c, TVC_ERR_ARG, "tvc_me_ctu: bad argument");
+  if (cfg->use_tables && (!c->me_tables || c->me_cur_slot != cur_slot || ref_index < 0 || ref_index >= c->me_num_refs ||
+                          c->me_ref_slots[ref_index] != ref_slot))
+    return set_err(c, TVC_ERR_STATE, "tvc_me_ctu: tables requested but tvc_me_prepass has not run for this picture / reference");
+  int r;
+  if ((r = ensure_census(c))) return r;
+  constexpr size_t N = TVC_ME_CENSUS;
+  if (!c->ctu_buf) {
+    TVC_CUDA(c, cudaMalloc(&c->ctu_buf, N * (sizeof(tvc_me_job) + sizeof(tvc_me_result) + sizeof(tvc_frac_job) + sizeof(tvc_frac_result))));
+    TVC_CUDA(c, cudaHostAlloc(&c->ctu_host, N * (sizeof(tvc_me_result) + sizeof(tvc_frac_result)), cudaHostAllocDefault));
+  }
+  // device layout: [int results][frac results][jobs][frac jobs] -- the results are contiguous: one copy back
+  tvc_me_result* d_int = (tvc_me_result*)c->ctu_buf;
+  tvc_frac_result* d_frac = (tvc_frac_result*)(d_int + N);
+  tvc_me_job* d_jobs = (tvc_me_job*)(d_frac + N);
+  tvc_frac_job* d_fjobs = (tvc_frac_job*)(d_jobs + N);
+  k_me_ctu_jobs<<<(int)((N + 127) / 128), 128, 0, c->stream>>>(c->cfg.width, c->cfg.height, c->num_ctus_x, ctu, ref_index, ref_slot, pred_qpel,
+                                                           *cfg, d_jobs);
+  TVC_LAUNCH_CHECK(c);
+  // no shared raster stage here: one block would walk the 729 raster candidates alone; the PUs that need the
+  // raster walk it themselves, in parallel
+  if ((r = launch_search(c, cur_slot, cfg->use_tables, (int)N, d_jobs, d_int, nullptr, nullptr))) return r;
+  if (cfg->do_frac) {
+    k_me_frame_frac_jobs<<<(int)((N + 127) / 128), 128, 0, c->stream>>>((int)N, d_jobs, d_int, cfg->hadamard, d_fjobs);
+    TVC_LAUNCH_CHECK(c);
+    if ((r = launch_frac(c, cur_slot, (int)N, d_fjobs, d_frac, true))) return r;
+  }
+  const size_t back = N * sizeof(tvc_me_result) + (cfg->do_frac ? N * sizeof(tvc_frac_result) : 0);
+  TVC_CUDA(c, cudaMemcpyAsync(c->ctu_host, c->ctu_buf, back, cudaMemcpyDeviceToHost, c->stream));
+  TVC_CUDA(c, cudaStreamSynchronize(c->stream));
+  memcpy(int_out, c->ctu_host, N * sizeof(tvc_me_result));
+  if (cfg->do_frac) memcpy(frac_out, (char*)c->ctu_host + N * sizeof(tvc_me_result), N * sizeof(tvc_frac_result));
   return TVC_OK;
 }
 

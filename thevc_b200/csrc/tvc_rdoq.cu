@@ -150,8 +150,10 @@ k_rdoq(int n, const tvc_rdoq_tu* __restrict__ tus, const tvc_est_bits* __restric
 {
   __shared__ RdoqWarp smem[kRdoqWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = blockIdx.x * kRdoqWarps + warp;
-  if (t >= n) return;
+  // TU lists are grouped by ascending size: walk them from the back so that the long 32x32 chains (1024 dependent
+  // steps) start first and the short 4x4 ones fill the machine behind them instead of leaving a tail
+  const int t = n - 1 - (blockIdx.x * kRdoqWarps + warp);
+  if (t < 0) return;
   RdoqWarp& S = smem[warp];
   const tvc_rdoq_tu tu = tus[t];
   const int log2 = tu.log2_size, w = 1 << log2, ncoef = w * w, ncg = ncoef >> 4, cgw = w >> 2;

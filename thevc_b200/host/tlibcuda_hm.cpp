@@ -7,6 +7,10 @@
 #include <cstring>
 #include <cmath>
 #include <vector>
+#include <map>
+#include <chrono>
+#include <algorithm>
+#include <utility>
 
 #define private public
 #define protected public
@@ -36,8 +40,33 @@ struct DevPic {                 // one registered TComPicYuv: host buffer range 
   unsigned long long stamp = 0;
 };
 
+// results of one tvc_me_ctu call: the census-wide searches of a (CTU, reference) group for one predictor
+struct GroupEntry {
+  int predx, predy, sr, fen, had;
+  unsigned lambda;
+  std::vector<tvc_me_result> ires;
+  std::vector<tvc_frac_result> fres;
+};
+struct Group {
+  std::vector<GroupEntry> e;
+  std::map<long long, int> seen;           // predictors that missed: a second miss of the same one builds an entry
+};
+struct LastHit {                           // the integer search just served by look-up: its fractional stage follows
+  bool valid = false;
+  int slot, x, y, w, h, mvx, mvy, predx, predy, had;
+  unsigned lambda;
+  tvc_frac_result fr;
+};
+
 struct State {
   tvc_ctx* h = nullptr;
+  bool on_lookup = true, verify = false;
+  std::map<long long, Group> groups;       // key = ctu * 64 + device slot of the reference; cleared per picture
+  std::map<unsigned, int> census_index;    // (x, y, w, h) inside the CTU -> census index
+  std::vector<tvc_me_center> center_guess; // [table ref][ctu]: first predictor of the previous picture's group (quarter pels)
+  LastHit last;
+  unsigned long long n_tz_lookup = 0, n_frac_lookup = 0, n_groups = 0;
+  double batch_seconds = 0.0, prepass_seconds = 0.0;      // host wall time spent inside tvc_me_ctu / picture_start
   bool on_me = true, on_frac = true, on_tq = true, on_rdoq = true, on_mc = true, on_tables = true, verbose = false, disabled = false;
   int w = 0, ht = 0;
   std::vector<DevPic> slots;
@@ -68,9 +97,49 @@ void die(const char* what, int rc)
 void report()
 {
   State& s = S();
+  if (s.h && s.on_lookup)
+    fprintf(stderr, "TLibCuda look-up: %llu of %llu xTZSearch and %llu of %llu xPatternSearchFracDIF calls served from %llu census-wide (CTU, reference) batches (%.3f s in tvc_me_ctu, %.3f s in picture uploads + SAD-table pre-passes)\n",
+            s.n_tz_lookup, s.n_tz, s.n_frac_lookup, s.n_frac, s.n_groups, s.batch_seconds, s.prepass_seconds);
   if (s.h)
     fprintf(stderr, "TLibCuda: %llu xTZSearch, %llu xPatternSearchFracDIF, %llu xT, %llu xIT, %llu xDeQuant, %llu xRateDistOptQuant, %llu xPredInterUni calls served; %llu kernel launches\n",
             s.n_tz, s.n_frac, s.n_xt, s.n_xit, s.n_dq, s.n_rdoq, s.n_mc, (unsigned long long)tvc_launch_count(s.h));
+}
+
+// TVC_HM=stats: no CUDA at all -- only count, per (picture, CTU, reference), how many integer searches the
+// reference runs and with how many distinct AMVP predictors (sizing data for the frame pre-pass look-up)
+struct PredStats {
+  bool on = false;
+  std::map<std::pair<long long, long long>, std::map<long long, unsigned> > m;    // (poc, ctu*64+ref) -> pred -> calls
+  std::map<std::pair<long long, long long>, long long> first;
+};
+PredStats& PS() { static PredStats p; return p; }
+
+void stats_report()
+{
+  PredStats& p = PS();
+  if (!p.on) return;
+  unsigned long long calls = 0, groups = 0, hit_first = 0, hit_mode = 0, distinct = 0, hit_top2 = 0, hit_top4 = 0;
+  unsigned long long hist[9] = {0};
+  for (auto& g : p.m) {
+    groups++;
+    unsigned best = 0, tot = 0;
+    std::vector<unsigned> cs;
+    for (auto& e : g.second) { tot += e.second; if (e.second > best) best = e.second; cs.push_back(e.second); }
+    std::sort(cs.begin(), cs.end());
+    calls += tot; hit_mode += best; distinct += g.second.size();
+    hit_first += g.second[p.first[g.first]];
+    unsigned t2 = 0, t4 = 0;
+    for (size_t i = 0; i < cs.size() && i < 4; i++) { if (i < 2) t2 += cs[cs.size() - 1 - i]; t4 += cs[cs.size() - 1 - i]; }
+    hit_top2 += t2; hit_top4 += t4;
+    hist[g.second.size() > 8 ? 8 : g.second.size()]++;
+  }
+  fprintf(stderr, "TLibCuda stats: %llu integer searches in %llu (picture, CTU, reference) groups; distinct predictors per group: mean %.2f; "
+                  "served by the group's FIRST predictor %.1f%%, by its most frequent %.1f%%, by the top 2 %.1f%%, top 4 %.1f%%\n",
+          calls, groups, groups ? (double)distinct / groups : 0.0, calls ? 100.0 * hit_first / calls : 0.0,
+          calls ? 100.0 * hit_mode / calls : 0.0, calls ? 100.0 * hit_top2 / calls : 0.0, calls ? 100.0 * hit_top4 / calls : 0.0);
+  fprintf(stderr, "TLibCuda stats: groups by number of distinct predictors 1..8+:");
+  for (int i = 1; i <= 8; i++) fprintf(stderr, " %llu", hist[i]);
+  fprintf(stderr, "\n");
 }
 
 void parse_env()
@@ -85,6 +154,9 @@ void parse_env()
   s.on_mc = strstr(e, "mc") != nullptr;
   s.on_tables = strstr(e, "tables") != nullptr;
   s.verbose = strstr(e, "verbose") != nullptr;
+  s.on_lookup = strstr(e, "nolookup") == nullptr;
+  s.verify = strstr(e, "verify") != nullptr;
+  if (strstr(e, "stats")) { PS().on = true; s.on_me = s.on_frac = s.on_tq = s.on_rdoq = s.on_mc = s.on_tables = false; atexit(stats_report); }
 }
 
 void ensure_ctx(int w, int ht)
@@ -157,6 +229,7 @@ bool locate(const short* p, int& slot, int& x, int& y)
 void tlibcuda_picture_start(TComPic* pic, TComSlice* slice)
 {
   TComPicYuv* org = pic->getPicYuvOrg();
+  const auto t_start = std::chrono::steady_clock::now();
   ensure_ctx(org->getWidth(), org->getHeight());
   State& s = S();
   if (!s.h || (!s.on_me && !s.on_frac)) return;
@@ -172,10 +245,36 @@ void tlibcuda_picture_start(TComPic* pic, TComSlice* slice)
       if (!seen && s.num_table_refs < 8) s.table_refs[s.num_table_refs++] = slot;
     }
   }
-  if (s.on_tables && s.num_table_refs > 0 && g_uiBitIncrement == 0)
-    CK(tvc_me_prepass(s.h, s.cur_slot, s.num_table_refs, s.table_refs, nullptr));
-  else
+  s.groups.clear();
+  s.last.valid = false;
+  if (s.census_index.empty()) {
+    tvc_census_pu cen[TVC_ME_CENSUS];
+    CK(tvc_me_census(cen));
+    for (int k = TVC_ME_CENSUS - 1; k >= 0; k--)
+      s.census_index[(unsigned)cen[k].x | ((unsigned)cen[k].y << 6) | ((unsigned)cen[k].w << 12) | ((unsigned)cen[k].h << 19)] = k;
+  }
+  const int nctu = ((org->getWidth() + 63) / 64) * ((org->getHeight() + 63) / 64);
+  if (s.on_tables && s.num_table_refs > 0 && g_uiBitIncrement == 0) {
+    // table centres: the predictor each (reference index, CTU) group started with in the previous picture (steady
+    // motion keeps it), clipped like a CTU-level clipMv; zero for the first inter picture
+    if ((int)s.center_guess.size() != 8 * nctu) s.center_guess.assign((size_t)8 * nctu, tvc_me_center{0, 0});
+    std::vector<tvc_me_center> cen((size_t)s.num_table_refs * nctu);
+    const int ctus_x = (org->getWidth() + 63) / 64;
+    for (int r = 0; r < s.num_table_refs; r++)
+      for (int k = 0; k < nctu; k++) {
+        tvc_me_center p = s.center_guess[(size_t)r * nctu + k];
+        const int x0 = (k % ctus_x) * 64, y0 = (k / ctus_x) * 64;
+        const int hmax = (org->getWidth() + 8 - x0 - 1) * 4, hmin = (-64 - 8 - x0 + 1) * 4;
+        const int vmax = (org->getHeight() + 8 - y0 - 1) * 4, vmin = (-64 - 8 - y0 + 1) * 4;
+        p.cx = (p.cx < hmin ? hmin : (p.cx > hmax ? hmax : p.cx)) >> 2;
+        p.cy = (p.cy < vmin ? vmin : (p.cy > vmax ? vmax : p.cy)) >> 2;
+        cen[(size_t)r * nctu + k] = p;
+      }
+    CK(tvc_me_prepass(s.h, s.cur_slot, s.num_table_refs, s.table_refs, cen.data()));
+  } else
     s.num_table_refs = 0;
+  CK(tvc_sync(s.h));
+  s.prepass_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
   if (s.verbose) fprintf(stderr, "TLibCuda: POC %d cur slot %d, %d reference(s) with SAD tables\n", slice->getPOC(), s.cur_slot, s.num_table_refs);
 }
 
@@ -183,6 +282,20 @@ bool tlibcuda_tz_search(TComDataCU* cu, TComPattern* key, short* refY, int refSt
                         unsigned& ruiSAD, TComRdCost* rd, TEncCfg* cfg, int searchRange)
 {
   State& s = S();
+  if (PS().on) {
+    const long long ctu = cu->getAddr();
+    long long ref = 0;
+    for (int i = 0; i < cu->getSlice()->getNumRefIdx(REF_PIC_LIST_0); i++) {     // which reference: by buffer range
+      TComPicYuv* r = cu->getSlice()->getRefPic(REF_PIC_LIST_0, i)->getPicYuvRec();
+      const ptrdiff_t off = refY - r->getLumaAddr();
+      if (off >= 0 && off < (ptrdiff_t)r->getStride() * r->getHeight()) { ref = i; break; }
+    }
+    const std::pair<long long, long long> key(cu->getSlice()->getPOC(), ctu * 64 + ref);
+    const long long pv = ((long long)rd->m_mvPredictor.getHor() << 20) ^ (rd->m_mvPredictor.getVer() & 0xfffff);
+    if (!PS().m.count(key)) PS().first[key] = pv;
+    PS().m[key][pv]++;
+    return false;
+  }
   if (!s.h || !s.on_me || s.cur_slot < 0) return false;
   int slot, x, y;
   if (!locate(refY, slot, x, y)) return false;
@@ -204,11 +317,60 @@ bool tlibcuda_tz_search(TComDataCU* cu, TComPattern* key, short* refY, int refSt
   start >>= 2;
   j.startx = start.getHor(); j.starty = start.getVer();
   j.lambda_cost = rd->m_uiCost;
+  s.n_tz++;
+  s.last.valid = false;
+  if (s.on_lookup && s.on_frac) {
+    // census-wide batch per (CTU, reference, predictor): the first search of a group pays for all of them
+    const int ctus_x = (s.w + 63) / 64, ctu = (y >> 6) * ctus_x + (x >> 6);
+    Group& g = s.groups[(long long)ctu * 64 + slot];
+    const int had = cfg->getUseHADME() ? 1 : 0;
+    GroupEntry* hit = nullptr;
+    for (auto& e : g.e)
+      if (e.predx == j.predx && e.predy == j.predy && e.lambda == j.lambda_cost && e.sr == searchRange && e.fen == j.fen && e.had == had) { hit = &e; break; }
+    if (!hit) {
+      const long long pv = ((long long)j.predx << 32) ^ (unsigned)j.predy;
+      if (g.e.empty() || (g.e.size() < 4 && g.seen[pv]++ >= 1)) {
+        g.e.emplace_back();
+        GroupEntry& e = g.e.back();
+        e.predx = j.predx; e.predy = j.predy; e.lambda = j.lambda_cost; e.sr = searchRange; e.fen = j.fen; e.had = had;
+        e.ires.resize(TVC_ME_CENSUS); e.fres.resize(TVC_ME_CENSUS);
+        tvc_me_frame_cfg fc = {searchRange, j.fen, had, j.ref_index >= 0 ? 1 : 0, 1, j.lambda_cost};
+        const auto t0 = std::chrono::steady_clock::now();
+        CK(tvc_me_ctu(s.h, s.cur_slot, j.ref_index, slot, ctu, tvc_me_center{j.predx, j.predy}, &fc, e.ires.data(), e.fres.data()));
+        s.batch_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        s.n_groups++;
+        if (g.e.size() == 1 && j.ref_index >= 0 && (size_t)(j.ref_index + 1) * (s.center_guess.size() / 8) <= s.center_guess.size())
+          s.center_guess[(size_t)j.ref_index * (s.center_guess.size() / 8) + ctu] = tvc_me_center{j.predx, j.predy};
+        hit = &e;
+      }
+    }
+    if (hit) {
+      auto it = s.census_index.find((unsigned)(x & 63) | ((unsigned)(y & 63) << 6) | ((unsigned)j.w << 12) | ((unsigned)j.h << 19));
+      if (it != s.census_index.end() && hit->ires[it->second].n_sads > 0) {
+        const tvc_me_result& r = hit->ires[it->second];
+        if (s.verify) {
+          tvc_me_result r2;
+          CK(tvc_me_search_batch(s.h, s.cur_slot, j.ref_index >= 0 ? 1 : 0, 1, &j, &r2));
+          if (r2.mvx != r.mvx || r2.mvy != r.mvy || r2.sad != r.sad) {
+            fprintf(stderr, "TLibCuda verify: look-up (%d,%d,%u) != single search (%d,%d,%u) for PU %dx%d at (%d,%d)\n", r.mvx, r.mvy, r.sad,
+                    r2.mvx, r2.mvy, r2.sad, j.w, j.h, x, y);
+            exit(EXIT_FAILURE);
+          }
+        }
+        rcMv.set(r.mvx, r.mvy);
+        ruiSAD = r.sad;
+        LastHit& l = s.last;
+        l.valid = true; l.slot = slot; l.x = x; l.y = y; l.w = j.w; l.h = j.h; l.mvx = r.mvx; l.mvy = r.mvy;
+        l.predx = j.predx; l.predy = j.predy; l.lambda = j.lambda_cost; l.had = had; l.fr = hit->fres[it->second];
+        s.n_tz_lookup++;
+        return true;
+      }
+    }
+  }
   tvc_me_result r;
   CK(tvc_me_search_batch(s.h, s.cur_slot, j.ref_index >= 0 ? 1 : 0, 1, &j, &r));
   rcMv.set(r.mvx, r.mvy);
   ruiSAD = r.sad;
-  s.n_tz++;
   return true;
 }
 
@@ -228,13 +390,25 @@ bool tlibcuda_frac_search(TComPattern* key, short* refY, int refStride, TComMv* 
   j.predx = rd->m_mvPredictor.getHor(); j.predy = rd->m_mvPredictor.getVer();
   j.lambda_cost = rd->m_uiCost;
   j.hadamard = cfg->getUseHADME() ? 1 : 0;
+  s.n_frac++;
   tvc_frac_result r;
-  CK(tvc_me_frac_batch(s.h, s.cur_slot, 1, &j, &r));
+  const LastHit& l = s.last;
+  if (l.valid && l.slot == slot && l.x == x && l.y == y && l.w == j.w && l.h == j.h && l.mvx == j.imvx && l.mvy == j.imvy &&
+      l.predx == j.predx && l.predy == j.predy && l.lambda == j.lambda_cost && l.had == j.hadamard) {
+    r = l.fr;
+    if (s.verify) {
+      tvc_frac_result r2;
+      CK(tvc_me_frac_batch(s.h, s.cur_slot, 1, &j, &r2));
+      if (memcmp(&r, &r2, sizeof(r)) != 0) { fprintf(stderr, "TLibCuda verify: fractional look-up differs for PU %dx%d at (%d,%d)\n", j.w, j.h, x, y); exit(EXIT_FAILURE); }
+    }
+    s.n_frac_lookup++;
+  } else
+    CK(tvc_me_frac_batch(s.h, s.cur_slot, 1, &j, &r));
+  s.last.valid = false;
   half.set(r.halfx, r.halfy);
   qter.set(r.qtrx, r.qtry);
   ruiCost = r.cost;
   rd->setCostScale(0);                      // side effect of the reference body (:4505)
-  s.n_frac++;
   return true;
 }
 

@@ -239,6 +239,16 @@ class TLibCuda:
                                      ptr(fres) if do_frac else None))
         return ires, fres
 
+    def me_ctu(self, cur_slot: int, ref_index: int, ref_slot: int, ctu: int, pred_qpel, lambda_cost: int, search_range: int = 64,
+               fen: bool = True, hadamard: bool = True, use_tables: bool = True):
+        """census-wide integer + fractional search of one (CTU, reference) group with an explicit predictor"""
+        ires = np.zeros(capi.ME_CENSUS, capi.ME_RESULT_DTYPE)
+        fres = np.zeros(capi.ME_CENSUS, capi.FRAC_RESULT_DTYPE)
+        cfg = MeFrameCfg(search_range, int(fen), int(hadamard), int(use_tables), 1, lambda_cost)
+        self._ck(self.L.tvc_me_ctu(self.h, cur_slot, ref_index, ref_slot, ctu, MeCenter(int(pred_qpel[0]), int(pred_qpel[1])),
+                                   C.byref(cfg), ptr(ires), ptr(fres)))
+        return ires, fres
+
     def me_frame_stats(self):
         st = np.zeros(3, np.uint64)
         self._ck(self.L.tvc_me_frame_stats(self.h, ptr(st)))
