@@ -116,3 +116,77 @@ def test_transform_round_trip_closes_at_1080p(ctx):
     qc = QuantCfg(0, 0, 0)
     assert t.L.tvc_fwd_tq_batch(t.h, 3, 1, capi.ptr(tu), C.byref(qc), capi.ptr(lev), None, 64, capi.ptr(abs_sum)) == 0
     assert abs_sum[0] == np.abs(lev).sum()
+
+
+def test_tq_rdoq_at_4k_10bit():
+    """BASELINE.json configs[3] size (3840x2160, internal 10-bit: the TQ-dominated all-intra case): every 32x32 luma TU
+    and 16x16 chroma TU of one picture through transform -> RDOQ -> dequant -> inverse transform -> reconstruction.
+    Properties: RDOQ never exceeds the plain-rounding level, uiAbsSum is the level sum, the reconstruction stays within
+    the quantiser's error bound of the source; 60 TUs are replayed by the oracle bit for bit."""
+    import oracle
+    import rdoq_cases as rc
+    from thevc_b200.capi import EstBits, RdoqTU
+    from thevc_b200.tlibcuda import HostPic
+    W4, H4, bd = 3840, 2160, 10
+    rng = np.random.default_rng(404)
+    t = TLibCuda(W4, H4, bd, num_slots=4)
+    try:
+        # slot 0: residual (smooth + noise, 10-bit range); slot 1: prediction (mid grey) -> slot 3: reconstruction
+        resi, pred = HostPic(W4, H4), HostPic(W4, H4)
+        for pl in range(3):
+            p = resi.plane(pl)
+            yy, xx = np.mgrid[0:p.shape[0], 0:p.shape[1]]
+            p[:] = (60 * np.sin(xx / 37.0) * np.cos(yy / 23.0) + rng.normal(0, 12, p.shape)).astype(np.int16)
+            pred.plane(pl)[:] = 512
+        t.upload(0, resi); t.upload(1, pred)
+        qp = 27
+        rows, rrows = [], []
+        off = 0
+        for pl, log2 in ((0, 5), (1, 4), (2, 4)):
+            n = 1 << log2
+            pw, ph = (W4, H4) if pl == 0 else (W4 // 2, H4 // 2)
+            q = qp + 12 if pl == 0 else 27 + 12      # chroma QP table is the identity below 30
+            for y in range(0, ph - n + 1, n):
+                for x in range(0, pw - n + 1, n):
+                    rows.append((pl, x, y, log2, 0, 0, q // 6, q % 6, q // 6, off))
+                    rrows.append((log2, int(pl == 0), 0, q // 6, q % 6, 0 if pl == 0 else 5, 0, off, rc.lambda_for(qp)))
+                    off += n * n
+        # the ABI wants ascending sizes: chroma 16x16 first
+        order = sorted(range(len(rows)), key=lambda i: rows[i][3])
+        tus = np.array([rows[i] for i in order], np.int32).view(capi.TU_DTYPE).reshape(-1)
+        rtus = np.zeros(len(order), capi.RDOQ_TU_DTYPE)
+        for j, i in enumerate(order):
+            rtus[j] = rrows[i]
+        est = rc.make_est(rng)
+        e = EstBits(); C.memmove(C.byref(e), C.byref(est), C.sizeof(e))
+        lev = np.zeros(off, np.int32); sums = np.zeros(len(tus), np.uint32)
+        qc = QuantCfg(1, 1, 0)
+        assert t.L.tvc_fwd_rdoq_batch(t.h, 0, len(tus), capi.ptr(tus), capi.ptr(rtus), 1, C.byref(e), C.byref(qc), capi.ptr(lev), None,
+                                      off, capi.ptr(sums)) == 0, t.L.tvc_last_error(t.h)
+        coef = np.zeros(off, np.int32)
+        assert t.L.tvc_fwd_transform_batch(t.h, 0, len(tus), capi.ptr(tus), capi.ptr(coef), off) == 0
+        qs = np.array([26214, 23302, 20560, 18396, 16384, 14564], np.int64)
+        for j in rng.choice(len(tus), 400, replace=False):
+            o, nn = int(tus["coef_offset"][j]), 1 << (2 * int(tus["log2_size"][j]))
+            qbits = 14 + int(tus["qp_per"][j]) + 15 - bd - int(tus["log2_size"][j])
+            plain = (np.abs(coef[o:o + nn].astype(np.int64)) * qs[int(tus["qp_rem"][j])] + (1 << (qbits - 1))) >> qbits
+            # sign-data hiding may move one level per 16-coefficient subset by one
+            assert np.all(np.abs(lev[o:o + nn]) <= plain + 1)
+        scan = {}
+        for j in rng.choice(len(tus), 60, replace=False):
+            log2 = int(tus["log2_size"][j]); nn = 1 << (2 * log2); o = int(tus["coef_offset"][j])
+            if log2 not in scan:
+                scan[log2] = np.zeros(nn, np.uint32); oracle.lib().orc_scan(0, log2, scan[log2])
+            par = oracle.RdoqParam(log2, int(rtus["is_luma"][j]), 0, int(rtus["qp_per"][j]), int(rtus["qp_rem"][j]), bd, int(rtus["cbf_ctx"][j]),
+                                   1, 0, float(rtus["lambda_"][j]))
+            q = np.zeros(nn, np.int32); s = C.c_uint32(0)
+            oracle.lib().orc_rdoq(np.ascontiguousarray(coef[o:o + nn]), q, None, C.byref(par), C.byref(est), scan[log2], C.byref(s))
+            assert np.array_equal(q, lev[o:o + nn]) and s.value == sums[j], j
+        assert t.L.tvc_inv_tq_batch(t.h, 2, 1, 3, len(tus), capi.ptr(tus), capi.ptr(lev), off) == 0
+        rec = t.download(3, with_margin=False)
+        # reconstruction error bound: |recon - (pred + resi)| is limited by the quantiser step (QP 27+12 -> step ~ 2^((39-4)/6) ~ 57
+        # in the 10-bit domain before the transform gain; per-sample errors stay well inside +-step)
+        err = np.abs(rec.y[:2144, :3840].astype(np.int32) - (512 + resi.y[:2144, :3840].astype(np.int32)))
+        assert err.max() < 160 and err.mean() < 20, (err.max(), err.mean())
+    finally:
+        t.close()

@@ -228,6 +228,7 @@ void tvc_ctx_destroy(tvc_ctx* c)
   if (c->fr_fjobs) cudaFree(c->fr_fjobs);
   if (c->fr_frac) cudaFree(c->fr_frac);
   if (c->fr_rast) cudaFree(c->fr_rast);
+  if (c->fr_sweep) cudaFree(c->fr_sweep);
   if (c->fr_stats) cudaFree(c->fr_stats);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;

@@ -75,6 +75,7 @@ struct tvc_ctx {
   tvc_frac_job* fr_fjobs = nullptr;
   tvc_frac_result* fr_frac = nullptr;
   void* fr_rast = nullptr;        // shared raster-stage results (RasterBest per job)
+  void* fr_sweep = nullptr;       // shared first-sweep results (SweepState per job)
   unsigned long long* fr_stats = nullptr;   // device: 3 work counters (tvc_me_frame_stats)
   size_t fr_cap = 0;              // entries
   // dedicated pinned staging of the asynchronous ME entry points (an event guards host reuse)

@@ -556,53 +556,28 @@ __device__ __forceinline__ void raster_scan(SearchCtx& s, int step, uint32_t dis
 // running (cost, first index) minimum in visiting order with strict '<' -- the state xTZSearchHelp
 // would reach.  k_me_search consumes the result when its own window equals the CTU's.
 struct RasterBest { uint32_t cost; int32_t idx; };
+// state of a PU's search after the start / zero tests and the first diamond sweep (IntTZSearchStruct fields);
+// n_sads == 0: not served by the shared stage
+struct SweepState { uint32_t best_sad; int32_t best_x, best_y; uint32_t best_dist; int32_t point_nr; uint32_t n_sads; };
 constexpr int kRastChunk = 4;                   // candidates per iteration
 constexpr int kRastThreads = 640;               // >= TVC_ME_CENSUS PU threads
+constexpr int kSweepMax = 2 + 4 + 3 * 8 + 3 * 16;   // start, zero, rounds d = 1 .. 64
 
-__global__ void __launch_bounds__(kRastThreads)
-k_me_raster(const tvc_me_job* __restrict__ jobs, const uint16_t* __restrict__ tables, const tvc_me_center* __restrict__ centers,
-            int num_ctus, int raster, int bi, RasterBest* __restrict__ out, unsigned long long* __restrict__ stats)
+// Walks N candidates in visiting order, kRastChunk at a time: threads 0..255 fetch the chunk's 1 KB candidate blocks
+// (pos(i, dx, dy) gives the table coordinates, false = skip), the block SADs become two 17x17 integral images per
+// candidate, then every thread runs consume(base) (PU threads read four corners per candidate).  The next chunk's
+// loads fly during the scans.
+template <class PosF, class MvcF, class ConsumeF>
+__device__ __forceinline__ void walk_candidates(int N, const uint4* __restrict__ tg, uint32_t (*IE)[17 * 17], uint32_t (*IA)[17 * 17],
+                                                uint32_t* s_mvc, int tid, PosF pos, MvcF mvc, ConsumeF consume)
 {
-  __shared__ uint32_t IE[kRastChunk][17 * 17];  // integral of even-row block SADs
-  __shared__ uint32_t IA[kRastChunk][17 * 17];  // integral of even+odd
-  __shared__ uint32_t s_mvc[kRastChunk];
-  const int ctu = blockIdx.x, ref = blockIdx.y, tid = threadIdx.x;
-  const size_t rc = (size_t)ref * num_ctus + ctu;
-  const tvc_me_job* jb0 = jobs + rc * TVC_ME_CENSUS;
-  const tvc_me_job j0 = jb0[0];                  // the 64x64 PU: its window is the CTU's
-  RasterBest* o = out + rc * TVC_ME_CENSUS;
-  const tvc_me_center cen = centers[rc];
-  const int nx = (j0.rx - j0.lx) / raster + 1, ny = (j0.by - j0.ty) / raster + 1, N = nx * ny;
-  const int x_last = j0.lx + (nx - 1) * raster, y_last = j0.ty + (ny - 1) * raster;
-  const bool covered = j0.w > 0 && j0.mode == TVC_ME_TZ && j0.lx - cen.cx >= -kMeR && x_last - cen.cx <= kMeR &&
-                       j0.ty - cen.cy >= -kMeR && y_last - cen.cy <= kMeR;
-  if (!covered) {                                // partial CTU / window leaves the table: every PU rasters on its own
-    for (int k = tid; k < TVC_ME_CENSUS; k += kRastThreads) o[k] = RasterBest{kNoCost, -1};
-    return;
-  }
-  const uint4* __restrict__ tg = reinterpret_cast<const uint4*>(tables + rc * kMeCtuElems);
-  // this thread's PU
-  const bool is_pu = tid < TVC_ME_CENSUS;
-  const tvc_census_pu cp = c_census[is_pu ? tid : 0];
-  const bool pu_ok = is_pu && jb0[is_pu ? tid : 0].w > 0;
-  const int bx0 = cp.x >> 2, by0 = cp.y >> 2, bx1 = (cp.x + cp.w) >> 2, by1 = (cp.y + cp.h) >> 2;
-  const int sub = (j0.fen && cp.h > 8) ? 1 : 0;
-  const int c00 = by0 * 17 + bx0, c01 = by0 * 17 + bx1, c10 = by1 * 17 + bx0, c11 = by1 * 17 + bx1;
-  uint32_t best = kNoCost;
-  int best_i = -1;
-  // loader role: thread t < 256 fetches granule (t & 63) of candidate (t >> 6) of the chunk
   const int lc = tid >> 6, lg = tid & 63;
   auto fetch = [&](int base) -> uint4 {
     const int i = base + lc;
-    if (tid >= 64 * kRastChunk || i >= N) return make_uint4(0, 0, 0, 0);
-    const int iy = i / nx, ix = i - iy * nx;
-    const int dx = j0.lx + ix * raster - cen.cx, dy = j0.ty + iy * raster - cen.cy;
+    int dx, dy;
+    if (tid >= 64 * kRastChunk || i >= N || !pos(i, dx, dy)) return make_uint4(0, 0, 0, 0);
     return __ldg(tg + me_granule(dy, dx, 0, 0) + lg);
   };
-  if (tid < 17 * kRastChunk) {                   // zero row / column of the integrals
-    const int c = tid / 17, k = tid % 17;
-    IE[c][k] = 0; IA[c][k] = 0; IE[c][k * 17] = 0; IA[c][k * 17] = 0;
-  }
   uint4 g = fetch(0);
   for (int base = 0; base < N; base += kRastChunk) {
     // (1) scatter the granule: block row lg >> 2, blocks 4*(lg & 3) .. +3
@@ -615,12 +590,9 @@ k_me_raster(const tvc_me_job* __restrict__ jobs, const uint16_t* __restrict__ ta
       a[0] = e0 + (g.z & 0xffffu); a[1] = e1 + (g.z >> 16); a[2] = e2 + (g.w & 0xffffu); a[3] = e3 + (g.w >> 16);
     } else if (tid < 64 * kRastChunk + kRastChunk) {
       const int c = tid - 64 * kRastChunk, i = base + c;
-      if (i < N) {
-        const int iy = i / nx, ix = i - iy * nx;
-        s_mvc[c] = mv_cost(j0.lambda_cost, j0.lx + ix * raster, j0.ty + iy * raster, 2, j0.predx, j0.predy);
-      }
+      if (i < N) s_mvc[c] = mvc(i);
     }
-    g = fetch(base + kRastChunk);                // next chunk's loads fly during the scans below
+    g = fetch(base + kRastChunk);
     __syncthreads();
     // (2) row prefix sums: 2 images x chunk x 16 rows
     if (tid < 2 * kRastChunk * 16) {
@@ -641,7 +613,134 @@ k_me_raster(const tvc_me_job* __restrict__ jobs, const uint16_t* __restrict__ ta
     }
     __syncthreads();
     // (4) every PU: cost of the chunk's candidates in visiting order
-    if (pu_ok) {
+    consume(base);
+    __syncthreads();
+  }
+}
+
+// Shared stages of the frame pre-pass, one CTA per (CTU, reference).  All 593 PUs of the CTU search around the same
+// predictor, so (a) the start / zero tests and the FIRST diamond sweep (xTZSearch :4320-4361: <= 78 candidates around
+// the clipped predictor) and (b) the raster stage (every 5th candidate of the window) visit the same candidates for
+// every PU: each candidate is read once (1 KB, coalesced) and every PU thread replays the reference's sequential
+// strict-'<' update on its own SAD.  PUs whose window / start differ from the CTU's (picture border: clipMv depends on
+// the CU origin), whose zero vector beats the predictor (the sweep then centres elsewhere) or whose candidates leave
+// the table window fall back to k_me_search's own evaluation.
+template <bool SWEEP>            // true: stage (a) only, false: stage (b) only -- two launches keep the raster at 2 CTAs per SM
+__global__ void __launch_bounds__(kRastThreads)
+k_me_raster(const tvc_me_job* __restrict__ jobs, const uint16_t* __restrict__ tables, const tvc_me_center* __restrict__ centers,
+            int num_ctus, int raster, int bi, RasterBest* __restrict__ out, SweepState* __restrict__ sweep_out,
+            unsigned long long* __restrict__ stats)
+{
+  __shared__ uint32_t IE[kRastChunk][17 * 17];  // integral of even-row block SADs
+  __shared__ uint32_t IA[kRastChunk][17 * 17];  // integral of even+odd
+  __shared__ uint32_t s_mvc[kRastChunk];
+  __shared__ int16_t s_cx[kSweepMax], s_cy[kSweepMax];
+  __shared__ uint8_t s_cvalid[kSweepMax], s_cpt[kSweepMax], s_cfirst[kSweepMax], s_clast[kSweepMax];
+  __shared__ uint32_t s_cdist[kSweepMax], s_cmv[kSweepMax];
+  __shared__ int s_sweep_ok;
+  const int ctu = blockIdx.x, ref = blockIdx.y, tid = threadIdx.x;
+  const size_t rc = (size_t)ref * num_ctus + ctu;
+  const tvc_me_job* jb0 = jobs + rc * TVC_ME_CENSUS;
+  const tvc_me_job j0 = jb0[0];                  // the 64x64 PU: its window is the CTU's
+  RasterBest* o = out + rc * TVC_ME_CENSUS;
+  SweepState* so = sweep_out ? sweep_out + rc * TVC_ME_CENSUS : nullptr;
+  const tvc_me_center cen = centers[rc];
+  const int nx = (j0.rx - j0.lx) / raster + 1, ny = (j0.by - j0.ty) / raster + 1, N = nx * ny;
+  const int x_last = j0.lx + (nx - 1) * raster, y_last = j0.ty + (ny - 1) * raster;
+  const bool usable = j0.w > 0 && j0.mode == TVC_ME_TZ;
+  const bool covered = usable && j0.lx - cen.cx >= -kMeR && x_last - cen.cx <= kMeR &&
+                       j0.ty - cen.cy >= -kMeR && y_last - cen.cy <= kMeR;
+  const uint4* __restrict__ tg = reinterpret_cast<const uint4*>(tables + rc * kMeCtuElems);
+  // this thread's PU
+  const bool is_pu = tid < TVC_ME_CENSUS;
+  const tvc_census_pu cp = c_census[is_pu ? tid : 0];
+  const tvc_me_job jb = jb0[is_pu ? tid : 0];
+  const bool pu_ok = is_pu && jb.w > 0;
+  const bool same = pu_ok && jb.lx == j0.lx && jb.ty == j0.ty && jb.rx == j0.rx && jb.by == j0.by && jb.startx == j0.startx &&
+                    jb.starty == j0.starty && jb.lambda_cost == j0.lambda_cost && jb.search_range == j0.search_range;
+  const int bx0 = cp.x >> 2, by0 = cp.y >> 2, bx1 = (cp.x + cp.w) >> 2, by1 = (cp.y + cp.h) >> 2;
+  const int sub = (j0.fen && cp.h > 8) ? 1 : 0;
+  const int c00 = by0 * 17 + bx0, c01 = by0 * 17 + bx1, c10 = by1 * 17 + bx0, c11 = by1 * 17 + bx1;
+  if (tid < 17 * kRastChunk) {                   // zero row / column of the integrals
+    const int c = tid / 17, k = tid % 17;
+    IE[c][k] = 0; IA[c][k] = 0; IE[c][k * 17] = 0; IA[c][k * 17] = 0;
+  }
+
+  // ---- (a) start, zero, first diamond sweep
+  int nsweep = 0;
+  for (int d = 1; d <= j0.search_range; d <<= 1) nsweep += round_size(d);
+  const int n1 = 2 + nsweep;
+  if (tid == 0) s_sweep_ok = (SWEEP && so && usable) ? 1 : 0;
+  __syncthreads();
+  if (SWEEP && so && usable && tid < n1) {
+    int x = 0, y = 0, pt = 0;
+    uint32_t dist = 0;
+    bool v = true, first = false, last = false;
+    if (tid == 0) { x = j0.startx; y = j0.starty; }
+    else if (tid >= 2) {
+      SearchCtx sc;
+      sc.lx = j0.lx; sc.ty = j0.ty; sc.rx = j0.rx; sc.by = j0.by;
+      int c = tid - 2, off = 0, d = 1;
+      while (c >= off + round_size(d)) { off += round_size(d); d <<= 1; }
+      v = diamond_cand(sc, j0.startx, j0.starty, d, c - off, x, y, pt, dist);
+      first = c == off; last = c == off + round_size(d) - 1;
+    }
+    s_cx[tid] = (int16_t)x; s_cy[tid] = (int16_t)y; s_cvalid[tid] = v; s_cpt[tid] = (uint8_t)pt; s_cdist[tid] = dist;
+    s_cfirst[tid] = first; s_clast[tid] = last;
+    s_cmv[tid] = mv_cost(j0.lambda_cost, x, y, 2, j0.predx, j0.predy);
+    const int dx = x - cen.cx, dy = y - cen.cy;
+    if (v && (dx < -kMeR || dx > kMeR || dy < -kMeR || dy > kMeR)) s_sweep_ok = 0;     // benign race: every writer stores 0
+  }
+  __syncthreads();
+  if (SWEEP && s_sweep_ok) {
+    uint32_t best = kNoCost, best_dist = 0, n_sads = 0;
+    int best_x = 0, best_y = 0, point_nr = 0, best_round = 0;
+    bool run = same;                             // this PU's sequential first search is still running
+    bool fallback = false;
+    walk_candidates(n1, tg, IE, IA, s_mvc, tid,
+      [&](int i, int& dx, int& dy) { dx = s_cx[i] - cen.cx; dy = s_cy[i] - cen.cy; return s_cvalid[i] != 0; },
+      [&](int i) { return s_cmv[i]; },
+      [&](int base) {
+        if (!run) return;
+#pragma unroll
+        for (int c = 0; c < kRastChunk; c++) {
+          const int i = base + c;
+          if (i >= n1) break;
+          if (s_cfirst[i]) best_round += 1;      // xTZ8PointDiamondSearch entry
+          if (s_cvalid[i]) {
+            const uint32_t* I = sub ? IE[c] : IA[c];
+            const uint32_t sad = I[c11] - I[c01] - I[c10] + I[c00];
+            const uint32_t cost = ((sad << sub) >> bi) + s_mvc[c];
+            n_sads++;
+            if (i == 0) { best = cost; best_x = s_cx[0]; best_y = s_cy[0]; }
+            else if (i == 1) {
+              if (cost < best) { fallback = true; run = false; break; }   // the zero vector wins: the sweep centres on (0,0) -> own search
+            } else if (cost < best) {
+              best = cost; best_x = s_cx[i]; best_y = s_cy[i]; best_dist = s_cdist[i]; point_nr = s_cpt[i]; best_round = 0;
+            }
+          }
+          if (s_clast[i] && best_round >= 3) { run = false; break; }       // bFirstSearchStop, uiFirstSearchRounds = 3
+        }
+      });
+    if (is_pu) so[tid] = (same && !fallback) ? SweepState{best, best_x, best_y, best_dist, point_nr, n_sads} : SweepState{0, 0, 0, 0, 0, 0};
+  } else if (SWEEP && is_pu && so) so[tid] = SweepState{0, 0, 0, 0, 0, 0};
+  if (SWEEP) {
+    if (tid == 0 && stats && s_sweep_ok) atomicAdd(&stats[2], (unsigned long long)n1);
+    return;
+  }
+
+  // ---- (b) raster
+  if (!covered) {                                // partial CTU / window leaves the table: every PU rasters on its own
+    if (is_pu) o[tid] = RasterBest{kNoCost, -1};
+    return;
+  }
+  uint32_t best = kNoCost;
+  int best_i = -1;
+  walk_candidates(N, tg, IE, IA, s_mvc, tid,
+    [&](int i, int& dx, int& dy) { const int iy = i / nx, ix = i - iy * nx; dx = j0.lx + ix * raster - cen.cx; dy = j0.ty + iy * raster - cen.cy; return true; },
+    [&](int i) { const int iy = i / nx, ix = i - iy * nx; return mv_cost(j0.lambda_cost, j0.lx + ix * raster, j0.ty + iy * raster, 2, j0.predx, j0.predy); },
+    [&](int base) {
+      if (!pu_ok) return;
 #pragma unroll
       for (int c = 0; c < kRastChunk; c++) {
         if (base + c < N) {
@@ -651,9 +750,7 @@ k_me_raster(const tvc_me_job* __restrict__ jobs, const uint16_t* __restrict__ ta
           if (cost < best) { best = cost; best_i = base + c; }
         }
       }
-    }
-    __syncthreads();
-  }
+    });
   if (is_pu) o[tid] = RasterBest{pu_ok ? best : kNoCost, pu_ok ? best_i : -1};
   if (tid == 0 && stats) atomicAdd(&stats[2], (unsigned long long)N);
 }
@@ -662,7 +759,7 @@ template <int MINB>
 __global__ void __launch_bounds__(128, MINB)
 k_me_search(PlaneTable pt, int cur_slot, int n, const tvc_me_job* __restrict__ jobs, tvc_me_result* __restrict__ out,
             const uint16_t* __restrict__ tables, const tvc_me_center* __restrict__ centers, int num_ctus, int ctus_x,
-            int bi, const RasterBest* __restrict__ rast, unsigned long long* __restrict__ stats)
+            int bi, const RasterBest* __restrict__ rast, const SweepState* __restrict__ sweep, unsigned long long* __restrict__ stats)
 {
   int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (j >= n) return;
@@ -711,7 +808,13 @@ k_me_search(PlaneTable pt, int cur_slot, int n, const tvc_me_job* __restrict__ j
   } else {
     // xTZSearch with TZ_SEARCH_CONFIGURATION (TEncSearch.cpp:293-309, 4302-4474)
     const int raster = 5, srange = jb.search_range;
-    {
+    SweepState sw = {0, 0, 0, 0, 0, 0};
+    if (sweep) sw = sweep[j];
+    if (sw.n_sads) {
+      // frame pre-pass: start / zero tests and the first sweep were replayed by the shared stage (k_me_raster)
+      s.best_sad = sw.best_sad; s.best_x = sw.best_x; s.best_y = sw.best_y; s.best_dist = sw.best_dist; s.point_nr = sw.point_nr;
+      s.best_round = 0; s.n_sads = sw.n_sads; served = sw.n_sads;
+    } else {
       // start point (the clipped predictor) then the zero vector (:4320, :4336-4339), sequentially
       const int x[1] = {s.lane == 0 ? jb.startx : 0}, y[1] = {s.lane == 0 ? jb.starty : 0};
       const bool valid[1] = {s.lane < 2};
@@ -727,7 +830,7 @@ k_me_search(PlaneTable pt, int cur_slot, int n, const tvc_me_job* __restrict__ j
     // first search :4346-4361.  All 76 candidates of the seven rounds are evaluated at once although the
     // reference usually stops after three rounds: measured on B200, issuing the rounds in stages (1..8,
     // 16..32, 64) costs more in serial latency (9.1 ms) than the speculative loads cost in bandwidth (8.2 ms).
-    diamond_sweep<3>(s, s.best_x, s.best_y, 1, srange, true);
+    if (!sw.n_sads) diamond_sweep<3>(s, s.best_x, s.best_y, 1, srange, true);
     if (s.best_dist == 1) { s.best_dist = 0; two_point(s); }   // :4382-4386
     if ((int)s.best_dist > raster) {                           // :4389-4400
       s.best_dist = raster;
@@ -740,7 +843,7 @@ k_me_search(PlaneTable pt, int cur_slot, int n, const tvc_me_job* __restrict__ j
         if (shared) {
           const int nx = (s.rx - s.lx) / raster + 1, ny = (s.by - s.ty) / raster + 1;
           s.n_sads += (uint32_t)(nx * ny);
-          served = (uint32_t)(nx * ny);
+          served += (uint32_t)(nx * ny);
           if (rb.cost < s.best_sad) {
             s.best_sad = rb.cost;
             s.best_x = s.lx + (rb.idx % nx) * raster;
@@ -1375,7 +1478,7 @@ int tvc_me_table_lookup(tvc_ctx* c, int ref_index, int pu_x, int pu_y, int pu_w,
 }
 
 static int launch_search(tvc_ctx* c, int cur_slot, int use_tables, int n, const tvc_me_job* jobs_dev, tvc_me_result* out_dev,
-                         const RasterBest* rast, unsigned long long* stats)
+                         const RasterBest* rast, const SweepState* sweep, unsigned long long* stats)
 {
   if (!c || !valid_slot(c, cur_slot) || n < 0 || (n && (!jobs_dev || !out_dev))) return set_err(c, TVC_ERR_ARG, "tvc_me_search_batch_dev: bad argument");
   if (use_tables && (!c->me_tables || c->me_num_refs == 0 || c->me_cur_slot != cur_slot))
@@ -1386,18 +1489,18 @@ static int launch_search(tvc_ctx* c, int cur_slot, int use_tables, int n, const 
   if (variant < 0) { const char* e = getenv("TVC_SEARCH_MINB"); variant = e ? atoi(e) : 4; }
   const uint16_t* tb = use_tables ? c->me_tables : nullptr;
   const int nctu = c->num_ctus_x * c->num_ctus_y;
-  if (variant >= 8) k_me_search<8><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast, stats);
-  else if (variant == 5) k_me_search<5><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast, stats);
-  else if (variant >= 6) k_me_search<6><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast, stats);
-  else if (variant >= 4) k_me_search<4><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast, stats);
-  else k_me_search<1><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast, stats);
+  if (variant >= 8) k_me_search<8><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast, sweep, stats);
+  else if (variant == 5) k_me_search<5><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast, sweep, stats);
+  else if (variant >= 6) k_me_search<6><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast, sweep, stats);
+  else if (variant >= 4) k_me_search<4><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast, sweep, stats);
+  else k_me_search<1><<<(n + 3) / 4, 128, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev, tb, c->me_centers, nctu, c->num_ctus_x, c->bi, rast, sweep, stats);
   TVC_LAUNCH_CHECK(c);
   return TVC_OK;
 }
 
 int tvc_me_search_batch_dev(tvc_ctx* c, int cur_slot, int use_tables, int n, const tvc_me_job* jobs_dev, tvc_me_result* out_dev)
 {
-  return launch_search(c, cur_slot, use_tables, n, jobs_dev, out_dev, nullptr, nullptr);
+  return launch_search(c, cur_slot, use_tables, n, jobs_dev, out_dev, nullptr, nullptr, nullptr);
 }
 
 int tvc_me_search_batch(tvc_ctx* c, int cur_slot, int use_tables, int n, const tvc_me_job* jobs, tvc_me_result* out)
@@ -1505,13 +1608,15 @@ int tvc_me_frame_dev(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slot
     if (c->fr_fjobs) cudaFree(c->fr_fjobs);
     if (c->fr_frac) cudaFree(c->fr_frac);
     if (c->fr_rast) cudaFree(c->fr_rast);
-    c->fr_rast = nullptr;
+    if (c->fr_sweep) cudaFree(c->fr_sweep);
+    c->fr_rast = nullptr; c->fr_sweep = nullptr;
     c->fr_jobs = nullptr; c->fr_int = nullptr; c->fr_fjobs = nullptr; c->fr_frac = nullptr; c->fr_cap = 0;
     TVC_CUDA(c, cudaMalloc(&c->fr_jobs, n * sizeof(tvc_me_job)));
     TVC_CUDA(c, cudaMalloc(&c->fr_int, n * sizeof(tvc_me_result)));
     TVC_CUDA(c, cudaMalloc(&c->fr_fjobs, n * sizeof(tvc_frac_job)));
     TVC_CUDA(c, cudaMalloc(&c->fr_frac, n * sizeof(tvc_frac_result)));
     TVC_CUDA(c, cudaMalloc(&c->fr_rast, n * 8));
+    TVC_CUDA(c, cudaMalloc(&c->fr_sweep, n * sizeof(SweepState)));
     c->fr_cap = n;
   }
   // predictors (quarter pels) and table centres (CTU-level clipMv, integer pels) on the host: tiny
@@ -1544,16 +1649,25 @@ int tvc_me_frame_dev(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slot
   if (!c->fr_stats) TVC_CUDA(c, cudaMalloc(&c->fr_stats, 3 * sizeof(unsigned long long)));
   TVC_CUDA(c, cudaMemsetAsync(c->fr_stats, 0, 3 * sizeof(unsigned long long), c->stream));
   const RasterBest* rast = nullptr;
-  static int use_rast = -1;      // tuning knob (TVC_ME_RASTER=0 walks the raster per PU)
+  const SweepState* sweep = nullptr;
+  static int use_rast = -1, use_sweep = -1;      // tuning knobs (TVC_ME_RASTER=0 / TVC_ME_SWEEP=0: every PU on its own)
   if (use_rast < 0) { const char* e = getenv("TVC_ME_RASTER"); use_rast = e ? atoi(e) : 1; }
+  if (use_sweep < 0) { const char* e = getenv("TVC_ME_SWEEP"); use_sweep = e ? atoi(e) : 1; }
   if (cfg->use_tables && use_rast) {
     ProfScope ps(c, TVC_PH_ME_RASTER);
     dim3 grd(nctu, num_refs);
-    k_me_raster<<<grd, kRastThreads, 0, c->stream>>>(c->fr_jobs, c->me_tables, c->me_centers, nctu, 5, c->bi, (RasterBest*)c->fr_rast, c->fr_stats);
+    if (use_sweep) {
+      k_me_raster<true><<<grd, kRastThreads, 0, c->stream>>>(c->fr_jobs, c->me_tables, c->me_centers, nctu, 5, c->bi, (RasterBest*)c->fr_rast,
+                                                             (SweepState*)c->fr_sweep, c->fr_stats);
+      TVC_LAUNCH_CHECK(c);
+    }
+    k_me_raster<false><<<grd, kRastThreads, 0, c->stream>>>(c->fr_jobs, c->me_tables, c->me_centers, nctu, 5, c->bi, (RasterBest*)c->fr_rast,
+                                                            nullptr, c->fr_stats);
     TVC_LAUNCH_CHECK(c);
     rast = (const RasterBest*)c->fr_rast;
+    if (use_sweep) sweep = (const SweepState*)c->fr_sweep;
   }
-  if ((r = launch_search(c, cur_slot, cfg->use_tables, (int)n, c->fr_jobs, c->fr_int, rast, c->fr_stats))) return r;
+  if ((r = launch_search(c, cur_slot, cfg->use_tables, (int)n, c->fr_jobs, c->fr_int, rast, sweep, c->fr_stats))) return r;
   if (cfg->do_frac) {
     {
       ProfScope ps(c, TVC_PH_OTHER);
@@ -1618,7 +1732,7 @@ int tvc_me_ctu(tvc_ctx* c, int cur_slot, int ref_index, int ref_slot, int ctu, t
   TVC_LAUNCH_CHECK(c);
   // no shared raster stage here: one block would walk the 729 raster candidates alone; the PUs that need the
   // raster walk it themselves, in parallel
-  if ((r = launch_search(c, cur_slot, cfg->use_tables, (int)N, d_jobs, d_int, nullptr, nullptr))) return r;
+  if ((r = launch_search(c, cur_slot, cfg->use_tables, (int)N, d_jobs, d_int, nullptr, nullptr, nullptr))) return r;
   if (cfg->do_frac) {
     k_me_frame_frac_jobs<<<(int)((N + 127) / 128), 128, 0, c->stream>>>((int)N, d_jobs, d_int, cfg->hadamard, d_fjobs);
     TVC_LAUNCH_CHECK(c);
