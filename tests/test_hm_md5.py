@@ -91,6 +91,18 @@ def test_bitstream_md5_identical_to_reference(tmp_path, cfg, frames, extra):
     assert dserved and " 0 xIT" not in dserved[-1], dc.stderr[-500:]
     print("decoder", dserved[-1])
     assert _md5(str(tmp_path / "dec_cuda.yuv")) == _md5(str(tmp_path / "dec.yuv"))
+    # C5 as BASELINE.json words it: BATCHED dequant + inverse transform and MC -- inter CUs deferred to one tvc_mc_batch + one
+    # tvc_inv_tq_batch per flush (before intra CUs and before the in-loop filters)
+    e = dict(os.environ, TVC_HM="tq,mc,batch")
+    db = subprocess.run([DEC_CUDA, "-b", cuda_bin, "-o", str(tmp_path / "dec_batch.yuv")], capture_output=True, text=True, timeout=1500, env=e)
+    assert db.returncode == 0, db.stdout[-800:] + db.stderr[-800:]
+    assert "ERROR" not in db.stdout and db.stdout.count("(OK)") >= frames
+    bl = [ln for ln in db.stderr.splitlines() if ln.startswith("TLibCuda picture batch:")]
+    assert bl, db.stderr[-500:]
+    print("decoder", bl[-1])
+    if "intra" not in cfg:
+        assert int(bl[-1].split()[3]) > 100, bl[-1]          # inter CUs really went through the batch
+    assert _md5(str(tmp_path / "dec_batch.yuv")) == _md5(str(tmp_path / "dec.yuv"))
 
 
 def test_census_lookup_serves_the_cu_loop(tmp_path):

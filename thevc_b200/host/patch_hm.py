@@ -67,7 +67,23 @@ def main():
     s = sub_once(s, r'(  Int    iQBits      = m_cQP\.m_iBits;\r?\n  Double dTemp       = 0;)',
                  r'  if ( !getUseScalingList() && tlibcuda_rdoq( pcCU, plSrcCoeff, piDstCoeff, piArlDstCoeff, uiWidth, uiHeight, uiAbsSum, (int)eTType, uiAbsPartIdx, m_cQP.m_iPer, m_cQP.m_iRem, m_dLambda, m_pcEstBitsSbac, m_bUseAdaptQpSelect ) ) return;\n\1',
                  "xRateDistOptQuant")
+    s = sub_once(s, r'(Void TComTrQuant::invtransformNxN\( Bool transQuantBypass, TextType eText, UInt uiMode,Pel\* rpcResidual, UInt uiStride, TCoeff\*   pcCoeff, UInt uiWidth, UInt uiHeight,  Int scalingListType, Bool useTransformSkip \)\r?\n\{\r?\n)',
+                 r'\1  if ( tlibcuda_defer_itransform( transQuantBypass, (int)eText, rpcResidual, uiStride, pcCoeff, uiWidth, uiHeight, m_cQP.m_iPer, m_cQP.m_iRem, useTransformSkip ) ) return;\n',
+                 "invtransformNxN")
     wr(os.path.join(out, "TLibCommon", "TComTrQuant.cpp"), s)
+    # ---- TDecCu.cpp / TDecGop.cpp: picture-level batch of the inter reconstruction
+    os.makedirs(os.path.join(out, "TLibDecoder"), exist_ok=True)
+    s = rd(os.path.join(lib, "TLibDecoder", "TDecCu.cpp"))
+    s = sub_once(s, r'(#include "TDecCu.h"\r?\n)', r'\1#include "tlibcuda_hm.h"\n', "TDecCu include")
+    s = sub_once(s, r'(Void TDecCu::xReconInter\( TComDataCU\* pcCU, UInt uiAbsPartIdx, UInt uiDepth \)\r?\n\{\r?\n)',
+                 r'\1  tlibcuda_dec_begin_inter( pcCU, m_ppcYuvResi[uiDepth] );\n', "xReconInter")
+    s = sub_once(s, r'(TDecCu::xReconIntraQT\( TComDataCU\* pcCU, UInt uiAbsPartIdx, UInt uiDepth \)\r?\n\{\r?\n)',
+                 r'\1  tlibcuda_dec_flush( pcCU->getPic() );\n', "xReconIntraQT")
+    wr(os.path.join(out, "TLibDecoder", "TDecCu.cpp"), s)
+    s = rd(os.path.join(lib, "TLibDecoder", "TDecGop.cpp"))
+    s = sub_once(s, r'(#include "TDecGop.h"\r?\n)', r'\1#include "tlibcuda_hm.h"\n', "TDecGop include")
+    s = sub_once(s, r'(Void TDecGop::filterPicture\(TComPic\*& rpcPic\)\r?\n\{\r?\n)', r'\1  tlibcuda_dec_flush( rpcPic );\n', "filterPicture")
+    wr(os.path.join(out, "TLibDecoder", "TDecGop.cpp"), s)
     # ---- TComPrediction.cpp: xPredInterUni (shared by encoder and decoder)
     s = rd(os.path.join(lib, "TLibCommon", "TComPrediction.cpp"))
     s = sub_once(s, r'(#include "TComPrediction.h"\r?\n)', r'\1#include "tlibcuda_hm.h"\n', "TComPrediction include")
@@ -75,7 +91,7 @@ def main():
                  r'\1  if ( tlibcuda_pred_inter_uni( pcCU, pcCU->getSlice()->getRefPic( eRefPicList, iRefIdx ), uiPartAddr, cMv.getHor(), cMv.getVer(), iWidth, iHeight, rpcYuvPred, bi ) ) return;\n',
                  "xPredInterUni", flags=re.S)
     wr(os.path.join(out, "TLibCommon", "TComPrediction.cpp"), s)
-    print("patched 5 files into", out)
+    print("patched 7 files into", out)
 
 
 if __name__ == "__main__":

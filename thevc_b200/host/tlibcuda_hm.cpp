@@ -58,9 +58,29 @@ struct LastHit {                           // the integer search just served by 
   tvc_frac_result fr;
 };
 
+// decoder picture batch: what is pending and the CU being announced
+struct DecCu { int x, y, w; };
+struct DecBatch {
+  bool on = false;                         // TVC_HM=...,batch
+  bool cu_open = false;                    // between tlibcuda_dec_begin_inter and the next begin / flush
+  int cu_x = 0, cu_y = 0;
+  const short* resi_base[3] = {nullptr, nullptr, nullptr};
+  int resi_stride[3] = {0, 0, 0};
+  std::vector<tvc_pu> pus;
+  std::vector<tvc_tu> tus;
+  std::vector<int32_t> levels;
+  std::vector<DecCu> cus;
+  bool half = false;                       // first list of a bi-predicted PU seen, waiting for the second
+  tvc_pu half_pu;
+  std::vector<short> stage[3];             // download staging (picture size, no margin)
+  unsigned long long n_flush = 0, n_cus = 0, n_pus = 0, n_tus = 0;
+  double seconds = 0.0;
+};
+
 struct State {
   tvc_ctx* h = nullptr;
   bool on_lookup = true, verify = false;
+  DecBatch dec;
   std::map<long long, Group> groups;       // key = ctu * 64 + device slot of the reference; cleared per picture
   std::map<unsigned, int> census_index;    // (x, y, w, h) inside the CTU -> census index
   std::vector<tvc_me_center> center_guess; // [table ref][ctu]: first predictor of the previous picture's group (quarter pels)
@@ -100,6 +120,9 @@ void report()
   if (s.h && s.on_lookup)
     fprintf(stderr, "TLibCuda look-up: %llu of %llu xTZSearch and %llu of %llu xPatternSearchFracDIF calls served from %llu census-wide (CTU, reference) batches (%.3f s in tvc_me_ctu, %.3f s in picture uploads + SAD-table pre-passes)\n",
             s.n_tz_lookup, s.n_tz, s.n_frac_lookup, s.n_frac, s.n_groups, s.batch_seconds, s.prepass_seconds);
+  if (s.h && s.dec.on)
+    fprintf(stderr, "TLibCuda picture batch: %llu inter CUs (%llu PUs, %llu TUs) reconstructed in %llu device batches, %.3f s in the batches\n",
+            s.dec.n_cus, s.dec.n_pus, s.dec.n_tus, s.dec.n_flush, s.dec.seconds);
   if (s.h)
     fprintf(stderr, "TLibCuda: %llu xTZSearch, %llu xPatternSearchFracDIF, %llu xT, %llu xIT, %llu xDeQuant, %llu xRateDistOptQuant, %llu xPredInterUni calls served; %llu kernel launches\n",
             s.n_tz, s.n_frac, s.n_xt, s.n_xit, s.n_dq, s.n_rdoq, s.n_mc, (unsigned long long)tvc_launch_count(s.h));
@@ -156,6 +179,7 @@ void parse_env()
   s.verbose = strstr(e, "verbose") != nullptr;
   s.on_lookup = strstr(e, "nolookup") == nullptr;
   s.verify = strstr(e, "verify") != nullptr;
+  s.dec.on = strstr(e, "batch") != nullptr;
   if (strstr(e, "stats")) { PS().on = true; s.on_me = s.on_frac = s.on_tq = s.on_rdoq = s.on_mc = s.on_tables = false; atexit(stats_report); }
 }
 
@@ -184,6 +208,8 @@ void ensure_ctx(int w, int ht)
   s.w = w; s.ht = ht;
   s.slots.assign(c.num_slots, DevPic());
   s.cur_slot = -1; s.num_table_refs = 0;
+  // the last two slots are the decoder batch's reconstruction and residual planes: never handed out as picture slots
+  s.slots[c.num_slots - 1].stamp = s.slots[c.num_slots - 2].stamp = ~0ull;
 }
 
 // slot of a picture buffer; uploads it when the slot does not hold this picture's current content
@@ -425,6 +451,22 @@ bool tlibcuda_pred_inter_uni(TComDataCU* cu, TComPic* refPic, unsigned partAddr,
   const int ctus_x = (int)cu->getPic()->getFrameWidthInCU();
   const int x = (int)(cu->getAddr() % ctus_x) * (int)g_uiMaxCUWidth + (int)g_auiRasterToPelX[raster];
   const int y = (int)(cu->getAddr() / ctus_x) * (int)g_uiMaxCUHeight + (int)g_auiRasterToPelY[raster];
+  if (s.dec.cu_open) {
+    // picture batch: record the PU; the two lists of a bi-predicted PU arrive as two consecutive calls (xPredInterBi)
+    DecBatch& d = s.dec;
+    if (!bi) {
+      d.pus.push_back(tvc_pu{x, y, w, h, slot, mvx, mvy, -1, 0, 0});
+    } else if (d.half && d.half_pu.x == x && d.half_pu.y == y && d.half_pu.w == w && d.half_pu.h == h) {
+      d.half_pu.ref_slot1 = slot; d.half_pu.mvx1 = mvx; d.half_pu.mvy1 = mvy;
+      d.pus.push_back(d.half_pu);
+      d.half = false;
+    } else {
+      d.half_pu = tvc_pu{x, y, w, h, slot, mvx, mvy, -1, 0, 0};
+      d.half = true;
+    }
+    s.n_mc++;
+    return true;
+  }
   CK(tvc_mc_block(s.h, slot, x, y, w, h, mvx, mvy, bi ? 1 : 0, dst->getLumaAddr(partAddr), (int)dst->getStride(),
                   dst->getCbAddr(partAddr), dst->getCrAddr(partAddr), (int)dst->getCStride()));
   s.n_mc++;
@@ -485,4 +527,82 @@ bool tlibcuda_rdoq(TComDataCU* cu, int* src, int* dst, int* arl, unsigned w, uns
                            cu->getSlice()->getPPS()->getSignHideFlag() ? 1 : 0, useArl ? 1 : 0, lambda, (const tvc_est_bits*)est, &absSum));
   s.n_rdoq++;
   return true;
+}
+
+// ---------------------------------------------------------------------------------------------- decoder picture batch
+bool tlibcuda_dec_begin_inter(TComDataCU* cu, TComYuv* resi)
+{
+  State& s = S();
+  TComPicYuv* rec = cu->getPic()->getPicYuvRec();
+  ensure_ctx(rec->getWidth(), rec->getHeight());
+  DecBatch& d = s.dec;
+  if (!s.h || !d.on || !s.on_mc || !s.on_tq) return false;
+  d.cu_open = true;
+  d.cu_x = (int)cu->getCUPelX(); d.cu_y = (int)cu->getCUPelY();
+  d.resi_base[0] = resi->getLumaAddr(); d.resi_base[1] = resi->getCbAddr(); d.resi_base[2] = resi->getCrAddr();
+  d.resi_stride[0] = (int)resi->getStride(); d.resi_stride[1] = d.resi_stride[2] = (int)resi->getCStride();
+  d.cus.push_back(DecCu{d.cu_x, d.cu_y, (int)cu->getWidth(0)});
+  return true;
+}
+
+bool tlibcuda_defer_itransform(bool bypass, int ttype, short* resi, unsigned stride, int* coeff, unsigned w, unsigned h, int per, int rem,
+                               bool transformSkip)
+{
+  State& s = S();
+  DecBatch& d = s.dec;
+  if (!d.cu_open || w != h) return false;
+  const int plane = ttype == TEXT_LUMA ? 0 : (ttype == TEXT_CHROMA_U ? 1 : 2);
+  const ptrdiff_t off = resi - d.resi_base[plane];
+  if (off < 0 || (int)stride != d.resi_stride[plane]) return false;      // not this CU's residual buffer: leave it to the host
+  const int sh = plane ? 1 : 0;
+  tvc_tu t;
+  memset(&t, 0, sizeof(t));
+  t.plane = plane;
+  t.x = (d.cu_x >> sh) + (int)(off % stride);
+  t.y = (d.cu_y >> sh) + (int)(off / stride);
+  t.log2_size = w == 4 ? 2 : (w == 8 ? 3 : (w == 16 ? 4 : 5));
+  t.flags = bypass ? TVC_TU_BYPASS : (transformSkip ? TVC_TU_SKIP : 0);
+  t.qp_per = per; t.qp_rem = rem; t.base_per = per;
+  t.coef_offset = (int)d.levels.size();
+  d.levels.insert(d.levels.end(), coeff, coeff + (size_t)w * h);
+  d.tus.push_back(t);
+  return true;
+}
+
+void tlibcuda_dec_flush(TComPic* pic)
+{
+  State& s = S();
+  DecBatch& d = s.dec;
+  d.cu_open = false;
+  if (!s.h || d.cus.empty()) return;
+  const auto t0 = std::chrono::steady_clock::now();
+  if (d.half) { d.pus.push_back(d.half_pu); d.half = false; }          // cannot happen without weighted prediction
+  const int rec_slot = (int)s.slots.size() - 1, resi_slot = (int)s.slots.size() - 2;
+  if (!d.pus.empty()) CK(tvc_mc_batch(s.h, rec_slot, (int)d.pus.size(), d.pus.data()));
+  if (!d.tus.empty()) {
+    // the ABI wants the TU list grouped by ascending size
+    std::stable_sort(d.tus.begin(), d.tus.end(), [](const tvc_tu& a, const tvc_tu& b) { return a.log2_size < b.log2_size; });
+    CK(tvc_inv_tq_batch(s.h, resi_slot, rec_slot, rec_slot, (int)d.tus.size(), d.tus.data(), d.levels.data(), d.levels.size()));
+  }
+  TComPicYuv* rec = pic->getPicYuvRec();
+  const int W = rec->getWidth(), H = rec->getHeight();
+  if (d.stage[0].size() != (size_t)W * H) {
+    d.stage[0].assign((size_t)W * H, 0);
+    d.stage[1].assign((size_t)(W / 2) * (H / 2), 0);
+    d.stage[2].assign((size_t)(W / 2) * (H / 2), 0);
+  }
+  CK(tvc_pic_download(s.h, rec_slot, d.stage[0].data(), W, d.stage[1].data(), d.stage[2].data(), W / 2, 0));
+  for (const DecCu& c : d.cus) {
+    for (int pl = 0; pl < 3; pl++) {
+      const int sh = pl ? 1 : 0, st = pl ? W / 2 : W;
+      short* dst = (pl == 0 ? rec->getLumaAddr() : (pl == 1 ? rec->getCbAddr() : rec->getCrAddr()));
+      const int ds = pl ? rec->getCStride() : rec->getStride();
+      const int x = c.x >> sh, y = c.y >> sh, n = c.w >> sh;
+      for (int r = 0; r < n; r++)
+        memcpy(dst + (ptrdiff_t)(y + r) * ds + x, d.stage[pl].data() + (size_t)(y + r) * st + x, (size_t)n * sizeof(short));
+    }
+  }
+  d.n_flush++; d.n_cus += d.cus.size(); d.n_pus += d.pus.size(); d.n_tus += d.tus.size();
+  d.pus.clear(); d.tus.clear(); d.levels.clear(); d.cus.clear();
+  d.seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }

@@ -42,6 +42,19 @@ bool tlibcuda_pred_inter_uni(TComDataCU* cu, TComPic* refPic, unsigned partAddr,
 bool tlibcuda_xT(unsigned mode, short* resi, unsigned stride, int* coef, int w, int h);
 bool tlibcuda_xIT(unsigned mode, int* coef, short* resi, unsigned stride, int w, int h);
 bool tlibcuda_xDeQuant(const int* src, int* dst, int w, int h, int per, int rem);
+/* ---- decoder, picture-level batch (TVC_HM=...,batch): inter CUs are not reconstructed one by one.  TDecCu::xReconInter
+ * (TDecCu.cpp:448-466) announces the CU; the reference's own motionCompensation / xDecodeInterTexture then run with their
+ * leaves recording instead of computing (xPredInterUni -> one tvc_pu, invtransformNxN -> one tvc_tu + its levels); the
+ * batch is executed -- one tvc_mc_batch + one tvc_inv_tq_batch for everything pending -- when an intra CU needs its
+ * neighbours (TDecCu::xReconIntraQT, :689) and before the in-loop filters (TDecGop::filterPicture, TDecGop.cpp:201), and
+ * the reconstructed CUs are copied into the picture. */
+class TComPic;
+bool tlibcuda_dec_begin_inter(TComDataCU* cu, TComYuv* resi);
+void tlibcuda_dec_flush(TComPic* pic);
+/* TComTrQuant::invtransformNxN (TComTrQuant.cpp:1428): true = recorded for the picture batch, nothing to do */
+bool tlibcuda_defer_itransform(bool bypass, int ttype, short* resi, unsigned stride, int* coeff, unsigned w, unsigned h, int per, int rem,
+                               bool transformSkip);
+
 /* TComTrQuant::xRateDistOptQuant (TComTrQuant.cpp:1719): est is m_pcEstBitsSbac (estBitsSbacStruct == tvc_est_bits) */
 bool tlibcuda_rdoq(TComDataCU* cu, int* src, int* dst, int* arl, unsigned w, unsigned h, unsigned& absSum, int ttype,
                    unsigned absPartIdx, int per, int rem, double lambda, const void* est, bool useArl);
