@@ -390,12 +390,33 @@ int tvc_xRateDistOptQuant(tvc_ctx* ctx, const int32_t* coef, int32_t* qcoef, int
                           int scan_idx, int qp_per, int qp_rem, int cbf_ctx, int sign_hide, int use_arl,
                           double lambda, const tvc_est_bits* est, uint32_t* abs_sum);
 
+/* ---------------------------------------------------------------------------------- deblocking filter
+ * SURVEY.md 8(f)-1.  Replaces the sample work of TComLoopFilter::loopFilterPic (TComLoopFilter.cpp:153-191):
+ * xEdgeFilterLuma / xEdgeFilterChroma (:571-797) with xPelFilterLuma / xPelFilterChroma / xUseStrongFiltering /
+ * xCalcDP / xCalcDQ (:799-921) and the tc / beta tables (:56-64), on a device-resident picture, in place: all vertical
+ * edges, then all horizontal edges (the reference's two passes; inside a pass edges lie 8 pels apart and touch at most
+ * 3 + 4 pels on either side, so their order does not matter).  The boundary strengths stay host work (they come out of
+ * the CU tree: xSetLoopfilterParam, xSetEdgefilterTU/PU, xGetBoundaryStrengthSingle, :266-569): the host hands over
+ * one record per 4-pel edge unit on the 8x8 grid.  Chroma edges (4:2:0) are derived from the same records: units with
+ * bs > 1 on the 16-pel luma grid, QP through g_aucChromaScale (TComRom.cpp:380-386).                               */
+typedef struct {
+  uint8_t bs;                  /* m_aapucBS at the unit: 0 none, 1, 2                                              */
+  uint8_t qp;                  /* (QP_P + QP_Q + 1) >> 1 of the two CUs (:627)                                     */
+  uint8_t flags;               /* bit 0: part P not filtered, bit 1: part Q not filtered (IPCM / lossless, :651-658) */
+  uint8_t reserved;
+} tvc_dbk_unit;
+/* ver: vertical edges, entry [(y >> 2) * ((width + 7) >> 3) + (x >> 3)] = edge at luma column x (multiple of 8), rows
+ * y .. y+3; hor: horizontal edges, entry [(y >> 3) * ((width + 3) >> 2) + (x >> 2)] = edge at luma row y (multiple of
+ * 8), columns x .. x+3.  Host arrays; either may be NULL (pass skipped).                                          */
+int tvc_deblock_pic(tvc_ctx* ctx, int slot, const tvc_dbk_unit* ver, const tvc_dbk_unit* hor, int beta_offset_div2,
+                    int tc_offset_div2);
+
 /* ---------------------------------------------------------------------------------- per-phase device timing
  * CUDA events recorded on the context stream around every kernel group, so that bench.py can report
  * each kernel's duration measured live inside the timed region (not under a profiler).         */
 enum {
   TVC_PH_ME_TABLES = 0, TVC_PH_ME_SEARCH = 1, TVC_PH_ME_FRAC = 2, TVC_PH_MC = 3, TVC_PH_FWD_TQ = 4,
-  TVC_PH_INV_TQ = 5, TVC_PH_OTHER = 6, TVC_PH_ME_RASTER = 7, TVC_PH_RDOQ = 8, TVC_PH_COUNT = 9
+  TVC_PH_INV_TQ = 5, TVC_PH_OTHER = 6, TVC_PH_ME_RASTER = 7, TVC_PH_RDOQ = 8, TVC_PH_DEBLOCK = 9, TVC_PH_COUNT = 10
 };
 int tvc_prof_enable(tvc_ctx* ctx, int on);
 /* synchronises the stream, adds the elapsed time of every recorded pair to per-phase sums and returns

@@ -63,7 +63,7 @@ def build(force: bool = False) -> None:
     """Compile libhm_oracle.so (always possible) and, when /root/reference is present,
     _ref/libhmref.so.  Building the checker is not using it."""
     so = os.path.join(HERE, "libhm_oracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("hm_oracle.c", "hm_oracle_me.c", "hm_oracle_tq.c", "hm_oracle_frame.c", "hm_oracle_rdoq.c", "hm_oracle.h")]
+    srcs = [os.path.join(HERE, f) for f in ("hm_oracle.c", "hm_oracle_me.c", "hm_oracle_tq.c", "hm_oracle_frame.c", "hm_oracle_rdoq.c", "hm_oracle_deblock.c", "hm_oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", HERE, "-B", "oracle"])
     ref_so = os.path.join(HERE, "_ref", "libhmref.so")
@@ -141,6 +141,7 @@ def lib():
     L.orc_rdoq.argtypes = [i32p, i32p, vp, C.POINTER(RdoqParam), C.POINTER(EstBits), u32p, C.POINTER(cu)]
     L.orc_rdoq.restype = None
     L.orc_rdoq_err_scale.argtypes = [ci, ci, ci]; L.orc_rdoq_err_scale.restype = C.c_double
+    L.orc_deblock_pic.argtypes = [vp, ci, vp, vp, ci, ci, ci, vp, vp, ci, ci, ci]; L.orc_deblock_pic.restype = None
     L.orc_census.argtypes = [vp]; L.orc_census.restype = None
     L.orc_me_frame_ctu.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, cu, ci, ci, ci, ci, ci, vp, vp]
     L.orc_me_frame_ctu.restype = None

@@ -161,6 +161,11 @@ double orc_rdoq_err_scale(int log2_size, int qp_rem, int bd);
 void orc_rdoq(const int32_t* coef, int32_t* qcoef, int32_t* arl, const orc_rdoq_param* p,
               const orc_est_bits* est, const uint32_t* scan, uint32_t* abs_sum);
 
+/* ------------------------------------------------------------------ deblocking (hm_oracle_deblock.c) */
+typedef struct { uint8_t bs, qp, flags, reserved; } orc_dbk_unit;      /* same layout as tvc_dbk_unit */
+void orc_deblock_pic(Pel* Y, int sy, Pel* U, Pel* V, int sc, int width, int height, const orc_dbk_unit* ver,
+                     const orc_dbk_unit* hor, int beta_off2, int tc_off2, int bd);
+
 /* ------------------------------------------------------------------ frame-level drivers (hm_oracle_frame.c) */
 #define ORC_CENSUS 593
 void orc_census(int16_t* out /* ORC_CENSUS * 6: x, y, w, h, cu_x, cu_y */);

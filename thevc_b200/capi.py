@@ -75,7 +75,7 @@ class MeFrameCfg(C.Structure):
 
 
 ME_CENSUS = 593
-PHASES = ("me_tables", "me_search", "me_frac", "mc", "fwd_tq", "inv_tq", "other", "me_raster", "rdoq")
+PHASES = ("me_tables", "me_search", "me_frac", "mc", "fwd_tq", "inv_tq", "other", "me_raster", "rdoq", "deblock")
 
 # numpy views of the ABI structs (same layout) for bulk results
 ME_RESULT_DTYPE = np.dtype([("mvx", "<i4"), ("mvy", "<i4"), ("sad", "<u4"), ("n_sads", "<u4")])
@@ -161,6 +161,7 @@ SIGNATURES = {
     "tvc_xT": (ci, [vp, ci, vp, ci, vp, ci, ci]),
     "tvc_xIT": (ci, [vp, ci, vp, vp, ci, ci, ci]),
     "tvc_xDeQuant": (ci, [vp, vp, vp, ci, ci, ci, ci]),
+    "tvc_deblock_pic": (ci, [vp, ci, vp, vp, ci, ci]),
     "tvc_prof_enable": (ci, [vp, ci]),
     "tvc_prof_read": (ci, [vp, vp, vp, ci]),
     "tvc_ubench": (ci, [vp, ci, C.POINTER(C.c_double)]),

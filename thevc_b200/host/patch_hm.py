@@ -84,6 +84,18 @@ def main():
     s = sub_once(s, r'(#include "TDecGop.h"\r?\n)', r'\1#include "tlibcuda_hm.h"\n', "TDecGop include")
     s = sub_once(s, r'(Void TDecGop::filterPicture\(TComPic\*& rpcPic\)\r?\n\{\r?\n)', r'\1  tlibcuda_dec_flush( rpcPic );\n', "filterPicture")
     wr(os.path.join(out, "TLibDecoder", "TDecGop.cpp"), s)
+    # ---- TComLoopFilter.cpp: the deblocking sample work (encoder and decoder)
+    s = rd(os.path.join(lib, "TLibCommon", "TComLoopFilter.cpp"))
+    s = sub_once(s, r'(#include "TComLoopFilter.h"\r?\n)', r'\1#include "tlibcuda_hm.h"\n', "TComLoopFilter include")
+    s = sub_once(s, r'(\n  // Horizontal filtering\r?\n  UInt uiCUAddr;\r?\n)', r'\n  tlibcuda_dbk_begin( pcPic );\1', "loopFilterPic begin")
+    s = sub_once(s, r'(    xDeblockCU\( pcCU, 0, 0, EDGE_HOR \);\r?\n  \}\r?\n)(\}\r?\n)',
+                 r'\1  tlibcuda_dbk_end( pcPic, m_betaOffsetDiv2, m_tcOffsetDiv2 );\n\2', "loopFilterPic end")
+    s = sub_once(s, r'(      iQP = \(iQP_P \+ iQP_Q \+ 1\) >> 1;\r?\n)',
+                 r'\1      if ( tlibcuda_dbk_unit( pcCU, uiAbsZorderIdx, iDir, iEdge, iIdx, uiBs, iQP, pcCUP, uiPartPIdx, pcCUQ, uiPartQIdx ) ) continue;\n',
+                 "xEdgeFilterLuma")
+    s = sub_once(s, r'(Void TComLoopFilter::xEdgeFilterChroma\( TComDataCU\* pcCU, UInt uiAbsZorderIdx, UInt uiDepth, Int iDir, Int iEdge \)\r?\n\{\r?\n)',
+                 r'\1  if ( tlibcuda_dbk_skip_chroma() ) return;\n', "xEdgeFilterChroma")
+    wr(os.path.join(out, "TLibCommon", "TComLoopFilter.cpp"), s)
     # ---- TComPrediction.cpp: xPredInterUni (shared by encoder and decoder)
     s = rd(os.path.join(lib, "TLibCommon", "TComPrediction.cpp"))
     s = sub_once(s, r'(#include "TComPrediction.h"\r?\n)', r'\1#include "tlibcuda_hm.h"\n', "TComPrediction include")
@@ -91,7 +103,7 @@ def main():
                  r'\1  if ( tlibcuda_pred_inter_uni( pcCU, pcCU->getSlice()->getRefPic( eRefPicList, iRefIdx ), uiPartAddr, cMv.getHor(), cMv.getVer(), iWidth, iHeight, rpcYuvPred, bi ) ) return;\n',
                  "xPredInterUni", flags=re.S)
     wr(os.path.join(out, "TLibCommon", "TComPrediction.cpp"), s)
-    print("patched 7 files into", out)
+    print("patched 8 files into", out)
 
 
 if __name__ == "__main__":

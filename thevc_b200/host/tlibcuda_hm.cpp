@@ -77,9 +77,21 @@ struct DecBatch {
   double seconds = 0.0;
 };
 
+// deblocking: the edge-unit records of the picture being filtered
+struct Dbk {
+  bool on = false, dump = false, active = false;
+  int w = 0, h = 0;
+  std::vector<tvc_dbk_unit> ver, hor;
+  std::vector<short> before[3];
+  int dumped = 0;
+  unsigned long long n_pics = 0, n_units = 0;
+  double seconds = 0.0;
+};
+
 struct State {
   tvc_ctx* h = nullptr;
   bool on_lookup = true, verify = false;
+  Dbk dbk;
   DecBatch dec;
   std::map<long long, Group> groups;       // key = ctu * 64 + device slot of the reference; cleared per picture
   std::map<unsigned, int> census_index;    // (x, y, w, h) inside the CTU -> census index
@@ -120,6 +132,9 @@ void report()
   if (s.h && s.on_lookup)
     fprintf(stderr, "TLibCuda look-up: %llu of %llu xTZSearch and %llu of %llu xPatternSearchFracDIF calls served from %llu census-wide (CTU, reference) batches (%.3f s in tvc_me_ctu, %.3f s in picture uploads + SAD-table pre-passes)\n",
             s.n_tz_lookup, s.n_tz, s.n_frac_lookup, s.n_frac, s.n_groups, s.batch_seconds, s.prepass_seconds);
+  if (s.dbk.on && s.dbk.n_pics)
+    fprintf(stderr, "TLibCuda deblocking: %llu pictures, %llu edge units filtered on the device, %.3f s (upload + 2 kernels + download)\n",
+            s.dbk.n_pics, s.dbk.n_units, s.dbk.seconds);
   if (s.h && s.dec.on)
     fprintf(stderr, "TLibCuda picture batch: %llu inter CUs (%llu PUs, %llu TUs) reconstructed in %llu device batches, %.3f s in the batches\n",
             s.dec.n_cus, s.dec.n_pus, s.dec.n_tus, s.dec.n_flush, s.dec.seconds);
@@ -180,16 +195,26 @@ void parse_env()
   s.on_lookup = strstr(e, "nolookup") == nullptr;
   s.verify = strstr(e, "verify") != nullptr;
   s.dec.on = strstr(e, "batch") != nullptr;
+  s.dbk.dump = strstr(e, "dbkdump") != nullptr;
+  s.dbk.on = !s.dbk.dump && strstr(e, "dbk") != nullptr;
   if (strstr(e, "stats")) { PS().on = true; s.on_me = s.on_frac = s.on_tq = s.on_rdoq = s.on_mc = s.on_tables = false; atexit(stats_report); }
+}
+
+void init_once()
+{
+  static bool done = false;
+  if (done) return;
+  done = true;
+  parse_env();
+  atexit(report);
 }
 
 void ensure_ctx(int w, int ht)
 {
   State& s = S();
   if (s.disabled || (s.h && s.w >= w && s.ht >= ht)) return;
-  static bool parsed = false;
-  if (!parsed) { parse_env(); parsed = true; atexit(report); }
-  if (!s.on_me && !s.on_frac && !s.on_tq && !s.on_rdoq && !s.on_mc) { s.disabled = true; return; }     // TVC_HM=none: the unmodified path
+  init_once();
+  if (!s.on_me && !s.on_frac && !s.on_tq && !s.on_rdoq && !s.on_mc && !s.dbk.on) { s.disabled = true; return; }     // TVC_HM=none: the unmodified path
   if (s.h) {                  // the decoder learns the picture size after its first transforms: start over with the real size
     tvc_ctx_destroy(s.h);
     s.h = nullptr;
@@ -605,4 +630,87 @@ void tlibcuda_dec_flush(TComPic* pic)
   d.n_flush++; d.n_cus += d.cus.size(); d.n_pus += d.pus.size(); d.n_tus += d.tus.size();
   d.pus.clear(); d.tus.clear(); d.levels.clear(); d.cus.clear();
   d.seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ---------------------------------------------------------------------------------------------- deblocking
+void tlibcuda_dbk_begin(TComPic* pic)
+{
+  init_once();
+  State& s = S();
+  Dbk& d = s.dbk;
+  d.active = false;
+  if (!d.on && !d.dump) return;
+  TComPicYuv* rec = pic->getPicYuvRec();
+  if (d.on) { ensure_ctx(rec->getWidth(), rec->getHeight()); if (!s.h) return; }
+  d.w = rec->getWidth(); d.h = rec->getHeight();
+  d.ver.assign((size_t)((d.w + 7) >> 3) * ((d.h + 3) >> 2), tvc_dbk_unit{0, 0, 0, 0});
+  d.hor.assign((size_t)((d.w + 3) >> 2) * ((d.h + 7) >> 3), tvc_dbk_unit{0, 0, 0, 0});
+  d.active = true;
+  if (d.dump) {
+    for (int pl = 0; pl < 3; pl++) {
+      const int w = pl ? d.w / 2 : d.w, h = pl ? d.h / 2 : d.h, st = pl ? rec->getCStride() : rec->getStride();
+      const short* src = pl == 0 ? rec->getLumaAddr() : (pl == 1 ? rec->getCbAddr() : rec->getCrAddr());
+      d.before[pl].resize((size_t)w * h);
+      for (int r = 0; r < h; r++) memcpy(&d.before[pl][(size_t)r * w], src + (ptrdiff_t)r * st, (size_t)w * sizeof(short));
+    }
+  }
+}
+
+bool tlibcuda_dbk_unit(TComDataCU* cu, unsigned absZorderIdx, int dir, int edge, unsigned idx, unsigned bs, int qp, TComDataCU* cuP,
+                       unsigned partP, TComDataCU* cuQ, unsigned partQ)
+{
+  Dbk& d = S().dbk;
+  if (!d.active) return false;
+  const int x0 = (int)cu->getCUPelX() + (int)g_auiRasterToPelX[g_auiZscanToRaster[absZorderIdx]];
+  const int y0 = (int)cu->getCUPelY() + (int)g_auiRasterToPelY[g_auiZscanToRaster[absZorderIdx]];
+  const int x = dir == 0 ? x0 + edge * 4 : x0 + (int)idx * 4, y = dir == 0 ? y0 + (int)idx * 4 : y0 + edge * 4;
+  // xEdgeFilterLuma :651-658
+  const bool pcm = cu->getSlice()->getSPS()->getUsePCM() && cu->getSlice()->getSPS()->getPCMFilterDisableFlag();
+  const bool keepP = (pcm && cuP->getIPCMFlag(partP)) || cuP->isLosslessCoded(partP);
+  const bool keepQ = (pcm && cuQ->getIPCMFlag(partQ)) || cuQ->isLosslessCoded(partQ);
+  tvc_dbk_unit u = {(uint8_t)bs, (uint8_t)qp, (uint8_t)((keepP ? 1 : 0) | (keepQ ? 2 : 0)), 0};
+  if (dir == 0) d.ver[(size_t)(y >> 2) * ((d.w + 7) >> 3) + (x >> 3)] = u;
+  else d.hor[(size_t)(y >> 3) * ((d.w + 3) >> 2) + (x >> 2)] = u;
+  d.n_units++;
+  return d.on;            // device mode: the host does not filter; dump mode: the reference filters as usual
+}
+
+bool tlibcuda_dbk_skip_chroma() { const Dbk& d = S().dbk; return d.active && d.on; }
+
+void tlibcuda_dbk_end(TComPic* pic, int betaOffsetDiv2, int tcOffsetDiv2)
+{
+  State& s = S();
+  Dbk& d = s.dbk;
+  if (!d.active) return;
+  d.active = false;
+  TComPicYuv* rec = pic->getPicYuvRec();
+  if (d.on) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const int slot = (int)s.slots.size() - 1;       // the reserved reconstruction slot
+    CK(tvc_pic_upload(s.h, slot, rec->getLumaAddr(), rec->getStride(), rec->getCbAddr(), rec->getCrAddr(), rec->getCStride(), 0));
+    CK(tvc_deblock_pic(s.h, slot, d.ver.data(), d.hor.data(), betaOffsetDiv2, tcOffsetDiv2));
+    CK(tvc_pic_download(s.h, slot, rec->getLumaAddr(), rec->getStride(), rec->getCbAddr(), rec->getCrAddr(), rec->getCStride(), 0));
+    d.n_pics++;
+    d.seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return;
+  }
+  // dump mode: picture before / after the reference's own filtering + the records, raw little-endian
+  const char* dir = getenv("TVC_DBK_DUMP");
+  const int limit = getenv("TVC_DBK_DUMP_PICS") ? atoi(getenv("TVC_DBK_DUMP_PICS")) : 4;
+  if (!dir || d.dumped >= limit) return;
+  char name[512];
+  snprintf(name, sizeof(name), "%s/dbk_%02d.bin", dir, d.dumped++);
+  FILE* f = fopen(name, "wb");
+  if (!f) return;
+  const int hdr[6] = {d.w, d.h, (int)(g_uiBitDepth + g_uiBitIncrement), betaOffsetDiv2, tcOffsetDiv2, pic->getPOC()};
+  fwrite(hdr, sizeof(int), 6, f);
+  fwrite(d.ver.data(), sizeof(tvc_dbk_unit), d.ver.size(), f);
+  fwrite(d.hor.data(), sizeof(tvc_dbk_unit), d.hor.size(), f);
+  for (int pl = 0; pl < 3; pl++) fwrite(d.before[pl].data(), sizeof(short), d.before[pl].size(), f);
+  for (int pl = 0; pl < 3; pl++) {
+    const int w = pl ? d.w / 2 : d.w, h = pl ? d.h / 2 : d.h, st = pl ? rec->getCStride() : rec->getStride();
+    const short* src = pl == 0 ? rec->getLumaAddr() : (pl == 1 ? rec->getCbAddr() : rec->getCrAddr());
+    for (int r = 0; r < h; r++) fwrite(src + (ptrdiff_t)r * st, sizeof(short), (size_t)w, f);
+  }
+  fclose(f);
 }

@@ -55,6 +55,17 @@ void tlibcuda_dec_flush(TComPic* pic);
 bool tlibcuda_defer_itransform(bool bypass, int ttype, short* resi, unsigned stride, int* coeff, unsigned w, unsigned h, int per, int rem,
                                bool transformSkip);
 
+/* ---- deblocking (TVC_HM=...,dbk): TComLoopFilter::loopFilterPic (TComLoopFilter.cpp:153) keeps deriving the boundary
+ * strengths on the host; xEdgeFilterLuma (:571) hands every edge unit with bs != 0 to tlibcuda_dbk_unit instead of
+ * filtering it, xEdgeFilterChroma (:680) is skipped (the device derives the chroma edges from the same records), and
+ * tlibcuda_dbk_end runs tvc_deblock_pic on the picture.  TVC_HM=dbkdump leaves the filtering to the reference and writes
+ * the picture before / after together with the records (the golden vectors of tests/golden/deblock_golden.npz). */
+void tlibcuda_dbk_begin(TComPic* pic);
+bool tlibcuda_dbk_unit(TComDataCU* cu, unsigned absZorderIdx, int dir, int edge, unsigned idx, unsigned bs, int qp, TComDataCU* cuP,
+                       unsigned partP, TComDataCU* cuQ, unsigned partQ);
+bool tlibcuda_dbk_skip_chroma();
+void tlibcuda_dbk_end(TComPic* pic, int betaOffsetDiv2, int tcOffsetDiv2);
+
 /* TComTrQuant::xRateDistOptQuant (TComTrQuant.cpp:1719): est is m_pcEstBitsSbac (estBitsSbacStruct == tvc_est_bits) */
 bool tlibcuda_rdoq(TComDataCU* cu, int* src, int* dst, int* arl, unsigned w, unsigned h, unsigned& absSum, int ttype,
                    unsigned absPartIdx, int per, int rem, double lambda, const void* est, bool useArl);

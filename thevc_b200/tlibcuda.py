@@ -324,6 +324,13 @@ class TLibCuda:
         self._ck(self.L.tvc_xDeQuant(self.h, ptr(q), ptr(out), n, n, per, rem))
         return out
 
+    def deblock_pic(self, slot: int, ver: Optional[np.ndarray], hor: Optional[np.ndarray], beta_offset_div2: int = 0,
+                    tc_offset_div2: int = 0):
+        """TComLoopFilter::loopFilterPic on a picture slot, in place; ver / hor: uint8 arrays [units, 4] (bs, qp, flags, 0)"""
+        pv = ptr(np.ascontiguousarray(ver, np.uint8)) if ver is not None else None
+        ph = ptr(np.ascontiguousarray(hor, np.uint8)) if hor is not None else None
+        self._ck(self.L.tvc_deblock_pic(self.h, slot, pv, ph, beta_offset_div2, tc_offset_div2))
+
     def prof_enable(self, on: bool = True):
         self._ck(self.L.tvc_prof_enable(self.h, int(on)))
 
