@@ -411,6 +411,21 @@ typedef struct {
 int tvc_deblock_pic(tvc_ctx* ctx, int slot, const tvc_dbk_unit* ver, const tvc_dbk_unit* hor, int beta_offset_div2,
                     int tc_offset_div2);
 
+/* ---------------------------------------------------------------------------------- sample adaptive offset (apply)
+ * SURVEY.md 8(f)-1, second half.  Replaces the sample work of TComSampleAdaptiveOffset::processSaoUnitAll ->
+ * processSaoCu -> processSaoCuOrg (TComSampleAdaptiveOffset.cpp:781-1003, 1072-1236) for one colour component of a
+ * single-slice picture.  The reference filters in place CTU by CTU and keeps the unfiltered left column / upper row
+ * in line buffers (m_pTmpL1/2, m_pTmpU1/2), i.e. every edge class is taken on the DEBLOCKED picture: here the
+ * deblocked picture is read from src_slot and the result written to dst_slot (a different slot), one thread per
+ * sample.  The SAO decision (offsets, types, merges) stays host work: one record per CTU, merges resolved.        */
+typedef struct {
+  int16_t type;                /* -1 off, 0..3 SAO_EO_0..3 (0 deg, 90 deg, 135 deg, 45 deg), 4 SAO_BO                */
+  int16_t eo[5];               /* m_iOffsetEo[edgeType 0..4] (already << m_uiSaoBitIncrease); eo[2] is 0          */
+  int16_t bo[32];              /* offset of band k = sample >> (bit_depth - 5) (the reference's offset[k + 1])     */
+} tvc_sao_unit;
+/* units: one per CTU in raster order (host array); samples of CTUs with type < 0 are copied                        */
+int tvc_sao_plane(tvc_ctx* ctx, int src_slot, int dst_slot, int plane, const tvc_sao_unit* units);
+
 /* ---------------------------------------------------------------------------------- per-phase device timing
  * CUDA events recorded on the context stream around every kernel group, so that bench.py can report
  * each kernel's duration measured live inside the timed region (not under a profiler).         */

@@ -142,6 +142,7 @@ def lib():
     L.orc_rdoq.restype = None
     L.orc_rdoq_err_scale.argtypes = [ci, ci, ci]; L.orc_rdoq_err_scale.restype = C.c_double
     L.orc_deblock_pic.argtypes = [vp, ci, vp, vp, ci, ci, ci, vp, vp, ci, ci, ci]; L.orc_deblock_pic.restype = None
+    L.orc_sao_plane.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, ci]; L.orc_sao_plane.restype = None
     L.orc_census.argtypes = [vp]; L.orc_census.restype = None
     L.orc_me_frame_ctu.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, cu, ci, ci, ci, ci, ci, vp, vp]
     L.orc_me_frame_ctu.restype = None

@@ -165,6 +165,8 @@ void orc_rdoq(const int32_t* coef, int32_t* qcoef, int32_t* arl, const orc_rdoq_
 typedef struct { uint8_t bs, qp, flags, reserved; } orc_dbk_unit;      /* same layout as tvc_dbk_unit */
 void orc_deblock_pic(Pel* Y, int sy, Pel* U, Pel* V, int sc, int width, int height, const orc_dbk_unit* ver,
                      const orc_dbk_unit* hor, int beta_off2, int tc_off2, int bd);
+typedef struct { int16_t type; int16_t eo[5]; int16_t bo[32]; } orc_sao_unit;      /* same layout as tvc_sao_unit */
+void orc_sao_plane(const Pel* src, Pel* dst, int stride, int w, int h, int ctu, int ctus_x, const orc_sao_unit* units, int bd);
 
 /* ------------------------------------------------------------------ frame-level drivers (hm_oracle_frame.c) */
 #define ORC_CENSUS 593

@@ -109,3 +109,33 @@ void orc_deblock_pic(Pel* Y, int sy, Pel* U, Pel* V, int sc, int width, int heig
         if (u->bs) filter_unit(Y, sy, U, V, sc, ux * 4, uy * 8, 1, u, beta_off2, tc_off2, bd);
       }
 }
+
+/* ------------------------------------------------------------------ SAO apply
+ * TComSampleAdaptiveOffset::processSaoUnitAll / processSaoCuOrg (TComSampleAdaptiveOffset.cpp:781-1003, 1072-1236) for one
+ * colour component of a single-slice picture.  The reference works in place and reads the unfiltered left column / upper
+ * row out of line buffers, the right / lower neighbours are not filtered yet: every edge class is therefore taken on the
+ * deblocked picture, restated here as src -> dst.  Pinned by tests/golden/sao_golden.npz (pictures before / after the
+ * reference's own SAOProcess with the per-CTU records it used). */
+void orc_sao_plane(const Pel* src, Pel* dst, int stride, int w, int h, int ctu, int ctus_x, const orc_sao_unit* units, int bd)
+{
+  const int maxv = (1 << bd) - 1;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      const orc_sao_unit* u = units + (y / ctu) * ctus_x + (x / ctu);
+      const ptrdiff_t o = (ptrdiff_t)y * stride + x;
+      int c = src[o], v = c;
+      if (u->type == 4) v = c + u->bo[c >> (bd - 5)];                           /* SAO_BO :985-996 */
+      else if (u->type >= 0) {
+        /* neighbour pair of the class: EO_0 left/right :846-862, EO_1 up/down :864-887, EO_2 135 deg :889-925, EO_3 45 deg :927-962 */
+        int ax, ay;
+        switch (u->type) { case 0: ax = -1; ay = 0; break; case 1: ax = 0; ay = -1; break; case 2: ax = -1; ay = -1; break; default: ax = -1; ay = 1; break; }
+        int okx = ax == 0 || (x > 0 && x < w - 1), oky = ay == 0 || (y > 0 && y < h - 1);
+        if (okx && oky) {
+          int a = src[o + ax + (ptrdiff_t)ay * stride], b = src[o - ax - (ptrdiff_t)ay * stride];
+          int e = (c > a) - (c < a) + (c > b) - (c < b) + 2;
+          v = c + u->eo[e];
+        }
+      }
+      dst[o] = (Pel)clip3(0, maxv, v);                                           /* m_pClipTable :192-215 */
+    }
+}

@@ -93,7 +93,7 @@ def test_bitstream_md5_identical_to_reference(tmp_path, cfg, frames, extra):
     assert _md5(str(tmp_path / "dec_cuda.yuv")) == _md5(str(tmp_path / "dec.yuv"))
     # C5 as BASELINE.json words it: BATCHED dequant + inverse transform and MC -- inter CUs deferred to one tvc_mc_batch + one
     # tvc_inv_tq_batch per flush (before intra CUs and before the in-loop filters)
-    e = dict(os.environ, TVC_HM="tq,mc,batch,dbk")          # + the deblocking filter on the device
+    e = dict(os.environ, TVC_HM="tq,mc,batch,dbk,sao")      # + deblocking and SAO apply on the device
     db = subprocess.run([DEC_CUDA, "-b", cuda_bin, "-o", str(tmp_path / "dec_batch.yuv")], capture_output=True, text=True, timeout=1500, env=e)
     assert db.returncode == 0, db.stdout[-800:] + db.stderr[-800:]
     assert "ERROR" not in db.stdout and db.stdout.count("(OK)") >= frames
@@ -106,6 +106,9 @@ def test_bitstream_md5_identical_to_reference(tmp_path, cfg, frames, extra):
     dl = [ln for ln in db.stderr.splitlines() if ln.startswith("TLibCuda deblocking:")]
     assert dl and int(dl[-1].split()[2]) >= frames, db.stderr[-500:]
     print("decoder", dl[-1])
+    sl = [ln for ln in db.stderr.splitlines() if ln.startswith("TLibCuda SAO:")]
+    if sl:
+        print("decoder", sl[-1])
 
 
 def test_census_lookup_serves_the_cu_loop(tmp_path):
@@ -120,11 +123,14 @@ def test_census_lookup_serves_the_cu_loop(tmp_path):
     _encode(ENC_REF, "encoder_lowdelay_P_main.cfg", yuv, w, h, frames, ref_bin)
     # + deblocking on the device: the picture digest SEI inside the bitstream hashes the final reconstruction, so an equal
     # bitstream md5 also proves the device-filtered pictures equal the reference's
-    r = _encode(ENC_CUDA, "encoder_lowdelay_P_main.cfg", yuv, w, h, frames, cuda_bin, env={"TVC_HM": "me,frac,tables,dbk"})
+    r = _encode(ENC_CUDA, "encoder_lowdelay_P_main.cfg", yuv, w, h, frames, cuda_bin, env={"TVC_HM": "me,frac,tables,dbk,sao"})
     assert _md5(cuda_bin) == _md5(ref_bin)
     dl = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda deblocking:")]
     assert dl and int(dl[-1].split()[2]) == frames, r.stderr[-600:]
     print(dl[-1])
+    sl = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda SAO:")]
+    assert sl and int(sl[-1].split()[2]) >= frames, r.stderr[-600:]
+    print(sl[-1])
     line = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda look-up:")]
     assert line, r.stderr[-600:]
     print(line[-1])

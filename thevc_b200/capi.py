@@ -162,6 +162,7 @@ SIGNATURES = {
     "tvc_xIT": (ci, [vp, ci, vp, vp, ci, ci, ci]),
     "tvc_xDeQuant": (ci, [vp, vp, vp, ci, ci, ci, ci]),
     "tvc_deblock_pic": (ci, [vp, ci, vp, vp, ci, ci]),
+    "tvc_sao_plane": (ci, [vp, ci, ci, ci, vp]),
     "tvc_prof_enable": (ci, [vp, ci]),
     "tvc_prof_read": (ci, [vp, vp, vp, ci]),
     "tvc_ubench": (ci, [vp, ci, C.POINTER(C.c_double)]),

@@ -135,9 +135,60 @@ k_deblock(int16_t* __restrict__ Y, int sy, int16_t* __restrict__ U, int16_t* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------- SAO apply
+// processSaoCuOrg (TComSampleAdaptiveOffset.cpp:781-1003) as a pure function of the deblocked picture: one thread per
+// sample, the CTU's record read through the read-only cache.  Picture-border samples keep their value for the classes
+// whose neighbour would lie outside (iStartX / iEndX / iStartY / iEndY, :848-849, 866-867, 891-895, 929-933).
+__global__ void __launch_bounds__(256)
+k_sao_plane(const int16_t* __restrict__ src, int16_t* __restrict__ dst, int stride, int w, int h, int ctu, int ctus_x,
+            const tvc_sao_unit* __restrict__ units, int bd)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const tvc_sao_unit* u = units + (y / ctu) * ctus_x + (x / ctu);
+  const ptrdiff_t o = (ptrdiff_t)y * stride + x;
+  const int c = src[o];
+  const int type = u->type;
+  int v = c;
+  if (type == 4) {
+    v = c + u->bo[c >> (bd - 5)];
+  } else if (type >= 0) {
+    const int dx = type == 1 ? 0 : 1;                        // neighbour a = (x - dx, y - dy), b = (x + dx, y + dy)
+    const int dy = type == 0 ? 0 : (type == 3 ? -1 : 1);     // 45 deg: a = (x - 1, y + 1), b = (x + 1, y - 1)
+    const bool ok = (dx == 0 || (x > 0 && x < w - 1)) && (dy == 0 || (y > 0 && y < h - 1));
+    if (ok) {
+      const int a = src[o - dx - (ptrdiff_t)dy * stride], b = src[o + dx + (ptrdiff_t)dy * stride];
+      const int e = (c > a) - (c < a) + (c > b) - (c < b) + 2;
+      v = c + u->eo[e];
+    }
+  }
+  const int maxv = (1 << bd) - 1;
+  dst[o] = (int16_t)(v < 0 ? 0 : (v > maxv ? maxv : v));
+}
+
 }  // namespace tvc
 
 using namespace tvc;
+
+extern "C" int tvc_sao_plane(tvc_ctx* c, int src_slot, int dst_slot, int plane, const tvc_sao_unit* units)
+{
+  if (!c || !valid_slot(c, src_slot) || !valid_slot(c, dst_slot) || src_slot == dst_slot || plane < 0 || plane > 2 || !units)
+    return set_err(c, TVC_ERR_ARG, "tvc_sao_plane: bad argument (source and destination must be different slots)");
+  const Pic& s = c->pics[src_slot];
+  const Pic& d = c->pics[dst_slot];
+  const int n = c->num_ctus_x * c->num_ctus_y;
+  int r;
+  if ((r = ensure_scratch(c, c->in, (size_t)n * sizeof(tvc_sao_unit)))) return r;
+  memcpy(c->in.host, units, (size_t)n * sizeof(tvc_sao_unit));
+  TVC_CUDA(c, cudaMemcpyAsync(c->in.dev, c->in.host, (size_t)n * sizeof(tvc_sao_unit), cudaMemcpyHostToDevice, c->stream));
+  const int w = s.w[plane], h = s.h[plane], ctu = c->cfg.max_cu >> (plane ? 1 : 0);
+  dim3 blk(64, 4), grd((w + 63) / 64, (h + 3) / 4);
+  ProfScope ps(c, TVC_PH_DEBLOCK);
+  k_sao_plane<<<grd, blk, 0, c->stream>>>(s.org[plane], d.org[plane], s.stride[plane], w, h, ctu, c->num_ctus_x, (const tvc_sao_unit*)c->in.dev,
+                                         c->cfg.bit_depth);
+  TVC_LAUNCH_CHECK(c);
+  return TVC_OK;
+}
 
 extern "C" int tvc_deblock_pic(tvc_ctx* c, int slot, const tvc_dbk_unit* ver, const tvc_dbk_unit* hor, int beta_offset_div2, int tc_offset_div2)
 {

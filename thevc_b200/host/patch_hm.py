@@ -96,6 +96,16 @@ def main():
     s = sub_once(s, r'(Void TComLoopFilter::xEdgeFilterChroma\( TComDataCU\* pcCU, UInt uiAbsZorderIdx, UInt uiDepth, Int iDir, Int iEdge \)\r?\n\{\r?\n)',
                  r'\1  if ( tlibcuda_dbk_skip_chroma() ) return;\n', "xEdgeFilterChroma")
     wr(os.path.join(out, "TLibCommon", "TComLoopFilter.cpp"), s)
+    # ---- TComSampleAdaptiveOffset.cpp: the SAO sample work (encoder and decoder)
+    s = rd(os.path.join(lib, "TLibCommon", "TComSampleAdaptiveOffset.cpp"))
+    s = sub_once(s, r'(#include "TComSampleAdaptiveOffset.h"\r?\n)', r'\1#include "tlibcuda_hm.h"\n', "TComSampleAdaptiveOffset include")
+    s = sub_once(s, r'(  memcpy\(m_pTmpU1, pRec, sizeof\(Pel\)\*picWidthTmp\);\r?\n)',
+                 r'  tlibcuda_sao_begin( m_pcPic, yCbCr, m_bUseNIF );\n\1', "processSaoUnitAll begin")
+    s = sub_once(s, r'(        )(processSaoCu\(addr, typeIdx, yCbCr\);\r?\n)',
+                 r'\1if ( !tlibcuda_sao_unit( addr, typeIdx, m_iOffsetEo, offset ) ) \2', "processSaoUnitAll unit")
+    s = sub_once(s, r'(    tmpUSwap = m_pTmpU1;\r?\n    m_pTmpU1 = m_pTmpU2;\r?\n    m_pTmpU2 = tmpUSwap;\r?\n  \}\r?\n)',
+                 r'\1  tlibcuda_sao_end( m_pcPic, yCbCr );\n', "processSaoUnitAll end")
+    wr(os.path.join(out, "TLibCommon", "TComSampleAdaptiveOffset.cpp"), s)
     # ---- TComPrediction.cpp: xPredInterUni (shared by encoder and decoder)
     s = rd(os.path.join(lib, "TLibCommon", "TComPrediction.cpp"))
     s = sub_once(s, r'(#include "TComPrediction.h"\r?\n)', r'\1#include "tlibcuda_hm.h"\n', "TComPrediction include")
@@ -103,7 +113,7 @@ def main():
                  r'\1  if ( tlibcuda_pred_inter_uni( pcCU, pcCU->getSlice()->getRefPic( eRefPicList, iRefIdx ), uiPartAddr, cMv.getHor(), cMv.getVer(), iWidth, iHeight, rpcYuvPred, bi ) ) return;\n',
                  "xPredInterUni", flags=re.S)
     wr(os.path.join(out, "TLibCommon", "TComPrediction.cpp"), s)
-    print("patched 8 files into", out)
+    print("patched 9 files into", out)
 
 
 if __name__ == "__main__":

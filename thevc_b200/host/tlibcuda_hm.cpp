@@ -26,6 +26,7 @@
 #include "TLibCommon/TComSlice.h"
 #include "TLibCommon/TComMv.h"
 #include "TLibCommon/TComYuv.h"
+#include "TLibCommon/TComSampleAdaptiveOffset.h"
 #include "TLibEncoder/TEncCfg.h"
 
 #include "tlibcuda_hm.h"
@@ -88,9 +89,21 @@ struct Dbk {
   double seconds = 0.0;
 };
 
+// SAO apply: the per-CTU records of the component being filtered
+struct Sao {
+  bool on = false, dump = false, active = false;
+  int comp = 0, w = 0, h = 0;
+  std::vector<tvc_sao_unit> units;
+  std::vector<short> before;
+  int dumped = 0;
+  unsigned long long n_planes = 0;
+  double seconds = 0.0;
+};
+
 struct State {
   tvc_ctx* h = nullptr;
   bool on_lookup = true, verify = false;
+  Sao sao;
   Dbk dbk;
   DecBatch dec;
   std::map<long long, Group> groups;       // key = ctu * 64 + device slot of the reference; cleared per picture
@@ -135,6 +148,8 @@ void report()
   if (s.dbk.on && s.dbk.n_pics)
     fprintf(stderr, "TLibCuda deblocking: %llu pictures, %llu edge units filtered on the device, %.3f s (upload + 2 kernels + download)\n",
             s.dbk.n_pics, s.dbk.n_units, s.dbk.seconds);
+  if (s.sao.on && s.sao.n_planes)
+    fprintf(stderr, "TLibCuda SAO: %llu planes filtered on the device, %.3f s (upload + kernel + download)\n", s.sao.n_planes, s.sao.seconds);
   if (s.h && s.dec.on)
     fprintf(stderr, "TLibCuda picture batch: %llu inter CUs (%llu PUs, %llu TUs) reconstructed in %llu device batches, %.3f s in the batches\n",
             s.dec.n_cus, s.dec.n_pus, s.dec.n_tus, s.dec.n_flush, s.dec.seconds);
@@ -195,6 +210,8 @@ void parse_env()
   s.on_lookup = strstr(e, "nolookup") == nullptr;
   s.verify = strstr(e, "verify") != nullptr;
   s.dec.on = strstr(e, "batch") != nullptr;
+  s.sao.dump = strstr(e, "saodump") != nullptr;
+  s.sao.on = !s.sao.dump && strstr(e, "sao") != nullptr;
   s.dbk.dump = strstr(e, "dbkdump") != nullptr;
   s.dbk.on = !s.dbk.dump && strstr(e, "dbk") != nullptr;
   if (strstr(e, "stats")) { PS().on = true; s.on_me = s.on_frac = s.on_tq = s.on_rdoq = s.on_mc = s.on_tables = false; atexit(stats_report); }
@@ -214,7 +231,7 @@ void ensure_ctx(int w, int ht)
   State& s = S();
   if (s.disabled || (s.h && s.w >= w && s.ht >= ht)) return;
   init_once();
-  if (!s.on_me && !s.on_frac && !s.on_tq && !s.on_rdoq && !s.on_mc && !s.dbk.on) { s.disabled = true; return; }     // TVC_HM=none: the unmodified path
+  if (!s.on_me && !s.on_frac && !s.on_tq && !s.on_rdoq && !s.on_mc && !s.dbk.on && !s.sao.on) { s.disabled = true; return; }     // TVC_HM=none: the unmodified path
   if (s.h) {                  // the decoder learns the picture size after its first transforms: start over with the real size
     tvc_ctx_destroy(s.h);
     s.h = nullptr;
@@ -712,5 +729,79 @@ void tlibcuda_dbk_end(TComPic* pic, int betaOffsetDiv2, int tcOffsetDiv2)
     const short* src = pl == 0 ? rec->getLumaAddr() : (pl == 1 ? rec->getCbAddr() : rec->getCrAddr());
     for (int r = 0; r < h; r++) fwrite(src + (ptrdiff_t)r * st, sizeof(short), (size_t)w, f);
   }
+  fclose(f);
+}
+
+// ---------------------------------------------------------------------------------------------- SAO apply
+static short* plane_of(TComPicYuv* rec, int comp) { return comp == 0 ? rec->getLumaAddr() : (comp == 1 ? rec->getCbAddr() : rec->getCrAddr()); }
+
+void tlibcuda_sao_begin(TComPic* pic, int yCbCr, bool useNIF)
+{
+  init_once();
+  State& s = S();
+  Sao& a = s.sao;
+  a.active = false;
+  if ((!a.on && !a.dump) || useNIF) return;
+  TComPicYuv* rec = pic->getPicYuvRec();
+  if (a.on) { ensure_ctx(rec->getWidth(), rec->getHeight()); if (!s.h) return; }
+  a.comp = yCbCr;
+  a.w = rec->getWidth() >> (yCbCr ? 1 : 0); a.h = rec->getHeight() >> (yCbCr ? 1 : 0);
+  tvc_sao_unit off;
+  memset(&off, 0, sizeof(off));
+  off.type = -1;
+  a.units.assign((size_t)pic->getNumCUsInFrame(), off);
+  a.active = true;
+  if (a.dump) {
+    const int st = yCbCr ? rec->getCStride() : rec->getStride();
+    a.before.resize((size_t)a.w * a.h);
+    for (int r = 0; r < a.h; r++) memcpy(&a.before[(size_t)r * a.w], plane_of(rec, yCbCr) + (ptrdiff_t)r * st, (size_t)a.w * sizeof(short));
+  }
+}
+
+bool tlibcuda_sao_unit(int addr, int typeIdx, const int* offsetEo, const int* offsetBands)
+{
+  Sao& a = S().sao;
+  if (!a.active) return false;
+  tvc_sao_unit& u = a.units[addr];
+  memset(&u, 0, sizeof(u));
+  u.type = (int16_t)typeIdx;
+  if (typeIdx == SAO_BO) for (int k = 0; k < 32; k++) u.bo[k] = (int16_t)offsetBands[k + 1];
+  else for (int k = 0; k < 5; k++) u.eo[k] = (int16_t)offsetEo[k];
+  return a.on;
+}
+
+void tlibcuda_sao_end(TComPic* pic, int yCbCr)
+{
+  State& s = S();
+  Sao& a = s.sao;
+  if (!a.active) return;
+  a.active = false;
+  TComPicYuv* rec = pic->getPicYuvRec();
+  const int st = yCbCr ? rec->getCStride() : rec->getStride();
+  if (a.on) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const int src = (int)s.slots.size() - 1, dst = (int)s.slots.size() - 2;     // the two reserved slots
+    if (yCbCr == 0)     // the chroma planes are still unfiltered when the luma pass runs: one upload serves all three components
+      CK(tvc_pic_upload(s.h, src, rec->getLumaAddr(), rec->getStride(), rec->getCbAddr(), rec->getCrAddr(), rec->getCStride(), 0));
+    CK(tvc_sao_plane(s.h, src, dst, yCbCr, a.units.data()));
+    CK(tvc_pic_download(s.h, dst, yCbCr == 0 ? rec->getLumaAddr() : nullptr, rec->getStride(), yCbCr == 1 ? rec->getCbAddr() : nullptr,
+                        yCbCr == 2 ? rec->getCrAddr() : nullptr, rec->getCStride(), 0));
+    a.n_planes++;
+    a.seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return;
+  }
+  const char* dir = getenv("TVC_SAO_DUMP");
+  const int limit = getenv("TVC_SAO_DUMP_PLANES") ? atoi(getenv("TVC_SAO_DUMP_PLANES")) : 6;
+  if (!dir || a.dumped >= limit) return;
+  char name[512];
+  snprintf(name, sizeof(name), "%s/sao_%02d.bin", dir, a.dumped++);
+  FILE* f = fopen(name, "wb");
+  if (!f) return;
+  const int hdr[8] = {a.w, a.h, (int)(g_uiBitDepth + g_uiBitIncrement), yCbCr, (int)g_uiMaxCUWidth >> (yCbCr ? 1 : 0), (int)pic->getFrameWidthInCU(),
+                      (int)a.units.size(), pic->getPOC()};
+  fwrite(hdr, sizeof(int), 8, f);
+  fwrite(a.units.data(), sizeof(tvc_sao_unit), a.units.size(), f);
+  fwrite(a.before.data(), sizeof(short), a.before.size(), f);
+  for (int r = 0; r < a.h; r++) fwrite(plane_of(rec, yCbCr) + (ptrdiff_t)r * st, sizeof(short), (size_t)a.w, f);
   fclose(f);
 }

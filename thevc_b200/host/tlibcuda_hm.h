@@ -66,6 +66,14 @@ bool tlibcuda_dbk_unit(TComDataCU* cu, unsigned absZorderIdx, int dir, int edge,
 bool tlibcuda_dbk_skip_chroma();
 void tlibcuda_dbk_end(TComPic* pic, int betaOffsetDiv2, int tcOffsetDiv2);
 
+/* ---- SAO apply (TVC_HM=...,sao): TComSampleAdaptiveOffset::processSaoUnitAll (TComSampleAdaptiveOffset.cpp:1072) keeps
+ * walking the CTUs and resolving merges; instead of processSaoCu every CTU's type and offset tables are recorded, and
+ * tlibcuda_sao_end runs tvc_sao_plane for the component.  Single-slice pictures only (m_bUseNIF == false), otherwise the
+ * reference code runs.  TVC_HM=saodump: the reference filters, planes before / after + records are written. */
+void tlibcuda_sao_begin(TComPic* pic, int yCbCr, bool useNIF);
+bool tlibcuda_sao_unit(int addr, int typeIdx, const int* offsetEo, const int* offsetBands);
+void tlibcuda_sao_end(TComPic* pic, int yCbCr);
+
 /* TComTrQuant::xRateDistOptQuant (TComTrQuant.cpp:1719): est is m_pcEstBitsSbac (estBitsSbacStruct == tvc_est_bits) */
 bool tlibcuda_rdoq(TComDataCU* cu, int* src, int* dst, int* arl, unsigned w, unsigned h, unsigned& absSum, int ttype,
                    unsigned absPartIdx, int per, int rem, double lambda, const void* est, bool useArl);

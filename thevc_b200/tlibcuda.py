@@ -331,6 +331,12 @@ class TLibCuda:
         ph = ptr(np.ascontiguousarray(hor, np.uint8)) if hor is not None else None
         self._ck(self.L.tvc_deblock_pic(self.h, slot, pv, ph, beta_offset_div2, tc_offset_div2))
 
+    def sao_plane(self, src_slot: int, dst_slot: int, plane: int, units: np.ndarray):
+        """SAO apply of one component; units: int16 [num_ctus, 38] = (type, eo[5], bo[32]) per CTU"""
+        units = np.ascontiguousarray(units, np.int16)
+        assert units.shape == (self.ctus_x * self.ctus_y, 38)
+        self._ck(self.L.tvc_sao_plane(self.h, src_slot, dst_slot, plane, ptr(units)))
+
     def prof_enable(self, on: bool = True):
         self._ck(self.L.tvc_prof_enable(self.h, int(on)))
 
