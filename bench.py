@@ -15,9 +15,9 @@ pictures (cfg/encoder_lowdelay_P_main.cfg: SR 64, FEN 1, HadamardME 1, AMP 1, 8-
   5. dequant + inverse transform + reconstruction for the same TUs.
 
 `value`  = frames/s with every input resident in HBM (device-pointer ABI entry points).
-`e2e`    = the same through the host-pointer C ABI: pictures, TU/PU lists and levels are copied
-           host->device from pinned memory and ME results, levels and the reconstruction are copied back,
-           all inside the timed region.
+`e2e`    = the same through the host-pointer C ABI: the new pictures (current original + newest reference
+           reconstruction) and the PU / TU lists are copied host->device from pinned memory and the ME
+           results, levels and the reconstruction are copied back, all inside the timed region.
 `--impl reference` times the CPU restatement of the same reference functions (oracle/, all host cores)
 on a bounded sample of CTUs of the same workload.
 
@@ -544,18 +544,20 @@ def gpu_arm(args):
     recon_h = type(wl.pics[0])(W, H, alloc=wl.alloc)
 
     def step_e2e():
-        for s, p in enumerate(wl.pics):
-            t.upload(s, p)
+        # per-picture input traffic of a low-delay encoder: the new original and the newest reconstruction (the three older
+        # references were uploaded when they were the newest)
+        t.upload(0, wl.pics[0])
+        t.upload(1, wl.pics[1])
         ck(L.tvc_me_frame(h, SLOT_CUR, NUM_REFS, refs, ptr(pred), C.byref(mcfg), ptr(ires_h), ptr(fres_h)))
         ck(L.tvc_mc_batch(h, SLOT_PRED, n_pu, ptr(wl.pus)))
         for pl, pw, ph in planes_wh:
             ck(L.tvc_pic_subtract(h, SLOT_RESI, SLOT_CUR, SLOT_PRED, pl, 0, 0, pw, ph))
-        ck(L.tvc_fwd_rdoq_batch(h, SLOT_RESI, n_tu, ptr(wl.tus), ptr(wl.rtus), 1, ptr(wl.est_bytes), C.byref(qc), ptr(levels_h), None,
-                                wl.coef_elems, ptr(abs_h)))
-        ck(L.tvc_inv_tq_batch(h, SLOT_RESI2, SLOT_PRED, SLOT_RECON, n_tu, ptr(wl.tus), ptr(levels_h), wl.coef_elems))
+        # transform + RDOQ, levels / uiAbsSum to the host, dequant + inverse + reconstruction from the device copy of the levels
+        ck(L.tvc_fwd_rdoq_recon_batch(h, SLOT_RESI, SLOT_RESI2, SLOT_PRED, SLOT_RECON, n_tu, ptr(wl.tus), ptr(wl.rtus), 1, ptr(wl.est_bytes),
+                                      C.byref(qc), ptr(levels_h), wl.coef_elems, ptr(abs_h)))
         t.download(SLOT_RECON, into=recon_h)
 
-    h2d = (NUM_REFS + 1) * wl.pic_bytes() + wl.pred.nbytes + wl.pus.nbytes + 2 * wl.tus.nbytes + wl.rtus.nbytes + wl.est_bytes.nbytes + levels_h.nbytes
+    h2d = 2 * wl.pic_bytes() + wl.pred.nbytes + wl.pus.nbytes + wl.tus.nbytes + wl.rtus.nbytes + wl.est_bytes.nbytes
     d2h = ires_h.nbytes + fres_h.nbytes + levels_h.nbytes + abs_h.nbytes + wl.pic_bytes()
 
     def barrier():

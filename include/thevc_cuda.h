@@ -385,6 +385,13 @@ int tvc_fwd_transform_batch_dev(tvc_ctx* ctx, int resi_slot, int n, const tvc_tu
 int tvc_fwd_rdoq_batch(tvc_ctx* ctx, int resi_slot, int n, const tvc_tu* tus, const tvc_rdoq_tu* rdoq_tus, int n_est,
                        const tvc_est_bits* est, const tvc_quant_cfg* qc, int32_t* levels, int32_t* arl, size_t coef_elems,
                        uint32_t* abs_sum);
+/* the whole residual round trip of a TU list in one call: transformNxN with RDOQ on, then invtransformNxN of the same levels
+ * and the reconstruction (what TEncSearch::xEstimateResidualQT / xEncodeResidualQT do per TU, batched): the levels and
+ * uiAbsSum go to the host (CABAC needs them), the inverse path reads the levels where RDOQ left them on the device.
+ * inv_resi_slot receives the reconstructed residual, recon_slot = Clip(pred_slot + residual).                     */
+int tvc_fwd_rdoq_recon_batch(tvc_ctx* ctx, int resi_slot, int inv_resi_slot, int pred_slot, int recon_slot, int n, const tvc_tu* tus,
+                             const tvc_rdoq_tu* rdoq_tus, int n_est, const tvc_est_bits* est, const tvc_quant_cfg* qc, int32_t* levels,
+                             size_t coef_elems, uint32_t* abs_sum);
 /* drop-in for one xRateDistOptQuant call on host blocks (w x w, raster)                          */
 int tvc_xRateDistOptQuant(tvc_ctx* ctx, const int32_t* coef, int32_t* qcoef, int32_t* arl, int w, int is_luma,
                           int scan_idx, int qp_per, int qp_rem, int cbf_ctx, int sign_hide, int use_arl,

@@ -208,3 +208,54 @@ def test_fwd_rdoq_batch_on_picture(orc, bd):
         assert np.count_nonzero(elev) > 2000
     finally:
         t.close()
+
+
+def test_fwd_rdoq_recon_round_trip(orc):
+    """tvc_fwd_rdoq_recon_batch == tvc_fwd_rdoq_batch followed by tvc_inv_tq_batch on the returned levels"""
+    from thevc_b200.capi import TU
+    from thevc_b200.tlibcuda import HostPic
+    rng = np.random.default_rng(3)
+    W, H, bd = 416, 240, 8
+    t = TLibCuda(W, H, bd, num_slots=6)
+    try:
+        resi, pred = HostPic(W, H), HostPic(W, H)
+        for pl in range(3):
+            resi.plane(pl)[:] = np.clip(np.rint(rng.laplace(0, 20, resi.plane(pl).shape)), -255, 255).astype(np.int16)
+            pred.plane(pl)[:] = rng.integers(0, 256, pred.plane(pl).shape).astype(np.int16)
+        t.upload(0, resi); t.upload(1, pred)
+        est = rc.make_est(rng)
+        tus, rtus = [], []
+        off = 0
+        for log2 in (2, 3, 4, 5):
+            n = 1 << log2
+            for pl in (0, 1, 2):
+                if pl and log2 == 5:
+                    continue
+                pw, ph = (W, H) if pl == 0 else (W // 2, H // 2)
+                for y in range(0, ph - n + 1, 2 * n):
+                    for x in range(0, pw - n + 1, 2 * n):
+                        tus.append(TU(pl, x, y, log2, 0, 0, 5, 2, 5, off))
+                        rtus.append(RdoqTU(log2, int(pl == 0), 0, 5, 2, -1 if pl == 0 else 5, 0, off, 40.0))
+                        off += n * n
+        qc = QuantCfg(0, 1, 0)
+        lev, _, sums = t.fwd_rdoq_batch(0, tus, rtus, [_to_abi_est(est)], qc, off)
+        t.inv_tq_batch(2, 1, 3, tus, lev)
+        a_resi, a_rec = t.download(2, with_margin=False), t.download(3, with_margin=False)
+        lev2 = np.zeros(off, np.int32); sums2 = np.zeros(len(tus), np.uint32)
+        from thevc_b200.tlibcuda import _arr
+        from thevc_b200.capi import ptr
+        ta, ra = _arr(TU, tus), _arr(RdoqTU, rtus)
+        e = _to_abi_est(est)
+        rcode = t.L.tvc_fwd_rdoq_recon_batch(t.h, 0, 4, 1, 5, len(tus), C.cast(ta, C.c_void_p), C.cast(ra, C.c_void_p), 1, C.byref(e), C.byref(qc),
+                                             ptr(lev2), off, ptr(sums2))
+        assert rcode == 0, t.L.tvc_last_error(t.h)
+        b_resi, b_rec = t.download(4, with_margin=False), t.download(5, with_margin=False)
+        assert np.array_equal(lev, lev2) and np.array_equal(sums, sums2)
+        for tu in tus:
+            n = 1 << tu.log2_size
+            for a, b in ((a_resi, b_resi), (a_rec, b_rec)):
+                pa, pb = (a.y, a.u, a.v)[tu.plane], (b.y, b.u, b.v)[tu.plane]
+                assert np.array_equal(pa[tu.y:tu.y + n, tu.x:tu.x + n], pb[tu.y:tu.y + n, tu.x:tu.x + n])
+        assert np.count_nonzero(lev) > 1000
+    finally:
+        t.close()

@@ -157,6 +157,7 @@ SIGNATURES = {
     "tvc_rdoq_batch_dev": (ci, [vp, ci, vp, ci, vp, C.POINTER(QuantCfg), vp, vp, vp, C.c_size_t, vp]),
     "tvc_fwd_transform_batch_dev": (ci, [vp, ci, ci, vp, vp, vp]),
     "tvc_fwd_rdoq_batch": (ci, [vp, ci, ci, vp, vp, ci, vp, C.POINTER(QuantCfg), vp, vp, C.c_size_t, vp]),
+    "tvc_fwd_rdoq_recon_batch": (ci, [vp, ci, ci, ci, ci, ci, vp, vp, ci, vp, C.POINTER(QuantCfg), vp, C.c_size_t, vp]),
     "tvc_xRateDistOptQuant": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, C.c_double, vp, C.POINTER(u32)]),
     "tvc_xT": (ci, [vp, ci, vp, ci, vp, ci, ci]),
     "tvc_xIT": (ci, [vp, ci, vp, vp, ci, ci, ci]),

@@ -142,6 +142,9 @@ struct ScanTables { const uint16_t* s[3][4]; };
 int ensure_scans(tvc_ctx* c, ScanTables& st);          // tvc_tq.cu
 // range-checks a host TU list (grouped by ascending log2_size) and counts TUs per size
 int validate_tus(tvc_ctx* c, int plane_slot, int n, const tvc_tu* tus, size_t coef_elems, int counts[4]);   // tvc_tq.cu
+// dequant (optional) + inverse transform of a device TU list, one launch per size; recon = Clip(pred + resi) when pred_slot >= 0
+int launch_inv(tvc_ctx* c, int resi_slot, int pred_slot, int recon_slot, const int counts[4], const tvc_tu* tus_dev,
+               const int32_t* levels_dev, int dequant);                                                          // tvc_tq.cu
 
 // ---- table layout of the ME pre-pass (shared by producer and consumers) ----------------------
 // T[ref][ctu][cand 129*129][by 16][q 4][par 2][bx 4] uint16: one candidate = 1 KB contiguous

@@ -569,8 +569,28 @@ int tvc_rdoq_batch(tvc_ctx* c, int n, const tvc_rdoq_tu* tus, int n_est, const t
   return TVC_OK;
 }
 
+static int fwd_rdoq_host(tvc_ctx* c, int resi_slot, int n, const tvc_tu* tus, const tvc_rdoq_tu* rtus, int n_est, const tvc_est_bits* est,
+                         const tvc_quant_cfg* qc, int32_t* levels, int32_t* arl, size_t coef_elems, uint32_t* abs_sum, int inv_resi_slot,
+                         int pred_slot, int recon_slot);
+
 int tvc_fwd_rdoq_batch(tvc_ctx* c, int resi_slot, int n, const tvc_tu* tus, const tvc_rdoq_tu* rtus, int n_est, const tvc_est_bits* est,
                        const tvc_quant_cfg* qc, int32_t* levels, int32_t* arl, size_t coef_elems, uint32_t* abs_sum)
+{
+  return fwd_rdoq_host(c, resi_slot, n, tus, rtus, n_est, est, qc, levels, arl, coef_elems, abs_sum, -1, -1, -1);
+}
+
+int tvc_fwd_rdoq_recon_batch(tvc_ctx* c, int resi_slot, int inv_resi_slot, int pred_slot, int recon_slot, int n, const tvc_tu* tus,
+                             const tvc_rdoq_tu* rtus, int n_est, const tvc_est_bits* est, const tvc_quant_cfg* qc, int32_t* levels,
+                             size_t coef_elems, uint32_t* abs_sum)
+{
+  if (!c || !valid_slot(c, inv_resi_slot) || !valid_slot(c, pred_slot) || !valid_slot(c, recon_slot))
+    return set_err(c, TVC_ERR_ARG, "tvc_fwd_rdoq_recon_batch: bad slot");
+  return fwd_rdoq_host(c, resi_slot, n, tus, rtus, n_est, est, qc, levels, nullptr, coef_elems, abs_sum, inv_resi_slot, pred_slot, recon_slot);
+}
+
+static int fwd_rdoq_host(tvc_ctx* c, int resi_slot, int n, const tvc_tu* tus, const tvc_rdoq_tu* rtus, int n_est, const tvc_est_bits* est,
+                         const tvc_quant_cfg* qc, int32_t* levels, int32_t* arl, size_t coef_elems, uint32_t* abs_sum, int inv_resi_slot,
+                         int pred_slot, int recon_slot)
 {
   if (!c || !valid_slot(c, resi_slot) || n < 0 || !qc || (n && (!tus || !rtus || !est || !levels || n_est < 1)) || (qc && qc->use_arl && n && !arl))
     return set_err(c, TVC_ERR_ARG, "tvc_fwd_rdoq_batch: bad argument");
@@ -600,6 +620,8 @@ int tvc_fwd_rdoq_batch(tvc_ctx* c, int resi_slot, int n, const tvc_tu* tus, cons
   if ((r = launch_rdoq(c, n, (const tvc_rdoq_tu*)(di + tu_b), (const tvc_est_bits*)(di + tu_b + rtu_b), *qc, d_coef, (int32_t*)dout,
                        (int32_t*)(dout + coef_b + abs_b), coef_elems, (uint32_t*)(dout + coef_b))))
     return r;
+  // round trip: dequant + inverse transform + reconstruction from the levels where they are
+  if (inv_resi_slot >= 0 && (r = launch_inv(c, inv_resi_slot, pred_slot, recon_slot, counts, (const tvc_tu*)di, (const int32_t*)dout, 1))) return r;
   const bool pin_out = is_pinned(levels) && (!want_arl || is_pinned(arl)) && (!abs_sum || is_pinned(abs_sum));
   if (pin_out) {
     TVC_CUDA(c, cudaMemcpyAsync(levels, dout, coef_elems * 4, cudaMemcpyDeviceToHost, c->stream));

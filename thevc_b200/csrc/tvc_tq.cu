@@ -443,8 +443,8 @@ static int launch_fwd(tvc_ctx* c, int resi_slot, const int counts[4], const tvc_
   return TVC_OK;
 }
 
-static int launch_inv(tvc_ctx* c, int resi_slot, int pred_slot, int recon_slot, const int counts[4], const tvc_tu* tus_dev,
-                      const int32_t* levels_dev, int dequant)
+int launch_inv(tvc_ctx* c, int resi_slot, int pred_slot, int recon_slot, const int counts[4], const tvc_tu* tus_dev,
+               const int32_t* levels_dev, int dequant)
 {
   int off = 0, bd = c->cfg.bit_depth;
   ProfScope ps(c, TVC_PH_INV_TQ);
