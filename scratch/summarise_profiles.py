@@ -69,6 +69,9 @@ def main():
     traffic_path = os.path.join(out, "traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
     per_phase = collections.defaultdict(lambda: [0, 0.0, 0.0])
+    issue = collections.defaultdict(list)
+    BOUND = {"me_tables": "hbm write", "me_raster": "shared-memory scans", "me_search": "latency (L2/HBM reads, 125 registers -> 16 warps/SM)",
+             "me_frac": "integer pipe (issue slots)", "rdoq": "latency (dependent FP64 chain)", "mc": "hbm", "fwd_tq": "hbm", "inv_tq": "hbm"}
     with open(os.path.join(out, tag + "_kernels_full.txt"), "w") as f:
         f.write("ncu --set full --clock-control none --import-source on: %s\n(one launch per kernel; under the profiler -- not a bench value)\n\n" % cmd)
         for row in rows:
@@ -89,9 +92,13 @@ def main():
                     return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
                 b = to_bytes(*vals["dram__bytes_read.sum"]) + to_bytes(*vals["dram__bytes_write.sum"])
                 per_phase[ph][0] += 1; per_phase[ph][1] += b
+                if "smsp__issue_active.avg.pct_of_peak_sustained_active" in vals:
+                    issue[ph].append(float(vals["smsp__issue_active.avg.pct_of_peak_sustained_active"][0].replace(",", "")))
     for ph, (c, b, _) in per_phase.items():
         e = traffic.get(ph) if isinstance(traffic.get(ph), dict) else {}
-        e.update({"dram_bytes_per_launch": b / c, "launches_in_capture": c, "capture": tag})
+        e.update({"dram_bytes_per_launch": b / c, "launches_in_capture": c, "capture": tag, "bound": BOUND.get(ph)})
+        if issue[ph]:
+            e["issue_slots_busy_pct"] = [round(v, 1) for v in issue[ph]]
         traffic[ph] = e
     json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
     print("wrote profiles/%s_* and traffic.json" % tag)
