@@ -202,6 +202,9 @@ def ref():
     R.ref_int_search.argtypes = [ci, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, C.c_double, ci, ci, ci, ci, ip]
     R.ref_int_search.restype = None
     R.ref_frac_search.argtypes = [vp, ci, vp, ci, ci, ci, ci, ci, C.c_double, ci, ci, ip]; R.ref_frac_search.restype = None
+    if hasattr(R, "ref_me_frame_ctu"):
+        R.ref_me_frame_ctu.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, C.c_double, ci, vp, vp, vp]
+        R.ref_me_frame_ctu.restype = None
     R.ref_mc_set_ref.argtypes = [vp, vp, vp, ci, ci]; R.ref_mc_set_ref.restype = None
     R.ref_mc_pu.argtypes = [ci, ci, ci, ci, ci, ci, ci, vp, vp, vp]; R.ref_mc_pu.restype = None
     R.ref_add_avg.argtypes = [vp] * 6 + [ci, ci] + [vp] * 3; R.ref_add_avg.restype = None

@@ -408,6 +408,36 @@ void ref_frac_search(short* org, int so, short* ref, int rs, int w, int h, int i
   out5[0] = half.getHor(); out5[1] = half.getVer(); out5[2] = qtr.getHor(); out5[3] = qtr.getVer(); out5[4] = (int)cost;
 }
 
+/* xMotionEstimation's integer + fractional stages for every census PU of one CTU against num_refs references, looped
+ * here so that the CPU baseline of bench.py times the reference's own compiled TEncSearch code and not Python call
+ * overhead.  census: 593 x (x, y, w, h, cu_x, cu_y) relative to the CTU (the caller passes tvc_me_census / orc_census).
+ * cur / refs[r]: pel (0,0) of padded luma planes of equal stride.  out_int: num_refs*593 x (mvx, mvy, sad, valid);
+ * out_frac: x (halfx, halfy, qtrx, qtry, cost). */
+void ref_me_frame_ctu(short* cur, short** refs, int num_refs, int stride, int pic_w, int pic_h, int ctu_x, int ctu_y,
+                      const int* pred_qpel, double lambda, int srange, const short* census, int* out_int, int* out_frac)
+{
+  for (int r = 0; r < num_refs; r++) {
+    const int predx = pred_qpel[2 * r], predy = pred_qpel[2 * r + 1];
+    for (int k = 0; k < 593; k++) {
+      const short* c = census + 6 * k;
+      const int x = ctu_x + c[0], y = ctu_y + c[1], w = c[2], h = c[3];
+      int* io = out_int + ((size_t)r * 593 + k) * 4;
+      int* fo = out_frac + ((size_t)r * 593 + k) * 5;
+      io[0] = io[1] = io[2] = io[3] = 0;
+      fo[0] = fo[1] = fo[2] = fo[3] = fo[4] = 0;
+      if (x + w > pic_w || y + h > pic_h) continue;
+      const int cu_x = ctu_x + c[4], cu_y = ctu_y + c[5];
+      int rng[4];
+      ref_set_search_range(cu_x, cu_y, predx, predy, srange, rng);
+      short* o = cur + (ptrdiff_t)y * stride + x;
+      short* rf = refs[r] + (ptrdiff_t)y * stride + x;
+      ref_int_search(1, o, stride, rf, stride, w, h, cu_x, cu_y, rng[0], rng[1], rng[2], rng[3], lambda, predx, predy, predx, predy, io);
+      io[3] = 1;
+      ref_frac_search(o, stride, rf, stride, w, h, io[0], io[1], lambda, predx, predy, fo);
+    }
+  }
+}
+
 /* ==================================================================================== motion compensation
  * TComPrediction::xPredInterLumaBlk / xPredInterChromaBlk (TComPrediction.cpp:554-645) on a real
  * TComPicYuv: the caller's padded planes are copied into it (margins included). */
