@@ -33,5 +33,5 @@ def test_reference_arm_under_torchrun_prints_one_line():
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
-    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] in ("reference", "port") and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0
