@@ -442,3 +442,41 @@ def test_rdoq(orc, hmref, bd):
                         changed += int(np.count_nonzero(np.abs(qa) != np.minimum(plain, 1 << 30)))
                         zeroed += int(np.count_nonzero((qa == 0) & (plain > 0)))
     assert changed > 5000 and zeroed > 3000, (changed, zeroed)
+
+
+def test_me_frame_ctu_against_reference_driver(orc, hmref):
+    """the census-wide search of whole CTUs (593 PUs x 2 references: xSetSearchRange + xTZSearch + xPatternSearchFracDIF):
+    restatement (orc_me_frame_ctu) == the reference's own TEncSearch looped by ref_me_frame_ctu, including a CTU at the
+    right / bottom picture border (clipped windows, PUs outside the picture)"""
+    import synth
+    if not hasattr(hmref, "ref_me_frame_ctu"):
+        pytest.skip("libhmref.so predates ref_me_frame_ctu")
+    W, H = 416, 240
+    hmref.ref_init(8)
+    hmref.ref_me_setup(W, H, 64, 1, 1)
+    seq = synth.make_sequence(W, H, 3)
+    cur = synth.to_hostpic(seq[2], W, H)
+    refs = [synth.to_hostpic(seq[1], W, H), synth.to_hostpic(seq[0], W, H)]
+    census = np.zeros((593, 6), np.int16)
+    orc.orc_census(census.ctypes.data_as(C.c_void_p))
+    rp = (C.c_void_p * 2)(*[ptr(r.buf_y, r.origin(0)).value for r in refs])
+    lam = 44.7
+    lc = orc.orc_lambda_motion_sad(lam)
+    rng = np.random.default_rng(12)
+    ctus_x = (W + 63) // 64
+    for ctu in (8, ctus_x - 1, ctus_x * 3 + 2):          # interior, right border, bottom (partial) row
+        x0, y0 = (ctu % ctus_x) * 64, (ctu // ctus_x) * 64
+        pred = rng.integers(-30, 31, 4).astype(np.int32)
+        oi = np.zeros((2 * 593, 4), np.int32); of = np.zeros((2 * 593, 5), np.int32)
+        hmref.ref_me_frame_ctu(ptr(cur.buf_y, cur.origin(0)), rp, 2, cur.stride, W, H, x0, y0, ptr(pred), lam, 64, ptr(census), ptr(oi), ptr(of))
+        ires = (oracle.MeResult * (2 * 593))(); fres = (oracle.FracResult * (2 * 593))()
+        orc.orc_me_frame_ctu(ptr(cur.buf_y, cur.origin(0)), rp, 2, cur.stride, W, H, x0, y0, ptr(pred), lc, 64, 1, 1, 1, 8, ires, fres)
+        valid = 0
+        for i in range(2 * 593):
+            if oi[i, 3] == 0:
+                assert ires[i].n_sads == 0
+                continue
+            valid += 1
+            assert (ires[i].mvx, ires[i].mvy, ires[i].sad) == tuple(int(v) for v in oi[i, :3]), (ctu, i)
+            assert (fres[i].halfx, fres[i].halfy, fres[i].qtrx, fres[i].qtry, fres[i].cost) == tuple(int(v) for v in of[i]), (ctu, i)
+        assert valid > 300
