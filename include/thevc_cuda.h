@@ -166,6 +166,9 @@ typedef struct { int32_t cx, cy; } tvc_me_center;   /* integer-pel window centre
  * that every read stays inside the padded reference plane.                                     */
 int tvc_me_prepass(tvc_ctx* ctx, int cur_slot, int num_refs, const int* ref_slots,
                    const tvc_me_center* centers);
+/* allocate the SAD tables for num_refs references ahead of time (17.04 MB per CTU and reference; tvc_me_prepass grows
+ * them on demand otherwise, and re-allocating tens of GB costs 0.2-0.6 s each time the reference count of a GOP grows) */
+int tvc_me_reserve(tvc_ctx* ctx, int num_refs);
 /* bytes of table storage tvc_me_prepass needs for num_refs references (allocated lazily)       */
 size_t tvc_me_table_bytes(tvc_ctx* ctx, int num_refs);
 /* device pointer to the tables of the last pre-pass and the (clamped) centres actually used    */

@@ -12,7 +12,7 @@ with open('$D/in.yuv','wb') as f:
     for y,u,v in seq:
         f.write(y.astype(np.uint8).tobytes()); f.write(u.astype(np.uint8).tobytes()); f.write(v.astype(np.uint8).tobytes())
 PY
-ARGS="-c build/hm/cfg/encoder_lowdelay_P_main.cfg -i $D/in.yuv -wdt 1920 -hgt 1080 -fr 30 -f $N --SEIpictureDigest=1"
+ARGS="-c build/hm/cfg/${CFG:-encoder_lowdelay_P_main.cfg} -i $D/in.yuv -wdt 1920 -hgt 1080 -fr 30 -f $N --SEIpictureDigest=1"
 ( time oracle/_ref/bin/TAppEncoderStatic $ARGS -b $D/ref.bin > $D/ref.log ) 2> $D/ref.time &
 ( time env TVC_HM=${TVC_HM:-me,frac,tables} build/hm/TAppEncoderCuda $ARGS -b $D/cuda.bin > $D/cuda.log 2> $D/cuda.err ) 2> $D/cuda.time
 wait

@@ -136,6 +136,7 @@ SIGNATURES = {
     "tvc_mc_batch_dev": (ci, [vp, ci, ci, vp]),
     "tvc_mc_block": (ci, [vp, ci, ci, ci, ci, ci, ci, ci, ci, vp, ci, vp, vp, ci]),
     "tvc_me_prepass": (ci, [vp, ci, ci, vp, vp]),
+    "tvc_me_reserve": (ci, [vp, ci]),
     "tvc_me_table_bytes": (C.c_size_t, [vp, ci]),
     "tvc_me_tables_dev": (ci, [vp, C.POINTER(vp), C.POINTER(vp)]),
     "tvc_me_table_lookup": (ci, [vp, ci, ci, ci, ci, ci, ci, ci, vp, vp]),

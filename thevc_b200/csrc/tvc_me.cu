@@ -1390,6 +1390,18 @@ size_t tvc_me_table_bytes(tvc_ctx* c, int num_refs)
   return (size_t)num_refs * c->num_ctus_x * c->num_ctus_y * kMeCtuElems * sizeof(uint16_t);
 }
 
+int tvc_me_reserve(tvc_ctx* c, int num_refs)
+{
+  if (!c || num_refs <= 0 || num_refs > 8) return set_err(c, TVC_ERR_ARG, "tvc_me_reserve: 1..8 references");
+  const size_t need = tvc_me_table_bytes(c, num_refs);
+  if (need <= c->me_table_bytes) return TVC_OK;
+  if (c->me_tables) { cudaStreamSynchronize(c->stream); cudaFree(c->me_tables); }
+  c->me_tables = nullptr; c->me_table_bytes = 0; c->me_num_refs = 0;
+  if (cudaMalloc(&c->me_tables, need) != cudaSuccess) { cudaGetLastError(); return set_err(c, TVC_ERR_NOMEM, "tvc_me_reserve: cannot allocate %zu bytes of SAD tables", need); }
+  c->me_table_bytes = need;
+  return TVC_OK;
+}
+
 int tvc_me_prepass(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slots, const tvc_me_center* centers)
 {
   if (!c || !valid_slot(c, cur_slot) || num_refs <= 0 || num_refs > 8 || !ref_slots)

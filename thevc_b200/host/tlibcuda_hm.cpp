@@ -338,12 +338,17 @@ void tlibcuda_picture_start(TComPic* pic, TComSlice* slice)
         p.cy = (p.cy < vmin ? vmin : (p.cy > vmax ? vmax : p.cy)) >> 2;
         cen[(size_t)r * nctu + k] = p;
       }
+    // a GOP ramps up to 4 references: one allocation instead of four growing ones (0.2-0.6 s each at 1080p); if the
+    // device cannot hold four (34.8 GB at 1080p) the tables grow on demand as before
+    static bool reserved = false;
+    if (!reserved) { reserved = true; if (tvc_me_reserve(s.h, s.num_table_refs > 4 ? s.num_table_refs : 4) != TVC_OK) (void)0; }
     CK(tvc_me_prepass(s.h, s.cur_slot, s.num_table_refs, s.table_refs, cen.data()));
   } else
     s.num_table_refs = 0;
   CK(tvc_sync(s.h));
-  s.prepass_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
-  if (s.verbose) fprintf(stderr, "TLibCuda: POC %d cur slot %d, %d reference(s) with SAD tables\n", slice->getPOC(), s.cur_slot, s.num_table_refs);
+  const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+  s.prepass_seconds += dt;
+  if (s.verbose) fprintf(stderr, "TLibCuda: POC %d cur slot %d, %d reference(s) with SAD tables, %.1f ms (uploads + tables)\n", slice->getPOC(), s.cur_slot, s.num_table_refs, dt * 1e3);
 }
 
 bool tlibcuda_tz_search(TComDataCU* cu, TComPattern* key, short* refY, int refStride, TComMv* lt, TComMv* rb, TComMv& rcMv,
