@@ -103,6 +103,7 @@ struct Sao {
 struct State {
   tvc_ctx* h = nullptr;
   bool on_lookup = true, verify = false;
+  bool wp = false;                         // weighted prediction in the current picture: ME / MC hooks stand down
   Sao sao;
   Dbk dbk;
   DecBatch dec;
@@ -301,6 +302,7 @@ void tlibcuda_picture_start(TComPic* pic, TComSlice* slice)
   ensure_ctx(org->getWidth(), org->getHeight());
   State& s = S();
   if (!s.h || (!s.on_me && !s.on_frac)) return;
+  s.wp = slice->getPPS()->getUseWP() || slice->getPPS()->getWPBiPred();
   s.cur_slot = slot_for(org, slice->getPOC(), true, false);
   s.num_table_refs = 0;
   for (int l = 0; l < 2; l++) {
@@ -370,6 +372,8 @@ bool tlibcuda_tz_search(TComDataCU* cu, TComPattern* key, short* refY, int refSt
     return false;
   }
   if (!s.h || !s.on_me || s.cur_slot < 0) return false;
+  // weighted prediction changes the distortion itself (setWpScalingDistParam, TEncSearch.cpp:4177): not ported, reference path
+  if (cu->getSlice()->getPPS()->getUseWP() || cu->getSlice()->getPPS()->getWPBiPred()) return false;
   int slot, x, y;
   if (!locate(refY, slot, x, y)) return false;
   (void)refStride;
@@ -451,7 +455,7 @@ bool tlibcuda_frac_search(TComPattern* key, short* refY, int refStride, TComMv* 
                           unsigned& ruiCost, TComRdCost* rd, TEncCfg* cfg, bool biPred)
 {
   State& s = S();
-  if (!s.h || !s.on_frac || s.cur_slot < 0 || biPred) return false;     // bi-pred search target is not the original picture
+  if (!s.h || !s.on_frac || s.cur_slot < 0 || biPred || s.wp) return false;     // bi-pred search target is not the original picture
   int slot, x, y;
   if (!locate(refY, slot, x, y)) return false;
   (void)refStride;
@@ -492,6 +496,7 @@ bool tlibcuda_pred_inter_uni(TComDataCU* cu, TComPic* refPic, unsigned partAddr,
   ensure_ctx(rec->getWidth(), rec->getHeight());
   State& s = S();
   if (!s.h || !s.on_mc) return false;
+  if (cu->getSlice()->getPPS()->getUseWP() || cu->getSlice()->getPPS()->getWPBiPred()) return false;   // weighted prediction: reference path
   const int slot = slot_for(rec, refPic->getPOC(), false, true);
   const unsigned z = cu->getZorderIdxInCU() + partAddr;
   const unsigned raster = g_auiZscanToRaster[z];
@@ -584,6 +589,7 @@ bool tlibcuda_dec_begin_inter(TComDataCU* cu, TComYuv* resi)
   ensure_ctx(rec->getWidth(), rec->getHeight());
   DecBatch& d = s.dec;
   if (!s.h || !d.on || !s.on_mc || !s.on_tq) return false;
+  if (cu->getSlice()->getPPS()->getUseWP() || cu->getSlice()->getPPS()->getWPBiPred()) return false;     // weighted prediction: host reconstruction
   d.cu_open = true;
   d.cu_x = (int)cu->getCUPelX(); d.cu_y = (int)cu->getCUPelY();
   d.resi_base[0] = resi->getLumaAddr(); d.resi_base[1] = resi->getCbAddr(); d.resi_base[2] = resi->getCrAddr();
