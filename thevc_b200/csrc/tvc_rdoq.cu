@@ -48,8 +48,8 @@ struct RdoqScratch {
   double* csig;       // pdCostSig
   double* cost0;      // pdCostCoeff0
   int32_t* level;     // chosen level (unsigned during the walk, signed after the output pass)
-  int32_t* rup;       // rateIncUp
-  int32_t* rdn;       // rateIncDown
+  int32_t* ctxw;      // flag-context state the level was chosen in (packed): rateIncUp / rateIncDown are derived from it where
+  int32_t* orig;      // sign-data hiding needs them, together with the level chosen THEN (zeroed groups keep their increments)
   int32_t* sigd;      // sigRateDelta
   int32_t* du;        // deltaU
 };
@@ -59,7 +59,7 @@ struct RdoqWarp {
   int32_t est[EB_INTS + 2];
   double cost0[16], sig0[16], sig1[16], coded[16], csig[16], lastc[16];
   double cg_sig[64];
-  int32_t lvl_dbl[16], max_lvl[16], sigd_in[16], sigd[16], level[16], rup[16], rdn[16], du[16];
+  int32_t lvl_dbl[16], max_lvl[16], sigd_in[16], sigd[16], level[16], ctxw[16], orig[16], du[16];
 };
 
 struct LvlState { int ctx_set, c1, c2, rice, c1_idx, c2_idx; };
@@ -141,6 +141,20 @@ __device__ __forceinline__ double rq_last_cost(const int32_t* est, double lambda
   if (cx > 3) r += 32768ll * ((cx - 2) >> 1);
   if (cy > 3) r += 32768ll * ((cy - 2) >> 1);
   return __dmul_rn(lambda, (double)r);
+}
+
+// rateIncUp / rateIncDown of a position (:1935-1944) from the packed context state and the level chosen there
+__device__ __forceinline__ void rq_rate_increments(const int32_t* est, int ctxw, int orig, int& rup, int& rdn)
+{
+  rup = 0; rdn = 0;
+  if (ctxw >= 0) return;                        // bit 31 clear: in front of the last significant coefficient, never initialised (memset 0)
+  const int one_ctx = ctxw & 31, abs_ctx = (ctxw >> 5) & 7;
+  LvlState s = {0, 0, 0, (ctxw >> 8) & 7, (ctxw >> 11) & 31, (ctxw >> 16) & 31};
+  if (orig > 0) {
+    const int now = rq_level_rate_int(est, orig, one_ctx, abs_ctx, s);
+    rup = rq_level_rate_int(est, orig + 1, one_ctx, abs_ctx, s) - now;
+    rdn = rq_level_rate_int(est, orig - 1, one_ctx, abs_ctx, s) - now;
+  } else rup = est[EB_GT1 + 2 * one_ctx];
 }
 
 __global__ void __launch_bounds__(kRdoqWarps * 32)
@@ -239,7 +253,7 @@ k_rdoq(int n, const tvc_rdoq_tu* __restrict__ tus, const tvc_est_bits* __restric
       uncoded_cost = __dadd_rn(uncoded_cost, c0);
       unsigned best = 0;
       double coded = 0.0, csig = 0.0;
-      int rup = 0, rdn = 0, du = 0, sigd = 0;
+      int ctxw = 0, du = 0, sigd = 0;
       if (max_lvl > 0 && last_pos < 0) {
         last_pos = sp;
         st.ctx_set = (sp < 16 || !is_luma) ? 0 : 2;
@@ -267,11 +281,10 @@ k_rdoq(int n, const tvc_rdoq_tu* __restrict__ tus, const tvc_est_bits* __restric
         }
         if (!is_last) sigd = S.sigd_in[k];
         du = (lvl_dbl - (int)(best << qbits)) >> (qbits - 8);
-        if (best > 0) {
-          const int now = rq_level_rate_int(est, (int)best, one_ctx, abs_ctx, st);
-          rup = rq_level_rate_int(est, (int)best + 1, one_ctx, abs_ctx, st) - now;
-          rdn = rq_level_rate_int(est, (int)best - 1, one_ctx, abs_ctx, st) - now;
-        } else rup = est[EB_GT1 + 2 * one_ctx];
+        // rateIncUp / rateIncDown (:1935-1944) are only read by sign-data hiding: keep the state they depend on and derive
+        // them there, lane-parallel, for the positions that are actually examined
+        ctxw = (int)(0x80000000u | (unsigned)one_ctx | ((unsigned)abs_ctx << 5) | ((unsigned)st.rice << 8) | ((unsigned)st.c1_idx << 11) |
+                     ((unsigned)st.c2_idx << 16));
         base_cost = __dadd_rn(base_cost, coded);
         if ((int)best >= rq_base_level(st) && best > (3u << st.rice)) st.rice = min(st.rice + 1, 4);
         if (best >= 1) st.c1_idx++;
@@ -295,7 +308,7 @@ k_rdoq(int n, const tvc_rdoq_tu* __restrict__ tus, const tvc_est_bits* __restric
       }
       if (lane == 0) {
         S.level[k] = (int)best; S.coded[k] = coded; S.csig[k] = csig;
-        S.rup[k] = rup; S.rdn[k] = rdn; S.du[k] = du; S.sigd[k] = sigd;
+        S.ctxw[k] = ctxw; S.orig[k] = (int)best; S.du[k] = du; S.sigd[k] = sigd;
       }
     }
     if (cg_nz) cg_flag |= 1ull << cgpos;
@@ -344,7 +357,7 @@ k_rdoq(int n, const tvc_rdoq_tu* __restrict__ tus, const tvc_est_bits* __restric
       double cd = S.coded[lane], cs = S.csig[lane];
       if (zero_out && lv) { lv = 0; cd = S.cost0[lane]; cs = 0.0; }
       G.level[g] = lv; G.coded[g] = cd; G.csig[g] = cs; G.cost0[g] = S.cost0[lane];
-      G.rup[g] = S.rup[lane]; G.rdn[g] = S.rdn[lane]; G.du[g] = S.du[lane]; G.sigd[g] = S.sigd[lane];
+      G.ctxw[g] = S.ctxw[lane]; G.orig[g] = S.orig[lane]; G.du[g] = S.du[lane]; G.sigd[g] = S.sigd[lane];
     }
     __syncwarp();
   }
@@ -444,15 +457,17 @@ k_rdoq(int n, const tvc_rdoq_tu* __restrict__ tus, const tvc_est_bits* __restric
     for (int k = is_top ? last_nz : 15; k >= 0; --k) {
       const size_t g = off + (size_t)(base + k);
       const int lv = lev[k], du = G.du[g];
+      int rup, rdn;
+      rq_rate_increments(est, G.ctxw[g], G.orig[g], rup, rdn);
       if (lv != 0) {
         const bool one = abs(lv) == 1;
-        const long long up = rd_factor * (long long)(-du) + G.rup[g];
-        long long down = rd_factor * (long long)du + G.rdn[g] - (one ? ((1 << 15) + G.sigd[g]) : 0);
+        const long long up = rd_factor * (long long)(-du) + rup;
+        long long down = rd_factor * (long long)du + rdn - (one ? ((1 << 15) + G.sigd[g]) : 0);
         if (is_top && last_nz == k && one) down -= 4 << 15;
         if (up < down) { cur = up; change = 1; }
         else { change = -1; cur = (k == first_nz && one) ? LLONG_MAX : down; }
       } else {
-        cur = rd_factor * (-(long long)abs(du)) + (1 << 15) + G.rup[g] + G.sigd[g];
+        cur = rd_factor * (-(long long)abs(du)) + (1 << 15) + rup + G.sigd[g];
         change = 1;
         if (k < first_nz) {
           const unsigned s = src[scan[base + k]] >= 0 ? 0u : 1u;
@@ -481,8 +496,8 @@ static int ensure_rdoq_scratch(tvc_ctx* c, size_t elems, RdoqScratch& G)
   G.csig = (double*)p; p += cap * 8;
   G.cost0 = (double*)p; p += cap * 8;
   G.level = (int32_t*)p; p += cap * 4;
-  G.rup = (int32_t*)p; p += cap * 4;
-  G.rdn = (int32_t*)p; p += cap * 4;
+  G.ctxw = (int32_t*)p; p += cap * 4;
+  G.orig = (int32_t*)p; p += cap * 4;
   G.sigd = (int32_t*)p; p += cap * 4;
   G.du = (int32_t*)p;
   return TVC_OK;
