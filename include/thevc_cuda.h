@@ -451,7 +451,8 @@ int tvc_prof_read(tvc_ctx* ctx, double* ms_sum, uint64_t* groups, int reset);
 /* ---------------------------------------------------------------------------------- diagnostics
  * integer-pipe micro-benchmarks used for the ME roofline denominator; returns the
  * measured rate in giga-instructions/s for the whole GPU                                        */
-enum { TVC_UB_VABSDIFF4 = 0, TVC_UB_IADD3 = 1, TVC_UB_IMAD = 2, TVC_UB_LDS128 = 3, TVC_UB_DP2A = 4 };
+enum { TVC_UB_VABSDIFF4 = 0, TVC_UB_IADD3 = 1, TVC_UB_IMAD = 2, TVC_UB_LDS128 = 3, TVC_UB_DP2A = 4,
+       TVC_UB_HBM_WRITE = 5 /* pure 16-byte coalesced stores over 8 GiB: the result is GB/s, the write-only HBM roofline */ };
 int tvc_ubench(tvc_ctx* ctx, int which, double* ginstr_per_s);
 
 #ifdef __cplusplus

@@ -141,7 +141,8 @@ __device__ __forceinline__ void sad_task_wo(int wo, const uint8_t* win, const ui
   }
 }
 
-__global__ void __launch_bounds__(256, 2)
+template <int DYB, int MINB>       // DYB consecutive dy per lane (register window), MINB resident CTAs per SM compiled for
+__global__ void __launch_bounds__(256, MINB)
 k_me_sad_tables(const __grid_constant__ MeMaps maps, int num_ctus, int ctus_x, int mx, int my,
                 const tvc_me_center* __restrict__ centers, uint16_t* __restrict__ tables)
 {
@@ -170,20 +171,21 @@ k_me_sad_tables(const __grid_constant__ MeMaps maps, int num_ctus, int ctus_x, i
   uint16_t* tbl = tables + ((size_t)ref * num_ctus + ctu) * kMeCtuElems;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = lane & 3, i8 = lane >> 2;
-  // tasks: [0,256) (a,g) 8 dx x 8 dy ; [256,272) (a) last dy row ; [272,274) dx=+64 column, 8 dy-groups
-  // per warp ; 274 the (+64,+64) corner.
-  for (int t = warp; t < 275; t += 8) {
-    if (t < 256) {
+  // tasks: [0,16*NG) (a,g) 8 dx x DYB dy ; then 16 (a) last dy row ; then NG/8 for the dx=+64 column (8 dy-groups per
+  // warp) ; last the (+64,+64) corner.  NG = 128 / DYB dy-groups.
+  constexpr int NG = 128 / DYB, T0 = 16 * NG, T1 = T0 + 16, T2 = T1 + NG / 8;
+  for (int t = warp; t <= T2; t += 8) {
+    if (t < T0) {
       int a = t & 15, g = t >> 4;
       int u = a + 16 * i8, al = (a + e) & 15;
-      sad_task_wo<8>(al >> 2, win, cur, u + 16 * q + e, (al & 3) * 8, g * 8, q, true, tbl, u);
-    } else if (t < 272) {
-      int a = t - 256;
+      sad_task_wo<DYB>(al >> 2, win, cur, u + 16 * q + e, (al & 3) * 8, g * DYB, q, true, tbl, u);
+    } else if (t < T1) {
+      int a = t - T0;
       int u = a + 16 * i8, al = (a + e) & 15;
       sad_task_wo<1>(al >> 2, win, cur, u + 16 * q + e, (al & 3) * 8, 128, q, true, tbl, u);
-    } else if (t < 274) {
-      int g = (t - 272) * 8 + i8;
-      sad_task_wo<8>(e >> 2, win, cur, 128 + 16 * q + e, (e & 3) * 8, g * 8, q, true, tbl, 128);
+    } else if (t < T2) {
+      int g = (t - T1) * 8 + i8;
+      sad_task_wo<DYB>(e >> 2, win, cur, 128 + 16 * q + e, (e & 3) * 8, g * DYB, q, true, tbl, 128);
     } else {
       sad_task_wo<1>(e >> 2, win, cur, 128 + 16 * q + e, (e & 3) * 8, 128, q, i8 == 0, tbl, 128);
     }
@@ -1329,6 +1331,26 @@ __global__ void k_ub_dp2a(uint32_t* out, int iters, uint32_t a0, uint32_t b0)
   for (int k = 0; k < 8; k++) s += acc[k];
   out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)s;
 }
+__global__ void k_ub_hbm_write(uint4* __restrict__ dst, size_t n16, uint32_t seed)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const uint4 v = make_uint4(seed, seed + 1, seed + 2, seed + 3);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = v;
+}
+// the SAD-table store pattern: a warp instruction writes 8 segments of 64 bytes that lie 16 KB apart (8 dx values x 4 quarters),
+// a lane's next store is the adjacent 64 bytes (next block row); seg_bytes = 64 reproduces it, 512 is one contiguous run per warp
+__global__ void k_ub_hbm_write_pat(uint4* __restrict__ dst, size_t n16, uint32_t seed, int seg16)
+{
+  const int lane = threadIdx.x & 31;
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const uint4 v = make_uint4(seed, seed + 1, seed + 2, seed + 3);
+  // the buffer is cut into 1 KB records (64 x 16 B); a warp owns 32 / seg16 records at a time, spaced 16 records apart
+  const int nseg = 32 / seg16, sl = lane / seg16, q = lane % seg16;
+  const size_t recs = n16 / 64;
+  for (size_t r0 = warp * 16 * nseg; r0 + 16 * nseg <= recs; r0 += nwarps * 16 * nseg)
+    for (int a = 0; a < 16; a++)                       // 16 interleaved record groups, like the 16 dx residues of the table tasks
+      for (int part = 0; part < 64 / seg16; part++) dst[(r0 + a + 16 * (size_t)sl) * 64 + part * seg16 + q] = v;
+}
 __global__ void k_ub_lds128(uint32_t* out, int iters)
 {
   __shared__ uint4 buf[1024];
@@ -1442,14 +1464,19 @@ int tvc_me_prepass(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slots,
   memset(&maps, 0, sizeof(maps));
   maps.cur = c->pics[cur_slot].tmap_cur;
   for (int rf = 0; rf < num_refs; rf++) maps.ref[rf] = c->pics[ref_slots[rf]].tmap_ref;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables));
-    attr_set = true;
+  static int variant = -1;       // tuning knob: 8 = 8-row register window, 2 CTAs/SM; 4 = 4-row window, 4 CTAs/SM
+  if (variant < 0) {
+    const char* ev = getenv("TVC_TABLE_DYB");
+    variant = ev ? atoi(ev) : 8;
+    TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables));
+    TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables));
+    TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables));
   }
   dim3 grd(nctu, num_refs);
   ProfScope ps(c, TVC_PH_ME_TABLES);
-  k_me_sad_tables<<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables);
+  if (variant == 4) k_me_sad_tables<4, 4><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables);
+  else if (variant == 43) k_me_sad_tables<4, 3><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables);
+  else k_me_sad_tables<8, 2><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables);
   TVC_LAUNCH_CHECK(c);
   c->me_num_refs = num_refs;
   c->me_cur_slot = cur_slot;
@@ -1760,7 +1787,34 @@ int tvc_me_ctu(tvc_ctx* c, int cur_slot, int ref_index, int ref_slot, int ctu, t
 
 int tvc_ubench(tvc_ctx* c, int which, double* ginstr_per_s)
 {
-  if (!c || !ginstr_per_s || which < 0 || which > 4) return set_err(c, TVC_ERR_ARG, "tvc_ubench: bad argument");
+  if (!c || !ginstr_per_s || which < 0 || which > 5) return set_err(c, TVC_ERR_ARG, "tvc_ubench: bad argument");
+  if (which == TVC_UB_HBM_WRITE) {
+    // write-only bandwidth: what a kernel that only stores (the SAD tables) can reach at best
+    const size_t bytes = (size_t)8 << 30;
+    uint4* buf = nullptr;
+    TVC_CUDA(c, cudaMalloc(&buf, bytes));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+      cudaEventRecord(e0, c->stream);
+      static int pat = -1;
+      if (pat < 0) { const char* ev = getenv("TVC_UB_WRITE_SEG16"); pat = ev ? atoi(ev) : 0; }
+      if (pat > 0) k_ub_hbm_write_pat<<<kNumSM * 16, 256, 0, c->stream>>>(buf, bytes / 16, (uint32_t)rep, pat);
+      else k_ub_hbm_write<<<kNumSM * 16, 256, 0, c->stream>>>(buf, bytes / 16, (uint32_t)rep);
+      cudaEventRecord(e1, c->stream);
+      cudaError_t e = cudaEventSynchronize(e1);
+      if (e != cudaSuccess) { cudaFree(buf); return check_cuda(c, e, "tvc_ubench"); }
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (rep > 0 && ms < best) best = ms;
+      c->launches++;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf);
+    *ginstr_per_s = (double)bytes / (best * 1e-3) / 1e9;
+    return TVC_OK;
+  }
   const int blocks = kNumSM * 8, threads = 256, iters = 4096;
   uint32_t* d = nullptr;
   TVC_CUDA(c, cudaMalloc(&d, (size_t)blocks * threads * 4));
