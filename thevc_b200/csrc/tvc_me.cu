@@ -129,6 +129,73 @@ __device__ __forceinline__ void sad_task(const uint8_t* __restrict__ win, const 
   }
 }
 
+// Row-split form of the same task: lane = (i2: 2 dx, yb: 4 block rows, q: 4 quarters).  At step t the four yb lanes of a dx hold
+// block rows 4t .. 4t+3 of the same candidates, so one warp store covers 256 contiguous bytes per candidate (two candidates per
+// instruction) instead of eight 64-byte pieces: measured with tvc_ubench, 64-byte pieces reach 5.5 TB/s, 256-byte runs 6.8 TB/s.
+// The price is the sliding window: every step reloads its DYB+3 window rows (26 instead of 12 shared-memory loads per 4 rows).
+template <int DYB, int WO>
+__device__ __forceinline__ void sad_task_rows(const uint8_t* __restrict__ win, const uint8_t* __restrict__ cur, int X, int SH,
+                                              int dyb, int q, int yb, uint16_t* __restrict__ tbl, int dxc)
+{
+  const uint8_t* wbase = win + (X & ~15);
+  const uint8_t* cbase = cur + 16 * q;
+  for (int t = 0; t < 4; t++) {
+    const int by = 4 * t + yb, y0 = 4 * by;
+    uint32_t C[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const uint4 c4 = *reinterpret_cast<const uint4*>(cbase + (y0 + r) * 64);
+      C[r][0] = c4.x; C[r][1] = c4.y; C[r][2] = c4.z; C[r][3] = c4.w;
+    }
+    uint32_t E[DYB][4], O[DYB][4];
+#pragma unroll
+    for (int j = 0; j < DYB + 3; j++) {
+      // window row dyb + y0 + j meets current row r at dy offset d = j - r
+      const uint4* p = reinterpret_cast<const uint4*>(wbase + (dyb + y0 + j) * kWinW);
+      const uint4 lo = p[0], hi = p[1];
+      const uint32_t W[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      uint32_t R[4];
+#pragma unroll
+      for (int m = 0; m < 4; m++) R[m] = __funnelshift_r(W[WO + m], W[WO + m + 1], SH);
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int d = j - r;
+        if (d >= 0 && d < DYB) {
+#pragma unroll
+          for (int m = 0; m < 4; m++) {
+            if (r == 0) E[d][m] = vsad4_acc(C[0][m], R[m], 0u);
+            else if (r == 1) O[d][m] = vsad4_acc(C[1][m], R[m], 0u);
+            else if (r == 2) E[d][m] = vsad4_acc(C[2][m], R[m], E[d][m]);
+            else O[d][m] = vsad4_acc(C[3][m], R[m], O[d][m]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < DYB; d++) {
+      uint4 o;
+      o.x = E[d][0] | (E[d][1] << 16);
+      o.y = E[d][2] | (E[d][3] << 16);
+      o.z = O[d][0] | (O[d][1] << 16);
+      o.w = O[d][2] | (O[d][3] << 16);
+      const size_t e = ((size_t)((dyb + d) * kMeC + dxc) * kMeCandGranules + by * 4 + q) * kMeGranule;
+      *reinterpret_cast<uint4*>(tbl + e) = o;
+    }
+  }
+}
+
+template <int DYB>
+__device__ __forceinline__ void sad_task_rows_wo(int wo, const uint8_t* win, const uint8_t* cur, int X, int SH, int dyb, int q, int yb,
+                                                 uint16_t* tbl, int dxc)
+{
+  switch (wo) {
+    case 0: sad_task_rows<DYB, 0>(win, cur, X, SH, dyb, q, yb, tbl, dxc); break;
+    case 1: sad_task_rows<DYB, 1>(win, cur, X, SH, dyb, q, yb, tbl, dxc); break;
+    case 2: sad_task_rows<DYB, 2>(win, cur, X, SH, dyb, q, yb, tbl, dxc); break;
+    default: sad_task_rows<DYB, 3>(win, cur, X, SH, dyb, q, yb, tbl, dxc); break;
+  }
+}
+
 template <int DYB>
 __device__ __forceinline__ void sad_task_wo(int wo, const uint8_t* win, const uint8_t* cur, int X, int SH, int dyb, int q,
                                             bool active, uint16_t* tbl, int dxc)
@@ -141,8 +208,8 @@ __device__ __forceinline__ void sad_task_wo(int wo, const uint8_t* win, const ui
   }
 }
 
-template <int DYB, int MINB>       // DYB consecutive dy per lane (register window), MINB resident CTAs per SM compiled for
-__global__ void __launch_bounds__(256, MINB)
+template <int DYB, int MINB, bool ROWS = false>   // DYB consecutive dy per lane (register window), MINB resident CTAs per SM compiled
+__global__ void __launch_bounds__(256, MINB)       // for, ROWS: row-split lane mapping of the bulk tasks (256-byte store runs)
 k_me_sad_tables(const __grid_constant__ MeMaps maps, int num_ctus, int ctus_x, int mx, int my,
                 const tvc_me_center* __restrict__ centers, uint16_t* __restrict__ tables)
 {
@@ -174,7 +241,16 @@ k_me_sad_tables(const __grid_constant__ MeMaps maps, int num_ctus, int ctus_x, i
   // tasks: [0,16*NG) (a,g) 8 dx x DYB dy ; then 16 (a) last dy row ; then NG/8 for the dx=+64 column (8 dy-groups per
   // warp) ; last the (+64,+64) corner.  NG = 128 / DYB dy-groups.
   constexpr int NG = 128 / DYB, T0 = 16 * NG, T1 = T0 + 16, T2 = T1 + NG / 8;
-  for (int t = warp; t <= T2; t += 8) {
+  if (ROWS) {
+    // bulk of the table (dx, dy < +64) in the row-split mapping: task = (a: dx residue mod 16, xb: 32-wide dx band, g: dy group)
+    const int i2 = lane >> 4, yb = (lane >> 2) & 3;
+    for (int t = warp; t < 64 * NG; t += 8) {
+      const int a = t & 15, xb = (t >> 4) & 3, g = t >> 6;
+      const int u = a + 16 * (2 * xb + i2), al = (a + e) & 15;
+      sad_task_rows_wo<DYB>(al >> 2, win, cur, u + 16 * q + e, (al & 3) * 8, g * DYB, q, yb, tbl, u);
+    }
+  }
+  for (int t = warp + (ROWS ? T0 : 0); t <= T2; t += 8) {
     if (t < T0) {
       int a = t & 15, g = t >> 4;
       int u = a + 16 * i8, al = (a + e) & 15;
@@ -1464,18 +1540,24 @@ int tvc_me_prepass(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slots,
   memset(&maps, 0, sizeof(maps));
   maps.cur = c->pics[cur_slot].tmap_cur;
   for (int rf = 0; rf < num_refs; rf++) maps.ref[rf] = c->pics[ref_slots[rf]].tmap_ref;
-  static int variant = -1;       // tuning knob: 8 = 8-row register window, 2 CTAs/SM; 4 = 4-row window, 4 CTAs/SM
+  // tuning knob (measured on B200, ms per 1080p picture x 4 references): 81 = row-split lane mapping, 8-row window, 2 CTAs/SM:
+  // 5.4 (default); 8 = column mapping (64-byte store pieces): 7.0; 4 / 43 = 4-row window at 4 / 3 CTAs/SM: 7.4 / 7.0; 41: 6.6
+  static int variant = -1;
   if (variant < 0) {
     const char* ev = getenv("TVC_TABLE_DYB");
-    variant = ev ? atoi(ev) : 8;
+    variant = ev ? atoi(ev) : 81;
     TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables));
     TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables));
     TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables));
+    TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables));
+    TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<4, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables));
   }
   dim3 grd(nctu, num_refs);
   ProfScope ps(c, TVC_PH_ME_TABLES);
   if (variant == 4) k_me_sad_tables<4, 4><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables);
   else if (variant == 43) k_me_sad_tables<4, 3><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables);
+  else if (variant == 81) k_me_sad_tables<8, 2, true><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables);
+  else if (variant == 41) k_me_sad_tables<4, 3, true><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables);
   else k_me_sad_tables<8, 2><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables);
   TVC_LAUNCH_CHECK(c);
   c->me_num_refs = num_refs;
