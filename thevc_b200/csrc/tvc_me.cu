@@ -477,7 +477,19 @@ __device__ __forceinline__ bool diamond_cand(const SearchCtx& s, int sx, int sy,
   return axis ? (ux == 0 ? yc : xc) : (inside || (yc && xc));
 }
 
-// Diamond rounds d = d0, 2*d0, ... <= dmax around (sx,sy).  All candidates of these rounds are known
+// candidate c (visiting order) of a sweep that starts at distance 1 -> (round distance d, index i inside the round): the rounds hold
+// 4, 8, 8, 8, 16, 16, 16 candidates (d = 1 .. 64), i.e. start at 0, 4, 12, 20, 28, 44, 60.  Closed form instead of walking the
+// rounds: the walk was 20 % of k_me_search's instructions in the ncu source view.
+__device__ __forceinline__ bool sweep_slot(int c, int dmax, int& d, int& i)
+{
+  if (c < 4) { d = 1; i = c; }
+  else if (c < 28) { d = 2 << ((c - 4) >> 3); i = (c - 4) & 7; }
+  else if (c < 76) { d = 16 << ((c - 28) >> 4); i = (c - 28) & 15; }
+  else { d = 128; i = 0; return false; }
+  return d <= dmax;
+}
+
+// Diamond rounds d = 1, 2, 4, ... <= dmax around (sx,sy) (d0 must be 1: every TZ sweep starts there).  All candidates of these rounds are known
 // beforehand, so they are evaluated together: candidate c (visiting order) is slot c >> 5 of lane
 // c & 31.  The reference's sequential update is then replayed as an ordered arg-min.
 // first_search: the reference stops when three consecutive rounds brought no improvement
@@ -492,14 +504,10 @@ __device__ __forceinline__ bool diamond_sweep(SearchCtx& s, int sx, int sy, int 
 #pragma unroll
   for (int k = 0; k < K; k++) {
     const int c = s.lane + 32 * k;
-    int off = 0, d = d0, pt;
+    int d, i, pt;
     uint32_t dist;
     valid[k] = false; x[k] = 0; y[k] = 0;
-    while (d <= dmax) {
-      const int sz = round_size(d);
-      if (c < off + sz) { valid[k] = diamond_cand(s, sx, sy, d, c - off, x[k], y[k], pt, dist); break; }
-      off += sz; d <<= 1;
-    }
+    if (sweep_slot(c, dmax, d, i)) valid[k] = diamond_cand(s, sx, sy, d, i, x[k], y[k], pt, dist);
   }
   eval_multi<K>(s, valid, x, y, cost);
   if (!first_search) {
@@ -516,11 +524,10 @@ __device__ __forceinline__ bool diamond_sweep(SearchCtx& s, int sx, int sy, int 
     const uint32_t mn = __reduce_min_sync(0xffffffffu, lb);
     if (mn < s.best_sad) {
       const int c = (int)__reduce_min_sync(0xffffffffu, (unsigned)(lb == mn ? lc : 0x7fffffff));
-      int off = 0, d = d0;
-      while (c >= off + round_size(d)) { off += round_size(d); d <<= 1; }
-      int bx, by, pt;
+      int d, i, bx, by, pt;
       uint32_t dist;
-      diamond_cand(s, sx, sy, d, c - off, bx, by, pt, dist);
+      sweep_slot(c, dmax, d, i);
+      diamond_cand(s, sx, sy, d, i, bx, by, pt, dist);
       s.best_sad = mn; s.best_x = bx; s.best_y = by; s.best_dist = dist; s.point_nr = pt; s.best_round = 0;
     }
     return false;
