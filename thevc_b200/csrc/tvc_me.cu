@@ -389,20 +389,30 @@ __device__ __forceinline__ void eval_multi(const SearchCtx& s, const bool (&vali
   for (int qi = 0; qi < 4; qi++) {
     if (qi < s.nq) {
       const uint32_t ma = s.m01[qi], mb = s.m23[qi];
+      // block rows in runs of <= 8: the packed u16 pairs of a run are summed as they are (a half stays <= 8 * 4 * 2040 = 65280)
+      // and unpacked once per run instead of once per granule
+      for (int r0 = 0; r0 < s.nby; r0 += 8) {
+        const int r1 = min(r0 + 8, s.nby);
+        uint32_t pk[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) pk[k] = 0;
 #pragma unroll kSearchRowUnroll
-      for (int r = 0; r < s.nby; r++) {
-        uint4 g[K];
+        for (int r = r0; r < r1; r++) {
+          uint4 g[K];
 #pragma unroll
-        for (int k = 0; k < K; k++)
-          if (tab[k]) g[k] = __ldg(tg + (base[k] + qi * kQtr + (uint32_t)r * kRow));
+          for (int k = 0; k < K; k++)
+            if (tab[k]) g[k] = __ldg(tg + (base[k] + qi * kQtr + (uint32_t)r * kRow));
 #pragma unroll
-        for (int k = 0; k < K; k++) {
-          if (tab[k]) {
-            uint32_t v = (g[k].x & ma) + (g[k].y & mb);         // packed u16 pairs, each <= 2 * 2040
-            if (all) v += (g[k].z & ma) + (g[k].w & mb);        // <= 4 * 2040 < 65536
-            sad[k] += (v & 0xffffu) + (v >> 16);
+          for (int k = 0; k < K; k++) {
+            if (tab[k]) {
+              uint32_t v = (g[k].x & ma) + (g[k].y & mb);         // packed u16 pairs, each <= 2 * 2040
+              if (all) v += (g[k].z & ma) + (g[k].w & mb);        // <= 4 * 2040
+              pk[k] += v;
+            }
           }
         }
+#pragma unroll
+        for (int k = 0; k < K; k++) sad[k] += (pk[k] & 0xffffu) + (pk[k] >> 16);
       }
     }
   }
