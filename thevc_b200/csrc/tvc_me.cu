@@ -1181,13 +1181,16 @@ k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ j
   if (live) {
     const int16_t* ref = pt.org[jb.ref_slot][0] + (ptrdiff_t)(jb.y + jb.imvy - 4) * gstride + jb.x + jb.imvx - 4;
     const int16_t* cur = pt.org[cur_slot][0] + (ptrdiff_t)jb.y * gstride + jb.x;
+    // n / d for the small loop counters below as one multiply + shift: m = ceil(2^20 / d) is exact for n < 2^20 / d (n <= 5184, d <= 72);
+    // the integer divisions were 10-18 % of the small size classes' instructions in the ncu source view
     const int rw = w + 8, rh = h + 8;
+    const unsigned m_rw = ((1u << 20) + rw - 1) / rw, m_w = ((1u << 20) + w - 1) / w;
     for (int i = tid; i < rw * rh; i += NT) {
-      int r = i / rw, x = i - r * rw;
+      int r = (int)(((unsigned)i * m_rw) >> 20), x = i - r * rw;
       S.R[r * SM::RP + x] = ref[(ptrdiff_t)r * gstride + x];
     }
     for (int i = tid; i < w * h; i += NT) {
-      int r = i / w, x = i - r * w;
+      int r = (int)(((unsigned)i * m_w) >> 20), x = i - r * w;
       S.org[r * MAXW + x] = cur[(ptrdiff_t)r * gstride + x];
     }
     if (tid < 12) S.cost[tid] = 0;
@@ -1196,8 +1199,9 @@ k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ j
   if (live) {
     // horizontal stage (isFirst, !isLast): H[f][r][xi], xi = 0..w <-> picture column xi-1, r = 0..h+7 <-> row r-4
     const int hw = w + 1, hh = h + 8;
+    const unsigned m_hw = ((1u << 20) + hw - 1) / hw;
     for (int i = tid; i < hw * hh; i += NT) {
-      int r = i / hw, xi = i - r * hw;
+      int r = (int)(((unsigned)i * m_hw) >> 20), xi = i - r * hw;
       const int16_t* p = &S.R[r * SM::RP + xi];          // taps: picture columns (xi-1)-3 .. (xi-1)+4 = R columns xi .. xi+7
       int t[8];
 #pragma unroll
@@ -1217,21 +1221,23 @@ k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ j
   const VRound vr = make_vround(bd);
   const bool t8 = jb.hadamard && ((w & 7) == 0) && ((h & 7) == 0);
   const int TS = t8 ? 8 : 4;
-  const int tiles_x = w / TS, tiles = tiles_x * (h / TS);
-  const int groups = NT / TS, ug = tid / TS, c = tid % TS;
+  const int tiles_x = t8 ? (w >> 3) : (w >> 2), tiles = tiles_x * (t8 ? (h >> 3) : (h >> 2));
+  const int groups = t8 ? NT / 8 : NT / 4, ug = t8 ? (tid >> 3) : (tid >> 2), c = t8 ? (tid & 7) : (tid & 3);
+  const unsigned m_tiles = ((1u << 20) + tiles - 1) / tiles, m_tx = ((1u << 20) + tiles_x - 1) / tiles_x;
   int basex = 0, basey = 0, hx = 0, hy = 0;
   uint32_t cost_half = 0;
   for (int pass = 0; pass < 2; pass++) {
     const int dq = pass == 0 ? 2 : 1;
     if (live) {
       const int units = 3 * tiles;
-      const int iters = (units + groups - 1) / groups;      // rounded up: every lane of a warp executes the shuffles
+      const int iters = t8 ? (units + NT / 8 - 1) / (NT / 8) : (units + NT / 4 - 1) / (NT / 4);      // rounded up: every lane of a warp executes the shuffles
       for (int it = 0; it < iters; it++) {
         const int u = it * groups + ug;
         const bool valid = u < units;
         const int uu = valid ? u : 0;
-        const int fxi = uu / tiles, t = uu - fxi * tiles;
-        const int tyy = (t / tiles_x) * TS, txx = (t % tiles_x) * TS;
+        const int fxi = (int)(((unsigned)uu * m_tiles) >> 20), t = uu - fxi * tiles;
+        const int trow = (int)(((unsigned)t * m_tx) >> 20);
+        const int tyy = trow * TS, txx = (t - trow * tiles_x) * TS;
         const int ox = fxi - 1;
         uint32_t v[3];
         if (t8) frac_unit<8, SM::CP>(&S.H[0][0], SM::HC * SM::CP, S.org, MAXW, basex + ox * dq, basey, dq, txx, tyy, c, true, vr, v);
