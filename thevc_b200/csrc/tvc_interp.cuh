@@ -6,7 +6,7 @@
 namespace tvc {
 
 // HEVC interpolation taps (H.265 8.5.3.3.3; reference: TComInterpolationFilter.cpp:55-73)
-static __constant__ int8_t c_luma_taps[4][8] = {
+static __constant__ __align__(8) int8_t c_luma_taps[4][8] = {
   {  0, 0,   0, 64,  0,   0, 0,  0 },
   { -1, 4, -10, 58, 17,  -5, 1,  0 },
   { -1, 4, -11, 40, 40, -11, 4, -1 },

@@ -1089,9 +1089,9 @@ __device__ __forceinline__ int vround_copy(int smp, const VRound& v)
 // 8 luma taps of fraction g packed as signed bytes: TA = c0..c3, TB = c4..c7 (operands of dp2a.lo / dp2a.hi)
 __device__ __forceinline__ void packed_taps(int g, int& ta, int& tb)
 {
-  const int8_t* cf = c_luma_taps[g];
-  ta = (cf[0] & 0xff) | ((cf[1] & 0xff) << 8) | ((cf[2] & 0xff) << 16) | ((int)cf[3] << 24);
-  tb = (cf[4] & 0xff) | ((cf[5] & 0xff) << 8) | ((cf[6] & 0xff) << 16) | ((int)cf[7] << 24);
+  // c_luma_taps is int8[4][8], 8-byte aligned: the eight taps of a fraction are two little-endian words already
+  const int2 t = reinterpret_cast<const int2*>(c_luma_taps)[g];
+  ta = t.x; tb = t.y;
 }
 
 template <int TS, int CP>
