@@ -601,6 +601,40 @@ def test_me_frac(ctx8, ctx10, orc, bd):
             (j.x, j.y, j.w, j.h, j.imvx, j.imvy, j.hadamard)
 
 
+def test_me_frac_bipred_target_range(ctx8, orc):
+    """fractional search on an 8-bit bi-prediction target (2 * org - pred: -255 .. 510), extremes included: the two-candidates-
+    per-Hadamard path keeps every coefficient inside int16 (64 * 510), and content beyond that range takes the single path"""
+    t = ctx8
+    rng = np.random.default_rng(91)
+    from thevc_b200.tlibcuda import HostPic
+    ref = _pic(rng, 8)
+    for case in range(2):
+        cur = HostPic(W, H)
+        lo, hi = (-255, 510) if case == 0 else (-2000, 2000)
+        cur.y[:] = rng.integers(lo, hi + 1, cur.y.shape).astype(np.int16)
+        cur.y[0:64, 0:64] = hi                    # saturated blocks against whatever the reference holds
+        cur.y[64:128, 0:64] = lo
+        cur.extend_border()
+        t.upload(0, cur); t.upload(1, ref)
+        pus = _ctu_pus()
+        lc = orc.orc_lambda_motion_sad(33.0)
+        jobs = []
+        for i in range(120):
+            ctu = int(rng.integers(0, t.ctus_x * (t.ctus_y - 1))) if i >= 26 else (0 if i < 13 else t.ctus_x)
+            cx0, cy0 = (ctu % t.ctus_x) * 64, (ctu // t.ctus_x) * 64
+            px, py, w, h = pus[i % 13] if i < 26 else pus[int(rng.integers(0, len(pus)))]
+            imvx, imvy = (int(v) for v in rng.integers(-12, 13, 2))
+            jobs.append(FracJob(1, cx0 + px, cy0 + py, w, h, imvx, imvy, int(rng.integers(-40, 41)), int(rng.integers(-40, 41)), lc, 1))
+        got = t.me_frac_batch(0, jobs)
+        for j, g in zip(jobs, got):
+            e = oracle.FracResult()
+            orc.orc_frac_search(optr(cur.buf_y, cur.origin(0) + j.y * cur.stride + j.x), cur.stride,
+                                optr(ref.buf_y, ref.origin(0) + j.y * ref.stride + j.x), ref.stride, j.w, j.h,
+                                j.imvx, j.imvy, 1, 0, 8, j.lambda_cost, j.predx, j.predy, C.byref(e))
+            assert (g.halfx, g.halfy, g.qtrx, g.qtry, g.cost_half, g.cost) == (e.halfx, e.halfy, e.qtrx, e.qtry, e.cost_half, e.cost), \
+                (case, j.x, j.y, j.w, j.h)
+
+
 # ----------------------------------------------------------------------------------- transform / quant
 def _tu_list(rng, bd, n_per_size=40):
     """non-overlapping TUs over the three planes, grouped by ascending size"""

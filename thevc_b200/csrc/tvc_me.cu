@@ -1034,6 +1034,40 @@ __device__ __forceinline__ int refine_index(bool half, int ox, int oy)
   return (int)(((half ? th : tq) >> (4 * key)) & 15);
 }
 
+// Two difference tiles through ONE Hadamard: P = dB * 65536 + dA is exact integer arithmetic under the butterflies (they are
+// linear), and for 8-bit content every coefficient stays inside int16 (|.| <= 64 * 510 = 32640 even for bi-prediction targets), so the two results are
+// recovered exactly from the halves.  One third of the fractional search's Hadamard work disappears (3 candidates -> 2 passes).
+template <int TS>
+__device__ __forceinline__ void had_cols2(const int (&dA)[TS], const int (&dB)[TS], int c, uint32_t& outA, uint32_t& outB)
+{
+  int d[TS];
+#pragma unroll
+  for (int r = 0; r < TS; r++) d[r] = dB[r] * 65536 + dA[r];
+#pragma unroll
+  for (int len = 1; len < TS; len <<= 1)
+#pragma unroll
+    for (int i = 0; i < TS; i += 2 * len)
+#pragma unroll
+      for (int k = i; k < i + len; k++) { int a = d[k], b = d[k + len]; d[k] = a + b; d[k + len] = a - b; }
+#pragma unroll
+  for (int m = 1; m < TS; m <<= 1) {
+    const int sgn = (c & m) ? -1 : 1;
+#pragma unroll
+    for (int r = 0; r < TS; r++) d[r] = __shfl_xor_sync(0xffffffffu, d[r], m) + sgn * d[r];
+  }
+  uint32_t sa = 0, sb = 0;
+#pragma unroll
+  for (int r = 0; r < TS; r++) {
+    const int lo = (int)(int16_t)(d[r] & 0xffff);
+    sa = __sad(lo, 0, sa);
+    sb = __sad((d[r] - lo) >> 16, 0, sb);
+  }
+#pragma unroll
+  for (int m = 1; m < TS; m <<= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, m); sb += __shfl_xor_sync(0xffffffffu, sb, m); }
+  outA = TS == 8 ? ((sa + 2) >> 2) : ((sa + 1) >> 1);
+  outB = TS == 8 ? ((sb + 2) >> 2) : ((sb + 1) >> 1);
+}
+
 template <int TS>
 __device__ __forceinline__ uint32_t had_cols(int (&d)[TS], int c)
 {
@@ -1064,7 +1098,7 @@ __device__ __forceinline__ uint32_t had_cols(int (&d)[TS], int c)
 // second-stage rounding of TComInterpolationFilter::filter (isFirst = false, isLast = true,
 // TComInterpolationFilter.cpp:204-238) and of filterCopy (:124-145) with the shifts / offsets of the job's
 // bit depth folded into constants: (Short)((sum + offset) >> shift), then clip to [0, maxv]
-struct VRound { int shift, offset, cshift, coffset, maxv; };
+struct VRound { int shift, offset, cshift, coffset, maxv; bool pack2; };
 __device__ __forceinline__ VRound make_vround(int bd)
 {
   VRound v;
@@ -1072,6 +1106,7 @@ __device__ __forceinline__ VRound make_vround(int bd)
   v.shift = kIfFilt + head; v.offset = (1 << (v.shift - 1)) + (kIfOffs << kIfFilt);
   v.cshift = head; v.coffset = kIfOffs + (head ? (1 << (head - 1)) : 0);
   v.maxv = (1 << bd) - 1;
+  v.pack2 = false;
   return v;
 }
 // The reference casts to Short before clipping.  Here the operands are this kernel's own first-stage
@@ -1112,12 +1147,11 @@ __device__ __forceinline__ void frac_unit(const int16_t* __restrict__ H, int pla
   int o[TS];
 #pragma unroll
   for (int r = 0; r < TS; r++) o[r] = org[(ty + r) * opitch + tx + c];
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
+  // difference column of candidate k (fy = fy0 + (k - 1) * dq)
+  auto diff = [&](int k, int (&d)[TS]) {
     const int fy = fy0 + (k - 1) * dq;
     const bool up = fy < 0;                                                  // row shift -1
     const int g = fy & 3;
-    int d[TS];
     // fy is the same for every thread of the CTA (it depends on the pass and on k only): uniform branches
     if (g == 0) {
       // integer row: the reference takes the filterCopy branch (TComInterpolationFilter.cpp:124-145); fy == 0 has
@@ -1144,6 +1178,21 @@ __device__ __forceinline__ void frac_unit(const int16_t* __restrict__ H, int pla
         d[r] = o[r] - vround_filter(sum, vr);
       }
     }
+  };
+  if (hadamard && vr.pack2) {
+    // 8-bit content: candidates 0 and 1 share one Hadamard (had_cols2), candidate 2 takes its own
+    int d0[TS], d1[TS];
+    diff(0, d0);
+    diff(1, d1);
+    had_cols2<TS>(d0, d1, c, out[0], out[1]);
+    diff(2, d0);
+    out[2] = had_cols<TS>(d0, c);
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    int d[TS];
+    diff(k, d);
     if (hadamard) out[k] = had_cols<TS>(d, c);
     else {
       uint32_t s = 0;
@@ -1178,6 +1227,7 @@ k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ j
   }
   const int w = live ? jb.w : 4, h = live ? jb.h : 4, bi = bd - 8;
   const int gstride = pt.stride[0];
+  int wide = 0;
   if (live) {
     const int16_t* ref = pt.org[jb.ref_slot][0] + (ptrdiff_t)(jb.y + jb.imvy - 4) * gstride + jb.x + jb.imvx - 4;
     const int16_t* cur = pt.org[cur_slot][0] + (ptrdiff_t)jb.y * gstride + jb.x;
@@ -1191,12 +1241,16 @@ k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ j
     }
     for (int i = tid; i < w * h; i += NT) {
       int r = (int)(((unsigned)i * m_w) >> 20), x = i - r * w;
-      S.org[r * MAXW + x] = cur[(ptrdiff_t)r * gstride + x];
+      const int16_t ov = cur[(ptrdiff_t)r * gstride + x];
+      S.org[r * MAXW + x] = ov;
+      wide |= (ov < -255) | (ov > 510);        // beyond an 8-bit bi-prediction target (2 * org - pred): |d| could exceed 510
     }
     if (tid < 12) S.cost[tid] = 0;
+    if (tid == 0) S.sel[2] = 0;
   }
   sync();
   if (live) {
+    if (wide) S.sel[2] = 1;                    // every writer stores the same value; read after the next barrier
     // horizontal stage (isFirst, !isLast): H[f][r][xi], xi = 0..w <-> picture column xi-1, r = 0..h+7 <-> row r-4
     const int hw = w + 1, hh = h + 8;
     const unsigned m_hw = ((1u << 20) + hw - 1) / hw;
@@ -1218,7 +1272,10 @@ k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ j
   }
   sync();
 
-  const VRound vr = make_vround(bd);
+  VRound vr = make_vround(bd);
+  // two candidates per Hadamard pass need every coefficient inside int16: |d| <= 510 (64 * 510 = 32640), i.e. 8-bit content
+  // including bi-prediction targets
+  vr.pack2 = bd == 8 && live && S.sel[2] == 0;
   const bool t8 = jb.hadamard && ((w & 7) == 0) && ((h & 7) == 0);
   const int TS = t8 ? 8 : 4;
   const int tiles_x = t8 ? (w >> 3) : (w >> 2), tiles = tiles_x * (t8 ? (h >> 3) : (h >> 2));
