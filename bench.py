@@ -177,6 +177,16 @@ class Workload:
         self.rtus = make_rdoq_list(self.tus, self.lam_luma, self.lam_chroma)
         self.est = rdoq_cases.make_est(np.random.default_rng(seed + 2))      # oracle.EstBits == tvc_est_bits layout
         self.est_bytes = np.frombuffer(bytes(self.est), np.uint8).copy()
+        if pinned:      # the lists a host builds per picture live in page-locked memory too (copied to the device where they lie)
+            import torch
+
+            def pin(a):
+                t = torch.zeros(a.nbytes, dtype=torch.uint8).pin_memory()
+                self._keep.append(t)
+                v = t.numpy().view(a.dtype).reshape(a.shape)
+                v[...] = a
+                return v
+            self.pus, self.tus, self.rtus, self.est_bytes, self.pred = (pin(a) for a in (self.pus, self.tus, self.rtus, self.est_bytes, self.pred))
 
     def pic_bytes(self):
         p = self.pics[0]

@@ -16,6 +16,7 @@ namespace tvc {
 constexpr int kNumSM = 148;          // B200
 constexpr int kMaxSlots = 32;
 constexpr int kMaxRefs = 16;
+constexpr int kMaxPipeChunks = 8;   // CTU-row chunks per reference of the pipelined frame pre-pass
 
 // Device-resident TComPicYuv: int16 planes with margins (TComPicYuv.cpp:71-127) and, for 8-bit
 // content, a packed u8 copy of luma for the integer-ME SIMD path.
@@ -81,6 +82,9 @@ struct tvc_ctx {
   // dedicated pinned staging of the asynchronous ME entry points (an event guards host reuse)
   tvc::Scratch me_stage, fr_stage;
   cudaEvent_t me_ev = nullptr, fr_ev = nullptr;
+  // pipelined frame pre-pass: search stream, fractional-search stream, per-chunk events
+  cudaStream_t pipe[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> pipe_ev;
   // per-phase timing (tvc_prof_*)
   bool prof_on = false;
   struct ProfPair { int phase; cudaEvent_t a, b; };

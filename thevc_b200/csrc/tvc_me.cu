@@ -211,13 +211,13 @@ __device__ __forceinline__ void sad_task_wo(int wo, const uint8_t* win, const ui
 template <int DYB, int MINB, bool ROWS = false>   // DYB consecutive dy per lane (register window), MINB resident CTAs per SM compiled
 __global__ void __launch_bounds__(256, MINB)       // for, ROWS: row-split lane mapping of the bulk tasks (256-byte store runs)
 k_me_sad_tables(const __grid_constant__ MeMaps maps, int num_ctus, int ctus_x, int mx, int my,
-                const tvc_me_center* __restrict__ centers, uint16_t* __restrict__ tables)
+                const tvc_me_center* __restrict__ centers, uint16_t* __restrict__ tables, int ctu0, int ref0)
 {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* win = smem;
   uint8_t* cur = smem + kSmemWin;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kSmemWin + kSmemCur);
-  const int ctu = blockIdx.x, ref = blockIdx.y;
+  const int ctu = blockIdx.x + ctu0, ref = blockIdx.y + ref0;     // (ctu0, ref0): first unit of a pipelined chunk
   const int cx0 = (ctu % ctus_x) * 64, cy0 = (ctu / ctus_x) * 64;
   const tvc_me_center cen = centers[(size_t)ref * num_ctus + ctu];
 
@@ -724,7 +724,7 @@ template <bool SWEEP>            // true: stage (a) only, false: stage (b) only 
 __global__ void __launch_bounds__(kRastThreads)
 k_me_raster(const tvc_me_job* __restrict__ jobs, const uint16_t* __restrict__ tables, const tvc_me_center* __restrict__ centers,
             int num_ctus, int raster, int bi, RasterBest* __restrict__ out, SweepState* __restrict__ sweep_out,
-            unsigned long long* __restrict__ stats)
+            unsigned long long* __restrict__ stats, int ctu0, int ref0)
 {
   __shared__ uint32_t IE[kRastChunk][17 * 17];  // integral of even-row block SADs
   __shared__ uint32_t IA[kRastChunk][17 * 17];  // integral of even+odd
@@ -733,7 +733,7 @@ k_me_raster(const tvc_me_job* __restrict__ jobs, const uint16_t* __restrict__ ta
   __shared__ uint8_t s_cvalid[kSweepMax], s_cpt[kSweepMax], s_cfirst[kSweepMax], s_clast[kSweepMax];
   __shared__ uint32_t s_cdist[kSweepMax], s_cmv[kSweepMax];
   __shared__ int s_sweep_ok;
-  const int ctu = blockIdx.x, ref = blockIdx.y, tid = threadIdx.x;
+  const int ctu = blockIdx.x + ctu0, ref = blockIdx.y + ref0, tid = threadIdx.x;
   const size_t rc = (size_t)ref * num_ctus + ctu;
   const tvc_me_job* jb0 = jobs + rc * TVC_ME_CENSUS;
   const tvc_me_job j0 = jb0[0];                  // the 64x64 PU: its window is the CTU's
@@ -1580,7 +1580,22 @@ int tvc_me_reserve(tvc_ctx* c, int num_refs)
   return TVC_OK;
 }
 
-int tvc_me_prepass(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slots, const tvc_me_center* centers)
+// side streams + events of the pipelined frame pre-pass (created on first use)
+static int ensure_pipe(tvc_ctx* c)
+{
+  if (c->pipe[0]) return TVC_OK;
+  int least = 0, greatest = 0;
+  TVC_CUDA(c, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  const int mid = greatest + 1 <= least ? greatest + 1 : greatest;
+  TVC_CUDA(c, cudaStreamCreateWithPriority(&c->pipe[0], cudaStreamNonBlocking, mid));
+  TVC_CUDA(c, cudaStreamCreateWithPriority(&c->pipe[1], cudaStreamNonBlocking, greatest));
+  c->pipe_ev.resize(1 + 2 * kMaxPipeChunks * 8);
+  for (auto& e : c->pipe_ev) TVC_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return TVC_OK;
+}
+
+// allocation, argument checks and the upload of the clamped table centres: everything of the pre-pass but the kernel
+static int prepass_prepare(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slots, const tvc_me_center* centers)
 {
   if (!c || !valid_slot(c, cur_slot) || num_refs <= 0 || num_refs > 8 || !ref_slots)
     return set_err(c, TVC_ERR_ARG, "tvc_me_prepass: bad argument (1..8 references)");
@@ -1616,10 +1631,21 @@ int tvc_me_prepass(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slots,
     }
   TVC_CUDA(c, cudaMemcpyAsync(c->me_centers, hc, sizeof(tvc_me_center) * (size_t)num_refs * nctu, cudaMemcpyHostToDevice, c->stream));
   TVC_CUDA(c, cudaEventRecord(c->me_ev, c->stream));
+  c->me_num_refs = num_refs;
+  c->me_cur_slot = cur_slot;
+  for (int rf = 0; rf < num_refs; rf++) c->me_ref_slots[rf] = ref_slots[rf];
+  return TVC_OK;
+}
+
+// SAD tables of CTUs [ctu0, ctu0 + nct) x references [ref0, ref0 + nrf) of the prepared pre-pass, on c->stream
+static int launch_tables(tvc_ctx* c, int ctu0, int nct, int ref0, int nrf)
+{
+  const int nctu = c->num_ctus_x * c->num_ctus_y;
+  const Pic& p = c->pics[c->me_cur_slot];
   MeMaps maps;
   memset(&maps, 0, sizeof(maps));
-  maps.cur = c->pics[cur_slot].tmap_cur;
-  for (int rf = 0; rf < num_refs; rf++) maps.ref[rf] = c->pics[ref_slots[rf]].tmap_ref;
+  maps.cur = p.tmap_cur;
+  for (int rf = 0; rf < c->me_num_refs; rf++) maps.ref[rf] = c->pics[c->me_ref_slots[rf]].tmap_ref;
   // tuning knob (measured on B200, ms per 1080p picture x 4 references): 81 = row-split lane mapping, 8-row window, 2 CTAs/SM:
   // 5.4 (default); 8 = column mapping (64-byte store pieces): 7.0; 4 / 43 = 4-row window at 4 / 3 CTAs/SM: 7.4 / 7.0; 41: 6.6
   static int variant = -1;
@@ -1632,18 +1658,22 @@ int tvc_me_prepass(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slots,
     TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables));
     TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<4, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables));
   }
-  dim3 grd(nctu, num_refs);
+  dim3 grd(nct, nrf);
   ProfScope ps(c, TVC_PH_ME_TABLES);
-  if (variant == 4) k_me_sad_tables<4, 4><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables);
-  else if (variant == 43) k_me_sad_tables<4, 3><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables);
-  else if (variant == 81) k_me_sad_tables<8, 2, true><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables);
-  else if (variant == 41) k_me_sad_tables<4, 3, true><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables);
-  else k_me_sad_tables<8, 2><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables);
+  if (variant == 4) k_me_sad_tables<4, 4><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables, ctu0, ref0);
+  else if (variant == 43) k_me_sad_tables<4, 3><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables, ctu0, ref0);
+  else if (variant == 81) k_me_sad_tables<8, 2, true><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables, ctu0, ref0);
+  else if (variant == 41) k_me_sad_tables<4, 3, true><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables, ctu0, ref0);
+  else k_me_sad_tables<8, 2><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables, ctu0, ref0);
   TVC_LAUNCH_CHECK(c);
-  c->me_num_refs = num_refs;
-  c->me_cur_slot = cur_slot;
-  for (int rf = 0; rf < num_refs; rf++) c->me_ref_slots[rf] = ref_slots[rf];
   return TVC_OK;
+}
+
+int tvc_me_prepass(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slots, const tvc_me_center* centers)
+{
+  int r = prepass_prepare(c, cur_slot, num_refs, ref_slots, centers);
+  if (r) return r;
+  return launch_tables(c, 0, c->num_ctus_x * c->num_ctus_y, 0, num_refs);
 }
 
 int tvc_me_tables_dev(tvc_ctx* c, void** tables, tvc_me_center** centers_dev)
@@ -1837,7 +1867,15 @@ int tvc_me_frame_dev(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slot
     centers[i].cx = x >> 2; centers[i].cy = y >> 2;
   }
   for (int k = 0; k < num_refs; k++) hslots[k] = ref_slots[k];
-  if (cfg->use_tables && (r = tvc_me_prepass(c, cur_slot, num_refs, ref_slots, centers.data()))) return r;
+  // Pipelined form (TVC_ME_PIPE=<chunks of CTU rows per reference>, off by default): the SAD tables of chunk k+1 (c->stream) run beside
+  // the raster + search of chunk k (pipe[0]) and the fractional search of chunk k-1 (pipe[1]; side streams at higher priority).
+  // Measured on B200 (1080p, 4 references): serial 19.8 ms, 1 / 2 / 4 chunks 20.4 / 20.9 / 21.8 ms with identical results -- the
+  // table kernel needs ~70 % of the integer issue slots to keep HBM saturated and fills the register file (2 x 256 x 128), so a
+  // co-resident CTA only displaces table work and the chunk tails add up.  Kept as a knob; per-phase profiling needs the serial form.
+  static int pipe_chunks = -1;
+  if (pipe_chunks < 0) { const char* e = getenv("TVC_ME_PIPE"); pipe_chunks = e ? atoi(e) : 0; if (pipe_chunks > kMaxPipeChunks) pipe_chunks = kMaxPipeChunks; }
+  const bool piped = cfg->use_tables && pipe_chunks > 0 && !c->prof_on;
+  if (cfg->use_tables && (r = prepass_prepare(c, cur_slot, num_refs, ref_slots, centers.data()))) return r;
   TVC_CUDA(c, cudaMemcpyAsync(c->fr_stage.dev, c->fr_stage.host, np * sizeof(tvc_me_center) + num_refs * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   TVC_CUDA(c, cudaEventRecord(c->fr_ev, c->stream));
   const tvc_me_center* dpred = (const tvc_me_center*)c->fr_stage.dev;
@@ -1849,33 +1887,87 @@ int tvc_me_frame_dev(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slot
   }
   if (!c->fr_stats) TVC_CUDA(c, cudaMalloc(&c->fr_stats, 3 * sizeof(unsigned long long)));
   TVC_CUDA(c, cudaMemsetAsync(c->fr_stats, 0, 3 * sizeof(unsigned long long), c->stream));
-  const RasterBest* rast = nullptr;
-  const SweepState* sweep = nullptr;
   static int use_rast = -1, use_sweep = -1;      // tuning knobs (TVC_ME_RASTER=0 / TVC_ME_SWEEP=0: every PU on its own)
   if (use_rast < 0) { const char* e = getenv("TVC_ME_RASTER"); use_rast = e ? atoi(e) : 1; }
   if (use_sweep < 0) { const char* e = getenv("TVC_ME_SWEEP"); use_sweep = e ? atoi(e) : 1; }
-  if (cfg->use_tables && use_rast) {
-    ProfScope ps(c, TVC_PH_ME_RASTER);
-    dim3 grd(nctu, num_refs);
-    if (use_sweep) {
-      k_me_raster<true><<<grd, kRastThreads, 0, c->stream>>>(c->fr_jobs, c->me_tables, c->me_centers, nctu, 5, c->bi, (RasterBest*)c->fr_rast,
-                                                             (SweepState*)c->fr_sweep, c->fr_stats);
+  // raster + first sweep + TZ search of the jobs of CTUs [ctu0, ctu0 + nct) x references [ref0, ref0 + nrf) on c->stream
+  auto search_part = [&](int ctu0, int nct, int ref0) -> int {
+    const RasterBest* rast = nullptr;
+    const SweepState* sweep = nullptr;
+    if (cfg->use_tables && use_rast) {
+      dim3 grd(nct, 1);
+      if (use_sweep) {
+        k_me_raster<true><<<grd, kRastThreads, 0, c->stream>>>(c->fr_jobs, c->me_tables, c->me_centers, nctu, 5, c->bi, (RasterBest*)c->fr_rast,
+                                                               (SweepState*)c->fr_sweep, c->fr_stats, ctu0, ref0);
+        TVC_LAUNCH_CHECK(c);
+      }
+      k_me_raster<false><<<grd, kRastThreads, 0, c->stream>>>(c->fr_jobs, c->me_tables, c->me_centers, nctu, 5, c->bi, (RasterBest*)c->fr_rast,
+                                                              nullptr, c->fr_stats, ctu0, ref0);
       TVC_LAUNCH_CHECK(c);
+      rast = (const RasterBest*)c->fr_rast;
+      if (use_sweep) sweep = (const SweepState*)c->fr_sweep;
     }
-    k_me_raster<false><<<grd, kRastThreads, 0, c->stream>>>(c->fr_jobs, c->me_tables, c->me_centers, nctu, 5, c->bi, (RasterBest*)c->fr_rast,
-                                                            nullptr, c->fr_stats);
-    TVC_LAUNCH_CHECK(c);
-    rast = (const RasterBest*)c->fr_rast;
-    if (use_sweep) sweep = (const SweepState*)c->fr_sweep;
-  }
-  if ((r = launch_search(c, cur_slot, cfg->use_tables, (int)n, c->fr_jobs, c->fr_int, rast, sweep, c->fr_stats))) return r;
-  if (cfg->do_frac) {
+    const size_t off = ((size_t)ref0 * nctu + ctu0) * TVC_ME_CENSUS;      // jobs of one reference's CTU range are contiguous
+    return launch_search(c, cur_slot, cfg->use_tables, nct * TVC_ME_CENSUS, c->fr_jobs + off, c->fr_int + off,
+                         rast ? rast + off : nullptr, sweep ? sweep + off : nullptr, c->fr_stats);
+  };
+  auto frac_part = [&](size_t off, size_t cnt) -> int {
     {
       ProfScope ps(c, TVC_PH_OTHER);
-      k_me_frame_frac_jobs<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((int)n, c->fr_jobs, c->fr_int, cfg->hadamard, c->fr_fjobs);
+      k_me_frame_frac_jobs<<<(unsigned)((cnt + 255) / 256), 256, 0, c->stream>>>((int)cnt, c->fr_jobs + off, c->fr_int + off, cfg->hadamard, c->fr_fjobs + off);
       TVC_LAUNCH_CHECK(c);
     }
-    if ((r = launch_frac(c, cur_slot, (int)n, c->fr_fjobs, c->fr_frac, true))) return r;
+    return launch_frac(c, cur_slot, (int)cnt, c->fr_fjobs + off, c->fr_frac + off, true);
+  };
+  if (!piped) {
+    if (cfg->use_tables && (r = launch_tables(c, 0, nctu, 0, num_refs))) return r;
+    if (cfg->use_tables && use_rast) {
+      ProfScope ps(c, TVC_PH_ME_RASTER);
+      dim3 grd(nctu, num_refs);
+      if (use_sweep) {
+        k_me_raster<true><<<grd, kRastThreads, 0, c->stream>>>(c->fr_jobs, c->me_tables, c->me_centers, nctu, 5, c->bi, (RasterBest*)c->fr_rast,
+                                                               (SweepState*)c->fr_sweep, c->fr_stats, 0, 0);
+        TVC_LAUNCH_CHECK(c);
+      }
+      k_me_raster<false><<<grd, kRastThreads, 0, c->stream>>>(c->fr_jobs, c->me_tables, c->me_centers, nctu, 5, c->bi, (RasterBest*)c->fr_rast,
+                                                              nullptr, c->fr_stats, 0, 0);
+      TVC_LAUNCH_CHECK(c);
+    }
+    const bool shared = cfg->use_tables && use_rast;
+    if ((r = launch_search(c, cur_slot, cfg->use_tables, (int)n, c->fr_jobs, c->fr_int, shared ? (const RasterBest*)c->fr_rast : nullptr,
+                           shared && use_sweep ? (const SweepState*)c->fr_sweep : nullptr, c->fr_stats))) return r;
+    if (cfg->do_frac && (r = frac_part(0, n))) return r;
+  } else {
+    if ((r = ensure_pipe(c))) return r;
+    cudaStream_t main_stream = c->stream;
+    struct Restore { tvc_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{c, main_stream};
+    TVC_CUDA(c, cudaEventRecord(c->pipe_ev[0], main_stream));            // jobs, centres, counters ready
+    TVC_CUDA(c, cudaStreamWaitEvent(c->pipe[0], c->pipe_ev[0], 0));
+    const int rows = c->num_ctus_y, parts = pipe_chunks < rows ? pipe_chunks : rows;
+    int k = 0;
+    for (int rf = 0; rf < num_refs; rf++)
+      for (int pt = 0; pt < parts; pt++, k++) {
+        const int y0 = rows * pt / parts, y1 = rows * (pt + 1) / parts;
+        const int ctu0 = y0 * c->num_ctus_x, nct = (y1 - y0) * c->num_ctus_x;
+        if (nct <= 0) continue;
+        cudaEvent_t ev_t = c->pipe_ev[1 + 2 * k], ev_s = c->pipe_ev[2 + 2 * k];
+        c->stream = main_stream;
+        if ((r = launch_tables(c, ctu0, nct, rf, 1))) return r;
+        TVC_CUDA(c, cudaEventRecord(ev_t, main_stream));
+        TVC_CUDA(c, cudaStreamWaitEvent(c->pipe[0], ev_t, 0));
+        c->stream = c->pipe[0];
+        if ((r = search_part(ctu0, nct, rf))) return r;
+        if (cfg->do_frac) {
+          TVC_CUDA(c, cudaEventRecord(ev_s, c->pipe[0]));
+          TVC_CUDA(c, cudaStreamWaitEvent(c->pipe[1], ev_s, 0));
+          c->stream = c->pipe[1];
+          if ((r = frac_part(((size_t)rf * nctu + ctu0) * TVC_ME_CENSUS, (size_t)nct * TVC_ME_CENSUS))) return r;
+        }
+      }
+    c->stream = main_stream;
+    cudaStream_t last = cfg->do_frac ? c->pipe[1] : c->pipe[0];
+    TVC_CUDA(c, cudaEventRecord(c->pipe_ev[0], last));                    // the side streams are in order: their last event covers all
+    TVC_CUDA(c, cudaStreamWaitEvent(main_stream, c->pipe_ev[0], 0));
   }
   if (int_dev) *int_dev = c->fr_int;
   if (frac_dev) *frac_dev = cfg->do_frac ? c->fr_frac : nullptr;
