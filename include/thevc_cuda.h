@@ -436,12 +436,45 @@ typedef struct {
 /* units: one per CTU in raster order (host array); samples of CTUs with type < 0 are copied                        */
 int tvc_sao_plane(tvc_ctx* ctx, int src_slot, int dst_slot, int plane, const tvc_sao_unit* units);
 
+/* ---------------------------------------------------------------------------------- intra 35-mode rough search
+ * SURVEY.md 8(f)-2.  Replaces the per-mode body of the rough search in TEncSearch::estIntraPredQT
+ * (TLibEncoder/TEncSearch.cpp:2530-2537): TComPrediction::predIntraLumaAng (TLibCommon/TComPrediction.cpp:337-366 ->
+ * xPredIntraPlanar :689-731, xPredIntraAng :186-335, predIntraGetPredValDC :127-165, xDCPredFiltering :1010-1031) on
+ * the reference samples TComPattern::initAdiPattern prepared (TLibCommon/TComPattern.cpp:213-307, including its
+ * [1 2 1] smoothing; which modes read the smoothed samples: getPredictorPtr :577-605) followed by TComRdCost::calcHAD
+ * (TLibCommon/TComRdCost.cpp:404-447), for all 35 modes of an N x N luma PU at once.  The neighbour substitution
+ * (fillReferenceSamples, TComPattern.cpp:368-552) depends on the CU tree and stays host work; so do the mode bits
+ * (xModeBitsIntra: CABAC state) and the candidate list (xUpdateCandList): the host adds bits * sqrt(lambda) to the
+ * returned SATDs in its own loop, in mode order, exactly as before.
+ * Reference samples travel as ONE LINE of 4N+1 Pels per PU, in the order initAdiPattern walks them (:277-288):
+ * left column from the bottom-left sample upwards (2N), the top-left corner, the row above from left to above-right
+ * (2N) -- i.e. column 0 (bottom to top) and row 0 of the reference's (2N+1)x(2N+1) m_piYuvExt array, UNFILTERED.   */
+typedef struct {
+  int32_t log2_size;           /* 2..6: N = 4..64 (64: the 2Nx2N PU of a 64x64 CU)                                 */
+  int32_t line_offset;         /* element offset of the PU's 4N+1 reference samples in `lines`                     */
+  int32_t org_offset;          /* element offset of the PU's original block in `org`                               */
+  int32_t org_stride;          /* elements                                                                         */
+  int32_t above, left;         /* bAbove / bLeft as predIntraLumaAng receives them (initAdiPattern sets both)      */
+} tvc_intra_job;
+#define TVC_INTRA_MODES 35
+/* sad[35 * i + mode] = calcHAD(org, prediction of `mode`) of job i (already >> bitIncrement); host arrays          */
+int tvc_intra_rough_batch(tvc_ctx* ctx, int n, const tvc_intra_job* jobs, const int16_t* lines, size_t line_elems,
+                          const int16_t* org, size_t org_elems, uint32_t* sad);
+/* the same on device-resident arrays, asynchronous on the context stream; preds_dev (optional): the 35 predictions of
+ * every job, job i mode m at element pred_offset[i] + m * N * N (pred_offset_dev: n element offsets, device)       */
+int tvc_intra_rough_batch_dev(tvc_ctx* ctx, int n, const tvc_intra_job* jobs_dev, const int16_t* lines_dev,
+                              const int16_t* org_dev, uint32_t* sad_dev, int16_t* preds_dev, const int64_t* pred_offset_dev);
+/* drop-in for ONE estIntraPredQT rough search: 35 SATDs of one PU; preds (optional, host): 35 x N x N predictions,
+ * mode-major = what predIntraLumaAng writes for each mode                                                          */
+int tvc_intra_rough(tvc_ctx* ctx, int log2_size, const int16_t* line, const int16_t* org, int org_stride, int above,
+                    int left, uint32_t sad[TVC_INTRA_MODES], int16_t* preds);
+
 /* ---------------------------------------------------------------------------------- per-phase device timing
  * CUDA events recorded on the context stream around every kernel group, so that bench.py can report
  * each kernel's duration measured live inside the timed region (not under a profiler).         */
 enum {
   TVC_PH_ME_TABLES = 0, TVC_PH_ME_SEARCH = 1, TVC_PH_ME_FRAC = 2, TVC_PH_MC = 3, TVC_PH_FWD_TQ = 4,
-  TVC_PH_INV_TQ = 5, TVC_PH_OTHER = 6, TVC_PH_ME_RASTER = 7, TVC_PH_RDOQ = 8, TVC_PH_DEBLOCK = 9, TVC_PH_COUNT = 10
+  TVC_PH_INV_TQ = 5, TVC_PH_OTHER = 6, TVC_PH_ME_RASTER = 7, TVC_PH_RDOQ = 8, TVC_PH_DEBLOCK = 9, TVC_PH_INTRA = 10, TVC_PH_COUNT = 11
 };
 int tvc_prof_enable(tvc_ctx* ctx, int on);
 /* synchronises the stream, adds the elapsed time of every recorded pair to per-phase sums and returns

@@ -182,6 +182,13 @@ void orc_fwd_rdoq_batch(const Pel* const* resi, int stride_y, int stride_c, int 
 void orc_inv_tq_batch(Pel* const* resi, const Pel* const* pred, Pel* const* recon, int stride_y, int stride_c, int n,
                       const int32_t* tus, int bd, const int32_t* levels);
 
+/* ------------------------------------------------------------------ intra rough search (hm_oracle_intra.c)
+ * line: 4N+1 reference samples (left column bottom to top, corner, row above left to right), see the file header */
+void orc_intra_filter_line(const Pel* line, int n, Pel* out);
+int orc_intra_mode_filtered(int mode, int log2n);
+void orc_intra_pred_luma(const Pel* line, int log2n, int mode, int above, int left, int bd, Pel* dst, int ds);
+void orc_intra_rough(const Pel* line, const Pel* org, int so, int log2n, int above, int left, int bd, uint32_t sad[35], Pel* preds);
+
 #ifdef __cplusplus
 }
 #endif

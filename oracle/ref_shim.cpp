@@ -495,4 +495,34 @@ void ref_add_avg(const short* a_y, const short* a_u, const short* a_v, const sho
   for (int r = 0; r < h / 2; r++) { memcpy(o_u + r * (w / 2), D->getCbAddr() + r * 32, w); memcpy(o_v + r * (w / 2), D->getCrAddr() + r * 32, w); }
 }
 
+/* ==================================================================================== intra rough search
+ * The reference's own predIntraLumaAng (TComPrediction.cpp:337-366, through TComPattern::getPredictorPtr :577-605) and
+ * calcHAD (TComRdCost.cpp:404-447), exactly as estIntraPredQT calls them per mode (TEncSearch.cpp:2530-2537).  The
+ * caller supplies what initAdiPattern leaves in m_piYuvExt: the unfiltered reference line and the smoothed one
+ * (4N+1 samples each: left column bottom to top, corner, row above left to right); initAdiPattern itself needs a
+ * live TComDataCU, its smoothing loop is pinned by the vectors dumped from the running encoder (tests/golden). */
+void ref_intra_rough(const short* line, const short* line_filtered, const short* org, int so, int log2n, int above, int left,
+                     unsigned* sad, short* preds)
+{
+  static TComPrediction* P = 0;
+  static TComPattern pat;
+  if (!P) { P = new TComPrediction; P->initTempBuff(); }
+  const int n = 1 << log2n, sw = 2 * n + 1, wh = sw * sw;
+  Int* adi = P->m_piYuvExt;
+  for (int b = 0; b < 2; b++) {
+    const short* ln = b ? line_filtered : line;
+    Int* a = adi + b * wh;
+    int l = 0;
+    for (int i = 0; i < 2 * n; i++) a[sw * (2 * n - i)] = ln[l++];
+    a[0] = ln[l++];
+    for (int i = 0; i < 2 * n; i++) a[1 + i] = ln[l++];
+  }
+  std::vector<short> tmp((size_t)n * n);
+  for (int mode = 0; mode < 35; mode++) {
+    short* d = preds ? preds + (size_t)mode * n * n : tmp.data();
+    P->predIntraLumaAng(&pat, (UInt)mode, d, (UInt)n, n, n, 0, above != 0, left != 0);
+    sad[mode] = s_rd->calcHAD(const_cast<short*>(org), so, d, n, n, n);
+  }
+}
+
 } /* extern "C" */

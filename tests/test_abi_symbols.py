@@ -34,7 +34,7 @@ def test_library_is_sm100a_and_has_native_kernels():
     from thevc_b200 import capi
     out = subprocess.run(["cuobjdump", "-lelf", capi.lib_path()], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3tvc15k_me_sad_tablesILi8ELi2ELb1EEEvNS_6MeMapsEiiiiPK13tvc_me_centerPt",
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3tvc15k_me_sad_tablesILi8ELi2ELb1EEEvNS_6MeMapsEiiiiPK13tvc_me_centerPtii",
                            capi.lib_path()], capture_output=True, text=True).stdout
     assert "VABSDIFF4" in sass          # u8 SIMD SAD
     assert "UTMALDG" in sass            # TMA staging of the search window

@@ -258,3 +258,23 @@ def test_cuda_reproduces_rdoq_goldens(bd):
                         assert np.array_equal(ga[o:o + nn], g["arl"][o:o + nn]), c
     finally:
         t.close()
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_oracle_reproduces_intra_rough_goldens(orc, bd):
+    """tests/golden/intra_rough.npz: reference samples, original blocks and the 35 uiSad values dumped by the reference
+    encoder's own estIntraPredQT (make_intra_golden.py): pins the reference-sample smoothing + the whole mode loop"""
+    g = np.load(os.path.join(HERE, "golden", "intra_rough.npz"))
+    key = "bd%d" % bd
+    log2s, lines, orgs, sads = g[key + "_log2"], g[key + "_lines"], g[key + "_orgs"], g[key + "_sads"]
+    assert set(int(v) for v in log2s) == {2, 3, 4, 5, 6}
+    lo = oo = 0
+    for i, log2n in enumerate(log2s):
+        n = 1 << int(log2n)
+        line = np.ascontiguousarray(lines[lo:lo + 4 * n + 1])
+        org = np.ascontiguousarray(orgs[oo:oo + n * n])
+        lo += 4 * n + 1; oo += n * n
+        sad = np.zeros(35, np.uint32)
+        orc.orc_intra_rough(ptr(line), ptr(org), n, int(log2n), 1, 1, bd, ptr(sad), None)
+        assert np.array_equal(sad, sads[i]), (i, int(log2n))
+    assert lo == len(lines) and oo == len(orgs)

@@ -137,3 +137,25 @@ def test_census_lookup_serves_the_cu_loop(tmp_path):
     f = line[-1].split()
     served, total = int(f[2]), int(f[4])
     assert total > 10000 and served > 0.8 * total, line[-1]
+
+
+@pytest.mark.parametrize("cfg,frames,w,h", [
+    ("encoder_intra_main.cfg", 2, 416, 240),          # C1: every PU is intra; 8-bit
+    ("encoder_intra_he10.cfg", 1, 416, 240),          # C4 at the CPU-runnable size: 10-bit internal
+    ("encoder_lowdelay_P_main.cfg", 2, 208, 120),     # intra PUs tested inside P pictures
+])
+def test_intra_rough_search_on_device(tmp_path, cfg, frames, w, h):
+    """SURVEY 8f-2 inside the real encoder: the 35-mode rough search of estIntraPredQT served by tvc_intra_rough for
+    EVERY PU size (intra4: also the 4x4 / 8x8 PUs the fast configuration leaves to the host).  A single differing SATD
+    changes a candidate list and with it the bitstream, so an equal md5 pins all of them."""
+    _need()
+    yuv = str(tmp_path / "in.yuv")
+    _yuv(yuv, w, h, frames)
+    ref_bin, cuda_bin = str(tmp_path / "ref.bin"), str(tmp_path / "cuda.bin")
+    _encode(ENC_REF, cfg, yuv, w, h, frames, ref_bin)
+    r = _encode(ENC_CUDA, cfg, yuv, w, h, frames, cuda_bin, env={"TVC_HM": "intra4"})
+    assert _md5(cuda_bin) == _md5(ref_bin)
+    il = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda intra rough search:")]
+    assert il, r.stderr[-600:]
+    print(il[-1])
+    assert int(il[-1].split()[4]) > 500 and " 0 smaller PUs" in il[-1], il[-1]

@@ -480,3 +480,28 @@ def test_me_frame_ctu_against_reference_driver(orc, hmref):
             assert (ires[i].mvx, ires[i].mvy, ires[i].sad) == tuple(int(v) for v in oi[i, :3]), (ctu, i)
             assert (fres[i].halfx, fres[i].halfy, fres[i].qtrx, fres[i].qtry, fres[i].cost) == tuple(int(v) for v in of[i]), (ctu, i)
         assert valid > 300
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_intra_rough_search(orc, hmref, bd):
+    """the restated predIntraLumaAng (planar, DC + edge filter, 33 angular modes with the projected side
+    reference, the pure horizontal / vertical edge filter and its clip) and calcHAD == the reference's own compiled
+    TComPrediction / TComPattern::getPredictorPtr / TComRdCost for every PU size, every mode, sample by sample"""
+    import intra_cases
+    if not hasattr(hmref, "ref_intra_rough"):
+        pytest.skip("libhmref.so predates ref_intra_rough")
+    hmref.ref_init(bd)
+    rng = np.random.default_rng(4242 + bd)
+    for log2n in (2, 3, 4, 5, 6):
+        n = 1 << log2n
+        for kind in intra_cases.KINDS:
+            line, org = intra_cases.make_case(rng, log2n, bd, kind)
+            filt = np.zeros_like(line)
+            orc.orc_intra_filter_line(ptr(line), n, ptr(filt))
+            for above, left in ((1, 1), (1, 0), (0, 1), (0, 0)):
+                osad, opred = intra_cases.oracle_rough(orc, line, org, log2n, bd, above, left, want_preds=True)
+                rsad, rpred = np.zeros(35, np.uint32), np.zeros((35, n, n), np.int16)
+                hmref.ref_intra_rough(ptr(line), ptr(filt), ptr(org), n, log2n, above, left, ptr(rsad), ptr(rpred))
+                bad = [m for m in range(35) if not np.array_equal(opred[m], rpred[m])]
+                assert not bad, (log2n, kind, above, left, bad)
+                assert np.array_equal(osad, rsad)

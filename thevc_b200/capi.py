@@ -75,10 +75,13 @@ class MeFrameCfg(C.Structure):
 
 
 ME_CENSUS = 593
-PHASES = ("me_tables", "me_search", "me_frac", "mc", "fwd_tq", "inv_tq", "other", "me_raster", "rdoq", "deblock")
+PHASES = ("me_tables", "me_search", "me_frac", "mc", "fwd_tq", "inv_tq", "other", "me_raster", "rdoq", "deblock", "intra")
 
 # numpy views of the ABI structs (same layout) for bulk results
 ME_RESULT_DTYPE = np.dtype([("mvx", "<i4"), ("mvy", "<i4"), ("sad", "<u4"), ("n_sads", "<u4")])
+INTRA_MODES = 35
+INTRA_JOB_DTYPE = np.dtype([("log2_size", "<i4"), ("line_offset", "<i4"), ("org_offset", "<i4"), ("org_stride", "<i4"),
+                            ("above", "<i4"), ("left", "<i4")])
 FRAC_RESULT_DTYPE = np.dtype([("halfx", "<i4"), ("halfy", "<i4"), ("qtrx", "<i4"), ("qtry", "<i4"), ("cost_half", "<u4"), ("cost", "<u4")])
 PU_DTYPE = np.dtype([(n, "<i4") for n in ("x", "y", "w", "h", "ref_slot0", "mvx0", "mvy0", "ref_slot1", "mvx1", "mvy1")])
 TU_DTYPE = np.dtype([(n, "<i4") for n in ("plane", "x", "y", "log2_size", "flags", "scan_idx", "qp_per", "qp_rem", "base_per", "coef_offset")])
@@ -165,6 +168,9 @@ SIGNATURES = {
     "tvc_xDeQuant": (ci, [vp, vp, vp, ci, ci, ci, ci]),
     "tvc_deblock_pic": (ci, [vp, ci, vp, vp, ci, ci]),
     "tvc_sao_plane": (ci, [vp, ci, ci, ci, vp]),
+    "tvc_intra_rough_batch": (ci, [vp, ci, vp, vp, C.c_size_t, vp, C.c_size_t, vp]),
+    "tvc_intra_rough_batch_dev": (ci, [vp, ci, vp, vp, vp, vp, vp, vp]),
+    "tvc_intra_rough": (ci, [vp, ci, vp, vp, ci, ci, ci, vp, vp]),
     "tvc_prof_enable": (ci, [vp, ci]),
     "tvc_prof_read": (ci, [vp, vp, vp, ci]),
     "tvc_ubench": (ci, [vp, ci, C.POINTER(C.c_double)]),

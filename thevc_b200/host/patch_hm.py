@@ -39,6 +39,15 @@ def main():
     s = sub_once(s, r'(Void TEncSearch::xPatternSearchFracDIF\(TComDataCU\* pcCU,.*?\n\s*\)\r?\n\{\r?\n)',
                  r'\1  if ( tlibcuda_frac_search( pcPatternKey, piRefY, iRefStride, pcMvInt, rcMvHalf, rcMvQter, ruiCost, m_pcRdCost, m_pcEncCfg, biPred ) ) return;\n',
                  "xPatternSearchFracDIF", flags=re.S)
+    # estIntraPredQT: the 35-mode rough search (predIntraLumaAng + calcHAD per mode) served from one device call per PU
+    s = sub_once(s, r'(\n)([ \t]*for\( Int modeIdx = 0; modeIdx < numModesAvailable; modeIdx\+\+ \)\r?\n)',
+                 r'\1      UInt tvcSad[35];\n      const Bool tvcHave = tlibcuda_intra_rough( m_piYuvExt, uiWidth, piOrg, uiStride, bAboveAvail, bLeftAvail, tvcSad );\n\2',
+                 "estIntraPredQT rough loop")
+    s = sub_once(s, r'(\n[ \t]*)(predIntraLumaAng\( pcCU->getPattern\(\), uiMode, piPred, uiStride, uiWidth, uiHeight, pcCU, bAboveAvail, bLeftAvail \);\r?\n\s*\r?\n\s*// use hadamard transform here\r?\n)',
+                 r'\1if ( !tvcHave ) \2', "estIntraPredQT predIntraLumaAng")
+    s = sub_once(s, r'UInt uiSad = m_pcRdCost->calcHAD\( piOrg, uiStride, piPred, uiStride, uiWidth, uiHeight \);',
+                 'UInt uiSad = tvcHave ? tvcSad[uiMode] : m_pcRdCost->calcHAD( piOrg, uiStride, piPred, uiStride, uiWidth, uiHeight ); tlibcuda_intra_note( uiMode, uiSad );',
+                 "estIntraPredQT calcHAD")
     wr(os.path.join(out, "TLibEncoder", "TEncSearch.cpp"), s)
 
     # ---- TEncGOP.cpp: picture-start hook before the slice is compressed

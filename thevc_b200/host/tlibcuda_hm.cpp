@@ -100,8 +100,23 @@ struct Sao {
   double seconds = 0.0;
 };
 
+// intra rough search: counters and the dump state
+struct Intra {
+  bool on = false, dump = false;
+  int min_width = 16;
+  unsigned long long n_pus = 0, n_host = 0;
+  double seconds = 0.0;
+  // dump mode: the PU being walked by the reference's own loop
+  int log2n = 0;
+  std::vector<short> line, org;
+  unsigned sads[35];
+  int per_size[7] = {0, 0, 0, 0, 0, 0, 0}, seen[7] = {0, 0, 0, 0, 0, 0, 0};
+  FILE* f = nullptr;
+};
+
 struct State {
   tvc_ctx* h = nullptr;
+  Intra intra;
   bool on_lookup = true, verify = false;
   bool wp = false;                         // weighted prediction in the current picture: ME / MC hooks stand down
   Sao sao;
@@ -151,6 +166,9 @@ void report()
             s.dbk.n_pics, s.dbk.n_units, s.dbk.seconds);
   if (s.sao.on && s.sao.n_planes)
     fprintf(stderr, "TLibCuda SAO: %llu planes filtered on the device, %.3f s (upload + kernel + download)\n", s.sao.n_planes, s.sao.seconds);
+  if (s.intra.on)
+    fprintf(stderr, "TLibCuda intra rough search: %llu PUs x 35 modes on the device (width >= %d), %llu smaller PUs by the reference's code, %.3f s in tvc_intra_rough\n",
+            s.intra.n_pus, s.intra.min_width, s.intra.n_host, s.intra.seconds);
   if (s.h && s.dec.on)
     fprintf(stderr, "TLibCuda picture batch: %llu inter CUs (%llu PUs, %llu TUs) reconstructed in %llu device batches, %.3f s in the batches\n",
             s.dec.n_cus, s.dec.n_pus, s.dec.n_tus, s.dec.n_flush, s.dec.seconds);
@@ -215,6 +233,11 @@ void parse_env()
   s.sao.on = !s.sao.dump && strstr(e, "sao") != nullptr;
   s.dbk.dump = strstr(e, "dbkdump") != nullptr;
   s.dbk.on = !s.dbk.dump && strstr(e, "dbk") != nullptr;
+  s.intra.dump = strstr(e, "intradump") != nullptr;
+  if (const char* p = strstr(e, "intra")) {
+    s.intra.on = !s.intra.dump;
+    if (s.intra.on && p[5] >= '0' && p[5] <= '9') s.intra.min_width = atoi(p + 5);
+  }
   if (strstr(e, "stats")) { PS().on = true; s.on_me = s.on_frac = s.on_tq = s.on_rdoq = s.on_mc = s.on_tables = false; atexit(stats_report); }
 }
 
@@ -232,7 +255,7 @@ void ensure_ctx(int w, int ht)
   State& s = S();
   if (s.disabled || (s.h && s.w >= w && s.ht >= ht)) return;
   init_once();
-  if (!s.on_me && !s.on_frac && !s.on_tq && !s.on_rdoq && !s.on_mc && !s.dbk.on && !s.sao.on) { s.disabled = true; return; }     // TVC_HM=none: the unmodified path
+  if (!s.on_me && !s.on_frac && !s.on_tq && !s.on_rdoq && !s.on_mc && !s.dbk.on && !s.sao.on && !s.intra.on) { s.disabled = true; return; }     // TVC_HM=none: the unmodified path
   if (s.h) {                  // the decoder learns the picture size after its first transforms: start over with the real size
     tvc_ctx_destroy(s.h);
     s.h = nullptr;
@@ -558,6 +581,75 @@ bool tlibcuda_xDeQuant(const int* src, int* dst, int w, int h, int per, int rem)
   CK(tvc_xDeQuant(s.h, src, dst, w, h, per, rem));
   s.n_dq++;
   return true;
+}
+
+// ---- intra rough search (TEncSearch::estIntraPredQT, TEncSearch.cpp:2530-2543)
+static void adi_to_line(const int* adi, int n, short* line)
+{
+  // initAdiPattern's own walk of m_piYuvExt (TComPattern.cpp:277-288): left column bottom to top, corner, row above
+  const int sw = 2 * n + 1;
+  int l = 0;
+  for (int i = 0; i < 2 * n; i++) line[l++] = (short)adi[sw * (2 * n - i)];
+  line[l++] = (short)adi[0];
+  for (int i = 0; i < 2 * n; i++) line[l++] = (short)adi[1 + i];
+}
+
+bool tlibcuda_intra_rough(const int* adiBuf, unsigned width, const short* org, unsigned orgStride, bool above, bool left, unsigned* sad35)
+{
+  init_once();
+  State& s = S();
+  Intra& a = s.intra;
+  if (!a.on && !a.dump) return false;
+  const int n = (int)width;
+  int log2n = 0;
+  while ((1 << log2n) < n) log2n++;
+  if (log2n < 2 || log2n > 6 || (1 << log2n) != n) return false;
+  short line[4 * 64 + 1];
+  if (a.dump) {
+    a.log2n = 0;
+    const int limit = getenv("TVC_INTRA_DUMP_PER_SIZE") ? atoi(getenv("TVC_INTRA_DUMP_PER_SIZE")) : 40;
+    const int stride = getenv("TVC_INTRA_DUMP_STRIDE") ? atoi(getenv("TVC_INTRA_DUMP_STRIDE")) : 37;
+    const int step = std::max(1, stride >> (2 * (log2n - 2)));      // a picture has 4x fewer PUs per size step: sample denser
+    if (!getenv("TVC_INTRA_DUMP") || a.per_size[log2n] >= limit || (a.seen[log2n]++ % step) != 0) return false;
+    adi_to_line(adiBuf, n, line);
+    a.log2n = log2n;
+    a.line.assign(line, line + 4 * n + 1);
+    a.org.resize((size_t)n * n);
+    for (int y = 0; y < n; y++) memcpy(&a.org[(size_t)y * n], org + (size_t)y * orgStride, sizeof(short) * n);
+    return false;           // the reference's loop runs and reports every uiSad through tlibcuda_intra_note
+  }
+  if (n < a.min_width) { a.n_host++; return false; }
+  if (!s.h && !s.disabled) ensure_ctx(64, 64);
+  if (!s.h) return false;
+  adi_to_line(adiBuf, n, line);
+  const auto t0 = std::chrono::steady_clock::now();
+  CK(tvc_intra_rough(s.h, log2n, line, org, (int)orgStride, above ? 1 : 0, left ? 1 : 0, sad35, nullptr));
+  a.seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  a.n_pus++;
+  return true;
+}
+
+void tlibcuda_intra_note(unsigned mode, unsigned sad)
+{
+  Intra& a = S().intra;
+  if (!a.dump || !a.log2n || mode >= 35) return;
+  a.sads[mode] = sad;
+  if (mode != 34) return;
+  // record: log2n, bit depth, line[4N+1], org[N*N], sad[35]; raw little-endian
+  if (!a.f) {
+    char name[1024];
+    snprintf(name, sizeof(name), "%s/intra_rough.bin", getenv("TVC_INTRA_DUMP"));
+    a.f = fopen(name, "wb");
+    if (!a.f) { fprintf(stderr, "TLibCuda: cannot write %s\n", name); exit(EXIT_FAILURE); }
+  }
+  const int hdr[2] = {a.log2n, (int)(g_uiBitDepth + g_uiBitIncrement)};
+  fwrite(hdr, sizeof(int), 2, a.f);
+  fwrite(a.line.data(), sizeof(short), a.line.size(), a.f);
+  fwrite(a.org.data(), sizeof(short), a.org.size(), a.f);
+  fwrite(a.sads, sizeof(unsigned), 35, a.f);
+  fflush(a.f);
+  a.per_size[a.log2n]++;
+  a.log2n = 0;
 }
 
 bool tlibcuda_rdoq(TComDataCU* cu, int* src, int* dst, int* arl, unsigned w, unsigned h, unsigned& absSum, int ttype,

@@ -74,6 +74,16 @@ void tlibcuda_sao_begin(TComPic* pic, int yCbCr, bool useNIF);
 bool tlibcuda_sao_unit(int addr, int typeIdx, const int* offsetEo, const int* offsetBands);
 void tlibcuda_sao_end(TComPic* pic, int yCbCr);
 
+/* ---- intra rough search (TVC_HM=...,intra[N]): TEncSearch::estIntraPredQT (TEncSearch.cpp:2530-2543).  Before the 35-mode
+ * loop the hook hands the reference samples initAdiPattern left in m_piYuvExt (unfiltered; column 0 and row 0 of the
+ * (2N+1)^2 array) and the original block to tvc_intra_rough and keeps the 35 SATDs; inside the loop predIntraLumaAng +
+ * calcHAD are skipped and uiSad is read from that array, the mode bits, the cost and the candidate list stay the
+ * reference's.  PUs narrower than N (default 16: below that one launch costs more than the host's 35 predictions) are
+ * left to the reference's code.  TVC_HM=intradump: nothing runs on the device, the reference's own uiSad values are
+ * written together with the line and the block (the golden vectors of tests/golden/intra_rough.npz). */
+bool tlibcuda_intra_rough(const int* adiBuf, unsigned width, const short* org, unsigned orgStride, bool above, bool left, unsigned* sad35);
+void tlibcuda_intra_note(unsigned mode, unsigned sad);
+
 /* TComTrQuant::xRateDistOptQuant (TComTrQuant.cpp:1719): est is m_pcEstBitsSbac (estBitsSbacStruct == tvc_est_bits) */
 bool tlibcuda_rdoq(TComDataCU* cu, int* src, int* dst, int* arl, unsigned w, unsigned h, unsigned& absSum, int ttype,
                    unsigned absPartIdx, int per, int rem, double lambda, const void* est, bool useArl);

@@ -337,6 +337,27 @@ class TLibCuda:
         assert units.shape == (self.ctus_x * self.ctus_y, 38)
         self._ck(self.L.tvc_sao_plane(self.h, src_slot, dst_slot, plane, ptr(units)))
 
+    def intra_rough(self, log2_size: int, line: np.ndarray, org: np.ndarray, above: bool = True, left: bool = True,
+                    want_preds: bool = False):
+        """35-mode rough search of one N x N luma PU (estIntraPredQT, TEncSearch.cpp:2530-2537): SATD per mode
+        [35] (+ the 35 predictions [35, N, N]); line: 4N+1 unfiltered reference samples, org: [N, N] (any row stride)"""
+        n = 1 << log2_size
+        line = np.ascontiguousarray(line, np.int16)
+        assert line.shape == (4 * n + 1,) and org.dtype == np.int16 and org.shape == (n, n) and org.strides[1] == 2
+        sad = np.zeros(capi.INTRA_MODES, np.uint32)
+        preds = np.zeros((capi.INTRA_MODES, n, n), np.int16) if want_preds else None
+        self._ck(self.L.tvc_intra_rough(self.h, log2_size, ptr(line), C.c_void_p(org.ctypes.data), org.strides[0] // 2, int(above), int(left),
+                                        ptr(sad), ptr(preds) if want_preds else None))
+        return (sad, preds) if want_preds else sad
+
+    def intra_rough_batch(self, jobs: np.ndarray, lines: np.ndarray, org: np.ndarray) -> np.ndarray:
+        """jobs: capi.INTRA_JOB_DTYPE [n]; lines / org: flat int16 arrays the jobs' offsets address; returns uint32 [n, 35]"""
+        jobs = np.ascontiguousarray(jobs, capi.INTRA_JOB_DTYPE)
+        lines, org = np.ascontiguousarray(lines, np.int16).reshape(-1), np.ascontiguousarray(org, np.int16).reshape(-1)
+        sad = np.zeros((len(jobs), capi.INTRA_MODES), np.uint32)
+        self._ck(self.L.tvc_intra_rough_batch(self.h, len(jobs), ptr(jobs), ptr(lines), lines.size, ptr(org), org.size, ptr(sad)))
+        return sad
+
     def prof_enable(self, on: bool = True):
         self._ck(self.L.tvc_prof_enable(self.h, int(on)))
 
