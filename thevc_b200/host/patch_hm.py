@@ -55,7 +55,22 @@ def main():
     s = sub_once(s, r'(#include "TEncGOP.h"\r?\n)', r'\1#include "tlibcuda_hm.h"\n', "TEncGOP include")
     s = sub_once(s, r'(\n)([ \t]*m_pcSliceEncoder->precompressSlice\( pcPic \);\r?\n)',
                  r'\1        tlibcuda_picture_start( pcPic, pcSlice );\n\2', "compressGOP")
+    # frame sharding of all-intra sequences: a shard that starts at frame k numbers its pictures from POC k and leaves
+    # the parameter sets to shard 0, so that the shards' streams concatenate to the single-run stream
+    s = sub_once(s, r'm_bSeqFirst           = true;', 'm_bSeqFirst           = tlibcuda_poc_offset() == 0;', "TEncGOP m_bSeqFirst")
+    s = sub_once(s, r'if\(uiPOCCurr>=m_pcCfg->getFrameToBeEncoded\(\)\)', 'if(uiPOCCurr>=m_pcCfg->getFrameToBeEncoded() + tlibcuda_poc_offset())',
+                 "compressGOP frame limit")
     wr(os.path.join(out, "TLibEncoder", "TEncGOP.cpp"), s)
+
+    s = rd(os.path.join(lib, "TLibEncoder", "TEncTop.cpp"))
+    s = sub_once(s, r'(#include "TEncTop.h"\r?\n)', r'\1#include "tlibcuda_hm.h"\n', "TEncTop include")
+    s = sub_once(s, r'm_iPOCLast          = -1;', 'm_iPOCLast          = -1 + (Int)tlibcuda_poc_offset();', "TEncTop m_iPOCLast")
+    wr(os.path.join(out, "TLibEncoder", "TEncTop.cpp"), s)
+    # the per-picture dQP array is allocated for FramesToBeEncoded entries and indexed by POC (TAppEncCfg.cpp:426, TEncSlice.cpp:246)
+    s = rd(os.path.join(lib, "TLibEncoder", "TEncSlice.cpp"))
+    s = sub_once(s, r'(#include "TEncSlice.h"\r?\n)', r'\1#include "tlibcuda_hm.h"\n', "TEncSlice include")
+    s = sub_once(s, r'dQP \+= pdQPs\[ rpcSlice->getPOC\(\) \];', 'dQP += pdQPs[ rpcSlice->getPOC() - (Int)tlibcuda_poc_offset() ];', "initEncSlice dQP")
+    wr(os.path.join(out, "TLibEncoder", "TEncSlice.cpp"), s)
 
     # ---- AnnexBwrite.h: gcc portability (non-const reference to an rvalue)
     s = rd(os.path.join(lib, "TLibEncoder", "AnnexBwrite.h"))
@@ -122,7 +137,7 @@ def main():
                  r'\1  if ( tlibcuda_pred_inter_uni( pcCU, pcCU->getSlice()->getRefPic( eRefPicList, iRefIdx ), uiPartAddr, cMv.getHor(), cMv.getVer(), iWidth, iHeight, rpcYuvPred, bi ) ) return;\n',
                  "xPredInterUni", flags=re.S)
     wr(os.path.join(out, "TLibCommon", "TComPrediction.cpp"), s)
-    print("patched 9 files into", out)
+    print("patched 11 files into", out)
 
 
 if __name__ == "__main__":

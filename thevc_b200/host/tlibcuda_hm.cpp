@@ -583,6 +583,13 @@ bool tlibcuda_xDeQuant(const int* src, int* dst, int w, int h, int per, int rem)
   return true;
 }
 
+unsigned tlibcuda_poc_offset()
+{
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("TVC_POC_OFFSET"); off = e ? atoi(e) : 0; if (off < 0) off = 0; }
+  return (unsigned)off;
+}
+
 // ---- intra rough search (TEncSearch::estIntraPredQT, TEncSearch.cpp:2530-2543)
 static void adi_to_line(const int* adi, int n, short* line)
 {

@@ -84,6 +84,13 @@ void tlibcuda_sao_end(TComPic* pic, int yCbCr);
 bool tlibcuda_intra_rough(const int* adiBuf, unsigned width, const short* org, unsigned orgStride, bool above, bool left, unsigned* sad35);
 void tlibcuda_intra_note(unsigned mode, unsigned sad);
 
+/* ---- frame sharding of all-intra sequences (thevc_b200/host/shard_encode.py).  TVC_POC_OFFSET=k: this process
+ * encodes the frames from input frame k on (-fs k) as POC k, k+1, ... (TEncTop::m_iPOCLast starts at k-1, TEncTop.cpp:54; the
+ * frame limit of compressGOP, TEncGOP.cpp:211, moves with it) and, for k > 0, writes no VPS/SPS/PPS (m_bSeqFirst,
+ * TEncGOP.cpp:86,680-712): with IntraPeriod 1 every picture is coded on its own, so the shards' NAL units are the single
+ * run's and the host only concatenates them.  No CUDA involved. */
+unsigned tlibcuda_poc_offset();
+
 /* TComTrQuant::xRateDistOptQuant (TComTrQuant.cpp:1719): est is m_pcEstBitsSbac (estBitsSbacStruct == tvc_est_bits) */
 bool tlibcuda_rdoq(TComDataCU* cu, int* src, int* dst, int* arl, unsigned w, unsigned h, unsigned& absSum, int ttype,
                    unsigned absPartIdx, int per, int rem, double lambda, const void* est, bool useArl);
