@@ -522,6 +522,78 @@ def aggregate_fps(ms_per_step, world):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
+def intra_rough_leg(t, wl, local, cpu_sample=64):
+    """SURVEY 8f-2 beside the P-picture step: the 35-mode rough search of EVERY intra PU of one 1080p picture (all five PU sizes
+    of every CTU: what an I picture's estIntraPredQT calls add up to) as one device batch; reference samples = the picture's own
+    neighbouring rows / columns (an I picture predicts from its reconstruction: same data volume, same arithmetic)."""
+    import torch
+    from thevc_b200 import capi
+    from thevc_b200.capi import ptr
+    pic = wl.pics[0]
+    plane = np.ascontiguousarray(pic.y)                      # H x W int16
+    Hh, Ww = plane.shape
+    jobs, lines, off = [], [], 0
+    for log2n in (6, 5, 4, 3, 2):
+        n = 1 << log2n
+        for y in range(0, Hh - n + 1, n):
+            for x in range(0, Ww - n + 1, n):
+                yy, xx = max(y, 1), max(x, 1)
+                left = plane[np.clip(np.arange(yy + 2 * n - 1, yy - 1, -1), 0, Hh - 1), xx - 1]
+                above = plane[yy - 1, np.clip(np.arange(xx, xx + 2 * n), 0, Ww - 1)]
+                lines.append(np.concatenate([left, plane[yy - 1:yy, xx - 1], above]))
+                jobs.append((log2n, off, y * Ww + x, Ww, 1, 1))
+                off += 4 * n + 1
+    jobs = np.array(jobs, capi.INTRA_JOB_DTYPE)
+    lines = np.concatenate(lines).astype(np.int16)
+    d_jobs = torch.from_numpy(jobs.view(np.uint8).reshape(-1).copy()).cuda(local)
+    d_lines, d_org = torch.from_numpy(lines).cuda(local), torch.from_numpy(plane.reshape(-1).copy()).cuda(local)
+    d_sad = torch.zeros(len(jobs) * 35, dtype=torch.int32, device="cuda")
+
+    def run():
+        rc = t.L.tvc_intra_rough_batch_dev(t.h, len(jobs), C.c_void_p(d_jobs.data_ptr()), C.c_void_p(d_lines.data_ptr()),
+                                           C.c_void_p(d_org.data_ptr()), C.c_void_p(d_sad.data_ptr()), None, None)
+        if rc:
+            raise RuntimeError("tvc_intra_rough_batch_dev: %s" % t.L.tvc_last_error(t.h).decode())
+    for _ in range(3):
+        run()
+    t.prof_enable(True)
+    t.prof_read(reset=True)
+    reps = 10
+    for _ in range(reps):
+        run()
+    ms = t.prof_read(reset=True)["intra"][0] / reps
+    t.prof_enable(False)
+    pels = float(sum((1 << (2 * int(j["log2_size"]))) for j in jobs)) * 35
+    out = {"pus": int(len(jobs)), "ms": ms, "satd_gpel_per_s": pels / (ms * 1e-3) / 1e9,
+           "algorithmic_GBps": (pels / 35 * 2 + lines.nbytes + len(jobs) * (24 + 140)) / (ms * 1e-3) / 1e9}
+    # the oracle (C restatement of predIntraLumaAng + calcHAD) on a strided sample of the same PUs, one core
+    try:
+        import time
+        import oracle
+        O = oracle.lib()
+        got = d_sad.cpu().numpy().view(np.uint32).reshape(-1, 35)
+        idx = np.linspace(0, len(jobs) - 1, cpu_sample).astype(int)
+        sad = np.zeros(35, np.uint32)
+        t0 = time.perf_counter()
+        spels = 0.0
+        for i in idx:
+            j = jobs[i]
+            n = 1 << int(j["log2_size"])
+            ln = np.ascontiguousarray(lines[j["line_offset"]:j["line_offset"] + 4 * n + 1])
+            O.orc_intra_rough(oracle.ptr(ln), C.c_void_p(plane.ctypes.data + 2 * int(j["org_offset"])), Ww, int(j["log2_size"]), 1, 1, BD,
+                              oracle.ptr(sad), None)
+            if not np.array_equal(sad, got[i]):
+                raise RuntimeError("intra rough search: device result of PU %d differs from the oracle" % i)
+            spels += n * n * 35
+        dt = time.perf_counter() - t0
+        out["cpu_oracle_gpel_per_s_1core"] = spels / dt / 1e9
+        out["cpu_sample"] = "%d PUs of all sizes, device result checked against each" % len(idx)
+    except ImportError:
+        pass
+    return out
+
+
+
 def gpu_arm(args):
     import torch
     from thevc_b200 import TLibCuda, capi
@@ -739,6 +811,11 @@ def gpu_arm(args):
         "tz_candidates_per_step": int(n_sads.sum()),
         "me_jobs_per_step": n_valid,
     }
+
+    try:
+        sub["intra_rough"] = intra_rough_leg(t, wl, local)
+    except Exception as ex:          # a side leg must never take the hot-path line down with it
+        sub["intra_rough"] = {"error": repr(ex)[:300]}
 
     # ---- CPU baseline (oracle port, one core, bounded sample)
     cpu = None
