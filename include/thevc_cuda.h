@@ -140,6 +140,19 @@ typedef struct {
 int tvc_mc_batch(tvc_ctx* ctx, int dst_slot, int n, const tvc_pu* pus);
 int tvc_mc_batch_dev(tvc_ctx* ctx, int dst_slot, int n, const tvc_pu* pus_dev);
 
+/* Prediction + distortion of candidate motions (merge / AMVP candidate evaluation).  For every entry: the luma
+ * prediction motionCompensation would write (uni-prediction: clipped pels; both lists: 14-bit intermediates + TComYuv::addAvg;
+ * MVs already clipped by TComDataCU::clipMv, identical-motion candidates already reduced to list 0 as xCheckIdenticalMotion does,
+ * TComPrediction.cpp:392-552) and its distortion against the ORIGINAL block of cur_slot at the same rectangle:
+ *   kind TVC_DIST_HADS / TVC_DIST_SAD = TEncSearch::xGetInterPredictionError (TEncSearch.cpp:3059-3081: setDistParam with
+ *   HadamardME on / off, iSubShift 0) as xMergeEstimation calls it per merge candidate (:3096-3149);
+ *   kind TVC_DIST_SAD                 = the xPredInterLumaBlk + getDistPart(DF_SAD) of TEncSearch::xGetTemplateCost (:4057-4118)
+ *                                       per AMVP candidate.
+ * The candidate lists, the bit counts and the comparisons (merge index bits, m_auiMVPIdxCost, strict "<" in candidate order) stay
+ * host work.  dist[i] is the reference's UInt (already >> bitIncrement).                                                        */
+int tvc_pred_cost_batch(tvc_ctx* ctx, int cur_slot, int kind, int n, const tvc_pu* pus, uint32_t* dist);
+int tvc_pred_cost_batch_dev(tvc_ctx* ctx, int cur_slot, int kind, int n, const tvc_pu* pus_dev, uint32_t* dist_dev);
+
 /* One PU, one reference list, into caller buffers: TComPrediction::xPredInterUni = xPredInterLumaBlk +
  * xPredInterChromaBlk (TComPrediction.cpp:483-490, 554-645).  (x, y, w, h) luma rectangle, MV already
  * clipped, dst_* point at the PU's first sample inside a TComYuv.  bi != 0 keeps the 14-bit intermediate

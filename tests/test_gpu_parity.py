@@ -784,3 +784,39 @@ def test_error_behaviour(ctx8):
     with pytest.raises(TvcError):
         ctx8.xT(0, np.zeros((8, 8), np.int16), 0, 8, 5)                           # unsupported size
     assert ctx8.launch_count() > 0
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_pred_cost_batch(ctx8, ctx10, orc, bd):
+    """merge / AMVP candidate evaluation = luma motion compensation of a candidate + HAD or SAD against the original
+    block (xGetInterPredictionError, TEncSearch.cpp:3059-3081; xGetTemplateCost :4057-4118).  Candidates of one PU overlap, every
+    PU shape, uni / bi, fractional / integer / far-clipped MVs, 8- and 10-bit."""
+    t = ctx8 if bd == 8 else ctx10
+    rng = np.random.default_rng(140 + bd)
+    cur = _pic(rng, bd)
+    refs = {1: _pic(rng, bd), 2: _pic(rng, bd)}
+    t.upload(0, cur); t.upload(1, refs[1]); t.upload(2, refs[2])
+    pus = []
+    for k in range(5 * len(PU_SHAPES)):
+        w, h = PU_SHAPES[k % len(PU_SHAPES)]
+        cx, cy = int(rng.integers(0, W // 64)) * 64, int(rng.integers(0, H // 64)) * 64          # a PU never crosses its CTU
+        px, py = cx + int(rng.integers(0, (64 - w) // 4 + 1)) * 4, cy + int(rng.integers(0, (64 - h) // 4 + 1)) * 4
+        for cand in range(5):                                 # five candidates of the same PU, as xMergeEstimation walks them
+            mv = [int(v) for v in rng.integers(-200, 200, 4)]
+            if cand == 3:
+                mv = [4 * (mv[0] // 4), 4 * (mv[1] // 4), mv[2], 4 * (mv[3] // 4)]
+            if cand == 4 and k % 6 == 0:
+                mv = [-4000, 4000, 4000, -4000]
+            m0, m1 = _clip_mv(orc, px, py, mv[0], mv[1]), _clip_mv(orc, px, py, mv[2], mv[3])
+            mode = (k + cand) % 3
+            pus.append(PU(px, py, w, h, 1, m0[0], m0[1], -1, 0, 0) if mode == 0 else
+                       PU(px, py, w, h, -1, 0, 0, 2, m1[0], m1[1]) if mode == 1 else
+                       PU(px, py, w, h, 1, m0[0], m0[1], 2, m1[0], m1[1]))
+    for kind, fn in ((capi.DIST_HADS, orc.orc_hads), (capi.DIST_SAD, orc.orc_sad_generic)):
+        got = t.pred_cost_batch(0, kind, pus)
+        for i, pu in enumerate(pus):
+            pred = np.ascontiguousarray(_oracle_mc(orc, refs, pu, bd)[0])
+            exp = fn(optr(cur.buf_y, cur.origin(0) + pu.y * cur.stride + pu.x), cur.stride, optr(pred), pu.w, pu.w, pu.h, bd - 8)
+            assert int(got[i]) == int(exp), (kind, i, pu.x, pu.y, pu.w, pu.h, pu.ref_slot0, pu.ref_slot1)
+    with pytest.raises(Exception):
+        t.pred_cost_batch(0, capi.DIST_SSE, pus[:1])

@@ -159,3 +159,25 @@ def test_intra_rough_search_on_device(tmp_path, cfg, frames, w, h):
     assert il, r.stderr[-600:]
     print(il[-1])
     assert int(il[-1].split()[4]) > 500 and " 0 smaller PUs" in il[-1], il[-1]
+
+
+@pytest.mark.parametrize("cfg,frames", [
+    ("encoder_lowdelay_P_main.cfg", 3),        # P slices: uni-predicted merge candidates, AMVP templates of 4 references
+    ("encoder_randomaccess_main.cfg", 5),      # B slices: bi-predicted candidates (addAvg), identical-motion reduction
+])
+def test_candidate_evaluation_on_device(tmp_path, cfg, frames):
+    """SURVEY 8f-3 inside the real encoder: every xMergeEstimation candidate set and every xGetTemplateCost call served by
+    tvc_pred_cost_batch; the merge / AMVP decisions, hence the bitstream, are the reference's."""
+    _need()
+    w, h = 208, 120
+    yuv = str(tmp_path / "in.yuv")
+    _yuv(yuv, w, h, frames)
+    ref_bin, cuda_bin = str(tmp_path / "ref.bin"), str(tmp_path / "cuda.bin")
+    _encode(ENC_REF, cfg, yuv, w, h, frames, ref_bin)
+    r = _encode(ENC_CUDA, cfg, yuv, w, h, frames, cuda_bin, env={"TVC_HM": "cand"})
+    assert _md5(cuda_bin) == _md5(ref_bin)
+    cl = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda candidate evaluation:")]
+    assert cl, r.stderr[-600:]
+    print(cl[-1])
+    f = cl[-1].split()
+    assert int(f[3]) > 100 and int(f[9]) > 1000, cl[-1]

@@ -168,6 +168,8 @@ SIGNATURES = {
     "tvc_xDeQuant": (ci, [vp, vp, vp, ci, ci, ci, ci]),
     "tvc_deblock_pic": (ci, [vp, ci, vp, vp, ci, ci]),
     "tvc_sao_plane": (ci, [vp, ci, ci, ci, vp]),
+    "tvc_pred_cost_batch": (ci, [vp, ci, ci, ci, vp, vp]),
+    "tvc_pred_cost_batch_dev": (ci, [vp, ci, ci, ci, vp, vp]),
     "tvc_intra_rough_batch": (ci, [vp, ci, vp, vp, C.c_size_t, vp, C.c_size_t, vp]),
     "tvc_intra_rough_batch_dev": (ci, [vp, ci, vp, vp, vp, vp, vp, vp]),
     "tvc_intra_rough": (ci, [vp, ci, vp, vp, ci, ci, ci, vp, vp]),

@@ -2,6 +2,7 @@
 // (TComInterpolationFilter.cpp:325-415; TComPrediction.cpp:410-658; TComYuv.cpp:520-581).
 #include "tvc_internal.cuh"
 #include "tvc_interp.cuh"
+#include "tvc_dist.cuh"
 
 namespace tvc {
 
@@ -129,6 +130,62 @@ __global__ void __launch_bounds__(256) k_mc_batch(PlaneTable pt, int dst_slot, i
   }
 }
 
+// luma prediction of one candidate (uni: clipped pels; both lists: 14-bit intermediates + addAvg) kept in shared memory, then its
+// distortion against the original block of cur_slot: the body of xGetInterPredictionError (TEncSearch.cpp:3059-3081: motionCompensation
+// + setDistParam(bHadamard) + DistFunc) and of xGetTemplateCost's prediction + SAD (TEncSearch.cpp:4057-4118).  CTA per candidate.
+__global__ void __launch_bounds__(256) k_pred_cost(PlaneTable pt, int cur_slot, int kind, int n, const tvc_pu* __restrict__ pus,
+                                                   uint32_t* __restrict__ out, int bd)
+{
+  __shared__ int16_t s_tmp[kMcMaxW * (kMcMaxH + 7)];
+  __shared__ int16_t s_l0[kMcMaxW * kMcMaxH];
+  __shared__ int16_t s_l1[kMcMaxW * kMcMaxH];
+  __shared__ uint32_t s_sum;
+  const tvc_pu pu = pus[blockIdx.x];
+  const int w = pu.w, h = pu.h, stride = pt.stride[0];
+  const bool use0 = pu.ref_slot0 >= 0, use1 = pu.ref_slot1 >= 0, bi = use0 && use1;
+  if (threadIdx.x == 0) s_sum = 0;
+  if (!bi) {
+    const int slot = use0 ? pu.ref_slot0 : pu.ref_slot1;
+    const int mvx = use0 ? pu.mvx0 : pu.mvx1, mvy = use0 ? pu.mvy0 : pu.mvy1;
+    mc_one_list<8>(pt.org[slot][0] + (ptrdiff_t)pu.y * stride + pu.x, stride, mvx, mvy, w, h, false, bd, s_tmp, s_l0, w);
+  } else {
+    mc_one_list<8>(pt.org[pu.ref_slot0][0] + (ptrdiff_t)pu.y * stride + pu.x, stride, pu.mvx0, pu.mvy0, w, h, true, bd, s_tmp, s_l0, w);
+    __syncthreads();
+    mc_one_list<8>(pt.org[pu.ref_slot1][0] + (ptrdiff_t)pu.y * stride + pu.x, stride, pu.mvx1, pu.mvy1, w, h, true, bd, s_tmp, s_l1, w);
+    __syncthreads();
+    const int shiftNum = kIfPrec + 1 - bd, offset = (1 << (shiftNum - 1)) + 2 * kIfOffs, maxv = (1 << bd) - 1;
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x) {      // TComYuv::addAvg, TComYuv.cpp:539-549
+      int v = ((int)s_l0[i] + (int)s_l1[i] + offset) >> shiftNum;
+      s_l0[i] = (int16_t)(v < 0 ? 0 : (v > maxv ? maxv : v));
+    }
+  }
+  __syncthreads();
+  const int16_t* org = pt.org[cur_slot][0] + (ptrdiff_t)pu.y * stride + pu.x;
+  uint32_t acc = 0;
+  if (kind == TVC_DIST_SAD) {
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+      const int y = i / w, x = i - y * w;
+      acc += (uint32_t)abs((int)org[(ptrdiff_t)y * stride + x] - (int)s_l0[i]);
+    }
+  } else if (!(w & 7) && !(h & 7)) {        // xGetHADs tiling (TComRdCost.cpp:2186-2287): PU sides are multiples of 4
+    const int tx = w >> 3, nt = tx * (h >> 3);
+    for (int t = threadIdx.x; t < nt; t += blockDim.x) {
+      const int ty = t / tx, txx = t - ty * tx;
+      acc += had_tile<8>(org + (ptrdiff_t)(ty * 8) * stride + txx * 8, stride, s_l0 + (ty * 8) * w + txx * 8, w);
+    }
+  } else {
+    const int tx = w >> 2, nt = tx * (h >> 2);
+    for (int t = threadIdx.x; t < nt; t += blockDim.x) {
+      const int ty = t / tx, txx = t - ty * tx;
+      acc += had_tile<4>(org + (ptrdiff_t)(ty * 4) * stride + txx * 4, stride, s_l0 + (ty * 4) * w + txx * 4, w);
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&s_sum, acc);
+  __syncthreads();
+  if (threadIdx.x == 0) out[blockIdx.x] = s_sum >> (bd - 8);
+}
+
 // one PU, one list, dense output [Y w*h][U (w/2)(h/2)][V]: the drop-in for xPredInterUni
 __global__ void __launch_bounds__(256) k_mc_block(PlaneTable pt, int ref_slot, int x, int y, int w, int h, int mvx, int mvy, int bi,
                                                   int bd, int16_t* __restrict__ out)
@@ -200,11 +257,9 @@ int tvc_mc_batch_dev(tvc_ctx* c, int dst_slot, int n, const tvc_pu* pus_dev)
   return TVC_OK;
 }
 
-int tvc_mc_batch(tvc_ctx* c, int dst_slot, int n, const tvc_pu* pus)
+static int validate_pus(tvc_ctx* c, int plane_slot, int n, const tvc_pu* pus, const char* who)
 {
-  if (!c || !valid_slot(c, dst_slot) || n < 0 || (n && !pus)) return set_err(c, TVC_ERR_ARG, "tvc_mc_batch: bad argument");
-  if (n == 0) return TVC_OK;
-  const Pic& p = c->pics[dst_slot];
+  const Pic& p = c->pics[plane_slot];
   for (int i = 0; i < n; i++) {
     const tvc_pu& u = pus[i];
     bool ok = u.w > 0 && u.h > 0 && u.w <= 64 && u.h <= 64 && !(u.w & 3) && !(u.h & 3) && u.x >= 0 && u.y >= 0 &&
@@ -218,14 +273,54 @@ int tvc_mc_batch(tvc_ctx* c, int dst_slot, int n, const tvc_pu* pus)
       int ix = u.x + (mvx >> 2), iy = u.y + (mvy >> 2);
       ok = ix - 3 >= -p.mx[0] && iy - 3 >= -p.my[0] && ix + u.w + 4 <= p.w[0] + p.mx[0] && iy + u.h + 4 <= p.h[0] + p.my[0];
     }
-    if (!ok) return set_err(c, TVC_ERR_ARG, "tvc_mc_batch: PU %d invalid or MV reaches outside the padded picture", i);
+    if (!ok) return set_err(c, TVC_ERR_ARG, "%s: PU %d invalid or MV reaches outside the padded picture", who, i);
   }
+  return TVC_OK;
+}
+
+int tvc_mc_batch(tvc_ctx* c, int dst_slot, int n, const tvc_pu* pus)
+{
+  if (!c || !valid_slot(c, dst_slot) || n < 0 || (n && !pus)) return set_err(c, TVC_ERR_ARG, "tvc_mc_batch: bad argument");
+  if (n == 0) return TVC_OK;
   int r;
+  if ((r = validate_pus(c, dst_slot, n, pus, "tvc_mc_batch"))) return r;
   if ((r = ensure_scratch(c, c->in, (size_t)n * sizeof(tvc_pu)))) return r;
   memcpy(c->in.host, pus, (size_t)n * sizeof(tvc_pu));
   TVC_CUDA(c, cudaMemcpyAsync(c->in.dev, c->in.host, (size_t)n * sizeof(tvc_pu), cudaMemcpyHostToDevice, c->stream));
   if ((r = tvc_mc_batch_dev(c, dst_slot, n, (const tvc_pu*)c->in.dev))) return r;
   TVC_CUDA(c, cudaStreamSynchronize(c->stream));
+  return TVC_OK;
+}
+
+int tvc_pred_cost_batch_dev(tvc_ctx* c, int cur_slot, int kind, int n, const tvc_pu* pus_dev, uint32_t* dist_dev)
+{
+  if (!c || !valid_slot(c, cur_slot) || n < 0 || (kind != TVC_DIST_SAD && kind != TVC_DIST_HADS) || (n && (!pus_dev || !dist_dev)))
+    return set_err(c, TVC_ERR_ARG, "tvc_pred_cost_batch_dev: bad argument (kind is TVC_DIST_SAD or TVC_DIST_HADS)");
+  if (n == 0) return TVC_OK;
+  ProfScope ps(c, TVC_PH_MC);
+  k_pred_cost<<<n, 256, 0, c->stream>>>(c->planes, cur_slot, kind, n, pus_dev, dist_dev, c->cfg.bit_depth);
+  TVC_LAUNCH_CHECK(c);
+  return TVC_OK;
+}
+
+int tvc_pred_cost_batch(tvc_ctx* c, int cur_slot, int kind, int n, const tvc_pu* pus, uint32_t* dist)
+{
+  if (!c || !valid_slot(c, cur_slot) || n < 0 || (kind != TVC_DIST_SAD && kind != TVC_DIST_HADS) || (n && (!pus || !dist)))
+    return set_err(c, TVC_ERR_ARG, "tvc_pred_cost_batch: bad argument (kind is TVC_DIST_SAD or TVC_DIST_HADS)");
+  if (n == 0) return TVC_OK;
+  int r;
+  if ((r = validate_pus(c, cur_slot, n, pus, "tvc_pred_cost_batch"))) return r;
+  for (int i = 0; i < n; i++)
+    if (pus[i].x + pus[i].w > c->pics[cur_slot].w[0] || pus[i].y + pus[i].h > c->pics[cur_slot].h[0])
+      return set_err(c, TVC_ERR_ARG, "tvc_pred_cost_batch: PU %d lies outside the picture", i);
+  if ((r = ensure_scratch(c, c->in, (size_t)n * sizeof(tvc_pu)))) return r;
+  if ((r = ensure_scratch(c, c->out, (size_t)n * 4))) return r;
+  memcpy(c->in.host, pus, (size_t)n * sizeof(tvc_pu));
+  TVC_CUDA(c, cudaMemcpyAsync(c->in.dev, c->in.host, (size_t)n * sizeof(tvc_pu), cudaMemcpyHostToDevice, c->stream));
+  if ((r = tvc_pred_cost_batch_dev(c, cur_slot, kind, n, (const tvc_pu*)c->in.dev, (uint32_t*)c->out.dev))) return r;
+  TVC_CUDA(c, cudaMemcpyAsync(c->out.host, c->out.dev, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  TVC_CUDA(c, cudaStreamSynchronize(c->stream));
+  memcpy(dist, c->out.host, (size_t)n * 4);
   return TVC_OK;
 }
 

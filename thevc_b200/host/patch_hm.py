@@ -39,6 +39,15 @@ def main():
     s = sub_once(s, r'(Void TEncSearch::xPatternSearchFracDIF\(TComDataCU\* pcCU,.*?\n\s*\)\r?\n\{\r?\n)',
                  r'\1  if ( tlibcuda_frac_search( pcPatternKey, piRefY, iRefStride, pcMvInt, rcMvHalf, rcMvQter, ruiCost, m_pcRdCost, m_pcEncCfg, biPred ) ) return;\n',
                  "xPatternSearchFracDIF", flags=re.S)
+    # xMergeEstimation / xGetTemplateCost: candidate evaluation (motion compensation + distortion) in one device call
+    s = sub_once(s, r'(\n)([ \t]*ruiCost = MAX_UINT;\r?\n[ \t]*for\( UInt uiMergeCand = 0; uiMergeCand < numValidMergeCand; \+\+uiMergeCand \)\r?\n)',
+                 r'\1  UInt tvcDist[MRG_MAX_NUM_CANDS];\n  const Bool tvcHave = tlibcuda_merge_costs( pcCU, iPUIdx, cMvFieldNeighbours, uhInterDirNeighbours, numValidMergeCand, m_pcEncCfg->getUseHADME(), tvcDist );\n\2',
+                 "xMergeEstimation loop")
+    s = sub_once(s, r'(\n[ \t]*)(xGetInterPredictionError\( pcCU, pcYuvOrg, iPUIdx, uiCostCand, m_pcEncCfg->getUseHADME\(\) \);)',
+                 r'\1if ( tvcHave ) uiCostCand = tvcDist[uiMergeCand]; else \2', "xMergeEstimation candidate")
+    s = sub_once(s, r'(  pcCU->clipMv\( cMvCand \);\r?\n)(\r?\n  // prediction pattern\r?\n)',
+                 r'\1  { UInt tvcSad = 0; if ( tlibcuda_template_sad( pcCU, pcCU->getSlice()->getRefPic( eRefPicList, iRefIdx ), uiPartAddr, cMvCand.getHor(), cMvCand.getVer(), iSizeX, iSizeY, tvcSad ) ) return (UInt) m_pcRdCost->calcRdCost( m_auiMVPIdxCost[iMVPIdx][iMVPNum], tvcSad, false, DF_SAD ); }\n\2',
+                 "xGetTemplateCost")
     # estIntraPredQT: the 35-mode rough search (predIntraLumaAng + calcHAD per mode) served from one device call per PU
     s = sub_once(s, r'(\n)([ \t]*for\( Int modeIdx = 0; modeIdx < numModesAvailable; modeIdx\+\+ \)\r?\n)',
                  r'\1      UInt tvcSad[35];\n      const Bool tvcHave = tlibcuda_intra_rough( m_piYuvExt, uiWidth, piOrg, uiStride, bAboveAvail, bLeftAvail, tvcSad );\n\2',

@@ -129,6 +129,9 @@ struct State {
   unsigned long long n_tz_lookup = 0, n_frac_lookup = 0, n_groups = 0;
   double batch_seconds = 0.0, prepass_seconds = 0.0;      // host wall time spent inside tvc_me_ctu / picture_start
   bool on_me = true, on_frac = true, on_tq = true, on_rdoq = true, on_mc = true, on_tables = true, verbose = false, disabled = false;
+  bool on_cand = false;                    // merge / AMVP candidate evaluation (TVC_HM=...,cand)
+  unsigned long long n_merge = 0, n_merge_cands = 0, n_template = 0;
+  double cand_seconds = 0.0;
   int w = 0, ht = 0;
   std::vector<DevPic> slots;
   unsigned long long clock = 0;
@@ -166,6 +169,9 @@ void report()
             s.dbk.n_pics, s.dbk.n_units, s.dbk.seconds);
   if (s.sao.on && s.sao.n_planes)
     fprintf(stderr, "TLibCuda SAO: %llu planes filtered on the device, %.3f s (upload + kernel + download)\n", s.sao.n_planes, s.sao.seconds);
+  if (s.on_cand)
+    fprintf(stderr, "TLibCuda candidate evaluation: %llu xMergeEstimation calls (%llu candidates) and %llu xGetTemplateCost calls on the device, %.3f s in tvc_pred_cost_batch\n",
+            s.n_merge, s.n_merge_cands, s.n_template, s.cand_seconds);
   if (s.intra.on)
     fprintf(stderr, "TLibCuda intra rough search: %llu PUs x 35 modes on the device (width >= %d), %llu smaller PUs by the reference's code, %.3f s in tvc_intra_rough\n",
             s.intra.n_pus, s.intra.min_width, s.intra.n_host, s.intra.seconds);
@@ -233,6 +239,7 @@ void parse_env()
   s.sao.on = !s.sao.dump && strstr(e, "sao") != nullptr;
   s.dbk.dump = strstr(e, "dbkdump") != nullptr;
   s.dbk.on = !s.dbk.dump && strstr(e, "dbk") != nullptr;
+  s.on_cand = strstr(e, "cand") != nullptr;
   s.intra.dump = strstr(e, "intradump") != nullptr;
   if (const char* p = strstr(e, "intra")) {
     s.intra.on = !s.intra.dump;
@@ -255,7 +262,7 @@ void ensure_ctx(int w, int ht)
   State& s = S();
   if (s.disabled || (s.h && s.w >= w && s.ht >= ht)) return;
   init_once();
-  if (!s.on_me && !s.on_frac && !s.on_tq && !s.on_rdoq && !s.on_mc && !s.dbk.on && !s.sao.on && !s.intra.on) { s.disabled = true; return; }     // TVC_HM=none: the unmodified path
+  if (!s.on_me && !s.on_frac && !s.on_tq && !s.on_rdoq && !s.on_mc && !s.dbk.on && !s.sao.on && !s.intra.on && !s.on_cand) { s.disabled = true; return; }     // TVC_HM=none: the unmodified path
   if (s.h) {                  // the decoder learns the picture size after its first transforms: start over with the real size
     tvc_ctx_destroy(s.h);
     s.h = nullptr;
@@ -324,7 +331,7 @@ void tlibcuda_picture_start(TComPic* pic, TComSlice* slice)
   const auto t_start = std::chrono::steady_clock::now();
   ensure_ctx(org->getWidth(), org->getHeight());
   State& s = S();
-  if (!s.h || (!s.on_me && !s.on_frac)) return;
+  if (!s.h || (!s.on_me && !s.on_frac && !s.on_cand)) return;
   s.wp = slice->getPPS()->getUseWP() || slice->getPPS()->getWPBiPred();
   s.cur_slot = slot_for(org, slice->getPOC(), true, false);
   s.num_table_refs = 0;
@@ -580,6 +587,76 @@ bool tlibcuda_xDeQuant(const int* src, int* dst, int w, int h, int per, int rem)
   if (!s.h || !s.on_tq || w != h) return false;
   CK(tvc_xDeQuant(s.h, src, dst, w, h, per, rem));
   s.n_dq++;
+  return true;
+}
+
+// ---- merge / AMVP candidate evaluation (TEncSearch::xMergeEstimation :3096-3149, xGetTemplateCost :4057-4118)
+static void pu_origin(TComDataCU* cu, unsigned partAddr, int& x, int& y)
+{
+  const unsigned raster = g_auiZscanToRaster[cu->getZorderIdxInCU() + partAddr];
+  const int ctus_x = (int)cu->getPic()->getFrameWidthInCU();
+  x = (int)(cu->getAddr() % ctus_x) * (int)g_uiMaxCUWidth + (int)g_auiRasterToPelX[raster];
+  y = (int)(cu->getAddr() / ctus_x) * (int)g_uiMaxCUHeight + (int)g_auiRasterToPelY[raster];
+}
+
+bool tlibcuda_merge_costs(TComDataCU* cu, int puIdx, TComMvField* cands, const unsigned char* interDir, int numCand, bool hadamard,
+                          unsigned* dist)
+{
+  State& s = S();
+  if (!s.h || !s.on_cand || s.cur_slot < 0 || s.wp || numCand <= 0 || numCand > 5) return false;
+  (void)interDir;
+  UInt partAddr = 0;
+  Int w = 0, h = 0;
+  cu->getPartIndexAndSize((UInt)puIdx, partAddr, w, h);
+  int x, y;
+  pu_origin(cu, partAddr, x, y);
+  TComSlice* sl = cu->getSlice();
+  tvc_pu pus[5];
+  for (int i = 0; i < numCand; i++) {
+    tvc_pu& p = pus[i];
+    p.x = x; p.y = y; p.w = w; p.h = h;
+    p.ref_slot0 = p.ref_slot1 = -1; p.mvx0 = p.mvy0 = p.mvx1 = p.mvy1 = 0;
+    const int r0 = cands[2 * i].getRefIdx(), r1 = cands[2 * i + 1].getRefIdx();
+    if (r0 < 0 && r1 < 0) return false;
+    TComMv m0 = cands[2 * i].getMv(), m1 = cands[2 * i + 1].getMv();
+    // xCheckIdenticalMotion (TComPrediction.cpp:392-408): same picture, same vector in both lists -> uni-prediction from list 0
+    bool use1 = r1 >= 0;
+    if (r0 >= 0 && r1 >= 0 && sl->isInterB() && sl->getRefPic(REF_PIC_LIST_0, r0)->getPOC() == sl->getRefPic(REF_PIC_LIST_1, r1)->getPOC() && m0 == m1)
+      use1 = false;
+    if (r0 >= 0) {
+      TComPic* rp = sl->getRefPic(REF_PIC_LIST_0, r0);
+      cu->clipMv(m0);                        // xPredInterUni :483-490
+      p.ref_slot0 = slot_for(rp->getPicYuvRec(), rp->getPOC(), false, true);
+      p.mvx0 = m0.getHor(); p.mvy0 = m0.getVer();
+    }
+    if (use1) {
+      TComPic* rp = sl->getRefPic(REF_PIC_LIST_1, r1);
+      cu->clipMv(m1);
+      p.ref_slot1 = slot_for(rp->getPicYuvRec(), rp->getPOC(), false, true);
+      p.mvx1 = m1.getHor(); p.mvy1 = m1.getVer();
+    }
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  CK(tvc_pred_cost_batch(s.h, s.cur_slot, hadamard ? TVC_DIST_HADS : TVC_DIST_SAD, numCand, pus, dist));
+  s.cand_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  s.n_merge++; s.n_merge_cands += (unsigned long long)numCand;
+  return true;
+}
+
+bool tlibcuda_template_sad(TComDataCU* cu, TComPic* refPic, unsigned partAddr, int mvx, int mvy, int w, int h, unsigned& sad)
+{
+  State& s = S();
+  if (!s.h || !s.on_cand || s.cur_slot < 0 || s.wp) return false;
+  tvc_pu p;
+  pu_origin(cu, partAddr, p.x, p.y);
+  p.w = w; p.h = h;
+  p.ref_slot0 = slot_for(refPic->getPicYuvRec(), refPic->getPOC(), false, true);
+  p.mvx0 = mvx; p.mvy0 = mvy;
+  p.ref_slot1 = -1; p.mvx1 = p.mvy1 = 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  CK(tvc_pred_cost_batch(s.h, s.cur_slot, TVC_DIST_SAD, 1, &p, &sad));
+  s.cand_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  s.n_template++;
   return true;
 }
 

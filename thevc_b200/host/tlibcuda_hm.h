@@ -84,6 +84,16 @@ void tlibcuda_sao_end(TComPic* pic, int yCbCr);
 bool tlibcuda_intra_rough(const int* adiBuf, unsigned width, const short* org, unsigned orgStride, bool above, bool left, unsigned* sad35);
 void tlibcuda_intra_note(unsigned mode, unsigned sad);
 
+/* ---- merge / AMVP candidate evaluation (TVC_HM=...,cand).  TEncSearch::xMergeEstimation (TEncSearch.cpp:3096-3149):
+ * before the candidate loop all candidates' motions go to one tvc_pred_cost_batch (luma motion compensation + HAD / SAD against
+ * the original, = xGetInterPredictionError per candidate); inside the loop uiCostCand is read from the result, the merge-index
+ * bits and the strict "<" stay.  TEncSearch::xGetTemplateCost (:4057-4118): the prediction + SAD of one AMVP candidate, the
+ * m_auiMVPIdxCost term stays.  Weighted prediction: reference path. */
+class TComMvField;
+bool tlibcuda_merge_costs(TComDataCU* cu, int puIdx, TComMvField* cands, const unsigned char* interDir, int numCand, bool hadamard,
+                          unsigned* dist);
+bool tlibcuda_template_sad(TComDataCU* cu, TComPic* refPic, unsigned partAddr, int mvx, int mvy, int w, int h, unsigned& sad);
+
 /* ---- frame sharding of all-intra sequences (thevc_b200/host/shard_encode.py).  TVC_POC_OFFSET=k: this process
  * encodes the frames from input frame k on (-fs k) as POC k, k+1, ... (TEncTop::m_iPOCLast starts at k-1, TEncTop.cpp:54; the
  * frame limit of compressGOP, TEncGOP.cpp:211, moves with it) and, for k > 0, writes no VPS/SPS/PPS (m_bSeqFirst,

@@ -173,6 +173,15 @@ class TLibCuda:
             arr = _arr(PU, pus)
             self._ck(self.L.tvc_mc_batch(self.h, dst_slot, len(pus), C.cast(arr, C.c_void_p)))
 
+    def pred_cost_batch(self, cur_slot: int, kind: int, pus: Sequence[PU]) -> np.ndarray:
+        """luma prediction + distortion (capi.DIST_SAD / DIST_HADS) of candidate motions against the original of cur_slot:
+        xGetInterPredictionError per merge candidate / xGetTemplateCost's prediction + SAD per AMVP candidate"""
+        out = np.zeros(len(pus), np.uint32)
+        if len(pus):
+            arr = _arr(PU, pus)
+            self._ck(self.L.tvc_pred_cost_batch(self.h, cur_slot, kind, len(pus), C.cast(arr, C.c_void_p), ptr(out)))
+        return out
+
     def mc_block(self, ref_slot: int, x: int, y: int, w: int, h: int, mvx: int, mvy: int, bi: bool):
         """one PU from one reference into dense arrays (Y w*h, U/V (w/2)*(h/2)); bi keeps 14-bit intermediates"""
         oy = np.zeros((h, w), np.int16); ou = np.zeros((h // 2, w // 2), np.int16); ov = np.zeros_like(ou)
