@@ -153,6 +153,23 @@ int tvc_mc_batch_dev(tvc_ctx* ctx, int dst_slot, int n, const tvc_pu* pus_dev);
 int tvc_pred_cost_batch(tvc_ctx* ctx, int cur_slot, int kind, int n, const tvc_pu* pus, uint32_t* dist);
 int tvc_pred_cost_batch_dev(tvc_ctx* ctx, int cur_slot, int kind, int n, const tvc_pu* pus_dev, uint32_t* dist_dev);
 
+/* The look-up form of the same evaluation (what makes it pay inside the CU loop, where the reference asks one PU at a time): for
+ * one (CTU, reference, clipped MV) the distortion of EVERY PU of the CTU with that motion, as three inclusive 2-D prefix sums over
+ * the CTU: SAD of the 4x4 blocks (17x17), xCalcHADs4x4 of the 4x4 tiles (17x17), xCalcHADs8x8 of the 8x8 tiles (9x9); entry (r, c)
+ * = sum over block / tile rows < r and columns < c, row 0 / column 0 are zero.  For a PU at (px, py, w, h) inside the CTU:
+ *   SAD  = S(I_sad4; px/4, py/4, w/4, h/4) >> bitIncrement                 (xGetSAD*, iSubShift 0)
+ *   HADs = S(I_had8; px/8, py/8, w/8, h/8) >> bitIncrement when w and h are multiples of 8, else S(I_had4; ...) >> bitIncrement
+ * with S(I; x, y, w, h) = I[y+h][x+w] - I[y][x+w] - I[y+h][x] + I[y][x].  Uni-prediction (clipped pels); the host keeps the grids
+ * of a picture in a table keyed by (CTU, reference, MV) and serves xGetTemplateCost / xMergeEstimation from it.                 */
+typedef struct {
+  int32_t ref_slot;
+  int32_t x0, y0;              /* CTU origin in the picture (multiples of 64)                                      */
+  int32_t mvx, mvy;            /* quarter-pel, after TComDataCU::clipMv                                            */
+} tvc_grid_job;
+#define TVC_GRID_WORDS (289 + 289 + 81)     /* I_sad4[17][17], I_had4[17][17], I_had8[9][9]                        */
+int tvc_ctu_cost_grids(tvc_ctx* ctx, int cur_slot, int n, const tvc_grid_job* jobs, uint32_t* grids /* n * TVC_GRID_WORDS */);
+int tvc_ctu_cost_grids_dev(tvc_ctx* ctx, int cur_slot, int n, const tvc_grid_job* jobs_dev, uint32_t* grids_dev);
+
 /* One PU, one reference list, into caller buffers: TComPrediction::xPredInterUni = xPredInterLumaBlk +
  * xPredInterChromaBlk (TComPrediction.cpp:483-490, 554-645).  (x, y, w, h) luma rectangle, MV already
  * clipped, dst_* point at the PU's first sample inside a TComYuv.  bi != 0 keeps the 14-bit intermediate

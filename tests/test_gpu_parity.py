@@ -820,3 +820,47 @@ def test_pred_cost_batch(ctx8, ctx10, orc, bd):
             assert int(got[i]) == int(exp), (kind, i, pu.x, pu.y, pu.w, pu.h, pu.ref_slot0, pu.ref_slot1)
     with pytest.raises(Exception):
         t.pred_cost_batch(0, capi.DIST_SSE, pus[:1])
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_ctu_cost_grids_serve_every_pu(ctx8, ctx10, orc, bd):
+    """the look-up form of SURVEY 8f-3: from the three prefix-sum grids of one (CTU, reference, MV) the SAD and the SATD of EVERY
+    PU of the 593-PU census with that motion, equal to predicting that PU alone and running xGetSAD / xGetHADs on it (interior CTU,
+    partial right / bottom CTUs, MVs clipped at all four picture edges, integer / half / quarter positions)"""
+    t = ctx8 if bd == 8 else ctx10
+    rng = np.random.default_rng(170 + bd)
+    cur, ref = _pic(rng, bd), _pic(rng, bd)
+    t.upload(0, cur); t.upload(1, ref)
+    census = t.me_census()
+    cases = [(64, 64, 13, -7), (128, 64, 0, 0), (192, 128, 8, 5), (384, 0, 2, 0), (384, 192, 0, 3), (0, 192, -9, 30),
+             (0, 0, -4000, -4000), (384, 192, 4000, 4000), (0, 192, -4000, 4000), (384, 0, 4000, -4000), (256, 128, 7, 7)]
+    jobs = np.zeros(len(cases), capi.GRID_JOB_DTYPE)
+    for i, (x0, y0, mvx, mvy) in enumerate(cases):
+        jobs[i] = (1, x0, y0, mvx, mvy)
+    # a far MV is clipped per CU in the reference; the CTU-level clip is what a 64x64 PU would use -- the grid must hold for it and,
+    # with the clamped window reads, for any MV value at all
+    for i, (x0, y0, mvx, mvy) in enumerate(cases):
+        if abs(mvx) > 1000:
+            jobs[i]["mvx"], jobs[i]["mvy"] = _clip_mv(orc, x0, y0, mvx, mvy)
+    sad4, had4, had8 = t.ctu_cost_grids(0, jobs)
+
+    def S(I, x, y, w, h):
+        return int(I[y + h, x + w]) - int(I[y, x + w]) - int(I[y + h, x]) + int(I[y, x])
+    checked = 0
+    for i, j in enumerate(jobs):
+        x0, y0, mvx, mvy = int(j["x0"]), int(j["y0"]), int(j["mvx"]), int(j["mvy"])
+        for (px, py, w, h) in census[:, :4]:
+            px, py, w, h = int(px), int(py), int(w), int(h)
+            if x0 + px + w > W or y0 + py + h > H:
+                continue
+            pred = np.zeros((h, w), np.int16)
+            orc.orc_pred_inter_luma_blk(optr(ref.buf_y, ref.origin(0) + (y0 + py) * ref.stride + x0 + px), ref.stride, mvx, mvy, w, h,
+                                        optr(pred), w, 0, bd)
+            o = optr(cur.buf_y, cur.origin(0) + (y0 + py) * cur.stride + x0 + px)
+            assert S(sad4[i], px // 4, py // 4, w // 4, h // 4) >> (bd - 8) == orc.orc_sad_generic(o, cur.stride, optr(pred), w, w, h, bd - 8)
+            got = S(had8[i], px // 8, py // 8, w // 8, h // 8) if (w % 8 == 0 and h % 8 == 0) else S(had4[i], px // 4, py // 4, w // 4, h // 4)
+            if w % 8 == 0 and h % 8 == 0:
+                assert px % 8 == 0 and py % 8 == 0
+            assert got >> (bd - 8) == orc.orc_hads(o, cur.stride, optr(pred), w, w, h, bd - 8), (i, px, py, w, h)
+            checked += 1
+    assert checked > 4000

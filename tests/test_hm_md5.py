@@ -161,11 +161,12 @@ def test_intra_rough_search_on_device(tmp_path, cfg, frames, w, h):
     assert int(il[-1].split()[4]) > 500 and " 0 smaller PUs" in il[-1], il[-1]
 
 
+@pytest.mark.parametrize("mode", ["cand", "candgrid"])
 @pytest.mark.parametrize("cfg,frames", [
     ("encoder_lowdelay_P_main.cfg", 3),        # P slices: uni-predicted merge candidates, AMVP templates of 4 references
     ("encoder_randomaccess_main.cfg", 5),      # B slices: bi-predicted candidates (addAvg), identical-motion reduction
 ])
-def test_candidate_evaluation_on_device(tmp_path, cfg, frames):
+def test_candidate_evaluation_on_device(tmp_path, cfg, frames, mode):
     """SURVEY 8f-3 inside the real encoder: every xMergeEstimation candidate set and every xGetTemplateCost call served by
     tvc_pred_cost_batch; the merge / AMVP decisions, hence the bitstream, are the reference's."""
     _need()
@@ -174,8 +175,14 @@ def test_candidate_evaluation_on_device(tmp_path, cfg, frames):
     _yuv(yuv, w, h, frames)
     ref_bin, cuda_bin = str(tmp_path / "ref.bin"), str(tmp_path / "cuda.bin")
     _encode(ENC_REF, cfg, yuv, w, h, frames, ref_bin)
-    r = _encode(ENC_CUDA, cfg, yuv, w, h, frames, cuda_bin, env={"TVC_HM": "cand"})
+    # cand: one device call per xMergeEstimation / xGetTemplateCost; candgrid: look-up in CTU-wide (CTU, reference, MV) cost grids
+    r = _encode(ENC_CUDA, cfg, yuv, w, h, frames, cuda_bin, env={"TVC_HM": mode})
     assert _md5(cuda_bin) == _md5(ref_bin)
+    if mode == "candgrid":
+        gl = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda candidate look-up:")]
+        assert gl, r.stderr[-600:]
+        print(gl[-1])
+        assert int(gl[-1].split()[3]) > 5 * int(gl[-1].split()[10]), gl[-1]       # mostly look-ups
     cl = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda candidate evaluation:")]
     assert cl, r.stderr[-600:]
     print(cl[-1])

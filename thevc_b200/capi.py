@@ -80,6 +80,8 @@ PHASES = ("me_tables", "me_search", "me_frac", "mc", "fwd_tq", "inv_tq", "other"
 # numpy views of the ABI structs (same layout) for bulk results
 ME_RESULT_DTYPE = np.dtype([("mvx", "<i4"), ("mvy", "<i4"), ("sad", "<u4"), ("n_sads", "<u4")])
 INTRA_MODES = 35
+GRID_WORDS = 289 + 289 + 81
+GRID_JOB_DTYPE = np.dtype([("ref_slot", "<i4"), ("x0", "<i4"), ("y0", "<i4"), ("mvx", "<i4"), ("mvy", "<i4")])
 INTRA_JOB_DTYPE = np.dtype([("log2_size", "<i4"), ("line_offset", "<i4"), ("org_offset", "<i4"), ("org_stride", "<i4"),
                             ("above", "<i4"), ("left", "<i4")])
 FRAC_RESULT_DTYPE = np.dtype([("halfx", "<i4"), ("halfy", "<i4"), ("qtrx", "<i4"), ("qtry", "<i4"), ("cost_half", "<u4"), ("cost", "<u4")])
@@ -170,6 +172,8 @@ SIGNATURES = {
     "tvc_sao_plane": (ci, [vp, ci, ci, ci, vp]),
     "tvc_pred_cost_batch": (ci, [vp, ci, ci, ci, vp, vp]),
     "tvc_pred_cost_batch_dev": (ci, [vp, ci, ci, ci, vp, vp]),
+    "tvc_ctu_cost_grids": (ci, [vp, ci, ci, vp, vp]),
+    "tvc_ctu_cost_grids_dev": (ci, [vp, ci, ci, vp, vp]),
     "tvc_intra_rough_batch": (ci, [vp, ci, vp, vp, C.c_size_t, vp, C.c_size_t, vp]),
     "tvc_intra_rough_batch_dev": (ci, [vp, ci, vp, vp, vp, vp, vp, vp]),
     "tvc_intra_rough": (ci, [vp, ci, vp, vp, ci, ci, ci, vp, vp]),

@@ -186,6 +186,83 @@ __global__ void __launch_bounds__(256) k_pred_cost(PlaneTable pt, int cur_slot, 
   if (threadIdx.x == 0) out[blockIdx.x] = s_sum >> (bd - 8);
 }
 
+// ---- CTU-wide candidate cost grids (the look-up form of merge / AMVP candidate evaluation)
+// One CTA per (CTU, reference, clipped MV): the 64x64 luma prediction at that MV (reference window staged into shared memory with
+// coordinates clamped to the padded plane = the picture's replicated border, so every sample equals what a PU-sized prediction
+// reads), then, against the original CTU, the SAD of every 4x4 block, the xCalcHADs4x4 value of every 4x4 tile and the xCalcHADs8x8
+// value of every 8x8 tile, each as an inclusive 2-D prefix sum (17x17, 17x17, 9x9).  The distortion of ANY PU of the CTU with this
+// motion is then four look-ups: a PU's SAD is the sum of its blocks (xGetSAD*, iSubShift 0), its SATD the sum of its tiles (xGetHADs
+// tiles from the PU origin; PU origins are multiples of 8 whenever both sides are, else multiples of 4).
+constexpr int kGridWin = 64 + 7;
+__global__ void __launch_bounds__(256) k_ctu_cost_grids(PlaneTable pt, int cur_slot, int n, const tvc_grid_job* __restrict__ jobs,
+                                                        uint32_t* __restrict__ out, int bd, int plane_w, int plane_h, int mx, int my)
+{
+  __shared__ int16_t s_win[kGridWin * kGridWin];
+  __shared__ int16_t s_tmp[kGridWin * 64];
+  __shared__ int16_t s_pred[64 * 64];
+  __shared__ uint32_t s_g[3][17 * 17];
+  const tvc_grid_job j = jobs[blockIdx.x];
+  const int stride = pt.stride[0], tid = threadIdx.x;
+  const int xf = j.mvx & 3, yf = j.mvy & 3;
+  const int wx0 = j.x0 + (j.mvx >> 2) - 3, wy0 = j.y0 + (j.mvy >> 2) - 3;
+  const int16_t* ref = pt.org[j.ref_slot][0];
+  for (int i = tid; i < kGridWin * kGridWin; i += 256) {
+    const int y = i / kGridWin, x = i - y * kGridWin;
+    const int gx = min(max(wx0 + x, -mx), plane_w + mx - 1), gy = min(max(wy0 + y, -my), plane_h + my - 1);
+    s_win[i] = ref[(ptrdiff_t)gy * stride + gx];
+  }
+  __syncthreads();
+  // xPredInterLumaBlk, bi = false (TComPrediction.cpp:554-590)
+  if (yf == 0) {
+    for (int i = tid; i < 4096; i += 256) s_pred[i] = if_sample<8>(s_win + ((i >> 6) + 3) * kGridWin + (i & 63) + 3, 1, xf, true, true, bd);
+  } else if (xf == 0) {
+    for (int i = tid; i < 4096; i += 256) s_pred[i] = if_sample<8>(s_win + ((i >> 6) + 3) * kGridWin + (i & 63) + 3, kGridWin, yf, true, true, bd);
+  } else {
+    for (int i = tid; i < kGridWin * 64; i += 256) s_tmp[i] = if_sample<8>(s_win + (i >> 6) * kGridWin + (i & 63) + 3, 1, xf, true, false, bd);
+    __syncthreads();
+    for (int i = tid; i < 4096; i += 256) s_pred[i] = if_sample<8>(s_tmp + ((i >> 6) + 3) * 64 + (i & 63), 64, yf, false, true, bd);
+  }
+  for (int i = tid; i < 3 * 17 * 17; i += 256) (&s_g[0][0])[i] = 0;
+  __syncthreads();
+  const int16_t* org = pt.org[cur_slot][0] + (ptrdiff_t)j.y0 * stride + j.x0;      // rows / columns past the picture lie in the slot's margin
+  {
+    const int by = tid >> 4, bx = tid & 15;
+    const int16_t* o = org + (ptrdiff_t)(by * 4) * stride + bx * 4;
+    const int16_t* p = s_pred + (by * 4) * 64 + bx * 4;
+    uint32_t sad = 0;
+#pragma unroll
+    for (int y = 0; y < 4; y++)
+#pragma unroll
+      for (int x = 0; x < 4; x++) sad += (uint32_t)abs((int)o[(ptrdiff_t)y * stride + x] - (int)p[y * 64 + x]);
+    s_g[0][(by + 1) * 17 + bx + 1] = sad;
+    s_g[1][(by + 1) * 17 + bx + 1] = had_tile<4>(o, stride, p, 64);
+    if (tid < 64) {
+      const int ty = tid >> 3, tx = tid & 7;
+      s_g[2][(ty + 1) * 17 + tx + 1] = had_tile<8>(org + (ptrdiff_t)(ty * 8) * stride + tx * 8, stride, s_pred + (ty * 8) * 64 + tx * 8, 64);
+    }
+  }
+  __syncthreads();
+  // prefix sums: rows, then columns (thread per line)
+  if (tid < 3 * 16) {
+    const int g = tid >> 4, r = (tid & 15) + 1;
+    if (g < 2 || r <= 8) { uint32_t a = 0; for (int c = 1; c <= (g < 2 ? 16 : 8); c++) { a += s_g[g][r * 17 + c]; s_g[g][r * 17 + c] = a; } }
+  }
+  __syncthreads();
+  if (tid < 3 * 16) {
+    const int g = tid >> 4, c = (tid & 15) + 1;
+    if (g < 2 || c <= 8) { uint32_t a = 0; for (int r = 1; r <= (g < 2 ? 16 : 8); r++) { a += s_g[g][r * 17 + c]; s_g[g][r * 17 + c] = a; } }
+  }
+  __syncthreads();
+  uint32_t* o = out + (size_t)blockIdx.x * TVC_GRID_WORDS;
+  for (int i = tid; i < TVC_GRID_WORDS; i += 256) {
+    uint32_t v;
+    if (i < 289) v = s_g[0][i];
+    else if (i < 578) v = s_g[1][i - 289];
+    else { const int k = i - 578; v = s_g[2][(k / 9) * 17 + (k % 9)]; }
+    o[i] = v;
+  }
+}
+
 // one PU, one list, dense output [Y w*h][U (w/2)(h/2)][V]: the drop-in for xPredInterUni
 __global__ void __launch_bounds__(256) k_mc_block(PlaneTable pt, int ref_slot, int x, int y, int w, int h, int mvx, int mvy, int bi,
                                                   int bd, int16_t* __restrict__ out)
@@ -321,6 +398,42 @@ int tvc_pred_cost_batch(tvc_ctx* c, int cur_slot, int kind, int n, const tvc_pu*
   TVC_CUDA(c, cudaMemcpyAsync(c->out.host, c->out.dev, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
   TVC_CUDA(c, cudaStreamSynchronize(c->stream));
   memcpy(dist, c->out.host, (size_t)n * 4);
+  return TVC_OK;
+}
+
+int tvc_ctu_cost_grids_dev(tvc_ctx* c, int cur_slot, int n, const tvc_grid_job* jobs_dev, uint32_t* grids_dev)
+{
+  if (!c || !valid_slot(c, cur_slot) || n < 0 || (n && (!jobs_dev || !grids_dev))) return set_err(c, TVC_ERR_ARG, "tvc_ctu_cost_grids_dev: bad argument");
+  if (n == 0) return TVC_OK;
+  const Pic& p = c->pics[cur_slot];
+  ProfScope ps(c, TVC_PH_MC);
+  k_ctu_cost_grids<<<n, 256, 0, c->stream>>>(c->planes, cur_slot, n, jobs_dev, grids_dev, c->cfg.bit_depth, p.w[0], p.h[0], p.mx[0], p.my[0]);
+  TVC_LAUNCH_CHECK(c);
+  return TVC_OK;
+}
+
+int tvc_ctu_cost_grids(tvc_ctx* c, int cur_slot, int n, const tvc_grid_job* jobs, uint32_t* grids)
+{
+  if (!c || !valid_slot(c, cur_slot) || n < 0 || (n && (!jobs || !grids))) return set_err(c, TVC_ERR_ARG, "tvc_ctu_cost_grids: bad argument");
+  if (n == 0) return TVC_OK;
+  const Pic& p = c->pics[cur_slot];
+  for (int i = 0; i < n; i++) {
+    const tvc_grid_job& j = jobs[i];
+    // the CTU lies in the picture; the MV may point anywhere within +-2^14 quarter pels (reads are clamped to the padded plane)
+    if (!valid_slot(c, j.ref_slot) || j.x0 < 0 || j.y0 < 0 || (j.x0 & 63) || (j.y0 & 63) || j.x0 >= p.w[0] || j.y0 >= p.h[0] ||
+        j.mvx < -(1 << 14) || j.mvx > (1 << 14) || j.mvy < -(1 << 14) || j.mvy > (1 << 14))
+      return set_err(c, TVC_ERR_ARG, "tvc_ctu_cost_grids: job %d invalid", i);
+  }
+  int r;
+  const size_t out_b = (size_t)n * TVC_GRID_WORDS * 4;
+  if ((r = ensure_scratch(c, c->in, (size_t)n * sizeof(tvc_grid_job)))) return r;
+  if ((r = ensure_scratch(c, c->out, out_b))) return r;
+  memcpy(c->in.host, jobs, (size_t)n * sizeof(tvc_grid_job));
+  TVC_CUDA(c, cudaMemcpyAsync(c->in.dev, c->in.host, (size_t)n * sizeof(tvc_grid_job), cudaMemcpyHostToDevice, c->stream));
+  if ((r = tvc_ctu_cost_grids_dev(c, cur_slot, n, (const tvc_grid_job*)c->in.dev, (uint32_t*)c->out.dev))) return r;
+  TVC_CUDA(c, cudaMemcpyAsync(c->out.host, c->out.dev, out_b, cudaMemcpyDeviceToHost, c->stream));
+  TVC_CUDA(c, cudaStreamSynchronize(c->stream));
+  memcpy(grids, c->out.host, out_b);
   return TVC_OK;
 }
 

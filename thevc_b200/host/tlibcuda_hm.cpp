@@ -10,6 +10,7 @@
 #include <map>
 #include <chrono>
 #include <algorithm>
+#include <unordered_map>
 #include <utility>
 
 #define private public
@@ -130,6 +131,10 @@ struct State {
   double batch_seconds = 0.0, prepass_seconds = 0.0;      // host wall time spent inside tvc_me_ctu / picture_start
   bool on_me = true, on_frac = true, on_tq = true, on_rdoq = true, on_mc = true, on_tables = true, verbose = false, disabled = false;
   bool on_cand = false;                    // merge / AMVP candidate evaluation (TVC_HM=...,cand)
+  bool on_cand_grid = false;               // ... served by look-up from CTU-wide cost grids (TVC_HM=...,candgrid)
+  struct Grid { uint32_t w[TVC_GRID_WORDS]; };
+  std::unordered_map<unsigned long long, Grid> grids;      // (CTU, reference slot, clipped MV) -> prefix-sum grids; cleared per picture
+  unsigned long long n_grid_hits = 0, n_grid_fills = 0;
   unsigned long long n_merge = 0, n_merge_cands = 0, n_template = 0;
   double cand_seconds = 0.0;
   int w = 0, ht = 0;
@@ -169,6 +174,9 @@ void report()
             s.dbk.n_pics, s.dbk.n_units, s.dbk.seconds);
   if (s.sao.on && s.sao.n_planes)
     fprintf(stderr, "TLibCuda SAO: %llu planes filtered on the device, %.3f s (upload + kernel + download)\n", s.sao.n_planes, s.sao.seconds);
+  if (s.on_cand_grid)
+    fprintf(stderr, "TLibCuda candidate look-up: %llu of %llu candidate costs served from %llu CTU-wide (CTU, reference, MV) cost grids\n",
+            s.n_grid_hits, s.n_grid_hits + s.n_grid_fills, s.n_grid_fills);
   if (s.on_cand)
     fprintf(stderr, "TLibCuda candidate evaluation: %llu xMergeEstimation calls (%llu candidates) and %llu xGetTemplateCost calls on the device, %.3f s in tvc_pred_cost_batch\n",
             s.n_merge, s.n_merge_cands, s.n_template, s.cand_seconds);
@@ -240,6 +248,7 @@ void parse_env()
   s.dbk.dump = strstr(e, "dbkdump") != nullptr;
   s.dbk.on = !s.dbk.dump && strstr(e, "dbk") != nullptr;
   s.on_cand = strstr(e, "cand") != nullptr;
+  s.on_cand_grid = strstr(e, "candgrid") != nullptr;
   s.intra.dump = strstr(e, "intradump") != nullptr;
   if (const char* p = strstr(e, "intra")) {
     s.intra.on = !s.intra.dump;
@@ -346,6 +355,7 @@ void tlibcuda_picture_start(TComPic* pic, TComSlice* slice)
     }
   }
   s.groups.clear();
+  s.grids.clear();
   s.last.valid = false;
   if (s.census_index.empty()) {
     tvc_census_pu cen[TVC_ME_CENSUS];
@@ -599,6 +609,36 @@ static void pu_origin(TComDataCU* cu, unsigned partAddr, int& x, int& y)
   y = (int)(cu->getAddr() / ctus_x) * (int)g_uiMaxCUHeight + (int)g_auiRasterToPelY[raster];
 }
 
+// cost of the PU at (px, py, w, h) inside its CTU with the clipped motion (slot, mvx, mvy): look-up in the CTU-wide grids, filled by one
+// tvc_ctu_cost_grids call on the first request of a (CTU, reference, MV)
+static unsigned grid_cost(TComDataCU* cu, unsigned partAddr, int w, int h, int slot, int mvx, int mvy, bool hadamard)
+{
+  State& s = S();
+  const unsigned raster = g_auiZscanToRaster[cu->getZorderIdxInCU() + partAddr];
+  const int px = (int)g_auiRasterToPelX[raster], py = (int)g_auiRasterToPelY[raster];
+  const unsigned long long key = ((unsigned long long)cu->getAddr() << 38) | ((unsigned long long)(slot & 63) << 32) |
+                                 ((unsigned long long)(mvx & 0xffff) << 16) | (unsigned long long)(mvy & 0xffff);
+  auto it = s.grids.find(key);
+  if (it == s.grids.end()) {
+    const int ctus_x = (int)cu->getPic()->getFrameWidthInCU();
+    tvc_grid_job j = {slot, (int)(cu->getAddr() % ctus_x) * 64, (int)(cu->getAddr() / ctus_x) * 64, mvx, mvy};
+    State::Grid g;
+    const auto t0 = std::chrono::steady_clock::now();
+    CK(tvc_ctu_cost_grids(s.h, s.cur_slot, 1, &j, g.w));
+    s.cand_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    it = s.grids.emplace(key, g).first;
+    s.n_grid_fills++;
+  } else
+    s.n_grid_hits++;
+  const uint32_t* g = it->second.w;
+  const bool h8 = hadamard && !(w & 7) && !(h & 7);
+  const uint32_t* I = !hadamard ? g : (h8 ? g + 578 : g + 289);
+  const int n = h8 ? 9 : 17, sh = h8 ? 3 : 2;
+  const int x0 = px >> sh, y0 = py >> sh, x1 = (px + w) >> sh, y1 = (py + h) >> sh;
+  const unsigned sum = I[y1 * n + x1] - I[y0 * n + x1] - I[y1 * n + x0] + I[y0 * n + x0];
+  return sum >> g_uiBitIncrement;
+}
+
 bool tlibcuda_merge_costs(TComDataCU* cu, int puIdx, TComMvField* cands, const unsigned char* interDir, int numCand, bool hadamard,
                           unsigned* dist)
 {
@@ -636,10 +676,20 @@ bool tlibcuda_merge_costs(TComDataCU* cu, int puIdx, TComMvField* cands, const u
       p.mvx1 = m1.getHor(); p.mvy1 = m1.getVer();
     }
   }
+  s.n_merge++; s.n_merge_cands += (unsigned long long)numCand;
+  bool all_uni = true;
+  for (int i = 0; i < numCand; i++) all_uni &= (pus[i].ref_slot0 < 0) != (pus[i].ref_slot1 < 0);
+  if (s.on_cand_grid && all_uni && g_uiMaxCUWidth == 64 && (((x & 7) == 0 && (y & 7) == 0) || (w & 7) || (h & 7))) {
+    for (int i = 0; i < numCand; i++) {
+      const tvc_pu& p = pus[i];
+      dist[i] = p.ref_slot0 >= 0 ? grid_cost(cu, partAddr, w, h, p.ref_slot0, p.mvx0, p.mvy0, hadamard)
+                                 : grid_cost(cu, partAddr, w, h, p.ref_slot1, p.mvx1, p.mvy1, hadamard);
+    }
+    return true;
+  }
   const auto t0 = std::chrono::steady_clock::now();
   CK(tvc_pred_cost_batch(s.h, s.cur_slot, hadamard ? TVC_DIST_HADS : TVC_DIST_SAD, numCand, pus, dist));
   s.cand_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  s.n_merge++; s.n_merge_cands += (unsigned long long)numCand;
   return true;
 }
 
@@ -651,6 +701,11 @@ bool tlibcuda_template_sad(TComDataCU* cu, TComPic* refPic, unsigned partAddr, i
   pu_origin(cu, partAddr, p.x, p.y);
   p.w = w; p.h = h;
   p.ref_slot0 = slot_for(refPic->getPicYuvRec(), refPic->getPOC(), false, true);
+  if (s.on_cand_grid && g_uiMaxCUWidth == 64) {
+    sad = grid_cost(cu, partAddr, w, h, p.ref_slot0, mvx, mvy, false);
+    s.n_template++;
+    return true;
+  }
   p.mvx0 = mvx; p.mvy0 = mvy;
   p.ref_slot1 = -1; p.mvx1 = p.mvy1 = 0;
   const auto t0 = std::chrono::steady_clock::now();

@@ -182,6 +182,13 @@ class TLibCuda:
             self._ck(self.L.tvc_pred_cost_batch(self.h, cur_slot, kind, len(pus), C.cast(arr, C.c_void_p), ptr(out)))
         return out
 
+    def ctu_cost_grids(self, cur_slot: int, jobs: np.ndarray):
+        """prefix-sum cost grids of (CTU, reference, MV) jobs (capi.GRID_JOB_DTYPE): (I_sad4 [n,17,17], I_had4 [n,17,17], I_had8 [n,9,9])"""
+        jobs = np.ascontiguousarray(jobs, capi.GRID_JOB_DTYPE)
+        out = np.zeros((len(jobs), capi.GRID_WORDS), np.uint32)
+        self._ck(self.L.tvc_ctu_cost_grids(self.h, cur_slot, len(jobs), ptr(jobs), ptr(out)))
+        return out[:, :289].reshape(-1, 17, 17), out[:, 289:578].reshape(-1, 17, 17), out[:, 578:].reshape(-1, 9, 9)
+
     def mc_block(self, ref_slot: int, x: int, y: int, w: int, h: int, mvx: int, mvy: int, bi: bool):
         """one PU from one reference into dense arrays (Y w*h, U/V (w/2)*(h/2)); bi keeps 14-bit intermediates"""
         oy = np.zeros((h, w), np.int16); ou = np.zeros((h // 2, w // 2), np.int16); ov = np.zeros_like(ou)
