@@ -466,6 +466,17 @@ typedef struct {
 /* units: one per CTU in raster order (host array); samples of CTUs with type < 0 are copied                        */
 int tvc_sao_plane(tvc_ctx* ctx, int src_slot, int dst_slot, int plane, const tvc_sao_unit* units);
 
+/* ---------------------------------------------------------------------------------- picture hash / PSNR sums
+ * what the decoded-picture-hash SEI and the PSNR report need of a reconstruction, taken where the picture
+ * already lies.  tvc_pic_hash = calcMD5 / calcCRC / calcChecksum (TLibCommon/TComPicYuvMD5.cpp:119-200; call sites
+ * TLibEncoder/TEncGOP.cpp:1150-1172, TLibDecoder/TDecGop.cpp:340-370): digest is the reference's unsigned char [3][16] (Y, Cb, Cr;
+ * MD5 16 bytes, CRC 2, checksum 4, the rest zero).  method = the SEI's hash type = --SEIpictureDigest.
+ * tvc_pic_ssd = the three UInt64 sums of squared differences of TEncGOP::xCalculateAddPSNR (TLibEncoder/TEncGOP.cpp:1582-1641)
+ * between two slots (original, reconstruction); the log10 stays with the caller.                                              */
+enum { TVC_HASH_MD5 = 1, TVC_HASH_CRC = 2, TVC_HASH_CHECKSUM = 3 };
+int tvc_pic_hash(tvc_ctx* ctx, int slot, int method, uint8_t* digest /* [3][16] */);
+int tvc_pic_ssd(tvc_ctx* ctx, int slot_a, int slot_b, uint64_t* ssd /* [3] */);
+
 /* ---------------------------------------------------------------------------------- intra 35-mode rough search
  * SURVEY.md 8(f)-2.  Replaces the per-mode body of the rough search in TEncSearch::estIntraPredQT
  * (TLibEncoder/TEncSearch.cpp:2530-2537): TComPrediction::predIntraLumaAng (TLibCommon/TComPrediction.cpp:337-366 ->

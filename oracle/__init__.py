@@ -63,7 +63,7 @@ def build(force: bool = False) -> None:
     """Compile libhm_oracle.so (always possible) and, when /root/reference is present,
     _ref/libhmref.so.  Building the checker is not using it."""
     so = os.path.join(HERE, "libhm_oracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("hm_oracle.c", "hm_oracle_me.c", "hm_oracle_tq.c", "hm_oracle_frame.c", "hm_oracle_rdoq.c", "hm_oracle_deblock.c", "hm_oracle_intra.c", "hm_oracle.h")]
+    srcs = [os.path.join(HERE, f) for f in ("hm_oracle.c", "hm_oracle_me.c", "hm_oracle_tq.c", "hm_oracle_frame.c", "hm_oracle_rdoq.c", "hm_oracle_deblock.c", "hm_oracle_intra.c", "hm_oracle_hash.c", "hm_oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", HERE, "-B", "oracle"])
     ref_so = os.path.join(HERE, "_ref", "libhmref.so")
@@ -155,6 +155,9 @@ def lib():
     L.orc_intra_mode_filtered.argtypes = [ci, ci]; L.orc_intra_mode_filtered.restype = ci
     L.orc_intra_pred_luma.argtypes = [vp, ci, ci, ci, ci, ci, vp, ci]; L.orc_intra_pred_luma.restype = None
     L.orc_intra_rough.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp]; L.orc_intra_rough.restype = None
+    for f in ("orc_md5_plane", "orc_crc_plane", "orc_checksum_plane"):
+        getattr(L, f).argtypes = [vp, ci, ci, ci, ci, vp]; getattr(L, f).restype = None
+    L.orc_ssd_plane.argtypes = [vp, ci, vp, ci, ci, ci]; L.orc_ssd_plane.restype = C.c_uint64
     _LIB = L
     return L
 
@@ -200,6 +203,8 @@ def ref():
         R.ref_est_bits_size.argtypes = []; R.ref_est_bits_size.restype = ci
     R.ref_dequant.argtypes = [i32p, i32p, ci, ci, ci, ci, ci]; R.ref_dequant.restype = None
     R.ref_extend_border.argtypes = [vp, ci, ci, ci, ci, ci]; R.ref_extend_border.restype = None
+    if hasattr(R, "ref_pic_hash"):
+        R.ref_pic_hash.argtypes = [ci, vp, vp, vp, ci, ci, vp]; R.ref_pic_hash.restype = None
     if hasattr(R, "ref_intra_rough"):
         R.ref_intra_rough.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, vp]; R.ref_intra_rough.restype = None
     ip = C.POINTER(ci)

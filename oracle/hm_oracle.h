@@ -189,6 +189,12 @@ int orc_intra_mode_filtered(int mode, int log2n);
 void orc_intra_pred_luma(const Pel* line, int log2n, int mode, int above, int left, int bd, Pel* dst, int ds);
 void orc_intra_rough(const Pel* line, const Pel* org, int so, int log2n, int above, int left, int bd, uint32_t sad[35], Pel* preds);
 
+/* ------------------------------------------------------------------ picture hashes / PSNR sums (hm_oracle_hash.c) */
+void orc_md5_plane(const Pel* plane, int w, int h, int stride, int bd, unsigned char digest[16]);
+void orc_crc_plane(const Pel* plane, int w, int h, int stride, int bd, unsigned char digest[16]);
+void orc_checksum_plane(const Pel* plane, int w, int h, int stride, int bd, unsigned char digest[16]);
+uint64_t orc_ssd_plane(const Pel* a, int sa, const Pel* b, int sb, int w, int h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,7 @@
 #include "TLibCommon/TComPicYuv.h"
 #include "TLibCommon/TComYuv.h"
 #include "TLibCommon/TComPrediction.h"
+#include "TLibCommon/TComPicYuv.h"
 #include "TLibEncoder/TEncCfg.h"
 #include "TLibEncoder/TEncSearch.h"
 #undef private
@@ -523,6 +524,24 @@ void ref_intra_rough(const short* line, const short* line_filtered, const short*
     P->predIntraLumaAng(&pat, (UInt)mode, d, (UInt)n, n, n, 0, above != 0, left != 0);
     sad[mode] = s_rd->calcHAD(const_cast<short*>(org), so, d, n, n, n);
   }
+}
+
+/* ==================================================================================== picture hashes
+ * the reference's own calcMD5 / calcCRC / calcChecksum (TComPicYuvMD5.cpp:119-200) on a TComPicYuv filled from dense planes */
+void ref_pic_hash(int method, const short* y, const short* u, const short* v, int w, int h, unsigned char* digest /* [3][16] */)
+{
+  TComPicYuv pic;
+  pic.create(w, h, g_uiMaxCUWidth, g_uiMaxCUHeight, g_uiMaxCUDepth);
+  for (int r = 0; r < h; r++) memcpy(pic.getLumaAddr() + (size_t)r * pic.getStride(), y + (size_t)r * w, sizeof(short) * w);
+  for (int r = 0; r < h / 2; r++) {
+    memcpy(pic.getCbAddr() + (size_t)r * pic.getCStride(), u + (size_t)r * (w / 2), sizeof(short) * (w / 2));
+    memcpy(pic.getCrAddr() + (size_t)r * pic.getCStride(), v + (size_t)r * (w / 2), sizeof(short) * (w / 2));
+  }
+  unsigned char d[3][16];
+  memset(d, 0, sizeof(d));
+  if (method == 1) calcMD5(pic, d); else if (method == 2) calcCRC(pic, d); else calcChecksum(pic, d);
+  memcpy(digest, d, sizeof(d));
+  pic.destroy();
 }
 
 } /* extern "C" */

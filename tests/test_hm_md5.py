@@ -188,3 +188,23 @@ def test_candidate_evaluation_on_device(tmp_path, cfg, frames, mode):
     print(cl[-1])
     f = cl[-1].split()
     assert int(f[3]) > 100 and int(f[9]) > 1000, cl[-1]
+
+
+@pytest.mark.parametrize("digest", [1, 2, 3])
+def test_picture_hash_on_device(tmp_path, digest):
+    """SURVEY 8f-4 inside the real encoder and decoder: the decoded-picture-hash SEI (MD5 / CRC / checksum) computed by tvc_pic_hash.
+    The SEI payload is part of the bitstream, so an equal md5 proves the encoder's digests; the hooked decoder recomputes them on the
+    device and must report (OK) for every picture."""
+    _need()
+    w, h, frames = 208, 120, 3
+    yuv = str(tmp_path / "in.yuv")
+    _yuv(yuv, w, h, frames)
+    ref_bin, cuda_bin = str(tmp_path / "ref.bin"), str(tmp_path / "cuda.bin")
+    ex = ("--SEIpictureDigest=%d" % digest,)
+    _encode(ENC_REF, "encoder_lowdelay_P_main.cfg", yuv, w, h, frames, ref_bin, extra=ex)
+    r = _encode(ENC_CUDA, "encoder_lowdelay_P_main.cfg", yuv, w, h, frames, cuda_bin, env={"TVC_HM": "hash"}, extra=ex)
+    assert _md5(cuda_bin) == _md5(ref_bin)
+    assert "TLibCuda picture hash: %d pictures" % frames in r.stderr, r.stderr[-400:]
+    d = subprocess.run([DEC_CUDA, "-b", cuda_bin], capture_output=True, text=True, timeout=600, env=dict(os.environ, TVC_HM="hash"))
+    assert d.returncode == 0 and "ERROR" not in d.stdout and d.stdout.count("(OK)") == frames, d.stdout[-600:]
+    assert "TLibCuda picture hash: %d pictures" % frames in d.stderr, d.stderr[-400:]

@@ -174,6 +174,8 @@ SIGNATURES = {
     "tvc_pred_cost_batch_dev": (ci, [vp, ci, ci, ci, vp, vp]),
     "tvc_ctu_cost_grids": (ci, [vp, ci, ci, vp, vp]),
     "tvc_ctu_cost_grids_dev": (ci, [vp, ci, ci, vp, vp]),
+    "tvc_pic_hash": (ci, [vp, ci, ci, vp]),
+    "tvc_pic_ssd": (ci, [vp, ci, ci, vp]),
     "tvc_intra_rough_batch": (ci, [vp, ci, vp, vp, C.c_size_t, vp, C.c_size_t, vp]),
     "tvc_intra_rough_batch_dev": (ci, [vp, ci, vp, vp, vp, vp, vp, vp]),
     "tvc_intra_rough": (ci, [vp, ci, vp, vp, ci, ci, ci, vp, vp]),

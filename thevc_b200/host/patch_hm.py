@@ -139,6 +139,13 @@ def main():
     s = sub_once(s, r'(    tmpUSwap = m_pTmpU1;\r?\n    m_pTmpU1 = m_pTmpU2;\r?\n    m_pTmpU2 = tmpUSwap;\r?\n  \}\r?\n)',
                  r'\1  tlibcuda_sao_end( m_pcPic, yCbCr );\n', "processSaoUnitAll end")
     wr(os.path.join(out, "TLibCommon", "TComSampleAdaptiveOffset.cpp"), s)
+    # ---- TComPicYuvMD5.cpp: the picture hashes of the digest SEI (encoder) and of its check (decoder)
+    s = rd(os.path.join(lib, "TLibCommon", "TComPicYuvMD5.cpp"))
+    s = sub_once(s, r'(#include "TComPicYuv.h"\r?\n)', r'\1#include "tlibcuda_hm.h"\n', "TComPicYuvMD5 include")
+    for fn, method in (("calcCRC", 2), ("calcChecksum", 3), ("calcMD5", 1)):
+        s = sub_once(s, r'(void %s\(TComPicYuv& pic, unsigned char digest\[3\]\[16\]\)\r?\n\{\r?\n)' % fn,
+                     r'\1  if ( tlibcuda_pic_hash( pic, %d, digest ) ) return;\n' % method, fn)
+    wr(os.path.join(out, "TLibCommon", "TComPicYuvMD5.cpp"), s)
     # ---- TComPrediction.cpp: xPredInterUni (shared by encoder and decoder)
     s = rd(os.path.join(lib, "TLibCommon", "TComPrediction.cpp"))
     s = sub_once(s, r'(#include "TComPrediction.h"\r?\n)', r'\1#include "tlibcuda_hm.h"\n', "TComPrediction include")
@@ -146,7 +153,7 @@ def main():
                  r'\1  if ( tlibcuda_pred_inter_uni( pcCU, pcCU->getSlice()->getRefPic( eRefPicList, iRefIdx ), uiPartAddr, cMv.getHor(), cMv.getVer(), iWidth, iHeight, rpcYuvPred, bi ) ) return;\n',
                  "xPredInterUni", flags=re.S)
     wr(os.path.join(out, "TLibCommon", "TComPrediction.cpp"), s)
-    print("patched 11 files into", out)
+    print("patched 12 files into", out)
 
 
 if __name__ == "__main__":

@@ -130,6 +130,8 @@ struct State {
   unsigned long long n_tz_lookup = 0, n_frac_lookup = 0, n_groups = 0;
   double batch_seconds = 0.0, prepass_seconds = 0.0;      // host wall time spent inside tvc_me_ctu / picture_start
   bool on_me = true, on_frac = true, on_tq = true, on_rdoq = true, on_mc = true, on_tables = true, verbose = false, disabled = false;
+  bool on_hash = false;                    // picture hashes on the device (TVC_HM=...,hash)
+  unsigned long long n_hash = 0;
   bool on_cand = false;                    // merge / AMVP candidate evaluation (TVC_HM=...,cand)
   bool on_cand_grid = false;               // ... served by look-up from CTU-wide cost grids (TVC_HM=...,candgrid)
   struct Grid { uint32_t w[TVC_GRID_WORDS]; };
@@ -174,6 +176,8 @@ void report()
             s.dbk.n_pics, s.dbk.n_units, s.dbk.seconds);
   if (s.sao.on && s.sao.n_planes)
     fprintf(stderr, "TLibCuda SAO: %llu planes filtered on the device, %.3f s (upload + kernel + download)\n", s.sao.n_planes, s.sao.seconds);
+  if (s.on_hash)
+    fprintf(stderr, "TLibCuda picture hash: %llu pictures hashed on the device\n", s.n_hash);
   if (s.on_cand_grid)
     fprintf(stderr, "TLibCuda candidate look-up: %llu of %llu candidate costs served from %llu CTU-wide (CTU, reference, MV) cost grids\n",
             s.n_grid_hits, s.n_grid_hits + s.n_grid_fills, s.n_grid_fills);
@@ -247,6 +251,7 @@ void parse_env()
   s.sao.on = !s.sao.dump && strstr(e, "sao") != nullptr;
   s.dbk.dump = strstr(e, "dbkdump") != nullptr;
   s.dbk.on = !s.dbk.dump && strstr(e, "dbk") != nullptr;
+  s.on_hash = strstr(e, "hash") != nullptr;
   s.on_cand = strstr(e, "cand") != nullptr;
   s.on_cand_grid = strstr(e, "candgrid") != nullptr;
   s.intra.dump = strstr(e, "intradump") != nullptr;
@@ -271,7 +276,7 @@ void ensure_ctx(int w, int ht)
   State& s = S();
   if (s.disabled || (s.h && s.w >= w && s.ht >= ht)) return;
   init_once();
-  if (!s.on_me && !s.on_frac && !s.on_tq && !s.on_rdoq && !s.on_mc && !s.dbk.on && !s.sao.on && !s.intra.on && !s.on_cand) { s.disabled = true; return; }     // TVC_HM=none: the unmodified path
+  if (!s.on_me && !s.on_frac && !s.on_tq && !s.on_rdoq && !s.on_mc && !s.dbk.on && !s.sao.on && !s.intra.on && !s.on_cand && !s.on_hash) { s.disabled = true; return; }     // TVC_HM=none: the unmodified path
   if (s.h) {                  // the decoder learns the picture size after its first transforms: start over with the real size
     tvc_ctx_destroy(s.h);
     s.h = nullptr;
@@ -292,6 +297,7 @@ void ensure_ctx(int w, int ht)
   s.cur_slot = -1; s.num_table_refs = 0;
   // the last two slots are the decoder batch's reconstruction and residual planes: never handed out as picture slots
   s.slots[c.num_slots - 1].stamp = s.slots[c.num_slots - 2].stamp = ~0ull;
+  s.slots[c.num_slots - 3].stamp = ~0ull;       // the picture being hashed (tlibcuda_pic_hash)
 }
 
 // slot of a picture buffer; uploads it when the slot does not hold this picture's current content
@@ -712,6 +718,21 @@ bool tlibcuda_template_sad(TComDataCU* cu, TComPic* refPic, unsigned partAddr, i
   CK(tvc_pred_cost_batch(s.h, s.cur_slot, TVC_DIST_SAD, 1, &p, &sad));
   s.cand_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   s.n_template++;
+  return true;
+}
+
+bool tlibcuda_pic_hash(TComPicYuv& pic, int method, unsigned char digest[3][16])
+{
+  init_once();
+  if (!S().on_hash) return false;
+  ensure_ctx(pic.getWidth(), pic.getHeight());
+  State& s = S();
+  if (!s.h) return false;
+  const int slot = (int)s.slots.size() - 3;
+  s.slots[slot].yuv = nullptr;                // content changes per call: never matched by slot_for
+  CK(tvc_pic_upload(s.h, slot, pic.getLumaAddr(), pic.getStride(), pic.getCbAddr(), pic.getCrAddr(), pic.getCStride(), 0));
+  CK(tvc_pic_hash(s.h, slot, method, &digest[0][0]));
+  s.n_hash++;
   return true;
 }
 

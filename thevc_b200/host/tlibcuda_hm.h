@@ -94,6 +94,12 @@ bool tlibcuda_merge_costs(TComDataCU* cu, int puIdx, TComMvField* cands, const u
                           unsigned* dist);
 bool tlibcuda_template_sad(TComDataCU* cu, TComPic* refPic, unsigned partAddr, int mvx, int mvy, int w, int h, unsigned& sad);
 
+/* ---- picture hash (TVC_HM=...,hash): calcMD5 / calcCRC / calcChecksum (TComPicYuvMD5.cpp:119-200) of the digest SEI
+ * (TEncGOP.cpp:1150-1172) and of the decoder's check (TDecGop.cpp:340-370): the picture goes into a device slot and tvc_pic_hash
+ * returns the reference's digest[3][16]. */
+class TComPicYuv;
+bool tlibcuda_pic_hash(TComPicYuv& pic, int method, unsigned char digest[3][16]);
+
 /* ---- frame sharding of all-intra sequences (thevc_b200/host/shard_encode.py).  TVC_POC_OFFSET=k: this process
  * encodes the frames from input frame k on (-fs k) as POC k, k+1, ... (TEncTop::m_iPOCLast starts at k-1, TEncTop.cpp:54; the
  * frame limit of compressGOP, TEncGOP.cpp:211, moves with it) and, for k > 0, writes no VPS/SPS/PPS (m_bSeqFirst,

@@ -374,6 +374,18 @@ class TLibCuda:
         self._ck(self.L.tvc_intra_rough_batch(self.h, len(jobs), ptr(jobs), ptr(lines), lines.size, ptr(org), org.size, ptr(sad)))
         return sad
 
+    def pic_hash(self, slot: int, method: int) -> np.ndarray:
+        """calcMD5 (1) / calcCRC (2) / calcChecksum (3) of the picture in a slot: uint8 [3, 16]"""
+        d = np.zeros((3, 16), np.uint8)
+        self._ck(self.L.tvc_pic_hash(self.h, slot, method, ptr(d)))
+        return d
+
+    def pic_ssd(self, slot_a: int, slot_b: int) -> np.ndarray:
+        """the three sums of squared differences of xCalculateAddPSNR: uint64 [3]"""
+        s = np.zeros(3, np.uint64)
+        self._ck(self.L.tvc_pic_ssd(self.h, slot_a, slot_b, ptr(s)))
+        return s
+
     def prof_enable(self, on: bool = True):
         self._ck(self.L.tvc_prof_enable(self.h, int(on)))
 
