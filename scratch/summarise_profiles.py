@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turn gpurun_out/ ncu outputs into the tracked summaries under profiles/.
 
-  python scratch/summarise_profiles.py <tag> <launches.csv> <full.ncu-rep> "<command the captures ran>"
+  python scratch/summarise_profiles.py <tag> <launches.csv> <full.ncu-rep> "<command the captures ran>" [more.ncu-rep ...]
 
 writes profiles/<tag>_launches.csv (copy), profiles/<tag>_launches_summary.txt (per-kernel share of the step),
 profiles/<tag>_kernels_full.txt (key counters of every kernel in the --set full capture) and updates
@@ -62,9 +62,14 @@ def main():
         for k, (c, ns) in sorted(t.items(), key=lambda kv: -kv[1][1]):
             f.write("%-60s launches %4d  time %10.3f ms  share %5.1f%%\n" % (k, c, ns / 1e6, 100 * ns / total))
     # full capture
-    q = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--metrics", ",".join(METRICS)], capture_output=True, text=True)
-    rr = list(csv.reader(io.StringIO(q.stdout)))
-    hdr, units, rows = rr[0], rr[1], rr[2:]
+    hdr, units, rows = None, None, []
+    for one in [rep] + sys.argv[5:]:          # further reports (single-kernel captures of other commands) are appended
+        q = subprocess.run(["ncu", "-i", one, "--page", "raw", "--csv", "--metrics", ",".join(METRICS)], capture_output=True, text=True)
+        rr = list(csv.reader(io.StringIO(q.stdout)))
+        if hdr is None:
+            hdr = rr[0]
+        assert rr[0] == hdr, "reports with different columns"
+        rows += [(r_, rr[1]) for r_ in rr[2:]]          # units differ between reports (us / ms, Kbyte / Gbyte)
     ki = hdr.index("Kernel Name")
     traffic_path = os.path.join(out, "traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
@@ -74,7 +79,7 @@ def main():
              "me_frac": "integer pipe (issue slots)", "rdoq": "latency (dependent FP64 chain)", "mc": "hbm", "fwd_tq": "hbm", "inv_tq": "hbm"}
     with open(os.path.join(out, tag + "_kernels_full.txt"), "w") as f:
         f.write("ncu --set full --clock-control none --import-source on: %s\n(one launch per kernel; under the profiler -- not a bench value)\n\n" % cmd)
-        for row in rows:
+        for row, units in rows:
             name = short(row[ki])
             f.write("%s  grid %s block %s\n" % (row[ki][:110], row[hdr.index("Grid Size")], row[hdr.index("Block Size")]))
             vals = {}
