@@ -604,9 +604,20 @@ def gpu_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: one JSON line only
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # stdout carries ONE JSON line: NCCL prints its version banner (and, with NCCL_DEBUG=INFO, its log) to stdout while the
+        # communicator comes up, so file descriptor 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     torch.cuda.set_device(local)
     stream = torch.cuda.Stream()
     wl = Workload(rank_seed(args.seed, rank), pinned=True)
