@@ -567,6 +567,8 @@ def intra_rough_leg(t, wl, local, cpu_sample=64):
     out = {"pus": int(len(jobs)), "ms": ms, "satd_gpel_per_s": pels / (ms * 1e-3) / 1e9,
            "algorithmic_GBps": (pels / 35 * 2 + lines.nbytes + len(jobs) * (24 + 140)) / (ms * 1e-3) / 1e9}
     # the oracle (C restatement of predIntraLumaAng + calcHAD) on a strided sample of the same PUs, one core
+    if cpu_sample <= 0:
+        return out
     try:
         import time
         import oracle
@@ -824,7 +826,7 @@ def gpu_arm(args):
     }
 
     try:
-        sub["intra_rough"] = intra_rough_leg(t, wl, local)
+        sub["intra_rough"] = intra_rough_leg(t, wl, local, cpu_sample=0 if args.no_cpu else 64)
     except Exception as ex:          # a side leg must never take the hot-path line down with it
         sub["intra_rough"] = {"error": repr(ex)[:300]}
 
