@@ -221,6 +221,7 @@ void tvc_ctx_destroy(tvc_ctx* c)
   }
   for (auto& p : c->prof_live) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : c->prof_pool) cudaEventDestroy(e);
+  if (c->fr_int_ready) cudaEventDestroy(c->fr_int_ready);
   for (auto e : c->pipe_ev) if (e) cudaEventDestroy(e);
   for (auto st : c->pipe) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
   if (c->me_ev) cudaEventDestroy(c->me_ev);

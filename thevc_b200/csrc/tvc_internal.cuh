@@ -85,6 +85,8 @@ struct tvc_ctx {
   // pipelined frame pre-pass: search stream, fractional-search stream, per-chunk events
   cudaStream_t pipe[2] = {nullptr, nullptr};
   std::vector<cudaEvent_t> pipe_ev;
+  cudaEvent_t fr_int_ready = nullptr;       // recorded after the integer search of the frame pre-pass (serial form)
+  bool fr_piped_last = false;
   // per-phase timing (tvc_prof_*)
   bool prof_on = false;
   struct ProfPair { int phase; cudaEvent_t a, b; };
@@ -146,6 +148,16 @@ struct ScanTables { const uint16_t* s[3][4]; };
 int ensure_scans(tvc_ctx* c, ScanTables& st);          // tvc_tq.cu
 // range-checks a host TU list (grouped by ascending log2_size) and counts TUs per size
 int validate_tus(tvc_ctx* c, int plane_slot, int n, const tvc_tu* tus, size_t coef_elems, int counts[4]);   // tvc_tq.cu
+// the per-record test of validate_tus (ordering of the list is checked by the caller)
+inline bool tu_record_ok(const Pic& p, const tvc_tu& t, size_t coef_elems)
+{
+  const int N = 1 << (t.log2_size & 7);
+  return !(t.log2_size < 2 || t.log2_size > 5 || t.plane < 0 || t.plane > 2 || t.scan_idx < 0 || t.scan_idx > 2 ||
+           t.x < 0 || t.y < 0 || t.x + N > p.w[t.plane] + p.mx[t.plane] || t.y + N > p.h[t.plane] + p.my[t.plane] ||
+           t.qp_rem < 0 || t.qp_rem > 5 || t.qp_per < 0 || t.qp_per > 12 || t.base_per < 0 || t.base_per > 12 ||
+           t.coef_offset < 0 || (size_t)t.coef_offset + (size_t)N * N > coef_elems ||
+           ((t.flags & (TVC_TU_DST | TVC_TU_SKIP)) && t.log2_size != 2));
+}
 // dequant (optional) + inverse transform of a device TU list, one launch per size; recon = Clip(pred + resi) when pred_slot >= 0
 int launch_inv(tvc_ctx* c, int resi_slot, int pred_slot, int recon_slot, const int counts[4], const tvc_tu* tus_dev,
                const int32_t* levels_dev, int dequant);                                                          // tvc_tq.cu

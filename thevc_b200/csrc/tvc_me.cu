@@ -1648,23 +1648,28 @@ static int launch_tables(tvc_ctx* c, int ctu0, int nct, int ref0, int nrf)
   for (int rf = 0; rf < c->me_num_refs; rf++) maps.ref[rf] = c->pics[c->me_ref_slots[rf]].tmap_ref;
   // tuning knob (measured on B200, ms per 1080p picture x 4 references): 81 = row-split lane mapping, 8-row window, 2 CTAs/SM:
   // 5.4 (default); 8 = column mapping (64-byte store pieces): 7.0; 4 / 43 = 4-row window at 4 / 3 CTAs/SM: 7.4 / 7.0; 41: 6.6
-  static int variant = -1;
+  static int variant = -1, pad = 0;
   if (variant < 0) {
     const char* ev = getenv("TVC_TABLE_DYB");
     variant = ev ? atoi(ev) : 81;
-    TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables));
-    TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables));
-    TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables));
-    TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables));
-    TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<4, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables));
+    // TVC_TABLE_SMEM_PAD=<KB>: unused dynamic shared memory that caps the resident table CTAs per SM (72 -> one), leaving registers
+    // for the search / fractional-search CTAs of the pipelined form (TVC_ME_PIPE)
+    const char* ep = getenv("TVC_TABLE_SMEM_PAD");
+    pad = ep ? atoi(ep) * 1024 : 0;
+    TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables + pad));
+    TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables + pad));
+    TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables + pad));
+    TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables + pad));
+    TVC_CUDA(c, cudaFuncSetAttribute(k_me_sad_tables<4, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTables + pad));
   }
+  const size_t smem_tables = kSmemTables + pad;
   dim3 grd(nct, nrf);
   ProfScope ps(c, TVC_PH_ME_TABLES);
-  if (variant == 4) k_me_sad_tables<4, 4><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables, ctu0, ref0);
-  else if (variant == 43) k_me_sad_tables<4, 3><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables, ctu0, ref0);
-  else if (variant == 81) k_me_sad_tables<8, 2, true><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables, ctu0, ref0);
-  else if (variant == 41) k_me_sad_tables<4, 3, true><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables, ctu0, ref0);
-  else k_me_sad_tables<8, 2><<<grd, 256, kSmemTables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables, ctu0, ref0);
+  if (variant == 4) k_me_sad_tables<4, 4><<<grd, 256, smem_tables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables, ctu0, ref0);
+  else if (variant == 43) k_me_sad_tables<4, 3><<<grd, 256, smem_tables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables, ctu0, ref0);
+  else if (variant == 81) k_me_sad_tables<8, 2, true><<<grd, 256, smem_tables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables, ctu0, ref0);
+  else if (variant == 41) k_me_sad_tables<4, 3, true><<<grd, 256, smem_tables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables, ctu0, ref0);
+  else k_me_sad_tables<8, 2><<<grd, 256, smem_tables, c->stream>>>(maps, nctu, c->num_ctus_x, p.mx[0], p.my[0], c->me_centers, c->me_tables, ctu0, ref0);
   TVC_LAUNCH_CHECK(c);
   return TVC_OK;
 }
@@ -1875,6 +1880,7 @@ int tvc_me_frame_dev(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slot
   static int pipe_chunks = -1;
   if (pipe_chunks < 0) { const char* e = getenv("TVC_ME_PIPE"); pipe_chunks = e ? atoi(e) : 0; if (pipe_chunks > kMaxPipeChunks) pipe_chunks = kMaxPipeChunks; }
   const bool piped = cfg->use_tables && pipe_chunks > 0 && !c->prof_on;
+  c->fr_piped_last = piped;
   if (cfg->use_tables && (r = prepass_prepare(c, cur_slot, num_refs, ref_slots, centers.data()))) return r;
   TVC_CUDA(c, cudaMemcpyAsync(c->fr_stage.dev, c->fr_stage.host, np * sizeof(tvc_me_center) + num_refs * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   TVC_CUDA(c, cudaEventRecord(c->fr_ev, c->stream));
@@ -1936,6 +1942,7 @@ int tvc_me_frame_dev(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slot
     const bool shared = cfg->use_tables && use_rast;
     if ((r = launch_search(c, cur_slot, cfg->use_tables, (int)n, c->fr_jobs, c->fr_int, shared ? (const RasterBest*)c->fr_rast : nullptr,
                            shared && use_sweep ? (const SweepState*)c->fr_sweep : nullptr, c->fr_stats))) return r;
+    if (c->fr_int_ready) TVC_CUDA(c, cudaEventRecord(c->fr_int_ready, c->stream));      // tvc_me_frame copies the integer results from here
     if (cfg->do_frac && (r = frac_part(0, n))) return r;
   } else {
     if ((r = ensure_pipe(c))) return r;
@@ -1990,12 +1997,24 @@ int tvc_me_frame(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slots, c
 {
   tvc_me_result* di = nullptr;
   tvc_frac_result* df = nullptr;
+  // the integer results (16 B per job: 19 MB at 1080p x 4 references) leave on a side stream while the fractional search still runs
+  const bool early = c && cfg && cfg->do_frac && int_out && is_pinned(int_out) && ensure_pipe(c) == TVC_OK;
+  if (early && !c->fr_int_ready) TVC_CUDA(c, cudaEventCreateWithFlags(&c->fr_int_ready, cudaEventDisableTiming));
   int r = tvc_me_frame_dev(c, cur_slot, num_refs, ref_slots, pred_qpel, cfg, &di, &df);
   if (r) return r;
   const size_t n = (size_t)num_refs * c->num_ctus_x * c->num_ctus_y * TVC_ME_CENSUS;
-  if (int_out) TVC_CUDA(c, cudaMemcpyAsync(int_out, di, n * sizeof(tvc_me_result), cudaMemcpyDeviceToHost, c->stream));
+  bool side = false;
+  if (int_out) {
+    if (early && !c->fr_piped_last) {
+      TVC_CUDA(c, cudaStreamWaitEvent(c->pipe[0], c->fr_int_ready, 0));
+      TVC_CUDA(c, cudaMemcpyAsync(int_out, di, n * sizeof(tvc_me_result), cudaMemcpyDeviceToHost, c->pipe[0]));
+      side = true;
+    } else
+      TVC_CUDA(c, cudaMemcpyAsync(int_out, di, n * sizeof(tvc_me_result), cudaMemcpyDeviceToHost, c->stream));
+  }
   if (frac_out && df) TVC_CUDA(c, cudaMemcpyAsync(frac_out, df, n * sizeof(tvc_frac_result), cudaMemcpyDeviceToHost, c->stream));
   TVC_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (side) TVC_CUDA(c, cudaStreamSynchronize(c->pipe[0]));
   return TVC_OK;
 }
 

@@ -20,6 +20,8 @@
 // Every double operation is written with __dmul_rn/__dadd_rn/__dsub_rn/__ddiv_rn so that no FMA contraction can
 // change a cost (the reference is x86-64 SSE2 code without FMA).
 #include "tvc_internal.cuh"
+#include <thread>
+#include <algorithm>
 
 #include <cfloat>
 #include <climits>
@@ -518,17 +520,59 @@ static int launch_rdoq(tvc_ctx* c, int n, const tvc_rdoq_tu* tus_dev, const tvc_
   return TVC_OK;
 }
 
+static inline bool rdoq_record_ok(const tvc_rdoq_tu& t, int n_est, size_t coef_elems)
+{
+  const size_t nn = (size_t)1 << (2 * (t.log2_size & 7));
+  return !(t.log2_size < 2 || t.log2_size > 5 || t.scan_idx < 0 || t.scan_idx > 2 || (t.scan_idx != 0 && t.log2_size > 3) ||
+           t.qp_rem < 0 || t.qp_rem > 5 || t.qp_per < 0 || t.qp_per > 12 || t.cbf_ctx > 14 || t.est_index < 0 || t.est_index >= n_est ||
+           t.coef_offset < 0 || (size_t)t.coef_offset + nn > coef_elems || !(t.lambda > 0.0) || !std::isfinite(t.lambda));
+}
+
 static int validate_rdoq(tvc_ctx* c, int n, const tvc_rdoq_tu* tus, int n_est, size_t coef_elems)
 {
-  for (int i = 0; i < n; i++) {
-    const tvc_rdoq_tu& t = tus[i];
-    const size_t nn = (size_t)1 << (2 * (t.log2_size & 7));
-    if (t.log2_size < 2 || t.log2_size > 5 || t.scan_idx < 0 || t.scan_idx > 2 || (t.scan_idx != 0 && t.log2_size > 3) ||
-        t.qp_rem < 0 || t.qp_rem > 5 || t.qp_per < 0 || t.qp_per > 12 || t.cbf_ctx > 14 || t.est_index < 0 || t.est_index >= n_est ||
-        t.coef_offset < 0 || (size_t)t.coef_offset + nn > coef_elems || !(t.lambda > 0.0) || !std::isfinite(t.lambda))
-      return set_err(c, TVC_ERR_ARG, "RDOQ TU %d invalid", i);
-  }
+  for (int i = 0; i < n; i++)
+    if (!rdoq_record_ok(tus[i], n_est, coef_elems)) return set_err(c, TVC_ERR_ARG, "RDOQ TU %d invalid", i);
   return TVC_OK;
+}
+
+// Both lists of a picture-sized batch in ONE pass, cut into ranges for a few host threads (2.6 x 10^5 records = 20 MB at 1080p: the
+// three serial passes cost 1.5-2.5 ms of host time).  Returns false on any finding; the caller then runs the serial validators, which
+// name the offending record.
+static bool validate_pair_fast(const Pic& p, int n, const tvc_tu* tus, const tvc_rdoq_tu* rtus, int n_est, size_t coef_elems, int counts[4])
+{
+  struct Part { int counts[4] = {0, 0, 0, 0}; int first = 0, last = 0; bool ok = true; };
+  unsigned hw = std::thread::hardware_concurrency();
+  const int nt = n < 32768 ? 1 : (int)std::min<unsigned>(8, hw ? hw : 1);
+  std::vector<Part> parts(nt);
+  auto work = [&](int k) {
+    Part& P = parts[k];
+    const int i0 = (int)((long long)n * k / nt), i1 = (int)((long long)n * (k + 1) / nt);
+    int prev = i0 < i1 ? tus[i0].log2_size : 2;
+    P.first = prev;
+    for (int i = i0; i < i1; i++) {
+      const tvc_tu& t = tus[i];
+      const tvc_rdoq_tu& r = rtus[i];
+      if (!tu_record_ok(p, t, coef_elems) || !rdoq_record_ok(r, n_est, coef_elems) || t.log2_size != r.log2_size ||
+          t.coef_offset != r.coef_offset || t.log2_size < prev) { P.ok = false; return; }
+      prev = t.log2_size;
+      P.counts[t.log2_size - 2]++;
+    }
+    P.last = prev;
+  };
+  std::vector<std::thread> th;
+  for (int k = 1; k < nt; k++) th.emplace_back(work, k);
+  work(0);
+  for (auto& t : th) t.join();
+  counts[0] = counts[1] = counts[2] = counts[3] = 0;
+  int prev = 2;
+  for (int k = 0; k < nt; k++) {
+    const Part& P = parts[k];
+    if (!P.ok) return false;
+    const bool empty = P.counts[0] + P.counts[1] + P.counts[2] + P.counts[3] == 0;
+    if (!empty) { if (P.first < prev) return false; prev = P.last; }
+    for (int l = 0; l < 4; l++) counts[l] += P.counts[l];
+  }
+  return true;
 }
 
 }  // namespace tvc
@@ -631,11 +675,15 @@ static int fwd_rdoq_host(tvc_ctx* c, int resi_slot, int n, const tvc_tu* tus, co
     memcpy(hi + tu_b + rtu_b, est, (size_t)n_est * sizeof(tvc_est_bits));
     TVC_CUDA(c, cudaMemcpyAsync(c->in.dev, hi, tu_b + rtu_b + est_b, cudaMemcpyHostToDevice, c->stream));
   }
-  r = validate_tus(c, resi_slot, n, tus, coef_elems, counts);
-  if (!r) r = validate_rdoq(c, n, rtus, n_est, coef_elems);
-  for (int i = 0; i < n && !r; i++)
-    if (tus[i].log2_size != rtus[i].log2_size || tus[i].coef_offset != rtus[i].coef_offset)
-      r = set_err(c, TVC_ERR_ARG, "tvc_fwd_rdoq_batch: TU %d of the two lists differ", i);
+  r = TVC_OK;
+  if (!validate_pair_fast(c->pics[resi_slot], n, tus, rtus, n_est, coef_elems, counts)) {
+    r = validate_tus(c, resi_slot, n, tus, coef_elems, counts);
+    if (!r) r = validate_rdoq(c, n, rtus, n_est, coef_elems);
+    for (int i = 0; i < n && !r; i++)
+      if (tus[i].log2_size != rtus[i].log2_size || tus[i].coef_offset != rtus[i].coef_offset)
+        r = set_err(c, TVC_ERR_ARG, "tvc_fwd_rdoq_batch: TU %d of the two lists differ", i);
+    if (!r) r = set_err(c, TVC_ERR_ARG, "tvc_fwd_rdoq_batch: invalid TU list");
+  }
   if (r) { cudaStreamSynchronize(c->stream); return r; }      // nothing but the copy was queued
   char* di = (char*)c->in.dev;
   char* dout = (char*)c->out.dev;

@@ -407,12 +407,7 @@ int validate_tus(tvc_ctx* c, int plane_slot, int n, const tvc_tu* tus, size_t co
   int prev = 2;
   for (int i = 0; i < n; i++) {
     const tvc_tu& t = tus[i];
-    int N = 1 << t.log2_size;
-    if (t.log2_size < 2 || t.log2_size > 5 || t.plane < 0 || t.plane > 2 || t.scan_idx < 0 || t.scan_idx > 2 ||
-        t.x < 0 || t.y < 0 || t.x + N > p.w[t.plane] + p.mx[t.plane] || t.y + N > p.h[t.plane] + p.my[t.plane] ||
-        t.qp_rem < 0 || t.qp_rem > 5 || t.qp_per < 0 || t.qp_per > 12 || t.base_per < 0 || t.base_per > 12 ||
-        t.coef_offset < 0 || (size_t)t.coef_offset + (size_t)N * N > coef_elems ||
-        ((t.flags & (TVC_TU_DST | TVC_TU_SKIP)) && t.log2_size != 2))
+    if (!tu_record_ok(p, t, coef_elems))
       return set_err(c, TVC_ERR_ARG, "TU %d invalid", i);
     if (t.log2_size < prev) return set_err(c, TVC_ERR_ARG, "TU list must be grouped by ascending log2_size (TU %d)", i);
     prev = t.log2_size;
