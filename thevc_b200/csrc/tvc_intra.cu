@@ -37,12 +37,12 @@ struct ModeParam {
   int ang, inv;
 };
 
-__device__ __forceinline__ ModeParam mode_param(const IntraSmem& S, int mode, int n, int log2n)
+__device__ __forceinline__ ModeParam mode_param(const int16_t* line_given, const int16_t* line_smoothed, int mode, int n, int log2n)
 {
   ModeParam p;
   const int dh = abs(mode - 10), dv = abs(mode - 26);
   const bool filt = mode != 1 && min(dh, dv) > (int)c_intra_filter_thr[log2n - 2];
-  p.R = S.line[filt ? 1 : 0] + 2 * n;
+  p.R = (filt ? line_smoothed : line_given) + 2 * n;
   p.kind = mode < 2 ? mode : 2;
   p.ver = mode >= 18;
   const int idx = p.ver ? mode - 26 : -(mode - 10);
@@ -124,7 +124,7 @@ __device__ __forceinline__ void rough_items(IntraSmem& S, int n, int log2n, bool
     const int mode = it / tiles, tile = it - mode * tiles;
     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
     const int y = ty * T + row, x0 = tx * T;
-    const ModeParam mp = mode_param(S, mode, n, log2n);
+    const ModeParam mp = mode_param(S.line[0], S.line[1], mode, n, log2n);
     int d[T];
 #pragma unroll
     for (int i = 0; i < T; i++) {
@@ -145,6 +145,7 @@ k_intra_rough(int n_jobs, const tvc_intra_job* __restrict__ jobs, const int16_t*
   const int job = blockIdx.x, tid = threadIdx.x;
   if (job >= n_jobs) return;
   const tvc_intra_job j = jobs[job];
+  if (j.log2_size <= 3) return;                    // served by k_intra_rough_small (warp per PU)
   const int log2n = j.log2_size, n = 1 << log2n, len = 4 * n + 1;
   const int16_t* ln = lines + j.line_offset;
   for (int i = tid; i < len; i += kIntraThreads) {
@@ -179,11 +180,87 @@ k_intra_rough(int n_jobs, const tvc_intra_job* __restrict__ jobs, const int16_t*
   if (tid < TVC_INTRA_MODES) sad[(size_t)job * TVC_INTRA_MODES + tid] = S.sad[tid] >> (bd - 8);
 }
 
+// ---- PUs of 4x4 and 8x8 (94 % of the intra PUs of a picture): one WARP per PU, kIntraSmallWarps PUs per CTA, no block-level barrier.
+// A mode has exactly one Hadamard tile here, so the tile sums are stored, not accumulated.
+constexpr int kIntraSmallWarps = 8;
+struct IntraSmallSmem {
+  int16_t line[2][36];
+  int16_t org[64];
+  uint32_t sad[TVC_INTRA_MODES + 1];
+};
+
+template <int T>
+__device__ __forceinline__ void rough_small(IntraSmallSmem& S, int log2n, int dc, bool above, bool left, int bd, int16_t* __restrict__ preds)
+{
+  constexpr int n = T;
+  const int lane = threadIdx.x & 31, row = lane % T, group = lane / T, groups = 32 / T;
+  const int max_pel = (1 << bd) - 1;
+  const bool dc_edges = above && left;
+  for (int base = 0; base < TVC_INTRA_MODES; base += groups) {
+    const int mode_raw = base + group;
+    const bool valid = mode_raw < TVC_INTRA_MODES;
+    const int mode = valid ? mode_raw : 0;
+    const ModeParam mp = mode_param(S.line[0], S.line[1], mode, n, log2n);
+    int d[T];
+#pragma unroll
+    for (int i = 0; i < T; i++) {
+      const int pv = pred_sample(mp, n, log2n, i, row, dc, dc_edges, max_pel);
+      if (preds && valid) preds[(size_t)mode * n * n + row * n + i] = (int16_t)pv;
+      d[i] = (int)S.org[row * n + i] - pv;
+    }
+    const uint32_t s = tile_had<T>(d, lane);
+    if (valid && row == 0) S.sad[mode] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kIntraSmallWarps * 32)
+k_intra_rough_small(int n_jobs, const tvc_intra_job* __restrict__ jobs, const int16_t* __restrict__ lines, const int16_t* __restrict__ org,
+                    uint32_t* __restrict__ sad, int16_t* __restrict__ preds, const int64_t* __restrict__ pred_offset, int bd)
+{
+  __shared__ IntraSmallSmem SS[kIntraSmallWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int job = blockIdx.x * kIntraSmallWarps + warp;
+  if (job >= n_jobs) return;
+  const tvc_intra_job j = jobs[job];
+  if (j.log2_size > 3) return;                     // served by k_intra_rough (CTA per PU)
+  IntraSmallSmem& S = SS[warp];
+  const int log2n = j.log2_size, n = 1 << log2n, len = 4 * n + 1;
+  const int16_t* ln = lines + j.line_offset;
+  for (int i = lane; i < len; i += 32) {
+    const int c = ln[i];
+    S.line[0][i] = (int16_t)c;
+    S.line[1][i] = (i == 0 || i == len - 1) ? (int16_t)c : (int16_t)((ln[i - 1] + 2 * c + ln[i + 1] + 2) >> 2);
+  }
+  const int16_t* ob = org + j.org_offset;
+  for (int i = lane; i < n * n; i += 32) S.org[i] = ob[(i >> log2n) * j.org_stride + (i & (n - 1))];
+  __syncwarp();
+  int sum = 0;
+  {
+    const int16_t* R = S.line[0] + 2 * n;
+    if (lane < n) sum = (j.above ? R[1 + lane] : 0) + (j.left ? R[-1 - lane] : 0);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+  }
+  int dc;
+  if (j.above && j.left) dc = (sum + n) / (2 * n);
+  else if (j.above || j.left) dc = (sum + n / 2) / n;
+  else dc = S.line[0][2 * n - 1];
+  int16_t* pj = preds ? preds + pred_offset[job] : nullptr;
+  if (n == 8) rough_small<8>(S, log2n, dc, j.above != 0, j.left != 0, bd, pj);
+  else rough_small<4>(S, log2n, dc, j.above != 0, j.left != 0, bd, pj);
+  __syncwarp();
+  for (int m = lane; m < TVC_INTRA_MODES; m += 32) sad[(size_t)job * TVC_INTRA_MODES + m] = S.sad[m] >> (bd - 8);
+}
+
 static int launch_intra(tvc_ctx* c, int n, const tvc_intra_job* jobs_dev, const int16_t* lines_dev, const int16_t* org_dev,
                         uint32_t* sad_dev, int16_t* preds_dev, const int64_t* pred_offset_dev)
 {
   ProfScope ps(c, TVC_PH_INTRA);
+  // both kernels walk the whole list; each serves the PU sizes it is built for and leaves the others at once
   k_intra_rough<<<n, kIntraThreads, 0, c->stream>>>(n, jobs_dev, lines_dev, org_dev, sad_dev, preds_dev, pred_offset_dev, c->cfg.bit_depth);
+  TVC_LAUNCH_CHECK(c);
+  k_intra_rough_small<<<(n + kIntraSmallWarps - 1) / kIntraSmallWarps, kIntraSmallWarps * 32, 0, c->stream>>>(n, jobs_dev, lines_dev, org_dev, sad_dev,
+                                                                                                           preds_dev, pred_offset_dev, c->cfg.bit_depth);
   TVC_LAUNCH_CHECK(c);
   return TVC_OK;
 }
