@@ -839,6 +839,18 @@ def gpu_arm(args):
         cpu = {"value": 1.0 / (per_ctu * equiv), "unit": UNIT, "cores": 1, "kind": cpu_kind(),
                "sample": "%d interior CTUs of %.1f CTU-equivalents per picture (%.1f s of CPU work): %s" % (len(ctus), equiv, wall, CPU_WHAT),
                "phase_s_per_ctu": {k: float(np.mean([r[k] for r in res])) for k in ("me", "mc", "fwd_tq", "inv_tq")}}
+        # metric (ii): ME distortion throughput as the reference counts it -- sample differences of the SADs its TZ search evaluates
+        # (w x (h >> iSubShift) per candidate) over its ME time (integer + fractional search; the reference driver times them together),
+        # against the same count over the device's raster + search + fractional-search time (the device additionally fills the full
+        # +-64 tables: me_sad_table_gpel_per_s)
+        sad_rows = np.where(chh > 8, chh >> 1, chh)                     # FEN: even rows only when the PU is taller than 8
+        per_pu = (cw * sad_rows)[None, None, :]
+        tz_pels = (n_sads * per_pu)                                     # [ref, ctu, pu]
+        me_s = float(sum(r["me"] for r in res))
+        cpu["me_tz_sad_gpel_per_s"] = float(tz_pels[:, ctus, :].sum()) / me_s / 1e9
+        dev_ms = ph_ms.get("me_search", 0.0) + ph_ms.get("me_raster", 0.0) + ph_ms.get("me_frac", 0.0)
+        if dev_ms > 0:
+            sub["me_tz_sad_gpel_per_s"] = float(tz_pels.sum()) / (dev_ms * 1e-3) / 1e9
 
     # ---- whole-encoder leg (metric (i) of BASELINE.json): after the context is gone so that the encoder's own 34.8 GB
     # of SAD tables fit beside nothing else
