@@ -15,7 +15,7 @@ PY
 python -m thevc_b200.host.shard_encode --cfg build/hm/cfg/$CFG -i $D/in.yuv -wdt 1920 -hgt 1080 --frames $F --shards $N -o $D/out.bin \
     --gpus $(seq -s, 0 $((N-1))) --hm $HM -- --SEIpictureDigest=1 > $D/shard.json
 wait
-echo "reference single run: $(cat $D/ref.time) s for $F frames; md5 $(md5sum < $D/ref.bin)"
-cat $D/shard.json
+echo "reference single run: $(cat $D/ref.time) s for $F frames; md5 $(md5sum < $D/ref.bin)" | tee $D/summary.txt
+cat $D/shard.json | tee -a $D/summary.txt
 grep -h "TLibCuda intra\|TLibCuda deblocking" $D/shard_00*.bin.log | head -4
 rm -f $D/in.yuv $D/*.bin
