@@ -259,3 +259,32 @@ def test_fwd_rdoq_recon_round_trip(orc):
         assert np.count_nonzero(lev) > 1000
     finally:
         t.close()
+
+
+def test_fwd_rdoq_list_validation_threaded(orc):
+    """a picture-sized pair of TU lists (65 536 records: the fused, threaded check of tvc_fwd_rdoq_batch) is accepted when valid and
+    rejected -- with the record named -- when one late record is out of range, when the two lists disagree, and when the list is not
+    grouped by ascending size; nothing runs on a rejected list (levels stay untouched)"""
+    import copy
+    from thevc_b200.capi import TU
+    from thevc_b200.tlibcuda import TvcError
+    W, H = 416, 240
+    t = TLibCuda(W, H, 8, num_slots=2)
+    try:
+        est = rc.make_est(np.random.default_rng(3))
+        n = 65536
+        tus = [TU(0, (i % 100) * 4, ((i // 100) % 59) * 4, 2, 0, 0, 5, 0, 5, 16 * i) for i in range(n)]
+        rtus = [RdoqTU(2, 1, 0, 5, 0, -1, 0, 16 * i, 20.0) for i in range(n)]
+        lev, _, _ = t.fwd_rdoq_batch(0, tus, rtus, [_to_abi_est(est)], QuantCfg(0, 1, 0), 16 * n)
+        assert lev.shape == (16 * n,)
+        for what, mutate, needle in (
+                ("late record out of range", lambda a, b: setattr(a[n - 5], "x", W + 400), "TU %d" % (n - 5)),
+                ("lists disagree", lambda a, b: setattr(b[n // 2 + 1], "coef_offset", 0), "TU %d" % (n // 2 + 1)),
+                ("not ascending", lambda a, b: (setattr(a[10], "log2_size", 3), setattr(b[10], "log2_size", 3)), "ascending")):
+            a, b = copy.deepcopy(tus), copy.deepcopy(rtus)
+            mutate(a, b)
+            with pytest.raises(TvcError) as e:
+                t.fwd_rdoq_batch(0, a, b, [_to_abi_est(est)], QuantCfg(0, 1, 0), 16 * n)
+            assert needle in str(e.value), (what, str(e.value))
+    finally:
+        t.close()
