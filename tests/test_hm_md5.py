@@ -39,7 +39,7 @@ def _yuv(path, w, h, n):
 
 def _encode(binary, cfg, yuv, w, h, n, out, env=None, extra=()):
     cmd = [binary, "-c", os.path.join(CFG, cfg), "-i", yuv, "-wdt", str(w), "-hgt", str(h), "-fr", "30", "-f", str(n), "-b", out,
-           "--SEIpictureDigest=1"] + list(extra)
+           "-o", os.devnull, "--SEIpictureDigest=1"] + list(extra)
     e = dict(os.environ)
     if env:
         e.update(env)

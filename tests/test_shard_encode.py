@@ -32,7 +32,7 @@ def _setup(tmp_path, cfg, w, h, frames):
             f.write(y.astype(np.uint8).tobytes()); f.write(u.astype(np.uint8).tobytes()); f.write(v.astype(np.uint8).tobytes())
     ref = str(tmp_path / "ref.bin")
     subprocess.run([ENC_REF, "-c", os.path.join(CFG, cfg), "-i", yuv, "-wdt", str(w), "-hgt", str(h), "-fr", "30", "-f", str(frames), "-b", ref,
-                    "--SEIpictureDigest=1"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
+                    "-o", os.devnull, "--SEIpictureDigest=1"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
     return yuv, hashlib.md5(open(ref, "rb").read()).hexdigest()
 
 

@@ -55,7 +55,7 @@ def shard_encode(cfg, yuv, w, h, frames, shards, out, gpus=None, hm="none", extr
         env = dict(os.environ, TVC_POC_OFFSET=str(start), TVC_HM=hm)
         if gpus:
             env["CUDA_VISIBLE_DEVICES"] = str(gpus[r % len(gpus)])
-        cmd = [encoder, "-c", cfg, "-i", yuv, "-wdt", str(w), "-hgt", str(h), "-fr", "30", "-fs", str(start), "-f", str(count), "-b", part] + list(extra)
+        cmd = [encoder, "-c", cfg, "-i", yuv, "-wdt", str(w), "-hgt", str(h), "-fr", "30", "-fs", str(start), "-f", str(count), "-b", part, "-o", os.devnull] + list(extra)
         log = open(part + ".log", "w")
         procs.append((part, log, subprocess.Popen(cmd, stdout=log, stderr=subprocess.STDOUT, env=env)))
     for part, log, p in procs:
