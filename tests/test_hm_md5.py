@@ -208,3 +208,22 @@ def test_picture_hash_on_device(tmp_path, digest):
     d = subprocess.run([DEC_CUDA, "-b", cuda_bin], capture_output=True, text=True, timeout=600, env=dict(os.environ, TVC_HM="hash"))
     assert d.returncode == 0 and "ERROR" not in d.stdout and d.stdout.count("(OK)") == frames, d.stdout[-600:]
     assert "TLibCuda picture hash: %d pictures" % frames in d.stderr, d.stderr[-400:]
+
+
+def test_frame_prepass_feeds_the_cu_loop(tmp_path):
+    """the north star's per-frame batched pre-pass inside the real encoder (TVC_HM=...,frame): from the second inter picture on one
+    tvc_me_frame call per picture searches the whole census with the predictor guesses; a (CTU, reference) group whose first real
+    AMVP predictor equals its guess takes its 593 integer + fractional results from that call, the others fall back to tvc_me_ctu.
+    Same bitstream as the unmodified reference."""
+    _need()
+    w, h, frames = 416, 240, 5
+    yuv = str(tmp_path / "in.yuv")
+    _yuv(yuv, w, h, frames)
+    ref_bin, cuda_bin = str(tmp_path / "ref.bin"), str(tmp_path / "cuda.bin")
+    _encode(ENC_REF, "encoder_lowdelay_P_main.cfg", yuv, w, h, frames, ref_bin)
+    r = _encode(ENC_CUDA, "encoder_lowdelay_P_main.cfg", yuv, w, h, frames, cuda_bin, env={"TVC_HM": "me,frac,tables,frame,candgrid"})
+    assert _md5(cuda_bin) == _md5(ref_bin)
+    fl = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda frame pre-pass:")]
+    assert fl, r.stderr[-600:]
+    print(fl[-1])
+    assert int(fl[-1].split()[3]) > 20, fl[-1]

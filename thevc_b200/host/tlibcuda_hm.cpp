@@ -130,6 +130,16 @@ struct State {
   unsigned long long n_tz_lookup = 0, n_frac_lookup = 0, n_groups = 0;
   double batch_seconds = 0.0, prepass_seconds = 0.0;      // host wall time spent inside tvc_me_ctu / picture_start
   bool on_me = true, on_frac = true, on_tq = true, on_rdoq = true, on_mc = true, on_tables = true, verbose = false, disabled = false;
+  // frame pre-pass consumed by the CU loop (TVC_HM=...,frame): one tvc_me_frame per picture with the predictor guesses; a group whose
+  // first real predictor equals its guess adopts these results instead of running tvc_me_ctu
+  bool on_frame = false, frame_valid = false;
+  std::vector<tvc_me_result> frame_int;
+  std::vector<tvc_frac_result> frame_frac;
+  std::vector<tvc_me_center> frame_pred;
+  unsigned frame_lambda = 0;
+  int frame_sr = 0, frame_fen = 0, frame_had = 0, frame_refs = 0, frame_nctu = 0;
+  int last_sr = -1, last_fen = 0, last_had = 0;          // what the CU loop asked for last (the next picture's pre-pass uses it)
+  unsigned long long n_frame_groups = 0;
   bool on_hash = false;                    // picture hashes on the device (TVC_HM=...,hash)
   unsigned long long n_hash = 0;
   bool on_cand = false;                    // merge / AMVP candidate evaluation (TVC_HM=...,cand)
@@ -168,6 +178,8 @@ void die(const char* what, int rc)
 void report()
 {
   State& s = S();
+  if (s.h && s.on_frame)
+    fprintf(stderr, "TLibCuda frame pre-pass: %llu (CTU, reference) groups took their 593 results from the picture-level tvc_me_frame call\n", s.n_frame_groups);
   if (s.h && s.on_lookup)
     fprintf(stderr, "TLibCuda look-up: %llu of %llu xTZSearch and %llu of %llu xPatternSearchFracDIF calls served from %llu census-wide (CTU, reference) batches (%.3f s in tvc_me_ctu, %.3f s in picture uploads + SAD-table pre-passes)\n",
             s.n_tz_lookup, s.n_tz, s.n_frac_lookup, s.n_frac, s.n_groups, s.batch_seconds, s.prepass_seconds);
@@ -251,6 +263,7 @@ void parse_env()
   s.sao.on = !s.sao.dump && strstr(e, "sao") != nullptr;
   s.dbk.dump = strstr(e, "dbkdump") != nullptr;
   s.dbk.on = !s.dbk.dump && strstr(e, "dbk") != nullptr;
+  s.on_frame = strstr(e, "frame") != nullptr;
   s.on_hash = strstr(e, "hash") != nullptr;
   s.on_cand = strstr(e, "cand") != nullptr;
   s.on_cand_grid = strstr(e, "candgrid") != nullptr;
@@ -390,9 +403,28 @@ void tlibcuda_picture_start(TComPic* pic, TComSlice* slice)
     // device cannot hold four (34.8 GB at 1080p) the tables grow on demand as before
     static bool reserved = false;
     if (!reserved) { reserved = true; if (tvc_me_reserve(s.h, s.num_table_refs > 4 ? s.num_table_refs : 4) != TVC_OK) (void)0; }
-    CK(tvc_me_prepass(s.h, s.cur_slot, s.num_table_refs, s.table_refs, cen.data()));
-  } else
+    s.frame_valid = false;
+    if (s.on_frame && s.on_lookup && s.on_frac && s.last_sr > 0 && !s.wp && slice->getLambdaLuma() > 0.0) {
+      // the whole census of the whole picture in one call: SAD tables around the guesses, TZ + fractional search of every PU with the
+      // guess as predictor (TComRdCost::setLambda, TComRdCost.cpp:167-173, for the rate weight)
+      double lam = slice->getLambdaLuma();
+      const double root = sqrt(lam);
+      const unsigned lc = (unsigned)floor(65536.0 * root);
+      s.frame_pred.resize((size_t)s.num_table_refs * nctu);
+      for (int r = 0; r < s.num_table_refs; r++)
+        for (int k = 0; k < nctu; k++) s.frame_pred[(size_t)r * nctu + k] = s.center_guess[(size_t)r * nctu + k];
+      const size_t n = (size_t)s.num_table_refs * nctu * TVC_ME_CENSUS;
+      s.frame_int.resize(n); s.frame_frac.resize(n);
+      tvc_me_frame_cfg fc = {s.last_sr, s.last_fen, s.last_had, 1, 1, lc};
+      CK(tvc_me_frame(s.h, s.cur_slot, s.num_table_refs, s.table_refs, s.frame_pred.data(), &fc, s.frame_int.data(), s.frame_frac.data()));
+      s.frame_valid = true; s.frame_lambda = lc; s.frame_sr = s.last_sr; s.frame_fen = s.last_fen; s.frame_had = s.last_had;
+      s.frame_refs = s.num_table_refs; s.frame_nctu = nctu;
+    } else
+      CK(tvc_me_prepass(s.h, s.cur_slot, s.num_table_refs, s.table_refs, cen.data()));
+  } else {
     s.num_table_refs = 0;
+    s.frame_valid = false;
+  }
   CK(tvc_sync(s.h));
   const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
   s.prepass_seconds += dt;
@@ -450,6 +482,20 @@ bool tlibcuda_tz_search(TComDataCU* cu, TComPattern* key, short* refY, int refSt
     GroupEntry* hit = nullptr;
     for (auto& e : g.e)
       if (e.predx == j.predx && e.predy == j.predy && e.lambda == j.lambda_cost && e.sr == searchRange && e.fen == j.fen && e.had == had) { hit = &e; break; }
+    s.last_sr = searchRange; s.last_fen = j.fen; s.last_had = had;
+    if (!hit && g.e.empty() && s.frame_valid && j.ref_index >= 0 && j.ref_index < s.frame_refs && ctu < s.frame_nctu &&
+        s.frame_lambda == j.lambda_cost && s.frame_sr == searchRange && s.frame_fen == j.fen && s.frame_had == had) {
+      const size_t gi = (size_t)j.ref_index * s.frame_nctu + ctu;
+      if (s.frame_pred[gi].cx == j.predx && s.frame_pred[gi].cy == j.predy) {       // the guess was right: the pre-pass already holds this group
+        g.e.emplace_back();
+        GroupEntry& e = g.e.back();
+        e.predx = j.predx; e.predy = j.predy; e.lambda = j.lambda_cost; e.sr = searchRange; e.fen = j.fen; e.had = had;
+        e.ires.assign(s.frame_int.begin() + gi * TVC_ME_CENSUS, s.frame_int.begin() + (gi + 1) * TVC_ME_CENSUS);
+        e.fres.assign(s.frame_frac.begin() + gi * TVC_ME_CENSUS, s.frame_frac.begin() + (gi + 1) * TVC_ME_CENSUS);
+        s.n_frame_groups++;
+        hit = &e;
+      }
+    }
     if (!hit) {
       const long long pv = ((long long)j.predx << 32) ^ (unsigned)j.predy;
       if (g.e.empty() || (g.e.size() < 4 && g.seen[pv]++ >= 1)) {
