@@ -469,7 +469,7 @@ def run_hm_encode(frames, device_index=0):
             for y, u, v in seq:
                 f.write(y.astype(np.uint8).tobytes()); f.write(u.astype(np.uint8).tobytes()); f.write(v.astype(np.uint8).tobytes())
         base = ["-c", cfg, "-i", yuv, "-wdt", str(W), "-hgt", str(H), "-fr", "30", "-f", str(frames), "--SEIpictureDigest=1", "-o", os.devnull]
-        env = dict(os.environ, TVC_HM="me,frac,tables,candgrid", CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(device_index)))
+        env = dict(os.environ, TVC_HM="me,frac,tables,frame,candgrid", CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(device_index)))
         t0 = time.perf_counter()
         pr = subprocess.Popen([enc_ref] + base + ["-b", os.path.join(d, "ref.bin")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         pc = subprocess.Popen([enc_cuda] + base + ["-b", os.path.join(d, "cuda.bin")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
