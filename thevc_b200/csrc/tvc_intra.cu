@@ -18,9 +18,14 @@ namespace tvc {
 constexpr int kIntraThreads = 128;
 constexpr int kIntraMaxN = 64;
 
+constexpr int kIntraExtLen = 3 * kIntraMaxN + 2;
 struct IntraSmem {
   int16_t line[2][4 * kIntraMaxN + 4];   // [0] as given, [1] smoothed; centre (corner) at index 2N
   int16_t org[kIntraMaxN * kIntraMaxN];
+  // per angular mode (2..34) the reference's refMain array (xPredIntraAng :228-260) in the vertical family's frame: entry N + i is
+  // main(i), i = -N .. 2N; negative i (negative angles only) are the projected side samples.  Built once per PU, so that a
+  // prediction sample is two loads and one multiply-add instead of the projection arithmetic.
+  int16_t ext[33][kIntraExtLen];
   uint32_t sad[TVC_INTRA_MODES];
   int dc;
 };
@@ -82,6 +87,20 @@ __device__ __forceinline__ int pred_sample(const ModeParam& p, int n, int log2n,
   return ((32 - df) * main_ref(i0) + df * main_ref(i0 + 1) + 16) >> 5;
 }
 
+// angular prediction sample from the extended line E (pointing at main(0)) of the mode
+__device__ __forceinline__ int pred_sample_ext(const ModeParam& p, const int16_t* __restrict__ E, const int16_t* __restrict__ R, int x, int y,
+                                               int max_pel)
+{
+  const int k = p.ver ? y : x, l = p.ver ? x : y;
+  if (p.ang == 0) {
+    int v = E[l + 1];
+    if (l == 0) { const int sm = p.ver ? 1 : -1; v += (R[-sm * (k + 1)] - R[0]) >> 1; v = v < 0 ? 0 : (v > max_pel ? max_pel : v); }
+    return v;
+  }
+  const int pos = (k + 1) * p.ang, di = pos >> 5, df = pos & 31, i0 = l + di + 1;
+  return df ? ((32 - df) * E[i0] + df * E[i0 + 1] + 16) >> 5 : E[i0];
+}
+
 template <int T>
 __device__ __forceinline__ uint32_t tile_had(int* d, int lane)
 {
@@ -127,8 +146,9 @@ __device__ __forceinline__ void rough_items(IntraSmem& S, int n, int log2n, bool
     const ModeParam mp = mode_param(S.line[0], S.line[1], mode, n, log2n);
     int d[T];
 #pragma unroll
+    const int16_t* E = S.ext[mode >= 2 ? mode - 2 : 0] + n;
     for (int i = 0; i < T; i++) {
-      const int pv = pred_sample(mp, n, log2n, x0 + i, y, S.dc, dc_edges, max_pel);
+      const int pv = mode >= 2 ? pred_sample_ext(mp, E, mp.R, x0 + i, y, max_pel) : pred_sample(mp, n, log2n, x0 + i, y, S.dc, dc_edges, max_pel);
       if (preds && valid) preds[(size_t)mode * n * n + y * n + x0 + i] = (int16_t)pv;
       d[i] = (int)S.org[y * n + x0 + i] - pv;
     }
@@ -158,6 +178,15 @@ k_intra_rough(int n_jobs, const tvc_intra_job* __restrict__ jobs, const int16_t*
   for (int i = tid; i < n * n; i += kIntraThreads) S.org[i] = ob[(i >> log2n) * j.org_stride + (i & (n - 1))];
   if (tid < TVC_INTRA_MODES) S.sad[tid] = 0;
   __syncthreads();
+  for (int e = tid; e < 33 * (3 * n + 1); e += kIntraThreads) {
+    const int m = e / (3 * n + 1), i = e - m * (3 * n + 1) - n;             // mode m + 2, main index i = -N .. 2N
+    const ModeParam mp = mode_param(S.line[0], S.line[1], m + 2, n, log2n);
+    const int sm = mp.ver ? 1 : -1;
+    int v = 0;
+    if (i >= 0) v = mp.R[sm * i];
+    else if (mp.ang < 0 && i > ((n * mp.ang) >> 5)) v = mp.R[-sm * ((128 + (-i) * mp.inv) >> 8)];     // the entries the reference extends (:243-247)
+    S.ext[m][i + n] = (int16_t)v;
+  }
   if (tid < 32) {       // predIntraGetPredValDC :127-165 on the unfiltered line
     int sum = 0;
     const int16_t* R = S.line[0] + 2 * n;
