@@ -4,6 +4,7 @@ library, SAD tables on) must write the SAME BITSTREAM as the unmodified referenc
 (oracle/_ref/bin/TAppEncoderStatic), and the reference decoder must accept it with matching picture
 hashes.  Both binaries are built from /root/reference by committed recipes (thevc_b200/host/Makefile,
 oracle/Makefile) and travel to the GPU box as build outputs; the test skips where they are absent."""
+import concurrent.futures
 import hashlib
 import os
 import subprocess
@@ -48,6 +49,19 @@ def _encode(binary, cfg, yuv, w, h, n, out, env=None, extra=()):
     return r
 
 
+_POOL = concurrent.futures.ThreadPoolExecutor(max_workers=4)
+
+
+def _encode_ref_bg(*args, **kw):
+    """the unmodified reference encoder runs on a host core while the hooked encoder runs in the test's own thread
+    (independent processes, independent outputs); .result() re-raises its assertion"""
+    return _POOL.submit(_encode, ENC_REF, *args, **kw)
+
+
+def _run_bg(cmd, env=None, timeout=1500):
+    return _POOL.submit(subprocess.run, cmd, capture_output=True, text=True, timeout=timeout, env=env)
+
+
 def _md5(path):
     return hashlib.md5(open(path, "rb").read()).hexdigest()
 
@@ -66,8 +80,9 @@ def test_bitstream_md5_identical_to_reference(tmp_path, cfg, frames, extra):
     yuv = str(tmp_path / "in.yuv")
     _yuv(yuv, w, h, frames)
     ref_bin, cuda_bin = str(tmp_path / "ref.bin"), str(tmp_path / "cuda.bin")
-    _encode(ENC_REF, cfg, yuv, w, h, frames, ref_bin, extra=extra)
+    ref_job = _encode_ref_bg(cfg, yuv, w, h, frames, ref_bin, extra=extra)
     r = _encode(ENC_CUDA, cfg, yuv, w, h, frames, cuda_bin, env={"TVC_HM": "me,frac,tq,rdoq,mc,tables,verify"}, extra=extra)
+    ref_job.result()
     served = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda:")]
     assert served and "kernel launches" in served[-1], r.stderr[-500:]
     print(served[-1])
@@ -79,12 +94,15 @@ def test_bitstream_md5_identical_to_reference(tmp_path, cfg, frames, extra):
     assert os.path.getsize(ref_bin) > 1000
     assert _md5(cuda_bin) == _md5(ref_bin)
     # the reference decoder accepts the stream and every picture hash matches
-    d = subprocess.run([DEC_REF, "-b", cuda_bin, "-o", str(tmp_path / "dec.yuv")], capture_output=True, text=True, timeout=600)
+    # the three decoder runs are independent processes reading the same stream: started together
+    d_job = _run_bg([DEC_REF, "-b", cuda_bin, "-o", str(tmp_path / "dec.yuv")], timeout=600)
+    dc_job = _run_bg([DEC_CUDA, "-b", cuda_bin, "-o", str(tmp_path / "dec_cuda.yuv")], env=dict(os.environ, TVC_HM="tq,mc"))
+    db_job = _run_bg([DEC_CUDA, "-b", cuda_bin, "-o", str(tmp_path / "dec_batch.yuv")], env=dict(os.environ, TVC_HM="tq,mc,batch,dbk,sao"))
+    d = d_job.result()
     assert d.returncode == 0
     assert "ERROR" not in d.stdout and d.stdout.count("(OK)") >= frames
     # C5: the reference decoder with the hooks (xIT, xDeQuant, xPredInterUni on the GPU) reconstructs the same pictures
-    e = dict(os.environ, TVC_HM="tq,mc")
-    dc = subprocess.run([DEC_CUDA, "-b", cuda_bin, "-o", str(tmp_path / "dec_cuda.yuv")], capture_output=True, text=True, timeout=1500, env=e)
+    dc = dc_job.result()
     assert dc.returncode == 0, dc.stdout[-800:] + dc.stderr[-800:]
     assert "ERROR" not in dc.stdout and dc.stdout.count("(OK)") >= frames
     dserved = [ln for ln in dc.stderr.splitlines() if ln.startswith("TLibCuda:")]
@@ -93,8 +111,7 @@ def test_bitstream_md5_identical_to_reference(tmp_path, cfg, frames, extra):
     assert _md5(str(tmp_path / "dec_cuda.yuv")) == _md5(str(tmp_path / "dec.yuv"))
     # C5 as BASELINE.json words it: BATCHED dequant + inverse transform and MC -- inter CUs deferred to one tvc_mc_batch + one
     # tvc_inv_tq_batch per flush (before intra CUs and before the in-loop filters)
-    e = dict(os.environ, TVC_HM="tq,mc,batch,dbk,sao")      # + deblocking and SAO apply on the device
-    db = subprocess.run([DEC_CUDA, "-b", cuda_bin, "-o", str(tmp_path / "dec_batch.yuv")], capture_output=True, text=True, timeout=1500, env=e)
+    db = db_job.result()                                      # + deblocking and SAO apply on the device
     assert db.returncode == 0, db.stdout[-800:] + db.stderr[-800:]
     assert "ERROR" not in db.stdout and db.stdout.count("(OK)") >= frames
     bl = [ln for ln in db.stderr.splitlines() if ln.startswith("TLibCuda picture batch:")]
@@ -120,10 +137,11 @@ def test_census_lookup_serves_the_cu_loop(tmp_path):
     yuv = str(tmp_path / "in.yuv")
     _yuv(yuv, w, h, frames)
     ref_bin, cuda_bin = str(tmp_path / "ref.bin"), str(tmp_path / "cuda.bin")
-    _encode(ENC_REF, "encoder_lowdelay_P_main.cfg", yuv, w, h, frames, ref_bin)
+    ref_job = _encode_ref_bg("encoder_lowdelay_P_main.cfg", yuv, w, h, frames, ref_bin)
     # + deblocking on the device: the picture digest SEI inside the bitstream hashes the final reconstruction, so an equal
     # bitstream md5 also proves the device-filtered pictures equal the reference's
     r = _encode(ENC_CUDA, "encoder_lowdelay_P_main.cfg", yuv, w, h, frames, cuda_bin, env={"TVC_HM": "me,frac,tables,dbk,sao"})
+    ref_job.result()
     assert _md5(cuda_bin) == _md5(ref_bin)
     dl = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda deblocking:")]
     assert dl and int(dl[-1].split()[2]) == frames, r.stderr[-600:]
@@ -152,8 +170,9 @@ def test_intra_rough_search_on_device(tmp_path, cfg, frames, w, h):
     yuv = str(tmp_path / "in.yuv")
     _yuv(yuv, w, h, frames)
     ref_bin, cuda_bin = str(tmp_path / "ref.bin"), str(tmp_path / "cuda.bin")
-    _encode(ENC_REF, cfg, yuv, w, h, frames, ref_bin)
+    ref_job = _encode_ref_bg(cfg, yuv, w, h, frames, ref_bin)
     r = _encode(ENC_CUDA, cfg, yuv, w, h, frames, cuda_bin, env={"TVC_HM": "intra4"})
+    ref_job.result()
     assert _md5(cuda_bin) == _md5(ref_bin)
     il = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda intra rough search:")]
     assert il, r.stderr[-600:]
@@ -174,9 +193,10 @@ def test_candidate_evaluation_on_device(tmp_path, cfg, frames, mode):
     yuv = str(tmp_path / "in.yuv")
     _yuv(yuv, w, h, frames)
     ref_bin, cuda_bin = str(tmp_path / "ref.bin"), str(tmp_path / "cuda.bin")
-    _encode(ENC_REF, cfg, yuv, w, h, frames, ref_bin)
+    ref_job = _encode_ref_bg(cfg, yuv, w, h, frames, ref_bin)
     # cand: one device call per xMergeEstimation / xGetTemplateCost; candgrid: look-up in CTU-wide (CTU, reference, MV) cost grids
     r = _encode(ENC_CUDA, cfg, yuv, w, h, frames, cuda_bin, env={"TVC_HM": mode})
+    ref_job.result()
     assert _md5(cuda_bin) == _md5(ref_bin)
     if mode == "candgrid":
         gl = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda candidate look-up:")]
@@ -201,8 +221,9 @@ def test_picture_hash_on_device(tmp_path, digest):
     _yuv(yuv, w, h, frames)
     ref_bin, cuda_bin = str(tmp_path / "ref.bin"), str(tmp_path / "cuda.bin")
     ex = ("--SEIpictureDigest=%d" % digest,)
-    _encode(ENC_REF, "encoder_lowdelay_P_main.cfg", yuv, w, h, frames, ref_bin, extra=ex)
+    ref_job = _encode_ref_bg("encoder_lowdelay_P_main.cfg", yuv, w, h, frames, ref_bin, extra=ex)
     r = _encode(ENC_CUDA, "encoder_lowdelay_P_main.cfg", yuv, w, h, frames, cuda_bin, env={"TVC_HM": "hash"}, extra=ex)
+    ref_job.result()
     assert _md5(cuda_bin) == _md5(ref_bin)
     assert "TLibCuda picture hash: %d pictures" % frames in r.stderr, r.stderr[-400:]
     d = subprocess.run([DEC_CUDA, "-b", cuda_bin], capture_output=True, text=True, timeout=600, env=dict(os.environ, TVC_HM="hash"))
@@ -220,8 +241,9 @@ def test_frame_prepass_feeds_the_cu_loop(tmp_path):
     yuv = str(tmp_path / "in.yuv")
     _yuv(yuv, w, h, frames)
     ref_bin, cuda_bin = str(tmp_path / "ref.bin"), str(tmp_path / "cuda.bin")
-    _encode(ENC_REF, "encoder_lowdelay_P_main.cfg", yuv, w, h, frames, ref_bin)
+    ref_job = _encode_ref_bg("encoder_lowdelay_P_main.cfg", yuv, w, h, frames, ref_bin)
     r = _encode(ENC_CUDA, "encoder_lowdelay_P_main.cfg", yuv, w, h, frames, cuda_bin, env={"TVC_HM": "me,frac,tables,frame,candgrid"})
+    ref_job.result()
     assert _md5(cuda_bin) == _md5(ref_bin)
     fl = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda frame pre-pass:")]
     assert fl, r.stderr[-600:]
