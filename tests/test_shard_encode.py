@@ -1,4 +1,5 @@
-"""Frame sharding of all-intra encodes (BASELINE configs[3]): N processes encode disjoint frame ranges, the host
+"""Sharding by independent units: frame ranges of all-intra encodes (BASELINE configs[3]) and closed intra periods of
+random-access encodes with IDR refresh (configs[2]).  N processes encode disjoint frame ranges, the host
 concatenates the Annex-B streams -> byte for byte the single-run stream of the UNMODIFIED reference encoder, and the
 reference decoder accepts it with every picture hash (OK).  CPU part: the shards run the reference's own code
 (TVC_HM=none; only the POC-offset patch of thevc_b200/host/patch_hm.py is exercised) -- this is the world-size-N host
@@ -25,14 +26,14 @@ def _need():
             pytest.skip("%s not built (needs /root/reference at build time)" % os.path.relpath(p, ROOT))
 
 
-def _setup(tmp_path, cfg, w, h, frames):
+def _setup(tmp_path, cfg, w, h, frames, extra=()):
     yuv = str(tmp_path / "in.yuv")
     with open(yuv, "wb") as f:
         for y, u, v in synth.make_sequence(w, h, frames):
             f.write(y.astype(np.uint8).tobytes()); f.write(u.astype(np.uint8).tobytes()); f.write(v.astype(np.uint8).tobytes())
     ref = str(tmp_path / "ref.bin")
     subprocess.run([ENC_REF, "-c", os.path.join(CFG, cfg), "-i", yuv, "-wdt", str(w), "-hgt", str(h), "-fr", "30", "-f", str(frames), "-b", ref,
-                    "-o", os.devnull, "--SEIpictureDigest=1"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
+                    "-o", os.devnull, "--SEIpictureDigest=1"] + list(extra), check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
     return yuv, hashlib.md5(open(ref, "rb").read()).hexdigest()
 
 
@@ -49,6 +50,42 @@ def test_inter_configurations_are_refused(tmp_path):
     _need()
     with pytest.raises(ValueError):
         se.shard_encode(os.path.join(CFG, "encoder_lowdelay_P_main.cfg"), "none.yuv", 64, 64, 4, 2, str(tmp_path / "o.bin"))
+    with pytest.raises(ValueError):         # random access as the cfg ships it: CRA, open GOP -> leading pictures cross the intra period
+        se.shard_encode(os.path.join(CFG, "encoder_randomaccess_main.cfg"), "none.yuv", 64, 64, 64, 2, str(tmp_path / "o.bin"))
+
+
+def test_intra_period_ranges():
+    # IntraPeriod 16, GOPSize 8: IDRs at 16, 32; a unit starts at the IDR's first leading picture (P - 7)
+    assert se.intra_period_ranges(34, 3, 16, 8) == [(0, 9), (9, 16), (25, 9)]
+    assert se.intra_period_ranges(34, 2, 16, 8) == [(0, 9), (9, 25)]
+    assert se.intra_period_ranges(34, 8, 16, 8) == [(0, 9), (9, 16), (25, 9)]          # more shards than units
+    assert se.intra_period_ranges(32, 4, 16, 8) == [(0, 9), (9, 23)]                   # POC 32 is not coded: no third unit
+    assert se.intra_period_ranges(30, 4, 16, 8) == [(0, 9), (9, 21)]                   # trailing partial GOP stays with its unit
+    assert se.intra_period_ranges(100, 4, 32, 8) == [(0, 25), (25, 32), (57, 32), (89, 11)]
+    cfg = os.path.join(CFG, "encoder_randomaccess_main.cfg")
+    if os.path.exists(cfg):
+        assert se.cfg_value(cfg, (), "IntraPeriod", "ip") == 32 and se.cfg_value(cfg, (), "GOPSize", "g") == 8
+        assert se.cfg_value(cfg, ("--IntraPeriod=16",), "IntraPeriod", "ip") == 16 and se.cfg_value(cfg, ("-ip", "48"), "IntraPeriod", "ip") == 48
+        assert se.plan_ranges(cfg, 100, 4, ("--DecodingRefreshType=2",)) == [(0, 25), (25, 32), (57, 32), (89, 11)]
+
+
+def test_closed_gop_intra_periods_shard_to_the_single_run_stream_cpu(tmp_path):
+    """BASELINE configs[2]: random access with IDR refresh; 34 pictures = units [0,9) [9,25) [25,34): the middle shard starts on
+    leading pictures (POC 9..15 are coded after IDR 16), the last one ends in a partial GOP"""
+    _need()
+    cfg, w, h, frames = "encoder_randomaccess_main.cfg", 128, 64, 34
+    extra = ["--IntraPeriod=16", "--DecodingRefreshType=2"]
+    yuv, ref_md5 = _setup(tmp_path, cfg, w, h, frames, extra)
+    for shards in (3, 2):
+        out = str(tmp_path / ("out%d.bin" % shards))
+        r = se.shard_encode(os.path.join(CFG, cfg), yuv, w, h, frames, shards, out, hm="none", extra=["--SEIpictureDigest=1"] + extra)
+        assert r["md5"] == ref_md5, (shards, r)
+    assert r["ranges"] == [(0, 9), (9, 25)]
+    log = open(str(tmp_path / "shard_001.bin.log")).read()
+    pocs = [int(ln.split()[1]) for ln in log.splitlines() if ln.startswith("POC")]
+    assert pocs[:8] == [16, 12, 10, 9, 11, 14, 13, 15] and sorted(pocs) == list(range(9, 34)), pocs
+    # no decoder leg here: the reference's OWN decoder stops (SIGSEGV) at the first leading picture behind an IDR of the reference
+    # encoder's own single-run stream (its POC restarts at the IDR), so the bar for this option is the encoder's bitstream md5
 
 
 @pytest.mark.parametrize("cfg", ["encoder_intra_main.cfg", "encoder_intra_he10.cfg"])

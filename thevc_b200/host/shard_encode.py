@@ -1,15 +1,27 @@
-"""Shard an ALL-INTRA encode across N processes / GPUs by frame range and concatenate the bitstreams (BASELINE
-configs[3]: "all-intra frames sharded across 8 B200").
+"""Shard an encode across N processes / GPUs by independent units and concatenate the bitstreams.
 
-With IntraPeriod 1 every picture is coded on its own (I slices, no reference pictures, entropy state reset per slice), so
-frame ranges are independent units: shard r encodes input frames [start_r, start_r + count_r) with `-fs start_r -f count_r`
-and TVC_POC_OFFSET=start_r (the hooked encoder then numbers its pictures from POC start_r and, for r > 0, writes no
-VPS/SPS/PPS; tlibcuda_hm.h).  No collective, no NCCL: the host concatenates the Annex-B streams, and the result is byte for
-byte the stream of a single run over all frames (tests/test_shard_encode.py checks the md5 against the unmodified
-reference encoder).  Inter configurations are refused: their pictures form one dependency chain per sequence.
+* ALL-INTRA (BASELINE configs[3]: "all-intra frames sharded across 8 B200"): with IntraPeriod 1 every picture is coded on its own
+  (I slices, no reference pictures, entropy state reset per slice), so frame ranges are the units: shard r encodes input frames
+  [start_r, start_r + count_r) with `-fs start_r -f count_r` and TVC_POC_OFFSET=start_r (the hooked encoder then numbers its
+  pictures from POC start_r and, for r > 0, writes no VPS/SPS/PPS; tlibcuda_hm.h).
+* CLOSED-GOP RANDOM ACCESS (BASELINE configs[2]: "independent intra periods sharded across 2/4/8 B200"): with
+  `--DecodingRefreshType=2` the picture at every multiple P of IntraPeriod is an IDR (TEncGOP::getNalUnitType, TLE/TEncGOP.cpp:1728-1742).
+  It is coded FIRST in its GOP (POC P-G+1 .. P for GOPSize G) and marks every earlier picture unused
+  (decodingRefreshMarking, :288), so the G-1 leading pictures coded after it reference only it and each other: the unit is the
+  frame range [P-G+1, P+IntraPeriod-G+1).  A shard that starts at input frame P-G+1 with TVC_POC_OFFSET = P-G+1 does not take
+  the first-picture exception (`iPOCLast == 0`, :206,1435; TEncTop.cpp:388), collects a full GOP and codes exactly the single
+  run's pictures in the single run's order; the encoder state that crosses pictures (m_iLastIDR :218, the SAO depth rates
+  TEncSampleAdaptiveOffset.cpp:1503,1788, the CABAC table choice TEncSbac.cpp:175) is set by the IDR before it is read.  With the
+  default `DecodingRefreshType 1` (CRA, open GOP) the leading pictures reference the previous intra period: refused.
+
+No collective, no NCCL: the host concatenates the Annex-B streams, and the result is byte for byte the stream of a single run
+over all frames (tests/test_shard_encode.py checks the md5 against the unmodified reference encoder).  Low-delay
+configurations (IntraPeriod -1) are refused: their pictures form one dependency chain per sequence.
 
     python -m thevc_b200.host.shard_encode --cfg build/hm/cfg/encoder_intra_main.cfg -i in.yuv -wdt 1920 -hgt 1080 \
         --frames 16 --shards 8 -o out.bin [--gpus 0,1,...] [--hm intra16] [-- extra encoder arguments]
+    python -m thevc_b200.host.shard_encode --cfg build/hm/cfg/encoder_randomaccess_main.cfg ... --frames 128 --shards 4 \
+        --hm me,frac,tables,candgrid -o out.bin -- --DecodingRefreshType=2
 """
 from __future__ import annotations
 
@@ -36,18 +48,55 @@ def frame_ranges(frames: int, shards: int):
     return out
 
 
-def cfg_is_all_intra(path: str) -> bool:
-    m = re.search(r"^\s*IntraPeriod\s*:\s*(-?\d+)", open(path, encoding="latin-1").read(), re.M)
-    return bool(m) and int(m.group(1)) == 1
+def cfg_value(path: str, extra, key: str, short: str | None = None, default: int | None = None):
+    """integer value of a cfg key, command-line arguments (`--Key=v`, `--Key v`, `-short v`) overriding the file as in TAppEncCfg"""
+    val = default
+    m = re.search(r"^\s*%s\s*:\s*(-?\d+)" % re.escape(key), open(path, encoding="latin-1").read(), re.M)
+    if m:
+        val = int(m.group(1))
+    extra = list(extra)
+    for i, a in enumerate(extra):
+        if a.startswith("--%s=" % key):
+            val = int(a.split("=", 1)[1])
+        elif (a == "--" + key or (short and a == "-" + short)) and i + 1 < len(extra):
+            val = int(extra[i + 1])
+    return val
+
+
+def cfg_is_all_intra(path: str, extra=()) -> bool:
+    return cfg_value(path, extra, "IntraPeriod", "ip") == 1
+
+
+def intra_period_ranges(frames: int, shards: int, intra_period: int, gop: int):
+    """closed-GOP units grouped into contiguous shards: unit k >= 1 starts at frame k * IntraPeriod - (GOPSize - 1), the first
+    leading picture of the IDR at k * IntraPeriod; an IDR that lies beyond the last frame opens no unit"""
+    starts = [0] + [p - (gop - 1) for p in range(intra_period, frames, intra_period)]
+    bounds = starts + [frames]
+    units = len(starts)
+    out = []
+    for r in range(shards):
+        a, b = units * r // shards, units * (r + 1) // shards
+        if b > a:
+            out.append((bounds[a], bounds[b] - bounds[a]))
+    return out
+
+
+def plan_ranges(cfg, frames, shards, extra=()):
+    ip = cfg_value(cfg, extra, "IntraPeriod", "ip")
+    if ip == 1:
+        return frame_ranges(frames, shards)
+    gop = cfg_value(cfg, extra, "GOPSize", "g", 1)
+    if ip is not None and ip > 1 and cfg_value(cfg, extra, "DecodingRefreshType", "dr", 0) == 2 and gop >= 1 and ip > gop and ip % gop == 0:     # TAppEncCfg.cpp:513-516 wants IntraPeriod > GOPSize for periodic IDRs
+        return intra_period_ranges(frames, shards, ip, gop)
+    raise ValueError("sharding needs independent units: an all-intra configuration (IntraPeriod 1) or closed intra periods "
+                     "(IntraPeriod a multiple of GOPSize with --DecodingRefreshType=2); other inter pictures depend on the previous unit")
 
 
 def shard_encode(cfg, yuv, w, h, frames, shards, out, gpus=None, hm="none", extra=(), encoder=ENC, workdir=None):
-    if not cfg_is_all_intra(cfg) or any(a.startswith("--IntraPeriod") or a == "-ip" for a in extra):
-        raise ValueError("frame sharding needs an all-intra configuration (IntraPeriod 1): inter pictures depend on their references")
+    ranges = plan_ranges(cfg, frames, shards, extra)
     if not os.path.exists(encoder):
         raise RuntimeError("%s is not built (make -C thevc_b200/host hm)" % encoder)
     workdir = workdir or os.path.dirname(os.path.abspath(out))
-    ranges = frame_ranges(frames, shards)
     procs = []
     t0 = time.perf_counter()
     for r, (start, count) in enumerate(ranges):
