@@ -50,6 +50,8 @@ def test_inter_configurations_are_refused(tmp_path):
     _need()
     with pytest.raises(ValueError):
         se.shard_encode(os.path.join(CFG, "encoder_lowdelay_P_main.cfg"), "none.yuv", 64, 64, 4, 2, str(tmp_path / "o.bin"))
+    with pytest.raises(ValueError):         # low delay with periodic IDRs: the pictures of the IDR's GOP are coded BEFORE it and belong to the previous unit
+        se.plan_ranges(os.path.join(CFG, "encoder_lowdelay_P_main.cfg"), 64, 2, ("--IntraPeriod=32", "--DecodingRefreshType=2"))
     with pytest.raises(ValueError):         # random access as the cfg ships it: CRA, open GOP -> leading pictures cross the intra period
         se.shard_encode(os.path.join(CFG, "encoder_randomaccess_main.cfg"), "none.yuv", 64, 64, 64, 2, str(tmp_path / "o.bin"))
 

@@ -81,12 +81,20 @@ def intra_period_ranges(frames: int, shards: int, intra_period: int, gop: int):
     return out
 
 
+def cfg_idr_leads_its_gop(path: str, gop: int) -> bool:
+    """the GOP entry coded first (Frame1) is the GOP's last picture in output order, the slot an IDR at a multiple of GOPSize falls in
+    (hierarchical-B random access; in the low-delay structures Frame1 is POC 1 and pictures before the IDR are coded before it)"""
+    m = re.search(r"^\s*Frame1\s*:\s*\S+\s+(\d+)", open(path, encoding="latin-1").read(), re.M)
+    return bool(m) and int(m.group(1)) == gop
+
+
 def plan_ranges(cfg, frames, shards, extra=()):
     ip = cfg_value(cfg, extra, "IntraPeriod", "ip")
     if ip == 1:
         return frame_ranges(frames, shards)
     gop = cfg_value(cfg, extra, "GOPSize", "g", 1)
-    if ip is not None and ip > 1 and cfg_value(cfg, extra, "DecodingRefreshType", "dr", 0) == 2 and gop >= 1 and ip > gop and ip % gop == 0:     # TAppEncCfg.cpp:513-516 wants IntraPeriod > GOPSize for periodic IDRs
+    if ip is not None and ip > 1 and cfg_value(cfg, extra, "DecodingRefreshType", "dr", 0) == 2 and gop > 1 and ip > gop and ip % gop == 0 \
+            and cfg_idr_leads_its_gop(cfg, gop):     # TAppEncCfg.cpp:513-516 wants IntraPeriod > GOPSize for periodic IDRs
         return intra_period_ranges(frames, shards, ip, gop)
     raise ValueError("sharding needs independent units: an all-intra configuration (IntraPeriod 1) or closed intra periods "
                      "(IntraPeriod a multiple of GOPSize with --DecodingRefreshType=2); other inter pictures depend on the previous unit")
