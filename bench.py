@@ -167,8 +167,10 @@ class Workload:
         # predictor guesses (quarter pels): the synthetic global motion (3,5) px/frame x temporal distance + noise
         self.pred = np.zeros((NUM_REFS, self.nctu, 2), np.int32)
         for r in range(NUM_REFS):
-            self.pred[r, :, 0] = -3 * 4 * (r + 1)      # background content moves by (-3,-5)*dt relative to the past
-            self.pred[r, :, 1] = -5 * 4 * (r + 1)
+            # tests/synth.py crops bg[5t:, 3t:]: the block at (x, y) of the current picture sits at (x + 3 dt, y + 5 dt) in the
+            # picture dt frames back, so the motion vector towards reference r (dt = r + 1) is +(3, 5) * dt pels
+            self.pred[r, :, 0] = 3 * 4 * (r + 1)
+            self.pred[r, :, 1] = 5 * 4 * (r + 1)
         self.pred += rng.integers(-6, 7, self.pred.shape).astype(np.int32)
         self.pus = make_pu_list(W, H, rng)
         self.tus, self.tu_counts, self.coef_elems = make_tu_list(W, H, QP, BD)

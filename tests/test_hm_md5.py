@@ -249,3 +249,37 @@ def test_frame_prepass_feeds_the_cu_loop(tmp_path):
     assert fl, r.stderr[-600:]
     print(fl[-1])
     assert int(fl[-1].split()[3]) > 20, fl[-1]
+
+
+@pytest.mark.parametrize("case,hm", [
+    ("ldp_240_24", "me,frac,tables,frame,candgrid,verify"),      # 24 P pictures: the encoder recycles its picture buffers from POC ~11 on
+    ("ra_240_33", "me,frac,tables,candgrid,dbk,sao,verify"),     # random access as the cfg ships it: crosses the CRA at POC 32
+    ("ldb_240_17", "me,frac,tables,frame,candgrid"),             # low-delay B: two lists over the same pictures
+])
+def test_long_sequences_with_recycled_picture_buffers(tmp_path, case, hm):
+    """TEncTop::xGetNewPicBuffer reuses the oldest TComPic once GOPSize + maxDecPicBuffering + 2 pictures exist; a device slot that
+    still mapped the recycled buffer used to resolve reference pointers to the OLD picture (round-1 ADVICE, high).  Sequences long
+    enough to recycle, device slots beyond the first 21 uploads, the frame pre-pass across many pictures; `verify` re-runs every
+    look-up as a single search.  md5 against the unmodified reference's single run (tests/golden/hm_md5.json, or the reference
+    itself when it is here)."""
+    _need()
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_hm_md5 as gold
+    cfg, w, h, frames, extra = gold.CASES[case]
+    yuv = str(tmp_path / "in.yuv")
+    _yuv(yuv, w, h, frames)
+    cuda_bin = str(tmp_path / "cuda.bin")
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "hm_md5.json"))).get(case)
+    ref_job = None if g else _encode_ref_bg(cfg, yuv, w, h, frames, str(tmp_path / "ref.bin"), extra=extra)
+    r = _encode(ENC_CUDA, cfg, yuv, w, h, frames, cuda_bin, env={"TVC_HM": hm}, extra=extra)
+    if ref_job:
+        ref_job.result()
+    want = g["md5"] if g else _md5(str(tmp_path / "ref.bin"))
+    assert _md5(cuda_bin) == want, [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda")]
+    line = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda look-up:")]
+    assert line, r.stderr[-600:]
+    print(line[-1])
+    f = line[-1].split()
+    assert int(f[2]) > 0.8 * int(f[4]), line[-1]

@@ -115,3 +115,37 @@ def test_sharded_stream_equals_single_run_gpu(tmp_path, cfg):
     assert r["md5"] == ref_md5, r
     log = open(str(tmp_path / "shard_001.bin.log")).read()
     assert "TLibCuda intra rough search:" in log and "POC    1" in log and "POC    2" in log and "POC    0" not in log
+
+
+def test_stateful_extra_arguments_are_refused():
+    for bad in (["--RateControl=1"], ["-f", "3"], ["-fs", "2"], ["--FrameSkip=4"], ["--TargetBitrate=1000"]):
+        with pytest.raises(ValueError):
+            se.check_extra(bad)
+    se.check_extra(["--SEIpictureDigest=1", "--DecodingRefreshType=2", "--IntraPeriod=16", "--RateControl=0"])
+    assert se.shards_per_gpu(1920, 1080, "me,frac,tables") == 4 and se.shards_per_gpu(416, 240, "me,frac,tables") >= 16
+    assert se.shards_per_gpu(3840, 2160, "intra16,dbk,sao") == 16
+
+
+@pytest.mark.gpu
+def test_intra_period_shards_with_device_hooks_gpu(tmp_path):
+    """BASELINE configs[2] at the CPU-runnable size with the ME hooks on in every shard: 33 pictures, IntraPeriod 16, IDR refresh =
+    units [0,9) [9,25) [25,33); the concatenation has the md5 of the unmodified reference's single run"""
+    _need()
+    import json
+    cfg, w, h, frames = "encoder_randomaccess_main.cfg", 416, 240, 33
+    extra = ["--DecodingRefreshType=2", "--IntraPeriod=16"]
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "hm_md5.json"))).get("ra_240_33_idr_ip16")
+    if g:
+        yuv = str(tmp_path / "in.yuv")
+        with open(yuv, "wb") as f:
+            for y, u, v in synth.make_sequence(w, h, frames):
+                f.write(y.astype(np.uint8).tobytes()); f.write(u.astype(np.uint8).tobytes()); f.write(v.astype(np.uint8).tobytes())
+        ref_md5 = g["md5"]
+    else:
+        yuv, ref_md5 = _setup(tmp_path, cfg, w, h, frames, extra)
+    out = str(tmp_path / "out.bin")
+    r = se.shard_encode(os.path.join(CFG, cfg), yuv, w, h, frames, 3, out, hm="me,frac,tables,candgrid,dbk,sao", extra=["--SEIpictureDigest=1"] + extra)
+    assert r["md5"] == ref_md5, r
+    assert r["ranges"] == [(0, 9), (9, 16), (25, 8)]
+    log = open(str(tmp_path / "shard_001.bin.log")).read()
+    assert "TLibCuda look-up:" in log and " 0 xTZSearch" not in log

@@ -101,7 +101,7 @@ def main():
                  r'  if ( !getUseScalingList() && tlibcuda_rdoq( pcCU, plSrcCoeff, piDstCoeff, piArlDstCoeff, uiWidth, uiHeight, uiAbsSum, (int)eTType, uiAbsPartIdx, m_cQP.m_iPer, m_cQP.m_iRem, m_dLambda, m_pcEstBitsSbac, m_bUseAdaptQpSelect ) ) return;\n\1',
                  "xRateDistOptQuant")
     s = sub_once(s, r'(Void TComTrQuant::invtransformNxN\( Bool transQuantBypass, TextType eText, UInt uiMode,Pel\* rpcResidual, UInt uiStride, TCoeff\*   pcCoeff, UInt uiWidth, UInt uiHeight,  Int scalingListType, Bool useTransformSkip \)\r?\n\{\r?\n)',
-                 r'\1  if ( tlibcuda_defer_itransform( transQuantBypass, (int)eText, rpcResidual, uiStride, pcCoeff, uiWidth, uiHeight, m_cQP.m_iPer, m_cQP.m_iRem, useTransformSkip ) ) return;\n',
+                 r'\1  if ( tlibcuda_defer_itransform( transQuantBypass, (int)eText, rpcResidual, uiStride, pcCoeff, uiWidth, uiHeight, m_cQP.m_iPer, m_cQP.m_iRem, useTransformSkip, getUseScalingList() ) ) return;\n',
                  "invtransformNxN")
     wr(os.path.join(out, "TLibCommon", "TComTrQuant.cpp"), s)
     # ---- TDecCu.cpp / TDecGop.cpp: picture-level batch of the inter reconstruction

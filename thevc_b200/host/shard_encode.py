@@ -100,35 +100,106 @@ def plan_ranges(cfg, frames, shards, extra=()):
                      "(IntraPeriod a multiple of GOPSize with --DecodingRefreshType=2); other inter pictures depend on the previous unit")
 
 
-def shard_encode(cfg, yuv, w, h, frames, shards, out, gpus=None, hm="none", extra=(), encoder=ENC, workdir=None):
+STATEFUL_OPTIONS = ("RateControl", "RateCtrl", "TargetBitrate", "NumLCUInUnit", "FrameSkip", "FramesToBeEncoded")
+
+
+def check_extra(extra):
+    """options that carry state across pictures (rate control) or move the frame window (-f / -fs: the shards set their own)
+    break the byte-identical concatenation and are refused"""
+    for a in extra:
+        key = a.lstrip("-").split("=", 1)[0]
+        if a in ("-f", "-fs") or key in STATEFUL_OPTIONS:
+            if key.startswith("Rate") and "=" in a and a.split("=", 1)[1] in ("0", "false"):
+                continue
+            raise ValueError("shard_encode: '%s' is not allowed in the extra encoder arguments (state across pictures / frame window)" % a)
+
+
+def visible_gpus():
+    """device indices of this box (nvidia-smi -L); [] without a driver"""
+    try:
+        r = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30)
+        return [i for i, ln in enumerate(r.stdout.splitlines()) if ln.startswith("GPU ")] if r.returncode == 0 else []
+    except (OSError, subprocess.TimeoutExpired):
+        return []
+
+
+def shards_per_gpu(w, h, hm, hbm_gb=150):
+    """how many shard processes one GPU holds: every process with the `tables` hook reserves the SAD tables of four references
+    (17.04 MB per (CTU, reference): 34.8 GB at 1080p)"""
+    if "tables" not in hm.split(","):
+        return 16
+    nctu = ((w + 63) // 64) * ((h + 63) // 64)
+    return max(1, int(hbm_gb * 1e9 // (nctu * 4 * 17.04e6 + 2e9)))
+
+
+def shard_encode(cfg, yuv, w, h, frames, shards, out, gpus=None, hm="none", extra=(), encoder=ENC, workdir=None, max_per_gpu=None):
+    check_extra(extra)
     ranges = plan_ranges(cfg, frames, shards, extra)
     if not os.path.exists(encoder):
         raise RuntimeError("%s is not built (make -C thevc_b200/host hm)" % encoder)
     workdir = workdir or os.path.dirname(os.path.abspath(out))
-    procs = []
+    device_hooks = hm not in ("", "none")
+    if device_hooks and not gpus:
+        gpus = visible_gpus()
+        if not gpus:
+            raise RuntimeError("shard_encode: device hooks (%s) need a GPU and none is visible" % hm)
+    cap = max_per_gpu or (shards_per_gpu(w, h, hm) if device_hooks else len(ranges))
+    load = {g: 0 for g in (gpus or [None])}
+    pending = list(enumerate(ranges))
+    running, parts = [], [None] * len(ranges)
     t0 = time.perf_counter()
-    for r, (start, count) in enumerate(ranges):
-        part = os.path.join(workdir, "shard_%03d.bin" % r)
-        env = dict(os.environ, TVC_POC_OFFSET=str(start), TVC_HM=hm)
-        if gpus:
-            env["CUDA_VISIBLE_DEVICES"] = str(gpus[r % len(gpus)])
-        cmd = [encoder, "-c", cfg, "-i", yuv, "-wdt", str(w), "-hgt", str(h), "-fr", "30", "-fs", str(start), "-f", str(count), "-b", part, "-o", os.devnull] + list(extra)
-        log = open(part + ".log", "w")
-        procs.append((part, log, subprocess.Popen(cmd, stdout=log, stderr=subprocess.STDOUT, env=env)))
-    for part, log, p in procs:
-        rc = p.wait()
-        log.close()
-        if rc != 0:
-            raise RuntimeError("shard %s failed (%d): %s" % (part, rc, open(part + ".log").read()[-800:]))
+    shard_wall = [0.0] * len(ranges)
+
+    def kill_all():
+        for _, _, _, _, p, _ in running:
+            if p.poll() is None:
+                p.kill()
+        for _, _, _, log, p, _ in running:
+            p.wait()
+            log.close()
+
+    try:
+        while pending or running:
+            # start every shard a GPU has room for (least loaded first)
+            while pending:
+                g = min(load, key=lambda k: load[k])
+                if load[g] >= cap:
+                    break
+                r, (start, count) = pending.pop(0)
+                part = os.path.join(workdir, "shard_%03d.bin" % r)
+                env = dict(os.environ, TVC_POC_OFFSET=str(start), TVC_HM=hm)
+                if g is not None:
+                    env["CUDA_VISIBLE_DEVICES"] = str(g)
+                cmd = [encoder, "-c", cfg, "-i", yuv, "-wdt", str(w), "-hgt", str(h), "-fr", "30", "-fs", str(start), "-f", str(count), "-b", part,
+                       "-o", os.devnull] + list(extra)
+                log = open(part + ".log", "w")
+                running.append((r, g, part, log, subprocess.Popen(cmd, stdout=log, stderr=subprocess.STDOUT, env=env), time.perf_counter()))
+                load[g] += 1
+                parts[r] = part
+            done = [x for x in running if x[4].poll() is not None]
+            if not done:
+                time.sleep(0.05)
+                continue
+            for x in done:
+                r, g, part, log, p, ts = x
+                running.remove(x)
+                log.close()
+                load[g] -= 1
+                shard_wall[r] = time.perf_counter() - ts
+                if p.returncode != 0:
+                    raise RuntimeError("shard %s failed (%d): %s" % (part, p.returncode, open(part + ".log").read()[-800:]))
+    except BaseException:
+        kill_all()          # one failed shard ends the job: the others are stopped, their logs closed
+        raise
     wall = time.perf_counter() - t0
     md5 = hashlib.md5()
     with open(out, "wb") as fo:                      # the whole exchange step of this path: concatenation on the host
-        for part, _, _ in procs:
+        for part in parts:
             data = open(part, "rb").read()
             fo.write(data)
             md5.update(data)
     return {"frames": frames, "shards": len(ranges), "ranges": ranges, "wall_s": wall, "fps": frames / wall, "md5": md5.hexdigest(),
-            "bytes": os.path.getsize(out)}
+            "bytes": os.path.getsize(out), "gpus": gpus, "shards_per_gpu_limit": cap, "shard_wall_s": [round(x, 2) for x in shard_wall], "hm": hm}
 
 
 def main():
@@ -142,10 +213,11 @@ def main():
     ap.add_argument("-o", "--out", required=True)
     ap.add_argument("--gpus", default="", help="comma list of device indices, one per shard (round robin)")
     ap.add_argument("--hm", default="none", help="TVC_HM hook list of the shards (none = the reference's own code)")
+    ap.add_argument("--max-per-gpu", type=int, default=0, help="shard processes per GPU at a time (default: derived from the SAD-table size)")
     ap.add_argument("extra", nargs="*")
     a = ap.parse_args()
     gpus = [int(g) for g in a.gpus.split(",") if g != ""] or None
-    print(json.dumps(shard_encode(a.cfg, a.input, a.wdt, a.hgt, a.frames, a.shards, a.out, gpus, a.hm, a.extra)))
+    print(json.dumps(shard_encode(a.cfg, a.input, a.wdt, a.hgt, a.frames, a.shards, a.out, gpus, a.hm, a.extra, max_per_gpu=a.max_per_gpu or None)))
 
 
 if __name__ == "__main__":

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <unordered_map>
 #include <utility>
+#include <string>
 
 #define private public
 #define protected public
@@ -143,6 +144,7 @@ struct State {
   bool on_hash = false;                    // picture hashes on the device (TVC_HM=...,hash)
   unsigned long long n_hash = 0;
   bool on_cand = false;                    // merge / AMVP candidate evaluation (TVC_HM=...,cand)
+  bool on_bipred = true;                   // bi-prediction refinement searches on the device (off: TVC_HM=...,nobipred)
   bool on_cand_grid = false;               // ... served by look-up from CTU-wide cost grids (TVC_HM=...,candgrid)
   struct Grid { uint32_t w[TVC_GRID_WORDS]; };
   std::unordered_map<unsigned long long, Grid> grids;      // (CTU, reference slot, clipped MV) -> prefix-sum grids; cleared per picture
@@ -244,35 +246,57 @@ void stats_report()
   fprintf(stderr, "\n");
 }
 
+// TVC_HM is a comma list; every entry is matched as a WHOLE token ("frame" does not switch "me" on, "candgrid" implies "cand",
+// "intraN" = intra rough search for PUs of width >= N).  Unset = me,frac,tq,rdoq,mc,tables (every per-call hook of the round-1 ABI);
+// dbk, sao, intra, cand, candgrid, hash, frame, batch, bipred are opt-in.  Unknown tokens are fatal: a typo must not silently
+// run the reference path.
 void parse_env()
 {
   State& s = S();
   const char* e = getenv("TVC_HM");
   if (!e) return;
-  s.on_me = strstr(e, "me") != nullptr;
-  s.on_frac = strstr(e, "frac") != nullptr;
-  s.on_tq = strstr(e, "tq") != nullptr;
-  s.on_rdoq = strstr(e, "rdoq") != nullptr;
-  s.on_mc = strstr(e, "mc") != nullptr;
-  s.on_tables = strstr(e, "tables") != nullptr;
-  s.verbose = strstr(e, "verbose") != nullptr;
-  s.on_lookup = strstr(e, "nolookup") == nullptr;
-  s.verify = strstr(e, "verify") != nullptr;
-  s.dec.on = strstr(e, "batch") != nullptr;
-  s.sao.dump = strstr(e, "saodump") != nullptr;
-  s.sao.on = !s.sao.dump && strstr(e, "sao") != nullptr;
-  s.dbk.dump = strstr(e, "dbkdump") != nullptr;
-  s.dbk.on = !s.dbk.dump && strstr(e, "dbk") != nullptr;
-  s.on_frame = strstr(e, "frame") != nullptr;
-  s.on_hash = strstr(e, "hash") != nullptr;
-  s.on_cand = strstr(e, "cand") != nullptr;
-  s.on_cand_grid = strstr(e, "candgrid") != nullptr;
-  s.intra.dump = strstr(e, "intradump") != nullptr;
-  if (const char* p = strstr(e, "intra")) {
-    s.intra.on = !s.intra.dump;
-    if (s.intra.on && p[5] >= '0' && p[5] <= '9') s.intra.min_width = atoi(p + 5);
+  s.on_me = s.on_frac = s.on_tq = s.on_rdoq = s.on_mc = s.on_tables = false;
+  std::string list(e);
+  size_t pos = 0;
+  while (pos <= list.size()) {
+    size_t q = list.find(',', pos);
+    if (q == std::string::npos) q = list.size();
+    std::string t = list.substr(pos, q - pos);
+    pos = q + 1;
+    while (!t.empty() && (t.back() == ' ' || t.back() == '\t')) t.pop_back();
+    while (!t.empty() && (t.front() == ' ' || t.front() == '\t')) t.erase(t.begin());
+    if (t.empty() || t == "none") continue;
+    if (t == "me") s.on_me = true;
+    else if (t == "frac") s.on_frac = true;
+    else if (t == "tq") s.on_tq = true;
+    else if (t == "rdoq") s.on_rdoq = true;
+    else if (t == "mc") s.on_mc = true;
+    else if (t == "tables") s.on_tables = true;
+    else if (t == "verbose") s.verbose = true;
+    else if (t == "nolookup") s.on_lookup = false;
+    else if (t == "verify") s.verify = true;
+    else if (t == "batch") s.dec.on = true;
+    else if (t == "saodump") s.sao.dump = true;
+    else if (t == "sao") s.sao.on = true;
+    else if (t == "dbkdump") s.dbk.dump = true;
+    else if (t == "dbk") s.dbk.on = true;
+    else if (t == "frame") s.on_frame = true;
+    else if (t == "hash") s.on_hash = true;
+    else if (t == "cand") s.on_cand = true;
+    else if (t == "candgrid") s.on_cand = s.on_cand_grid = true;
+    else if (t == "bipred") s.on_bipred = true;
+    else if (t == "nobipred") s.on_bipred = false;
+    else if (t == "intradump") s.intra.dump = true;
+    else if (t.compare(0, 5, "intra") == 0 && t.find_first_not_of("0123456789", 5) == std::string::npos) {
+      s.intra.on = true;
+      if (t.size() > 5) s.intra.min_width = atoi(t.c_str() + 5);
+    } else if (t == "stats") PS().on = true;
+    else { fprintf(stderr, "TLibCuda: unknown TVC_HM entry '%s'\n", t.c_str()); exit(EXIT_FAILURE); }
   }
-  if (strstr(e, "stats")) { PS().on = true; s.on_me = s.on_frac = s.on_tq = s.on_rdoq = s.on_mc = s.on_tables = false; atexit(stats_report); }
+  if (s.sao.dump) s.sao.on = false;
+  if (s.dbk.dump) s.dbk.on = false;
+  if (s.intra.dump) s.intra.on = false;
+  if (PS().on) { s.on_me = s.on_frac = s.on_tq = s.on_rdoq = s.on_mc = s.on_tables = false; atexit(stats_report); }
 }
 
 void init_once()
@@ -294,6 +318,13 @@ void ensure_ctx(int w, int ht)
     tvc_ctx_destroy(s.h);
     s.h = nullptr;
   }
+  if (g_uiMaxCUWidth != 64 || g_uiMaxCUHeight != 64) {
+    // the kernels' CTU geometry (census, SAD tables, cost grids) is the 64x64 CTU of every cfg the reference ships: any other
+    // MaxCUWidth runs the reference's own code below every hook instead of dying in tvc_ctx_create
+    fprintf(stderr, "TLibCuda: MaxCUWidth %u is not supported by the device path (64 only): hooks off, the reference's code runs\n", g_uiMaxCUWidth);
+    s.disabled = true;
+    return;
+  }
   tvc_config c;
   c.width = w; c.height = ht;
   c.bit_depth = (int)(g_uiBitDepth + g_uiBitIncrement);
@@ -302,7 +333,8 @@ void ensure_ctx(int w, int ht)
   c.device = 0;
   int rc = tvc_ctx_create(&c, &s.h);
   if (rc != TVC_OK) {
-    fprintf(stderr, "TLibCuda: tvc_ctx_create failed (%d): no CUDA device -- there is no CPU fallback\n", rc);
+    fprintf(stderr, "TLibCuda: tvc_ctx_create failed (%d): %s -- there is no CPU fallback\n", rc,
+            rc == TVC_ERR_ARG ? "unsupported picture geometry" : "no usable CUDA device");
     exit(EXIT_FAILURE);
   }
   s.w = w; s.ht = ht;
@@ -323,8 +355,20 @@ int slot_for(TComPicYuv* yuv, int poc, bool is_org, bool with_margin)
     DevPic& d = s.slots[i];
     if (d.yuv == yuv && d.poc == poc && d.is_org == is_org) { d.stamp = ++s.clock; return (int)i; }
   }
-  for (size_t i = 0; i < s.slots.size(); i++)
-    if (s.slots[i].stamp < oldest) { oldest = s.slots[i].stamp; free_slot = (int)i; }
+  // the encoder recycles its picture buffers (TEncTop::xGetNewPicBuffer, TEncTop.cpp:411-452: once the list holds
+  // GOPSize + maxDecPicBuffering + 2 pictures the oldest unreferenced TComPic is reused): a slot that still maps this buffer
+  // with ANOTHER POC holds a picture that no longer exists on the host.  It is taken over, so that no two slots ever alias one
+  // host buffer and locate() cannot resolve a pointer to stale device content.
+  for (size_t i = 0; i < s.slots.size(); i++) {
+    DevPic& d = s.slots[i];
+    if (d.yuv == yuv && d.is_org == is_org && d.stamp != ~0ull) {
+      if (free_slot < 0) free_slot = (int)i;
+      else d = DevPic();
+    }
+  }
+  if (free_slot < 0)
+    for (size_t i = 0; i < s.slots.size(); i++)
+      if (s.slots[i].stamp < oldest) { oldest = s.slots[i].stamp; free_slot = (int)i; }
   DevPic& d = s.slots[free_slot];
   d.yuv = yuv; d.poc = poc; d.is_org = is_org; d.stamp = ++s.clock;
   CK(tvc_pic_upload(s.h, free_slot, yuv->getLumaAddr(), yuv->getStride(), yuv->getCbAddr(), yuv->getCrAddr(), yuv->getCStride(),
@@ -336,19 +380,22 @@ int slot_for(TComPicYuv* yuv, int poc, bool is_org, bool with_margin)
 bool locate(const short* p, int& slot, int& x, int& y)
 {
   State& s = S();
+  unsigned long long best = 0;
+  bool found = false;
   for (size_t i = 0; i < s.slots.size(); i++) {
     DevPic& d = s.slots[i];
-    if (!d.yuv || d.is_org) continue;
+    if (!d.yuv || d.is_org || d.stamp == ~0ull) continue;
     const short* org = d.yuv->getLumaAddr();
     const int stride = d.yuv->getStride();
     const ptrdiff_t off = p - org;
     if (off < 0 || off >= (ptrdiff_t)stride * d.yuv->getHeight()) continue;
-    y = (int)(off / stride); x = (int)(off % stride);
-    if (x >= d.yuv->getWidth()) continue;
-    slot = (int)i;
-    return true;
+    const int yy = (int)(off / stride), xx = (int)(off % stride);
+    if (xx >= d.yuv->getWidth()) continue;
+    if (found && d.stamp < best) continue;        // slot_for keeps one slot per host buffer; should two ever match, the newest upload wins
+    found = true; best = d.stamp;
+    slot = (int)i; x = xx; y = yy;
   }
-  return false;
+  return found;
 }
 
 }  // namespace
@@ -450,6 +497,7 @@ bool tlibcuda_tz_search(TComDataCU* cu, TComPattern* key, short* refY, int refSt
     return false;
   }
   if (!s.h || !s.on_me || s.cur_slot < 0) return false;
+  if (searchRange < 1 || searchRange > TVC_ME_RANGE) return false;      // SearchRange beyond the kernels' +-64 window: the reference's own search
   // weighted prediction changes the distortion itself (setWpScalingDistParam, TEncSearch.cpp:4177): not ported, reference path
   if (cu->getSlice()->getPPS()->getUseWP() || cu->getSlice()->getPPS()->getWPBiPred()) return false;
   int slot, x, y;
@@ -888,6 +936,9 @@ bool tlibcuda_dec_begin_inter(TComDataCU* cu, TComYuv* resi)
   DecBatch& d = s.dec;
   if (!s.h || !d.on || !s.on_mc || !s.on_tq) return false;
   if (cu->getSlice()->getPPS()->getUseWP() || cu->getSlice()->getPPS()->getWPBiPred()) return false;     // weighted prediction: host reconstruction
+  // scaling lists: the batch dequantises with the flat per / rem tables only, so such a stream's CUs are never opened and the
+  // reference's own xDeQuant( scalingListType ) reconstructs them (TComTrQuant.cpp:1272-1355)
+  if (cu->getSlice()->getSPS()->getScalingListFlag()) { d.cu_open = false; return false; }
   d.cu_open = true;
   d.cu_x = (int)cu->getCUPelX(); d.cu_y = (int)cu->getCUPelY();
   d.resi_base[0] = resi->getLumaAddr(); d.resi_base[1] = resi->getCbAddr(); d.resi_base[2] = resi->getCrAddr();
@@ -897,11 +948,15 @@ bool tlibcuda_dec_begin_inter(TComDataCU* cu, TComYuv* resi)
 }
 
 bool tlibcuda_defer_itransform(bool bypass, int ttype, short* resi, unsigned stride, int* coeff, unsigned w, unsigned h, int per, int rem,
-                               bool transformSkip)
+                               bool transformSkip, bool scalingList)
 {
   State& s = S();
   DecBatch& d = s.dec;
   if (!d.cu_open || w != h) return false;
+  if (scalingList && !bypass) {            // cannot happen: tlibcuda_dec_begin_inter does not open a CU of a scaling-list stream
+    fprintf(stderr, "TLibCuda: scaling-list TU inside the decoder picture batch\n");
+    exit(EXIT_FAILURE);
+  }
   const int plane = ttype == TEXT_LUMA ? 0 : (ttype == TEXT_CHROMA_U ? 1 : 2);
   const ptrdiff_t off = resi - d.resi_base[plane];
   if (off < 0 || (int)stride != d.resi_stride[plane]) return false;      // not this CU's residual buffer: leave it to the host

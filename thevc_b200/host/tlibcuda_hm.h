@@ -9,8 +9,9 @@
  * reference's own code below the hook runs -- that is the reference's implementation, not a CPU
  * fallback of ours.  A CUDA error is fatal (exit(EXIT_FAILURE)), like the reference's own errors.
  *
- * Which hooks are active is chosen with the environment variable TVC_HM (comma list of
- * me,frac,tq,rdoq,mc,tables; default all; "none" runs the unmodified path).
+ * Which hooks are active is chosen with the environment variable TVC_HM: a comma list of whole tokens.  Unset = the per-call
+ * hooks me,frac,tq,rdoq,mc,tables; opt-in: frame, candgrid / cand, dbk, sao, intra[N], hash, batch (decoder), verify, verbose,
+ * nobipred (bi-prediction refinement back on the reference's code); "none" runs the unmodified path; an unknown token is fatal.
  */
 #ifndef TLIBCUDA_HM_H
 #define TLIBCUDA_HM_H
@@ -53,7 +54,7 @@ bool tlibcuda_dec_begin_inter(TComDataCU* cu, TComYuv* resi);
 void tlibcuda_dec_flush(TComPic* pic);
 /* TComTrQuant::invtransformNxN (TComTrQuant.cpp:1428): true = recorded for the picture batch, nothing to do */
 bool tlibcuda_defer_itransform(bool bypass, int ttype, short* resi, unsigned stride, int* coeff, unsigned w, unsigned h, int per, int rem,
-                               bool transformSkip);
+                               bool transformSkip, bool scalingList);
 
 /* ---- deblocking (TVC_HM=...,dbk): TComLoopFilter::loopFilterPic (TComLoopFilter.cpp:153) keeps deriving the boundary
  * strengths on the host; xEdgeFilterLuma (:571) hands every edge unit with bs != 0 to tlibcuda_dbk_unit instead of
