@@ -199,6 +199,12 @@ int tvc_me_prepass(tvc_ctx* ctx, int cur_slot, int num_refs, const int* ref_slot
 /* allocate the SAD tables for num_refs references ahead of time (17.04 MB per CTU and reference; tvc_me_prepass grows
  * them on demand otherwise, and re-allocating tens of GB costs 0.2-0.6 s each time the reference count of a GOP grows) */
 int tvc_me_reserve(tvc_ctx* ctx, int num_refs);
+/* 1 when the census entry points below (tvc_me_frame, tvc_me_ctu with cfg->use_tables) read SAD tables from HBM and therefore
+ * need tvc_me_prepass for the picture first (TVC_ME_FUSED=0, the round-1 form); 0 when they compute every SAD on demand from a
+ * search window staged in shared memory (default; tvc_me_group.cu) and no table is ever written.                              */
+int tvc_me_uses_tables(tvc_ctx* ctx);
+/* choose the form per context: 1 group search, 0 SAD tables, -1 back to the environment's choice */
+int tvc_me_set_fused(tvc_ctx* ctx, int on);
 /* bytes of table storage tvc_me_prepass needs for num_refs references (allocated lazily)       */
 size_t tvc_me_table_bytes(tvc_ctx* ctx, int num_refs);
 /* device pointer to the tables of the last pre-pass and the (clamped) centres actually used    */
@@ -308,10 +314,11 @@ int tvc_me_frame_dev(tvc_ctx* ctx, int cur_slot, int num_refs, const int* ref_sl
 int tvc_me_ctu(tvc_ctx* ctx, int cur_slot, int ref_index, int ref_slot, int ctu, tvc_me_center pred_qpel,
                const tvc_me_frame_cfg* cfg, tvc_me_result* int_out, tvc_frac_result* frac_out);
 
-/* work counters of the last tvc_me_frame[_dev] call (for roofline accounting): stats[0] = 16-byte table
- * granules the reference-visible candidates of k_me_search required (candidates each PU search evaluated
- * itself x granules of that PU; speculative evaluations not counted), stats[1] = candidates served by the
- * shared raster stage, stats[2] = raster candidates walked by k_me_raster (1 KB each).  Synchronises.  */
+/* work counters of the last tvc_me_frame[_dev] call (for roofline accounting).  Default (group search): stats[0] = candidate
+ * SAD grids (64x64 absolute differences each) computed from the staged windows, stats[1] = candidate grids computed from the
+ * reference plane in global memory (candidates beyond the staged window), stats[2] = lock-step rounds summed over the groups.
+ * TVC_ME_FUSED=0 (SAD tables): stats[0] = 16-byte table granules the reference-visible candidates of k_me_search required,
+ * stats[1] = candidates served by the shared raster stage, stats[2] = raster candidates walked by k_me_raster.  Synchronises. */
 int tvc_me_frame_stats(tvc_ctx* ctx, uint64_t stats[3]);
 
 /* ---------------------------------------------------------------------------------- transform / quant

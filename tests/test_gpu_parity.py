@@ -466,9 +466,19 @@ def test_me_search_10bit_direct(ctx10, orc):
         assert (g.mvx, g.mvy, g.sad, g.n_sads) == (e.mvx, e.mvy, e.sad, e.n_sads)
 
 
-def test_me_frame_prepass(ctx8, orc):
+@pytest.fixture(params=[1, 0], ids=["group-search", "sad-tables"])
+def ctx8_form(request, ctx8):
+    """both forms of the fast integer stage: the group search (default; SADs on demand from the staged window) and the round-1
+    form with full SAD tables in HBM (TVC_ME_FUSED=0)"""
+    ctx8.L.tvc_me_set_fused(ctx8.h, request.param)
+    assert ctx8.L.tvc_me_uses_tables(ctx8.h) == 1 - request.param
+    yield ctx8
+    ctx8.L.tvc_me_set_fused(ctx8.h, -1)
+
+
+def test_me_frame_prepass(ctx8_form, orc):
     """frame pre-pass = for every census PU x CTU x reference: xSetSearchRange + xTZSearch + xPatternSearchFracDIF"""
-    t = ctx8
+    t = ctx8_form
     seq = synth.make_sequence(W, H, 3)
     cur = synth.to_hostpic(seq[2], W, H)
     refs = [synth.to_hostpic(seq[1], W, H), synth.to_hostpic(seq[0], W, H)]
@@ -516,12 +526,72 @@ def test_me_frame_prepass(ctx8, orc):
     assert checked > 2000
 
 
-def test_me_ctu_group(ctx8, orc):
+@pytest.mark.parametrize("kind", ["far-motion", "noise", "static-with-far-predictor"])
+def test_me_group_search_hard_content(ctx8, orc, kind):
+    """the group search where the PUs of a CTU disagree: content that moved far from the predictor (first sweep lands at distance
+    > 5: raster stage + several refinement rounds), pure noise (every PU ends somewhere else: hundreds of distinct candidates per
+    round) and a predictor far from a static scene (the zero vector wins: sweeps centred outside the staged window, candidates
+    from the reference plane in global memory).  Every PU of every CTU against the per-PU kernel (SADs straight from the
+    pictures, itself oracle-checked), a sample against the oracle."""
+    t = ctx8
+    rng = np.random.default_rng({"far-motion": 71, "noise": 72, "static-with-far-predictor": 73}[kind])
+    nctu = t.ctus_x * t.ctus_y
+    base = synth.random_pic(rng, W + 128, H + 128, 8, extend=False).y
+    k3 = np.ones(3) / 3.0
+    sm = np.apply_along_axis(lambda r: np.convolve(r, k3, mode="same"), 1, base.astype(np.float64))
+    sm = np.apply_along_axis(lambda c: np.convolve(c, k3, mode="same"), 0, sm)
+    cur, ref = synth.random_pic(rng, W, H, 8, extend=False), synth.random_pic(rng, W, H, 8, extend=False)
+    if kind == "far-motion":
+        cur.y[:] = np.rint(sm[64:64 + H, 64:64 + W]); ref.y[:] = np.rint(sm[64 - 29:64 - 29 + H, 64 + 37:64 + 37 + W])
+        pred = rng.integers(-8, 9, (1, nctu, 2)).astype(np.int32)
+    elif kind == "noise":
+        pred = rng.integers(-60, 61, (1, nctu, 2)).astype(np.int32)
+    else:
+        cur.y[:] = np.rint(sm[64:64 + H, 64:64 + W]); ref.y[:] = cur.y + rng.integers(-2, 3, cur.y.shape)
+        pred = np.zeros((1, nctu, 2), np.int32)
+        pred[0, :, 0] = rng.choice([-600, 520, 300], nctu); pred[0, :, 1] = rng.choice([-380, 410, 280], nctu)
+    cur.extend_border(); ref.extend_border()
+    t.upload(0, cur); t.upload(1, ref)
+    lc = orc.orc_lambda_motion_sad(33.0)
+    t.L.tvc_me_set_fused(t.h, 1)
+    try:
+        ires, _ = t.me_frame(0, [1], pred, lc, do_frac=False)
+        stats = t.me_frame_stats()
+    finally:
+        t.L.tvc_me_set_fused(t.h, -1)
+    ires0, _ = t.me_frame(0, [1], pred, lc, use_tables=False, do_frac=False)
+    bad = np.argwhere(ires != ires0)
+    assert bad.size == 0, (kind, bad[:5], ires[tuple(bad[0])], ires0[tuple(bad[0])])
+    print(kind, stats, "mean candidates per search", float(ires["n_sads"][ires["n_sads"] > 0].mean()))
+    census = t.me_census()
+    checked = 0
+    for ctu in rng.choice(nctu, 6, replace=False):
+        x0, y0 = (ctu % t.ctus_x) * 64, (ctu // t.ctus_x) * 64
+        for k in rng.choice(593, 12, replace=False):
+            px, py, w, h, cux, cuy = (int(v) for v in census[k])
+            x, y = x0 + px, y0 + py
+            if x + w > W or y + h > H:
+                continue
+            g = oracle.CuGeom(W, H, x0 + cux, y0 + cuy, 64)
+            predx, predy = int(pred[0, ctu, 0]), int(pred[0, ctu, 1])
+            lx, ty, rx, by = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+            orc.orc_set_search_range(C.byref(g), predx, predy, 64, C.byref(lx), C.byref(ty), C.byref(rx), C.byref(by))
+            e = oracle.MeResult()
+            orc.orc_tz_search(C.byref(g), optr(cur.buf_y, cur.origin(0) + y * cur.stride + x), cur.stride,
+                              optr(ref.buf_y, ref.origin(0) + y * ref.stride + x), ref.stride, w, h, lx.value, ty.value, rx.value, by.value,
+                              64, 1, 0, lc, predx, predy, predx, predy, C.byref(e))
+            gi = ires[0, ctu, k]
+            assert (gi["mvx"], gi["mvy"], gi["sad"], gi["n_sads"]) == (e.mvx, e.mvy, e.sad, e.n_sads), (kind, ctu, k)
+            checked += 1
+    assert checked > 40
+
+
+def test_me_ctu_group(ctx8_form, orc):
     """tvc_me_ctu: one (CTU, reference) census group with an explicit predictor.  The frame pre-pass run with that
     predictor for the CTU gives the same 593 results (itself oracle-checked above); predictors different from the one the
     SAD tables were centred on are served too (candidates outside the table window are evaluated from the pictures),
     checked against the oracle; and the table-less form agrees."""
-    t = ctx8
+    t = ctx8_form
     seq = synth.make_sequence(W, H, 3)
     cur = synth.to_hostpic(seq[2], W, H)
     refs = [synth.to_hostpic(seq[1], W, H), synth.to_hostpic(seq[0], W, H)]

@@ -207,7 +207,8 @@ def test_candidate_evaluation_on_device(tmp_path, cfg, frames, mode):
     assert cl, r.stderr[-600:]
     print(cl[-1])
     f = cl[-1].split()
-    assert int(f[3]) > 100 and int(f[9]) > 1000, cl[-1]
+    # candgrid leaves bi-predicted merge sets (most of a B slice's) to the reference's code: only the AMVP templates are certain to be many
+    assert (int(f[3]) > 100 or mode == "candgrid") and int(f[9]) > 1000, cl[-1]
 
 
 @pytest.mark.parametrize("digest", [1, 2, 3])

@@ -142,6 +142,8 @@ SIGNATURES = {
     "tvc_mc_block": (ci, [vp, ci, ci, ci, ci, ci, ci, ci, ci, vp, ci, vp, vp, ci]),
     "tvc_me_prepass": (ci, [vp, ci, ci, vp, vp]),
     "tvc_me_reserve": (ci, [vp, ci]),
+    "tvc_me_uses_tables": (ci, [vp]),
+    "tvc_me_set_fused": (ci, [vp, ci]),
     "tvc_me_table_bytes": (C.c_size_t, [vp, ci]),
     "tvc_me_tables_dev": (ci, [vp, C.POINTER(vp), C.POINTER(vp)]),
     "tvc_me_table_lookup": (ci, [vp, ci, ci, ci, ci, ci, ci, ci, vp, vp]),

@@ -187,6 +187,7 @@ int tvc_ctx_create(const tvc_config* cfg, tvc_ctx** out)
       if (c->encode_tiled) {
         int rows = p.h[0] + 2 * p.my[0];
         if (make_tmap_u8(c, &p.tmap_cur, p.buf8, p.stride8, rows, p.stride8, 64, 64) == TVC_OK &&
+            make_tmap_u8(c, &p.tmap_cur80, p.buf8, p.stride8, rows, p.stride8, 80, 64) == TVC_OK &&
             make_tmap_u8(c, &p.tmap_ref, p.buf8, p.stride8, rows, p.stride8, 208, 192) == TVC_OK)
           p.has_tmap = true;
       }
@@ -232,6 +233,10 @@ void tvc_ctx_destroy(tvc_ctx* c)
   if (c->fr_frac) cudaFree(c->fr_frac);
   if (c->fr_rast) cudaFree(c->fr_rast);
   if (c->fr_sweep) cudaFree(c->fr_sweep);
+  if (c->grp_sidx) cudaFree(c->grp_sidx);
+  if (c->grp_census) cudaFree(c->grp_census);
+  if (c->grp_fb_list) cudaFree(c->grp_fb_list);
+  if (c->grp_fb_count) cudaFree(c->grp_fb_count);
   if (c->fr_stats) cudaFree(c->fr_stats);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;

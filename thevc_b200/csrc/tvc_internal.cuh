@@ -30,6 +30,7 @@ struct Pic {
   uint8_t* org8 = nullptr;
   int stride8 = 0;
   CUtensorMap tmap_cur;                            // u8 luma, box 64x64
+  CUtensorMap tmap_cur80;                          // u8 luma, box 80x64 (the group search stages the CTU at pitch 80)
   CUtensorMap tmap_ref;                            // u8 luma, box 208x192 (192 + 16 alignment slack)
   bool has_tmap = false;
 };
@@ -79,6 +80,13 @@ struct tvc_ctx {
   void* fr_sweep = nullptr;       // shared first-sweep results (SweepState per job)
   unsigned long long* fr_stats = nullptr;   // device: 3 work counters (tvc_me_frame_stats)
   size_t fr_cap = 0;              // entries
+  // group search (tvc_me_group.cu): sweep-offset table, census, list of the PUs handed back to the per-PU kernel
+  int me_fused = -1;              // -1: TVC_ME_FUSED (default on), 0 / 1: set by tvc_me_set_fused
+  void* grp_sidx = nullptr;
+  void* grp_census = nullptr;
+  int* grp_fb_list = nullptr;
+  int* grp_fb_count = nullptr;
+  size_t grp_fb_cap = 0;
   // dedicated pinned staging of the asynchronous ME entry points (an event guards host reuse)
   tvc::Scratch me_stage, fr_stage;
   cudaEvent_t me_ev = nullptr, fr_ev = nullptr;
@@ -161,6 +169,16 @@ inline bool tu_record_ok(const Pic& p, const tvc_tu& t, size_t coef_elems)
 // dequant (optional) + inverse transform of a device TU list, one launch per size; recon = Clip(pred + resi) when pred_slot >= 0
 int launch_inv(tvc_ctx* c, int resi_slot, int pred_slot, int recon_slot, const int counts[4], const tvc_tu* tus_dev,
                const int32_t* levels_dev, int dequant);                                                          // tvc_tq.cu
+
+}  // namespace tvc
+// group search over census groups ([group][593] jobs) and the per-PU kernel over a device-resident job list (tvc_me_group.cu / tvc_me.cu)
+int tvc_launch_me_group(tvc_ctx* c, int cur_slot, int ngroups, const tvc_me_job* jobs_dev, tvc_me_result* out_dev, int num_refs,
+                        const int* ref_slots, int ref_index_fixed, unsigned long long* stats);
+int tvc_launch_me_search_list(tvc_ctx* c, int cur_slot, const int* list_dev, const int* count_dev, const tvc_me_job* jobs_dev,
+                              tvc_me_result* out_dev);
+namespace tvc {
+// true unless TVC_ME_FUSED=0: the census entry points (tvc_me_frame, tvc_me_ctu) search with the group kernel instead of SAD tables
+bool me_fused_enabled(const tvc_ctx* c);
 
 // ---- table layout of the ME pre-pass (shared by producer and consumers) ----------------------
 // T[ref][ctu][cand 129*129][by 16][q 4][par 2][bx 4] uint16: one candidate = 1 KB contiguous

@@ -15,6 +15,7 @@
 //      interpolation around the integer MV and 9+9 Hadamard SATD evaluations, one CTA per job,
 //      14-bit intermediates in shared memory, Hadamard butterflies in registers + warp shuffles.
 #include "tvc_internal.cuh"
+#include "tvc_me.cuh"
 #include "tvc_interp.cuh"
 #include <stdlib.h>
 
@@ -27,49 +28,6 @@ constexpr int kWinW = 208, kWinH = 192;
 constexpr int kSmemWin = kWinW * kWinH;          // 36864
 constexpr int kSmemCur = 64 * 64;                // 4096
 constexpr int kSmemTables = kSmemWin + kSmemCur + 64;
-
-struct MeMaps {
-  CUtensorMap cur;
-  CUtensorMap ref[8];
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
-{
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar)
-{
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
-      : "memory");
-}
-
-__device__ __forceinline__ uint32_t vsad4_acc(uint32_t a, uint32_t b, uint32_t c)
-{
-  uint32_t d;
-  asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-}
 
 // one warp task.  Lane parameters: X = byte offset of the lane's 16-byte cur quarter inside a window
 // row for its dx (X = dx+64 + 16q, X & 15 == align16 for all lanes), dyb = first dy (0-based, i.e.
@@ -308,19 +266,6 @@ __constant__ tvc_census_pu c_census[TVC_ME_CENSUS];     // partition census of a
 // independent 16-byte loads in flight) and the sequential update is replayed afterwards as an
 // ordered arg-min per round: the first candidate in visiting order that attains the round minimum
 // wins iff it is strictly below the best so far -- exactly the state the sequential loop ends in.
-__device__ __forceinline__ uint32_t mv_comp_bits(int v)
-{
-  // xGetComponentBits (TComRdCost.cpp:270-284): 2*floor(log2(t)) + 1 with t = v<=0 ? -2v+1 : 2v
-  uint32_t t = (v <= 0) ? (uint32_t)((-v << 1) + 1) : (uint32_t)(v << 1);
-  return 2u * (31u - (uint32_t)__clz(t)) + 1u;
-}
-__device__ __forceinline__ uint32_t mv_cost(uint32_t lc, int x, int y, int scale, int px, int py)
-{
-  uint32_t bits = mv_comp_bits((x << scale) - px) + mv_comp_bits((y << scale) - py);
-  return (lc * bits) >> 16;
-}
-
-constexpr uint32_t kNoCost = 0xFFFFFFFFu;
 #ifndef TVC_SEARCH_ROW_UNROLL
 #define TVC_SEARCH_ROW_UNROLL 1
 #endif
@@ -432,71 +377,6 @@ __device__ __forceinline__ void eval_multi(const SearchCtx& s, const bool (&vali
 #pragma unroll
   for (int k = 0; k < K; k++)
     cost[k] = valid[k] ? ((sad[k] << s.sub) >> s.bi) + mv_cost(s.lc, x[k], y[k], 2, s.px, s.py) : kNoCost;
-}
-
-__device__ __forceinline__ int round_size(int d) { return d == 1 ? 4 : (d <= 8 ? 8 : 16); }
-
-// i-th candidate (visiting order) of xTZ8PointDiamondSearch (TEncSearch.cpp:535-707) around (sx,sy) at
-// distance d, with the reference's own border tests: an axis point (top / left / right / bottom at
-// distance d) is tested against the one edge it can cross, an off-axis point is taken when the four
-// axis points are inside ("check border") or else when it passes the vertical and the horizontal edge
-// on its own side.  The centre CAN be outside the window (the zero vector is probed unconditionally,
-// :4336-4339), so these are not the same as "point in window" and are restated as written.
-// Branch-free: every lane of a batch holds a different i.
-//   d == 1 : 4 points  top(2) left(4) right(5) bottom(7)
-//   d <= 8 : 8 points  top(2) TL(1) TR(3) left(4) right(5) BL(6) BR(8) bottom(7); diagonals at d/2, tagged d/2
-//   d  > 8 : 16 points top left right bottom, then k = 1..3: (xl,yt) (xr,yt) (xl,yb) (xr,yb), all tagged 0 / d
-__device__ __forceinline__ bool diamond_cand(const SearchCtx& s, int sx, int sy, int d, int i, int& x, int& y, int& pt,
-                                             uint32_t& dist)
-{
-  int ux, uy, unit, ptn;          // offset = (ux, uy) * unit
-  bool axis;
-  if (d == 1) {
-    // i: 0 top, 1 left, 2 right, 3 bottom
-    ux = (i == 1) ? -1 : (i == 2 ? 1 : 0);
-    uy = (i == 0) ? -1 : (i == 3 ? 1 : 0);
-    unit = 1; axis = true;
-    ptn = (0x7542 >> (4 * i)) & 15;
-    dist = 1;
-  } else if (d <= 8) {
-    // nibble tables indexed by i (LSB first): ux+2, uy+2 in half-distance units, point number
-    ux = (int)((0x23140312u >> (4 * i)) & 15) - 2;     // 0,-1,+1,-2,+2,-1,+1,0
-    uy = (int)((0x43322110u >> (4 * i)) & 15) - 2;     // -2,-1,-1,0,0,+1,+1,+2
-    ptn = (int)((0x78654312u >> (4 * i)) & 15);        // 2,1,3,4,5,6,8,7
-    unit = d >> 1;
-    axis = (ux == 0) || (uy == 0);
-    dist = axis ? (uint32_t)d : (uint32_t)(d >> 1);
-  } else {
-    unit = d >> 2;
-    if (i < 4) {
-      ux = (i == 1) ? -4 : (i == 2 ? 4 : 0);
-      uy = (i == 0) ? -4 : (i == 3 ? 4 : 0);
-      axis = true;
-    } else {
-      const int k = ((i - 4) >> 2) + 1, j = (i - 4) & 3;
-      ux = (j & 1) ? k : -k;
-      uy = (j & 2) ? 4 - k : k - 4;
-      axis = false;
-    }
-    ptn = 0; dist = (uint32_t)d;
-  }
-  x = sx + ux * unit; y = sy + uy * unit; pt = ptn;
-  const bool yc = uy < 0 ? (y >= s.ty) : (y <= s.by);
-  const bool xc = ux < 0 ? (x >= s.lx) : (x <= s.rx);
-  const bool inside = (sy - d) >= s.ty && (sy + d) <= s.by && (sx - d) >= s.lx && (sx + d) <= s.rx;
-  return axis ? (ux == 0 ? yc : xc) : (inside || (yc && xc));
-}
-
-// candidate c (visiting order) of a sweep that starts at distance 1 -> (round distance d, index i inside the round): the rounds hold
-// 4, 8, 8, 8, 16, 16, 16 candidates (d = 1 .. 64), i.e. start at 0, 4, 12, 20, 28, 44, 60.  Closed form instead of walking the
-// rounds: the walk was 20 % of k_me_search's instructions in the ncu source view.
-__device__ __forceinline__ bool sweep_slot(int c, int dmax, int& d, int& i)
-{
-  if (c < 4) { d = 1; i = c; }
-  else if (c < 28) { d = 2 << ((c - 4) >> 3); i = (c - 4) & 7; }
-  else if (c < 76) { d = 16 << ((c - 28) >> 4); i = (c - 28) & 15; }
-  else { d = 128; i = 0; return false; }
-  return d <= dmax;
 }
 
 // Diamond rounds d = 1, 2, 4, ... <= dmax around (sx,sy) (d0 must be 1: every TZ sweep starts there).  All candidates of these rounds are known
@@ -850,14 +730,13 @@ k_me_raster(const tvc_me_job* __restrict__ jobs, const uint16_t* __restrict__ ta
   if (tid == 0 && stats) atomicAdd(&stats[2], (unsigned long long)N);
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB)
-k_me_search(PlaneTable pt, int cur_slot, int n, const tvc_me_job* __restrict__ jobs, tvc_me_result* __restrict__ out,
-            const uint16_t* __restrict__ tables, const tvc_me_center* __restrict__ centers, int num_ctus, int ctus_x,
-            int bi, const RasterBest* __restrict__ rast, const SweepState* __restrict__ sweep, unsigned long long* __restrict__ stats)
+// one PU job by one warp (warp-collective: all 32 lanes call it with the same j)
+__device__ __forceinline__ void me_search_job(int j, const PlaneTable& pt, int cur_slot, const tvc_me_job* __restrict__ jobs,
+                                              tvc_me_result* __restrict__ out, const uint16_t* __restrict__ tables,
+                                              const tvc_me_center* __restrict__ centers, int num_ctus, int ctus_x, int bi,
+                                              const RasterBest* __restrict__ rast, const SweepState* __restrict__ sweep,
+                                              unsigned long long* __restrict__ stats)
 {
-  int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (j >= n) return;
   const tvc_me_job jb = jobs[j];
   if (jb.w <= 0) {                       // census PU outside the picture (frame pre-pass)
     if ((threadIdx.x & 31) == 0) out[j] = tvc_me_result{0, 0, 0u, 0u};
@@ -970,6 +849,28 @@ k_me_search(PlaneTable pt, int cur_slot, int n, const tvc_me_job* __restrict__ j
       atomicAdd(&stats[1], (unsigned long long)served);
     }
   }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_me_search(PlaneTable pt, int cur_slot, int n, const tvc_me_job* __restrict__ jobs, tvc_me_result* __restrict__ out,
+            const uint16_t* __restrict__ tables, const tvc_me_center* __restrict__ centers, int num_ctus, int ctus_x,
+            int bi, const RasterBest* __restrict__ rast, const SweepState* __restrict__ sweep, unsigned long long* __restrict__ stats)
+{
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= n) return;
+  me_search_job(j, pt, cur_slot, jobs, out, tables, centers, num_ctus, ctus_x, bi, rast, sweep, stats);
+}
+
+// the jobs named by a device-resident list (the PUs the group kernel of tvc_me_group.cu handed back: candidates beyond its
+// bitmap, round cap): a fixed grid walks the list, SADs straight from the pictures
+__global__ void __launch_bounds__(128, 4)
+k_me_search_list(PlaneTable pt, int cur_slot, const int* __restrict__ list, const int* __restrict__ count, const tvc_me_job* __restrict__ jobs,
+                 tvc_me_result* __restrict__ out, int ctus_x, int bi)
+{
+  const int n = *count;
+  for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += gridDim.x * (blockDim.x >> 5))
+    me_search_job(list[i], pt, cur_slot, jobs, out, nullptr, nullptr, 0, ctus_x, bi, nullptr, nullptr, nullptr);
 }
 
 __global__ void k_me_table_lookup(const uint16_t* __restrict__ tables, const tvc_me_center* __restrict__ centers,
@@ -1560,6 +1461,27 @@ static int launch_frac(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job* jobs
 
 using namespace tvc;
 
+int tvc_launch_me_search_list(tvc_ctx* c, int cur_slot, const int* list_dev, const int* count_dev, const tvc_me_job* jobs_dev,
+                              tvc_me_result* out_dev)
+{
+  k_me_search_list<<<kNumSM * 4, 128, 0, c->stream>>>(c->planes, cur_slot, list_dev, count_dev, jobs_dev, out_dev, c->num_ctus_x, c->bi);
+  TVC_LAUNCH_CHECK(c);
+  return TVC_OK;
+}
+
+namespace tvc {
+bool me_fused_enabled(const tvc_ctx* c)
+{
+  int on = c->me_fused;
+  if (on < 0) {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("TVC_ME_FUSED"); env = e ? atoi(e) : 1; }
+    on = env;
+  }
+  return on != 0 && c->cfg.bit_depth == 8 && !c->pics.empty() && c->pics[0].has_tmap;
+}
+}  // namespace tvc
+
 extern "C" {
 
 size_t tvc_me_table_bytes(tvc_ctx* c, int num_refs)
@@ -1567,6 +1489,15 @@ size_t tvc_me_table_bytes(tvc_ctx* c, int num_refs)
   if (!c || num_refs <= 0) return 0;
   return (size_t)num_refs * c->num_ctus_x * c->num_ctus_y * kMeCtuElems * sizeof(uint16_t);
 }
+
+int tvc_me_set_fused(tvc_ctx* c, int on)
+{
+  if (!c) return TVC_ERR_ARG;
+  c->me_fused = on < 0 ? -1 : (on ? 1 : 0);
+  return TVC_OK;
+}
+
+int tvc_me_uses_tables(tvc_ctx* c) { return (c && !me_fused_enabled(c) && c->cfg.bit_depth == 8) ? 1 : 0; }
 
 int tvc_me_reserve(tvc_ctx* c, int num_refs)
 {
@@ -1879,9 +1810,14 @@ int tvc_me_frame_dev(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slot
   // co-resident CTA only displaces table work and the chunk tails add up.  Kept as a knob; per-phase profiling needs the serial form.
   static int pipe_chunks = -1;
   if (pipe_chunks < 0) { const char* e = getenv("TVC_ME_PIPE"); pipe_chunks = e ? atoi(e) : 0; if (pipe_chunks > kMaxPipeChunks) pipe_chunks = kMaxPipeChunks; }
-  const bool piped = cfg->use_tables && pipe_chunks > 0 && !c->prof_on;
+  // use_tables selects the fast integer stage.  Default: the group kernel (tvc_me_group.cu: one CTA per (CTU, reference), SADs on
+  // demand from the staged window, nothing written to HBM but the results); TVC_ME_FUSED=0: the round-1 form (full SAD tables
+  // in HBM, shared raster / first-sweep stage, per-PU search reading the tables).  10-bit content has no u8 planes: per-PU search.
+  const bool fused = cfg->use_tables && me_fused_enabled(c);
+  const bool legacy_tables = cfg->use_tables && !fused && c->cfg.bit_depth == 8;
+  const bool piped = legacy_tables && pipe_chunks > 0 && !c->prof_on;
   c->fr_piped_last = piped;
-  if (cfg->use_tables && (r = prepass_prepare(c, cur_slot, num_refs, ref_slots, centers.data()))) return r;
+  if (legacy_tables && (r = prepass_prepare(c, cur_slot, num_refs, ref_slots, centers.data()))) return r;
   TVC_CUDA(c, cudaMemcpyAsync(c->fr_stage.dev, c->fr_stage.host, np * sizeof(tvc_me_center) + num_refs * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   TVC_CUDA(c, cudaEventRecord(c->fr_ev, c->stream));
   const tvc_me_center* dpred = (const tvc_me_center*)c->fr_stage.dev;
@@ -1925,9 +1861,13 @@ int tvc_me_frame_dev(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slot
     }
     return launch_frac(c, cur_slot, (int)cnt, c->fr_fjobs + off, c->fr_frac + off, true);
   };
-  if (!piped) {
-    if (cfg->use_tables && (r = launch_tables(c, 0, nctu, 0, num_refs))) return r;
-    if (cfg->use_tables && use_rast) {
+  if (fused) {
+    if ((r = tvc_launch_me_group(c, cur_slot, num_refs * nctu, c->fr_jobs, c->fr_int, num_refs, ref_slots, -1, c->fr_stats))) return r;
+    if (c->fr_int_ready) TVC_CUDA(c, cudaEventRecord(c->fr_int_ready, c->stream));
+    if (cfg->do_frac && (r = frac_part(0, n))) return r;
+  } else if (!piped) {
+    if (legacy_tables && (r = launch_tables(c, 0, nctu, 0, num_refs))) return r;
+    if (legacy_tables && use_rast) {
       ProfScope ps(c, TVC_PH_ME_RASTER);
       dim3 grd(nctu, num_refs);
       if (use_sweep) {
@@ -1939,8 +1879,8 @@ int tvc_me_frame_dev(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slot
                                                               nullptr, c->fr_stats, 0, 0);
       TVC_LAUNCH_CHECK(c);
     }
-    const bool shared = cfg->use_tables && use_rast;
-    if ((r = launch_search(c, cur_slot, cfg->use_tables, (int)n, c->fr_jobs, c->fr_int, shared ? (const RasterBest*)c->fr_rast : nullptr,
+    const bool shared = legacy_tables && use_rast;
+    if ((r = launch_search(c, cur_slot, legacy_tables ? 1 : 0, (int)n, c->fr_jobs, c->fr_int, shared ? (const RasterBest*)c->fr_rast : nullptr,
                            shared && use_sweep ? (const SweepState*)c->fr_sweep : nullptr, c->fr_stats))) return r;
     if (c->fr_int_ready) TVC_CUDA(c, cudaEventRecord(c->fr_int_ready, c->stream));      // tvc_me_frame copies the integer results from here
     if (cfg->do_frac && (r = frac_part(0, n))) return r;
@@ -2024,8 +1964,9 @@ int tvc_me_ctu(tvc_ctx* c, int cur_slot, int ref_index, int ref_slot, int ctu, t
   if (!c || !valid_slot(c, cur_slot) || !valid_slot(c, ref_slot) || !cfg || cfg->search_range < 1 || cfg->search_range > TVC_ME_RANGE ||
       ctu < 0 || ctu >= c->num_ctus_x * c->num_ctus_y || !int_out || (cfg->do_frac && !frac_out))
     return set_err(c, TVC_ERR_ARG, "tvc_me_ctu: bad argument");
-  if (cfg->use_tables && (!c->me_tables || c->me_cur_slot != cur_slot || ref_index < 0 || ref_index >= c->me_num_refs ||
-                          c->me_ref_slots[ref_index] != ref_slot))
+  const bool fused = cfg->use_tables && me_fused_enabled(c);
+  if (cfg->use_tables && !fused && (!c->me_tables || c->me_cur_slot != cur_slot || ref_index < 0 || ref_index >= c->me_num_refs ||
+                                    c->me_ref_slots[ref_index] != ref_slot))
     return set_err(c, TVC_ERR_STATE, "tvc_me_ctu: tables requested but tvc_me_prepass has not run for this picture / reference");
   int r;
   if ((r = ensure_census(c))) return r;
@@ -2044,7 +1985,9 @@ int tvc_me_ctu(tvc_ctx* c, int cur_slot, int ref_index, int ref_slot, int ctu, t
   TVC_LAUNCH_CHECK(c);
   // no shared raster stage here: one block would walk the 729 raster candidates alone; the PUs that need the
   // raster walk it themselves, in parallel
-  if ((r = launch_search(c, cur_slot, cfg->use_tables, (int)N, d_jobs, d_int, nullptr, nullptr, nullptr))) return r;
+  if (fused) {
+    if ((r = tvc_launch_me_group(c, cur_slot, 1, d_jobs, d_int, 1, &ref_slot, 0, nullptr))) return r;
+  } else if ((r = launch_search(c, cur_slot, cfg->use_tables, (int)N, d_jobs, d_int, nullptr, nullptr, nullptr))) return r;
   if (cfg->do_frac) {
     k_me_frame_frac_jobs<<<(int)((N + 127) / 128), 128, 0, c->stream>>>((int)N, d_jobs, d_int, cfg->hadamard, d_fjobs);
     TVC_LAUNCH_CHECK(c);

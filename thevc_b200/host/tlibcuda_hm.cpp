@@ -149,12 +149,13 @@ struct State {
   struct Grid { uint32_t w[TVC_GRID_WORDS]; };
   std::unordered_map<unsigned long long, Grid> grids;      // (CTU, reference slot, clipped MV) -> prefix-sum grids; cleared per picture
   unsigned long long n_grid_hits = 0, n_grid_fills = 0;
-  unsigned long long n_merge = 0, n_merge_cands = 0, n_template = 0;
+  unsigned long long n_merge = 0, n_merge_cands = 0, n_template = 0, n_merge_host = 0;
   double cand_seconds = 0.0;
   int w = 0, ht = 0;
   std::vector<DevPic> slots;
   unsigned long long clock = 0;
   int cur_slot = -1;
+  bool tables_live = false;                // SAD tables of the current picture exist in HBM (TVC_ME_FUSED=0 only)
   int table_refs[8];
   int num_table_refs = 0;
   unsigned long long n_tz = 0, n_frac = 0, n_xt = 0, n_xit = 0, n_dq = 0, n_mc = 0, n_rdoq = 0;
@@ -193,8 +194,8 @@ void report()
   if (s.on_hash)
     fprintf(stderr, "TLibCuda picture hash: %llu pictures hashed on the device\n", s.n_hash);
   if (s.on_cand_grid)
-    fprintf(stderr, "TLibCuda candidate look-up: %llu of %llu candidate costs served from %llu CTU-wide (CTU, reference, MV) cost grids\n",
-            s.n_grid_hits, s.n_grid_hits + s.n_grid_fills, s.n_grid_fills);
+    fprintf(stderr, "TLibCuda candidate look-up: %llu of %llu candidate costs served from %llu CTU-wide (CTU, reference, MV) cost grids; %llu bi-predicted merge sets left to the reference's code\n",
+            s.n_grid_hits, s.n_grid_hits + s.n_grid_fills, s.n_grid_fills, s.n_merge_host);
   if (s.on_cand)
     fprintf(stderr, "TLibCuda candidate evaluation: %llu xMergeEstimation calls (%llu candidates) and %llu xGetTemplateCost calls on the device, %.3f s in tvc_pred_cost_batch\n",
             s.n_merge, s.n_merge_cands, s.n_template, s.cand_seconds);
@@ -430,7 +431,9 @@ void tlibcuda_picture_start(TComPic* pic, TComSlice* slice)
       s.census_index[(unsigned)cen[k].x | ((unsigned)cen[k].y << 6) | ((unsigned)cen[k].w << 12) | ((unsigned)cen[k].h << 19)] = k;
   }
   const int nctu = ((org->getWidth() + 63) / 64) * ((org->getHeight() + 63) / 64);
+  s.tables_live = false;
   if (s.on_tables && s.num_table_refs > 0 && g_uiBitIncrement == 0) {
+    const bool hbm_tables = tvc_me_uses_tables(s.h) != 0;       // TVC_ME_FUSED=0: the round-1 form with SAD tables in HBM
     // table centres: the predictor each (reference index, CTU) group started with in the previous picture (steady
     // motion keeps it), clipped like a CTU-level clipMv; zero for the first inter picture
     if ((int)s.center_guess.size() != 8 * nctu) s.center_guess.assign((size_t)8 * nctu, tvc_me_center{0, 0});
@@ -449,7 +452,7 @@ void tlibcuda_picture_start(TComPic* pic, TComSlice* slice)
     // a GOP ramps up to 4 references: one allocation instead of four growing ones (0.2-0.6 s each at 1080p); if the
     // device cannot hold four (34.8 GB at 1080p) the tables grow on demand as before
     static bool reserved = false;
-    if (!reserved) { reserved = true; if (tvc_me_reserve(s.h, s.num_table_refs > 4 ? s.num_table_refs : 4) != TVC_OK) (void)0; }
+    if (hbm_tables && !reserved) { reserved = true; if (tvc_me_reserve(s.h, s.num_table_refs > 4 ? s.num_table_refs : 4) != TVC_OK) (void)0; }
     s.frame_valid = false;
     if (s.on_frame && s.on_lookup && s.on_frac && s.last_sr > 0 && !s.wp && slice->getLambdaLuma() > 0.0) {
       // the whole census of the whole picture in one call: SAD tables around the guesses, TZ + fractional search of every PU with the
@@ -466,8 +469,11 @@ void tlibcuda_picture_start(TComPic* pic, TComSlice* slice)
       CK(tvc_me_frame(s.h, s.cur_slot, s.num_table_refs, s.table_refs, s.frame_pred.data(), &fc, s.frame_int.data(), s.frame_frac.data()));
       s.frame_valid = true; s.frame_lambda = lc; s.frame_sr = s.last_sr; s.frame_fen = s.last_fen; s.frame_had = s.last_had;
       s.frame_refs = s.num_table_refs; s.frame_nctu = nctu;
-    } else
+      s.tables_live = hbm_tables;
+    } else if (hbm_tables) {
       CK(tvc_me_prepass(s.h, s.cur_slot, s.num_table_refs, s.table_refs, cen.data()));
+      s.tables_live = true;
+    }
   } else {
     s.num_table_refs = 0;
     s.frame_valid = false;
@@ -567,7 +573,7 @@ bool tlibcuda_tz_search(TComDataCU* cu, TComPattern* key, short* refY, int refSt
         const tvc_me_result& r = hit->ires[it->second];
         if (s.verify) {
           tvc_me_result r2;
-          CK(tvc_me_search_batch(s.h, s.cur_slot, j.ref_index >= 0 ? 1 : 0, 1, &j, &r2));
+          CK(tvc_me_search_batch(s.h, s.cur_slot, (s.tables_live && j.ref_index >= 0) ? 1 : 0, 1, &j, &r2));
           if (r2.mvx != r.mvx || r2.mvy != r.mvy || r2.sad != r.sad) {
             fprintf(stderr, "TLibCuda verify: look-up (%d,%d,%u) != single search (%d,%d,%u) for PU %dx%d at (%d,%d)\n", r.mvx, r.mvy, r.sad,
                     r2.mvx, r2.mvy, r2.sad, j.w, j.h, x, y);
@@ -585,7 +591,7 @@ bool tlibcuda_tz_search(TComDataCU* cu, TComPattern* key, short* refY, int refSt
     }
   }
   tvc_me_result r;
-  CK(tvc_me_search_batch(s.h, s.cur_slot, j.ref_index >= 0 ? 1 : 0, 1, &j, &r));
+  CK(tvc_me_search_batch(s.h, s.cur_slot, (s.tables_live && j.ref_index >= 0) ? 1 : 0, 1, &j, &r));
   rcMv.set(r.mvx, r.mvy);
   ruiSAD = r.sad;
   return true;
@@ -787,6 +793,11 @@ bool tlibcuda_merge_costs(TComDataCU* cu, int puIdx, TComMvField* cands, const u
     }
     return true;
   }
+  // bi-predicted candidate sets (B slices) have no look-up form: the average of two predictions is not a sum of per-list block
+  // costs.  In look-up mode they stay with the reference's own xGetInterPredictionError (a per-call device evaluation costs a
+  // launch + synchronise per xMergeEstimation: measured at 1080p random access, 267 s of a 527 s encode); `cand` alone keeps
+  // every candidate set on the device (parity configuration of the tests).
+  if (s.on_cand_grid) { s.n_merge--; s.n_merge_cands -= (unsigned long long)numCand; s.n_merge_host++; return false; }
   const auto t0 = std::chrono::steady_clock::now();
   CK(tvc_pred_cost_batch(s.h, s.cur_slot, hadamard ? TVC_DIST_HADS : TVC_DIST_SAD, numCand, pus, dist));
   s.cand_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
