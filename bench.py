@@ -449,32 +449,44 @@ def workload_config():
 
 
 # --------------------------------------------------------------------------------------- whole-encoder leg
+ENC_REF = os.path.join(ROOT, "oracle", "_ref", "bin", "TAppEncoderStatic")
+ENC_CUDA = os.path.join(ROOT, "build", "hm", "TAppEncoderCuda")
+LDP_CFG = os.path.join(ROOT, "build", "hm", "cfg", "encoder_lowdelay_P_main.cfg")
+HM_HOOKS = "me,frac,tables,frame,candgrid"
+
+
+def _write_yuv(path, frames, seed):
+    import synth
+    seq = synth.make_sequence(W, H, frames, seed=seed)
+    with open(path, "wb") as f:
+        for y, u, v in seq:
+            f.write(y.astype(np.uint8).tobytes()); f.write(u.astype(np.uint8).tobytes()); f.write(v.astype(np.uint8).tobytes())
+
+
+def _enc_args(yuv, frames, out):
+    return ["-c", LDP_CFG, "-i", yuv, "-wdt", str(W), "-hgt", str(H), "-fr", "30", "-f", str(frames), "--SEIpictureDigest=1", "-o", os.devnull, "-b", out]
+
+
 def run_hm_encode(frames, device_index=0):
     """BASELINE.json metric (i): end-to-end 1080p low-delay-P encode.  The unmodified reference encoder
     (oracle/_ref/bin/TAppEncoderStatic) and the reference encoder with the TLibCuda hooks (build/hm/TAppEncoderCuda:
-    integer + fractional ME of the CU loop served by look-up from census-wide tvc_me_ctu batches on the GPU; CABAC, RDO,
-    transforms stay the host's own code) encode the same synthetic 1920x1080 sequence, concurrently, one process each.
-    fps = frames / wall time of the whole process (start-up, I picture and file I/O included); bitstream md5 compared."""
+    integer + fractional ME of the CU loop served by look-up from census-wide device batches, merge / AMVP candidate costs from
+    device cost grids; CABAC, RDO, transforms stay the host's own code) encode the same synthetic 1920x1080 sequence, concurrently,
+    one process each.  >= 17 pictures: four references are active from POC 4 on and the encoder recycles its picture buffers.
+    fps = frames / wall time of the whole process (start-up, I picture and file I/O included); bitstream md5 compared with each
+    other and, for the 17-picture default, with the committed md5 of the reference's single run (tests/golden/hm_md5.json)."""
     import hashlib
     import tempfile
-    import synth
-    enc_ref = os.path.join(ROOT, "oracle", "_ref", "bin", "TAppEncoderStatic")
-    enc_cuda = os.path.join(ROOT, "build", "hm", "TAppEncoderCuda")
-    cfg = os.path.join(ROOT, "build", "hm", "cfg", "encoder_lowdelay_P_main.cfg")
-    for pth in (enc_ref, enc_cuda, cfg):
+    for pth in (ENC_REF, ENC_CUDA, LDP_CFG):
         if not os.path.exists(pth):
             return {"unavailable": "%s not built (needs /root/reference at build time)" % os.path.relpath(pth, ROOT)}
     with tempfile.TemporaryDirectory() as d:
         yuv = os.path.join(d, "in.yuv")
-        seq = synth.make_sequence(W, H, frames, seed=20261018)
-        with open(yuv, "wb") as f:
-            for y, u, v in seq:
-                f.write(y.astype(np.uint8).tobytes()); f.write(u.astype(np.uint8).tobytes()); f.write(v.astype(np.uint8).tobytes())
-        base = ["-c", cfg, "-i", yuv, "-wdt", str(W), "-hgt", str(H), "-fr", "30", "-f", str(frames), "--SEIpictureDigest=1", "-o", os.devnull]
-        env = dict(os.environ, TVC_HM="me,frac,tables,frame,candgrid", CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(device_index)))
+        _write_yuv(yuv, frames, 20261018)
+        env = dict(os.environ, TVC_HM=HM_HOOKS, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(device_index)))
         t0 = time.perf_counter()
-        pr = subprocess.Popen([enc_ref] + base + ["-b", os.path.join(d, "ref.bin")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        pc = subprocess.Popen([enc_cuda] + base + ["-b", os.path.join(d, "cuda.bin")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+        pr = subprocess.Popen([ENC_REF] + _enc_args(yuv, frames, os.path.join(d, "ref.bin")), stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        pc = subprocess.Popen([ENC_CUDA] + _enc_args(yuv, frames, os.path.join(d, "cuda.bin")), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
         done = {}
 
         def wait(name, p):
@@ -494,12 +506,69 @@ def run_hm_encode(frames, device_index=0):
         def ets(out):
             return [int(ln.split("[ET")[1].split("]")[0]) for ln in out.splitlines() if ln.startswith("POC") and "[ET" in ln]
         m_ref, m_cuda = md5(os.path.join(d, "ref.bin")), md5(os.path.join(d, "cuda.bin"))
+        golden = None
+        try:
+            g = json.load(open(os.path.join(ROOT, "tests", "golden", "hm_md5.json"))).get("ldp_1080_%d" % frames)
+            golden = g["md5"] if g else None
+        except Exception:
+            pass
         served = [ln for ln in done["cuda"][3].splitlines() if ln.startswith("TLibCuda")]
-        return {"frames": frames, "config": "cfg/encoder_lowdelay_P_main.cfg 1920x1080 synthetic, 1 I + %d P pictures, one process per encoder" % (frames - 1),
-                "reference_fps": frames / done["ref"][0], "ours_fps": frames / done["cuda"][0],
-                "reference_wall_s": done["ref"][0], "ours_wall_s": done["cuda"][0],
-                "reference_picture_seconds": ets(done["ref"][2]), "ours_picture_seconds": ets(done["cuda"][2]),
-                "bitstream_md5_equal": m_ref == m_cuda, "bitstream_md5": m_cuda, "hooks": served}
+        out = {"frames": frames, "config": "cfg/encoder_lowdelay_P_main.cfg 1920x1080 synthetic, 1 I + %d P pictures, one process per encoder, "
+                                           "TVC_HM=%s" % (frames - 1, HM_HOOKS),
+               "reference_fps": frames / done["ref"][0], "ours_fps": frames / done["cuda"][0], "speedup": done["ref"][0] / done["cuda"][0],
+               "reference_wall_s": done["ref"][0], "ours_wall_s": done["cuda"][0],
+               "reference_picture_seconds": ets(done["ref"][2]), "ours_picture_seconds": ets(done["cuda"][2]),
+               "bitstream_md5_equal": m_ref == m_cuda, "bitstream_md5": m_cuda, "golden_md5": golden,
+               "golden_md5_equal": (m_cuda == golden) if golden else None, "hooks": served}
+        if m_ref != m_cuda or (golden and m_cuda != golden):
+            out["error"] = "bitstream md5 differs: ours %s reference %s golden %s" % (m_cuda, m_ref, golden)
+        return out
+
+
+def _pinned_encoder(args):
+    """worker of run_cpu_encoder_baseline: own sequence, then one unmodified reference encoder pinned to one core"""
+    core, frames, seed, workdir, start_at = args
+    yuv, out = os.path.join(workdir, "in_%d.yuv" % core), os.path.join(workdir, "ref_%d.bin" % core)
+    _write_yuv(yuv, frames, seed)
+    while time.time() < start_at:          # all encoders start together, after every sequence is on disk
+        time.sleep(0.01)
+    t0 = time.perf_counter()
+    cmd = [ENC_REF] + _enc_args(yuv, frames, out)
+    try:
+        os.sched_setaffinity(0, {core})
+    except (AttributeError, OSError):
+        pass
+    r = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    dt = time.perf_counter() - t0
+    os.remove(yuv)
+    return core, r.returncode, dt
+
+
+def run_cpu_encoder_baseline(frames):
+    """BASELINE.md 3.4 / north star: the reference encoder on the GPU box's own host cores, one process pinned per core, each on an
+    independent synthetic sequence of the same configuration; aggregate and per-core fps with the core count.  A reported
+    baseline, bounded to `frames` pictures per process so that the default bench stays within minutes."""
+    import multiprocessing as mp
+    import tempfile
+    if not os.path.exists(ENC_REF) or not os.path.exists(LDP_CFG):
+        return {"unavailable": "oracle/_ref/bin/TAppEncoderStatic not built (needs /root/reference at build time)"}
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = list(range(os.cpu_count() or 1))
+    with tempfile.TemporaryDirectory() as d:
+        start_at = time.time() + 6.0 + 0.4 * frames
+        with mp.get_context("fork").Pool(len(cores)) as pool:
+            res = pool.map(_pinned_encoder, [(c, frames, 20261018 + 104729 * (i + 1), d, start_at) for i, c in enumerate(cores)], chunksize=1)
+    bad = [r for r in res if r[1] != 0]
+    if bad:
+        return {"error": "reference encoder failed on cores %s" % [r[0] for r in bad]}
+    walls = [r[2] for r in res]
+    return {"cores": len(cores), "frames_per_process": frames, "kind": "reference",
+            "config": "cfg/encoder_lowdelay_P_main.cfg 1920x1080 synthetic, 1 I + %d P pictures per process, one unmodified reference encoder pinned per "
+                      "host core, independent sequences" % (frames - 1),
+            "aggregate_fps": len(cores) * frames / max(walls), "per_core_fps": frames / (sum(walls) / len(walls)),
+            "wall_s_max": max(walls), "wall_s_mean": sum(walls) / len(walls)}
 
 
 # --------------------------------------------------------------------------------------- N > 1 host logic
@@ -890,11 +959,26 @@ def gpu_arm(args):
     # of SAD tables fit beside nothing else
     t.close()
     t = None
+    failed = None
     if world == 1 and args.hm_frames > 0:
         try:
             sub["hm_encode"] = run_hm_encode(args.hm_frames, local)
-        except Exception as ex:      # the leg must never take the hot-path line down with it
+        except Exception as ex:
             sub["hm_encode"] = {"error": repr(ex)[:300]}
+        if "error" in sub["hm_encode"]:
+            failed = "hm_encode: " + sub["hm_encode"]["error"]
+        if not args.no_cpu and args.cpu_enc_frames > 0:
+            try:
+                sub["cpu_baseline_encoder"] = run_cpu_encoder_baseline(args.cpu_enc_frames)
+            except Exception as ex:
+                sub["cpu_baseline_encoder"] = {"error": repr(ex)[:300]}
+            h, c = sub["hm_encode"], sub["cpu_baseline_encoder"]
+            if "ours_fps" in h and "aggregate_fps" in c:
+                # metric (i) side by side: one hooked encoder process on 1 GPU + 1 host core, the reference on 1 core, the reference on every core
+                sub["encode_fps"] = {"ours_1gpu_1process": h["ours_fps"], "reference_1core": h["reference_fps"],
+                                     "reference_all_cores_aggregate": c["aggregate_fps"], "reference_per_core_under_full_load": c["per_core_fps"],
+                                     "host_cores": c["cores"], "note": "ours / reference_1core over %d pictures; the all-core baseline runs %d pictures per "
+                                     "process" % (h["frames"], c["frames_per_process"])}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -903,6 +987,10 @@ def gpu_arm(args):
                     "ms_per_step": ms_e2e, "steps": k_e2e},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "detail": sub}
     print(json.dumps(line))
+    if failed:           # the line above is complete, but a broken encoder leg (exit code, md5 mismatch) fails the bench
+        sys.stdout.flush()
+        print("bench.py: " + failed, file=sys.stderr)
+        sys.exit(3)
 
 
 def main():
@@ -914,7 +1002,8 @@ def main():
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--cpu-ctus", type=int, default=48, help="CTUs of the CPU-baseline sample (1 core)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--hm-frames", type=int, default=5, help="pictures of the whole-encoder 1080p leg (0 = skip)")
+    ap.add_argument("--hm-frames", type=int, default=17, help="pictures of the whole-encoder 1080p leg (0 = skip)")
+    ap.add_argument("--cpu-enc-frames", type=int, default=5, help="pictures per process of the all-cores reference-encoder baseline (0 = skip)")
     ap.add_argument("--ref-ctus-per-core", type=int, default=4, help="--impl reference: CTUs per core and step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

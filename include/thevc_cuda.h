@@ -268,6 +268,14 @@ typedef struct {
 int tvc_me_frac_batch(tvc_ctx* ctx, int cur_slot, int n, const tvc_frac_job* jobs, tvc_frac_result* out);
 int tvc_me_frac_batch_dev(tvc_ctx* ctx, int cur_slot, int n, const tvc_frac_job* jobs_dev, tvc_frac_result* out_dev);
 
+/* Bi-prediction refinement of one PU: TEncSearch::xMotionEstimation with bBi (TEncSearch.cpp:4120-4207).  The search target is
+ * not the picture but the block 2 * org - pred(other list) the host built (TComYuv::removeHighFreq, TComYuv.cpp:583-633; values
+ * -255 .. 510 for 8-bit content): it is copied into `target_slot` at the PU's position, then xPatternSearch (exhaustive raster of
+ * the +-bipredSearchRange window, :4227-4283; job->mode must be TVC_ME_FULL) and xPatternSearchFracDIF (:4476-4514) run against
+ * job->ref_slot in ONE call (one copy up, three kernels, one copy back).  Synchronous.                                          */
+int tvc_me_bipred(tvc_ctx* ctx, int target_slot, const int16_t* target, int target_stride, const tvc_me_job* job, int hadamard,
+                  tvc_me_result* int_out, tvc_frac_result* frac_out);
+
 /* ---------------------------------------------------------------------------------- frame-level ME pre-pass
  * The TEncCu frame pre-pass named by the north star: for one picture and up to 8 references it
  * runs tvc_me_prepass (SAD tables), then -- for EVERY PU of the HM partition census of every CTU

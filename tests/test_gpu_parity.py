@@ -454,6 +454,40 @@ def test_me_search_full_bipred_window(ctx8, orc):
             assert (g.mvx, g.mvy, g.sad, g.n_sads) == (e.mvx, e.mvy, e.sad, e.n_sads)
 
 
+@pytest.mark.parametrize("bd", [8, 10])
+def test_me_bipred_refinement(ctx8, ctx10, orc, bd):
+    """tvc_me_bipred = xMotionEstimation's bBi branch: the pattern is the host's block 2 * org - pred(other list) (values beyond the
+    pel range), xPatternSearch over the +-4 window around the list's current vector, then xPatternSearchFracDIF -- one device call"""
+    t = ctx8 if bd == 8 else ctx10
+    rng = np.random.default_rng(90 + bd)
+    ref = _pic(rng, bd)
+    t.upload(1, ref)
+    maxv = (1 << bd) - 1
+    lc = orc.orc_lambda_motion_sad(47.0)
+    n = 0
+    for (w, h) in PU_SHAPES[::2] + [(64, 64), (8, 4)]:
+        x, y = int(rng.integers(0, (W - w) // 4 + 1)) * 4, int(rng.integers(0, (H - h) // 4 + 1)) * 4
+        cx, cy = int(rng.integers(-20, 21)), int(rng.integers(-20, 21))
+        # 2 * org - pred: anywhere in [-maxv, 2 * maxv]; make it resemble the reference block near (cx, cy) so that the search has a minimum
+        tgt = np.zeros((h, w), np.int16)
+        for r in range(h):
+            o = ref.origin(0) + (y + cy + 1 + r) * ref.stride + x + cx - 1
+            tgt[r] = ref.buf_y.reshape(-1)[o:o + w]
+        tgt = np.clip(2 * tgt.astype(np.int32) - rng.integers(0, maxv + 1, (h, w)), -maxv, 2 * maxv).astype(np.int16)
+        predx, predy = int(rng.integers(-90, 91)), int(rng.integers(-90, 91))
+        job = MeJob(-1, 1, x, y, w, h, capi.ME_FULL, 1, 64, cx - 4, cy - 4, cx + 4, cy + 4, predx, predy, 0, 0, lc)
+        gi, gf = t.me_bipred(3, tgt, job, hadamard=True)
+        e = oracle.MeResult()
+        r0 = optr(ref.buf_y, ref.origin(0) + y * ref.stride + x)
+        orc.orc_pattern_search(optr(tgt), w, r0, ref.stride, w, h, cx - 4, cy - 4, cx + 4, cy + 4, 1, bd - 8, lc, predx, predy, C.byref(e))
+        assert (gi.mvx, gi.mvy, gi.sad, gi.n_sads) == (e.mvx, e.mvy, e.sad, e.n_sads), (w, h)
+        f = oracle.FracResult()
+        orc.orc_frac_search(optr(tgt), w, r0, ref.stride, w, h, e.mvx, e.mvy, 1, bd - 8, bd, lc, predx, predy, C.byref(f))
+        assert (gf.halfx, gf.halfy, gf.qtrx, gf.qtry, gf.cost_half, gf.cost) == (f.halfx, f.halfy, f.qtrx, f.qtry, f.cost_half, f.cost), (w, h)
+        n += 1
+    assert n >= 12
+
+
 def test_me_search_10bit_direct(ctx10, orc):
     t = ctx10
     rng = np.random.default_rng(63)
@@ -565,9 +599,9 @@ def test_me_group_search_hard_content(ctx8, orc, kind):
     print(kind, stats, "mean candidates per search", float(ires["n_sads"][ires["n_sads"] > 0].mean()))
     census = t.me_census()
     checked = 0
-    for ctu in rng.choice(nctu, 6, replace=False):
+    for ctu in (int(v) for v in rng.choice(nctu, 6, replace=False)):
         x0, y0 = (ctu % t.ctus_x) * 64, (ctu // t.ctus_x) * 64
-        for k in rng.choice(593, 12, replace=False):
+        for k in (int(v) for v in rng.choice(593, 12, replace=False)):
             px, py, w, h, cux, cuy = (int(v) for v in census[k])
             x, y = x0 + px, y0 + py
             if x + w > W or y + h > H:

@@ -81,8 +81,15 @@ def test_bitstream_md5_identical_to_reference(tmp_path, cfg, frames, extra):
     _yuv(yuv, w, h, frames)
     ref_bin, cuda_bin = str(tmp_path / "ref.bin"), str(tmp_path / "cuda.bin")
     ref_job = _encode_ref_bg(cfg, yuv, w, h, frames, ref_bin, extra=extra)
-    r = _encode(ENC_CUDA, cfg, yuv, w, h, frames, cuda_bin, env={"TVC_HM": "me,frac,tq,rdoq,mc,tables,verify"}, extra=extra)
+    r = _encode(ENC_CUDA, cfg, yuv, w, h, frames, cuda_bin, env={"TVC_HM": "me,frac,tq,rdoq,mc,tables,bipred,verify"}, extra=extra)
     ref_job.result()
+    if "randomaccess" in cfg or cfg == "encoder_lowdelay_main.cfg":
+        # B slices: every bi-prediction refinement (xPatternSearch on 2 * org - pred + its xPatternSearchFracDIF) ran on the device
+        bl = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda bi-prediction refinement:")]
+        assert bl, r.stderr[-800:]
+        print(bl[-1])
+        f = bl[-1].split()
+        assert int(f[3]) > 100 and int(f[6]) == int(f[3]) and int(f[15]) == 0, bl[-1]
     served = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda:")]
     assert served and "kernel launches" in served[-1], r.stderr[-500:]
     print(served[-1])

@@ -75,6 +75,9 @@ class MeFrameCfg(C.Structure):
 
 
 ME_CENSUS = 593
+# tvc_ubench selectors (include/thevc_cuda.h)
+UB_VABSDIFF4, UB_IADD3, UB_IMAD, UB_LDS128, UB_DP2A, UB_HBM_WRITE = 0, 1, 2, 3, 4, 5
+
 PHASES = ("me_tables", "me_search", "me_frac", "mc", "fwd_tq", "inv_tq", "other", "me_raster", "rdoq", "deblock", "intra")
 
 # numpy views of the ABI structs (same layout) for bulk results
@@ -143,6 +146,7 @@ SIGNATURES = {
     "tvc_me_prepass": (ci, [vp, ci, ci, vp, vp]),
     "tvc_me_reserve": (ci, [vp, ci]),
     "tvc_me_uses_tables": (ci, [vp]),
+    "tvc_me_bipred": (ci, [vp, ci, vp, ci, vp, ci, vp, vp]),
     "tvc_me_set_fused": (ci, [vp, ci]),
     "tvc_me_table_bytes": (C.c_size_t, [vp, ci]),
     "tvc_me_tables_dev": (ci, [vp, C.POINTER(vp), C.POINTER(vp)]),

@@ -81,8 +81,9 @@ struct tvc_ctx {
   unsigned long long* fr_stats = nullptr;   // device: 3 work counters (tvc_me_frame_stats)
   size_t fr_cap = 0;              // entries
   // group search (tvc_me_group.cu): sweep-offset table, census, list of the PUs handed back to the per-PU kernel
+  void* bi_buf = nullptr;         // tvc_me_bipred: job / results of one refinement search (device) and its pinned staging
+  void* bi_host = nullptr;
   int me_fused = -1;              // -1: TVC_ME_FUSED (default on), 0 / 1: set by tvc_me_set_fused
-  void* grp_sidx = nullptr;
   void* grp_census = nullptr;
   int* grp_fb_list = nullptr;
   int* grp_fb_count = nullptr;

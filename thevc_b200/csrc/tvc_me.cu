@@ -1738,6 +1738,48 @@ int tvc_me_frac_batch(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job* jobs,
 }
 
 
+int tvc_me_bipred(tvc_ctx* c, int target_slot, const int16_t* target, int target_stride, const tvc_me_job* job, int hadamard,
+                  tvc_me_result* int_out, tvc_frac_result* frac_out)
+{
+  if (!c || !valid_slot(c, target_slot) || !target || !job || !int_out || !frac_out || target_stride < job->w)
+    return set_err(c, TVC_ERR_ARG, "tvc_me_bipred: bad argument");
+  const tvc_me_job& j = *job;
+  const Pic& p = c->pics[target_slot];
+  bool ok = valid_slot(c, j.ref_slot) && j.ref_slot != target_slot && j.w > 0 && j.h > 0 && j.w <= 64 && j.h <= 64 && !(j.w & 3) && !(j.h & 3) &&
+            j.x >= 0 && j.y >= 0 && j.x + j.w <= p.w[0] + p.mx[0] && j.y + j.h <= p.h[0] + p.my[0] && j.lx <= j.rx && j.ty <= j.by &&
+            j.rx - j.lx <= 2 * TVC_ME_RANGE && j.by - j.ty <= 2 * TVC_ME_RANGE && j.mode == TVC_ME_FULL;
+  // every candidate, with the 8-tap reach of the fractional stage around it, must read inside the padded reference plane
+  if (ok) ok = j.x + j.lx - 5 >= -p.mx[0] && j.y + j.ty - 5 >= -p.my[0] && j.x + j.w + j.rx + 5 <= p.w[0] + p.mx[0] && j.y + j.h + j.by + 5 <= p.h[0] + p.my[0];
+  if (!ok) return set_err(c, TVC_ERR_ARG, "tvc_me_bipred: job invalid or reaches outside the padded picture");
+  if (!c->bi_buf) {
+    TVC_CUDA(c, cudaMalloc(&c->bi_buf, sizeof(tvc_me_job) + sizeof(tvc_me_result) + sizeof(tvc_frac_job) + sizeof(tvc_frac_result) + 64));
+    TVC_CUDA(c, cudaHostAlloc(&c->bi_host, 64 * 64 * sizeof(int16_t) + sizeof(tvc_me_job) + sizeof(tvc_me_result) + sizeof(tvc_frac_result) + 64, cudaHostAllocDefault));
+  }
+  // device: [job][int result][frac result][frac job]; host (pinned): [target block w x h][job][int result][frac result]
+  tvc_me_job* d_job = (tvc_me_job*)c->bi_buf;
+  tvc_me_result* d_int = (tvc_me_result*)(d_job + 1);
+  tvc_frac_result* d_frac = (tvc_frac_result*)(d_int + 1);
+  tvc_frac_job* d_fjob = (tvc_frac_job*)(d_frac + 1);
+  int16_t* h_blk = (int16_t*)c->bi_host;
+  tvc_me_job* h_job = (tvc_me_job*)(h_blk + 64 * 64);
+  tvc_me_result* h_int = (tvc_me_result*)(h_job + 1);
+  for (int r = 0; r < j.h; r++) memcpy(h_blk + (size_t)r * j.w, target + (ptrdiff_t)r * target_stride, sizeof(int16_t) * j.w);
+  *h_job = j;
+  TVC_CUDA(c, cudaMemcpy2DAsync(p.org[0] + (ptrdiff_t)j.y * p.stride[0] + j.x, sizeof(int16_t) * p.stride[0], h_blk, sizeof(int16_t) * j.w,
+                                sizeof(int16_t) * j.w, j.h, cudaMemcpyHostToDevice, c->stream));
+  TVC_CUDA(c, cudaMemcpyAsync(d_job, h_job, sizeof(tvc_me_job), cudaMemcpyHostToDevice, c->stream));
+  int r;
+  if ((r = launch_search(c, target_slot, 0, 1, d_job, d_int, nullptr, nullptr, nullptr))) return r;
+  k_me_frame_frac_jobs<<<1, 32, 0, c->stream>>>(1, d_job, d_int, hadamard, d_fjob);
+  TVC_LAUNCH_CHECK(c);
+  if ((r = launch_frac(c, target_slot, 1, d_fjob, d_frac, false))) return r;
+  TVC_CUDA(c, cudaMemcpyAsync(h_int, d_int, sizeof(tvc_me_result) + sizeof(tvc_frac_result), cudaMemcpyDeviceToHost, c->stream));
+  TVC_CUDA(c, cudaStreamSynchronize(c->stream));
+  *int_out = *h_int;
+  *frac_out = *(const tvc_frac_result*)(h_int + 1);
+  return TVC_OK;
+}
+
 int tvc_me_census(tvc_census_pu* out)
 {
   if (!out) return TVC_ERR_ARG;

@@ -7,12 +7,13 @@
 //
 // All 593 PUs of the census search the same window around the same predictor (xSetSearchRange, TEncSearch.cpp:4209-4225), so the
 // CTA works CANDIDATE-major in lock-step rounds of the TZ state machine (xTZSearch, :4302-4474):
-//   1. every PU thread posts the candidates its next step visits (start + zero vector, a diamond sweep of <= 76 points, the two
-//      points of xTZ2PointSearch, the raster grid) into a bitmap over +-128 pels around the window centre;
-//   2. the set bits -- the UNION over the PUs -- are enumerated (block scan) and processed in chunks: one warp per candidate
+//   1. every PU thread names the REQUEST its next step makes -- (start + zero vector), a diamond sweep of <= 76 points around a
+//      centre, the two points of xTZ2PointSearch around a best point, the raster grid -- and the distinct requests of the round
+//      are collected in a shared-memory hash table: PUs that make the same request visit the same candidates;
+//   2. the candidates of the requests become slots (request, visiting index, position) processed in chunks: one warp per slot
 //      turns the 64x64 absolute differences (VABSDIFF4, window rows from shared memory, conflict-free 128-bit loads) into the
-//      even-row / odd-row SADs of the 256 4x4 blocks (the FEN row sub-sampling of TEncSearch.cpp:324-330 needs them apart),
-//      two 17x17 integral images per candidate follow, and every PU thread reads its SAD with four loads per image;
+//      even-row / odd-row SADs of the 256 4x4 blocks (the FEN row sub-sampling of TEncSearch.cpp:324-330 needs them apart) and
+//      integrates them into two 17x17 integral images; every PU thread reads the SAD of the slots of ITS request with four loads;
 //   3. every PU thread replays the reference's sequential strict-'<' update on its own costs (ordered arg-min: cost and visiting
 //      index packed into one word) and moves its state machine on.
 // Candidates outside the staged window (zero vector of a far predictor, PUs at the picture border whose clipMv differs from
@@ -25,17 +26,17 @@ namespace tvc {
 
 constexpr int kGT = 640;                       // threads: one per census PU (593), whole warps
 constexpr int kGWarps = kGT / 32;
-constexpr int kGChunk = 40;                    // candidates per chunk (two per warp)
+constexpr int kGChunk = 40;                    // candidate slots per chunk (two per warp)
 constexpr int kGWinW = 208, kGWinH = 192;      // staged window: 64 + 2 * 64 columns + 16 bytes of TMA alignment slack
 constexpr int kGCurP = 80;                     // pitch of the staged CTU (80 = 20 words: rows 0..7 start in distinct bank groups)
-constexpr int kGBm = 256;                      // the candidate bitmap covers dx, dy in [-128, 127] around the window centre
-constexpr int kGBmWords = kGBm * kGBm / 32;
-constexpr int kGList = 2048;                   // candidates enumerated per pass
+constexpr int kGHash = 1024;                   // hash slots of the request table (<= 593 distinct requests per round)
+constexpr int kGSlots = 4096;                  // candidate slots per pass
+constexpr int kGClsPerPass = kGSlots / 76;     // 53 sweep requests fill one pass
 constexpr int kGMaxRounds = 64;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
-constexpr int kSidxDim = 129;                  // sweep-offset table: (oy + 64) * 129 + ox + 64 -> visiting index or 255
 
 enum { PH_INIT = 0, PH_FIRST = 1, PH_TWO_F = 2, PH_RASTER = 3, PH_REFINE = 4, PH_TWO_R = 5, PH_DONE = 6, PH_FALLBACK = 7 };
+enum { RQ_INIT = 1, RQ_SWEEP = 2, RQ_TWO = 3, RQ_RASTER = 4 };       // request kinds (0 = empty hash slot)
 
 struct GroupMaps {
   CUtensorMap cur;                 // u8 luma of the current picture, box 80 x 64
@@ -44,18 +45,22 @@ struct GroupMaps {
   int stride8;
 };
 
+// one request = one distinct (kind, anchor, window) among the PUs of a round: every PU that makes it visits the same candidates
+struct Request { int16_t kind, aux, ax, ay, lx, ty, rx, by; };
+struct Slot { int16_t x, y; uint16_t req, idx; };      // candidate (absolute integer MV) of request `req`, visiting index idx
+
 struct GroupSmem {
   alignas(128) uint8_t win[kGWinW * kGWinH];
   alignas(128) uint8_t cur[kGCurP * 64];
   alignas(16) uint32_t IE[kGChunk][17 * 17];   // integral of the even-row block SADs
   uint32_t IA[kGChunk][17 * 17];               // integral of even + odd
-  uint32_t bm[kGBmWords];                      // candidates requested this round
-  uint32_t cbm[kGBmWords];                     // sweep centres already posted this round (PUs with the group's window)
-  uint16_t list[kGList];
+  alignas(8) unsigned long long hkey[kGHash];  // request keys (open addressing)
+  unsigned long long rcnt[kGT];                // per request: valid candidates per sweep round (7 x 5 bits)
+  Request req[kGT];
+  uint16_t hreq[kGHash];                       // hash slot -> request index
+  Slot slot[kGSlots];
   uint32_t mvc[kGChunk];
-  int16_t cx[kGChunk], cy[kGChunk];
-  uint32_t warp_tot[kGWarps];
-  int total, zero_extra, raster_same;
+  int nreq, nslot;
   alignas(8) uint64_t bar;
 };
 
@@ -137,9 +142,29 @@ __device__ __forceinline__ void grid_store(uint32_t (&v)[8][2], int lane, uint32
   }
 }
 
+// raw block SADs of one candidate -> integral images, by the warp that computed them (no block barrier): row prefix sums
+// (lane = image x row), then column prefix sums (lane = image x column)
+__device__ __forceinline__ void grid_integrate(uint32_t* __restrict__ IEc, uint32_t* __restrict__ IAc, int lane)
+{
+  __syncwarp();
+  {
+    uint32_t* p = ((lane & 16) ? IAc : IEc) + ((lane & 15) + 1) * 17 + 1;
+    uint32_t s = 0;
+#pragma unroll
+    for (int x = 0; x < 16; x++) { s += p[x]; p[x] = s; }
+  }
+  __syncwarp();
+  {
+    uint32_t* p = ((lane & 16) ? IAc : IEc) + 17 + (lane & 15) + 1;
+    uint32_t s = 0;
+#pragma unroll
+    for (int r = 0; r < 16; r++) { s += p[r * 17]; p[r * 17] = s; }
+  }
+}
+
 __global__ void __launch_bounds__(kGT, 1)
 k_me_group(const __grid_constant__ GroupMaps maps, const tvc_me_job* __restrict__ jobs, tvc_me_result* __restrict__ out,
-           const tvc_census_pu* __restrict__ census, const uint8_t* __restrict__ sidx, int pic_w, int pic_h, int mx, int my,
+           const tvc_census_pu* __restrict__ census, int pic_w, int pic_h, int mx, int my,
            int ref_index_fixed, int* __restrict__ fb_list, int* __restrict__ fb_count, unsigned long long* __restrict__ stats)
 {
   extern __shared__ __align__(128) uint8_t g_smem[];
@@ -170,13 +195,13 @@ k_me_group(const __grid_constant__ GroupMaps maps, const tvc_me_job* __restrict_
     tma_load_2d(S.win, &maps.ref[ref], wx - e16, my + y0 + ceny - kMeR, &S.bar);
     tma_load_2d(S.cur, &maps.cur, mx + x0, my + y0, &S.bar);
   }
-  // while the copies fly: per-PU set-up, bitmaps and integral borders cleared
-  for (int i = tid; i < kGBmWords; i += kGT) { S.bm[i] = 0; S.cbm[i] = 0; }
+  // while the copies fly: per-PU set-up, request table and integral borders cleared
+  for (int i = tid; i < kGHash; i += kGT) S.hkey[i] = 0ull;
   for (int i = tid; i < kGChunk * 17; i += kGT) {
     const int c = i / 17, k = i % 17;
     S.IE[c][k] = 0; S.IA[c][k] = 0; S.IE[c][k * 17] = 0; S.IA[c][k * 17] = 0;
   }
-  if (tid == 0) { S.zero_extra = 0; S.raster_same = 0; }
+  if (tid == 0) { S.nreq = 0; S.nslot = 0; }
 
   const bool is_pu = tid < TVC_ME_CENSUS;
   const tvc_me_job jb = jobs[gbase + (is_pu ? tid : 0)];
@@ -186,7 +211,7 @@ k_me_group(const __grid_constant__ GroupMaps maps, const tvc_me_job* __restrict_
   const int sub = (jb.fen && cp.h > 8) ? 1 : 0;
   const int c00 = (cp.y >> 2) * 17 + (cp.x >> 2), c01 = (cp.y >> 2) * 17 + ((cp.x + cp.w) >> 2);
   const int c10 = ((cp.y + cp.h) >> 2) * 17 + (cp.x >> 2), c11 = ((cp.y + cp.h) >> 2) * 17 + ((cp.x + cp.w) >> 2);
-  const int dmax = jb.search_range, raster = 5;
+  const int dmax = j0.search_range, raster = 5;              // the census shares range, predictor and lambda
   int nsweep = 0;
   for (int d = 1; d <= dmax; d <<= 1) nsweep += round_size(d);
   const int rnx = (win.rx - win.lx) / raster + 1, rny = (win.by - win.ty) / raster + 1;
@@ -196,120 +221,114 @@ k_me_group(const __grid_constant__ GroupMaps maps, const tvc_me_job* __restrict_
   uint32_t best = kNone, best_dist = 0, n_sads = 0;
   int best_x = 0, best_y = 0, point_nr = 0, sx = 0, sy = 0;
   uint32_t rmin[7];
-  unsigned long long cnt = 0;
-  uint32_t acc = kNone, nvalid = 0;
+  uint32_t acc = kNone;
   unsigned long long st_win = 0, st_glob = 0, st_rounds = 0;
-
-  // post a candidate (absolute integer MV) into the round's bitmap; false: beyond the bitmap
-  auto post = [&](int x, int y) -> bool {
-    const int bx = x - cenx + 128, by = y - ceny + 128;
-    if ((unsigned)bx > 255u || (unsigned)by > 255u || (bx == 255 && by == 255)) return false;
-    atomicOr(&S.bm[(by * kGBm + bx) >> 5], 1u << (bx & 31));
-    return true;
-  };
 
   mbar_wait(&S.bar, 0);
   __syncthreads();
 
   for (int round = 0; round < kGMaxRounds; round++) {
-    // ------------------------------------------------------------------ 1. requests
-    acc = kNone; nvalid = 0;
-    if (phase == PH_INIT) {
-      if (!post(jb.startx, jb.starty)) phase = PH_FALLBACK;
-    } else if (phase == PH_FIRST || phase == PH_REFINE) {
+    // ------------------------------------------------------------------ 1. requests: distinct (kind, anchor, window) of this round
+    acc = kNone;
+    int kind = 0, aux = 0, ax = 0, ay = 0;
+    if (phase == PH_INIT) { kind = RQ_INIT; ax = jb.startx; ay = jb.starty; rmin[0] = rmin[1] = kNone; }
+    else if (phase == PH_FIRST || phase == PH_REFINE) {
+      kind = RQ_SWEEP; ax = sx; ay = sy;
       if (phase == PH_FIRST) {
 #pragma unroll
         for (int r = 0; r < 7; r++) rmin[r] = kNone;
-        cnt = 0;
       }
-      bool need = true;
-      if (same) {                                // PUs with the group's window and this centre post the same set: once is enough
-        const int bx = sx - cenx + 128, by = sy - ceny + 128;
-        if ((unsigned)bx <= 255u && (unsigned)by <= 255u)
-          need = !(atomicOr(&S.cbm[(by * kGBm + bx) >> 5], 1u << (bx & 31)) & (1u << (bx & 31)));
+    } else if (phase == PH_TWO_F || phase == PH_TWO_R) { kind = RQ_TWO; ax = best_x; ay = best_y; aux = point_nr; }
+    else if (phase == PH_RASTER) kind = RQ_RASTER;
+    if (!__syncthreads_or(kind != 0)) break;
+    int hslot = 0;
+    bool owner = false;
+    if (kind) {
+      // kind 3 bits | aux 4 bits | window id 10 bits (0: the group's window, else the PU's own) | ax 16 bits | ay 16 bits
+      const unsigned long long key = (unsigned long long)kind | ((unsigned long long)(aux & 15) << 3) |
+                                     ((unsigned long long)(same ? 0 : tid + 1) << 7) | ((unsigned long long)(uint16_t)ax << 17) |
+                                     ((unsigned long long)(uint16_t)ay << 33);
+      uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 54);
+      for (;;) {
+        const unsigned long long old = atomicCAS(&S.hkey[h], 0ull, key);
+        if (old == 0ull) { owner = true; break; }
+        if (old == key) break;
+        h = (h + 1) & (kGHash - 1);
       }
-      if (need) {
-        for (int c = 0; c < nsweep; c++) {
-          int d, i, x, y, pt;
-          uint32_t dist;
-          sweep_slot(c, dmax, d, i);
-          if (diamond_cand(win, sx, sy, d, i, x, y, pt, dist) && !post(x, y)) { phase = PH_FALLBACK; break; }
-        }
-      }
-    } else if (phase == PH_TWO_F || phase == PH_TWO_R) {
-      int x[2], y[2];
-      bool v[2];
-      two_points(win, best_x, best_y, point_nr, x, y, v);
-      if ((v[0] && !post(x[0], y[0])) || (v[1] && !post(x[1], y[1]))) phase = PH_FALLBACK;
-    } else if (phase == PH_RASTER) {
-      if (same) S.raster_same = 1;               // benign race: every writer stores 1; posted cooperatively below
-      else {
-        for (int i = 0; i < rnx * rny; i++)
-          if (!post(win.lx + (i % rnx) * raster, win.ty + (i / rnx) * raster)) { phase = PH_FALLBACK; break; }
-      }
+      hslot = (int)h;
     }
-    if (round == 0 && tid == 0) {                // the zero vector (TEncSearch.cpp:4336-4339): probed by every PU
-      const int bx = -cenx + 128, by = -ceny + 128;
-      if ((unsigned)bx > 255u || (unsigned)by > 255u || (bx == 255 && by == 255)) S.zero_extra = 1;
-      else atomicOr(&S.bm[(by * kGBm + bx) >> 5], 1u << (bx & 31));
+    __syncthreads();
+    if (owner) {
+      const int r = atomicAdd(&S.nreq, 1);
+      S.hreq[hslot] = (uint16_t)r;
+      S.req[r] = Request{(int16_t)kind, (int16_t)aux, (int16_t)ax, (int16_t)ay, (int16_t)win.lx, (int16_t)win.ty, (int16_t)win.rx, (int16_t)win.by};
+      S.rcnt[r] = 0ull;
     }
-    const int any = __syncthreads_or(phase < PH_DONE);
-    if (!any) break;
-    if (S.raster_same) {
-      const int jnx = (j0.rx - j0.lx) / raster + 1, jny = (j0.by - j0.ty) / raster + 1;
-      for (int i = tid; i < jnx * jny; i += kGT) post(j0.lx + (i % jnx) * raster, j0.ty + (i / jnx) * raster);   // inside +-64 of the centre
-      __syncthreads();
-    }
+    __syncthreads();
+    const int my_req = kind ? (int)S.hreq[hslot] : -1;
+    const int nreq = S.nreq;
     st_rounds++;
 
-    // ------------------------------------------------------------------ 2. enumerate the union (block scan over the bitmap words)
-    int my_cnt = 0, my_off = 0;
-    if (tid < kGBmWords / 4) {
-#pragma unroll
-      for (int w = 0; w < 4; w++) my_cnt += __popc(S.bm[4 * tid + w]);
-    }
-    {
-      int incl = my_cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-      if (lane == 31) S.warp_tot[warp] = (uint32_t)incl;
+    // ------------------------------------------------------------------ 2. passes: candidate slots of a run of requests, chunk by chunk
+    for (int r0 = 0; r0 < nreq;) {
+      int r1 = r0, budget = 0;
+      while (r1 < nreq) {
+        const int b = S.req[r1].kind == RQ_RASTER ? 1024 : 76;
+        if (budget + b > kGSlots) break;
+        budget += b; r1++;
+      }
+      if (tid == 0) S.nslot = 0;
       __syncthreads();
-      int wbase = 0;
-      for (int w = 0; w < warp; w++) wbase += (int)S.warp_tot[w];
-      my_off = wbase + incl - my_cnt;
-      if (tid == kGT - 1) S.total = wbase + incl;
-      __syncthreads();
-    }
-    const int nbits = S.total, ntot = nbits + (round == 0 ? S.zero_extra : 0);
-
-    for (int lo = 0; lo < ntot; lo += kGList) {
-      const int hi = min(lo + kGList, ntot), npass = hi - lo;
-      if (tid < kGBmWords / 4 && my_off < hi && my_off + my_cnt > lo) {
-        int pos = my_off;
-#pragma unroll
-        for (int w = 0; w < 4; w++) {
-          uint32_t word = S.bm[4 * tid + w];
-          while (word) {
-            const int b = __ffs(word) - 1;
-            word &= word - 1;
-            if (pos >= lo && pos < hi) S.list[pos - lo] = (uint16_t)((4 * tid + w) * 32 + b);
-            pos++;
+      for (int it = tid; it < (r1 - r0) * 76; it += kGT) {
+        const int r = r0 + it / 76, c = it % 76;
+        const Request rq = S.req[r];
+        const Win rw = {rq.lx, rq.ty, rq.rx, rq.by};
+        int x = 0, y = 0;
+        bool v = false;
+        if (rq.kind == RQ_SWEEP) {
+          if (c < nsweep) {
+            int d, i, pt;
+            uint32_t dist;
+            sweep_slot(c, dmax, d, i);
+            v = diamond_cand(rw, rq.ax, rq.ay, d, i, x, y, pt, dist);
+            if (v) atomicAdd(&S.rcnt[r], 1ull << (5 * (c < 4 ? 0 : (c < 28 ? 1 + ((c - 4) >> 3) : 4 + ((c - 28) >> 4)))));
+          }
+        } else if (rq.kind == RQ_INIT) {
+          v = c < 2;                             // start point, then the zero vector (TEncSearch.cpp:4320, 4336-4339)
+          if (c == 0) { x = rq.ax; y = rq.ay; }
+        } else if (rq.kind == RQ_TWO) {
+          if (c < 2) {
+            int tx[2], ty2[2];
+            bool tv[2];
+            two_points(rw, rq.ax, rq.ay, rq.aux, tx, ty2, tv);
+            x = tx[c]; y = ty2[c]; v = tv[c];
+            if (v) atomicAdd(&S.rcnt[r], 1ull);
           }
         }
+        if (v) {
+          const int k = atomicAdd(&S.nslot, 1);
+          S.slot[k] = Slot{(int16_t)x, (int16_t)y, (uint16_t)r, (uint16_t)c};
+        }
       }
-      if (tid == 0 && nbits >= lo && nbits < hi && ntot > nbits) S.list[nbits - lo] = 0xFFFFu;      // the zero vector beyond the bitmap
+      for (int r = r0; r < r1; r++) {
+        const Request rq = S.req[r];
+        if (rq.kind != RQ_RASTER) continue;      // uniform: every thread reads the same record
+        const int nx = (rq.rx - rq.lx) / raster + 1, ny = (rq.by - rq.ty) / raster + 1;
+        for (int i = tid; i < nx * ny; i += kGT) {
+          const int k = atomicAdd(&S.nslot, 1);
+          S.slot[k] = Slot{(int16_t)(rq.lx + (i % nx) * raster), (int16_t)(rq.ty + (i / nx) * raster), (uint16_t)r, (uint16_t)i};
+        }
+      }
       __syncthreads();
+      const int nslot = S.nslot;
 
-      for (int cb0 = 0; cb0 < npass; cb0 += kGChunk) {
-        const int nc = min(kGChunk, npass - cb0);
-        // ---- 2a. block SAD grids, one warp per candidate
+      for (int cb0 = 0; cb0 < nslot; cb0 += kGChunk) {
+        const int nc = min(kGChunk, nslot - cb0);
+        // ---- 2a. one warp per candidate: block SAD grid, then its two integral images
         for (int ci = warp; ci < nc; ci += kGWarps) {
-          const uint32_t code = S.list[cb0 + ci];
-          int dx, dy;
-          if (code == 0xFFFFu) { dx = -cenx; dy = -ceny; }
-          else { dx = (int)(code & 255u) - 128; dy = (int)(code >> 8) - 128; }
-          const int x = cenx + dx, y = ceny + dy;
-          if (lane == 0) { S.cx[ci] = (int16_t)x; S.cy[ci] = (int16_t)y; S.mvc[ci] = mv_cost(j0.lambda_cost, x, y, 2, j0.predx, j0.predy); }
+          const Slot sl = S.slot[cb0 + ci];
+          const int x = sl.x, y = sl.y, dx = x - cenx, dy = y - ceny;
+          if (lane == 0) S.mvc[ci] = mv_cost(j0.lambda_cost, x, y, 2, j0.predx, j0.predy);
           const int q = lane >> 3, g = lane & 7;
           const uint8_t* cbp = S.cur + g * kGCurP + 16 * q;
           uint32_t v[8][2];
@@ -325,91 +344,46 @@ k_me_group(const __grid_constant__ GroupMaps maps, const tvc_me_job* __restrict_
             }
             if (lane == 0) st_win++;
           } else {
+            // beyond the staged window (zero vector of a far predictor, border PUs clipped differently): rows from the u8 plane
             const uint8_t* rp = maps.ref8[ref] + (ptrdiff_t)(y0 + y + g) * maps.stride8 + (x0 + x + 16 * q);
             grid_rows_global(rp, maps.stride8, cbp, v);
             if (lane == 0) st_glob++;
           }
           grid_store(v, lane, S.IE[ci], S.IA[ci]);
+          grid_integrate(S.IE[ci], S.IA[ci], lane);
         }
         __syncthreads();
-        // ---- 2b. integral images: row prefix sums, then column prefix sums
-        for (int wk = tid; wk < 2 * nc * 16; wk += kGT) {
-          const int img = wk / (nc * 16), c = (wk / 16) % nc, r = wk % 16;
-          uint32_t* p = (img ? S.IA[c] : S.IE[c]) + (r + 1) * 17 + 1;
-          uint32_t s = 0;
-#pragma unroll
-          for (int x = 0; x < 16; x++) { s += p[x]; p[x] = s; }
-        }
-        __syncthreads();
-        for (int wk = tid; wk < 2 * nc * 16; wk += kGT) {
-          const int img = wk / (nc * 16), c = (wk / 16) % nc, x = wk % 16;
-          uint32_t* p = (img ? S.IA[c] : S.IE[c]) + 17 + x + 1;
-          uint32_t s = 0;
-#pragma unroll
-          for (int r = 0; r < 16; r++) { s += p[r * 17]; p[r * 17] = s; }
-        }
-        __syncthreads();
-        // ---- 3. every PU: cost of the chunk's candidates it visits, ordered arg-min
-        if (phase < PH_DONE) {
-          int tx[2] = {0, 0}, ty2[2] = {0, 0};
-          bool tv[2] = {false, false};
-          if (phase == PH_TWO_F || phase == PH_TWO_R) two_points(win, best_x, best_y, point_nr, tx, ty2, tv);
+        // ---- 3. every PU: cost of the chunk's candidates that belong to its request, ordered arg-min
+        if (my_req >= 0) {
           for (int ci = 0; ci < nc; ci++) {
-            const int x = S.cx[ci], y = S.cy[ci];
-            uint32_t key = kNone;              // visiting index of (x, y) in this PU's step, kNone: not visited
-            int rr = 0;
-            if (phase == PH_INIT) {
-              if (x == jb.startx && y == jb.starty) key = 0;
-              if (x == 0 && y == 0) key = key == 0 ? 2 : 1;      // 2: the start IS the zero vector
-            } else if (phase == PH_FIRST || phase == PH_REFINE) {
-              const int ox = x - sx, oy = y - sy;
-              if ((unsigned)(ox + 64) <= 128u && (unsigned)(oy + 64) <= 128u) {
-                const int c = __ldg(&sidx[(oy + 64) * kSidxDim + ox + 64]);
-                if (c < nsweep) {
-                  int d, i, xx, yy, pt;
-                  uint32_t dist;
-                  sweep_slot(c, dmax, d, i);
-                  if (diamond_cand(win, sx, sy, d, i, xx, yy, pt, dist)) {
-                    key = phase == PH_FIRST ? (uint32_t)i : (uint32_t)c;
-                    rr = c < 4 ? 0 : (c < 28 ? 1 + ((c - 4) >> 3) : 4 + ((c - 28) >> 4));
-                  }
-                }
-              }
-            } else if (phase == PH_RASTER) {
-              const int ax = x - win.lx, ay = y - win.ty;
-              if (ax >= 0 && x <= win.rx && ay >= 0 && y <= win.by && (ax % raster) == 0 && (ay % raster) == 0)
-                key = (uint32_t)((ay / raster) * rnx + ax / raster);
-            } else {
-              if (tv[0] && x == tx[0] && y == ty2[0]) key = 0;
-              else if (tv[1] && x == tx[1] && y == ty2[1]) key = 1;
-            }
-            if (key == kNone) continue;
+            const Slot sl = S.slot[cb0 + ci];
+            if ((int)sl.req != my_req) continue;
             const uint32_t* I = sub ? S.IE[ci] : S.IA[ci];
             const uint32_t sad = I[c11] - I[c01] - I[c10] + I[c00];
             const uint32_t cost = (sad << sub) + S.mvc[ci];
+            const uint32_t c = sl.idx;
             if (phase == PH_INIT) {
-              if (key != 1) rmin[0] = cost;                     // start
-              if (key != 0) rmin[1] = cost;                     // zero vector
+              if (c == 0) rmin[0] = cost;
+              else rmin[1] = cost;
             } else if (phase == PH_FIRST) {
-              const uint32_t pk = (cost << 4) | key;
+              const int rr = c < 4 ? 0 : (c < 28 ? 1 + (int)((c - 4) >> 3) : 4 + (int)((c - 28) >> 4));
+              const uint32_t i = c < 4 ? c : (c < 28 ? ((c - 4) & 7u) : ((c - 28) & 15u));
+              const uint32_t pk = (cost << 4) | i;
 #pragma unroll
               for (int r = 0; r < 7; r++)
                 if (r == rr) rmin[r] = min(rmin[r], pk);
-              cnt += 1ull << (5 * rr);
-            } else if (phase == PH_REFINE) {
-              acc = min(acc, (cost << 7) | key); nvalid++;
-            } else if (phase == PH_RASTER) {
-              acc = min(acc, (cost << 10) | key);
-            } else {
-              acc = min(acc, (cost << 1) | key);
-            }
+            } else if (phase == PH_REFINE) acc = min(acc, (cost << 7) | c);
+            else if (phase == PH_RASTER) acc = min(acc, (cost << 10) | c);
+            else acc = min(acc, (cost << 1) | c);
           }
         }
         __syncthreads();
       }
+      r0 = r1;
     }
 
     // ------------------------------------------------------------------ 4. replay the sequential update, move the state machine
+    const unsigned long long cnt = my_req >= 0 ? S.rcnt[my_req] : 0ull;
     bool to_after_first = false, to_refine_entry = false;
     if (phase == PH_INIT) {
       best = rmin[0]; best_x = jb.startx; best_y = jb.starty;
@@ -436,11 +410,11 @@ k_me_group(const __grid_constant__ GroupMaps maps, const tvc_me_job* __restrict_
       if (best_dist == 1) { best_dist = 0; phase = PH_TWO_F; }  // :4382-4386
       else to_after_first = true;
     } else if (phase == PH_TWO_F || phase == PH_TWO_R) {
-      int x[2], y[2];
-      bool v[2];
-      two_points(win, best_x, best_y, point_nr, x, y, v);
-      n_sads += (v[0] ? 1u : 0u) + (v[1] ? 1u : 0u);
+      n_sads += (uint32_t)(cnt & 31ull);
       if (acc != kNone && (acc >> 1) < best) {
+        int x[2], y[2];
+        bool v[2];
+        two_points(win, best_x, best_y, point_nr, x, y, v);
         best = acc >> 1; best_x = x[acc & 1u]; best_y = y[acc & 1u];
         best_dist = 2; point_nr = 0;
       }
@@ -456,7 +430,8 @@ k_me_group(const __grid_constant__ GroupMaps maps, const tvc_me_job* __restrict_
       }
       to_refine_entry = true;
     } else if (phase == PH_REFINE) {
-      n_sads += nvalid;
+#pragma unroll
+      for (int r = 0; r < 7; r++) n_sads += (uint32_t)((cnt >> (5 * r)) & 31ull);
       if (acc != kNone && (acc >> 7) < best) {
         int d, i, pt;
         sweep_slot((int)(acc & 127u), dmax, d, i);
@@ -477,9 +452,9 @@ k_me_group(const __grid_constant__ GroupMaps maps, const tvc_me_job* __restrict_
       if (best_dist > 0) { sx = best_x; sy = best_y; best_dist = 0; point_nr = 0; phase = PH_REFINE; }
       else phase = PH_DONE;
     }
-    // bitmaps of the next round
-    for (int i = tid; i < kGBmWords; i += kGT) { S.bm[i] = 0; S.cbm[i] = 0; }
-    if (tid == 0) S.raster_same = 0;
+    // request table of the next round
+    for (int i = tid; i < kGHash; i += kGT) S.hkey[i] = 0ull;
+    if (tid == 0) S.nreq = 0;
     __syncthreads();
   }
 
@@ -490,7 +465,7 @@ k_me_group(const __grid_constant__ GroupMaps maps, const tvc_me_job* __restrict_
       else { r.mvx = 0; r.mvy = 0; r.sad = 0; r.n_sads = 0; }
       out[gbase + tid] = r;
     } else {
-      // handed back: the per-PU kernel finishes it from the pictures (candidates beyond the bitmap, a mode other than TZ, round cap)
+      // handed back: the per-PU kernel finishes it from the pictures (a mode other than TZ, round cap)
       const int k = atomicAdd(fb_count, 1);
       fb_list[k] = (int)(gbase + tid);
     }
@@ -500,30 +475,6 @@ k_me_group(const __grid_constant__ GroupMaps maps, const tvc_me_job* __restrict_
     if (st_glob) atomicAdd(&stats[1], st_glob);
     if (tid == 0) atomicAdd(&stats[2], st_rounds);
   }
-}
-
-// (oy + 64) * 129 + (ox + 64) -> visiting index of the offset in a sweep that starts at distance 1 (sweep_slot / diamond_cand order)
-static void build_sweep_index(uint8_t* t)
-{
-  memset(t, 255, kSidxDim * kSidxDim);
-  auto put = [&](int ox, int oy, int c) {
-    uint8_t& e = t[(oy + 64) * kSidxDim + ox + 64];
-    if (e != 255) { fprintf(stderr, "tvc: sweep offsets collide (%d,%d)\n", ox, oy); abort(); }
-    e = (uint8_t)c;
-  };
-  int c = 0;
-  const int o1[4][2] = {{0, -1}, {-1, 0}, {1, 0}, {0, 1}};
-  for (int i = 0; i < 4; i++) put(o1[i][0], o1[i][1], c++);
-  const int ux8[8] = {0, -1, 1, -2, 2, -1, 1, 0}, uy8[8] = {-2, -1, -1, 0, 0, 1, 1, 2};
-  for (int d = 2; d <= 8; d <<= 1)
-    for (int i = 0; i < 8; i++) put(ux8[i] * (d >> 1), uy8[i] * (d >> 1), c++);
-  for (int d = 16; d <= 64; d <<= 1)
-    for (int i = 0; i < 16; i++) {
-      int ux, uy;
-      if (i < 4) { ux = i == 1 ? -4 : (i == 2 ? 4 : 0); uy = i == 0 ? -4 : (i == 3 ? 4 : 0); }
-      else { const int k = ((i - 4) >> 2) + 1, j = (i - 4) & 3; ux = (j & 1) ? k : -k; uy = (j & 2) ? 4 - k : k - 4; }
-      put(ux * (d >> 2), uy * (d >> 2), c++);
-    }
 }
 
 }  // namespace tvc
@@ -536,17 +487,13 @@ int tvc_launch_me_group(tvc_ctx* c, int cur_slot, int ngroups, const tvc_me_job*
                         const int* ref_slots, int ref_index_fixed, unsigned long long* stats)
 {
   if (!c->pics[cur_slot].has_tmap || c->cfg.bit_depth != 8) return set_err(c, TVC_ERR_STATE, "group search: needs the 8-bit u8 planes and tensor maps");
-  if (!c->grp_sidx) {
-    std::vector<uint8_t> t(kSidxDim * kSidxDim);
-    build_sweep_index(t.data());
+  if (!c->grp_census) {
     tvc_census_pu cen[TVC_ME_CENSUS];
     tvc_me_census(cen);
-    TVC_CUDA(c, cudaMalloc(&c->grp_sidx, t.size()));
     TVC_CUDA(c, cudaMalloc(&c->grp_census, sizeof(cen)));
     TVC_CUDA(c, cudaMalloc(&c->grp_fb_count, sizeof(int)));
-    TVC_CUDA(c, cudaMemcpyAsync(c->grp_sidx, t.data(), t.size(), cudaMemcpyHostToDevice, c->stream));
     TVC_CUDA(c, cudaMemcpyAsync(c->grp_census, cen, sizeof(cen), cudaMemcpyHostToDevice, c->stream));
-    TVC_CUDA(c, cudaStreamSynchronize(c->stream));         // the sources are stack / local buffers
+    TVC_CUDA(c, cudaStreamSynchronize(c->stream));         // the source is a stack buffer
     TVC_CUDA(c, cudaFuncSetAttribute(k_me_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)));
   }
   const size_t njobs = (size_t)ngroups * TVC_ME_CENSUS;
@@ -570,7 +517,7 @@ int tvc_launch_me_group(tvc_ctx* c, int cur_slot, int ngroups, const tvc_me_job*
   TVC_CUDA(c, cudaMemsetAsync(c->grp_fb_count, 0, sizeof(int), c->stream));
   {
     ProfScope ps(c, TVC_PH_ME_SEARCH);
-    k_me_group<<<ngroups, kGT, sizeof(GroupSmem), c->stream>>>(maps, jobs_dev, out_dev, (const tvc_census_pu*)c->grp_census, (const uint8_t*)c->grp_sidx,
+    k_me_group<<<ngroups, kGT, sizeof(GroupSmem), c->stream>>>(maps, jobs_dev, out_dev, (const tvc_census_pu*)c->grp_census,
                                                                c->cfg.width, c->cfg.height, p.mx[0], p.my[0], ref_index_fixed, c->grp_fb_list,
                                                                c->grp_fb_count, stats);
     TVC_LAUNCH_CHECK(c);

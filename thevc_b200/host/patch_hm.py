@@ -36,6 +36,9 @@ def main():
     s = sub_once(s, r'(Void TEncSearch::xTZSearch\( TComDataCU\* pcCU,[^\n]*\r?\n\{\r?\n)',
                  r'\1  if ( tlibcuda_tz_search( pcCU, pcPatternKey, piRefY, iRefStride, pcMvSrchRngLT, pcMvSrchRngRB, rcMv, ruiSAD, m_pcRdCost, m_pcEncCfg, m_iSearchRange ) ) return;\n',
                  "xTZSearch")
+    s = sub_once(s, r'(Void TEncSearch::xPatternSearch\( TComPattern\* pcPatternKey, Pel\* piRefY, Int iRefStride, TComMv\* pcMvSrchRngLT, TComMv\* pcMvSrchRngRB, TComMv& rcMv, UInt& ruiSAD \)\r?\n\{\r?\n)',
+                 r'\1  if ( tlibcuda_full_search( pcPatternKey, piRefY, iRefStride, pcMvSrchRngLT, pcMvSrchRngRB, rcMv, ruiSAD, m_pcRdCost, m_pcEncCfg ) ) return;\n',
+                 "xPatternSearch")
     s = sub_once(s, r'(Void TEncSearch::xPatternSearchFracDIF\(TComDataCU\* pcCU,.*?\n\s*\)\r?\n\{\r?\n)',
                  r'\1  if ( tlibcuda_frac_search( pcPatternKey, piRefY, iRefStride, pcMvInt, rcMvHalf, rcMvQter, ruiCost, m_pcRdCost, m_pcEncCfg, biPred ) ) return;\n',
                  "xPatternSearchFracDIF", flags=re.S)

@@ -128,6 +128,8 @@ struct State {
   std::map<unsigned, int> census_index;    // (x, y, w, h) inside the CTU -> census index
   std::vector<tvc_me_center> center_guess; // [table ref][ctu]: first predictor of the previous picture's group (quarter pels)
   LastHit last;
+  LastHit last_bi;                         // the bi-prediction refinement just run: its fractional stage follows
+  unsigned long long n_bi = 0, n_bi_frac = 0, n_bi_host = 0;
   unsigned long long n_tz_lookup = 0, n_frac_lookup = 0, n_groups = 0;
   double batch_seconds = 0.0, prepass_seconds = 0.0;      // host wall time spent inside tvc_me_ctu / picture_start
   bool on_me = true, on_frac = true, on_tq = true, on_rdoq = true, on_mc = true, on_tables = true, verbose = false, disabled = false;
@@ -144,7 +146,7 @@ struct State {
   bool on_hash = false;                    // picture hashes on the device (TVC_HM=...,hash)
   unsigned long long n_hash = 0;
   bool on_cand = false;                    // merge / AMVP candidate evaluation (TVC_HM=...,cand)
-  bool on_bipred = true;                   // bi-prediction refinement searches on the device (off: TVC_HM=...,nobipred)
+  bool on_bipred = false;                  // bi-prediction refinement searches on the device (off: TVC_HM=...,nobipred)
   bool on_cand_grid = false;               // ... served by look-up from CTU-wide cost grids (TVC_HM=...,candgrid)
   struct Grid { uint32_t w[TVC_GRID_WORDS]; };
   std::unordered_map<unsigned long long, Grid> grids;      // (CTU, reference slot, clipped MV) -> prefix-sum grids; cleared per picture
@@ -199,6 +201,9 @@ void report()
   if (s.on_cand)
     fprintf(stderr, "TLibCuda candidate evaluation: %llu xMergeEstimation calls (%llu candidates) and %llu xGetTemplateCost calls on the device, %.3f s in tvc_pred_cost_batch\n",
             s.n_merge, s.n_merge_cands, s.n_template, s.cand_seconds);
+  if (s.h && (s.n_bi || s.n_bi_host))
+    fprintf(stderr, "TLibCuda bi-prediction refinement: %llu xPatternSearch + %llu xPatternSearchFracDIF calls on the device (tvc_me_bipred), %llu left to the reference's code\n",
+            s.n_bi, s.n_bi_frac, s.n_bi_host);
   if (s.intra.on)
     fprintf(stderr, "TLibCuda intra rough search: %llu PUs x 35 modes on the device (width >= %d), %llu smaller PUs by the reference's code, %.3f s in tvc_intra_rough\n",
             s.intra.n_pus, s.intra.min_width, s.intra.n_host, s.intra.seconds);
@@ -344,6 +349,7 @@ void ensure_ctx(int w, int ht)
   // the last two slots are the decoder batch's reconstruction and residual planes: never handed out as picture slots
   s.slots[c.num_slots - 1].stamp = s.slots[c.num_slots - 2].stamp = ~0ull;
   s.slots[c.num_slots - 3].stamp = ~0ull;       // the picture being hashed (tlibcuda_pic_hash)
+  s.slots[c.num_slots - 4].stamp = ~0ull;       // the bi-prediction search target (tlibcuda_full_search)
 }
 
 // slot of a picture buffer; uploads it when the slot does not hold this picture's current content
@@ -601,9 +607,27 @@ bool tlibcuda_frac_search(TComPattern* key, short* refY, int refStride, TComMv* 
                           unsigned& ruiCost, TComRdCost* rd, TEncCfg* cfg, bool biPred)
 {
   State& s = S();
-  if (!s.h || !s.on_frac || s.cur_slot < 0 || biPred || s.wp) return false;     // bi-pred search target is not the original picture
+  if (!s.h || !s.on_frac || s.cur_slot < 0 || s.wp) return false;
   int slot, x, y;
   if (!locate(refY, slot, x, y)) return false;
+  if (biPred) {
+    // the search target is 2 * org - pred(other list), not the picture: tlibcuda_full_search ran the integer AND the fractional
+    // stage against it in one device call (tvc_me_bipred); without the `bipred` hook the reference's own code runs
+    const LastHit& b = s.last_bi;
+    if (b.valid && b.slot == slot && b.x == x && b.y == y && b.w == key->getROIYWidth() && b.h == key->getROIYHeight() &&
+        b.mvx == mvInt->getHor() && b.mvy == mvInt->getVer() && b.predx == rd->m_mvPredictor.getHor() && b.predy == rd->m_mvPredictor.getVer() &&
+        b.lambda == rd->m_uiCost && b.had == (cfg->getUseHADME() ? 1 : 0)) {
+      half.set(b.fr.halfx, b.fr.halfy);
+      qter.set(b.fr.qtrx, b.fr.qtry);
+      ruiCost = b.fr.cost;
+      rd->setCostScale(0);
+      s.last_bi.valid = false;
+      s.n_bi_frac++;
+      return true;
+    }
+    s.n_bi_host++;
+    return false;
+  }
   (void)refStride;
   tvc_frac_job j;
   memset(&j, 0, sizeof(j));
@@ -632,6 +656,38 @@ bool tlibcuda_frac_search(TComPattern* key, short* refY, int refStride, TComMv* 
   qter.set(r.qtrx, r.qtry);
   ruiCost = r.cost;
   rd->setCostScale(0);                      // side effect of the reference body (:4505)
+  return true;
+}
+
+bool tlibcuda_full_search(TComPattern* key, short* refY, int refStride, TComMv* lt, TComMv* rb, TComMv& rcMv, unsigned& ruiSAD,
+                          TComRdCost* rd, TEncCfg* cfg)
+{
+  State& s = S();
+  s.last_bi.valid = false;
+  if (!s.h || !s.on_bipred || !s.on_me || !s.on_frac || s.cur_slot < 0 || s.wp) return false;
+  int slot, x, y;
+  if (!locate(refY, slot, x, y)) return false;
+  (void)refStride;
+  tvc_me_job j;
+  memset(&j, 0, sizeof(j));
+  j.ref_slot = slot; j.ref_index = -1;
+  j.x = x; j.y = y; j.w = key->getROIYWidth(); j.h = key->getROIYHeight();
+  j.mode = TVC_ME_FULL;
+  j.fen = cfg->getUseFastEnc() ? 1 : 0;
+  j.search_range = TVC_ME_RANGE;
+  j.lx = lt->getHor(); j.ty = lt->getVer(); j.rx = rb->getHor(); j.by = rb->getVer();
+  j.predx = rd->m_mvPredictor.getHor(); j.predy = rd->m_mvPredictor.getVer();
+  j.lambda_cost = rd->m_uiCost;
+  if (j.rx - j.lx > 2 * TVC_ME_RANGE || j.by - j.ty > 2 * TVC_ME_RANGE) return false;
+  const int had = cfg->getUseHADME() ? 1 : 0;
+  tvc_me_result ri;
+  LastHit& b = s.last_bi;
+  CK(tvc_me_bipred(s.h, (int)s.slots.size() - 4, key->getROIY(), key->getPatternLStride(), &j, had, &ri, &b.fr));
+  rcMv.set(ri.mvx, ri.mvy);
+  ruiSAD = ri.sad;
+  b.valid = true; b.slot = slot; b.x = x; b.y = y; b.w = j.w; b.h = j.h; b.mvx = ri.mvx; b.mvy = ri.mvy;
+  b.predx = j.predx; b.predy = j.predy; b.lambda = j.lambda_cost; b.had = had;
+  s.n_bi++;
   return true;
 }
 

@@ -32,6 +32,11 @@ void tlibcuda_picture_start(TComPic* pic, TComSlice* slice);
 /* TEncSearch::xTZSearch (TEncSearch.cpp:4302) */
 bool tlibcuda_tz_search(TComDataCU* cu, TComPattern* key, short* refY, int refStride, TComMv* lt, TComMv* rb, TComMv& rcMv,
                         unsigned& ruiSAD, TComRdCost* rd, TEncCfg* cfg, int searchRange);
+/* TEncSearch::xPatternSearch (TEncSearch.cpp:4227): the exhaustive search of the bi-prediction refinement (xMotionEstimation with bBi:
+ * the pattern is 2 * org - pred of the other list, the window +-bipredSearchRange).  TVC_HM=...,bipred: integer and fractional stage
+ * of that refinement in one device call (tvc_me_bipred); the xPatternSearchFracDIF call that follows takes its result from it. */
+bool tlibcuda_full_search(TComPattern* key, short* refY, int refStride, TComMv* lt, TComMv* rb, TComMv& rcMv, unsigned& ruiSAD,
+                          TComRdCost* rd, TEncCfg* cfg);
 /* TEncSearch::xPatternSearchFracDIF (TEncSearch.cpp:4476) */
 bool tlibcuda_frac_search(TComPattern* key, short* refY, int refStride, TComMv* mvInt, TComMv& half, TComMv& qter,
                           unsigned& ruiCost, TComRdCost* rd, TEncCfg* cfg, bool biPred);

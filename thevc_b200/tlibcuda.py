@@ -223,6 +223,13 @@ class TLibCuda:
             self._ck(self.L.tvc_me_search_batch(self.h, cur_slot, int(use_tables), n, C.cast(arr, C.c_void_p), C.cast(res, C.c_void_p)))
         return list(res)
 
+    def me_bipred(self, target_slot: int, target: np.ndarray, job: MeJob, hadamard: bool = True):
+        """target: int16 [h, w] block (2 * org - pred of the other list); returns (MeResult, FracResult)"""
+        blk = np.ascontiguousarray(target, np.int16)
+        ri, rf = MeResult(), FracResult()
+        self._ck(self.L.tvc_me_bipred(self.h, target_slot, ptr(blk), blk.shape[1], C.byref(job), int(hadamard), C.byref(ri), C.byref(rf)))
+        return ri, rf
+
     def me_frac_batch(self, cur_slot: int, jobs: Sequence[FracJob]):
         n = len(jobs)
         res = (FracResult * n)()
