@@ -201,7 +201,7 @@ int tvc_me_prepass(tvc_ctx* ctx, int cur_slot, int num_refs, const int* ref_slot
 int tvc_me_reserve(tvc_ctx* ctx, int num_refs);
 /* 1 when the census entry points below (tvc_me_frame, tvc_me_ctu with cfg->use_tables) read SAD tables from HBM and therefore
  * need tvc_me_prepass for the picture first (TVC_ME_FUSED=0, the round-1 form); 0 when they compute every SAD on demand from a
- * search window staged in shared memory (default; tvc_me_group.cu) and no table is ever written.                              */
+ * search window staged in shared memory (default; k_me_group) and no table is ever written.                              */
 int tvc_me_uses_tables(tvc_ctx* ctx);
 /* choose the form per context: 1 group search, 0 SAD tables, -1 back to the environment's choice */
 int tvc_me_set_fused(tvc_ctx* ctx, int on);
@@ -310,6 +310,12 @@ typedef struct {
  * int_out / frac_out: host arrays of num_refs * num_ctus * TVC_ME_CENSUS entries (either may be NULL). */
 int tvc_me_frame(tvc_ctx* ctx, int cur_slot, int num_refs, const int* ref_slots, const tvc_me_center* pred_qpel,
                  const tvc_me_frame_cfg* cfg, tvc_me_result* int_out, tvc_frac_result* frac_out);
+/* the same, both stages, with each job's result in 16 bytes instead of 40 (what TEncSearch::xMotionEstimation consumes: the integer
+ * vector with its ruiSAD, the two refinement offsets and the final ruiCost).  A census PU outside the picture has sad == cost ==
+ * 0xFFFFFFFF.  cfg->do_frac must be set.  At 1080p x 4 references: 19 MB back instead of 48 MB.                                   */
+typedef struct { int16_t mvx, mvy; int8_t halfx, halfy, qtrx, qtry; uint32_t sad; uint32_t cost; } tvc_me_packed;
+int tvc_me_frame_packed(tvc_ctx* ctx, int cur_slot, int num_refs, const int* ref_slots, const tvc_me_center* pred_qpel,
+                        const tvc_me_frame_cfg* cfg, tvc_me_packed* out);
 /* asynchronous, results stay on the device (pred_qpel is still a HOST array: it is tiny)         */
 int tvc_me_frame_dev(tvc_ctx* ctx, int cur_slot, int num_refs, const int* ref_slots, const tvc_me_center* pred_qpel,
                      const tvc_me_frame_cfg* cfg, tvc_me_result** int_dev, tvc_frac_result** frac_dev);
@@ -322,11 +328,11 @@ int tvc_me_frame_dev(tvc_ctx* ctx, int cur_slot, int num_refs, const int* ref_sl
 int tvc_me_ctu(tvc_ctx* ctx, int cur_slot, int ref_index, int ref_slot, int ctu, tvc_me_center pred_qpel,
                const tvc_me_frame_cfg* cfg, tvc_me_result* int_out, tvc_frac_result* frac_out);
 
-/* work counters of the last tvc_me_frame[_dev] call (for roofline accounting).  Default (group search): stats[0] = candidate
- * SAD grids (64x64 absolute differences each) computed from the staged windows, stats[1] = candidate grids computed from the
- * reference plane in global memory (candidates beyond the staged window), stats[2] = lock-step rounds summed over the groups.
- * TVC_ME_FUSED=0 (SAD tables): stats[0] = 16-byte table granules the reference-visible candidates of k_me_search required,
- * stats[1] = candidates served by the shared raster stage, stats[2] = raster candidates walked by k_me_raster.  Synchronises. */
+/* work counters of the last tvc_me_frame[_dev] call (for roofline accounting).  Default (group search): stats[0] = candidate SADs
+ * the searches evaluated (the reference's own count: sum of n_sads), stats[1] = sample differences of those (w x (h >> iSubShift)
+ * per candidate), stats[2] = 0.  TVC_ME_FUSED=0 (SAD tables): stats[0] = 16-byte table granules the reference-visible candidates of
+ * k_me_search required, stats[1] = candidates served by the shared raster stage, stats[2] = raster candidates walked by
+ * k_me_raster.  Synchronises.                                                                                                */
 int tvc_me_frame_stats(tvc_ctx* ctx, uint64_t stats[3]);
 
 /* ---------------------------------------------------------------------------------- transform / quant
@@ -440,6 +446,11 @@ int tvc_fwd_rdoq_batch(tvc_ctx* ctx, int resi_slot, int n, const tvc_tu* tus, co
 int tvc_fwd_rdoq_recon_batch(tvc_ctx* ctx, int resi_slot, int inv_resi_slot, int pred_slot, int recon_slot, int n, const tvc_tu* tus,
                              const tvc_rdoq_tu* rdoq_tus, int n_est, const tvc_est_bits* est, const tvc_quant_cfg* qc, int32_t* levels,
                              size_t coef_elems, uint32_t* abs_sum);
+/* the same with the levels returned as int16 (what CABAC codes fits 16 bits: TComTrQuant.cpp:1298 clips to [-32768, 32767]): half
+ * the bytes of a picture's largest device-to-host transfer.  A level beyond 16 bits is an error (TVC_ERR_ARG); no ARL output. */
+int tvc_fwd_rdoq_recon_batch16(tvc_ctx* ctx, int resi_slot, int inv_resi_slot, int pred_slot, int recon_slot, int n, const tvc_tu* tus,
+                               const tvc_rdoq_tu* rdoq_tus, int n_est, const tvc_est_bits* est, const tvc_quant_cfg* qc,
+                               int16_t* levels16, size_t coef_elems, uint32_t* abs_sum);
 /* drop-in for one xRateDistOptQuant call on host blocks (w x w, raster)                          */
 int tvc_xRateDistOptQuant(tvc_ctx* ctx, const int32_t* coef, int32_t* qcoef, int32_t* arl, int w, int is_luma,
                           int scan_idx, int qp_per, int qp_rem, int cbf_ctx, int sign_hide, int use_arl,

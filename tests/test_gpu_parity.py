@@ -620,6 +620,28 @@ def test_me_group_search_hard_content(ctx8, orc, kind):
     assert checked > 40
 
 
+def test_me_frame_packed(ctx8, orc):
+    """tvc_me_frame_packed: the 16-byte records hold exactly what tvc_me_frame returns in 40 bytes (minus cost_half / n_sads)"""
+    t = ctx8
+    seq = synth.make_sequence(W, H, 2)
+    t.upload(0, synth.to_hostpic(seq[1], W, H)); t.upload(1, synth.to_hostpic(seq[0], W, H))
+    nctu = t.ctus_x * t.ctus_y
+    pred = np.random.default_rng(66).integers(-30, 31, (1, nctu, 2)).astype(np.int32)
+    lc = orc.orc_lambda_motion_sad(50.0)
+    ires, fres = t.me_frame(0, [1], pred, lc)
+    from thevc_b200.capi import MeFrameCfg, ptr
+    out = np.zeros((1, nctu, 593), capi.ME_PACKED_DTYPE)
+    refs = (C.c_int * 1)(1)
+    cfg = MeFrameCfg(64, 1, 1, 1, 1, lc)
+    rc_ = t.L.tvc_me_frame_packed(t.h, 0, 1, refs, ptr(pred), C.byref(cfg), ptr(out))
+    assert rc_ == 0, t.L.tvc_last_error(t.h)
+    ok = ires["n_sads"] > 0
+    assert ok.sum() > 5000 and (~ok).sum() > 0
+    for name, src in (("mvx", ires), ("mvy", ires), ("sad", ires), ("halfx", fres), ("halfy", fres), ("qtrx", fres), ("qtry", fres), ("cost", fres)):
+        assert np.array_equal(out[name][ok].astype(np.int64), src[name][ok].astype(np.int64)), name
+    assert np.all(out["sad"][~ok] == 0xFFFFFFFF) and np.all(out["cost"][~ok] == 0xFFFFFFFF)
+
+
 def test_me_ctu_group(ctx8_form, orc):
     """tvc_me_ctu: one (CTU, reference) census group with an explicit predictor.  The frame pre-pass run with that
     predictor for the CTU gives the same 593 results (itself oracle-checked above); predictors different from the one the

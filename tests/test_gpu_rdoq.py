@@ -257,6 +257,14 @@ def test_fwd_rdoq_recon_round_trip(orc):
                 pa, pb = (a.y, a.u, a.v)[tu.plane], (b.y, b.u, b.v)[tu.plane]
                 assert np.array_equal(pa[tu.y:tu.y + n, tu.x:tu.x + n], pb[tu.y:tu.y + n, tu.x:tu.x + n])
         assert np.count_nonzero(lev) > 1000
+        # the 16-bit form: same levels as int16, same sums, same reconstruction
+        lev16 = np.zeros(off, np.int16); sums3 = np.zeros(len(tus), np.uint32)
+        rcode = t.L.tvc_fwd_rdoq_recon_batch16(t.h, 0, 4, 1, 5, len(tus), C.cast(ta, C.c_void_p), C.cast(ra, C.c_void_p), 1, C.byref(e), C.byref(qc),
+                                               ptr(lev16), off, ptr(sums3))
+        assert rcode == 0, t.L.tvc_last_error(t.h)
+        assert np.array_equal(lev16.astype(np.int32), lev) and np.array_equal(sums3, sums)
+        c_rec = t.download(5, with_margin=False)
+        assert np.array_equal(c_rec.y, b_rec.y) and np.array_equal(c_rec.u, b_rec.u)
     finally:
         t.close()
 

@@ -89,7 +89,7 @@ def test_bitstream_md5_identical_to_reference(tmp_path, cfg, frames, extra):
         assert bl, r.stderr[-800:]
         print(bl[-1])
         f = bl[-1].split()
-        assert int(f[3]) > 100 and int(f[6]) == int(f[3]) and int(f[15]) == 0, bl[-1]
+        assert int(f[3]) > 100 and int(f[6]) == int(f[3]) and int(f[13]) == 0, bl[-1]
     served = [ln for ln in r.stderr.splitlines() if ln.startswith("TLibCuda:")]
     assert served and "kernel launches" in served[-1], r.stderr[-500:]
     print(served[-1])

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libthevc_cuda.so")
-SOURCES = ["tvc_ctx.cu", "tvc_dist.cu", "tvc_interp.cu", "tvc_tq.cu", "tvc_rdoq.cu", "tvc_deblock.cu", "tvc_intra.cu", "tvc_hash.cu", "tvc_me.cu", "tvc_me_group.cu"]
+SOURCES = ["tvc_ctx.cu", "tvc_dist.cu", "tvc_interp.cu", "tvc_tq.cu", "tvc_rdoq.cu", "tvc_deblock.cu", "tvc_intra.cu", "tvc_hash.cu", "tvc_me.cu"]
 HEADERS = ["tvc_internal.cuh", "tvc_interp.cuh", "tvc_dist.cuh", "tvc_me.cuh", os.path.join("..", "..", "include", "thevc_cuda.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]

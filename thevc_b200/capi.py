@@ -82,6 +82,7 @@ PHASES = ("me_tables", "me_search", "me_frac", "mc", "fwd_tq", "inv_tq", "other"
 
 # numpy views of the ABI structs (same layout) for bulk results
 ME_RESULT_DTYPE = np.dtype([("mvx", "<i4"), ("mvy", "<i4"), ("sad", "<u4"), ("n_sads", "<u4")])
+ME_PACKED_DTYPE = np.dtype([("mvx", "<i2"), ("mvy", "<i2"), ("halfx", "i1"), ("halfy", "i1"), ("qtrx", "i1"), ("qtry", "i1"), ("sad", "<u4"), ("cost", "<u4")])
 INTRA_MODES = 35
 GRID_WORDS = 289 + 289 + 81
 GRID_JOB_DTYPE = np.dtype([("ref_slot", "<i4"), ("x0", "<i4"), ("y0", "<i4"), ("mvx", "<i4"), ("mvy", "<i4")])
@@ -146,6 +147,7 @@ SIGNATURES = {
     "tvc_me_prepass": (ci, [vp, ci, ci, vp, vp]),
     "tvc_me_reserve": (ci, [vp, ci]),
     "tvc_me_uses_tables": (ci, [vp]),
+    "tvc_me_frame_packed": (ci, [vp, ci, ci, vp, vp, C.POINTER(MeFrameCfg), vp]),
     "tvc_me_bipred": (ci, [vp, ci, vp, ci, vp, ci, vp, vp]),
     "tvc_me_set_fused": (ci, [vp, ci]),
     "tvc_me_table_bytes": (C.c_size_t, [vp, ci]),
@@ -170,6 +172,7 @@ SIGNATURES = {
     "tvc_fwd_transform_batch_dev": (ci, [vp, ci, ci, vp, vp, vp]),
     "tvc_fwd_rdoq_batch": (ci, [vp, ci, ci, vp, vp, ci, vp, C.POINTER(QuantCfg), vp, vp, C.c_size_t, vp]),
     "tvc_fwd_rdoq_recon_batch": (ci, [vp, ci, ci, ci, ci, ci, vp, vp, ci, vp, C.POINTER(QuantCfg), vp, C.c_size_t, vp]),
+    "tvc_fwd_rdoq_recon_batch16": (ci, [vp, ci, ci, ci, ci, ci, vp, vp, ci, vp, C.POINTER(QuantCfg), vp, C.c_size_t, vp]),
     "tvc_xRateDistOptQuant": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, C.c_double, vp, C.POINTER(u32)]),
     "tvc_xT": (ci, [vp, ci, vp, ci, vp, ci, ci]),
     "tvc_xIT": (ci, [vp, ci, vp, vp, ci, ci, ci]),

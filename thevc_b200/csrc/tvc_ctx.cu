@@ -233,11 +233,9 @@ void tvc_ctx_destroy(tvc_ctx* c)
   if (c->fr_frac) cudaFree(c->fr_frac);
   if (c->fr_rast) cudaFree(c->fr_rast);
   if (c->fr_sweep) cudaFree(c->fr_sweep);
-  if (c->grp_census) cudaFree(c->grp_census);
+  if (c->fr_packed) cudaFree(c->fr_packed);
   if (c->bi_buf) cudaFree(c->bi_buf);
   if (c->bi_host) cudaFreeHost(c->bi_host);
-  if (c->grp_fb_list) cudaFree(c->grp_fb_list);
-  if (c->grp_fb_count) cudaFree(c->grp_fb_count);
   if (c->fr_stats) cudaFree(c->fr_stats);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;

@@ -80,14 +80,11 @@ struct tvc_ctx {
   void* fr_sweep = nullptr;       // shared first-sweep results (SweepState per job)
   unsigned long long* fr_stats = nullptr;   // device: 3 work counters (tvc_me_frame_stats)
   size_t fr_cap = 0;              // entries
-  // group search (tvc_me_group.cu): sweep-offset table, census, list of the PUs handed back to the per-PU kernel
+  void* fr_packed = nullptr;      // tvc_me_frame_packed: 16-byte results (device)
+  size_t fr_packed_cap = 0;
   void* bi_buf = nullptr;         // tvc_me_bipred: job / results of one refinement search (device) and its pinned staging
   void* bi_host = nullptr;
   int me_fused = -1;              // -1: TVC_ME_FUSED (default on), 0 / 1: set by tvc_me_set_fused
-  void* grp_census = nullptr;
-  int* grp_fb_list = nullptr;
-  int* grp_fb_count = nullptr;
-  size_t grp_fb_cap = 0;
   // dedicated pinned staging of the asynchronous ME entry points (an event guards host reuse)
   tvc::Scratch me_stage, fr_stage;
   cudaEvent_t me_ev = nullptr, fr_ev = nullptr;
@@ -172,7 +169,7 @@ int launch_inv(tvc_ctx* c, int resi_slot, int pred_slot, int recon_slot, const i
                const int32_t* levels_dev, int dequant);                                                          // tvc_tq.cu
 
 }  // namespace tvc
-// group search over census groups ([group][593] jobs) and the per-PU kernel over a device-resident job list (tvc_me_group.cu / tvc_me.cu)
+// group search over census groups ([group][593] jobs) and the per-PU kernel over a device-resident job list (tvc_me.cu)
 int tvc_launch_me_group(tvc_ctx* c, int cur_slot, int ngroups, const tvc_me_job* jobs_dev, tvc_me_result* out_dev, int num_refs,
                         const int* ref_slots, int ref_index_fixed, unsigned long long* stats);
 int tvc_launch_me_search_list(tvc_ctx* c, int cur_slot, const int* list_dev, const int* count_dev, const tvc_me_job* jobs_dev,

@@ -274,6 +274,14 @@ __constant__ tvc_census_pu c_census[TVC_ME_CENSUS];     // partition census of a
 #endif
 constexpr int kSearchRowUnroll = TVC_SEARCH_ROW_UNROLL;
 
+// the staged search window of a (CTU, reference) group (k_me_group)
+struct GrpWin {
+  const uint8_t* win;           // shared memory: 208 x 192 u8, window of +-64 around (cenx, ceny), e16 bytes of alignment slack on the left
+  const uint8_t* cur;           // shared memory: the CTU, pitch kGrpCurP
+  const uint8_t* plane8;        // the reference's u8 luma plane, pel (0,0)
+  int pitch8, cenx, ceny, e16, x0, y0;
+};
+
 struct SearchCtx {
   // SAD sources
   const uint16_t* tbl;      // table of (ref, ctu) or nullptr
@@ -282,6 +290,11 @@ struct SearchCtx {
   uint32_t m01[4], m23[4];  // per touched quarter: packed-u16 masks of the blocks inside the PU
   const int16_t* org; int so;
   const int16_t* ref; int rs;   // co-located pel of the PU in the reference plane
+  // group search (k_me_group): u8 search window + CTU staged in shared memory, SADs computed per lane on demand
+  const uint8_t* win8;          // nullptr: not in this mode.  Else: window byte of the PU's top-left at candidate (wcx, wcy) - (64, 64)
+  const uint8_t* cur8;          // the PU's top-left in the staged CTU (pitch kGrpCurP)
+  const uint8_t* gref8;         // co-located byte of the PU in the reference's u8 plane (candidates beyond the window)
+  int gpitch8, wcx, wcy;
   int w, h, sub, bi;
   uint32_t lc; int px, py;
   int lx, ty, rx, by;
@@ -305,6 +318,32 @@ __device__ __noinline__ uint32_t direct_sad_warp(const int16_t* __restrict__ org
   return warp_sum_u32(acc);
 }
 
+constexpr int kGrpWinW = 208, kGrpWinH = 192, kGrpCurP = 80;
+
+// SAD of one candidate by ONE lane, 8-bit samples packed four to a word: the reference row is read as aligned words and shifted
+// into place (the candidate's byte alignment differs from lane to lane), VABSDIFF4 accumulates four absolute differences per
+// instruction.  rows = h >> sub rows at a row step of 1 << sub (TEncSearch.cpp:324-330); xGetSAD* of TComRdCost.cpp:518-989.
+__device__ __forceinline__ uint32_t sad_u8_lane(const uint8_t* __restrict__ ref, int rpitch, const uint8_t* __restrict__ cur, int w4, int rows,
+                                                int sub)
+{
+  const int a = (int)((uintptr_t)ref & 3), sh = a * 8;
+  const uint32_t* rb = reinterpret_cast<const uint32_t*>(ref - a);
+  const uint32_t* cb = reinterpret_cast<const uint32_t*>(cur);
+  const int rstride = (rpitch << sub) >> 2, cstride = (kGrpCurP << sub) >> 2;
+  uint32_t acc = 0;
+  for (int r = 0; r < rows; r++) {
+    uint32_t prev = rb[0];
+#pragma unroll 4
+    for (int j = 0; j < w4; j++) {
+      const uint32_t nxt = rb[j + 1];
+      acc = vsad4_acc(cb[j], __funnelshift_r(prev, nxt, sh), acc);
+      prev = nxt;
+    }
+    rb += rstride; cb += cstride;
+  }
+  return acc;
+}
+
 // cost (SAD + MV rate at scale 2) of this lane's K candidates; kNoCost for slots without one.  The K
 // table sums run interleaved so that K * granules independent 16-byte loads are in flight per lane.
 // Warp-collective: every lane must call it.
@@ -312,6 +351,24 @@ template <int K>
 __device__ __forceinline__ void eval_multi(const SearchCtx& s, const bool (&valid)[K], const int (&x)[K], const int (&y)[K],
                                            uint32_t (&cost)[K])
 {
+  if (s.win8) {
+    // group search: every lane computes the SAD of its own candidates from the staged window (or, beyond it, from the u8 plane)
+    const int w4 = s.w >> 2, rows = s.h >> s.sub;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      cost[k] = kNoCost;
+      if (valid[k]) {
+        const int dx = x[k] - s.wcx, dy = y[k] - s.wcy;
+        uint32_t sad;
+        if (dx >= -kMeR && dx <= kMeR && dy >= -kMeR && dy <= kMeR)
+          sad = sad_u8_lane(s.win8 + (dy + kMeR) * kGrpWinW + dx + kMeR, kGrpWinW, s.cur8, w4, rows, s.sub);
+        else
+          sad = sad_u8_lane(s.gref8 + (ptrdiff_t)y[k] * s.gpitch8 + x[k], s.gpitch8, s.cur8, w4, rows, s.sub);
+        cost[k] = (sad << s.sub) + mv_cost(s.lc, x[k], y[k], 2, s.px, s.py);
+      }
+    }
+    return;
+  }
   uint32_t sad[K];
   bool tab[K], direct[K];
   uint32_t base[K];             // granule index inside this (ref, CTU) table (1.06 M granules: fits 32 bits)
@@ -385,9 +442,59 @@ __device__ __forceinline__ void eval_multi(const SearchCtx& s, const bool (&vali
 // first_search: the reference stops when three consecutive rounds brought no improvement
 // (bFirstSearchStop, uiFirstSearchRounds = 3; TEncSearch.cpp:4346-4361): candidates of later rounds were
 // evaluated speculatively and are neither counted nor used; returns true when stopped.
+// First search of the group kernel, in two stages.  There a SAD is real arithmetic (not a table read), and the reference usually
+// stops after three or four rounds (bFirstSearchStop): rounds d = 1 .. 8 (28 candidates, one per lane) are evaluated and replayed
+// first, rounds d = 16 .. 64 (48 candidates, two per lane) only when the search is still running.  Same visiting order, same
+// strict-'<' replay, same count as the one-shot form.
+template <int K>
+__device__ __forceinline__ bool sweep_stage(SearchCtx& s, int sx, int sy, int c0, int dfirst, int dlast, int dmax)
+{
+  bool valid[K];
+  int x[K], y[K];
+  uint32_t cost[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const int c = c0 + s.lane + 32 * k;
+    int d, i, pt;
+    uint32_t dist;
+    valid[k] = false; x[k] = 0; y[k] = 0;
+    if (sweep_slot(c, dmax, d, i) && d >= dfirst && d <= dlast) valid[k] = diamond_cand(s, sx, sy, d, i, x[k], y[k], pt, dist);
+  }
+  eval_multi<K>(s, valid, x, y, cost);
+  int off = c0;
+  for (int d = dfirst; d <= dlast && d <= dmax; d <<= 1) {
+    const int sz = round_size(d);
+    uint32_t c = kNoCost;
+    unsigned pos = 0xffu;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const int ci = c0 + s.lane + 32 * k;
+      if (ci >= off && ci < off + sz) { c = cost[k]; pos = (unsigned)(ci - off); }
+    }
+    s.best_round += 1;
+    s.n_sads += __popc(__ballot_sync(0xffffffffu, c != kNoCost));
+    const uint32_t mn = __reduce_min_sync(0xffffffffu, c);
+    if (mn < s.best_sad) {
+      const int i = (int)__reduce_min_sync(0xffffffffu, c == mn ? pos : 0xffu);
+      int bx, by, pt;
+      uint32_t dist;
+      diamond_cand(s, sx, sy, d, i, bx, by, pt, dist);
+      s.best_sad = mn; s.best_x = bx; s.best_y = by; s.best_dist = dist; s.point_nr = pt; s.best_round = 0;
+    }
+    if (s.best_round >= 3) return true;
+    off += sz;
+  }
+  return false;
+}
+
 template <int K>
 __device__ __forceinline__ bool diamond_sweep(SearchCtx& s, int sx, int sy, int d0, int dmax, bool first_search)
 {
+  if (first_search && s.win8) {
+    if (sweep_stage<1>(s, sx, sy, 0, 1, 8, dmax)) return true;
+    if (dmax < 16) return false;
+    return sweep_stage<2>(s, sx, sy, 28, 16, 64, dmax);
+  }
   bool valid[K];
   int x[K], y[K];
   uint32_t cost[K];
@@ -735,7 +842,7 @@ __device__ __forceinline__ void me_search_job(int j, const PlaneTable& pt, int c
                                               tvc_me_result* __restrict__ out, const uint16_t* __restrict__ tables,
                                               const tvc_me_center* __restrict__ centers, int num_ctus, int ctus_x, int bi,
                                               const RasterBest* __restrict__ rast, const SweepState* __restrict__ sweep,
-                                              unsigned long long* __restrict__ stats)
+                                              unsigned long long* __restrict__ stats, const GrpWin* gw = nullptr)
 {
   const tvc_me_job jb = jobs[j];
   if (jb.w <= 0) {                       // census PU outside the picture (frame pre-pass)
@@ -752,6 +859,14 @@ __device__ __forceinline__ void me_search_job(int j, const PlaneTable& pt, int c
   s.lc = jb.lambda_cost; s.px = jb.predx; s.py = jb.predy;
   s.lx = jb.lx; s.ty = jb.ty; s.rx = jb.rx; s.by = jb.by;
   s.tbl = nullptr; s.tcx = 0; s.tcy = 0;
+  s.win8 = nullptr; s.cur8 = nullptr; s.gref8 = nullptr; s.gpitch8 = 0; s.wcx = 0; s.wcy = 0;
+  if (gw) {
+    const int px = jb.x - gw->x0, py = jb.y - gw->y0;        // the PU inside its CTU
+    s.win8 = gw->win + py * kGrpWinW + px + gw->e16;
+    s.cur8 = gw->cur + py * kGrpCurP + px;
+    s.gref8 = gw->plane8 + (ptrdiff_t)jb.y * gw->pitch8 + jb.x;
+    s.gpitch8 = gw->pitch8; s.wcx = gw->cenx; s.wcy = gw->ceny;
+  }
   int ctu = (jb.y >> 6) * ctus_x + (jb.x >> 6);
   if (tables) {
     s.tbl = tables + ((size_t)jb.ref_index * num_ctus + ctu) * kMeCtuElems;
@@ -844,7 +959,10 @@ __device__ __forceinline__ void me_search_job(int j, const PlaneTable& pt, int c
     r.sad = s.best_sad - mv_cost(s.lc, s.best_x, s.best_y, 2, s.px, s.py);
     r.n_sads = s.n_sads;
     out[j] = r;
-    if (stats) {
+    if (stats && gw) {
+      atomicAdd(&stats[0], (unsigned long long)s.n_sads);
+      atomicAdd(&stats[1], (unsigned long long)s.n_sads * (unsigned)(s.w * (s.h >> s.sub)));
+    } else if (stats) {
       atomicAdd(&stats[0], (unsigned long long)(s.n_sads - served) * (unsigned)(s.nby * s.nq));
       atomicAdd(&stats[1], (unsigned long long)served);
     }
@@ -871,6 +989,77 @@ k_me_search_list(PlaneTable pt, int cur_slot, const int* __restrict__ list, cons
   const int n = *count;
   for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += gridDim.x * (blockDim.x >> 5))
     me_search_job(list[i], pt, cur_slot, jobs, out, nullptr, nullptr, 0, ctus_x, bi, nullptr, nullptr, nullptr);
+}
+
+// ================================================================================ (2c) group search
+// Integer search of a whole (CTU, reference) census group by ONE CTA without SAD tables.  Round 1 wrote the full +-64 tables of
+// every (CTU, reference) to HBM (17 MB each, 34.8 GB per 1080p picture with four references) although only 18 % of the bytes
+// were ever read; here the 208 x 192 u8 search window and the 64 x 64 u8 CTU are staged into shared memory once (two TMA box
+// copies) and every SAD a search asks for is computed on the spot: warp per PU (the 593 census PUs are taken from a shared
+// counter, largest first), lane per candidate, VABSDIFF4 over words of the staged window.  The TZ control flow is the per-PU
+// kernel's (diamond_sweep / two_point / raster_scan with the ordered arg-min replay), so the results -- MV, ruiSAD, number of
+// SADs -- are those of xTZSearch; candidates beyond the staged window (the zero vector of a far predictor, PUs whose clipMv
+// differs from the CTU's at the picture border) read the reference's u8 plane in global memory through the same routine.
+struct GroupMaps {
+  CUtensorMap cur;                 // u8 luma of the current picture, box 80 x 64
+  CUtensorMap ref[8];              // u8 luma of each reference, box 208 x 192
+  const uint8_t* ref8[8];          // the same planes, pel (0,0)
+  int stride8;
+};
+constexpr int kGrpThreads = 256;
+constexpr int kGrpSmem = kGrpWinW * kGrpWinH + kGrpCurP * 64 + 64;
+
+template <int MINB>
+__global__ void __launch_bounds__(kGrpThreads, MINB)
+k_me_group(const __grid_constant__ GroupMaps maps, PlaneTable pt, int cur_slot, const tvc_me_job* __restrict__ jobs,
+           tvc_me_result* __restrict__ out, int pic_w, int pic_h, int mx, int my, int ref_index_fixed, int ctus_x,
+           unsigned long long* __restrict__ stats, int split)
+{
+  extern __shared__ __align__(128) uint8_t gsm[];
+  uint8_t* win = gsm;
+  uint8_t* cur = gsm + kGrpWinW * kGrpWinH;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(gsm + kGrpWinW * kGrpWinH + kGrpCurP * 64);
+  int* next = reinterpret_cast<int*>(bar + 1);
+  const int tid = threadIdx.x, lane = tid & 31;
+  // split > 1: `split` CTAs share one group (each stages the window and takes every split-th PU): the single-group call of
+  // tvc_me_ctu is latency-bound, one CTA would walk the 593 PUs alone
+  const int part = (int)(blockIdx.x % (unsigned)split);
+  const size_t gbase = (size_t)(blockIdx.x / (unsigned)split) * TVC_ME_CENSUS;
+  const tvc_me_job j0 = jobs[gbase];                       // the 64x64 PU sits at the CTU origin; its start is the window centre
+  const int x0 = j0.x, y0 = j0.y;
+  const int ref = ref_index_fixed >= 0 ? ref_index_fixed : j0.ref_index;
+  // window centre: the group's start point, moved so that the staged window stays inside the padded plane
+  int cenx = j0.startx, ceny = j0.starty;
+  {
+    int lo_x = -mx - x0 + kMeR, hi_x = pic_w + mx - x0 - 64 - kMeR;
+    int lo_y = -my - y0 + kMeR, hi_y = pic_h + my - y0 - 64 - kMeR;
+    if (hi_x < lo_x) hi_x = lo_x;
+    if (hi_y < lo_y) hi_y = lo_y;
+    cenx = min(hi_x, max(lo_x, cenx)); ceny = min(hi_y, max(lo_y, ceny));
+  }
+  const int wx = mx + x0 + cenx - kMeR, e16 = wx & 15;     // TMA wants a 16-byte aligned start: load from wx - e16
+  if (tid == 0) {
+    *next = 0;
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(bar, kGrpWinW * kGrpWinH + kGrpCurP * 64);
+    tma_load_2d(win, &maps.ref[ref], wx - e16, my + y0 + ceny - kMeR, bar);
+    tma_load_2d(cur, &maps.cur, mx + x0, my + y0, bar);
+  }
+  mbar_wait(bar, 0);
+  GrpWin gw;
+  gw.win = win; gw.cur = cur; gw.plane8 = maps.ref8[ref]; gw.pitch8 = maps.stride8;
+  gw.cenx = cenx; gw.ceny = ceny; gw.e16 = e16; gw.x0 = x0; gw.y0 = y0;
+  for (;;) {
+    int k = 0;
+    if (lane == 0) k = atomicAdd(next, 1);
+    k = part + split * __shfl_sync(0xffffffffu, k, 0);
+    if (k >= TVC_ME_CENSUS) break;
+    me_search_job((int)(gbase + k), pt, cur_slot, jobs, out, nullptr, nullptr, 0, ctus_x, 0, nullptr, nullptr, stats, &gw);
+  }
 }
 
 __global__ void k_me_table_lookup(const uint16_t* __restrict__ tables, const tvc_me_center* __restrict__ centers,
@@ -1329,6 +1518,21 @@ __global__ void k_me_frame_frac_jobs(int n, const tvc_me_job* __restrict__ jobs,
   fj[i] = f;
 }
 
+// integer + fractional result of a job in 16 bytes (tvc_me_packed): what TEncSearch::xMotionEstimation takes from the two stages
+__global__ void k_me_pack(int n, const tvc_me_result* __restrict__ ri, const tvc_frac_result* __restrict__ rf, tvc_me_packed* __restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const tvc_me_result a = ri[i];
+  const tvc_frac_result b = rf[i];
+  tvc_me_packed p;
+  p.mvx = (int16_t)a.mvx; p.mvy = (int16_t)a.mvy;
+  p.halfx = (int8_t)b.halfx; p.halfy = (int8_t)b.halfy; p.qtrx = (int8_t)b.qtrx; p.qtry = (int8_t)b.qtry;
+  p.sad = a.n_sads ? a.sad : 0xFFFFFFFFu;
+  p.cost = a.n_sads ? b.cost : 0xFFFFFFFFu;
+  out[i] = p;
+}
+
 // ================================================================================ micro-benchmarks
 __global__ void k_ub_vabsdiff4(uint32_t* out, int iters, uint32_t a0, uint32_t b0)
 {
@@ -1460,6 +1664,43 @@ static int launch_frac(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job* jobs
 }  // namespace tvc
 
 using namespace tvc;
+
+// group kernel over `ngroups` census groups (jobs laid out [group][593]).  ref_index_fixed >= 0: every group searches
+// maps.ref[ref_index_fixed] (tvc_me_ctu), else the group's own job.ref_index.
+int tvc_launch_me_group(tvc_ctx* c, int cur_slot, int ngroups, const tvc_me_job* jobs_dev, tvc_me_result* out_dev, int num_refs,
+                        const int* ref_slots, int ref_index_fixed, unsigned long long* stats)
+{
+  if (!c->pics[cur_slot].has_tmap || c->cfg.bit_depth != 8) return set_err(c, TVC_ERR_STATE, "group search: needs the 8-bit u8 planes and tensor maps");
+  static int minb = -1;          // tuning knob: resident CTAs per SM the kernel is compiled for (2: 128 registers, no spill; 3: 80)
+  if (minb < 0) {
+    const char* e = getenv("TVC_GROUP_MINB");
+    minb = e ? atoi(e) : 2;
+    TVC_CUDA(c, cudaFuncSetAttribute(k_me_group<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGrpSmem));
+    TVC_CUDA(c, cudaFuncSetAttribute(k_me_group<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGrpSmem));
+  }
+  GroupMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const Pic& p = c->pics[cur_slot];
+  maps.cur = p.tmap_cur80;
+  for (int r = 0; r < num_refs && r < 8; r++) {
+    const Pic& rp = c->pics[ref_slots[r]];
+    if (!rp.has_tmap) return set_err(c, TVC_ERR_ARG, "group search: reference slot without tensor map");
+    maps.ref[r] = rp.tmap_ref;
+    maps.ref8[r] = rp.org8;
+  }
+  maps.stride8 = p.stride8;
+  ProfScope ps(c, TVC_PH_ME_SEARCH);
+  // few groups (tvc_me_ctu: one): spread each over several CTAs so that the call fills the machine
+  const int split = ngroups >= 2 * kNumSM ? 1 : (ngroups >= kNumSM / 4 ? 4 : 24);
+  if (minb >= 3)
+    k_me_group<3><<<ngroups * split, kGrpThreads, kGrpSmem, c->stream>>>(maps, c->planes, cur_slot, jobs_dev, out_dev, c->cfg.width, c->cfg.height,
+                                                                         p.mx[0], p.my[0], ref_index_fixed, c->num_ctus_x, stats, split);
+  else
+    k_me_group<2><<<ngroups * split, kGrpThreads, kGrpSmem, c->stream>>>(maps, c->planes, cur_slot, jobs_dev, out_dev, c->cfg.width, c->cfg.height,
+                                                                         p.mx[0], p.my[0], ref_index_fixed, c->num_ctus_x, stats, split);
+  TVC_LAUNCH_CHECK(c);
+  return TVC_OK;
+}
 
 int tvc_launch_me_search_list(tvc_ctx* c, int cur_slot, const int* list_dev, const int* count_dev, const tvc_me_job* jobs_dev,
                               tvc_me_result* out_dev)
@@ -1997,6 +2238,28 @@ int tvc_me_frame(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slots, c
   if (frac_out && df) TVC_CUDA(c, cudaMemcpyAsync(frac_out, df, n * sizeof(tvc_frac_result), cudaMemcpyDeviceToHost, c->stream));
   TVC_CUDA(c, cudaStreamSynchronize(c->stream));
   if (side) TVC_CUDA(c, cudaStreamSynchronize(c->pipe[0]));
+  return TVC_OK;
+}
+
+int tvc_me_frame_packed(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_slots, const tvc_me_center* pred_qpel,
+                        const tvc_me_frame_cfg* cfg, tvc_me_packed* out)
+{
+  if (!c || !cfg || !cfg->do_frac || !out) return set_err(c, TVC_ERR_ARG, "tvc_me_frame_packed: needs both stages (cfg->do_frac) and an output array");
+  tvc_me_result* di = nullptr;
+  tvc_frac_result* df = nullptr;
+  int r = tvc_me_frame_dev(c, cur_slot, num_refs, ref_slots, pred_qpel, cfg, &di, &df);
+  if (r) return r;
+  const size_t n = (size_t)num_refs * c->num_ctus_x * c->num_ctus_y * TVC_ME_CENSUS;
+  if (n > c->fr_packed_cap) {
+    if (c->fr_packed) cudaFree(c->fr_packed);
+    c->fr_packed = nullptr; c->fr_packed_cap = 0;
+    TVC_CUDA(c, cudaMalloc(&c->fr_packed, n * sizeof(tvc_me_packed)));
+    c->fr_packed_cap = n;
+  }
+  k_me_pack<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((int)n, di, df, (tvc_me_packed*)c->fr_packed);
+  TVC_LAUNCH_CHECK(c);
+  TVC_CUDA(c, cudaMemcpyAsync(out, c->fr_packed, n * sizeof(tvc_me_packed), cudaMemcpyDeviceToHost, c->stream));
+  TVC_CUDA(c, cudaStreamSynchronize(c->stream));
   return TVC_OK;
 }
 

@@ -603,7 +603,7 @@ int tvc_rdoq_batch(tvc_ctx* c, int n, const tvc_rdoq_tu* tus, int n_est, const t
                abs_b = up((size_t)n * 4);
   const bool want_arl = qc->use_arl != 0;
   if ((r = ensure_scratch(c, c->in, tu_b + est_b + coef_b))) return r;
-  if ((r = ensure_scratch(c, c->out, 2 * coef_b + abs_b))) return r;
+  if ((r = ensure_scratch(c, c->out, 2 * coef_b + abs_b + 512))) return r;
   char* hi = (char*)c->in.host;
   memcpy(hi, tus, (size_t)n * sizeof(tvc_rdoq_tu));
   memcpy(hi + tu_b, est, (size_t)n_est * sizeof(tvc_est_bits));
@@ -630,12 +630,37 @@ int tvc_rdoq_batch(tvc_ctx* c, int n, const tvc_rdoq_tu* tus, int n_est, const t
 
 static int fwd_rdoq_host(tvc_ctx* c, int resi_slot, int n, const tvc_tu* tus, const tvc_rdoq_tu* rtus, int n_est, const tvc_est_bits* est,
                          const tvc_quant_cfg* qc, int32_t* levels, int32_t* arl, size_t coef_elems, uint32_t* abs_sum, int inv_resi_slot,
-                         int pred_slot, int recon_slot);
+                         int pred_slot, int recon_slot, int16_t* levels16 = nullptr);
+
+__global__ void k_levels_to_i16(const int32_t* __restrict__ src, int16_t* __restrict__ dst, size_t n, int* __restrict__ overflow)
+{
+  // two levels per thread and step: 8-byte loads, 4-byte stores
+  const size_t n2 = n >> 1, stride = (size_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+    const int2 v = reinterpret_cast<const int2*>(src)[i];
+    bad |= v.x < -32768 || v.x > 32767 || v.y < -32768 || v.y > 32767;
+    reinterpret_cast<uint32_t*>(dst)[i] = ((uint32_t)v.x & 0xffffu) | ((uint32_t)v.y << 16);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) { const int v = src[n - 1]; bad |= v < -32768 || v > 32767; dst[n - 1] = (int16_t)v; }
+  if (bad) atomicOr(overflow, 1);
+}
 
 int tvc_fwd_rdoq_batch(tvc_ctx* c, int resi_slot, int n, const tvc_tu* tus, const tvc_rdoq_tu* rtus, int n_est, const tvc_est_bits* est,
                        const tvc_quant_cfg* qc, int32_t* levels, int32_t* arl, size_t coef_elems, uint32_t* abs_sum)
 {
   return fwd_rdoq_host(c, resi_slot, n, tus, rtus, n_est, est, qc, levels, arl, coef_elems, abs_sum, -1, -1, -1);
+}
+
+int tvc_fwd_rdoq_recon_batch16(tvc_ctx* c, int resi_slot, int inv_resi_slot, int pred_slot, int recon_slot, int n, const tvc_tu* tus,
+                               const tvc_rdoq_tu* rtus, int n_est, const tvc_est_bits* est, const tvc_quant_cfg* qc, int16_t* levels16,
+                               size_t coef_elems, uint32_t* abs_sum)
+{
+  if (!c || !valid_slot(c, inv_resi_slot) || !valid_slot(c, pred_slot) || !valid_slot(c, recon_slot) || !levels16)
+    return set_err(c, TVC_ERR_ARG, "tvc_fwd_rdoq_recon_batch16: bad argument");
+  if (qc && qc->use_arl) return set_err(c, TVC_ERR_ARG, "tvc_fwd_rdoq_recon_batch16: no ARL output in the 16-bit form");
+  return fwd_rdoq_host(c, resi_slot, n, tus, rtus, n_est, est, qc, (int32_t*)levels16, nullptr, coef_elems, abs_sum, inv_resi_slot, pred_slot,
+                       recon_slot, levels16);
 }
 
 int tvc_fwd_rdoq_recon_batch(tvc_ctx* c, int resi_slot, int inv_resi_slot, int pred_slot, int recon_slot, int n, const tvc_tu* tus,
@@ -649,7 +674,7 @@ int tvc_fwd_rdoq_recon_batch(tvc_ctx* c, int resi_slot, int inv_resi_slot, int p
 
 static int fwd_rdoq_host(tvc_ctx* c, int resi_slot, int n, const tvc_tu* tus, const tvc_rdoq_tu* rtus, int n_est, const tvc_est_bits* est,
                          const tvc_quant_cfg* qc, int32_t* levels, int32_t* arl, size_t coef_elems, uint32_t* abs_sum, int inv_resi_slot,
-                         int pred_slot, int recon_slot)
+                         int pred_slot, int recon_slot, int16_t* levels16)
 {
   if (!c || !valid_slot(c, resi_slot) || n < 0 || !qc || (n && (!tus || !rtus || !est || !levels || n_est < 1)) || (qc && qc->use_arl && n && !arl))
     return set_err(c, TVC_ERR_ARG, "tvc_fwd_rdoq_batch: bad argument");
@@ -694,6 +719,29 @@ static int fwd_rdoq_host(tvc_ctx* c, int resi_slot, int n, const tvc_tu* tus, co
     return r;
   // round trip: dequant + inverse transform + reconstruction from the levels where they are
   if (inv_resi_slot >= 0 && (r = launch_inv(c, inv_resi_slot, pred_slot, recon_slot, counts, (const tvc_tu*)di, (const int32_t*)dout, 1))) return r;
+  if (levels16) {
+    // the levels are what CABAC codes: 16-bit values (TComTrQuant clips them to [-32768, 32767], TComTrQuant.cpp:1298); they go back
+    // as int16 -- half the bytes of the largest device-to-host transfer of a picture.  A level beyond 16 bits raises an error.
+    int16_t* d16 = (int16_t*)(dout + coef_b + abs_b);              // the ARL area is unused in this form
+    int* d_flag = (int*)(dout + coef_b + abs_b + up(coef_elems * 2));
+    TVC_CUDA(c, cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream));
+    k_levels_to_i16<<<kNumSM * 8, 256, 0, c->stream>>>((const int32_t*)dout, d16, coef_elems, d_flag);
+    TVC_LAUNCH_CHECK(c);
+    int* h_flag = (int*)((char*)c->out.host + coef_b + abs_b + up(coef_elems * 2));
+    TVC_CUDA(c, cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (is_pinned(levels16) && (!abs_sum || is_pinned(abs_sum))) {
+      TVC_CUDA(c, cudaMemcpyAsync(levels16, d16, coef_elems * 2, cudaMemcpyDeviceToHost, c->stream));
+      if (abs_sum) TVC_CUDA(c, cudaMemcpyAsync(abs_sum, dout + coef_b, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+      TVC_CUDA(c, cudaStreamSynchronize(c->stream));
+    } else {
+      TVC_CUDA(c, cudaMemcpyAsync((char*)c->out.host + coef_b, dout + coef_b, abs_b + coef_elems * 2, cudaMemcpyDeviceToHost, c->stream));
+      TVC_CUDA(c, cudaStreamSynchronize(c->stream));
+      memcpy(levels16, (char*)c->out.host + coef_b + abs_b, coef_elems * 2);
+      if (abs_sum) memcpy(abs_sum, (char*)c->out.host + coef_b, (size_t)n * 4);
+    }
+    if (*h_flag) return set_err(c, TVC_ERR_ARG, "tvc_fwd_rdoq_recon_batch16: a level does not fit 16 bits (use the 32-bit form)");
+    return TVC_OK;
+  }
   const bool pin_out = is_pinned(levels) && (!want_arl || is_pinned(arl)) && (!abs_sum || is_pinned(abs_sum));
   if (pin_out) {
     TVC_CUDA(c, cudaMemcpyAsync(levels, dout, coef_elems * 4, cudaMemcpyDeviceToHost, c->stream));
