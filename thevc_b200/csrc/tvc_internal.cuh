@@ -80,6 +80,8 @@ struct tvc_ctx {
   void* fr_sweep = nullptr;       // shared first-sweep results (SweepState per job)
   unsigned long long* fr_stats = nullptr;   // device: 3 work counters (tvc_me_frame_stats)
   size_t fr_cap = 0;              // entries
+  void* frac_done = nullptr;      // per census job: served by the CU-level fractional kernel (device)
+  size_t frac_done_cap = 0;
   void* fr_packed = nullptr;      // tvc_me_frame_packed: 16-byte results (device)
   size_t fr_packed_cap = 0;
   void* bi_buf = nullptr;         // tvc_me_bipred: job / results of one refinement search (device) and its pinned staging

@@ -1298,7 +1298,7 @@ __device__ __forceinline__ void frac_unit(const int16_t* __restrict__ H, int pla
 template <int MAXW, int MAXH, int NT, int JPC>
 __global__ void __launch_bounds__(NT * JPC)
 k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ jobs, tvc_frac_result* __restrict__ out, int bd,
-          int span, int stride, int first)
+          int span, int stride, int first, const uint8_t* __restrict__ done)
 {
   using SM = FracSmem<MAXW, MAXH>;
   extern __shared__ __align__(16) uint8_t fsm[];
@@ -1310,9 +1310,10 @@ k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ j
   const int ji = have ? (b / span) * stride + first + (b % span) : 0;
   auto sync = [&]() { if (JPC == 1) __syncthreads(); else __syncwarp(); };
   const tvc_frac_job jb = jobs[ji];
-  const bool live = have && jb.w > 0 && jb.w <= MAXW && jb.h <= MAXH;
+  const bool served = have && done && done[ji];            // the CU-level kernel (k_me_frac_cu) already wrote this job's result
+  const bool live = have && !served && jb.w > 0 && jb.w <= MAXW && jb.h <= MAXH;
   if (!live) {
-    if (have && tid == 0 && jb.w <= 0) out[ji] = tvc_frac_result{0, 0, 0, 0, 0u, 0u};   // census PU outside the picture
+    if (have && !served && tid == 0 && jb.w <= 0) out[ji] = tvc_frac_result{0, 0, 0, 0, 0u, 0u};   // census PU outside the picture
     if (JPC == 1) return;
   }
   const int w = live ? jb.w : 4, h = live ? jb.h : 4, bi = bd - 8;
@@ -1421,6 +1422,183 @@ k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ j
       r.halfx = hx; r.halfy = hy; r.qtrx = S.sel[0]; r.qtry = S.sel[1];
       r.cost_half = cost_half; r.cost = S.cost[9];
       out[ji] = r;
+    }
+    sync();
+  }
+}
+
+// ================================================================================ (3b) fractional search, CU level
+// In the census every CU carries 13 PUs (5 at 8x8) that tile the same block seven (three) times over.  When the integer search
+// gave all of them the SAME vector -- the common case: coherent motion inside a CU -- they share the reference window, the
+// horizontal planes and every Hadamard tile: a tile's SATD at a fractional candidate is one number whichever PU sums it.  One CTA
+// (thread group) per CU then runs xPatternSearchFracDIF once over the CU: pass 1 evaluates the nine half-sample candidates tile by
+// tile and adds each tile into every PU that contains it (8x8 tiles for PUs whose sides are multiples of 8, 4x4 tiles for the
+// others, as xGetHADs tiles them, TComRdCost.cpp:2186-2287), each PU picks its own best half offset (xPatternRefinement with its
+// own sums); pass 2 does the same for the nine quarter-sample candidates around every DISTINCT half offset the PUs chose, tiles
+// restricted to the PUs that chose it.  CUs whose PUs disagree (or that stick out of the picture) are left to the per-PU kernel
+// (`done` stays 0).  Results are identical: the sums are the same integers added in another order.
+constexpr int kCuMaxPu = 13;
+
+template <int CUW>
+struct FracCuSmem {
+  FracSmem<CUW, CUW> f;
+  uint32_t cost[kCuMaxPu][12];
+  int8_t px[kCuMaxPu], py[kCuMaxPu], pw[kCuMaxPu], ph[kCuMaxPu];      // PU rectangles inside the CU
+  int8_t hx[kCuMaxPu], hy[kCuMaxPu], t8[kCuMaxPu];
+  uint32_t cost_half[kCuMaxPu];
+  int agree;
+};
+
+template <int CUW, int NT, int JPC>
+__global__ void __launch_bounds__(NT * JPC)
+k_me_frac_cu(PlaneTable pt, int cur_slot, int ncu, const tvc_frac_job* __restrict__ jobs, tvc_frac_result* __restrict__ out,
+             uint8_t* __restrict__ done, int bd, int cu_per_group, int np, int first)
+{
+  using SM = FracCuSmem<CUW>;
+  using FS = FracSmem<CUW, CUW>;
+  extern __shared__ __align__(16) uint8_t fsm[];
+  const int grp = threadIdx.x / NT, tid = threadIdx.x % NT;
+  SM& S = reinterpret_cast<SM*>(fsm)[grp];
+  const int b = blockIdx.x * JPC + grp;
+  const bool have = b < ncu;
+  const int base = have ? (b / cu_per_group) * TVC_ME_CENSUS + first + (b % cu_per_group) * np : 0;
+  auto sync = [&]() { if (JPC == 1) __syncthreads(); else __syncwarp(); };
+  const tvc_frac_job j0 = jobs[base];                    // the 2Nx2N PU = the CU
+  if (tid == 0) S.agree = have ? 1 : 0;
+  sync();
+  if (have && tid < np) {
+    const tvc_frac_job jk = jobs[base + tid];
+    if (jk.w <= 0 || j0.w != CUW || jk.imvx != j0.imvx || jk.imvy != j0.imvy) S.agree = 0;      // benign race: every writer stores 0
+    S.px[tid] = (int8_t)(jk.x - j0.x); S.py[tid] = (int8_t)(jk.y - j0.y); S.pw[tid] = (int8_t)jk.w; S.ph[tid] = (int8_t)jk.h;
+    S.t8[tid] = (jk.hadamard && !(jk.w & 7) && !(jk.h & 7)) ? 1 : 0;
+    S.hx[tid] = 0; S.hy[tid] = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) S.cost[tid][i] = 0;
+  }
+  sync();
+  const bool live = have && S.agree != 0;
+  if (!live && JPC == 1) return;
+  const int w = CUW, h = CUW, bi = bd - 8;
+  const int gstride = pt.stride[0];
+  int wide = 0;
+  if (tid == 0) S.f.sel[2] = 0;
+  if (live) {
+    const int16_t* ref = pt.org[j0.ref_slot][0] + (ptrdiff_t)(j0.y + j0.imvy - 4) * gstride + j0.x + j0.imvx - 4;
+    const int16_t* cur = pt.org[cur_slot][0] + (ptrdiff_t)j0.y * gstride + j0.x;
+    constexpr int rw = CUW + 8;
+    for (int i = tid; i < rw * rw; i += NT) {
+      const int r = i / rw, x = i - r * rw;
+      S.f.R[r * FS::RP + x] = ref[(ptrdiff_t)r * gstride + x];
+    }
+    for (int i = tid; i < w * h; i += NT) {
+      const int r = i / CUW, x = i - r * CUW;
+      const int16_t ov = cur[(ptrdiff_t)r * gstride + x];
+      S.f.org[r * CUW + x] = ov;
+      wide |= (ov < -255) | (ov > 510);
+    }
+  }
+  sync();
+  if (live) {
+    if (wide) S.f.sel[2] = 1;
+    constexpr int hw = CUW + 1, hh = CUW + 8;
+    for (int i = tid; i < hw * hh; i += NT) {
+      const int r = i / hw, xi = i - r * hw;
+      const int16_t* p = &S.f.R[r * FS::RP + xi];
+      int t[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) t[k] = p[k];
+      S.f.H[0][xi * FS::CP + r] = if_copy(t[3], true, false, bd);
+#pragma unroll
+      for (int f = 1; f < 4; f++) {
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) sum += t[k] * (int)c_luma_taps[f][k];
+        S.f.H[f][xi * FS::CP + r] = if_round(sum, true, false, bd);
+      }
+    }
+  }
+  sync();
+  VRound vr = make_vround(bd);
+  vr.pack2 = bd == 8 && live && S.f.sel[2] == 0;
+  const bool hadamard = j0.hadamard != 0;
+  bool any8 = false, any4 = false;
+  if (live)
+    for (int k = 0; k < np; k++) { any8 |= S.t8[k] != 0; any4 |= S.t8[k] == 0; }
+
+  for (int pass = 0; pass < 2; pass++) {
+    const int dq = pass == 0 ? 2 : 1;
+    if (live) {
+      // pass 1: one base (the integer vector); pass 2: every distinct half offset the PUs picked, in xPatternRefinement's order
+      for (int hb = 0; hb < (pass == 0 ? 1 : 9); hb++) {
+        const int bhx = pass == 0 ? 0 : c_refine_h[hb][0], bhy = pass == 0 ? 0 : c_refine_h[hb][1];
+        unsigned m8 = 0, m4 = 0;                       // PUs that take part in this base, by tile type
+        for (int k = 0; k < np; k++)
+          if (pass == 0 || (S.hx[k] == bhx && S.hy[k] == bhy)) { if (S.t8[k]) m8 |= 1u << k; else m4 |= 1u << k; }
+        if (!(m8 | m4)) continue;
+        const int basex = bhx * 2, basey = bhy * 2;
+        for (int tt = 0; tt < 2; tt++) {
+          const unsigned mem = tt == 0 ? m8 : m4;
+          if (!mem) continue;
+          const int TS = tt == 0 ? 8 : 4;
+          const int tiles_x = CUW / TS, tiles = tiles_x * tiles_x, units = 3 * tiles;
+          const int groups = NT / TS, ug = tid / TS, c = tid % TS;
+          const int iters = (units + groups - 1) / groups;
+          for (int it = 0; it < iters; it++) {
+            const int u = it * groups + ug;
+            const bool valid = u < units;
+            const int uu = valid ? u : 0;
+            const int fxi = uu / tiles, t = uu - fxi * tiles;
+            const int trow = t / tiles_x, tyy = trow * TS, txx = (t - trow * tiles_x) * TS;
+            // PUs of this base and tile type that contain the tile
+            unsigned hit = 0;
+            for (int k = 0; k < np; k++)
+              if (((mem >> k) & 1u) && txx >= S.px[k] && txx < S.px[k] + S.pw[k] && tyy >= S.py[k] && tyy < S.py[k] + S.ph[k]) hit |= 1u << k;
+            const int ox = fxi - 1;
+            uint32_t v[3] = {0, 0, 0};
+            // frac_unit shuffles with the full-warp mask: the whole warp takes it or skips it (pass 2: tiles outside every PU of this base)
+            if (__any_sync(0xffffffffu, hit != 0)) {
+              if (tt == 0) frac_unit<8, FS::CP>(&S.f.H[0][0], FS::HC * FS::CP, S.f.org, CUW, basex + ox * dq, basey, dq, txx, tyy, c, true, vr, v);
+              else frac_unit<4, FS::CP>(&S.f.H[0][0], FS::HC * FS::CP, S.f.org, CUW, basex + ox * dq, basey, dq, txx, tyy, c, hadamard, vr, v);
+            }
+            if (valid && c == 0 && hit) {
+              for (int k = 0; k < np; k++)
+                if ((hit >> k) & 1u) {
+#pragma unroll
+                  for (int q = 0; q < 3; q++) atomicAdd(&S.cost[k][refine_index(pass == 0, ox, q - 1)], v[q]);
+                }
+            }
+          }
+        }
+      }
+    }
+    sync();
+    // xPatternRefinement (TEncSearch.cpp:730-757) per PU: lane i holds candidate i
+    if (tid < 32) {
+      for (int k = 0; k < np; k++) {
+        const int scale = pass == 0 ? 1 : 0;
+        const int phx = live ? S.hx[k] : 0, phy = live ? S.hy[k] : 0;
+        const int ax = pass == 0 ? (j0.imvx << 1) : (((j0.imvx << 1) + phx) << 1);
+        const int ay = pass == 0 ? (j0.imvy << 1) : (((j0.imvy << 1) + phy) << 1);
+        const int i = tid < 9 ? tid : 0;
+        const int8_t* rf = pass == 0 ? c_refine_h[i] : c_refine_q[i];
+        uint32_t dcost = 0xFFFFFFFFu;
+        if (live && tid < 9) dcost = (S.cost[k][i] >> bi) + mv_cost(j0.lambda_cost, ax + rf[0], ay + rf[1], scale, j0.predx, j0.predy);
+        const uint32_t best = __reduce_min_sync(0xffffffffu, dcost);
+        const int best_i = __ffs(__ballot_sync(0xffffffffu, dcost == best)) - 1;
+        __syncwarp();
+        if (live && tid == best_i) {
+          if (pass == 0) { S.hx[k] = rf[0]; S.hy[k] = rf[1]; S.cost_half[k] = best; }
+          else {
+            tvc_frac_result r;
+            r.halfx = phx; r.halfy = phy; r.qtrx = rf[0]; r.qtry = rf[1];
+            r.cost_half = S.cost_half[k]; r.cost = best;
+            out[base + k] = r;
+            done[base + k] = 1;
+          }
+        }
+        if (live && tid < 9) S.cost[k][tid] = 0;
+        __syncwarp();
+      }
     }
     sync();
   }
@@ -1632,7 +1810,7 @@ __global__ void k_ub_lds128(uint32_t* out, int iters)
 
 template <int MAXW, int MAXH, int NT, int JPC>
 static int launch_frac_class(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job* jobs_dev, tvc_frac_result* out_dev, int span,
-                             int stride, int first)
+                             int stride, int first, const uint8_t* done = nullptr)
 {
   if (n <= 0) return TVC_OK;
   constexpr size_t smem = sizeof(FracSmem<MAXW, MAXH>) * JPC;
@@ -1642,23 +1820,60 @@ static int launch_frac_class(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job
     attr_set = true;
   }
   k_me_frac<MAXW, MAXH, NT, JPC><<<(n + JPC - 1) / JPC, NT * JPC, smem, c->stream>>>(c->planes, cur_slot, n, jobs_dev, out_dev,
-                                                                                      c->cfg.bit_depth, span, stride, first);
+                                                                                      c->cfg.bit_depth, span, stride, first, done);
   TVC_LAUNCH_CHECK(c);
   return TVC_OK;
 }
 
 // census == true: jobs are laid out [ref*ctu][593] in census order; one launch per CU depth so that the
 // thread count and shared memory of a CTA fit the PU sizes of that depth
+template <int CUW, int NT, int JPC>
+static int launch_frac_cu(tvc_ctx* c, int cur_slot, int groups, const tvc_frac_job* jobs_dev, tvc_frac_result* out_dev, uint8_t* done,
+                          int cu_per_group, int np, int first)
+{
+  constexpr size_t smem = sizeof(FracCuSmem<CUW>) * JPC;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TVC_CUDA(c, cudaFuncSetAttribute(k_me_frac_cu<CUW, NT, JPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int ncu = groups * cu_per_group;
+  k_me_frac_cu<CUW, NT, JPC><<<(ncu + JPC - 1) / JPC, NT * JPC, smem, c->stream>>>(c->planes, cur_slot, ncu, jobs_dev, out_dev, done,
+                                                                                   c->cfg.bit_depth, cu_per_group, np, first);
+  TVC_LAUNCH_CHECK(c);
+  return TVC_OK;
+}
+
+// census == true: jobs are laid out [ref*ctu][593] in census order.  First the CU-level kernels (one launch per CU depth) serve every CU
+// whose PUs share their integer vector; then one per-PU launch per depth -- thread count and shared memory of a CTA fit the PU sizes of
+// that depth -- serves the rest (TVC_FRAC_CU=0: everything per PU)
 static int launch_frac(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job* jobs_dev, tvc_frac_result* out_dev, bool census)
 {
   ProfScope ps(c, TVC_PH_ME_FRAC);
   if (!census) return launch_frac_class<64, 64, 256, 1>(c, cur_slot, n, jobs_dev, out_dev, n, 0, 0);
   const int groups = n / TVC_ME_CENSUS;
   int r;
-  if ((r = launch_frac_class<64, 64, 256, 1>(c, cur_slot, groups * 13, jobs_dev, out_dev, 13, TVC_ME_CENSUS, 0))) return r;
-  if ((r = launch_frac_class<32, 32, 128, 1>(c, cur_slot, groups * 52, jobs_dev, out_dev, 52, TVC_ME_CENSUS, 13))) return r;
-  if ((r = launch_frac_class<16, 16, 32, 4>(c, cur_slot, groups * 208, jobs_dev, out_dev, 208, TVC_ME_CENSUS, 65))) return r;
-  return launch_frac_class<8, 8, 32, 4>(c, cur_slot, groups * 320, jobs_dev, out_dev, 320, TVC_ME_CENSUS, 273);
+  static int use_cu = -1;
+  if (use_cu < 0) { const char* e = getenv("TVC_FRAC_CU"); use_cu = e ? atoi(e) : 1; }
+  uint8_t* done = nullptr;
+  if (use_cu) {
+    if ((size_t)n > c->frac_done_cap) {
+      if (c->frac_done) cudaFree(c->frac_done);
+      c->frac_done = nullptr; c->frac_done_cap = 0;
+      TVC_CUDA(c, cudaMalloc(&c->frac_done, (size_t)n));
+      c->frac_done_cap = (size_t)n;
+    }
+    done = (uint8_t*)c->frac_done;
+    TVC_CUDA(c, cudaMemsetAsync(done, 0, (size_t)n, c->stream));
+    if ((r = launch_frac_cu<64, 256, 1>(c, cur_slot, groups, jobs_dev, out_dev, done, 1, 13, 0))) return r;
+    if ((r = launch_frac_cu<32, 128, 1>(c, cur_slot, groups, jobs_dev, out_dev, done, 4, 13, 13))) return r;
+    if ((r = launch_frac_cu<16, 32, 4>(c, cur_slot, groups, jobs_dev, out_dev, done, 16, 13, 65))) return r;
+    if ((r = launch_frac_cu<8, 32, 4>(c, cur_slot, groups, jobs_dev, out_dev, done, 64, 5, 273))) return r;
+  }
+  if ((r = launch_frac_class<64, 64, 256, 1>(c, cur_slot, groups * 13, jobs_dev, out_dev, 13, TVC_ME_CENSUS, 0, done))) return r;
+  if ((r = launch_frac_class<32, 32, 128, 1>(c, cur_slot, groups * 52, jobs_dev, out_dev, 52, TVC_ME_CENSUS, 13, done))) return r;
+  if ((r = launch_frac_class<16, 16, 32, 4>(c, cur_slot, groups * 208, jobs_dev, out_dev, 208, TVC_ME_CENSUS, 65, done))) return r;
+  return launch_frac_class<8, 8, 32, 4>(c, cur_slot, groups * 320, jobs_dev, out_dev, 320, TVC_ME_CENSUS, 273, done);
 }
 
 }  // namespace tvc
