@@ -692,6 +692,17 @@ def gpu_arm(args):
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
     torch.cuda.set_device(local)
+    if world > 1:
+        # one rank per GPU on one host: every rank keeps to its own share of the cores (the host side of the end-to-end step --
+        # list validation threads, staging copies -- otherwise competes with seven other ranks for the same cores)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            lw = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+            per = max(1, len(cores) // max(1, lw))
+            mine = cores[local * per:(local + 1) * per] or cores
+            os.sched_setaffinity(0, set(mine))
+        except (AttributeError, OSError, ValueError):
+            pass
     stream = torch.cuda.Stream()
     wl = Workload(rank_seed(args.seed, rank), pinned=True)
     t = TLibCuda(W, H, BD, num_slots=NUM_SLOTS, device=local, stream=stream.cuda_stream)
@@ -801,8 +812,8 @@ def gpu_arm(args):
     # integer-ME candidate counts of this workload (for the algorithmic byte count of the search kernel);
     # run once more outside the timed region, results to the host
     ires_flat = np.zeros((NUM_REFS * wl.nctu * 593, 4), np.int32)
-    mcfg_nofrac = MeFrameCfg(SEARCH_RANGE, 1, 1, 1, 0, lc)
-    ck(L.tvc_me_frame(h, SLOT_CUR, NUM_REFS, refs, ptr(pred), C.byref(mcfg_nofrac), ptr(ires_flat), None))
+    fres_flat = np.zeros((NUM_REFS * wl.nctu * 593, 6), np.int32)
+    ck(L.tvc_me_frame(h, SLOT_CUR, NUM_REFS, refs, ptr(pred), C.byref(mcfg), ptr(ires_flat), ptr(fres_flat)))
     n_sads = ires_flat[:, 3].astype(np.int64).reshape(NUM_REFS, wl.nctu, 593)
     me_stats = t.me_frame_stats()       # exact work counters of that call (table granules, raster candidates)
 

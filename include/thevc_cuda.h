@@ -330,7 +330,7 @@ int tvc_me_ctu(tvc_ctx* ctx, int cur_slot, int ref_index, int ref_slot, int ctu,
 
 /* work counters of the last tvc_me_frame[_dev] call (for roofline accounting).  Default (group search): stats[0] = candidate SADs
  * the searches evaluated (the reference's own count: sum of n_sads), stats[1] = sample differences of those (w x (h >> iSubShift)
- * per candidate), stats[2] = 0.  TVC_ME_FUSED=0 (SAD tables): stats[0] = 16-byte table granules the reference-visible candidates of
+ * per candidate), stats[2] = census jobs whose fractional search was served at CU level (k_me_frac_cu).  TVC_ME_FUSED=0 (SAD tables): stats[0] = 16-byte table granules the reference-visible candidates of
  * k_me_search required, stats[1] = candidates served by the shared raster stage, stats[2] = raster candidates walked by
  * k_me_raster.  Synchronises.                                                                                                */
 int tvc_me_frame_stats(tvc_ctx* ctx, uint64_t stats[3]);

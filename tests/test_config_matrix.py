@@ -8,7 +8,8 @@
 Every stream must have the md5 of the UNMODIFIED reference encoder's single run.  Those single runs take 5-25 minutes each on one
 host core, so their md5s are committed fixtures (tests/golden/hm_md5.json, written by tests/golden/make_hm_md5.py in the container that
 has /root/reference); the inputs are the seeded synthetic sequences of tests/synth.py.  The encodes are independent processes: a
-session fixture starts all of them together (wave 2 = what would not fit in HBM beside wave 1) and each test waits for its own.
+session fixture starts all of them together (the group search needs no SAD tables, so they all fit in HBM side by side) and each test
+waits for its own.
 Every run leaves a JSON record (md5, wall time, fps, hook counters) under gpurun_out/matrix/ -> copied to profiles/.
 
 TVC_SKIP_FULLSIZE=1 skips the whole file (bounded smoke runs)."""
@@ -107,21 +108,22 @@ def matrix(tmp_path_factory):
     ngpu = max(1, len(se.visible_gpus()))
     pool = concurrent.futures.ThreadPoolExecutor(8)
     t0 = time.perf_counter()
-    jobs = {
-        "ldp_1080_17": pool.submit(_single, "ldp_1080_17", str(base / "c2"), FAST_HM),
-        "ra_1080_33": pool.submit(_single, "ra_1080_33", str(base / "c3"), FAST_HM),
-        "he10_2160_8": pool.submit(_sharded, "he10_2160_8", str(base / "c4"), "intra16,dbk,sao", 8, True),
+    # TVC_MATRIX_CASES=a,b,...: only these cases run (multi-GPU boxes are charged per GPU: the sharded cases alone there)
+    only = [c for c in os.environ.get("TVC_MATRIX_CASES", "").split(",") if c]
+    plan = {
+        "ldp_1080_17": lambda: _single("ldp_1080_17", str(base / "c2"), FAST_HM),
+        "ra_1080_33": lambda: _single("ra_1080_33", str(base / "c3"), FAST_HM),
+        "he10_2160_8": lambda: _sharded("he10_2160_8", str(base / "c4"), "intra16,dbk,sao", 8, True),
+        "ra_1080_66_idr": lambda: _sharded("ra_1080_66_idr", str(base / "c3s"), FAST_HM, max(3, ngpu)),
+        "ra_1080_66_idr_ip16": lambda: _sharded("ra_1080_66_idr_ip16", str(base / "c3t"), FAST_HM, max(5, ngpu)),
     }
-
-    def wave2():
-        # the three intra-period shards reserve their own SAD tables: started when the two single runs have released theirs
-        if ngpu == 1:
-            jobs["ldp_1080_17"].result(); jobs["ra_1080_33"].result()
-        return _sharded("ra_1080_66_idr", str(base / "c3s"), FAST_HM, max(3, ngpu))
-    jobs["ra_1080_66_idr"] = pool.submit(wave2)
+    default = ["ldp_1080_17", "ra_1080_33", "he10_2160_8", "ra_1080_66_idr"]
+    jobs = {name: pool.submit(plan[name]) for name in (only or default)}
     out = {}
 
     def get(name):
+        if name not in jobs:
+            pytest.skip("%s not in TVC_MATRIX_CASES" % name)
         if name not in out:
             rec = jobs[name].result()
             rec["gpus_visible"] = ngpu
@@ -169,3 +171,13 @@ def test_configs3_intra_he10_2160p_frame_shards(matrix):
     _check(rec)
     assert rec["shards"] == 8
     assert rec["decoder_rc"] == 0 and rec["decoder_errors"] == 0 and rec["decoder_ok_pictures"] == 8, rec
+
+
+def test_configs2_random_access_1080p_intra_period_16_shards(matrix):
+    """the same sequence with --IntraPeriod=16: five closed intra periods, enough units for five GPUs (runs when asked for with
+    TVC_MATRIX_CASES; the cfg's own IntraPeriod 32 gives three units over 66 pictures)"""
+    if "ra_1080_66_idr_ip16" not in os.environ.get("TVC_MATRIX_CASES", ""):
+        pytest.skip("ra_1080_66_idr_ip16 only with TVC_MATRIX_CASES")
+    rec = matrix("ra_1080_66_idr_ip16")
+    _check(rec)
+    assert rec["shards"] == 5

@@ -239,6 +239,27 @@ def test_picture_hash_on_device(tmp_path, digest):
     assert "TLibCuda picture hash: %d pictures" % frames in d.stderr, d.stderr[-400:]
 
 
+def test_psnr_sums_on_device(tmp_path):
+    """SURVEY 8f-4, second half: the three UInt64 sums of squared differences of TEncGOP::xCalculateAddPSNR from tvc_pic_ssd
+    (TVC_HM=psnr).  The encoder prints the PSNR of every picture: the hooked encoder's lines equal the reference's digit for digit."""
+    _need()
+    import re
+    w, h, frames = 208, 120, 3
+    yuv = str(tmp_path / "in.yuv")
+    _yuv(yuv, w, h, frames)
+    ref_bin, cuda_bin = str(tmp_path / "ref.bin"), str(tmp_path / "cuda.bin")
+    ref_job = _encode_ref_bg("encoder_lowdelay_P_main.cfg", yuv, w, h, frames, ref_bin)
+    r = _encode(ENC_CUDA, "encoder_lowdelay_P_main.cfg", yuv, w, h, frames, cuda_bin, env={"TVC_HM": "psnr"})
+    ref = ref_job.result()
+    assert _md5(cuda_bin) == _md5(ref_bin)
+
+    def psnr(out):
+        return re.findall(r"\[Y\s+[\d.]+ dB\s+U\s+[\d.]+ dB\s+V\s+[\d.]+ dB\]", out)
+    a, b = psnr(r.stdout), psnr(ref.stdout)
+    assert len(a) == frames and a == b, (a, b)
+    assert "TLibCuda PSNR: the squared-difference sums of %d pictures" % frames in r.stderr, r.stderr[-400:]
+
+
 def test_frame_prepass_feeds_the_cu_loop(tmp_path):
     """the north star's per-frame batched pre-pass inside the real encoder (TVC_HM=...,frame): from the second inter picture on one
     tvc_me_frame call per picture searches the whole census with the predictor guesses; a (CTU, reference) group whose first real

@@ -122,8 +122,12 @@ def test_stateful_extra_arguments_are_refused():
         with pytest.raises(ValueError):
             se.check_extra(bad)
     se.check_extra(["--SEIpictureDigest=1", "--DecodingRefreshType=2", "--IntraPeriod=16", "--RateControl=0"])
-    assert se.shards_per_gpu(1920, 1080, "me,frac,tables") == 4 and se.shards_per_gpu(416, 240, "me,frac,tables") >= 16
-    assert se.shards_per_gpu(3840, 2160, "intra16,dbk,sao") == 16
+    assert se.shards_per_gpu(1920, 1080, "me,frac,tables") == 16 and se.shards_per_gpu(3840, 2160, "intra16,dbk,sao") == 16
+    os.environ["TVC_ME_FUSED"] = "0"          # the round-1 form reserves 34.8 GB of SAD tables per 1080p process
+    try:
+        assert se.shards_per_gpu(1920, 1080, "me,frac,tables") == 4 and se.shards_per_gpu(416, 240, "me,frac,tables") >= 16
+    finally:
+        del os.environ["TVC_ME_FUSED"]
 
 
 @pytest.mark.gpu

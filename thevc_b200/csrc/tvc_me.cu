@@ -326,6 +326,8 @@ constexpr int kGrpWinW = 208, kGrpWinH = 192, kGrpCurP = 80;
 __device__ __forceinline__ uint32_t sad_u8_lane(const uint8_t* __restrict__ ref, int rpitch, const uint8_t* __restrict__ cur, int w4, int rows,
                                                 int sub)
 {
+  // measured on B200 (ms of k_me_group per 1080p picture x 4 references): this plain form 5.8; two rows per step with four
+  // independent accumulators 6.8; row loop unrolled per PU width behind a non-inlined call 10.0 -- the simple loop stays
   const int a = (int)((uintptr_t)ref & 3), sh = a * 8;
   const uint32_t* rb = reinterpret_cast<const uint32_t*>(ref - a);
   const uint32_t* cb = reinterpret_cast<const uint32_t*>(cur);
@@ -1312,6 +1314,9 @@ k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ j
   const tvc_frac_job jb = jobs[ji];
   const bool served = have && done && done[ji];            // the CU-level kernel (k_me_frac_cu) already wrote this job's result
   const bool live = have && !served && jb.w > 0 && jb.w <= MAXW && jb.h <= MAXH;
+  if (JPC > 1 && done) {                                   // every job of this CTA already served: leave at once
+    if (__syncthreads_and(!have || served)) return;
+  }
   if (!live) {
     if (have && !served && tid == 0 && jb.w <= 0) out[ji] = tvc_frac_result{0, 0, 0, 0, 0u, 0u};   // census PU outside the picture
     if (JPC == 1) return;
@@ -1437,7 +1442,7 @@ k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ j
 // own sums); pass 2 does the same for the nine quarter-sample candidates around every DISTINCT half offset the PUs chose, tiles
 // restricted to the PUs that chose it.  CUs whose PUs disagree (or that stick out of the picture) are left to the per-PU kernel
 // (`done` stays 0).  Results are identical: the sums are the same integers added in another order.
-constexpr int kCuMaxPu = 13;
+constexpr int kCuMaxPu = 33;        // a 16x16 CU with its four 8x8 children: 13 + 4 x 5 PUs
 
 template <int CUW>
 struct FracCuSmem {
@@ -1446,13 +1451,15 @@ struct FracCuSmem {
   int8_t px[kCuMaxPu], py[kCuMaxPu], pw[kCuMaxPu], ph[kCuMaxPu];      // PU rectangles inside the CU
   int8_t hx[kCuMaxPu], hy[kCuMaxPu], t8[kCuMaxPu];
   uint32_t cost_half[kCuMaxPu];
-  int agree;
+  int jidx[kCuMaxPu];             // census job of each PU
+  unsigned long long mask8[(CUW / 8) * (CUW / 8)], mask4[(CUW / 4) * (CUW / 4)];      // per Hadamard tile: the PUs that contain it
+  int agree, np;
 };
 
-template <int CUW, int NT, int JPC>
+template <int CUW, int NT, int JPC, bool CHILD>     // CHILD (16x16 only): the CU's four 8x8 children join when they share the vector too
 __global__ void __launch_bounds__(NT * JPC)
 k_me_frac_cu(PlaneTable pt, int cur_slot, int ncu, const tvc_frac_job* __restrict__ jobs, tvc_frac_result* __restrict__ out,
-             uint8_t* __restrict__ done, int bd, int cu_per_group, int np, int first)
+             uint8_t* __restrict__ done, int bd, int cu_per_group, int np, int first, unsigned long long* __restrict__ stats)
 {
   using SM = FracCuSmem<CUW>;
   using FS = FracSmem<CUW, CUW>;
@@ -1464,20 +1471,42 @@ k_me_frac_cu(PlaneTable pt, int cur_slot, int ncu, const tvc_frac_job* __restric
   const int base = have ? (b / cu_per_group) * TVC_ME_CENSUS + first + (b % cu_per_group) * np : 0;
   auto sync = [&]() { if (JPC == 1) __syncthreads(); else __syncwarp(); };
   const tvc_frac_job j0 = jobs[base];                    // the 2Nx2N PU = the CU
-  if (tid == 0) S.agree = have ? 1 : 0;
+  if (tid == 0) { S.agree = have ? 1 : 0; S.np = CHILD ? np + 20 : np; }
   sync();
-  if (have && tid < np) {
-    const tvc_frac_job jk = jobs[base + tid];
-    if (jk.w <= 0 || j0.w != CUW || jk.imvx != j0.imvx || jk.imvy != j0.imvy) S.agree = 0;      // benign race: every writer stores 0
-    S.px[tid] = (int8_t)(jk.x - j0.x); S.py[tid] = (int8_t)(jk.y - j0.y); S.pw[tid] = (int8_t)jk.w; S.ph[tid] = (int8_t)jk.h;
-    S.t8[tid] = (jk.hadamard && !(jk.w & 7) && !(jk.h & 7)) ? 1 : 0;
-    S.hx[tid] = 0; S.hy[tid] = 0;
+  // census job of PU k: the CU's own parts, then (CHILD) the five parts of each 8x8 child (depth 3 of the census: 8 x 8 CUs in
+  // raster order from index 273, five PUs each; the 16x16 CU `cu` of the 4 x 4 grid covers children (2 cx + i, 2 cy + j))
+  const int npx = CHILD ? np + 20 : np;
+  if (have && !(done[base])) {
+    for (int k = tid; k < npx; k += NT) {
+      int ji = base + k;
+      if (CHILD && k >= np) {
+        const int cu = b % cu_per_group, cx = cu & 3, cy = cu >> 2, ch = (k - np) / 5, part = (k - np) % 5;
+        ji = (b / cu_per_group) * TVC_ME_CENSUS + 273 + (((2 * cy + (ch >> 1)) * 8) + 2 * cx + (ch & 1)) * 5 + part;
+      }
+      const tvc_frac_job jk = jobs[ji];
+      const bool same = jk.w > 0 && j0.w == CUW && jk.imvx == j0.imvx && jk.imvy == j0.imvy;
+      if (!same) { if (k < np) S.agree = 0; else S.np = np; }      // a child that differs: the CU goes alone (benign races: same value from every writer)
+      S.jidx[k] = ji;
+      S.px[k] = (int8_t)(jk.x - j0.x); S.py[k] = (int8_t)(jk.y - j0.y); S.pw[k] = (int8_t)jk.w; S.ph[k] = (int8_t)jk.h;
+      S.t8[k] = (jk.hadamard && !(jk.w & 7) && !(jk.h & 7)) ? 1 : 0;
+      S.hx[k] = 0; S.hy[k] = 0;
 #pragma unroll
-    for (int i = 0; i < 12; i++) S.cost[tid][i] = 0;
-  }
+      for (int i = 0; i < 12; i++) S.cost[k][i] = 0;
+    }
+  } else if (tid == 0) S.agree = 0;              // already served (an 8x8 CU taken by its parent's launch)
   sync();
   const bool live = have && S.agree != 0;
   if (!live && JPC == 1) return;
+  np = live ? S.np : 0;                          // PUs served here: the CU's own, plus its children when they all agree
+  for (int t = tid; t < (CUW / 8) * (CUW / 8) + (CUW / 4) * (CUW / 4); t += NT) {
+    const bool is8 = t < (CUW / 8) * (CUW / 8);
+    const int tt = is8 ? t : t - (CUW / 8) * (CUW / 8), n = is8 ? CUW / 8 : CUW / 4, ts = is8 ? 8 : 4;
+    const int tx = (tt % n) * ts, ty = (tt / n) * ts;
+    unsigned long long m = 0;
+    for (int k = 0; k < np; k++)
+      if ((S.t8[k] != 0) == is8 && tx >= S.px[k] && tx < S.px[k] + S.pw[k] && ty >= S.py[k] && ty < S.py[k] + S.ph[k]) m |= 1ull << k;
+    if (is8) S.mask8[tt] = m; else S.mask4[tt] = m;
+  }
   const int w = CUW, h = CUW, bi = bd - 8;
   const int gstride = pt.stride[0];
   int wide = 0;
@@ -1531,13 +1560,13 @@ k_me_frac_cu(PlaneTable pt, int cur_slot, int ncu, const tvc_frac_job* __restric
       // pass 1: one base (the integer vector); pass 2: every distinct half offset the PUs picked, in xPatternRefinement's order
       for (int hb = 0; hb < (pass == 0 ? 1 : 9); hb++) {
         const int bhx = pass == 0 ? 0 : c_refine_h[hb][0], bhy = pass == 0 ? 0 : c_refine_h[hb][1];
-        unsigned m8 = 0, m4 = 0;                       // PUs that take part in this base, by tile type
+        unsigned long long m8 = 0, m4 = 0;            // PUs that take part in this base, by tile type
         for (int k = 0; k < np; k++)
-          if (pass == 0 || (S.hx[k] == bhx && S.hy[k] == bhy)) { if (S.t8[k]) m8 |= 1u << k; else m4 |= 1u << k; }
+          if (pass == 0 || (S.hx[k] == bhx && S.hy[k] == bhy)) { if (S.t8[k]) m8 |= 1ull << k; else m4 |= 1ull << k; }
         if (!(m8 | m4)) continue;
         const int basex = bhx * 2, basey = bhy * 2;
         for (int tt = 0; tt < 2; tt++) {
-          const unsigned mem = tt == 0 ? m8 : m4;
+          const unsigned long long mem = tt == 0 ? m8 : m4;
           if (!mem) continue;
           const int TS = tt == 0 ? 8 : 4;
           const int tiles_x = CUW / TS, tiles = tiles_x * tiles_x, units = 3 * tiles;
@@ -1550,9 +1579,7 @@ k_me_frac_cu(PlaneTable pt, int cur_slot, int ncu, const tvc_frac_job* __restric
             const int fxi = uu / tiles, t = uu - fxi * tiles;
             const int trow = t / tiles_x, tyy = trow * TS, txx = (t - trow * tiles_x) * TS;
             // PUs of this base and tile type that contain the tile
-            unsigned hit = 0;
-            for (int k = 0; k < np; k++)
-              if (((mem >> k) & 1u) && txx >= S.px[k] && txx < S.px[k] + S.pw[k] && tyy >= S.py[k] && tyy < S.py[k] + S.ph[k]) hit |= 1u << k;
+            const unsigned long long hit = mem & (tt == 0 ? S.mask8[t] : S.mask4[t]);
             const int ox = fxi - 1;
             uint32_t v[3] = {0, 0, 0};
             // frac_unit shuffles with the full-warp mask: the whole warp takes it or skips it (pass 2: tiles outside every PU of this base)
@@ -1560,45 +1587,45 @@ k_me_frac_cu(PlaneTable pt, int cur_slot, int ncu, const tvc_frac_job* __restric
               if (tt == 0) frac_unit<8, FS::CP>(&S.f.H[0][0], FS::HC * FS::CP, S.f.org, CUW, basex + ox * dq, basey, dq, txx, tyy, c, true, vr, v);
               else frac_unit<4, FS::CP>(&S.f.H[0][0], FS::HC * FS::CP, S.f.org, CUW, basex + ox * dq, basey, dq, txx, tyy, c, hadamard, vr, v);
             }
-            if (valid && c == 0 && hit) {
-              for (int k = 0; k < np; k++)
-                if ((hit >> k) & 1u) {
+            if (valid && c == 0) {
+              for (unsigned long long hm = hit; hm; hm &= hm - 1) {
+                const int k = __ffsll((long long)hm) - 1;
 #pragma unroll
-                  for (int q = 0; q < 3; q++) atomicAdd(&S.cost[k][refine_index(pass == 0, ox, q - 1)], v[q]);
-                }
+                for (int q = 0; q < 3; q++) atomicAdd(&S.cost[k][refine_index(pass == 0, ox, q - 1)], v[q]);
+              }
             }
           }
         }
       }
     }
     sync();
-    // xPatternRefinement (TEncSearch.cpp:730-757) per PU: lane i holds candidate i
-    if (tid < 32) {
-      for (int k = 0; k < np; k++) {
+    // xPatternRefinement (TEncSearch.cpp:730-757), one lane per PU: dist >> bitIncrement + rate, strict '<' in the listed order
+    if (tid < 32 && live) {
+      for (int k = tid; k < np; k += 32) {
         const int scale = pass == 0 ? 1 : 0;
-        const int phx = live ? S.hx[k] : 0, phy = live ? S.hy[k] : 0;
+        const int phx = S.hx[k], phy = S.hy[k];
         const int ax = pass == 0 ? (j0.imvx << 1) : (((j0.imvx << 1) + phx) << 1);
         const int ay = pass == 0 ? (j0.imvy << 1) : (((j0.imvy << 1) + phy) << 1);
-        const int i = tid < 9 ? tid : 0;
-        const int8_t* rf = pass == 0 ? c_refine_h[i] : c_refine_q[i];
-        uint32_t dcost = 0xFFFFFFFFu;
-        if (live && tid < 9) dcost = (S.cost[k][i] >> bi) + mv_cost(j0.lambda_cost, ax + rf[0], ay + rf[1], scale, j0.predx, j0.predy);
-        const uint32_t best = __reduce_min_sync(0xffffffffu, dcost);
-        const int best_i = __ffs(__ballot_sync(0xffffffffu, dcost == best)) - 1;
-        __syncwarp();
-        if (live && tid == best_i) {
-          if (pass == 0) { S.hx[k] = rf[0]; S.hy[k] = rf[1]; S.cost_half[k] = best; }
-          else {
-            tvc_frac_result r;
-            r.halfx = phx; r.halfy = phy; r.qtrx = rf[0]; r.qtry = rf[1];
-            r.cost_half = S.cost_half[k]; r.cost = best;
-            out[base + k] = r;
-            done[base + k] = 1;
-          }
+        uint32_t best = 0xFFFFFFFFu;
+        int best_i = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+          const int8_t* rf = pass == 0 ? c_refine_h[i] : c_refine_q[i];
+          const uint32_t dcost = (S.cost[k][i] >> bi) + mv_cost(j0.lambda_cost, ax + rf[0], ay + rf[1], scale, j0.predx, j0.predy);
+          if (dcost < best) { best = dcost; best_i = i; }
+          S.cost[k][i] = 0;
         }
-        if (live && tid < 9) S.cost[k][tid] = 0;
-        __syncwarp();
+        const int8_t* rf = pass == 0 ? c_refine_h[best_i] : c_refine_q[best_i];
+        if (pass == 0) { S.hx[k] = rf[0]; S.hy[k] = rf[1]; S.cost_half[k] = best; }
+        else {
+          tvc_frac_result r;
+          r.halfx = phx; r.halfy = phy; r.qtrx = rf[0]; r.qtry = rf[1];
+          r.cost_half = S.cost_half[k]; r.cost = best;
+          out[S.jidx[k]] = r;
+          done[S.jidx[k]] = 1;
+        }
       }
+      if (pass == 1 && tid == 0 && stats) atomicAdd(&stats[2], (unsigned long long)np);
     }
     sync();
   }
@@ -1827,19 +1854,19 @@ static int launch_frac_class(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job
 
 // census == true: jobs are laid out [ref*ctu][593] in census order; one launch per CU depth so that the
 // thread count and shared memory of a CTA fit the PU sizes of that depth
-template <int CUW, int NT, int JPC>
+template <int CUW, int NT, int JPC, bool CHILD = false>
 static int launch_frac_cu(tvc_ctx* c, int cur_slot, int groups, const tvc_frac_job* jobs_dev, tvc_frac_result* out_dev, uint8_t* done,
                           int cu_per_group, int np, int first)
 {
   constexpr size_t smem = sizeof(FracCuSmem<CUW>) * JPC;
   static bool attr_set = false;
   if (!attr_set) {
-    TVC_CUDA(c, cudaFuncSetAttribute(k_me_frac_cu<CUW, NT, JPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TVC_CUDA(c, cudaFuncSetAttribute(k_me_frac_cu<CUW, NT, JPC, CHILD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const int ncu = groups * cu_per_group;
-  k_me_frac_cu<CUW, NT, JPC><<<(ncu + JPC - 1) / JPC, NT * JPC, smem, c->stream>>>(c->planes, cur_slot, ncu, jobs_dev, out_dev, done,
-                                                                                   c->cfg.bit_depth, cu_per_group, np, first);
+  k_me_frac_cu<CUW, NT, JPC, CHILD><<<(ncu + JPC - 1) / JPC, NT * JPC, smem, c->stream>>>(c->planes, cur_slot, ncu, jobs_dev, out_dev, done,
+                                                                                          c->cfg.bit_depth, cu_per_group, np, first, me_fused_enabled(c) ? c->fr_stats : nullptr);
   TVC_LAUNCH_CHECK(c);
   return TVC_OK;
 }
@@ -1867,7 +1894,7 @@ static int launch_frac(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job* jobs
     TVC_CUDA(c, cudaMemsetAsync(done, 0, (size_t)n, c->stream));
     if ((r = launch_frac_cu<64, 256, 1>(c, cur_slot, groups, jobs_dev, out_dev, done, 1, 13, 0))) return r;
     if ((r = launch_frac_cu<32, 128, 1>(c, cur_slot, groups, jobs_dev, out_dev, done, 4, 13, 13))) return r;
-    if ((r = launch_frac_cu<16, 32, 4>(c, cur_slot, groups, jobs_dev, out_dev, done, 16, 13, 65))) return r;
+    if ((r = launch_frac_cu<16, 32, 4, true>(c, cur_slot, groups, jobs_dev, out_dev, done, 16, 13, 65))) return r;      // + its 8x8 children
     if ((r = launch_frac_cu<8, 32, 4>(c, cur_slot, groups, jobs_dev, out_dev, done, 64, 5, 273))) return r;
   }
   if ((r = launch_frac_class<64, 64, 256, 1>(c, cur_slot, groups * 13, jobs_dev, out_dev, 13, TVC_ME_CENSUS, 0, done))) return r;

@@ -21,6 +21,7 @@
 // change a cost (the reference is x86-64 SSE2 code without FMA).
 #include "tvc_internal.cuh"
 #include <thread>
+#include <sched.h>
 #include <algorithm>
 
 #include <cfloat>
@@ -541,7 +542,10 @@ static int validate_rdoq(tvc_ctx* c, int n, const tvc_rdoq_tu* tus, int n_est, s
 static bool validate_pair_fast(const Pic& p, int n, const tvc_tu* tus, const tvc_rdoq_tu* rtus, int n_est, size_t coef_elems, int counts[4])
 {
   struct Part { int counts[4] = {0, 0, 0, 0}; int first = 0, last = 0; bool ok = true; };
+  // as many threads as this process may run on (a rank pinned to its share of the host cores gets its share), at most 8
   unsigned hw = std::thread::hardware_concurrency();
+  cpu_set_t cpus;
+  if (sched_getaffinity(0, sizeof(cpus), &cpus) == 0 && CPU_COUNT(&cpus) > 0) hw = (unsigned)CPU_COUNT(&cpus);
   const int nt = n < 32768 ? 1 : (int)std::min<unsigned>(8, hw ? hw : 1);
   std::vector<Part> parts(nt);
   auto work = [&](int k) {

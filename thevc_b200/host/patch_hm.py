@@ -72,6 +72,19 @@ def main():
     s = sub_once(s, r'm_bSeqFirst           = true;', 'm_bSeqFirst           = tlibcuda_poc_offset() == 0;', "TEncGOP m_bSeqFirst")
     s = sub_once(s, r'if\(uiPOCCurr>=m_pcCfg->getFrameToBeEncoded\(\)\)', 'if(uiPOCCurr>=m_pcCfg->getFrameToBeEncoded() + tlibcuda_poc_offset())',
                  "compressGOP frame limit")
+    # xCalculateAddPSNR: the three sums of squared differences of a picture from one device call
+    m = re.search(r'Void TEncGOP::xCalculateAddPSNR\(.*?\n\}\r?\n', s, flags=re.S)
+    assert m, "xCalculateAddPSNR not found"
+    body = m.group(0)
+    n_loops = body.count("for( y = 0; y < iHeight; y++ )")
+    assert n_loops == 3, "xCalculateAddPSNR: %d row loops" % n_loops
+    first = body.index("for( y = 0; y < iHeight; y++ )")
+    body = (body[:first] + "UInt64 tvcSsd[3];\n  const Bool tvcHaveSsd = tlibcuda_pic_ssd( pcPic->getPicYuvOrg(), pcPicD, m_pcEncTop->getPad(0), "
+            "m_pcEncTop->getPad(1), tvcSsd );\n  " + body[first:])
+    body = body.replace("for( y = 0; y < iHeight; y++ )", "for( y = 0; !tvcHaveSsd && y < iHeight; y++ )")
+    body = sub_once(body, r'(\n)([ \t]*unsigned int maxval = 255 \* \(1<<\(g_uiBitDepth \+ g_uiBitIncrement -8\)\);\r?\n)',
+                    r'\1  if ( tvcHaveSsd ) { uiSSDY = tvcSsd[0]; uiSSDU = tvcSsd[1]; uiSSDV = tvcSsd[2]; }\n\2', "xCalculateAddPSNR sums")
+    s = s[:m.start()] + body + s[m.end():]
     wr(os.path.join(out, "TLibEncoder", "TEncGOP.cpp"), s)
 
     s = rd(os.path.join(lib, "TLibEncoder", "TEncTop.cpp"))

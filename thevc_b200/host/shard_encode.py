@@ -124,9 +124,10 @@ def visible_gpus():
 
 
 def shards_per_gpu(w, h, hm, hbm_gb=150):
-    """how many shard processes one GPU holds: every process with the `tables` hook reserves the SAD tables of four references
-    (17.04 MB per (CTU, reference): 34.8 GB at 1080p)"""
-    if "tables" not in hm.split(","):
+    """how many shard processes one GPU holds.  The default integer search (group search: windows staged in shared memory) needs no
+    table memory; only the round-1 form (TVC_ME_FUSED=0 with the `tables` hook) reserves the SAD tables of four references per
+    process (17.04 MB per (CTU, reference): 34.8 GB at 1080p)"""
+    if "tables" not in hm.split(",") or os.environ.get("TVC_ME_FUSED", "1") != "0":
         return 16
     nctu = ((w + 63) // 64) * ((h + 63) // 64)
     return max(1, int(hbm_gb * 1e9 // (nctu * 4 * 17.04e6 + 2e9)))

@@ -145,6 +145,8 @@ struct State {
   unsigned long long n_frame_groups = 0;
   bool on_hash = false;                    // picture hashes on the device (TVC_HM=...,hash)
   unsigned long long n_hash = 0;
+  bool on_psnr = false;                    // PSNR sums on the device (TVC_HM=...,psnr)
+  unsigned long long n_psnr = 0;
   bool on_cand = false;                    // merge / AMVP candidate evaluation (TVC_HM=...,cand)
   bool on_bipred = false;                  // bi-prediction refinement searches on the device (off: TVC_HM=...,nobipred)
   bool on_cand_grid = false;               // ... served by look-up from CTU-wide cost grids (TVC_HM=...,candgrid)
@@ -195,6 +197,8 @@ void report()
     fprintf(stderr, "TLibCuda SAO: %llu planes filtered on the device, %.3f s (upload + kernel + download)\n", s.sao.n_planes, s.sao.seconds);
   if (s.on_hash)
     fprintf(stderr, "TLibCuda picture hash: %llu pictures hashed on the device\n", s.n_hash);
+  if (s.on_psnr)
+    fprintf(stderr, "TLibCuda PSNR: the squared-difference sums of %llu pictures computed on the device\n", s.n_psnr);
   if (s.on_cand_grid)
     fprintf(stderr, "TLibCuda candidate look-up: %llu of %llu candidate costs served from %llu CTU-wide (CTU, reference, MV) cost grids; %llu bi-predicted merge sets left to the reference's code\n",
             s.n_grid_hits, s.n_grid_hits + s.n_grid_fills, s.n_grid_fills, s.n_merge_host);
@@ -288,6 +292,7 @@ void parse_env()
     else if (t == "dbk") s.dbk.on = true;
     else if (t == "frame") s.on_frame = true;
     else if (t == "hash") s.on_hash = true;
+    else if (t == "psnr") s.on_psnr = true;
     else if (t == "cand") s.on_cand = true;
     else if (t == "candgrid") s.on_cand = s.on_cand_grid = true;
     else if (t == "bipred") s.on_bipred = true;
@@ -319,7 +324,7 @@ void ensure_ctx(int w, int ht)
   State& s = S();
   if (s.disabled || (s.h && s.w >= w && s.ht >= ht)) return;
   init_once();
-  if (!s.on_me && !s.on_frac && !s.on_tq && !s.on_rdoq && !s.on_mc && !s.dbk.on && !s.sao.on && !s.intra.on && !s.on_cand && !s.on_hash) { s.disabled = true; return; }     // TVC_HM=none: the unmodified path
+  if (!s.on_me && !s.on_frac && !s.on_tq && !s.on_rdoq && !s.on_mc && !s.dbk.on && !s.sao.on && !s.intra.on && !s.on_cand && !s.on_hash && !s.on_psnr) { s.disabled = true; return; }     // TVC_HM=none: the unmodified path
   if (s.h) {                  // the decoder learns the picture size after its first transforms: start over with the real size
     tvc_ctx_destroy(s.h);
     s.h = nullptr;
@@ -894,6 +899,25 @@ bool tlibcuda_pic_hash(TComPicYuv& pic, int method, unsigned char digest[3][16])
   CK(tvc_pic_upload(s.h, slot, pic.getLumaAddr(), pic.getStride(), pic.getCbAddr(), pic.getCrAddr(), pic.getCStride(), 0));
   CK(tvc_pic_hash(s.h, slot, method, &digest[0][0]));
   s.n_hash++;
+  return true;
+}
+
+bool tlibcuda_pic_ssd(TComPicYuv* org, TComPicYuv* rec, int padx, int pady, unsigned long long ssd[3])
+{
+  init_once();
+  State& s = S();
+  if (!s.on_psnr || padx || pady) return false;
+  ensure_ctx(rec->getWidth(), rec->getHeight());
+  if (!s.h) return false;
+  // two of the reserved slots: the original and the reconstruction as they are on the host now (after the in-loop filters)
+  const int a = (int)s.slots.size() - 3, b = (int)s.slots.size() - 4;
+  s.slots[a].yuv = nullptr; s.slots[b].yuv = nullptr;
+  CK(tvc_pic_upload(s.h, a, org->getLumaAddr(), org->getStride(), org->getCbAddr(), org->getCrAddr(), org->getCStride(), 0));
+  CK(tvc_pic_upload(s.h, b, rec->getLumaAddr(), rec->getStride(), rec->getCbAddr(), rec->getCrAddr(), rec->getCStride(), 0));
+  uint64_t v[3];
+  CK(tvc_pic_ssd(s.h, a, b, v));
+  ssd[0] = v[0]; ssd[1] = v[1]; ssd[2] = v[2];
+  s.n_psnr++;
   return true;
 }
 

@@ -106,6 +106,11 @@ bool tlibcuda_template_sad(TComDataCU* cu, TComPic* refPic, unsigned partAddr, i
 class TComPicYuv;
 bool tlibcuda_pic_hash(TComPicYuv& pic, int method, unsigned char digest[3][16]);
 
+/* TEncGOP::xCalculateAddPSNR (TEncGOP.cpp:1582-1641; TVC_HM=...,psnr): the three UInt64 sums of squared differences between the original
+ * and the final reconstruction from one device call (tvc_pic_ssd); the PSNR arithmetic in doubles stays the reference's.  Pictures
+ * with conformance padding are left to the reference's loops. */
+bool tlibcuda_pic_ssd(TComPicYuv* org, TComPicYuv* rec, int padx, int pady, unsigned long long ssd[3]);
+
 /* ---- frame sharding of all-intra sequences (thevc_b200/host/shard_encode.py).  TVC_POC_OFFSET=k: this process
  * encodes the frames from input frame k on (-fs k) as POC k, k+1, ... (TEncTop::m_iPOCLast starts at k-1, TEncTop.cpp:54; the
  * frame limit of compressGOP, TEncGOP.cpp:211, moves with it) and, for k > 0, writes no VPS/SPS/PPS (m_bSeqFirst,

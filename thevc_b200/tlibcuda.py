@@ -277,7 +277,7 @@ class TLibCuda:
         self._ck(self.L.tvc_me_frame_stats(self.h, ptr(st)))
         if self.L.tvc_me_uses_tables(self.h):      # TVC_ME_FUSED=0: SAD tables in HBM
             return {"form": "sad-tables", "search_granules": int(st[0]), "raster_served_candidates": int(st[1]), "raster_candidates": int(st[2])}
-        return {"form": "group-search", "candidate_sads": int(st[0]), "sample_differences": int(st[1])}
+        return {"form": "group-search", "candidate_sads": int(st[0]), "sample_differences": int(st[1]), "frac_jobs_served_at_cu_level": int(st[2])}
 
     # ------------------------------------------------------------------ TQ
     def fwd_transform_batch(self, resi_slot: int, tus: Sequence[TU], coef_elems: int) -> np.ndarray:
