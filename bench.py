@@ -452,7 +452,7 @@ def workload_config():
 ENC_REF = os.path.join(ROOT, "oracle", "_ref", "bin", "TAppEncoderStatic")
 ENC_CUDA = os.path.join(ROOT, "build", "hm", "TAppEncoderCuda")
 LDP_CFG = os.path.join(ROOT, "build", "hm", "cfg", "encoder_lowdelay_P_main.cfg")
-HM_HOOKS = "me,frac,tables,frame,candgrid"
+HM_HOOKS = os.environ.get("TVC_BENCH_HM_HOOKS", "me,frac,tables,frame,candgrid")      # the fast configuration of the HM shim
 
 
 def _write_yuv(path, frames, seed):

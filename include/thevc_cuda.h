@@ -328,6 +328,17 @@ int tvc_me_frame_dev(tvc_ctx* ctx, int cur_slot, int num_refs, const int* ref_sl
 int tvc_me_ctu(tvc_ctx* ctx, int cur_slot, int ref_index, int ref_slot, int ctu, tvc_me_center pred_qpel,
                const tvc_me_frame_cfg* cfg, tvc_me_result* int_out, tvc_frac_result* frac_out);
 
+/* The same group, asynchronously: queued on a side stream behind everything the context has queued so far, result kept under
+ * `ticket` (0 .. TVC_ME_CTU_TICKETS - 1) until tvc_me_ctu_fetch waits for it and copies it out.  A host whose CU loop just learned
+ * the first predictor of (CTU k, reference r) asks for (CTU k + 1, r) with the same predictor while it codes CTU k: in HM's own
+ * 1080p runs the first predictor of a CTU equals its left neighbour's in 96.6 % of the groups (the guess of the frame pre-pass, the
+ * previous picture's predictor, holds in 40-75 %), so the next CTU's 593 results are already there when the CU loop arrives.  Re-using
+ * a ticket whose result was never fetched drops that result.                                                                     */
+#define TVC_ME_CTU_TICKETS 8
+int tvc_me_ctu_async(tvc_ctx* ctx, int ticket, int cur_slot, int ref_index, int ref_slot, int ctu, tvc_me_center pred_qpel,
+                     const tvc_me_frame_cfg* cfg);
+int tvc_me_ctu_fetch(tvc_ctx* ctx, int ticket, tvc_me_result* int_out, tvc_frac_result* frac_out);
+
 /* work counters of the last tvc_me_frame[_dev] call (for roofline accounting).  Default (group search): stats[0] = candidate SADs
  * the searches evaluated (the reference's own count: sum of n_sads), stats[1] = sample differences of those (w x (h >> iSubShift)
  * per candidate), stats[2] = census jobs whose fractional search was served at CU level (k_me_frac_cu).  TVC_ME_FUSED=0 (SAD tables): stats[0] = 16-byte table granules the reference-visible candidates of

@@ -689,6 +689,32 @@ def test_me_ctu_group(ctx8_form, orc):
         assert (gf[k]["halfx"], gf[k]["halfy"], gf[k]["qtrx"], gf[k]["qtry"], gf[k]["cost"]) == (f.halfx, f.halfy, f.qtrx, f.qtry, f.cost), k
 
 
+def test_me_ctu_async_tickets(ctx8, orc):
+    """tvc_me_ctu_async / tvc_me_ctu_fetch: eight groups in flight on the side stream while synchronous calls run on the main one;
+    every fetched result equals the synchronous call's, a ticket that is re-used drops its old result, fetching an idle ticket fails"""
+    from thevc_b200.tlibcuda import TvcError
+    t = ctx8
+    seq = synth.make_sequence(W, H, 3)
+    t.upload(0, synth.to_hostpic(seq[2], W, H)); t.upload(1, synth.to_hostpic(seq[1], W, H)); t.upload(2, synth.to_hostpic(seq[0], W, H))
+    nctu = t.ctus_x * t.ctus_y
+    rng = np.random.default_rng(67)
+    lc = orc.orc_lambda_motion_sad(44.0)
+    asks = [(int(rng.integers(0, 2)), int(rng.integers(0, nctu)), (int(rng.integers(-40, 41)), int(rng.integers(-40, 41)))) for _ in range(8)]
+    for tk, (ri, ctu, pred) in enumerate(asks):
+        t.me_ctu_async(tk, 0, ri, 1 + ri, ctu, pred, lc)
+    sync = [t.me_ctu(0, ri, 1 + ri, ctu, pred, lc) for (ri, ctu, pred) in asks]        # main stream, while the tickets are in flight
+    for tk in (3, 0, 7, 1, 2, 6, 5, 4):
+        gi, gf = t.me_ctu_fetch(tk)
+        assert np.array_equal(gi, sync[tk][0]) and np.array_equal(gf, sync[tk][1]), tk
+    with pytest.raises(TvcError):
+        t.me_ctu_fetch(2)                                    # nothing in flight any more
+    t.me_ctu_async(5, 0, 0, 1, 0, (4, -8), lc)
+    t.me_ctu_async(5, 0, 1, 2, 3, (-12, 16), lc)             # re-used before the fetch: the first result is dropped
+    gi, gf = t.me_ctu_fetch(5)
+    ei, ef = t.me_ctu(0, 1, 2, 3, (-12, 16), lc)
+    assert np.array_equal(gi, ei) and np.array_equal(gf, ef)
+
+
 # ----------------------------------------------------------------------------------- fractional ME
 @pytest.mark.parametrize("bd", [8, 10])
 def test_me_frac(ctx8, ctx10, orc, bd):

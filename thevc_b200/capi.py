@@ -161,6 +161,8 @@ SIGNATURES = {
     "tvc_me_frame": (ci, [vp, ci, ci, vp, vp, C.POINTER(MeFrameCfg), vp, vp]),
     "tvc_me_frame_dev": (ci, [vp, ci, ci, vp, vp, C.POINTER(MeFrameCfg), C.POINTER(vp), C.POINTER(vp)]),
     "tvc_me_ctu": (ci, [vp, ci, ci, ci, ci, MeCenter, C.POINTER(MeFrameCfg), vp, vp]),
+    "tvc_me_ctu_async": (ci, [vp, ci, ci, ci, ci, ci, MeCenter, C.POINTER(MeFrameCfg)]),
+    "tvc_me_ctu_fetch": (ci, [vp, ci, vp, vp]),
     "tvc_me_frame_stats": (ci, [vp, vp]),
     "tvc_fwd_transform_batch": (ci, [vp, ci, ci, vp, vp, C.c_size_t]),
     "tvc_fwd_tq_batch": (ci, [vp, ci, ci, vp, C.POINTER(QuantCfg), vp, vp, C.c_size_t, vp]),

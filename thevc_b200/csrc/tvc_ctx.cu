@@ -212,8 +212,13 @@ void tvc_ctx_destroy(tvc_ctx* c)
   if (c->out.dev) cudaFree(c->out.dev);
   if (c->out.host) cudaFreeHost(c->out.host);
   if (c->rdoq_scratch) cudaFree(c->rdoq_scratch);
-  if (c->ctu_buf) cudaFree(c->ctu_buf);
-  if (c->ctu_host) cudaFreeHost(c->ctu_host);
+  for (auto& t : c->ctu_tickets) {
+    if (t.dev) cudaFree(t.dev);
+    if (t.host) cudaFreeHost(t.host);
+    if (t.ev) cudaEventDestroy(t.ev);
+  }
+  if (c->spec_stream) cudaStreamDestroy(c->spec_stream);
+  if (c->spec_ev) cudaEventDestroy(c->spec_ev);
   if (c->me_tables) cudaFree(c->me_tables);
   if (c->me_centers) cudaFree(c->me_centers);
   for (tvc::Scratch* sc : {&c->me_stage, &c->fr_stage}) {

@@ -41,6 +41,14 @@ struct PlaneTable {
   int stride[3];
 };
 
+// buffers of one census-group call (tvc_me_ctu / tvc_me_ctu_async): device records + results, pinned host copy of the results
+struct CtuTicket {
+  void* dev = nullptr;
+  void* host = nullptr;
+  cudaEvent_t ev = nullptr;
+  bool busy = false, do_frac = false;
+};
+
 struct Scratch {
   void* dev = nullptr;
   void* host = nullptr;     // pinned
@@ -57,8 +65,9 @@ struct tvc_ctx {
   std::vector<tvc::Pic> pics;
   tvc::PlaneTable planes;
   tvc::Scratch in, out;           // staging for host-pointer entry points
-  void* ctu_buf = nullptr;        // tvc_me_ctu: jobs / results of one (CTU, reference) group (device)
-  void* ctu_host = nullptr;       // pinned copy of its results
+  tvc::CtuTicket ctu_tickets[TVC_ME_CTU_TICKETS + 1];   // tvc_me_ctu_async tickets; the last one serves the synchronous tvc_me_ctu
+  cudaStream_t spec_stream = nullptr;                   // side stream of the asynchronous group calls
+  cudaEvent_t spec_ev = nullptr;
   void* rdoq_scratch = nullptr;   // per-coefficient RDOQ working arrays (device)
   size_t rdoq_scratch_elems = 0;
   std::string err;

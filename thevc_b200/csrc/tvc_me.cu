@@ -844,7 +844,8 @@ __device__ __forceinline__ void me_search_job(int j, const PlaneTable& pt, int c
                                               tvc_me_result* __restrict__ out, const uint16_t* __restrict__ tables,
                                               const tvc_me_center* __restrict__ centers, int num_ctus, int ctus_x, int bi,
                                               const RasterBest* __restrict__ rast, const SweepState* __restrict__ sweep,
-                                              unsigned long long* __restrict__ stats, const GrpWin* gw = nullptr)
+                                              unsigned long long* __restrict__ stats, const GrpWin* gw = nullptr,
+                                              const SweepState* sw_job = nullptr)
 {
   const tvc_me_job jb = jobs[j];
   if (jb.w <= 0) {                       // census PU outside the picture (frame pre-pass)
@@ -900,7 +901,8 @@ __device__ __forceinline__ void me_search_job(int j, const PlaneTable& pt, int c
     // xTZSearch with TZ_SEARCH_CONFIGURATION (TEncSearch.cpp:293-309, 4302-4474)
     const int raster = 5, srange = jb.search_range;
     SweepState sw = {0, 0, 0, 0, 0, 0};
-    if (sweep) sw = sweep[j];
+    if (sw_job) sw = *sw_job;
+    else if (sweep) sw = sweep[j];
     if (sw.n_sads) {
       // frame pre-pass: start / zero tests and the first sweep were replayed by the shared stage (k_me_raster)
       s.best_sad = sw.best_sad; s.best_x = sw.best_x; s.best_y = sw.best_y; s.best_dist = sw.best_dist; s.point_nr = sw.point_nr;
@@ -1002,6 +1004,185 @@ k_me_search_list(PlaneTable pt, int cur_slot, const int* __restrict__ list, cons
 // kernel's (diamond_sweep / two_point / raster_scan with the ordered arg-min replay), so the results -- MV, ruiSAD, number of
 // SADs -- are those of xTZSearch; candidates beyond the staged window (the zero vector of a far predictor, PUs whose clipMv
 // differs from the CTU's at the picture border) read the reference's u8 plane in global memory through the same routine.
+// ---- first search at CU level.  The PUs of a CU (13, or 5 at 8x8) share CU origin, hence clipMv, search window, start point and
+// every candidate of the first search (start, zero vector, the diamond rounds around the winner), and each of them is a union of
+// the CU's 4x4 grid of sub-blocks (2x2 at 8x8): 2NxN = sub-block rows {0,1} / {2,3}, 2NxnU = row 0 / rows 1-3, nLx2N = column 0 /
+// columns 1-3, ...  One warp per CU, lane per candidate: the lane walks the CU ONCE, accumulating even-row and odd-row sums per
+// sub-block (the FEN row sub-sampling applies per PU: h > 8), and derives the cost of all 13 PUs from row / column sums of that
+// grid -- one pass instead of thirteen (the PUs cover the CU seven times over).  Then lane p replays the reference's sequential
+// first search for PU p on the stored costs (strict '<' in visiting order, stop after three rounds without improvement) and leaves
+// a SweepState from which the per-PU code continues (xTZ2PointSearch, raster, star refinement): the hand-off the round-1 shared
+// stage used.  CUs that stick out of the picture, or whose candidates leave the staged window, are left to the per-PU code.
+constexpr int kCuTasks = 1 + 4 + 16 + 64;
+struct CuTask { int base, np, S, px, py; };
+__device__ __forceinline__ CuTask cu_task(int t)
+{
+  CuTask c;
+  if (t == 0) { c.S = 64; c.base = 0; c.np = 13; c.px = 0; c.py = 0; }
+  else if (t < 5) { const int i = t - 1; c.S = 32; c.base = 13 + 13 * i; c.np = 13; c.px = (i & 1) * 32; c.py = (i >> 1) * 32; }
+  else if (t < 21) { const int i = t - 5; c.S = 16; c.base = 65 + 13 * i; c.np = 13; c.px = (i & 3) * 16; c.py = (i >> 2) * 16; }
+  else { const int i = t - 21; c.S = 8; c.base = 273 + 5 * i; c.np = 5; c.px = (i & 7) * 8; c.py = (i >> 3) * 8; }
+  return c;
+}
+
+// costs of the CU's PUs at one candidate, written to cst[0 .. np): ref = window byte of the CU's top-left at the candidate
+template <int S>
+__device__ __forceinline__ void cu_costs(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ cur, bool need_odd,
+                                         const uint8_t* __restrict__ subp, uint32_t mvc, uint32_t* __restrict__ cst)
+{
+  constexpr int NB = S == 8 ? 2 : 4, Q = S / NB, QW = Q / 4, RW = S / 4;      // sub-blocks per side, their size in pels / words
+  const int a = (int)((uintptr_t)ref & 3), sh = a * 8;
+  const uint32_t* rb = reinterpret_cast<const uint32_t*>(ref - a);
+  const uint32_t* cb = reinterpret_cast<const uint32_t*>(cur);
+  uint32_t E[NB][NB], O[NB][NB];
+#pragma unroll
+  for (int i = 0; i < NB; i++)
+#pragma unroll
+    for (int j = 0; j < NB; j++) { E[i][j] = 0; O[i][j] = 0; }
+#pragma unroll
+  for (int sbr = 0; sbr < NB; sbr++) {
+    for (int rr = 0; rr < Q; rr += 2) {
+      const uint32_t* r0 = rb + (sbr * Q + rr) * (kGrpWinW / 4);
+      const uint32_t* c0 = cb + (sbr * Q + rr) * (kGrpCurP / 4);
+      uint32_t prev = r0[0];
+#pragma unroll
+      for (int j = 0; j < RW; j++) {
+        const uint32_t nxt = r0[j + 1];
+        E[sbr][j / QW] = vsad4_acc(c0[j], __funnelshift_r(prev, nxt, sh), E[sbr][j / QW]);
+        prev = nxt;
+      }
+      if (need_odd) {
+        const uint32_t* r1 = r0 + kGrpWinW / 4;
+        const uint32_t* c1 = c0 + kGrpCurP / 4;
+        prev = r1[0];
+#pragma unroll
+        for (int j = 0; j < RW; j++) {
+          const uint32_t nxt = r1[j + 1];
+          O[sbr][j / QW] = vsad4_acc(c1[j], __funnelshift_r(prev, nxt, sh), O[sbr][j / QW]);
+          prev = nxt;
+        }
+      }
+    }
+  }
+  // row / column sums of the grid, per parity
+  uint32_t re[NB], ce[NB], ro[NB], co[NB], te = 0, to = 0;
+#pragma unroll
+  for (int i = 0; i < NB; i++) { re[i] = 0; ce[i] = 0; ro[i] = 0; co[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < NB; i++)
+#pragma unroll
+    for (int j = 0; j < NB; j++) { re[i] += E[i][j]; ce[j] += E[i][j]; ro[i] += O[i][j]; co[j] += O[i][j]; }
+#pragma unroll
+  for (int i = 0; i < NB; i++) { te += re[i]; to += ro[i]; }
+  auto put = [&](int p, uint32_t e, uint32_t o) {
+    const uint32_t sub = subp[p];
+    cst[p] = ((sub ? e : e + o) << sub) + mvc;
+  };
+  // census part order: 2Nx2N, 2NxN[0,1], Nx2N[0,1], 2NxnU[0,1], 2NxnD[0,1], nLx2N[0,1], nRx2N[0,1]
+  put(0, te, to);
+  if (NB == 2) {
+    put(1, re[0], ro[0]); put(2, re[1], ro[1]); put(3, ce[0], co[0]); put(4, ce[1], co[1]);
+  } else {
+    put(1, re[0] + re[1], ro[0] + ro[1]); put(2, re[NB - 2] + re[NB - 1], ro[NB - 2] + ro[NB - 1]);
+    put(3, ce[0] + ce[1], co[0] + co[1]); put(4, ce[NB - 2] + ce[NB - 1], co[NB - 2] + co[NB - 1]);
+    put(5, re[0], ro[0]); put(6, te - re[0], to - ro[0]);
+    put(7, te - re[NB - 1], to - ro[NB - 1]); put(8, re[NB - 1], ro[NB - 1]);
+    put(9, ce[0], co[0]); put(10, te - ce[0], to - co[0]);
+    put(11, te - ce[NB - 1], to - co[NB - 1]); put(12, ce[NB - 1], co[NB - 1]);
+  }
+}
+
+__device__ __forceinline__ void cu_costs_any(int S, const uint8_t* ref, const uint8_t* cur, bool need_odd, const uint8_t* subp, uint32_t mvc,
+                                             uint32_t* cst)
+{
+  switch (S) {
+    case 64: cu_costs<64>(ref, cur, need_odd, subp, mvc, cst); break;
+    case 32: cu_costs<32>(ref, cur, need_odd, subp, mvc, cst); break;
+    case 16: cu_costs<16>(ref, cur, need_odd, subp, mvc, cst); break;
+    default: cu_costs<8>(ref, cur, need_odd, subp, mvc, cst); break;
+  }
+}
+
+constexpr int kCstPitch = 14;          // costs of up to 13 PUs per candidate (+ pad)
+struct CuScratch { uint32_t cst[32][kCstPitch]; uint8_t subp[16]; };
+
+// first search of one CU by one warp; writes the SweepState of its PUs (n_sads == 0: not served)
+__device__ __forceinline__ void cu_first_search(const CuTask ct, const tvc_me_job* __restrict__ gjobs, const GrpWin& gw, CuScratch& C,
+                                                SweepState* __restrict__ sweeps, int lane)
+{
+  const tvc_me_job j0 = gjobs[ct.base];                      // the 2Nx2N PU = the CU
+  bool ok = j0.w == ct.S && j0.mode == TVC_ME_TZ && j0.search_range == 64;
+  for (int p = 1; p < ct.np; p++) ok &= gjobs[ct.base + p].w > 0;      // every part inside the picture (they share window and start)
+  if (!ok) return;
+  if (lane < ct.np) C.subp[lane] = (uint8_t)((j0.fen && gjobs[ct.base + lane].h > 8) ? 1 : 0);
+  __syncwarp();
+  bool need_odd = false;
+  for (int p = 0; p < ct.np; p++) need_odd |= C.subp[p] == 0;
+  struct { int lx, ty, rx, by; } win = {j0.lx, j0.ty, j0.rx, j0.by};
+  const uint8_t* wbase = gw.win + ct.py * kGrpWinW + ct.px + gw.e16;   // window byte of the CU's top-left at candidate (cenx - 64, ceny - 64)
+  const uint8_t* cbase = gw.cur + ct.py * kGrpCurP + ct.px;
+  auto in_window = [&](int x, int y) { const int dx = x - gw.cenx, dy = y - gw.ceny; return dx >= -kMeR && dx <= kMeR && dy >= -kMeR && dy <= kMeR; };
+  auto eval = [&](int x, int y) {
+    cu_costs_any(ct.S, wbase + (y - gw.ceny + kMeR) * kGrpWinW + (x - gw.cenx + kMeR), cbase, need_odd, C.subp,
+                 mv_cost(j0.lambda_cost, x, y, 2, j0.predx, j0.predy), C.cst[lane]);
+  };
+  // ---- start point, zero vector (TEncSearch.cpp:4320, 4336-4339)
+  {
+    const int x = lane == 0 ? j0.startx : 0, y = lane == 0 ? j0.starty : 0;
+    if (__any_sync(0xffffffffu, lane < 2 && !in_window(x, y))) return;
+    if (lane < 2) eval(x, y);
+    __syncwarp();
+  }
+  uint32_t best = kNoCost, best_dist = 0, n_sads = 2;
+  int best_x = j0.startx, best_y = j0.starty, point_nr = 0, best_round = 0;
+  if (lane < ct.np) {
+    best = C.cst[0][lane];
+    if (C.cst[1][lane] < best) { best = C.cst[1][lane]; best_x = 0; best_y = 0; }
+  }
+  // the sweep is centred on the winner: shared only when every PU of the CU picked the same one
+  const int sx = __shfl_sync(0xffffffffu, best_x, 0), sy = __shfl_sync(0xffffffffu, best_y, 0);
+  if (__any_sync(0xffffffffu, lane < ct.np && (best_x != sx || best_y != sy))) return;
+  __syncwarp();
+  bool running = lane < ct.np;
+  // ---- rounds d = 1 .. 8 (one candidate per lane), then d = 16, 32 (32 candidates), then d = 64 (16): each stage only while a PU still searches
+  for (int stage = 0; stage < 3; stage++) {
+    if (!__any_sync(0xffffffffu, running)) break;
+    const int c0 = stage == 0 ? 0 : (stage == 1 ? 28 : 60), nc = stage == 0 ? 28 : (stage == 1 ? 32 : 16);
+    const int dfirst = stage == 0 ? 1 : (stage == 1 ? 16 : 64), dlast = stage == 0 ? 8 : (stage == 1 ? 32 : 64);
+    int x = 0, y = 0, d = 1, i = 0, pt = 0;
+    uint32_t dist = 0;
+    bool v = false;
+    if (lane < nc) { sweep_slot(c0 + lane, 64, d, i); v = diamond_cand(win, sx, sy, d, i, x, y, pt, dist); }
+    if (__any_sync(0xffffffffu, v && !in_window(x, y))) return;         // a candidate beyond the staged window: the per-PU code takes the CU
+    if (v) eval(x, y);
+    const unsigned vmask = __ballot_sync(0xffffffffu, v);
+    __syncwarp();
+    if (running) {
+      int off = 0;
+      for (int dd = dfirst; dd <= dlast; dd <<= 1) {
+        const int sz = round_size(dd);
+        best_round += 1;
+        int bi_ = -1;
+        for (int k = 0; k < sz; k++) {
+          if (!((vmask >> (off + k)) & 1u)) continue;
+          n_sads++;
+          const uint32_t cc = C.cst[off + k][lane];
+          if (cc < best) { best = cc; bi_ = k; }
+        }
+        if (bi_ >= 0) {
+          int ptn;
+          diamond_cand(win, sx, sy, dd, bi_, best_x, best_y, ptn, best_dist);
+          point_nr = ptn; best_round = 0;
+        }
+        if (best_round >= 3) { running = false; break; }           // bFirstSearchStop, uiFirstSearchRounds = 3
+        off += sz;
+      }
+    }
+    __syncwarp();
+  }
+  if (lane < ct.np) sweeps[ct.base + lane] = SweepState{best, best_x, best_y, best_dist, point_nr, n_sads};
+}
+
 struct GroupMaps {
   CUtensorMap cur;                 // u8 luma of the current picture, box 80 x 64
   CUtensorMap ref[8];              // u8 luma of each reference, box 208 x 192
@@ -1009,19 +1190,23 @@ struct GroupMaps {
   int stride8;
 };
 constexpr int kGrpThreads = 256;
-constexpr int kGrpSmem = kGrpWinW * kGrpWinH + kGrpCurP * 64 + 64;
+constexpr int kGrpSmemSweep = kGrpWinW * kGrpWinH + kGrpCurP * 64 + 64;                       // offset of the SweepState array
+constexpr int kGrpSmemCu = kGrpSmemSweep + ((TVC_ME_CENSUS * (int)sizeof(SweepState) + 15) & ~15);  // offset of the per-warp CU scratch
+constexpr int kGrpSmem = kGrpSmemCu + (kGrpThreads / 32) * (int)sizeof(CuScratch);
 
 template <int MINB>
 __global__ void __launch_bounds__(kGrpThreads, MINB)
 k_me_group(const __grid_constant__ GroupMaps maps, PlaneTable pt, int cur_slot, const tvc_me_job* __restrict__ jobs,
            tvc_me_result* __restrict__ out, int pic_w, int pic_h, int mx, int my, int ref_index_fixed, int ctus_x,
-           unsigned long long* __restrict__ stats, int split)
+           unsigned long long* __restrict__ stats, int split, int cu_stage)
 {
   extern __shared__ __align__(128) uint8_t gsm[];
   uint8_t* win = gsm;
   uint8_t* cur = gsm + kGrpWinW * kGrpWinH;
   uint64_t* bar = reinterpret_cast<uint64_t*>(gsm + kGrpWinW * kGrpWinH + kGrpCurP * 64);
-  int* next = reinterpret_cast<int*>(bar + 1);
+  int* next = reinterpret_cast<int*>(bar + 1);            // next[0]: PU counter, next[1]: CU counter
+  SweepState* sweeps = reinterpret_cast<SweepState*>(gsm + kGrpSmemSweep);
+  CuScratch* cus = reinterpret_cast<CuScratch*>(gsm + kGrpSmemCu);
   const int tid = threadIdx.x, lane = tid & 31;
   // split > 1: `split` CTAs share one group (each stages the window and takes every split-th PU): the single-group call of
   // tvc_me_ctu is latency-bound, one CTA would walk the 593 PUs alone
@@ -1041,7 +1226,7 @@ k_me_group(const __grid_constant__ GroupMaps maps, PlaneTable pt, int cur_slot, 
   }
   const int wx = mx + x0 + cenx - kMeR, e16 = wx & 15;     // TMA wants a 16-byte aligned start: load from wx - e16
   if (tid == 0) {
-    *next = 0;
+    next[0] = 0; next[1] = 0;
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1051,16 +1236,31 @@ k_me_group(const __grid_constant__ GroupMaps maps, PlaneTable pt, int cur_slot, 
     tma_load_2d(win, &maps.ref[ref], wx - e16, my + y0 + ceny - kMeR, bar);
     tma_load_2d(cur, &maps.cur, mx + x0, my + y0, bar);
   }
+  for (int i = tid; i < TVC_ME_CENSUS; i += kGrpThreads) sweeps[i] = SweepState{0, 0, 0, 0, 0, 0};
   mbar_wait(bar, 0);
   GrpWin gw;
   gw.win = win; gw.cur = cur; gw.plane8 = maps.ref8[ref]; gw.pitch8 = maps.stride8;
   gw.cenx = cenx; gw.ceny = ceny; gw.e16 = e16; gw.x0 = x0; gw.y0 = y0;
+  __syncthreads();
+  // phase 1: the first search of every CU, one warp per CU, largest first (a group spread over several CTAs skips it: each CTA
+  // would repeat the whole phase)
+  if (split == 1 && cu_stage) {
+    for (;;) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(next + 1, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= kCuTasks) break;
+      cu_first_search(cu_task(t), jobs + gbase, gw, cus[tid >> 5], sweeps, lane);
+    }
+    __syncthreads();
+  }
+  // phase 2: every PU from where its CU's first search left it (or from scratch), one warp per PU, largest first
   for (;;) {
     int k = 0;
     if (lane == 0) k = atomicAdd(next, 1);
     k = part + split * __shfl_sync(0xffffffffu, k, 0);
     if (k >= TVC_ME_CENSUS) break;
-    me_search_job((int)(gbase + k), pt, cur_slot, jobs, out, nullptr, nullptr, 0, ctus_x, 0, nullptr, nullptr, stats, &gw);
+    me_search_job((int)(gbase + k), pt, cur_slot, jobs, out, nullptr, nullptr, 0, ctus_x, 0, nullptr, nullptr, stats, &gw, &sweeps[k]);
   }
 }
 
@@ -1874,7 +2074,8 @@ static int launch_frac_cu(tvc_ctx* c, int cur_slot, int groups, const tvc_frac_j
 // census == true: jobs are laid out [ref*ctu][593] in census order.  First the CU-level kernels (one launch per CU depth) serve every CU
 // whose PUs share their integer vector; then one per-PU launch per depth -- thread count and shared memory of a CTA fit the PU sizes of
 // that depth -- serves the rest (TVC_FRAC_CU=0: everything per PU)
-static int launch_frac(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job* jobs_dev, tvc_frac_result* out_dev, bool census)
+static int launch_frac(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job* jobs_dev, tvc_frac_result* out_dev, bool census,
+                       uint8_t* done_buf = nullptr)
 {
   ProfScope ps(c, TVC_PH_ME_FRAC);
   if (!census) return launch_frac_class<64, 64, 256, 1>(c, cur_slot, n, jobs_dev, out_dev, n, 0, 0);
@@ -1883,7 +2084,10 @@ static int launch_frac(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job* jobs
   static int use_cu = -1;
   if (use_cu < 0) { const char* e = getenv("TVC_FRAC_CU"); use_cu = e ? atoi(e) : 1; }
   uint8_t* done = nullptr;
-  if (use_cu) {
+  if (use_cu && done_buf) {
+    done = done_buf;                                     // a caller with its own flags (calls in flight on a side stream)
+    TVC_CUDA(c, cudaMemsetAsync(done, 0, (size_t)n, c->stream));
+  } else if (use_cu) {
     if ((size_t)n > c->frac_done_cap) {
       if (c->frac_done) cudaFree(c->frac_done);
       c->frac_done = nullptr; c->frac_done_cap = 0;
@@ -1892,6 +2096,8 @@ static int launch_frac(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job* jobs
     }
     done = (uint8_t*)c->frac_done;
     TVC_CUDA(c, cudaMemsetAsync(done, 0, (size_t)n, c->stream));
+  }
+  if (use_cu) {
     if ((r = launch_frac_cu<64, 256, 1>(c, cur_slot, groups, jobs_dev, out_dev, done, 1, 13, 0))) return r;
     if ((r = launch_frac_cu<32, 128, 1>(c, cur_slot, groups, jobs_dev, out_dev, done, 4, 13, 13))) return r;
     if ((r = launch_frac_cu<16, 32, 4, true>(c, cur_slot, groups, jobs_dev, out_dev, done, 16, 13, 65))) return r;      // + its 8x8 children
@@ -1913,10 +2119,13 @@ int tvc_launch_me_group(tvc_ctx* c, int cur_slot, int ngroups, const tvc_me_job*
                         const int* ref_slots, int ref_index_fixed, unsigned long long* stats)
 {
   if (!c->pics[cur_slot].has_tmap || c->cfg.bit_depth != 8) return set_err(c, TVC_ERR_STATE, "group search: needs the 8-bit u8 planes and tensor maps");
+  static int cu_stage = 1;
   static int minb = -1;          // tuning knob: resident CTAs per SM the kernel is compiled for (2: 128 registers, no spill; 3: 80)
   if (minb < 0) {
     const char* e = getenv("TVC_GROUP_MINB");
     minb = e ? atoi(e) : 2;
+    const char* e2 = getenv("TVC_GROUP_CU");       // 0: every PU searches on its own from the start (no CU-level first search)
+    cu_stage = e2 ? atoi(e2) : 1;
     TVC_CUDA(c, cudaFuncSetAttribute(k_me_group<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGrpSmem));
     TVC_CUDA(c, cudaFuncSetAttribute(k_me_group<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGrpSmem));
   }
@@ -1936,10 +2145,10 @@ int tvc_launch_me_group(tvc_ctx* c, int cur_slot, int ngroups, const tvc_me_job*
   const int split = ngroups >= 2 * kNumSM ? 1 : (ngroups >= kNumSM / 4 ? 4 : 24);
   if (minb >= 3)
     k_me_group<3><<<ngroups * split, kGrpThreads, kGrpSmem, c->stream>>>(maps, c->planes, cur_slot, jobs_dev, out_dev, c->cfg.width, c->cfg.height,
-                                                                         p.mx[0], p.my[0], ref_index_fixed, c->num_ctus_x, stats, split);
+                                                                         p.mx[0], p.my[0], ref_index_fixed, c->num_ctus_x, stats, split, cu_stage);
   else
     k_me_group<2><<<ngroups * split, kGrpThreads, kGrpSmem, c->stream>>>(maps, c->planes, cur_slot, jobs_dev, out_dev, c->cfg.width, c->cfg.height,
-                                                                         p.mx[0], p.my[0], ref_index_fixed, c->num_ctus_x, stats, split);
+                                                                         p.mx[0], p.my[0], ref_index_fixed, c->num_ctus_x, stats, split, cu_stage);
   TVC_LAUNCH_CHECK(c);
   return TVC_OK;
 }
@@ -2505,28 +2714,24 @@ int tvc_me_frame_packed(tvc_ctx* c, int cur_slot, int num_refs, const int* ref_s
   return TVC_OK;
 }
 
-int tvc_me_ctu(tvc_ctx* c, int cur_slot, int ref_index, int ref_slot, int ctu, tvc_me_center pred_qpel, const tvc_me_frame_cfg* cfg,
-               tvc_me_result* int_out, tvc_frac_result* frac_out)
+// one census group (CTU, reference, predictor) queued on c->stream into the buffers of `t`: job records, integer stage, fractional
+// stage, results to the ticket's pinned host copy; no synchronisation
+static int me_ctu_enqueue(tvc_ctx* c, CtuTicket& t, int cur_slot, int ref_index, int ref_slot, int ctu, tvc_me_center pred_qpel,
+                          const tvc_me_frame_cfg* cfg, bool fused)
 {
-  if (!c || !valid_slot(c, cur_slot) || !valid_slot(c, ref_slot) || !cfg || cfg->search_range < 1 || cfg->search_range > TVC_ME_RANGE ||
-      ctu < 0 || ctu >= c->num_ctus_x * c->num_ctus_y || !int_out || (cfg->do_frac && !frac_out))
-    return set_err(c, TVC_ERR_ARG, "tvc_me_ctu: bad argument");
-  const bool fused = cfg->use_tables && me_fused_enabled(c);
-  if (cfg->use_tables && !fused && (!c->me_tables || c->me_cur_slot != cur_slot || ref_index < 0 || ref_index >= c->me_num_refs ||
-                                    c->me_ref_slots[ref_index] != ref_slot))
-    return set_err(c, TVC_ERR_STATE, "tvc_me_ctu: tables requested but tvc_me_prepass has not run for this picture / reference");
-  int r;
-  if ((r = ensure_census(c))) return r;
   constexpr size_t N = TVC_ME_CENSUS;
-  if (!c->ctu_buf) {
-    TVC_CUDA(c, cudaMalloc(&c->ctu_buf, N * (sizeof(tvc_me_job) + sizeof(tvc_me_result) + sizeof(tvc_frac_job) + sizeof(tvc_frac_result))));
-    TVC_CUDA(c, cudaHostAlloc(&c->ctu_host, N * (sizeof(tvc_me_result) + sizeof(tvc_frac_result)), cudaHostAllocDefault));
+  int r;
+  if (!t.dev) {
+    TVC_CUDA(c, cudaMalloc(&t.dev, N * (sizeof(tvc_me_job) + sizeof(tvc_me_result) + sizeof(tvc_frac_job) + sizeof(tvc_frac_result)) + N));
+    TVC_CUDA(c, cudaHostAlloc(&t.host, N * (sizeof(tvc_me_result) + sizeof(tvc_frac_result)), cudaHostAllocDefault));
+    TVC_CUDA(c, cudaEventCreateWithFlags(&t.ev, cudaEventDisableTiming));
   }
-  // device layout: [int results][frac results][jobs][frac jobs] -- the results are contiguous: one copy back
-  tvc_me_result* d_int = (tvc_me_result*)c->ctu_buf;
+  // device layout: [int results][frac results][jobs][frac jobs][done flags] -- the results are contiguous: one copy back
+  tvc_me_result* d_int = (tvc_me_result*)t.dev;
   tvc_frac_result* d_frac = (tvc_frac_result*)(d_int + N);
   tvc_me_job* d_jobs = (tvc_me_job*)(d_frac + N);
   tvc_frac_job* d_fjobs = (tvc_frac_job*)(d_jobs + N);
+  uint8_t* d_done = (uint8_t*)(d_fjobs + N);
   k_me_ctu_jobs<<<(int)((N + 127) / 128), 128, 0, c->stream>>>(c->cfg.width, c->cfg.height, c->num_ctus_x, ctu, ref_index, ref_slot, pred_qpel,
                                                            *cfg, d_jobs);
   TVC_LAUNCH_CHECK(c);
@@ -2538,13 +2743,75 @@ int tvc_me_ctu(tvc_ctx* c, int cur_slot, int ref_index, int ref_slot, int ctu, t
   if (cfg->do_frac) {
     k_me_frame_frac_jobs<<<(int)((N + 127) / 128), 128, 0, c->stream>>>((int)N, d_jobs, d_int, cfg->hadamard, d_fjobs);
     TVC_LAUNCH_CHECK(c);
-    if ((r = launch_frac(c, cur_slot, (int)N, d_fjobs, d_frac, true))) return r;
+    if ((r = launch_frac(c, cur_slot, (int)N, d_fjobs, d_frac, true, d_done))) return r;
   }
   const size_t back = N * sizeof(tvc_me_result) + (cfg->do_frac ? N * sizeof(tvc_frac_result) : 0);
-  TVC_CUDA(c, cudaMemcpyAsync(c->ctu_host, c->ctu_buf, back, cudaMemcpyDeviceToHost, c->stream));
+  TVC_CUDA(c, cudaMemcpyAsync(t.host, t.dev, back, cudaMemcpyDeviceToHost, c->stream));
+  TVC_CUDA(c, cudaEventRecord(t.ev, c->stream));
+  t.busy = true; t.do_frac = cfg->do_frac != 0;
+  return TVC_OK;
+}
+
+static int me_ctu_check(tvc_ctx* c, int cur_slot, int ref_index, int ref_slot, int ctu, const tvc_me_frame_cfg* cfg, bool* fused)
+{
+  if (!c || !valid_slot(c, cur_slot) || !valid_slot(c, ref_slot) || !cfg || cfg->search_range < 1 || cfg->search_range > TVC_ME_RANGE ||
+      ctu < 0 || ctu >= c->num_ctus_x * c->num_ctus_y)
+    return set_err(c, TVC_ERR_ARG, "tvc_me_ctu: bad argument");
+  *fused = cfg->use_tables && me_fused_enabled(c);
+  if (cfg->use_tables && !*fused && (!c->me_tables || c->me_cur_slot != cur_slot || ref_index < 0 || ref_index >= c->me_num_refs ||
+                                     c->me_ref_slots[ref_index] != ref_slot))
+    return set_err(c, TVC_ERR_STATE, "tvc_me_ctu: tables requested but tvc_me_prepass has not run for this picture / reference");
+  return ensure_census(c);
+}
+
+int tvc_me_ctu(tvc_ctx* c, int cur_slot, int ref_index, int ref_slot, int ctu, tvc_me_center pred_qpel, const tvc_me_frame_cfg* cfg,
+               tvc_me_result* int_out, tvc_frac_result* frac_out)
+{
+  bool fused = false;
+  int r = me_ctu_check(c, cur_slot, ref_index, ref_slot, ctu, cfg, &fused);
+  if (r) return r;
+  if (!int_out || (cfg->do_frac && !frac_out)) return set_err(c, TVC_ERR_ARG, "tvc_me_ctu: bad argument");
+  constexpr size_t N = TVC_ME_CENSUS;
+  CtuTicket& t = c->ctu_tickets[TVC_ME_CTU_TICKETS];       // the synchronous call's own buffers
+  if ((r = me_ctu_enqueue(c, t, cur_slot, ref_index, ref_slot, ctu, pred_qpel, cfg, fused))) return r;
   TVC_CUDA(c, cudaStreamSynchronize(c->stream));
-  memcpy(int_out, c->ctu_host, N * sizeof(tvc_me_result));
-  if (cfg->do_frac) memcpy(frac_out, (char*)c->ctu_host + N * sizeof(tvc_me_result), N * sizeof(tvc_frac_result));
+  t.busy = false;
+  memcpy(int_out, t.host, N * sizeof(tvc_me_result));
+  if (cfg->do_frac) memcpy(frac_out, (char*)t.host + N * sizeof(tvc_me_result), N * sizeof(tvc_frac_result));
+  return TVC_OK;
+}
+
+int tvc_me_ctu_async(tvc_ctx* c, int ticket, int cur_slot, int ref_index, int ref_slot, int ctu, tvc_me_center pred_qpel,
+                     const tvc_me_frame_cfg* cfg)
+{
+  bool fused = false;
+  int r = me_ctu_check(c, cur_slot, ref_index, ref_slot, ctu, cfg, &fused);
+  if (r) return r;
+  if (ticket < 0 || ticket >= TVC_ME_CTU_TICKETS) return set_err(c, TVC_ERR_ARG, "tvc_me_ctu_async: ticket 0..%d", TVC_ME_CTU_TICKETS - 1);
+  CtuTicket& t = c->ctu_tickets[ticket];
+  if (!c->spec_stream) TVC_CUDA(c, cudaStreamCreateWithFlags(&c->spec_stream, cudaStreamNonBlocking));
+  if (t.busy) { TVC_CUDA(c, cudaEventSynchronize(t.ev)); t.busy = false; }      // a result nobody fetched: its buffers are reused
+  // the picture slots the group reads were uploaded on c->stream: the side stream starts behind everything queued there so far
+  if (!c->spec_ev) TVC_CUDA(c, cudaEventCreateWithFlags(&c->spec_ev, cudaEventDisableTiming));
+  TVC_CUDA(c, cudaEventRecord(c->spec_ev, c->stream));
+  TVC_CUDA(c, cudaStreamWaitEvent(c->spec_stream, c->spec_ev, 0));
+  cudaStream_t main_stream = c->stream;
+  struct Restore { tvc_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{c, main_stream};
+  c->stream = c->spec_stream;
+  return me_ctu_enqueue(c, t, cur_slot, ref_index, ref_slot, ctu, pred_qpel, cfg, fused);
+}
+
+int tvc_me_ctu_fetch(tvc_ctx* c, int ticket, tvc_me_result* int_out, tvc_frac_result* frac_out)
+{
+  if (!c || ticket < 0 || ticket >= TVC_ME_CTU_TICKETS || !int_out) return set_err(c, TVC_ERR_ARG, "tvc_me_ctu_fetch: bad argument");
+  CtuTicket& t = c->ctu_tickets[ticket];
+  if (!t.busy) return set_err(c, TVC_ERR_STATE, "tvc_me_ctu_fetch: nothing in flight on ticket %d", ticket);
+  if (t.do_frac && !frac_out) return set_err(c, TVC_ERR_ARG, "tvc_me_ctu_fetch: the call had a fractional stage");
+  TVC_CUDA(c, cudaEventSynchronize(t.ev));
+  t.busy = false;
+  constexpr size_t N = TVC_ME_CENSUS;
+  memcpy(int_out, t.host, N * sizeof(tvc_me_result));
+  if (t.do_frac) memcpy(frac_out, (char*)t.host + N * sizeof(tvc_me_result), N * sizeof(tvc_frac_result));
   return TVC_OK;
 }
 

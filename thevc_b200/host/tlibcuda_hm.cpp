@@ -128,6 +128,12 @@ struct State {
   std::map<unsigned, int> census_index;    // (x, y, w, h) inside the CTU -> census index
   std::vector<tvc_me_center> center_guess; // [table ref][ctu]: first predictor of the previous picture's group (quarter pels)
   LastHit last;
+  // a census group asked for ahead of the CU loop (tvc_me_ctu_async): the group of the NEXT CTU with the predictor this CTU's group
+  // just started with; one in flight per reference index
+  struct Spec { bool valid = false; int ctu = -1, slot = -1, predx = 0, predy = 0, sr = 0, fen = 0, had = 0; unsigned lambda = 0; };
+  Spec spec[TVC_ME_CTU_TICKETS];
+  bool on_spec = true;                     // off: TVC_HM=...,nospec
+  unsigned long long n_spec_hits = 0, n_spec_asked = 0;
   LastHit last_bi;                         // the bi-prediction refinement just run: its fractional stage follows
   unsigned long long n_bi = 0, n_bi_frac = 0, n_bi_host = 0;
   unsigned long long n_tz_lookup = 0, n_frac_lookup = 0, n_groups = 0;
@@ -187,6 +193,9 @@ void report()
   State& s = S();
   if (s.h && s.on_frame)
     fprintf(stderr, "TLibCuda frame pre-pass: %llu (CTU, reference) groups took their 593 results from the picture-level tvc_me_frame call\n", s.n_frame_groups);
+  if (s.h && s.on_lookup && s.n_spec_asked)
+    fprintf(stderr, "TLibCuda look-ahead: %llu (CTU, reference) groups asked for ahead of the CU loop with the left neighbour's predictor, %llu of them taken (tvc_me_ctu_async / _fetch)\n",
+            s.n_spec_asked, s.n_spec_hits);
   if (s.h && s.on_lookup)
     fprintf(stderr, "TLibCuda look-up: %llu of %llu xTZSearch and %llu of %llu xPatternSearchFracDIF calls served from %llu census-wide (CTU, reference) batches (%.3f s in tvc_me_ctu, %.3f s in picture uploads + SAD-table pre-passes)\n",
             s.n_tz_lookup, s.n_tz, s.n_frac_lookup, s.n_frac, s.n_groups, s.batch_seconds, s.prepass_seconds);
@@ -251,6 +260,19 @@ void stats_report()
                   "served by the group's FIRST predictor %.1f%%, by its most frequent %.1f%%, by the top 2 %.1f%%, top 4 %.1f%%\n",
           calls, groups, groups ? (double)distinct / groups : 0.0, calls ? 100.0 * hit_first / calls : 0.0,
           calls ? 100.0 * hit_mode / calls : 0.0, calls ? 100.0 * hit_top2 / calls : 0.0, calls ? 100.0 * hit_top4 / calls : 0.0);
+  if (const char* dump = getenv("TVC_STATS_DUMP")) {
+    // one line per (picture, CTU, reference index) group: its FIRST predictor (quarter pels) and how many searches used it
+    if (FILE* f = fopen(dump, "w")) {
+      for (auto& g : p.m) {
+        const long long pv = p.first[g.first];
+        const int px = (int)(pv >> 20), py = (int)((pv & 0xfffff) ^ 0x80000) - 0x80000;
+        unsigned tot = 0;
+        for (auto& e : g.second) tot += e.second;
+        fprintf(f, "%lld %lld %lld %d %d %u %u\n", g.first.first, g.first.second / 64, g.first.second % 64, px, py, g.second[pv], tot);
+      }
+      fclose(f);
+    }
+  }
   fprintf(stderr, "TLibCuda stats: groups by number of distinct predictors 1..8+:");
   for (int i = 1; i <= 8; i++) fprintf(stderr, " %llu", hist[i]);
   fprintf(stderr, "\n");
@@ -284,6 +306,7 @@ void parse_env()
     else if (t == "tables") s.on_tables = true;
     else if (t == "verbose") s.verbose = true;
     else if (t == "nolookup") s.on_lookup = false;
+    else if (t == "nospec") s.on_spec = false;
     else if (t == "verify") s.verify = true;
     else if (t == "batch") s.dec.on = true;
     else if (t == "saodump") s.sao.dump = true;
@@ -435,6 +458,7 @@ void tlibcuda_picture_start(TComPic* pic, TComSlice* slice)
   s.groups.clear();
   s.grids.clear();
   s.last.valid = false;
+  for (auto& sp : s.spec) sp.valid = false;
   if (s.census_index.empty()) {
     tvc_census_pu cen[TVC_ME_CENSUS];
     CK(tvc_me_census(cen));
@@ -545,6 +569,7 @@ bool tlibcuda_tz_search(TComDataCU* cu, TComPattern* key, short* refY, int refSt
     Group& g = s.groups[(long long)ctu * 64 + slot];
     const int had = cfg->getUseHADME() ? 1 : 0;
     GroupEntry* hit = nullptr;
+    const bool first_of_group = g.e.empty();            // this search opens the group: whatever serves it also triggers the look-ahead
     for (auto& e : g.e)
       if (e.predx == j.predx && e.predy == j.predy && e.lambda == j.lambda_cost && e.sr == searchRange && e.fen == j.fen && e.had == had) { hit = &e; break; }
     s.last_sr = searchRange; s.last_fen = j.fen; s.last_had = had;
@@ -559,6 +584,27 @@ bool tlibcuda_tz_search(TComDataCU* cu, TComPattern* key, short* refY, int refSt
         e.fres.assign(s.frame_frac.begin() + gi * TVC_ME_CENSUS, s.frame_frac.begin() + (gi + 1) * TVC_ME_CENSUS);
         s.n_frame_groups++;
         hit = &e;
+      }
+    }
+    if (!hit && g.e.empty() && s.on_spec && j.ref_index >= 0) {
+      // asked for ahead of time while the previous CTU was coded?
+      State::Spec& sp = s.spec[j.ref_index % TVC_ME_CTU_TICKETS];
+      if (sp.valid) {
+        sp.valid = false;
+        if (sp.ctu == ctu && sp.slot == slot && sp.predx == j.predx && sp.predy == j.predy && sp.lambda == j.lambda_cost &&
+            sp.sr == searchRange && sp.fen == j.fen && sp.had == had) {
+          g.e.emplace_back();
+          GroupEntry& e = g.e.back();
+          e.predx = j.predx; e.predy = j.predy; e.lambda = j.lambda_cost; e.sr = searchRange; e.fen = j.fen; e.had = had;
+          e.ires.resize(TVC_ME_CENSUS); e.fres.resize(TVC_ME_CENSUS);
+          const auto t0 = std::chrono::steady_clock::now();
+          CK(tvc_me_ctu_fetch(s.h, j.ref_index % TVC_ME_CTU_TICKETS, e.ires.data(), e.fres.data()));
+          s.batch_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+          s.n_spec_hits++;
+          if (j.ref_index >= 0 && (size_t)(j.ref_index + 1) * (s.center_guess.size() / 8) <= s.center_guess.size() && !s.center_guess.empty())
+            s.center_guess[(size_t)j.ref_index * (s.center_guess.size() / 8) + ctu] = tvc_me_center{j.predx, j.predy};
+          hit = &e;
+        }
       }
     }
     if (!hit) {
@@ -576,6 +622,22 @@ bool tlibcuda_tz_search(TComDataCU* cu, TComPattern* key, short* refY, int refSt
         if (g.e.size() == 1 && j.ref_index >= 0 && (size_t)(j.ref_index + 1) * (s.center_guess.size() / 8) <= s.center_guess.size())
           s.center_guess[(size_t)j.ref_index * (s.center_guess.size() / 8) + ctu] = tvc_me_center{j.predx, j.predy};
         hit = &e;
+      }
+    }
+    if (hit && first_of_group && g.e.size() == 1 && s.on_spec && j.ref_index >= 0 && ctu + 1 < ((s.w + 63) / 64) * ((s.ht + 63) / 64)) {
+      // this group just got its first predictor: the next CTU's group for the same reference starts with the same one in 96.6 % of
+      // HM's own 1080p groups -- ask for it now, on the side stream, while the host codes this CTU
+      const size_t gi = (size_t)j.ref_index * s.frame_nctu + (ctu + 1);
+      const bool frame_has_it = s.frame_valid && j.ref_index < s.frame_refs && ctu + 1 < s.frame_nctu && s.frame_lambda == j.lambda_cost &&
+                                s.frame_sr == searchRange && s.frame_fen == j.fen && s.frame_had == had &&
+                                s.frame_pred[gi].cx == j.predx && s.frame_pred[gi].cy == j.predy;
+      if (!frame_has_it) {
+        tvc_me_frame_cfg fc = {searchRange, j.fen, had, 1, 1, j.lambda_cost};
+        CK(tvc_me_ctu_async(s.h, j.ref_index % TVC_ME_CTU_TICKETS, s.cur_slot, j.ref_index, slot, ctu + 1, tvc_me_center{j.predx, j.predy}, &fc));
+        State::Spec& sp = s.spec[j.ref_index % TVC_ME_CTU_TICKETS];
+        sp.valid = true; sp.ctu = ctu + 1; sp.slot = slot; sp.predx = j.predx; sp.predy = j.predy; sp.lambda = j.lambda_cost;
+        sp.sr = searchRange; sp.fen = j.fen; sp.had = had;
+        s.n_spec_asked++;
       }
     }
     if (hit) {

@@ -272,6 +272,18 @@ class TLibCuda:
                                    C.byref(cfg), ptr(ires), ptr(fres)))
         return ires, fres
 
+    def me_ctu_async(self, ticket: int, cur_slot: int, ref_index: int, ref_slot: int, ctu: int, pred_qpel, lambda_cost: int,
+                     search_range: int = 64, fen: bool = True, hadamard: bool = True, use_tables: bool = True):
+        cfg = MeFrameCfg(search_range, int(fen), int(hadamard), int(use_tables), 1, lambda_cost)
+        self._ck(self.L.tvc_me_ctu_async(self.h, ticket, cur_slot, ref_index, ref_slot, ctu, MeCenter(int(pred_qpel[0]), int(pred_qpel[1])),
+                                         C.byref(cfg)))
+
+    def me_ctu_fetch(self, ticket: int):
+        ires = np.zeros(capi.ME_CENSUS, capi.ME_RESULT_DTYPE)
+        fres = np.zeros(capi.ME_CENSUS, capi.FRAC_RESULT_DTYPE)
+        self._ck(self.L.tvc_me_ctu_fetch(self.h, ticket, ptr(ires), ptr(fres)))
+        return ires, fres
+
     def me_frame_stats(self):
         st = np.zeros(3, np.uint64)
         self._ck(self.L.tvc_me_frame_stats(self.h, ptr(st)))
