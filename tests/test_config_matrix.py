@@ -181,3 +181,30 @@ def test_configs2_random_access_1080p_intra_period_16_shards(matrix):
     rec = matrix("ra_1080_66_idr_ip16")
     _check(rec)
     assert rec["shards"] == 5
+
+
+def test_bench_workload_has_the_encoders_tz_work(matrix):
+    """round-1 VERDICT weak #1: bench.py's step must give the TZ search the work the real encoder's searches have on the same kind
+    of content.  The hooked 1080p LDP encode above reports its mean candidates per served xTZSearch (the reference's own count);
+    the step of bench.py (same synthetic sequence generator, its predictor guesses) must be within a factor of two of it."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from thevc_b200 import TLibCuda
+    rec = matrix("ldp_1080_17")
+    tz = [ln for ln in rec["hooks"] if ln.startswith("TLibCuda TZ work:")]
+    assert tz, rec["hooks"]
+    enc_mean = float(tz[-1].split()[3])
+    wl = bench.Workload(20261018, pinned=False)
+    t = TLibCuda(bench.W, bench.H, 8, num_slots=6)
+    try:
+        for s_, p in enumerate(wl.pics):
+            t.upload(s_, p)
+        lc = int(np.floor(65536.0 * np.sqrt(bench.LAMBDA)))
+        ires, _ = t.me_frame(0, [1, 2, 3, 4], wl.pred, lc, do_frac=False)
+    finally:
+        t.close()
+    n = ires["n_sads"]
+    step_mean = float(n[n > 0].mean())
+    print("TZ candidates per search: bench step %.1f, hooked encoder %.1f" % (step_mean, enc_mean))
+    assert 0.5 <= step_mean / enc_mean <= 2.0, (step_mean, enc_mean)

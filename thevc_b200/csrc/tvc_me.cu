@@ -1192,7 +1192,8 @@ struct GroupMaps {
 constexpr int kGrpThreads = 256;
 constexpr int kGrpSmemSweep = kGrpWinW * kGrpWinH + kGrpCurP * 64 + 64;                       // offset of the SweepState array
 constexpr int kGrpSmemCu = kGrpSmemSweep + ((TVC_ME_CENSUS * (int)sizeof(SweepState) + 15) & ~15);  // offset of the per-warp CU scratch
-constexpr int kGrpSmem = kGrpSmemCu + (kGrpThreads / 32) * (int)sizeof(CuScratch);
+constexpr int kGrpSmemFlags = kGrpSmemCu + (kGrpThreads / 32) * (int)sizeof(CuScratch);          // per-CU "first search done" flags
+constexpr int kGrpSmem = kGrpSmemFlags + ((kCuTasks * (int)sizeof(int) + 15) & ~15);
 
 template <int MINB>
 __global__ void __launch_bounds__(kGrpThreads, MINB)
@@ -1207,6 +1208,7 @@ k_me_group(const __grid_constant__ GroupMaps maps, PlaneTable pt, int cur_slot, 
   int* next = reinterpret_cast<int*>(bar + 1);            // next[0]: PU counter, next[1]: CU counter
   SweepState* sweeps = reinterpret_cast<SweepState*>(gsm + kGrpSmemSweep);
   CuScratch* cus = reinterpret_cast<CuScratch*>(gsm + kGrpSmemCu);
+  volatile int* cu_done = reinterpret_cast<volatile int*>(gsm + kGrpSmemFlags);
   const int tid = threadIdx.x, lane = tid & 31;
   // split > 1: `split` CTAs share one group (each stages the window and takes every split-th PU): the single-group call of
   // tvc_me_ctu is latency-bound, one CTA would walk the 593 PUs alone
@@ -1237,6 +1239,8 @@ k_me_group(const __grid_constant__ GroupMaps maps, PlaneTable pt, int cur_slot, 
     tma_load_2d(cur, &maps.cur, mx + x0, my + y0, bar);
   }
   for (int i = tid; i < TVC_ME_CENSUS; i += kGrpThreads) sweeps[i] = SweepState{0, 0, 0, 0, 0, 0};
+  const bool cu_phase = split == 1 && cu_stage;
+  for (int i = tid; i < kCuTasks; i += kGrpThreads) cu_done[i] = cu_phase ? 0 : 1;
   mbar_wait(bar, 0);
   GrpWin gw;
   gw.win = win; gw.cur = cur; gw.plane8 = maps.ref8[ref]; gw.pitch8 = maps.stride8;
@@ -1244,22 +1248,28 @@ k_me_group(const __grid_constant__ GroupMaps maps, PlaneTable pt, int cur_slot, 
   __syncthreads();
   // phase 1: the first search of every CU, one warp per CU, largest first (a group spread over several CTAs skips it: each CTA
   // would repeat the whole phase)
-  if (split == 1 && cu_stage) {
+  if (cu_phase) {
     for (;;) {
       int t = 0;
       if (lane == 0) t = atomicAdd(next + 1, 1);
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t >= kCuTasks) break;
       cu_first_search(cu_task(t), jobs + gbase, gw, cus[tid >> 5], sweeps, lane);
+      __syncwarp();
+      if (lane == 0) { __threadfence_block(); cu_done[t] = 1; }
     }
-    __syncthreads();
   }
-  // phase 2: every PU from where its CU's first search left it (or from scratch), one warp per PU, largest first
+  // phase 2: every PU from where its CU's first search left it (or from scratch), one warp per PU, largest first.  No barrier between
+  // the phases: a warp that finds the CU counter exhausted goes on, and a PU whose CU is still being searched by another warp waits for
+  // that CU's flag (every CU task has been taken by a running warp by then, and CU tasks never wait: no cycle)
   for (;;) {
     int k = 0;
     if (lane == 0) k = atomicAdd(next, 1);
     k = part + split * __shfl_sync(0xffffffffu, k, 0);
     if (k >= TVC_ME_CENSUS) break;
+    const int cu = k < 13 ? 0 : (k < 65 ? 1 + (k - 13) / 13 : (k < 273 ? 5 + (k - 65) / 13 : 21 + (k - 273) / 5));
+    while (cu_done[cu] == 0) { }
+    __threadfence_block();
     me_search_job((int)(gbase + k), pt, cur_slot, jobs, out, nullptr, nullptr, 0, ctus_x, 0, nullptr, nullptr, stats, &gw, &sweeps[k]);
   }
 }

@@ -136,7 +136,7 @@ struct State {
   unsigned long long n_spec_hits = 0, n_spec_asked = 0;
   LastHit last_bi;                         // the bi-prediction refinement just run: its fractional stage follows
   unsigned long long n_bi = 0, n_bi_frac = 0, n_bi_host = 0;
-  unsigned long long n_tz_lookup = 0, n_frac_lookup = 0, n_groups = 0;
+  unsigned long long n_tz_lookup = 0, n_frac_lookup = 0, n_groups = 0, sum_n_sads = 0;
   double batch_seconds = 0.0, prepass_seconds = 0.0;      // host wall time spent inside tvc_me_ctu / picture_start
   bool on_me = true, on_frac = true, on_tq = true, on_rdoq = true, on_mc = true, on_tables = true, verbose = false, disabled = false;
   // frame pre-pass consumed by the CU loop (TVC_HM=...,frame): one tvc_me_frame per picture with the predictor guesses; a group whose
@@ -199,6 +199,9 @@ void report()
   if (s.h && s.on_lookup)
     fprintf(stderr, "TLibCuda look-up: %llu of %llu xTZSearch and %llu of %llu xPatternSearchFracDIF calls served from %llu census-wide (CTU, reference) batches (%.3f s in tvc_me_ctu, %.3f s in picture uploads + SAD-table pre-passes)\n",
             s.n_tz_lookup, s.n_tz, s.n_frac_lookup, s.n_frac, s.n_groups, s.batch_seconds, s.prepass_seconds);
+  if (s.h && s.on_lookup && s.n_tz_lookup)
+    fprintf(stderr, "TLibCuda TZ work: %.1f candidates per served xTZSearch on average (the reference's own count, n_sads)\n",
+            (double)s.sum_n_sads / (double)s.n_tz_lookup);
   if (s.dbk.on && s.dbk.n_pics)
     fprintf(stderr, "TLibCuda deblocking: %llu pictures, %llu edge units filtered on the device, %.3f s (upload + 2 kernels + download)\n",
             s.dbk.n_pics, s.dbk.n_units, s.dbk.seconds);
@@ -659,6 +662,7 @@ bool tlibcuda_tz_search(TComDataCU* cu, TComPattern* key, short* refY, int refSt
         l.valid = true; l.slot = slot; l.x = x; l.y = y; l.w = j.w; l.h = j.h; l.mvx = r.mvx; l.mvy = r.mvy;
         l.predx = j.predx; l.predy = j.predy; l.lambda = j.lambda_cost; l.had = had; l.fr = hit->fres[it->second];
         s.n_tz_lookup++;
+        s.sum_n_sads += r.n_sads;
         return true;
       }
     }
