@@ -240,6 +240,7 @@ void tvc_ctx_destroy(tvc_ctx* c)
   if (c->fr_sweep) cudaFree(c->fr_sweep);
   if (c->fr_packed) cudaFree(c->fr_packed);
   if (c->frac_done) cudaFree(c->frac_done);
+  if (c->frac_list) cudaFree(c->frac_list);
   if (c->bi_buf) cudaFree(c->bi_buf);
   if (c->bi_host) cudaFreeHost(c->bi_host);
   if (c->fr_stats) cudaFree(c->fr_stats);

@@ -91,6 +91,8 @@ struct tvc_ctx {
   size_t fr_cap = 0;              // entries
   void* frac_done = nullptr;      // per census job: served by the CU-level fractional kernel (device)
   size_t frac_done_cap = 0;
+  void* frac_list = nullptr;      // four counters + the lists of census jobs left to the per-PU fractional kernels (device ints)
+  size_t frac_list_cap = 0;
   void* fr_packed = nullptr;      // tvc_me_frame_packed: 16-byte results (device)
   size_t fr_packed_cap = 0;
   void* bi_buf = nullptr;         // tvc_me_bipred: job / results of one refinement search (device) and its pinned staging

@@ -295,6 +295,7 @@ struct SearchCtx {
   const uint8_t* cur8;          // the PU's top-left in the staged CTU (pitch kGrpCurP)
   const uint8_t* gref8;         // co-located byte of the PU in the reference's u8 plane (candidates beyond the window)
   int gpitch8, wcx, wcy;
+  bool grp;                     // group search; a compile-time constant wherever me_search_job is inlined (the other form's code drops out)
   int w, h, sub, bi;
   uint32_t lc; int px, py;
   int lx, ty, rx, by;
@@ -346,6 +347,110 @@ __device__ __forceinline__ uint32_t sad_u8_lane(const uint8_t* __restrict__ ref,
   return acc;
 }
 
+// The same loop behind ONE call for every place of the group kernel that asks for a SAD.  k_me_group inlines the TZ control code of
+// a PU once per call site (start / zero, the staged sweeps, the two-point step, raster, star refinement); with the SAD loop inlined
+// into each of them the kernel was 318 KB of SASS, its eight warps sat in different copies of the same loop and ncu's top stall
+// was "no instruction" (4.9 warp-cycles per issue, instruction-cache hit rate 65 %).  Operands are byte offsets into the CTA's
+// dynamic shared memory so that the loads stay LDS (a pointer argument would make them generic).
+#ifndef TVC_GRP_VAR
+#define TVC_GRP_VAR 14           // bit 0: SAD loop behind a call, bit 1: compact CU cost routine behind a call, bit 2: the whole
+                                 // candidate cost behind the call, bit 3: SAD loop per PU width.  Measured on B200, ms of k_me_group per
+                                 // 1080p picture x 4 references (quarter-pel predictor guesses): 0: 3.18, 1: 3.24, 2: 2.96, 3: 3.14,
+                                 // 6: 3.13, 11: 2.39, 14: 2.30 (then 1.93 with the statistics summed per warp); same results for all
+#endif
+// bit 3 of TVC_GRP_VAR: the SAD loop per PU width.  Most census PUs are narrow (320 of 593 belong to 8x8 CUs: one or two words
+// per row), where the generic loop spends two of every seven instructions on its own control; the width is uniform over the
+// warp, so one switch picks a row loop with the words unrolled, two rows per trip (census heights give even row counts), the
+// current block read with the widest aligned load.
+template <int W4>
+__device__ __forceinline__ uint32_t sad_rows_w(const uint32_t* __restrict__ rb, const uint32_t* __restrict__ cb, int sh, int rows,
+                                               int rstride, int cstride)
+{
+  constexpr int V = (W4 % 4 == 0) ? 4 : ((W4 % 2 == 0) ? 2 : 1);
+  uint32_t acc[2] = {0, 0};
+#pragma unroll 1
+  for (int r = 0; r < rows; r += 2) {
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      const uint32_t* rr = rb + t * rstride;
+      const uint32_t* cc = cb + t * cstride;
+      uint32_t w[W4 + 1], c[W4];
+#pragma unroll
+      for (int j = 0; j <= W4; j++) w[j] = rr[j];
+      if (V == 4) {
+#pragma unroll
+        for (int j = 0; j < W4; j += 4) {
+          const uint4 q = *reinterpret_cast<const uint4*>(cc + j);
+          c[j] = q.x; c[j + 1] = q.y; c[j + 2] = q.z; c[j + 3] = q.w;
+        }
+      } else if (V == 2) {
+#pragma unroll
+        for (int j = 0; j < W4; j += 2) {
+          const uint2 q = *reinterpret_cast<const uint2*>(cc + j);
+          c[j] = q.x; c[j + 1] = q.y;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < W4; j++) c[j] = cc[j];
+      }
+#pragma unroll
+      for (int j = 0; j < W4; j++) acc[t] = vsad4_acc(c[j], __funnelshift_r(w[j], w[j + 1], sh), acc[t]);
+    }
+    rb += 2 * rstride; cb += 2 * cstride;
+  }
+  return acc[0] + acc[1];
+}
+
+__device__ __forceinline__ uint32_t sad_u8_smem_body(uint32_t ref_off, uint32_t cur_off, int w4, int rows, int sub)
+{
+  extern __shared__ __align__(128) uint8_t gsm[];
+#if TVC_GRP_VAR & 8
+  const int a = (int)(ref_off & 3u), sh = a * 8;
+  const uint32_t* rb = reinterpret_cast<const uint32_t*>(gsm + (ref_off - a));
+  const uint32_t* cb = reinterpret_cast<const uint32_t*>(gsm + cur_off);
+  const int rstride = (kGrpWinW << sub) >> 2, cstride = (kGrpCurP << sub) >> 2;
+  // vector loads of the current block need its alignment (census PUs have it: a part as wide as 16 / 8 pels starts on a multiple)
+  const int need = (w4 & 3) == 0 ? 15 : ((w4 & 1) == 0 ? 7 : 3);
+  const int sel = ((cur_off & need) == 0 && (rows & 1) == 0) ? w4 : 0;
+  switch (sel) {
+    case 1: return sad_rows_w<1>(rb, cb, sh, rows, rstride, cstride);
+    case 2: return sad_rows_w<2>(rb, cb, sh, rows, rstride, cstride);
+    case 3: return sad_rows_w<3>(rb, cb, sh, rows, rstride, cstride);
+    case 4: return sad_rows_w<4>(rb, cb, sh, rows, rstride, cstride);
+    case 6: return sad_rows_w<6>(rb, cb, sh, rows, rstride, cstride);
+    case 8: return sad_rows_w<8>(rb, cb, sh, rows, rstride, cstride);
+    case 12: return sad_rows_w<12>(rb, cb, sh, rows, rstride, cstride);
+    case 16: return sad_rows_w<16>(rb, cb, sh, rows, rstride, cstride);
+    default: break;
+  }
+#endif
+  return sad_u8_lane(gsm + ref_off, kGrpWinW, gsm + cur_off, w4, rows, sub);
+}
+
+__device__ __noinline__ uint32_t sad_u8_smem(uint32_t ref_off, uint32_t cur_off, int w4, int rows, int sub)
+{
+  return sad_u8_smem_body(ref_off, cur_off, w4, rows, sub);
+}
+__device__ __noinline__ uint32_t sad_u8_plane(const uint8_t* __restrict__ ref, int rpitch, uint32_t cur_off, int w4, int rows, int sub)
+{
+  extern __shared__ __align__(128) uint8_t gsm[];
+  return sad_u8_lane(ref, rpitch, gsm + cur_off, w4, rows, sub);
+}
+
+// bit 2 of TVC_GRP_VAR: the whole candidate cost (window test, address, SAD, MV rate) behind the call
+__device__ __noinline__ uint32_t grp_cand_cost(uint32_t win_off, uint32_t cur_off, const uint8_t* __restrict__ gref8, int gpitch8, int dx, int dy,
+                                               int x, int y, int w4_rows_sub, uint32_t lc, int px, int py)
+{
+  extern __shared__ __align__(128) uint8_t gsm[];
+  const int w4 = w4_rows_sub & 0xff, rows = (w4_rows_sub >> 8) & 0xff, sub = w4_rows_sub >> 16;
+  uint32_t sad;
+  if (dx >= -kMeR && dx <= kMeR && dy >= -kMeR && dy <= kMeR)
+    sad = sad_u8_smem_body(win_off + (uint32_t)((dy + kMeR) * kGrpWinW + dx + kMeR), cur_off, w4, rows, sub);
+  else
+    sad = sad_u8_lane(gref8 + (ptrdiff_t)y * gpitch8 + x, gpitch8, gsm + cur_off, w4, rows, sub);
+  return (sad << sub) + mv_cost(lc, x, y, 2, px, py);
+}
+
 // cost (SAD + MV rate at scale 2) of this lane's K candidates; kNoCost for slots without one.  The K
 // table sums run interleaved so that K * granules independent 16-byte loads are in flight per lane.
 // Warp-collective: every lane must call it.
@@ -353,7 +458,7 @@ template <int K>
 __device__ __forceinline__ void eval_multi(const SearchCtx& s, const bool (&valid)[K], const int (&x)[K], const int (&y)[K],
                                            uint32_t (&cost)[K])
 {
-  if (s.win8) {
+  if (s.grp) {
     // group search: every lane computes the SAD of its own candidates from the staged window (or, beyond it, from the u8 plane)
     const int w4 = s.w >> 2, rows = s.h >> s.sub;
 #pragma unroll
@@ -361,12 +466,26 @@ __device__ __forceinline__ void eval_multi(const SearchCtx& s, const bool (&vali
       cost[k] = kNoCost;
       if (valid[k]) {
         const int dx = x[k] - s.wcx, dy = y[k] - s.wcy;
+#if TVC_GRP_VAR & 4
+        extern __shared__ __align__(128) uint8_t gsm[];
+        cost[k] = grp_cand_cost((uint32_t)(s.win8 - gsm), (uint32_t)(s.cur8 - gsm), s.gref8, s.gpitch8, dx, dy, x[k], y[k],
+                                w4 | (rows << 8) | (s.sub << 16), s.lc, s.px, s.py);
+#else
         uint32_t sad;
+#if TVC_GRP_VAR & 1
+        extern __shared__ __align__(128) uint8_t gsm[];
+        if (dx >= -kMeR && dx <= kMeR && dy >= -kMeR && dy <= kMeR)
+          sad = sad_u8_smem((uint32_t)(s.win8 - gsm) + (uint32_t)((dy + kMeR) * kGrpWinW + dx + kMeR), (uint32_t)(s.cur8 - gsm), w4, rows, s.sub);
+        else
+          sad = sad_u8_plane(s.gref8 + (ptrdiff_t)y[k] * s.gpitch8 + x[k], s.gpitch8, (uint32_t)(s.cur8 - gsm), w4, rows, s.sub);
+#else
         if (dx >= -kMeR && dx <= kMeR && dy >= -kMeR && dy <= kMeR)
           sad = sad_u8_lane(s.win8 + (dy + kMeR) * kGrpWinW + dx + kMeR, kGrpWinW, s.cur8, w4, rows, s.sub);
         else
           sad = sad_u8_lane(s.gref8 + (ptrdiff_t)y[k] * s.gpitch8 + x[k], s.gpitch8, s.cur8, w4, rows, s.sub);
+#endif
         cost[k] = (sad << s.sub) + mv_cost(s.lc, x[k], y[k], 2, s.px, s.py);
+#endif
       }
     }
     return;
@@ -492,7 +611,7 @@ __device__ __forceinline__ bool sweep_stage(SearchCtx& s, int sx, int sy, int c0
 template <int K>
 __device__ __forceinline__ bool diamond_sweep(SearchCtx& s, int sx, int sy, int d0, int dmax, bool first_search)
 {
-  if (first_search && s.win8) {
+  if (first_search && s.grp) {
     if (sweep_stage<1>(s, sx, sy, 0, 1, 8, dmax)) return true;
     if (dmax < 16) return false;
     return sweep_stage<2>(s, sx, sy, 28, 16, 64, dmax);
@@ -845,7 +964,7 @@ __device__ __forceinline__ void me_search_job(int j, const PlaneTable& pt, int c
                                               const tvc_me_center* __restrict__ centers, int num_ctus, int ctus_x, int bi,
                                               const RasterBest* __restrict__ rast, const SweepState* __restrict__ sweep,
                                               unsigned long long* __restrict__ stats, const GrpWin* gw = nullptr,
-                                              const SweepState* sw_job = nullptr)
+                                              const SweepState* sw_job = nullptr, unsigned long long* grp_acc = nullptr)
 {
   const tvc_me_job jb = jobs[j];
   if (jb.w <= 0) {                       // census PU outside the picture (frame pre-pass)
@@ -863,6 +982,7 @@ __device__ __forceinline__ void me_search_job(int j, const PlaneTable& pt, int c
   s.lx = jb.lx; s.ty = jb.ty; s.rx = jb.rx; s.by = jb.by;
   s.tbl = nullptr; s.tcx = 0; s.tcy = 0;
   s.win8 = nullptr; s.cur8 = nullptr; s.gref8 = nullptr; s.gpitch8 = 0; s.wcx = 0; s.wcy = 0;
+  s.grp = gw != nullptr;
   if (gw) {
     const int px = jb.x - gw->x0, py = jb.y - gw->y0;        // the PU inside its CTU
     s.win8 = gw->win + py * kGrpWinW + px + gw->e16;
@@ -963,7 +1083,12 @@ __device__ __forceinline__ void me_search_job(int j, const PlaneTable& pt, int c
     r.sad = s.best_sad - mv_cost(s.lc, s.best_x, s.best_y, 2, s.px, s.py);
     r.n_sads = s.n_sads;
     out[j] = r;
-    if (stats && gw) {
+    if (grp_acc) {
+      // group kernel: the warp sums its PUs and adds once at the end (two atomics per PU on the same two words, 2.4 M per 1080p
+      // picture, were 34 % of the kernel's stall samples: every warp's next PU waited for the L2 to take the previous one's pair)
+      grp_acc[0] += (unsigned long long)s.n_sads;
+      grp_acc[1] += (unsigned long long)s.n_sads * (unsigned)(s.w * (s.h >> s.sub));
+    } else if (stats && gw) {
       atomicAdd(&stats[0], (unsigned long long)s.n_sads);
       atomicAdd(&stats[1], (unsigned long long)s.n_sads * (unsigned)(s.w * (s.h >> s.sub)));
     } else if (stats) {
@@ -1092,9 +1217,90 @@ __device__ __forceinline__ void cu_costs(const uint8_t* __restrict__ ref, const 
   }
 }
 
+// The same sums by loops over the sub-block rows and the row pairs instead of straight-line code (cu_costs<64> unrolled is 40 KB
+// of SASS that a warp streams through once per candidate, pushing the other warps' loops out of the instruction cache), behind a
+// call, operands as offsets into the CTA's dynamic shared memory (see sad_u8_smem).
+template <int S>
+__device__ __noinline__ void cu_costs_smem(uint32_t ref_off, uint32_t cur_off, bool need_odd, uint32_t subp_off, uint32_t mvc, uint32_t cst_off)
+{
+  extern __shared__ __align__(128) uint8_t gsm[];
+  constexpr int NB = S == 8 ? 2 : 4, Q = S / NB, QW = Q / 4, RW = S / 4;
+  const uint8_t* ref = gsm + ref_off;
+  const int a = (int)(ref_off & 3u), sh = a * 8;                       // gsm is 128-byte aligned
+  const uint32_t* rb = reinterpret_cast<const uint32_t*>(ref - a);
+  const uint32_t* cb = reinterpret_cast<const uint32_t*>(gsm + cur_off);
+  const uint8_t* subp = gsm + subp_off;
+  uint32_t* cst = reinterpret_cast<uint32_t*>(gsm + cst_off);
+  uint32_t re[NB], ce[NB], ro[NB], co[NB], te = 0, to = 0;
+#pragma unroll
+  for (int i = 0; i < NB; i++) { re[i] = 0; ce[i] = 0; ro[i] = 0; co[i] = 0; }
+#pragma unroll 1
+  for (int sbr = 0; sbr < NB; sbr++) {
+    uint32_t e[NB], o[NB];
+#pragma unroll
+    for (int j = 0; j < NB; j++) { e[j] = 0; o[j] = 0; }
+#pragma unroll 1
+    for (int rr = 0; rr < Q; rr += 2) {
+      const uint32_t* r0 = rb + (sbr * Q + rr) * (kGrpWinW / 4);
+      const uint32_t* c0 = cb + (sbr * Q + rr) * (kGrpCurP / 4);
+      uint32_t prev = r0[0];
+#pragma unroll
+      for (int j = 0; j < RW; j++) {
+        const uint32_t nxt = r0[j + 1];
+        e[j / QW] = vsad4_acc(c0[j], __funnelshift_r(prev, nxt, sh), e[j / QW]);
+        prev = nxt;
+      }
+      if (need_odd) {
+        const uint32_t* r1 = r0 + kGrpWinW / 4;
+        const uint32_t* c1 = c0 + kGrpCurP / 4;
+        prev = r1[0];
+#pragma unroll
+        for (int j = 0; j < RW; j++) {
+          const uint32_t nxt = r1[j + 1];
+          o[j / QW] = vsad4_acc(c1[j], __funnelshift_r(prev, nxt, sh), o[j / QW]);
+          prev = nxt;
+        }
+      }
+    }
+    uint32_t rse = 0, rso = 0;
+#pragma unroll
+    for (int j = 0; j < NB; j++) { rse += e[j]; rso += o[j]; ce[j] += e[j]; co[j] += o[j]; }
+#pragma unroll
+    for (int i = 0; i < NB; i++) if (i == sbr) { re[i] = rse; ro[i] = rso; }
+    te += rse; to += rso;
+  }
+  auto put = [&](int p, uint32_t ev, uint32_t ov) {
+    const uint32_t sub = subp[p];
+    cst[p] = ((sub ? ev : ev + ov) << sub) + mvc;
+  };
+  put(0, te, to);
+  if (NB == 2) {
+    put(1, re[0], ro[0]); put(2, re[1], ro[1]); put(3, ce[0], co[0]); put(4, ce[1], co[1]);
+  } else {
+    put(1, re[0] + re[1], ro[0] + ro[1]); put(2, re[NB - 2] + re[NB - 1], ro[NB - 2] + ro[NB - 1]);
+    put(3, ce[0] + ce[1], co[0] + co[1]); put(4, ce[NB - 2] + ce[NB - 1], co[NB - 2] + co[NB - 1]);
+    put(5, re[0], ro[0]); put(6, te - re[0], to - ro[0]);
+    put(7, te - re[NB - 1], to - ro[NB - 1]); put(8, re[NB - 1], ro[NB - 1]);
+    put(9, ce[0], co[0]); put(10, te - ce[0], to - co[0]);
+    put(11, te - ce[NB - 1], to - co[NB - 1]); put(12, ce[NB - 1], co[NB - 1]);
+  }
+}
+
 __device__ __forceinline__ void cu_costs_any(int S, const uint8_t* ref, const uint8_t* cur, bool need_odd, const uint8_t* subp, uint32_t mvc,
                                              uint32_t* cst)
 {
+#if TVC_GRP_VAR & 2
+  extern __shared__ __align__(128) uint8_t gsm[];
+  const uint32_t ro_ = (uint32_t)(ref - gsm), co_ = (uint32_t)(cur - gsm), so_ = (uint32_t)(subp - gsm);
+  const uint32_t to_ = (uint32_t)(reinterpret_cast<const uint8_t*>(cst) - gsm);
+  switch (S) {
+    case 64: cu_costs_smem<64>(ro_, co_, need_odd, so_, mvc, to_); break;
+    case 32: cu_costs_smem<32>(ro_, co_, need_odd, so_, mvc, to_); break;
+    case 16: cu_costs_smem<16>(ro_, co_, need_odd, so_, mvc, to_); break;
+    default: cu_costs_smem<8>(ro_, co_, need_odd, so_, mvc, to_); break;
+  }
+  return;
+#endif
   switch (S) {
     case 64: cu_costs<64>(ref, cur, need_odd, subp, mvc, cst); break;
     case 32: cu_costs<32>(ref, cur, need_odd, subp, mvc, cst); break;
@@ -1262,6 +1468,7 @@ k_me_group(const __grid_constant__ GroupMaps maps, PlaneTable pt, int cur_slot, 
   // phase 2: every PU from where its CU's first search left it (or from scratch), one warp per PU, largest first.  No barrier between
   // the phases: a warp that finds the CU counter exhausted goes on, and a PU whose CU is still being searched by another warp waits for
   // that CU's flag (every CU task has been taken by a running warp by then, and CU tasks never wait: no cycle)
+  unsigned long long acc[2] = {0ull, 0ull};
   for (;;) {
     int k = 0;
     if (lane == 0) k = atomicAdd(next, 1);
@@ -1270,7 +1477,11 @@ k_me_group(const __grid_constant__ GroupMaps maps, PlaneTable pt, int cur_slot, 
     const int cu = k < 13 ? 0 : (k < 65 ? 1 + (k - 13) / 13 : (k < 273 ? 5 + (k - 65) / 13 : 21 + (k - 273) / 5));
     while (cu_done[cu] == 0) { }
     __threadfence_block();
-    me_search_job((int)(gbase + k), pt, cur_slot, jobs, out, nullptr, nullptr, 0, ctus_x, 0, nullptr, nullptr, stats, &gw, &sweeps[k]);
+    me_search_job((int)(gbase + k), pt, cur_slot, jobs, out, nullptr, nullptr, 0, ctus_x, 0, nullptr, nullptr, stats, &gw, &sweeps[k], acc);
+  }
+  if (lane == 0 && stats && acc[0]) {
+    atomicAdd(&stats[0], acc[0]);
+    atomicAdd(&stats[1], acc[1]);
   }
 }
 
@@ -1507,29 +1718,24 @@ __device__ __forceinline__ void frac_unit(const int16_t* __restrict__ H, int pla
   }
 }
 
-template <int MAXW, int MAXH, int NT, int JPC>
-__global__ void __launch_bounds__(NT * JPC)
-k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ jobs, tvc_frac_result* __restrict__ out, int bd,
-          int span, int stride, int first, const uint8_t* __restrict__ done)
+// one job by one thread group (NT threads: the CTA when JPC == 1, else a warp).  LISTED: called from the loop of k_me_frac_listed
+// (the job is known to be unserved; a group returns on its own).
+template <int MAXW, int MAXH, int NT, int JPC, bool LISTED>
+__device__ __forceinline__ void frac_job_run(const PlaneTable& pt, int cur_slot, const tvc_frac_job* __restrict__ jobs,
+                                             tvc_frac_result* __restrict__ out, int bd, FracSmem<MAXW, MAXH>& S, int tid, int ji, bool have,
+                                             const uint8_t* __restrict__ done)
 {
   using SM = FracSmem<MAXW, MAXH>;
-  extern __shared__ __align__(16) uint8_t fsm[];
-  const int grp = threadIdx.x / NT, tid = threadIdx.x % NT;
-  SM& S = reinterpret_cast<SM*>(fsm)[grp];
-  // job index: the frame pre-pass launches one census size class at a time (span jobs out of every stride)
-  const int b = blockIdx.x * JPC + grp;
-  const bool have = b < n;
-  const int ji = have ? (b / span) * stride + first + (b % span) : 0;
   auto sync = [&]() { if (JPC == 1) __syncthreads(); else __syncwarp(); };
   const tvc_frac_job jb = jobs[ji];
-  const bool served = have && done && done[ji];            // the CU-level kernel (k_me_frac_cu) already wrote this job's result
+  const bool served = !LISTED && have && done && done[ji];  // the CU-level kernel (k_me_frac_cu) already wrote this job's result
   const bool live = have && !served && jb.w > 0 && jb.w <= MAXW && jb.h <= MAXH;
-  if (JPC > 1 && done) {                                   // every job of this CTA already served: leave at once
+  if (!LISTED && JPC > 1 && done) {                        // every job of this CTA already served: leave at once
     if (__syncthreads_and(!have || served)) return;
   }
   if (!live) {
     if (have && !served && tid == 0 && jb.w <= 0) out[ji] = tvc_frac_result{0, 0, 0, 0, 0u, 0u};   // census PU outside the picture
-    if (JPC == 1) return;
+    if (JPC == 1 || LISTED) return;
   }
   const int w = live ? jb.w : 4, h = live ? jb.h : 4, bi = bd - 8;
   const int gstride = pt.stride[0];
@@ -1639,6 +1845,61 @@ k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ j
       out[ji] = r;
     }
     sync();
+  }
+}
+
+template <int MAXW, int MAXH, int NT, int JPC>
+__global__ void __launch_bounds__(NT * JPC)
+k_me_frac(PlaneTable pt, int cur_slot, int n, const tvc_frac_job* __restrict__ jobs, tvc_frac_result* __restrict__ out, int bd,
+          int span, int stride, int first, const uint8_t* __restrict__ done)
+{
+  using SM = FracSmem<MAXW, MAXH>;
+  extern __shared__ __align__(16) uint8_t fsm[];
+  const int grp = threadIdx.x / NT, tid = threadIdx.x % NT;
+  SM& S = reinterpret_cast<SM*>(fsm)[grp];
+  // job index: the frame pre-pass launches one census size class at a time (span jobs out of every stride)
+  const int b = blockIdx.x * JPC + grp;
+  const bool have = b < n;
+  const int ji = have ? (b / span) * stride + first + (b % span) : 0;
+  frac_job_run<MAXW, MAXH, NT, JPC, false>(pt, cur_slot, jobs, out, bd, S, tid, ji, have, done);
+}
+
+// The census jobs the CU-level kernels left unserved (`done` == 0: CUs whose PUs found different integer vectors, CUs at the picture
+// border; 9 % of the jobs of a 1080p picture), as four lists by census size class.  With one CTA per job (or four) over ALL jobs the
+// per-PU kernels launched 402 000 CTAs per picture of which nine in ten read a flag and left: 0.95 ms at the CTA launch rate.
+__global__ void __launch_bounds__(256)
+k_frac_rest_lists(const uint8_t* __restrict__ done, int n, int groups, int* __restrict__ lists, int* __restrict__ counts)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+  const bool rest = i < n && done[i] == 0;
+  const int k = i < n ? i % TVC_ME_CENSUS : 0;
+  const int cls = k < 13 ? 0 : (k < 65 ? 1 : (k < 273 ? 2 : 3));
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const unsigned m = __ballot_sync(0xffffffffu, rest && cls == c);
+    if (!m) continue;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(&counts[c], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    const int first = c == 0 ? 0 : (c == 1 ? 13 : (c == 2 ? 65 : 273));
+    if (rest && cls == c) lists[(size_t)groups * first + base + __popc(m & ((1u << lane) - 1))] = i;
+  }
+}
+
+// the listed jobs of one size class: a grid that fills the machine once, thread group g takes list entries g, g + G, g + 2G, ...
+template <int MAXW, int MAXH, int NT, int JPC>
+__global__ void __launch_bounds__(NT * JPC)
+k_me_frac_listed(PlaneTable pt, int cur_slot, const int* __restrict__ list, const int* __restrict__ count, const tvc_frac_job* __restrict__ jobs,
+                 tvc_frac_result* __restrict__ out, int bd)
+{
+  using SM = FracSmem<MAXW, MAXH>;
+  extern __shared__ __align__(16) uint8_t fsm[];
+  const int grp = threadIdx.x / NT, tid = threadIdx.x % NT;
+  SM& S = reinterpret_cast<SM*>(fsm)[grp];
+  const int n = *count;
+  for (int i = blockIdx.x * JPC + grp; i < n; i += gridDim.x * JPC) {
+    frac_job_run<MAXW, MAXH, NT, JPC, true>(pt, cur_slot, jobs, out, bd, S, tid, list[i], true, nullptr);
+    if (JPC == 1) __syncthreads(); else __syncwarp();
   }
 }
 
@@ -2062,6 +2323,22 @@ static int launch_frac_class(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job
   return TVC_OK;
 }
 
+template <int MAXW, int MAXH, int NT, int JPC>
+static int launch_frac_listed(tvc_ctx* c, int cur_slot, const int* list, const int* count, const tvc_frac_job* jobs_dev, tvc_frac_result* out_dev)
+{
+  constexpr size_t smem = sizeof(FracSmem<MAXW, MAXH>) * JPC;
+  static int grid = 0;
+  if (!grid) {
+    TVC_CUDA(c, cudaFuncSetAttribute(k_me_frac_listed<MAXW, MAXH, NT, JPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    TVC_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_me_frac_listed<MAXW, MAXH, NT, JPC>, NT * JPC, smem));
+    grid = kNumSM * (occ > 0 ? occ : 1);
+  }
+  k_me_frac_listed<MAXW, MAXH, NT, JPC><<<grid, NT * JPC, smem, c->stream>>>(c->planes, cur_slot, list, count, jobs_dev, out_dev, c->cfg.bit_depth);
+  TVC_LAUNCH_CHECK(c);
+  return TVC_OK;
+}
+
 // census == true: jobs are laid out [ref*ctu][593] in census order; one launch per CU depth so that the
 // thread count and shared memory of a CTA fit the PU sizes of that depth
 template <int CUW, int NT, int JPC, bool CHILD = false>
@@ -2112,6 +2389,26 @@ static int launch_frac(tvc_ctx* c, int cur_slot, int n, const tvc_frac_job* jobs
     if ((r = launch_frac_cu<32, 128, 1>(c, cur_slot, groups, jobs_dev, out_dev, done, 4, 13, 13))) return r;
     if ((r = launch_frac_cu<16, 32, 4, true>(c, cur_slot, groups, jobs_dev, out_dev, done, 16, 13, 65))) return r;      // + its 8x8 children
     if ((r = launch_frac_cu<8, 32, 4>(c, cur_slot, groups, jobs_dev, out_dev, done, 64, 5, 273))) return r;
+  }
+  static int use_lists = -1;
+  if (use_lists < 0) { const char* e = getenv("TVC_FRAC_LISTS"); use_lists = e ? atoi(e) : 1; }
+  if (done && use_lists && groups >= kNumSM) {
+    // picture-level call: the per-PU kernels walk lists of the unserved jobs (a single group keeps the direct launch: few CTAs)
+    if ((size_t)n + 4 > c->frac_list_cap) {
+      if (c->frac_list) cudaFree(c->frac_list);
+      c->frac_list = nullptr; c->frac_list_cap = 0;
+      TVC_CUDA(c, cudaMalloc(&c->frac_list, ((size_t)n + 4) * sizeof(int)));
+      c->frac_list_cap = (size_t)n + 4;
+    }
+    int* counts = (int*)c->frac_list;                    // four counters, then the lists (class c at groups * first(c))
+    int* lists = counts + 4;
+    TVC_CUDA(c, cudaMemsetAsync(counts, 0, 4 * sizeof(int), c->stream));
+    k_frac_rest_lists<<<(n + 255) / 256, 256, 0, c->stream>>>(done, n, groups, lists, counts);
+    TVC_LAUNCH_CHECK(c);
+    if ((r = launch_frac_listed<64, 64, 256, 1>(c, cur_slot, lists, counts + 0, jobs_dev, out_dev))) return r;
+    if ((r = launch_frac_listed<32, 32, 128, 1>(c, cur_slot, lists + (size_t)groups * 13, counts + 1, jobs_dev, out_dev))) return r;
+    if ((r = launch_frac_listed<16, 16, 32, 4>(c, cur_slot, lists + (size_t)groups * 65, counts + 2, jobs_dev, out_dev))) return r;
+    return launch_frac_listed<8, 8, 32, 4>(c, cur_slot, lists + (size_t)groups * 273, counts + 3, jobs_dev, out_dev);
   }
   if ((r = launch_frac_class<64, 64, 256, 1>(c, cur_slot, groups * 13, jobs_dev, out_dev, 13, TVC_ME_CENSUS, 0, done))) return r;
   if ((r = launch_frac_class<32, 32, 128, 1>(c, cur_slot, groups * 52, jobs_dev, out_dev, 52, TVC_ME_CENSUS, 13, done))) return r;
