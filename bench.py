@@ -945,6 +945,29 @@ def gpu_arm(args):
         "me_jobs_per_step": n_valid,
     }
 
+    # k_me_group launches its CTAs longest group first, by the durations the previous picture-level call of the same shape measured
+    # (a CTU that was expensive against a reference in the last picture usually is again).  The bench repeats ONE picture, the best
+    # case for that history; this side leg times the same call right after a call of another shape (two references), i.e. with no
+    # usable history (references interleaved, launch order otherwise), so that both numbers are on record.
+    if fused:
+        try:
+            refs2 = (C.c_int * 2)(refs[0], refs[1])
+            ms_hist, ms_nohist = [], []
+            t.prof_enable(True)
+            for _ in range(4):
+                ck(L.tvc_me_frame_dev(h, SLOT_CUR, 2, refs2, None, C.byref(mcfg), C.byref(pi), C.byref(pf)))
+                t.prof_read(reset=True)
+                ck(L.tvc_me_frame_dev(h, SLOT_CUR, NUM_REFS, refs, ptr(pred), C.byref(mcfg), C.byref(pi), C.byref(pf)))
+                ms_nohist.append(t.prof_read(reset=True)["me_search"][0])
+                ck(L.tvc_me_frame_dev(h, SLOT_CUR, NUM_REFS, refs, ptr(pred), C.byref(mcfg), C.byref(pi), C.byref(pf)))
+                ms_hist.append(t.prof_read(reset=True)["me_search"][0])
+            t.prof_enable(False)
+            sub["me_group_launch_order"] = {"policy": "longest group first by the previous call's CTA durations (TVC_GROUP_ORDER=4); first call / new shape: references interleaved",
+                                            "me_search_ms_with_history": float(np.median(ms_hist)), "me_search_ms_without_history": float(np.median(ms_nohist)),
+                                            "note": "the timed steps repeat one picture, so they run with history"}
+        except Exception as ex:
+            sub["me_group_launch_order"] = {"error": repr(ex)[:300]}
+
     try:
         sub["intra_rough"] = intra_rough_leg(t, wl, local, cpu_sample=0 if args.no_cpu else 64)
     except Exception as ex:          # a side leg must never take the hot-path line down with it

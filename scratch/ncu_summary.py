@@ -15,6 +15,9 @@ want = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
+        'sm__icc_request_hit_rate.pct', 'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__issue_active.avg.pct_of_peak_sustained_elapsed',
+        'sm__cycles_active.avg', 'sm__cycles_active.max', 'sm__cycles_elapsed.avg', 'smsp__thread_inst_executed_per_inst_executed.ratio',
         'launch__shared_mem_per_block_dynamic', 'launch__grid_size', 'launch__block_size', 'smsp__inst_executed.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']
 idx = [(n, h.index(n)) for n in want if n in h]
 for row in r[2:]:

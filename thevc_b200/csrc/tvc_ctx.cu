@@ -241,6 +241,8 @@ void tvc_ctx_destroy(tvc_ctx* c)
   if (c->fr_packed) cudaFree(c->fr_packed);
   if (c->frac_done) cudaFree(c->frac_done);
   if (c->frac_list) cudaFree(c->frac_list);
+  if (c->grp_cost) cudaFree(c->grp_cost);
+  if (c->grp_order) cudaFree(c->grp_order);
   if (c->bi_buf) cudaFree(c->bi_buf);
   if (c->bi_host) cudaFreeHost(c->bi_host);
   if (c->fr_stats) cudaFree(c->fr_stats);

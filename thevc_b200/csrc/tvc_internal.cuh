@@ -91,6 +91,9 @@ struct tvc_ctx {
   size_t fr_cap = 0;              // entries
   void* frac_done = nullptr;      // per census job: served by the CU-level fractional kernel (device)
   size_t frac_done_cap = 0;
+  void* grp_cost = nullptr;       // k_me_group: duration of each group's CTA in the last picture-level call (device u32[4096])
+  void* grp_order = nullptr;      // the groups by descending cost (device int[4096]); valid for grp_order_n groups
+  int grp_order_n = 0;
   void* frac_list = nullptr;      // four counters + the lists of census jobs left to the per-PU fractional kernels (device ints)
   size_t frac_list_cap = 0;
   void* fr_packed = nullptr;      // tvc_me_frame_packed: 16-byte results (device)

@@ -1405,9 +1405,11 @@ template <int MINB>
 __global__ void __launch_bounds__(kGrpThreads, MINB)
 k_me_group(const __grid_constant__ GroupMaps maps, PlaneTable pt, int cur_slot, const tvc_me_job* __restrict__ jobs,
            tvc_me_result* __restrict__ out, int pic_w, int pic_h, int mx, int my, int ref_index_fixed, int ctus_x,
-           unsigned long long* __restrict__ stats, int split, int cu_stage)
+           unsigned long long* __restrict__ stats, int split, int cu_stage, int order, int num_refs,
+           const int* __restrict__ order_list, uint32_t* __restrict__ cost_out)
 {
   extern __shared__ __align__(128) uint8_t gsm[];
+  const long long t_start = clock64();
   uint8_t* win = gsm;
   uint8_t* cur = gsm + kGrpWinW * kGrpWinH;
   uint64_t* bar = reinterpret_cast<uint64_t*>(gsm + kGrpWinW * kGrpWinH + kGrpCurP * 64);
@@ -1419,7 +1421,23 @@ k_me_group(const __grid_constant__ GroupMaps maps, PlaneTable pt, int cur_slot, 
   // split > 1: `split` CTAs share one group (each stages the window and takes every split-th PU): the single-group call of
   // tvc_me_ctu is latency-bound, one CTA would walk the 593 PUs alone
   const int part = (int)(blockIdx.x % (unsigned)split);
-  const size_t gbase = (size_t)(blockIdx.x / (unsigned)split) * TVC_ME_CENSUS;
+  // which group this CTA takes.  Groups are laid out [reference][CTU]; the far references cost most (larger motion: more rounds,
+  // the raster stage), and in launch order they came last: the kernel's tail was a few SMs finishing the heaviest CTAs while the
+  // rest idled (ncu: SMs active 62 % of the kernel's duration).  order 1: last group first; 2: references interleaved;
+  // 3: both (a wave mixes the references, the farthest first).  order_list (picture-level calls after the first): the groups by
+  // the time each took in the previous call of the same shape, longest first -- a CTU that was expensive against a reference in the
+  // last picture usually is again (measured on B200, 1080p x 4 references: launch order 1.95 ms, interleaved 1.71, by last cost see DESIGN)
+  int gi = (int)(blockIdx.x / (unsigned)split);
+  if (order_list) gi = order_list[gi];
+  else {
+    const int ng = (int)(gridDim.x / (unsigned)split);
+    if (order & 2) {
+      const int per = ng / num_refs;                       // CTUs per reference
+      if (per * num_refs == ng) gi = (gi % num_refs) * per + gi / num_refs;
+    }
+    if (order & 1) gi = ng - 1 - gi;
+  }
+  const size_t gbase = (size_t)gi * TVC_ME_CENSUS;
   const tvc_me_job j0 = jobs[gbase];                       // the 64x64 PU sits at the CTU origin; its start is the window centre
   const int x0 = j0.x, y0 = j0.y;
   const int ref = ref_index_fixed >= 0 ? ref_index_fixed : j0.ref_index;
@@ -1483,6 +1501,31 @@ k_me_group(const __grid_constant__ GroupMaps maps, PlaneTable pt, int cur_slot, 
     atomicAdd(&stats[0], acc[0]);
     atomicAdd(&stats[1], acc[1]);
   }
+  // the CTA's duration (its last warp's), in units of 16 clocks: the next call's launch order
+  if (lane == 0 && cost_out) atomicMax(&cost_out[gi], (uint32_t)((clock64() - t_start) >> 4) + 1u);
+}
+
+// groups by descending cost: one CTA, bitonic sort of (cost, index) keys in shared memory (n <= 4096)
+__global__ void __launch_bounds__(1024)
+k_group_order(const uint32_t* __restrict__ cost, int n, int* __restrict__ order_list)
+{
+  __shared__ unsigned long long key[4096];
+  for (int i = threadIdx.x; i < 4096; i += 1024)
+    key[i] = i < n ? (((unsigned long long)(0xffffffffu - cost[i]) << 32) | (unsigned)i) : ~0ull;     // ascending key = descending cost, ties by index
+  __syncthreads();
+  for (int k = 2; k <= 4096; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < 4096; i += 1024) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = key[i], b = key[l];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { key[i] = b; key[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < n; i += 1024) order_list[i] = (int)(key[i] & 0xffffffffu);
 }
 
 __global__ void k_me_table_lookup(const uint16_t* __restrict__ tables, const tvc_me_center* __restrict__ centers,
@@ -2450,12 +2493,35 @@ int tvc_launch_me_group(tvc_ctx* c, int cur_slot, int ngroups, const tvc_me_job*
   ProfScope ps(c, TVC_PH_ME_SEARCH);
   // few groups (tvc_me_ctu: one): spread each over several CTAs so that the call fills the machine
   const int split = ngroups >= 2 * kNumSM ? 1 : (ngroups >= kNumSM / 4 ? 4 : 24);
+  static int order = -1;           // 0 launch order, 1 reversed, 2 references interleaved, 3 both, 4 (default): by the previous call's cost
+  if (order < 0) { const char* e = getenv("TVC_GROUP_ORDER"); order = e ? atoi(e) : 4; }
+  const int nr = num_refs > 0 ? num_refs : 1;
+  // picture-level calls on the context's own stream keep a cost per group and launch the next call of the same shape longest first
+  const int* order_list = nullptr;
+  uint32_t* cost_out = nullptr;
+  if (order == 4 && split == 1 && ngroups <= 4096 && ref_index_fixed < 0) {
+    if (!c->grp_cost) {
+      TVC_CUDA(c, cudaMalloc(&c->grp_cost, 4096 * sizeof(uint32_t)));
+      TVC_CUDA(c, cudaMalloc(&c->grp_order, 4096 * sizeof(int)));
+      c->grp_order_n = 0;
+    }
+    if (c->grp_order_n == ngroups) order_list = (const int*)c->grp_order;
+    cost_out = (uint32_t*)c->grp_cost;
+    TVC_CUDA(c, cudaMemsetAsync(cost_out, 0, (size_t)ngroups * sizeof(uint32_t), c->stream));
+  }
+  const int ord = order == 4 ? 2 : order;
   if (minb >= 3)
     k_me_group<3><<<ngroups * split, kGrpThreads, kGrpSmem, c->stream>>>(maps, c->planes, cur_slot, jobs_dev, out_dev, c->cfg.width, c->cfg.height,
-                                                                         p.mx[0], p.my[0], ref_index_fixed, c->num_ctus_x, stats, split, cu_stage);
+                                                                         p.mx[0], p.my[0], ref_index_fixed, c->num_ctus_x, stats, split, cu_stage, ord, nr,
+                                                                         order_list, cost_out);
   else
     k_me_group<2><<<ngroups * split, kGrpThreads, kGrpSmem, c->stream>>>(maps, c->planes, cur_slot, jobs_dev, out_dev, c->cfg.width, c->cfg.height,
-                                                                         p.mx[0], p.my[0], ref_index_fixed, c->num_ctus_x, stats, split, cu_stage);
+                                                                         p.mx[0], p.my[0], ref_index_fixed, c->num_ctus_x, stats, split, cu_stage, ord, nr,
+                                                                         order_list, cost_out);
+  if (cost_out) {
+    k_group_order<<<1, 1024, 0, c->stream>>>(cost_out, ngroups, (int*)c->grp_order);
+    c->grp_order_n = ngroups;
+  }
   TVC_LAUNCH_CHECK(c);
   return TVC_OK;
 }
