@@ -881,7 +881,7 @@ def gpu_arm(args):
         # group search: the staged window + CTU of every (CTU, reference) in, one job record in and one result out per PU;
         # arithmetic = the sample differences of the candidates the reference's TZ search evaluates, four per vabsdiff4
         alg_bytes["me_search"] = n_groups * (208 * 192 + 80 * 64) + n_valid * (72 + 16)
-        bound["me_search"] = "integer pipe / shared-memory loads"
+        bound["me_search"] = "issue slots (per-lane SAD: shared-memory loads + funnel shifts + VABSDIFF4, and the TZ control flow); 17 of 32 lanes active on average"
         int_ops["me_search"] = float(me_stats["sample_differences"]) / 4.0
     else:
         table_bytes = t.me_table_bytes(NUM_REFS)

@@ -1,11 +1,5 @@
 #!/bin/bash
-# round 2, call G: CU-level fractional search: parity + bench + per-kernel list
+# round 2, call G: gprof flat profile of the hooked encoder (build/hm_pg = the same sources with -pg), 1 I + 4 P pictures at 1080p, fast hook set
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
-O=gpurun_out; mkdir -p $O
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "me_" > $O/r02g_parity.log 2>&1; echo "parity rc=$?" | tee -a $O/r02g_parity.log
-tail -8 $O/r02g_parity.log
-timeout 600 python -m pytest tests/test_gpu_properties.py -x -q -m gpu > $O/r02g_props.log 2>&1; echo "props rc=$?"; tail -3 $O/r02g_props.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/r02g_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/r02g_smoke.log
-timeout 900 python bench.py --steps 10 --warmup 3 --hm-frames 5 --cpu-enc-frames 0 > $O/r02g_bench.json 2> $O/r02g_bench.err; echo "bench rc=$?"; tail -3 $O/r02g_bench.err
-CMD="python bench.py --steps 2 --warmup 1 --no-cpu --hm-frames 0"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/r02g_launches.csv $CMD > $O/r02g_ncu_l.log 2>&1; echo "ncu list rc=$?"
+TVC_HM=me,frac,tables,frame,candgrid timeout 170 bash scratch/hm1080_gprof.sh 5 > gpurun_out/r02g_gprof.log 2>&1; echo "gprof rc=$?"
+tail -5 gpurun_out/hm1080pg/enc.log; grep TLibCuda gpurun_out/hm1080pg/enc.err | tail -8

@@ -13,7 +13,7 @@ def num(r, n):
     u = units[col(n)]
     return v * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9}.get(u, 1.0)
 phase_of = [("k_me_group", "me_search_group"), ("k_me_frac", "me_frac"), ("k_rdoq", "rdoq"), ("k_mc_batch", "mc"), ("k_fwd_tq", "fwd_tq"), ("k_inv_tq", "inv_tq")]
-bound = {"me_search_group": "integer pipe + shared-memory loads (per-lane SAD from the staged window; no table traffic)",
+bound = {"me_search_group": "issue slots: per-lane SAD from the staged window (LDS + funnel shift + VABSDIFF4) and the TZ control flow; no table traffic",
          "me_frac": "integer pipe (dp2a vertical taps, Hadamard butterflies)", "rdoq": "issue slots (dependent FP64 chain per TU)",
          "mc": "latency (small launch)", "fwd_tq": "latency / integer pipe (matrix-form transform)", "inv_tq": "latency (global loads, low occupancy at 16x16 / 32x32)"}
 acc = {}
