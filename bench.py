@@ -4,9 +4,9 @@
 A "step" is one pass of the ported hot path over one synthetic 1920x1080 P picture with 4 reference
 pictures (cfg/encoder_lowdelay_P_main.cfg: SR 64, FEN 1, HadamardME 1, AMP 1, 8-bit):
 
-  1. ME frame pre-pass  : SAD tables of all 129x129 integer candidates per CTU and reference, then for
-                          every PU of the partition census (593 per CTU) x 4 references the integer TZ
-                          search (xTZSearch) and the fractional search (xPatternSearchFracDIF);
+  1. ME frame pre-pass  : for every PU of the partition census (593 per CTU) x 4 references the integer TZ
+                          search (xTZSearch; SADs computed on demand from TMA-staged search windows, no SAD
+                          tables in HBM) and the fractional search (xPatternSearchFracDIF);
   2. motion compensation: Y/U/V prediction of the whole picture from a PU partition with quarter-pel MVs;
   3. residual           : org - pred (three planes);
   4. transform + RDOQ   : every TU size (luma 4..32, chroma 4..16) tiled over the picture (the residual
@@ -444,10 +444,17 @@ def reference_arm(args):
 
 
 def workload_config():
+    # distinct device buffers one step streams through (no SAD tables in the round-2 form): per census job a tvc_me_job (72 B), a
+    # tvc_me_result (16), a tvc_frac_job (44), a tvc_frac_result (24) and 5 B of flags / list entries; coefficients and levels as
+    # int32 over every TU size; the RDOQ scratch (ncu: 449 MB written per step); 13 int16 / u8 picture planes
+    n_jobs = NUM_REFS * ((W + 63) // 64) * ((H + 63) // 64) * 593
+    rec_mb = n_jobs * (72 + 16 + 44 + 24 + 5) / 1e6
     return {"workload": "cfg/encoder_lowdelay_P_main.cfg 1920x1080 8-bit synthetic, 1 P picture x 4 refs, SR 64, FEN 1, HAD 1: "
-                        "ME pre-pass (SAD tables + TZ + frac for the 593-PU census of 510 CTUs) + MC + residual + T + RDOQ + IQ/IT",
+                        "ME pre-pass (integer TZ + fractional search for the 593-PU census of 510 CTUs x 4 refs) + MC + residual + T + RDOQ + IQ/IT",
             "width": W, "height": H, "num_refs": NUM_REFS, "search_range": SEARCH_RANGE, "qp": QP,
-            "l2": "inputs+outputs per step (34.8 GB of SAD tables) exceed the 126 MB L2; no explicit flush",
+            "l2": "inputs larger than L2, no explicit flush: one step streams %.0f MB of job / result records, 90 MB of coefficient + level "
+                  "buffers, the RDOQ scratch and 13 picture planes (8.1 MB int16 / 2.7 MB u8 each) -- more than 0.4 GB of distinct buffers "
+                  "against the 126 MB L2; ncu measures about 1 GB of DRAM traffic per step (profiles/traffic.json)" % rec_mb,
             "parallelism": "independent sequences per GPU, no collective"}
 
 
@@ -995,8 +1002,7 @@ def gpu_arm(args):
         if dev_ms > 0:
             sub["me_tz_sad_gpel_per_s"] = float(tz_pels.sum()) / (dev_ms * 1e-3) / 1e9
 
-    # ---- whole-encoder leg (metric (i) of BASELINE.json): after the context is gone so that the encoder's own 34.8 GB
-    # of SAD tables fit beside nothing else
+    # ---- whole-encoder leg (metric (i) of BASELINE.json): after the context is gone (the encoder process opens its own)
     t.close()
     t = None
     failed = None
