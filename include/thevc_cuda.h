@@ -278,7 +278,7 @@ int tvc_me_bipred(tvc_ctx* ctx, int target_slot, const int16_t* target, int targ
 
 /* ---------------------------------------------------------------------------------- frame-level ME pre-pass
  * The TEncCu frame pre-pass named by the north star: for one picture and up to 8 references it
- * runs tvc_me_prepass (SAD tables), then -- for EVERY PU of the HM partition census of every CTU
+ * runs -- for EVERY PU of the HM partition census of every CTU
  * (593 PU instances per CTU = 13 part shapes x 21 CUs at depths 0-2 + 5 x 64 CUs at
  * depth 3; census order below) and every reference -- xMotionEstimation's integer stage
  * (xSetSearchRange + xTZSearch, TEncSearch.cpp:4209-4225, 4302-4474) and fractional stage
@@ -286,8 +286,11 @@ int tvc_me_bipred(tvc_ctx* ctx, int target_slot, const int16_t* target, int targ
  * output of the CU loop, so the pre-pass takes one predictor GUESS per
  * (reference, CTU), in quarter pels; it is used as rate predictor, search-window centre (after
  * TComDataCU::clipMv with the PU's own CU origin, TComDataCU.cpp:3505-3517) and TZ start of every
- * PU of that CTU, and (clipped with the CTU origin, >> 2) as the SAD-table centre.  A host whose
- * real predictor differs re-runs tvc_me_search_batch for that PU; it still reads the tables.
+ * PU of that CTU, and (clipped with the CTU origin, >> 2) as the centre of the search window the
+ * group kernel stages (default form: every SAD is computed on demand from that window, nothing is
+ * written to HBM but the results; with TVC_ME_FUSED=0 / tvc_me_set_fused(ctx, 0) the round-1 form
+ * runs tvc_me_prepass first and the searches read its SAD tables).  A host whose real predictor
+ * differs asks again with tvc_me_ctu (one CTU, one reference) or tvc_me_search_batch (single PUs).
  *
  * Census order inside a CTU (index 0..592): depth 0,1,2,3; CUs of a depth in raster order; parts of
  * a CU: 2Nx2N, 2NxN[0,1], Nx2N[0,1], then (CU >= 16 only) 2NxnU[0,1], 2NxnD[0,1], nLx2N[0,1],
